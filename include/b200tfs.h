@@ -1,0 +1,282 @@
+/* b200tfs.h - C ABI of libb200tfs.so: the TensorProto / PredictRequest / PredictResponse wire codec
+ * of zendesk/min-tfs-client's Predict hot path, run as hand-written sm_100a CUDA kernels.
+ *
+ * The reference has no FFI: its hot path is Python calling the protobuf runtime.  The seams this
+ * library replaces are (paths relative to the reference checkout):
+ *
+ *   encode   tensor_serving_client/min_tfs_client/tensors.py:28-35   ndarray_to_tensor_proto
+ *            tensor_serving_client/min_tfs_client/tensors.py:17-25   write_values_to_tensor_proto
+ *            tensor_serving_client/min_tfs_client/requests.py:41-48  PredictRequest assembly
+ *            protobuf_srcs/tensorflow_serving/apis/prediction_service_pb2_grpc.py:52
+ *                                                                     PredictRequest.SerializeToString
+ *   decode   protobuf_srcs/tensorflow_serving/apis/prediction_service_pb2_grpc.py:53
+ *                                                                     PredictResponse.FromString
+ *            tensor_serving_client/min_tfs_client/tensors.py:38-46   extract_shape, tensor_proto_to_ndarray
+ *   dtypes   tensor_serving_client/min_tfs_client/constants.py:13-29 numpy <-> DT_* <-> TensorProto field
+ *
+ * Plain C: pointers, sizes, int status codes.  No torch / numpy / protobuf types cross this line.
+ * Every function returns B200TFS_OK (0) or a negative B200TFS_E_* code; b200tfs_last_error() gives
+ * the thread-local message.  Nothing here ever falls back to a CPU codec: without a CUDA device
+ * b200tfs_create() fails with B200TFS_E_CUDA and every codec entry point needs a context.
+ *
+ * Threading: a b200tfs_ctx owns one CUDA stream plus pinned/device scratch and is NOT re-entrant;
+ * use one context per calling thread (contexts are cheap).  Distinct contexts are independent.
+ */
+#ifndef B200TFS_H_
+#define B200TFS_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define B200TFS_ABI_VERSION 1
+
+/* ---- status codes ---------------------------------------------------------------------------- */
+#define B200TFS_OK 0
+#define B200TFS_E_DTYPE (-1)        /* dtype not in the reference's table / cast not supported   (ValueError) */
+#define B200TFS_E_SHAPE (-2)        /* bad rank / dims / element count != prod(shape)            (ValueError) */
+#define B200TFS_E_SIZE (-3)         /* caller buffer too small                                                */
+#define B200TFS_E_PARSE (-4)        /* malformed protobuf wire                                   (DecodeError) */
+#define B200TFS_E_CUDA (-5)         /* CUDA runtime error / no device                                          */
+#define B200TFS_E_TOOBIG (-6)       /* message would exceed protobuf's 2 GiB limit                            */
+#define B200TFS_E_ARG (-7)          /* bad argument                                                            */
+#define B200TFS_E_NONCANONICAL (-8) /* valid wire, but a layout the device parser does not tabulate            */
+#define B200TFS_E_RANGE (-9)        /* decoded integer does not fit the target dtype          (OverflowError) */
+#define B200TFS_E_KEY (-10)         /* dtype enum absent / unmapped on decode                       (KeyError) */
+
+/* ---- tensorflow.DataType values used on this path (types.proto:12-68; pinned by the reference's
+ *      tests/unit/min_tfs_client/types_test.py:7-23) ------------------------------------------------ */
+#define B200TFS_DT_INVALID 0
+#define B200TFS_DT_FLOAT 1
+#define B200TFS_DT_DOUBLE 2
+#define B200TFS_DT_INT32 3
+#define B200TFS_DT_UINT8 4
+#define B200TFS_DT_INT16 5
+#define B200TFS_DT_INT8 6
+#define B200TFS_DT_STRING 7
+#define B200TFS_DT_COMPLEX64 8
+#define B200TFS_DT_INT64 9
+#define B200TFS_DT_BOOL 10
+#define B200TFS_DT_BFLOAT16 14 /* not in the reference's table; TF convention (half_val bit patterns) */
+#define B200TFS_DT_UINT16 17
+#define B200TFS_DT_COMPLEX128 18
+#define B200TFS_DT_HALF 19
+#define B200TFS_DT_UINT32 22
+#define B200TFS_DT_UINT64 23
+/* unpack-only pseudo dtype: decode DT_HALF the way the reference does - half_val integers taken as
+ * VALUES and converted to float16 (18688 -> 18688.0), SURVEY 8a Q7 - instead of TF's bit patterns */
+#define B200TFS_DT_HALF_REFQUIRK (-19)
+
+/* ---- encode flags (b200tfs_tensor.flags) ------------------------------------------------------- */
+#define B200TFS_F_TENSOR_CONTENT 0x1u /* emit raw little-endian bytes in tensor_content (field 4) instead of the
+                                         typed repeated field the reference writes (tensors.py:17-25)            */
+#define B200TFS_F_KEEP_SNAN 0x2u      /* do NOT quiet float32 signalling NaNs.  Default quiets them, because the
+                                         reference routes every float32 through a Python double (tensors.py:22). */
+#define B200TFS_F_PRESERIALIZED 0x4u  /* `data` already holds a serialised TensorProto of `packed_len` bytes (how the
+                                         host hands over DT_STRING tensors, tensors.py:24): spliced in verbatim        */
+
+/* ---- decode flags (b200tfs_output.flags, set by the parser) ----------------------------------- */
+#define B200TFS_OF_TENSOR_CONTENT 0x1u /* values arrived in tensor_content                                        */
+#define B200TFS_OF_MULTI_CHUNK 0x2u    /* values field split over several occurrences / unpacked elements         */
+#define B200TFS_OF_DIM_INFERRED 0x4u   /* one dim was -1 and was inferred from the element count                 */
+#define B200TFS_OF_HAS_UNKNOWN 0x8u    /* unknown fields were skipped inside this entry                           */
+#define B200TFS_OF_RANK0 0x10u         /* no dims: the reference raises TypeError here (reshape() with no args)   */
+#define B200TFS_OF_VARINT 0x20u        /* values are packed varints: element count is checked while unpacking    */
+
+/* map-entry order for requests with several inputs */
+#define B200TFS_ORDER_GIVEN 0 /* emit in the order of b200tfs_request.inputs                                     */
+#define B200TFS_ORDER_UPB 1   /* the order SerializeToString(deterministic=True) gives with the protobuf (upb)
+                                 runtime the oracle was pinned against: bytewise, but a key that is a strict prefix
+                                 of another sorts AFTER it                                                          */
+#define B200TFS_ORDER_BYTES 2 /* plain bytewise order (shorter prefix first)                                     */
+
+#define B200TFS_MAX_RANK 16   /* decode table limit; encode accepts any rank up to 254 (TF's limit)            */
+#define B200TFS_MAX_CHUNKS 8  /* value-field occurrences tabulated per output before E_NONCANONICAL             */
+
+typedef struct b200tfs_ctx b200tfs_ctx;
+
+/* One tensor to encode.  `data` is a DEVICE pointer for b200tfs_encode_* and a HOST pointer for the
+ * *_host variants; elements are C-contiguous, little-endian, in `src_dtype`.  `wire_dtype` is the
+ * DT_* written into the TensorProto; if it differs from src_dtype the kernel casts while packing
+ * (HALF->FLOAT and BFLOAT16->FLOAT, both exact; see b200tfs_cast_supported()).                   */
+typedef struct b200tfs_tensor {
+  const void* data;
+  int32_t src_dtype;
+  int32_t wire_dtype;
+  int32_t rank;
+  uint32_t flags;       /* B200TFS_F_*                                                        */
+  const int64_t* dims;  /* rank entries                                                       */
+  const char* key;      /* map key bytes (UTF-8, not NUL terminated); ignored for bare protos */
+  int64_t key_len;
+  uint64_t packed_len;  /* varint dtypes: byte length of the packed payload; filled by
+                           b200tfs_measure(); ignored (recomputed) for fixed-width dtypes     */
+} b200tfs_tensor;
+
+/* One PredictRequest (predict.proto:12-27; assembled as reference requests.py:41-48 does). */
+typedef struct b200tfs_request {
+  const char* model_name;
+  int64_t model_name_len;
+  int32_t has_version;  /* model_version is not None (requests.py:44)                          */
+  int32_t order;        /* B200TFS_ORDER_*                                                     */
+  int64_t version;
+  int32_t n_inputs;
+  int32_t reserved;
+  const b200tfs_tensor* inputs;
+} b200tfs_request;
+
+/* One decoded output of a PredictResponse (predict.proto:30-40), as tabulated by the parse kernel.
+ * All offsets are byte offsets from the start of the wire arena handed to the parse call.          */
+typedef struct b200tfs_output {
+  uint64_t key_off;    /* map key bytes (last `key` occurrence of the winning entry)            */
+  uint32_t key_len;
+  int32_t dtype;       /* DT_* (last occurrence wins; 0 if absent)                              */
+  int32_t rank;
+  uint32_t flags;      /* B200TFS_OF_*                                                          */
+  int32_t value_field; /* TensorProto field the dtype maps to (constants.py:13-29), 0 = unmapped */
+  int32_t n_chunks;    /* occurrences of that field (packed runs or single unpacked elements)   */
+  int64_t dims[B200TFS_MAX_RANK];          /* after -1 inference                                */
+  uint64_t chunk_off[B200TFS_MAX_CHUNKS];
+  uint64_t chunk_len[B200TFS_MAX_CHUNKS];
+  uint64_t content_off; /* tensor_content (field 4), last occurrence; content_len 0 if absent   */
+  uint64_t content_len;
+  uint64_t msg_off;     /* the TensorProto sub-message itself (last `value` occurrence)         */
+  uint64_t msg_len;
+  uint64_t n_elems;     /* prod(dims)                                                           */
+  uint64_t dst_bytes;   /* n_elems * element size of `dtype` in memory                          */
+  uint64_t n_strings;   /* string_val occurrences (strings are unpacked on the host)            */
+  int32_t status;       /* B200TFS_OK, or the error tensor_proto_to_ndarray raises for it       */
+  int32_t reserved;
+} b200tfs_output;
+
+typedef struct b200tfs_model_spec {
+  uint64_t name_off;  /* offsets from the start of the wire arena                              */
+  uint32_t name_len;
+  uint32_t signature_len;
+  uint64_t signature_off;
+  uint64_t label_off;
+  uint32_t label_len;
+  int32_t has_version;
+  int64_t version;
+} b200tfs_model_spec;
+
+/* ---- library / context ----------------------------------------------------------------------- */
+int b200tfs_abi_version(void);
+const char* b200tfs_last_error(void);
+int b200tfs_device_count(int* count);
+int b200tfs_create(int device, b200tfs_ctx** out);
+int b200tfs_destroy(b200tfs_ctx* ctx);
+int b200tfs_sync(b200tfs_ctx* ctx);
+void* b200tfs_stream(b200tfs_ctx* ctx); /* the cudaStream_t every call on this context is ordered on */
+int b200tfs_kernel_launches(b200tfs_ctx* ctx, uint64_t* count); /* kernels launched so far on this context */
+
+/* ---- memory + timing helpers so a ctypes host needs nothing but this library ------------------- */
+int b200tfs_malloc(b200tfs_ctx* ctx, uint64_t bytes, void** dptr);
+int b200tfs_free(b200tfs_ctx* ctx, void* dptr);
+int b200tfs_host_alloc(uint64_t bytes, void** hptr); /* pinned */
+int b200tfs_host_free(void* hptr);
+int b200tfs_memcpy_h2d(b200tfs_ctx* ctx, void* dst_dev, const void* src_host, uint64_t bytes); /* async */
+int b200tfs_memcpy_d2h(b200tfs_ctx* ctx, void* dst_host, const void* src_dev, uint64_t bytes); /* async */
+int b200tfs_memcpy_d2d(b200tfs_ctx* ctx, void* dst_dev, const void* src_dev, uint64_t bytes);  /* async */
+int b200tfs_memset(b200tfs_ctx* ctx, void* dst_dev, int value, uint64_t bytes);                /* async */
+int b200tfs_event_create(void** ev);
+int b200tfs_event_destroy(void* ev);
+int b200tfs_event_record(b200tfs_ctx* ctx, void* ev);
+int b200tfs_event_sync(void* ev);
+int b200tfs_event_elapsed_ms(void* start, void* stop, float* ms);
+
+/* ---- dtype table (constants.py:13-29, types.py:19-42) ------------------------------------------ */
+/* element size in memory of a DT_* (0 if not a fixed-size numeric dtype on this path)            */
+int b200tfs_dtype_size(int32_t dtype);
+/* TensorProto field number the reference stores this dtype in (5 float_val, 6 double_val, 7 int_val,
+ * 8 string_val, 9 scomplex_val, 10 int64_val, 11 bool_val, 12 dcomplex_val, 13 half_val, 16 uint32_val,
+ * 17 uint64_val); 0 if unmapped                                                                    */
+int b200tfs_dtype_field(int32_t dtype);
+/* 1 if the encoder can read src_dtype memory and emit wire_dtype                                   */
+int b200tfs_cast_supported(int32_t src_dtype, int32_t wire_dtype);
+
+/* ---- sizes (host, closed form) ----------------------------------------------------------------- */
+/* TensorProto for one tensor: header_len = bytes before the payload, total_len = whole message.
+ * Varint dtypes need tensor->packed_len (see b200tfs_measure).                                     */
+int b200tfs_tensor_proto_size(const b200tfs_tensor* t, uint64_t* header_len, uint64_t* total_len);
+int b200tfs_request_size(const b200tfs_request* r, uint64_t* total_len);
+/* The non-payload bytes, computed on the host exactly as the kernels will write them: the header of
+ * one TensorProto (08 dtype 12 shape [values tag + length]) ...                                     */
+int b200tfs_tensor_proto_header(const b200tfs_tensor* t, void* buf, uint64_t cap, uint64_t* len);
+/* ... and every framing byte of a PredictRequest, concatenated in wire order, with - per input in
+ * emission order - where its payload starts in the final message (payload_off), how long it is
+ * (payload_len) and which inputs[] index it is (perm).  Needs no device.                           */
+int b200tfs_request_frame(const b200tfs_request* r, void* buf, uint64_t cap, uint64_t* frame_len,
+                          uint64_t* payload_off, uint64_t* payload_len, int32_t* perm);
+/* Order the inputs of a request the way `order` says; writes a permutation of 0..n-1.              */
+int b200tfs_order_keys(int32_t n, const char* const* keys, const int64_t* key_lens, int32_t order,
+                       int32_t* perm);
+/* Arena bytes needed to encode these records with b200tfs_encode_* (records are placed so that the
+ * largest payload of each lands 128-byte aligned; the arena base must be 256-byte aligned).        */
+int b200tfs_tensor_arena_size(int32_t n, const b200tfs_tensor* tensors, uint64_t* bytes);
+int b200tfs_request_arena_size(int32_t n, const b200tfs_request* reqs, uint64_t* bytes);
+
+/* ---- encode (device tensors -> device wire arena) ---------------------------------------------- */
+/* Pass 1 for the varint-packed dtypes (int_val / int64_val / uint32_val / uint64_val / half_val):
+ * fills tensors[i].packed_len on the device and copies the lengths back (synchronises).            */
+int b200tfs_measure(b200tfs_ctx* ctx, int32_t n, b200tfs_tensor* tensors);
+/* n bare TensorProtos (what ndarray_to_tensor_proto(...).SerializeToString() returns).
+ * rec_off/rec_len (host arrays of n) receive where each message lies inside the arena.  Async.     */
+int b200tfs_encode_tensor_protos(b200tfs_ctx* ctx, int32_t n, const b200tfs_tensor* tensors,
+                                 void* arena_dev, uint64_t arena_cap, uint64_t* rec_off,
+                                 uint64_t* rec_len);
+/* n PredictRequests (what PredictRequest.SerializeToString() returns for the request the reference
+ * builds in requests.py:41-48).  Async.                                                            */
+int b200tfs_encode_requests(b200tfs_ctx* ctx, int32_t n, const b200tfs_request* reqs, void* arena_dev,
+                            uint64_t arena_cap, uint64_t* rec_off, uint64_t* rec_len);
+
+/* ---- decode (device wire arena -> table -> device tensors) -------------------------------------- */
+/* Parse n PredictResponse messages lying at rec_off[i]..+rec_len[i] of the device arena.  Runs the
+ * parse kernel, then copies the table back (synchronises).  outs has n*max_outputs slots (record i
+ * uses outs[i*max_outputs ...]); n_outs[i] receives the number of distinct keys; specs[i] the
+ * model_spec.  rec_status[i] is B200TFS_OK or the error for that record.  Returns B200TFS_OK if the
+ * kernel ran, even when individual records carry errors.                                           */
+int b200tfs_parse_responses(b200tfs_ctx* ctx, const void* arena_dev, int32_t n, const uint64_t* rec_off,
+                            const uint64_t* rec_len, int32_t max_outputs, b200tfs_output* outs,
+                            int32_t* n_outs, b200tfs_model_spec* specs, int32_t* rec_status);
+/* Same walk for n bare TensorProto messages (tensor_proto_to_ndarray on a single message): one
+ * output per record, key_len = 0.                                                                  */
+int b200tfs_parse_tensor_protos(b200tfs_ctx* ctx, const void* arena_dev, int32_t n,
+                                const uint64_t* rec_off, const uint64_t* rec_len, b200tfs_output* outs,
+                                int32_t* rec_status);
+/* Unpack m tabulated outputs into device buffers: dst[j] receives outs[j].dst_bytes bytes (or
+ * n_elems * sizeof(dst_dtype[j]) when dst_dtype[j] != outs[j].dtype and the cast is supported:
+ * FLOAT -> HALF / BFLOAT16 round-to-nearest-even).  status[j] (host, filled after an internal sync
+ * only if `status` is non-NULL) reports per-output errors found while unpacking (element count
+ * mismatch, integer out of range).  Async when status is NULL.                                    */
+int b200tfs_unpack_outputs(b200tfs_ctx* ctx, const void* arena_dev, int32_t m, const b200tfs_output* outs,
+                           void* const* dst_dev, const int32_t* dst_dtype, int32_t* status);
+
+/* ---- host-buffer convenience (what a client binds; H2D / D2H happen inside) -------------------- */
+/* tensors[].data are HOST pointers (pinned or pageable).  Encodes n requests and leaves the wire
+ * bytes in wire_host (capacity wire_cap); rec_off/rec_len as above.  Synchronous.                  */
+int b200tfs_encode_requests_host(b200tfs_ctx* ctx, int32_t n, const b200tfs_request* reqs,
+                                 void* wire_host, uint64_t wire_cap, uint64_t* rec_off,
+                                 uint64_t* rec_len);
+int b200tfs_encode_tensor_protos_host(b200tfs_ctx* ctx, int32_t n, const b200tfs_tensor* tensors,
+                                      void* wire_host, uint64_t wire_cap, uint64_t* rec_off,
+                                      uint64_t* rec_len);
+/* Decode n responses held in HOST memory: copies them to the device, parses, and returns the table
+ * (offsets are relative to wire_host).  Follow with b200tfs_unpack_outputs_host.                   */
+int b200tfs_parse_responses_host(b200tfs_ctx* ctx, const void* wire_host, int32_t n,
+                                 const uint64_t* rec_off, const uint64_t* rec_len, int32_t max_outputs,
+                                 b200tfs_output* outs, int32_t* n_outs, b200tfs_model_spec* specs,
+                                 int32_t* rec_status);
+int b200tfs_parse_tensor_protos_host(b200tfs_ctx* ctx, const void* wire_host, int32_t n,
+                                     const uint64_t* rec_off, const uint64_t* rec_len,
+                                     b200tfs_output* outs, int32_t* rec_status);
+/* Unpack outputs of the most recent *_parse_*_host call on this context into HOST buffers.         */
+int b200tfs_unpack_outputs_host(b200tfs_ctx* ctx, int32_t m, const b200tfs_output* outs,
+                                void* const* dst_host, const int32_t* dst_dtype, int32_t* status);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B200TFS_H_ */

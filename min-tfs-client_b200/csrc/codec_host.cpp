@@ -1,0 +1,1042 @@
+// codec_host.cpp - host half of libb200tfs.so: the C ABI of include/b200tfs.h, the wire-size
+// arithmetic, the header planner (tags, varint lengths, dims, keys - everything on the wire that is
+// not tensor payload) and the launch plans handed to the kernels in kernels.cu.
+//
+// The planner restates the framing the reference gets from protobuf for
+//   TensorProto{dtype, tensor_shape{dim{size}}, <typed packed field>}      tensors.py:28-35
+//   PredictRequest{model_spec{name, version{value}}, inputs{key -> proto}}  requests.py:41-48
+// (proto3 rules: fields in ascending number, zero scalars elided, packed repeated scalars, map entries
+// always carry key and value) - SURVEY.md 8(a) a1-a3 and quirks Q1-Q5.  There is deliberately no CPU
+// implementation of the payload path here: payload bytes only ever move inside the CUDA kernels.
+#include <cuda_runtime.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <algorithm>
+#include <string>
+#include <vector>
+
+#include "../../include/b200tfs.h"
+#include "kernels.h"
+#include "plan.h"
+#include "wire.h"
+
+using namespace b200tfs;
+
+// ------------------------------------------------------------------------------------------------
+// errors
+// ------------------------------------------------------------------------------------------------
+static thread_local char g_err[512] = "";
+
+static int fail(int code, const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof g_err, fmt, ap);
+  va_end(ap);
+  return code;
+}
+
+#define CU(call)                                                                                   \
+  do {                                                                                             \
+    cudaError_t e_ = (call);                                                                       \
+    if (e_ != cudaSuccess) return fail(B200TFS_E_CUDA, "%s: %s", #call, cudaGetErrorString(e_));   \
+  } while (0)
+
+// ------------------------------------------------------------------------------------------------
+// context
+// ------------------------------------------------------------------------------------------------
+namespace {
+
+struct Growable {  // device or pinned buffer that only grows
+  void* p = nullptr;
+  uint64_t cap = 0;
+};
+
+constexpr int kSlots = 4;
+
+struct Slot {  // one in-flight plan upload: pinned image + device image + completion event
+  Growable host, dev;
+  cudaEvent_t done = nullptr;
+  bool pending = false;
+};
+
+}  // namespace
+
+struct b200tfs_ctx {
+  int device = 0;
+  int sm_count = 148;
+  cudaStream_t stream = nullptr;
+  Slot slots[kSlots];
+  int next_slot = 0;
+  Growable scratch_dev;   // parse tables / varint tile tables
+  Growable scratch_host;  // pinned mirror of the parse tables
+  Growable stage_dev;     // *_host entry points: tensors (encode) or wire (decode) staged on the device
+  Growable arena_dev;     // *_host entry points: wire arena (encode) / unpacked tensors (decode)
+  uint64_t launches = 0;
+  uint32_t tile_bytes_override = 0;
+};
+
+static int grow_dev(b200tfs_ctx* c, Growable& g, uint64_t need) {
+  if (need <= g.cap) return B200TFS_OK;
+  uint64_t cap = std::max<uint64_t>(need, g.cap * 2);
+  cap = (cap + 0xFFFFull) & ~0xFFFFull;
+  CU(cudaStreamSynchronize(c->stream));
+  if (g.p) CU(cudaFree(g.p));
+  g.p = nullptr; g.cap = 0;
+  CU(cudaMalloc(&g.p, cap));
+  g.cap = cap;
+  return B200TFS_OK;
+}
+static int grow_host(b200tfs_ctx* c, Growable& g, uint64_t need) {
+  if (need <= g.cap) return B200TFS_OK;
+  uint64_t cap = std::max<uint64_t>(need, g.cap * 2);
+  cap = (cap + 0xFFFull) & ~0xFFFull;
+  CU(cudaStreamSynchronize(c->stream));
+  if (g.p) CU(cudaFreeHost(g.p));
+  g.p = nullptr; g.cap = 0;
+  CU(cudaHostAlloc(&g.p, cap, cudaHostAllocDefault));
+  g.cap = cap;
+  return B200TFS_OK;
+}
+
+// claim an upload slot with room for `bytes` in both images
+static int claim_slot(b200tfs_ctx* c, uint64_t bytes, Slot** out) {
+  Slot& s = c->slots[c->next_slot];
+  c->next_slot = (c->next_slot + 1) % kSlots;
+  if (s.pending) { CU(cudaEventSynchronize(s.done)); s.pending = false; }
+  int rc;
+  if ((rc = grow_host(c, s.host, bytes))) return rc;
+  if ((rc = grow_dev(c, s.dev, bytes))) return rc;
+  *out = &s;
+  return B200TFS_OK;
+}
+
+extern "C" {
+
+int b200tfs_abi_version(void) { return B200TFS_ABI_VERSION; }
+const char* b200tfs_last_error(void) { return g_err; }
+
+int b200tfs_device_count(int* count) {
+  if (!count) return fail(B200TFS_E_ARG, "count is NULL");
+  *count = 0;
+  cudaError_t e = cudaGetDeviceCount(count);
+  if (e != cudaSuccess) { *count = 0; return fail(B200TFS_E_CUDA, "cudaGetDeviceCount: %s", cudaGetErrorString(e)); }
+  return B200TFS_OK;
+}
+
+int b200tfs_create(int device, b200tfs_ctx** out) {
+  if (!out) return fail(B200TFS_E_ARG, "out is NULL");
+  *out = nullptr;
+  int n = 0;
+  cudaError_t e = cudaGetDeviceCount(&n);
+  if (e != cudaSuccess || n == 0)
+    return fail(B200TFS_E_CUDA, "no CUDA device (%s): this library has no CPU path", e == cudaSuccess ? "count=0" : cudaGetErrorString(e));
+  if (device < 0 || device >= n) return fail(B200TFS_E_ARG, "device %d out of range (have %d)", device, n);
+  CU(cudaSetDevice(device));
+  b200tfs_ctx* c = new b200tfs_ctx();
+  c->device = device;
+  cudaDeviceProp prop;
+  if (cudaGetDeviceProperties(&prop, device) == cudaSuccess) c->sm_count = prop.multiProcessorCount;
+  e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking);
+  if (e != cudaSuccess) { delete c; return fail(B200TFS_E_CUDA, "cudaStreamCreate: %s", cudaGetErrorString(e)); }
+  for (auto& s : c->slots) {
+    e = cudaEventCreateWithFlags(&s.done, cudaEventDisableTiming);
+    if (e != cudaSuccess) { delete c; return fail(B200TFS_E_CUDA, "cudaEventCreate: %s", cudaGetErrorString(e)); }
+  }
+  const char* tb = getenv("B200TFS_TILE_BYTES");
+  if (tb) c->tile_bytes_override = (uint32_t)strtoul(tb, nullptr, 10);
+  *out = c;
+  return B200TFS_OK;
+}
+
+int b200tfs_destroy(b200tfs_ctx* c) {
+  if (!c) return B200TFS_OK;
+  cudaSetDevice(c->device);
+  cudaStreamSynchronize(c->stream);
+  for (auto& s : c->slots) {
+    if (s.host.p) cudaFreeHost(s.host.p);
+    if (s.dev.p) cudaFree(s.dev.p);
+    if (s.done) cudaEventDestroy(s.done);
+  }
+  if (c->scratch_dev.p) cudaFree(c->scratch_dev.p);
+  if (c->scratch_host.p) cudaFreeHost(c->scratch_host.p);
+  if (c->stage_dev.p) cudaFree(c->stage_dev.p);
+  if (c->arena_dev.p) cudaFree(c->arena_dev.p);
+  cudaStreamDestroy(c->stream);
+  delete c;
+  return B200TFS_OK;
+}
+
+int b200tfs_sync(b200tfs_ctx* c) {
+  if (!c) return fail(B200TFS_E_ARG, "ctx is NULL");
+  CU(cudaStreamSynchronize(c->stream));
+  return B200TFS_OK;
+}
+void* b200tfs_stream(b200tfs_ctx* c) { return c ? (void*)c->stream : nullptr; }
+int b200tfs_kernel_launches(b200tfs_ctx* c, uint64_t* count) {
+  if (!c || !count) return fail(B200TFS_E_ARG, "NULL argument");
+  *count = c->launches;
+  return B200TFS_OK;
+}
+
+// ---- memory / events ------------------------------------------------------------------------
+int b200tfs_malloc(b200tfs_ctx* c, uint64_t bytes, void** dptr) {
+  if (!c || !dptr) return fail(B200TFS_E_ARG, "NULL argument");
+  CU(cudaSetDevice(c->device));
+  CU(cudaMalloc(dptr, bytes ? bytes : 1));
+  return B200TFS_OK;
+}
+int b200tfs_free(b200tfs_ctx* c, void* dptr) {
+  if (!c) return fail(B200TFS_E_ARG, "ctx is NULL");
+  CU(cudaSetDevice(c->device));
+  CU(cudaFree(dptr));
+  return B200TFS_OK;
+}
+int b200tfs_host_alloc(uint64_t bytes, void** hptr) {
+  if (!hptr) return fail(B200TFS_E_ARG, "hptr is NULL");
+  CU(cudaHostAlloc(hptr, bytes ? bytes : 1, cudaHostAllocPortable));
+  return B200TFS_OK;
+}
+int b200tfs_host_free(void* hptr) { CU(cudaFreeHost(hptr)); return B200TFS_OK; }
+int b200tfs_memcpy_h2d(b200tfs_ctx* c, void* d, const void* h, uint64_t n) {
+  if (!c) return fail(B200TFS_E_ARG, "ctx is NULL");
+  if (n) CU(cudaMemcpyAsync(d, h, n, cudaMemcpyHostToDevice, c->stream));
+  return B200TFS_OK;
+}
+int b200tfs_memcpy_d2h(b200tfs_ctx* c, void* h, const void* d, uint64_t n) {
+  if (!c) return fail(B200TFS_E_ARG, "ctx is NULL");
+  if (n) CU(cudaMemcpyAsync(h, d, n, cudaMemcpyDeviceToHost, c->stream));
+  return B200TFS_OK;
+}
+int b200tfs_memcpy_d2d(b200tfs_ctx* c, void* d, const void* s, uint64_t n) {
+  if (!c) return fail(B200TFS_E_ARG, "ctx is NULL");
+  if (n) CU(cudaMemcpyAsync(d, s, n, cudaMemcpyDeviceToDevice, c->stream));
+  return B200TFS_OK;
+}
+int b200tfs_memset(b200tfs_ctx* c, void* d, int v, uint64_t n) {
+  if (!c) return fail(B200TFS_E_ARG, "ctx is NULL");
+  if (n) CU(cudaMemsetAsync(d, v, n, c->stream));
+  return B200TFS_OK;
+}
+int b200tfs_event_create(void** ev) {
+  if (!ev) return fail(B200TFS_E_ARG, "ev is NULL");
+  cudaEvent_t e;
+  CU(cudaEventCreate(&e));
+  *ev = e;
+  return B200TFS_OK;
+}
+int b200tfs_event_destroy(void* ev) { CU(cudaEventDestroy((cudaEvent_t)ev)); return B200TFS_OK; }
+int b200tfs_event_record(b200tfs_ctx* c, void* ev) {
+  if (!c) return fail(B200TFS_E_ARG, "ctx is NULL");
+  CU(cudaEventRecord((cudaEvent_t)ev, c->stream));
+  return B200TFS_OK;
+}
+int b200tfs_event_sync(void* ev) { CU(cudaEventSynchronize((cudaEvent_t)ev)); return B200TFS_OK; }
+int b200tfs_event_elapsed_ms(void* a, void* b, float* ms) {
+  if (!ms) return fail(B200TFS_E_ARG, "ms is NULL");
+  CU(cudaEventElapsedTime(ms, (cudaEvent_t)a, (cudaEvent_t)b));
+  return B200TFS_OK;
+}
+
+// ---- dtype table -------------------------------------------------------------------------------
+int b200tfs_dtype_size(int32_t dt) { return (int)dtype_info(dt).elem_size; }
+int b200tfs_dtype_field(int32_t dt) { return (int)dtype_info(dt).field; }
+int b200tfs_cast_supported(int32_t src, int32_t wire) {
+  if (src == wire) return dtype_info(src).kind != VK_NONE && dtype_info(src).kind != VK_STRING;
+  return (wire == DT_FLOAT && (src == DT_HALF || src == DT_BFLOAT16)) ? 1 : 0;
+}
+
+}  // extern "C"
+
+// ------------------------------------------------------------------------------------------------
+// wire-size arithmetic and header bytes
+// ------------------------------------------------------------------------------------------------
+namespace {
+
+constexpr uint64_t kProtoLimit = 0x7FFFFFFFull;  // protobuf's 2 GiB message limit
+
+struct TensorLayout {
+  uint64_t n_elems = 0;
+  uint64_t payload_len = 0;  // bytes of the values field body on the wire (0: field omitted)
+  uint64_t header_len = 0;   // bytes before the payload
+  uint32_t op = OP_COPY;     // MoveOp for fixed-width payloads
+  bool varint = false;       // payload produced by the varint kernels
+  DtypeInfo src_info{}, wire_info{};
+};
+
+int tensor_layout(const b200tfs_tensor& t, TensorLayout* L, std::vector<uint8_t>* hdr) {
+  if (t.flags & B200TFS_F_PRESERIALIZED) {  // an already serialised TensorProto: all payload, no header
+    if (t.packed_len > kProtoLimit) return fail(B200TFS_E_TOOBIG, "serialised TensorProto exceeds 2 GiB");
+    L->n_elems = t.packed_len; L->payload_len = t.packed_len; L->header_len = 0; L->op = OP_COPY; L->varint = false;
+    return B200TFS_OK;
+  }
+  if (t.rank < 0 || t.rank > 254) return fail(B200TFS_E_SHAPE, "rank %d outside [0, 254]", t.rank);
+  if (t.rank && !t.dims) return fail(B200TFS_E_ARG, "dims is NULL");
+  L->src_info = dtype_info(t.src_dtype);
+  L->wire_info = dtype_info(t.wire_dtype);
+  if (L->src_info.kind == VK_NONE || L->wire_info.kind == VK_NONE)
+    return fail(B200TFS_E_DTYPE, "dtype %d -> %d is not in the TensorProto table", t.src_dtype, t.wire_dtype);
+  if (L->src_info.kind == VK_STRING || L->wire_info.kind == VK_STRING)
+    return fail(B200TFS_E_DTYPE, "DT_STRING tensors are assembled on the host (string_val is not a device payload)");
+  if (!b200tfs_cast_supported(t.src_dtype, t.wire_dtype))
+    return fail(B200TFS_E_DTYPE, "cast DT %d -> DT %d is not supported", t.src_dtype, t.wire_dtype);
+  uint64_t n = 1;
+  for (int i = 0; i < t.rank; ++i) {
+    int64_t d = t.dims[i];
+    if (d < 0) return fail(B200TFS_E_SHAPE, "negative dim %lld", (long long)d);
+    if (d && n > kProtoLimit * 16 / (uint64_t)d) return fail(B200TFS_E_TOOBIG, "tensor too large for one protobuf message");
+    n *= (uint64_t)d;
+  }
+  L->n_elems = n;
+  const bool content = (t.flags & B200TFS_F_TENSOR_CONTENT) != 0;
+  const bool cast = t.src_dtype != t.wire_dtype;
+  uint32_t field;
+  if (content) {
+    field = F_CONTENT;
+    L->payload_len = n * L->wire_info.elem_size;
+    L->op = cast ? (t.src_dtype == DT_HALF ? OP_H2F : OP_B2F) : OP_COPY;
+  } else {
+    field = L->wire_info.field;
+    switch (L->wire_info.kind) {
+      case VK_FIXED:
+        L->payload_len = n * L->wire_info.elem_size;
+        if (cast) L->op = (t.src_dtype == DT_HALF) ? OP_H2F : OP_B2F;
+        else L->op = (t.wire_dtype == DT_FLOAT && !(t.flags & B200TFS_F_KEEP_SNAN)) ? OP_QUIET_SRC : OP_COPY;
+        break;
+      case VK_BOOL:
+        L->payload_len = n;
+        L->op = OP_BOOL;
+        break;
+      default:  // VK_VARINT
+        L->varint = true;
+        if (n && t.packed_len == 0)
+          return fail(B200TFS_E_ARG, "varint dtype %d: packed_len not set, call b200tfs_measure first", t.wire_dtype);
+        L->payload_len = n ? t.packed_len : 0;
+        break;
+    }
+  }
+  if (L->payload_len > kProtoLimit) return fail(B200TFS_E_TOOBIG, "payload of %llu bytes exceeds protobuf's 2 GiB limit", (unsigned long long)L->payload_len);
+  // header: 08 vi(dtype) 12 vi(shape_len) {12 vi(dim_len) [08 vi(size)]}* [tag vi(payload_len)]
+  uint8_t tmp[16];
+  size_t base = hdr ? hdr->size() : 0;
+  uint64_t shape_len = 0;
+  for (int i = 0; i < t.rank; ++i) shape_len += 2 + (t.dims[i] ? 1 + varint_len((uint64_t)t.dims[i]) : 0);
+  uint64_t hl = 1 + varint_len((uint64_t)(uint32_t)t.wire_dtype) + 1 + varint_len(shape_len) + shape_len;
+  if (L->payload_len) hl += varint_len(tag_of(field, WT_LEN)) + varint_len(L->payload_len);
+  L->header_len = hl;
+  if (hdr) {
+    auto put = [&](const uint8_t* p, uint32_t k) { hdr->insert(hdr->end(), p, p + k); };
+    tmp[0] = 0x08; put(tmp, 1);
+    put(tmp, put_varint(tmp, (uint64_t)(uint32_t)t.wire_dtype));
+    tmp[0] = 0x12; put(tmp, 1);
+    put(tmp, put_varint(tmp, shape_len));
+    for (int i = 0; i < t.rank; ++i) {
+      uint64_t d = (uint64_t)t.dims[i];
+      tmp[0] = 0x12; put(tmp, 1);
+      if (d) {
+        tmp[0] = (uint8_t)(1 + varint_len(d)); tmp[1] = 0x08; put(tmp, 2);
+        put(tmp, put_varint(tmp, d));
+      } else {
+        tmp[0] = 0x00; put(tmp, 1);  // Dim(size=0) is an empty sub-message (Q2)
+      }
+    }
+    if (L->payload_len) {
+      put(tmp, put_varint(tmp, tag_of(field, WT_LEN)));
+      put(tmp, put_varint(tmp, L->payload_len));
+    }
+    if (hdr->size() - base != hl) return fail(B200TFS_E_ARG, "internal: header length mismatch");
+  }
+  return B200TFS_OK;
+}
+
+// key order.  UPB: bytewise on the common prefix; on a tie the LONGER key first.
+int order_keys(int32_t n, const char* const* keys, const int64_t* lens, int32_t order, int32_t* perm) {
+  for (int i = 0; i < n; ++i) perm[i] = i;
+  if (order == B200TFS_ORDER_GIVEN) return B200TFS_OK;
+  if (order != B200TFS_ORDER_UPB && order != B200TFS_ORDER_BYTES) return fail(B200TFS_E_ARG, "unknown key order %d", order);
+  std::stable_sort(perm, perm + n, [&](int a, int b) {
+    size_t la = (size_t)lens[a], lb = (size_t)lens[b];
+    int c = memcmp(keys[a], keys[b], std::min(la, lb));
+    if (c) return c < 0;
+    if (la == lb) return false;
+    return order == B200TFS_ORDER_UPB ? la > lb : la < lb;
+  });
+  return B200TFS_OK;
+}
+
+struct VarJob {  // one varint-packed payload (handled by the varint kernels after move_kernel)
+  const uint8_t* src;
+  uint8_t* dst;
+  uint64_t n_elems;
+  uint64_t packed_len;
+  int32_t src_dtype;
+};
+
+// Accumulates the pieces of a batch of records into a plan image.
+struct PlanBuilder {
+  std::vector<MoveItem> items;
+  std::vector<SmallItem> smalls;
+  std::vector<uint8_t> blob;
+  std::vector<VarJob> varjobs;
+  uint64_t large_bytes = 0;
+
+  void header(uint8_t* dst, size_t blob_off, size_t n) {
+    // split long headers so one warp never walks more than kSmallMax bytes
+    while (n) {
+      uint32_t k = (uint32_t)std::min<size_t>(n, kSmallMax);
+      smalls.push_back(SmallItem{(uint64_t)blob_off, dst, k, OP_COPY | OP_FLAG_BLOB});
+      dst += k; blob_off += k; n -= k;
+    }
+  }
+  void payload(const uint8_t* src, uint8_t* dst, uint64_t n_out, uint32_t op) {
+    if (!n_out) return;
+    if (n_out <= kSmallMax) smalls.push_back(SmallItem{(uint64_t)(uintptr_t)src, dst, (uint32_t)n_out, op});
+    else { items.push_back(MoveItem{src, dst, n_out, op, 0}); large_bytes += n_out; }
+  }
+};
+
+uint32_t pick_vec_per_tile(const b200tfs_ctx* c, uint64_t large_bytes) {
+  uint64_t tile = c->tile_bytes_override;
+  if (!tile) {
+    uint64_t target_tiles = (uint64_t)c->sm_count * 4;
+    tile = (large_bytes + target_tiles - 1) / target_tiles;
+    tile = (tile + 4095) & ~4095ull;
+    tile = std::min<uint64_t>(std::max<uint64_t>(tile, 4096), 65536);
+  }
+  tile = std::max<uint64_t>(tile & ~31ull, 32);
+  return (uint32_t)(tile / 16);
+}
+
+// Serialise the plan image and launch move_kernel.  blob offsets inside SmallItems are rebased onto
+// the image.
+int launch_plan(b200tfs_ctx* c, PlanBuilder& pb) {
+  if (pb.items.empty() && pb.smalls.empty()) return B200TFS_OK;
+  const uint32_t vpt = pick_vec_per_tile(c, pb.large_bytes);
+  // tiles
+  uint64_t n_tiles = 0;
+  uint32_t uniform = 0;
+  bool is_uniform = !pb.items.empty();
+  for (auto& it : pb.items) {
+    uint64_t vecs = (it.n_out + 15) >> 4;
+    uint64_t t = std::max<uint64_t>(1, (vecs + vpt - 1) / vpt);
+    if (n_tiles + t > 0x7FFFFFFFull) return fail(B200TFS_E_TOOBIG, "batch needs more than 2^31 tiles");
+    it.first_tile = (uint32_t)n_tiles;
+    if (&it == &pb.items[0]) uniform = (uint32_t)t; else if (t != uniform) is_uniform = false;
+    n_tiles += t;
+  }
+  if (!is_uniform) uniform = 0;
+  PlanHeader ph{};
+  ph.n_items = (uint32_t)pb.items.size();
+  ph.n_tiles = (uint32_t)n_tiles;
+  ph.n_small = (uint32_t)pb.smalls.size();
+  ph.uniform_tpi = uniform;
+  ph.vec_per_tile = vpt;
+  uint64_t off = (sizeof(PlanHeader) + 15) & ~15ull;
+  ph.off_items = (uint32_t)off; off += pb.items.size() * sizeof(MoveItem);
+  ph.off_tiles = (uint32_t)off; if (!uniform) off += n_tiles * sizeof(TileRef);
+  off = (off + 15) & ~15ull;
+  ph.off_small = (uint32_t)off; off += pb.smalls.size() * sizeof(SmallItem);
+  const uint64_t off_blob = off;
+  off += pb.blob.size();
+  const uint64_t image = (off + 15) & ~15ull;
+  if (image > 0xFFFFFFFFull) return fail(B200TFS_E_TOOBIG, "plan image larger than 4 GiB");
+
+  uint8_t inline_buf[kInlinePlanBytes];
+  uint8_t* img;
+  Slot* slot = nullptr;
+  const bool inl = image <= kInlinePlanBytes;
+  if (inl) img = inline_buf;
+  else {
+    int rc = claim_slot(c, image, &slot);
+    if (rc) return rc;
+    img = (uint8_t*)slot->host.p;
+  }
+  memcpy(img, &ph, sizeof ph);
+  if (!pb.items.empty()) memcpy(img + ph.off_items, pb.items.data(), pb.items.size() * sizeof(MoveItem));
+  if (!uniform && n_tiles) {
+    TileRef* tr = (TileRef*)(img + ph.off_tiles);
+    for (uint32_t i = 0; i < pb.items.size(); ++i) {
+      uint32_t t0 = pb.items[i].first_tile;
+      uint32_t t1 = (i + 1 < pb.items.size()) ? pb.items[i + 1].first_tile : (uint32_t)n_tiles;
+      for (uint32_t t = t0; t < t1; ++t) tr[t] = TileRef{i, t - t0};
+    }
+  }
+  SmallItem* sm = (SmallItem*)(img + ph.off_small);
+  for (size_t i = 0; i < pb.smalls.size(); ++i) {
+    sm[i] = pb.smalls[i];
+    if (sm[i].op & OP_FLAG_BLOB) sm[i].src += off_blob;
+  }
+  if (!pb.blob.empty()) memcpy(img + off_blob, pb.blob.data(), pb.blob.size());
+
+  const uint8_t* plan_dev = nullptr;
+  if (!inl) {
+    CU(cudaMemcpyAsync(slot->dev.p, img, image, cudaMemcpyHostToDevice, c->stream));
+    plan_dev = (const uint8_t*)slot->dev.p;
+  }
+  CU(launch_move(plan_dev, img, (uint32_t)image, ph.n_tiles, ph.n_small, c->stream));
+  c->launches += 1;
+  if (slot) { CU(cudaEventRecord(slot->done, c->stream)); slot->pending = true; }
+  return B200TFS_OK;
+}
+
+// record placement: slots start 256-byte aligned, then padded so the record's largest payload
+// starts 128-byte aligned (the vector path then needs no realignment for it)
+inline uint64_t place_record(uint64_t cursor, uint64_t largest_payload_off) {
+  uint64_t slot = (cursor + 255) & ~255ull;
+  uint64_t pad = (128 - (largest_payload_off & 127)) & 127;
+  return slot + pad;
+}
+
+// Lay one TensorProto at arena+rec_off; appends its pieces to the plan.  `hdr_prefix` bytes (entry
+// framing) have already been appended to pb.blob starting at blob_mark and precede the proto header.
+int plan_tensor(const b200tfs_tensor& t, const TensorLayout& L, uint8_t* dst_payload, PlanBuilder& pb) {
+  if (!L.payload_len) return B200TFS_OK;
+  if (L.varint) {
+    pb.varjobs.push_back(VarJob{(const uint8_t*)t.data, dst_payload, L.n_elems, L.payload_len, t.src_dtype});
+    return B200TFS_OK;
+  }
+  pb.payload((const uint8_t*)t.data, dst_payload, L.payload_len, L.op);
+  return B200TFS_OK;
+}
+
+int run_varjobs(b200tfs_ctx* c, PlanBuilder& pb);  // varint.cpp part below
+
+struct RequestLayout {
+  std::vector<TensorLayout> tl;
+  std::vector<int32_t> perm;
+  std::vector<uint64_t> tp_len, entry_len;
+  uint64_t spec_len = 0, version_len = 0, total = 0;
+  uint64_t largest_off = 0;
+  std::vector<uint64_t> payload_off;
+};
+
+int request_layout(const b200tfs_request& r, RequestLayout* R) {
+  if (r.n_inputs < 0) return fail(B200TFS_E_ARG, "n_inputs < 0");
+  if (r.n_inputs && !r.inputs) return fail(B200TFS_E_ARG, "inputs is NULL");
+  if (r.model_name_len < 0 || (r.model_name_len && !r.model_name)) return fail(B200TFS_E_ARG, "bad model_name");
+  const int n = r.n_inputs;
+  R->tl.resize(n); R->perm.resize(n); R->tp_len.resize(n); R->entry_len.resize(n); R->payload_off.resize(n);
+  std::vector<const char*> keys(n);
+  std::vector<int64_t> lens(n);
+  for (int i = 0; i < n; ++i) {
+    if (r.inputs[i].key_len < 0 || (r.inputs[i].key_len && !r.inputs[i].key)) return fail(B200TFS_E_ARG, "bad key on input %d", i);
+    keys[i] = r.inputs[i].key ? r.inputs[i].key : "";
+    lens[i] = r.inputs[i].key_len;
+  }
+  int rc = order_keys(n, keys.data(), lens.data(), r.order, R->perm.data());
+  if (rc) return rc;
+  // model_spec{ 0A vi name  [12 vi {08 vi(version)}] }
+  uint64_t spec = 0;
+  if (r.model_name_len) spec += 1 + varint_len((uint64_t)r.model_name_len) + (uint64_t)r.model_name_len;
+  R->version_len = 0;
+  if (r.has_version) {
+    R->version_len = r.version ? 1 + varint_len((uint64_t)r.version) : 0;
+    spec += 2 + R->version_len;
+  }
+  R->spec_len = spec;
+  uint64_t total = 1 + varint_len(spec) + spec;
+  uint64_t largest = 0;
+  R->largest_off = 0;
+  for (int j = 0; j < n; ++j) {
+    const b200tfs_tensor& t = r.inputs[R->perm[j]];
+    TensorLayout& L = R->tl[j];
+    if ((rc = tensor_layout(t, &L, nullptr))) return rc;
+    uint64_t tp = L.header_len + L.payload_len;
+    if (tp > kProtoLimit) return fail(B200TFS_E_TOOBIG, "TensorProto of %llu bytes exceeds 2 GiB", (unsigned long long)tp);
+    R->tp_len[j] = tp;
+    uint64_t el = 1 + varint_len((uint64_t)t.key_len) + (uint64_t)t.key_len + 1 + varint_len(tp) + tp;
+    R->entry_len[j] = el;
+    uint64_t entry_hdr = 1 + varint_len(el) + 1 + varint_len((uint64_t)t.key_len) + (uint64_t)t.key_len + 1 + varint_len(tp);
+    uint64_t payload_off = total + entry_hdr + L.header_len;
+    R->payload_off[j] = payload_off;
+    if (L.payload_len > largest) { largest = L.payload_len; R->largest_off = payload_off; }
+    total += 1 + varint_len(el) + el;
+  }
+  if (total > kProtoLimit) return fail(B200TFS_E_TOOBIG, "PredictRequest of %llu bytes exceeds protobuf's 2 GiB limit", (unsigned long long)total);
+  R->total = total;
+  return B200TFS_OK;
+}
+
+// append the wire bytes of request r to the plan, record at arena + rec_off
+int plan_request(const b200tfs_request& r, const RequestLayout& R, uint8_t* rec, PlanBuilder& pb) {
+  uint8_t tmp[16];
+  auto put = [&](const uint8_t* p, size_t k) { pb.blob.insert(pb.blob.end(), p, p + k); };
+  size_t mark = pb.blob.size();
+  uint8_t* cursor = rec;  // where the pending header run (blob[mark:]) will land
+  tmp[0] = 0x0A; put(tmp, 1);
+  put(tmp, put_varint(tmp, R.spec_len));
+  if (r.model_name_len) {
+    tmp[0] = 0x0A; put(tmp, 1);
+    put(tmp, put_varint(tmp, (uint64_t)r.model_name_len));
+    put((const uint8_t*)r.model_name, (size_t)r.model_name_len);
+  }
+  if (r.has_version) {
+    tmp[0] = 0x12; tmp[1] = (uint8_t)R.version_len; put(tmp, 2);
+    if (r.version) { tmp[0] = 0x08; put(tmp, 1); put(tmp, put_varint(tmp, (uint64_t)r.version)); }
+  }
+  for (int j = 0; j < r.n_inputs; ++j) {
+    const b200tfs_tensor& t = r.inputs[R.perm[j]];
+    tmp[0] = 0x12; put(tmp, 1);
+    put(tmp, put_varint(tmp, R.entry_len[j]));
+    tmp[0] = 0x0A; put(tmp, 1);
+    put(tmp, put_varint(tmp, (uint64_t)t.key_len));
+    if (t.key_len) put((const uint8_t*)t.key, (size_t)t.key_len);
+    tmp[0] = 0x12; put(tmp, 1);
+    put(tmp, put_varint(tmp, R.tp_len[j]));
+    TensorLayout L;
+    int rc = tensor_layout(t, &L, &pb.blob);
+    if (rc) return rc;
+    if (L.payload_len) {
+      size_t run = pb.blob.size() - mark;
+      pb.header(cursor, mark, run);
+      cursor += run;
+      if ((rc = plan_tensor(t, L, cursor, pb))) return rc;
+      cursor += L.payload_len;
+      mark = pb.blob.size();
+    }
+  }
+  size_t run = pb.blob.size() - mark;
+  if (run) { pb.header(cursor, mark, run); cursor += run; }
+  if ((uint64_t)(cursor - rec) != R.total) return fail(B200TFS_E_ARG, "internal: request length mismatch");
+  return B200TFS_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int b200tfs_tensor_proto_size(const b200tfs_tensor* t, uint64_t* header_len, uint64_t* total_len) {
+  if (!t) return fail(B200TFS_E_ARG, "tensor is NULL");
+  TensorLayout L;
+  int rc = tensor_layout(*t, &L, nullptr);
+  if (rc) return rc;
+  if (L.header_len + L.payload_len > kProtoLimit) return fail(B200TFS_E_TOOBIG, "TensorProto exceeds 2 GiB");
+  if (header_len) *header_len = L.header_len;
+  if (total_len) *total_len = L.header_len + L.payload_len;
+  return B200TFS_OK;
+}
+
+int b200tfs_request_size(const b200tfs_request* r, uint64_t* total_len) {
+  if (!r) return fail(B200TFS_E_ARG, "request is NULL");
+  RequestLayout R;
+  int rc = request_layout(*r, &R);
+  if (rc) return rc;
+  if (total_len) *total_len = R.total;
+  return B200TFS_OK;
+}
+
+int b200tfs_tensor_proto_header(const b200tfs_tensor* t, void* buf, uint64_t cap, uint64_t* len) {
+  if (!t || !len) return fail(B200TFS_E_ARG, "NULL argument");
+  TensorLayout L;
+  std::vector<uint8_t> h;
+  int rc = tensor_layout(*t, &L, &h);
+  if (rc) return rc;
+  *len = h.size();
+  if (h.size() > cap) return fail(B200TFS_E_SIZE, "header needs %zu bytes", h.size());
+  if (!h.empty()) memcpy(buf, h.data(), h.size());
+  return B200TFS_OK;
+}
+
+int b200tfs_request_frame(const b200tfs_request* r, void* buf, uint64_t cap, uint64_t* frame_len, uint64_t* payload_off,
+                          uint64_t* payload_len, int32_t* perm) {
+  if (!r || !frame_len) return fail(B200TFS_E_ARG, "NULL argument");
+  RequestLayout R;
+  int rc = request_layout(*r, &R);
+  if (rc) return rc;
+  PlanBuilder pb;  // planned against a NULL arena: only the blob (frame bytes in wire order) is used
+  if ((rc = plan_request(*r, R, nullptr, pb))) return rc;
+  *frame_len = pb.blob.size();
+  for (int j = 0; j < r->n_inputs; ++j) {
+    if (payload_off) payload_off[j] = R.payload_off[j];
+    if (payload_len) payload_len[j] = R.tl[j].payload_len;
+    if (perm) perm[j] = R.perm[j];
+  }
+  if (pb.blob.size() > cap) return fail(B200TFS_E_SIZE, "frame needs %zu bytes", pb.blob.size());
+  if (!pb.blob.empty()) memcpy(buf, pb.blob.data(), pb.blob.size());
+  return B200TFS_OK;
+}
+
+int b200tfs_order_keys(int32_t n, const char* const* keys, const int64_t* key_lens, int32_t order, int32_t* perm) {
+  if (n < 0 || (n && (!keys || !key_lens || !perm))) return fail(B200TFS_E_ARG, "bad arguments");
+  return order_keys(n, keys, key_lens, order, perm);
+}
+
+int b200tfs_tensor_arena_size(int32_t n, const b200tfs_tensor* tensors, uint64_t* bytes) {
+  if (n < 0 || (n && !tensors) || !bytes) return fail(B200TFS_E_ARG, "bad arguments");
+  uint64_t cursor = 0;
+  for (int i = 0; i < n; ++i) {
+    TensorLayout L;
+    int rc = tensor_layout(tensors[i], &L, nullptr);
+    if (rc) return rc;
+    cursor = place_record(cursor, L.header_len) + L.header_len + L.payload_len;
+  }
+  *bytes = (cursor + 255) & ~255ull;
+  return B200TFS_OK;
+}
+
+int b200tfs_request_arena_size(int32_t n, const b200tfs_request* reqs, uint64_t* bytes) {
+  if (n < 0 || (n && !reqs) || !bytes) return fail(B200TFS_E_ARG, "bad arguments");
+  uint64_t cursor = 0;
+  RequestLayout R;
+  for (int i = 0; i < n; ++i) {
+    int rc = request_layout(reqs[i], &R);
+    if (rc) return rc;
+    cursor = place_record(cursor, R.largest_off) + R.total;
+  }
+  *bytes = (cursor + 255) & ~255ull;
+  return B200TFS_OK;
+}
+
+int b200tfs_encode_tensor_protos(b200tfs_ctx* c, int32_t n, const b200tfs_tensor* tensors, void* arena_dev, uint64_t arena_cap,
+                                 uint64_t* rec_off, uint64_t* rec_len) {
+  if (!c || n < 0 || (n && (!tensors || !arena_dev || !rec_off || !rec_len))) return fail(B200TFS_E_ARG, "bad arguments");
+  if ((uintptr_t)arena_dev & 255) return fail(B200TFS_E_ARG, "arena must be 256-byte aligned");
+  CU(cudaSetDevice(c->device));
+  PlanBuilder pb;
+  uint64_t cursor = 0;
+  for (int i = 0; i < n; ++i) {
+    TensorLayout L;
+    size_t mark = pb.blob.size();
+    int rc = tensor_layout(tensors[i], &L, &pb.blob);
+    if (rc) return rc;
+    uint64_t total = L.header_len + L.payload_len;
+    if (total > kProtoLimit) return fail(B200TFS_E_TOOBIG, "TensorProto exceeds 2 GiB");
+    if (L.payload_len && !tensors[i].data) return fail(B200TFS_E_ARG, "tensor %d: data pointer is NULL", i);
+    uint64_t off = place_record(cursor, L.header_len);
+    if (off + total > arena_cap) return fail(B200TFS_E_SIZE, "arena too small: need %llu bytes", (unsigned long long)(off + total));
+    uint8_t* rec = (uint8_t*)arena_dev + off;
+    pb.header(rec, mark, L.header_len);
+    if ((rc = plan_tensor(tensors[i], L, rec + L.header_len, pb))) return rc;
+    rec_off[i] = off; rec_len[i] = total;
+    cursor = off + total;
+  }
+  int rc = launch_plan(c, pb);
+  if (rc) return rc;
+  return run_varjobs(c, pb);
+}
+
+int b200tfs_encode_requests(b200tfs_ctx* c, int32_t n, const b200tfs_request* reqs, void* arena_dev, uint64_t arena_cap,
+                            uint64_t* rec_off, uint64_t* rec_len) {
+  if (!c || n < 0 || (n && (!reqs || !arena_dev || !rec_off || !rec_len))) return fail(B200TFS_E_ARG, "bad arguments");
+  if ((uintptr_t)arena_dev & 255) return fail(B200TFS_E_ARG, "arena must be 256-byte aligned");
+  CU(cudaSetDevice(c->device));
+  PlanBuilder pb;
+  RequestLayout R;
+  uint64_t cursor = 0;
+  for (int i = 0; i < n; ++i) {
+    int rc = request_layout(reqs[i], &R);
+    if (rc) return rc;
+    for (int j = 0; j < reqs[i].n_inputs; ++j)
+      if (R.tl[j].payload_len && !reqs[i].inputs[R.perm[j]].data) return fail(B200TFS_E_ARG, "request %d: tensor data pointer is NULL", i);
+    uint64_t off = place_record(cursor, R.largest_off);
+    if (off + R.total > arena_cap) return fail(B200TFS_E_SIZE, "arena too small: need %llu bytes", (unsigned long long)(off + R.total));
+    if ((rc = plan_request(reqs[i], R, (uint8_t*)arena_dev + off, pb))) return rc;
+    rec_off[i] = off; rec_len[i] = R.total;
+    cursor = off + R.total;
+  }
+  int rc = launch_plan(c, pb);
+  if (rc) return rc;
+  return run_varjobs(c, pb);
+}
+
+// ---- decode ------------------------------------------------------------------------------------
+static int parse_common(b200tfs_ctx* c, const void* arena_dev, int32_t n, const uint64_t* rec_off, const uint64_t* rec_len,
+                        int32_t max_outputs, bool bare, b200tfs_output* outs, int32_t* n_outs, b200tfs_model_spec* specs,
+                        int32_t* rec_status) {
+  if (!c || n < 0 || (n && (!arena_dev || !rec_off || !rec_len || !outs || !rec_status))) return fail(B200TFS_E_ARG, "bad arguments");
+  if (!bare && (max_outputs <= 0 || !n_outs || !specs)) return fail(B200TFS_E_ARG, "bad arguments");
+  if (n == 0) return B200TFS_OK;
+  CU(cudaSetDevice(c->device));
+  if (bare) max_outputs = 1;
+  const uint64_t b_off = 0, b_len = b_off + 8ull * n, b_outs = (b_len + 8ull * n + 15) & ~15ull;
+  const uint64_t b_nouts = b_outs + sizeof(b200tfs_output) * (uint64_t)n * max_outputs;
+  const uint64_t b_specs = (b_nouts + 4ull * n + 15) & ~15ull;
+  const uint64_t b_status = b_specs + sizeof(b200tfs_model_spec) * (uint64_t)n;
+  const uint64_t total = (b_status + 4ull * n + 15) & ~15ull;
+  int rc;
+  if ((rc = grow_dev(c, c->scratch_dev, total))) return rc;
+  if ((rc = grow_host(c, c->scratch_host, total))) return rc;
+  uint8_t* h = (uint8_t*)c->scratch_host.p;
+  uint8_t* d = (uint8_t*)c->scratch_dev.p;
+  memcpy(h + b_off, rec_off, 8ull * n);
+  memcpy(h + b_len, rec_len, 8ull * n);
+  CU(cudaMemcpyAsync(d, h, b_outs, cudaMemcpyHostToDevice, c->stream));
+  if (bare)
+    CU(launch_parse_tensors((const uint8_t*)arena_dev, (const uint64_t*)(d + b_off), (const uint64_t*)(d + b_len), n,
+                            (b200tfs_output*)(d + b_outs), (int32_t*)(d + b_status), c->stream));
+  else
+    CU(launch_parse_responses((const uint8_t*)arena_dev, (const uint64_t*)(d + b_off), (const uint64_t*)(d + b_len), n, max_outputs,
+                              (b200tfs_output*)(d + b_outs), (int32_t*)(d + b_nouts), (b200tfs_model_spec*)(d + b_specs),
+                              (int32_t*)(d + b_status), c->stream));
+  c->launches += 1;
+  CU(cudaMemcpyAsync(h + b_outs, d + b_outs, total - b_outs, cudaMemcpyDeviceToHost, c->stream));
+  CU(cudaStreamSynchronize(c->stream));
+  memcpy(rec_status, h + b_status, 4ull * n);
+  if (bare) {
+    memcpy(outs, h + b_outs, sizeof(b200tfs_output) * (uint64_t)n);
+  } else {
+    memcpy(n_outs, h + b_nouts, 4ull * n);
+    memcpy(specs, h + b_specs, sizeof(b200tfs_model_spec) * (uint64_t)n);
+    for (int i = 0; i < n; ++i) {
+      int k = rec_status[i] == B200TFS_OK ? n_outs[i] : 0;
+      memcpy(outs + (size_t)i * max_outputs, h + b_outs + sizeof(b200tfs_output) * (uint64_t)i * max_outputs, sizeof(b200tfs_output) * (size_t)k);
+    }
+  }
+  return B200TFS_OK;
+}
+
+int b200tfs_parse_responses(b200tfs_ctx* c, const void* arena_dev, int32_t n, const uint64_t* rec_off, const uint64_t* rec_len,
+                            int32_t max_outputs, b200tfs_output* outs, int32_t* n_outs, b200tfs_model_spec* specs,
+                            int32_t* rec_status) {
+  return parse_common(c, arena_dev, n, rec_off, rec_len, max_outputs, false, outs, n_outs, specs, rec_status);
+}
+
+int b200tfs_parse_tensor_protos(b200tfs_ctx* c, const void* arena_dev, int32_t n, const uint64_t* rec_off, const uint64_t* rec_len,
+                                b200tfs_output* outs, int32_t* rec_status) {
+  return parse_common(c, arena_dev, n, rec_off, rec_len, 1, true, outs, nullptr, nullptr, rec_status);
+}
+
+}  // extern "C"
+
+// ------------------------------------------------------------------------------------------------
+// unpack
+// ------------------------------------------------------------------------------------------------
+namespace {
+
+struct VarDecodeJob {
+  const uint8_t* src[B200TFS_MAX_CHUNKS];
+  uint64_t len[B200TFS_MAX_CHUNKS];
+  int n_chunks;
+  uint8_t* dst;
+  uint64_t n_elems;
+  int32_t dtype;
+  int32_t out_index;
+  bool half_as_value;
+};
+
+int run_vardecode(b200tfs_ctx* c, std::vector<VarDecodeJob>& jobs, int32_t* status);  // below
+
+}  // namespace
+
+extern "C" int b200tfs_unpack_outputs(b200tfs_ctx* c, const void* arena_dev, int32_t m, const b200tfs_output* outs, void* const* dst_dev,
+                                      const int32_t* dst_dtype, int32_t* status) {
+  if (!c || m < 0 || (m && (!arena_dev || !outs || !dst_dev))) return fail(B200TFS_E_ARG, "bad arguments");
+  CU(cudaSetDevice(c->device));
+  PlanBuilder pb;
+  std::vector<VarDecodeJob> vjobs;
+  const uint8_t* w = (const uint8_t*)arena_dev;
+  for (int j = 0; j < m; ++j) {
+    const b200tfs_output& o = outs[j];
+    if (status) status[j] = B200TFS_OK;
+    if (!o.n_elems) continue;
+    DtypeInfo di = dtype_info(o.dtype);
+    if (di.kind == VK_NONE || di.kind == VK_STRING) return fail(B200TFS_E_DTYPE, "output %d: dtype %d has no device payload", j, o.dtype);
+    if (!dst_dev[j]) return fail(B200TFS_E_ARG, "output %d: dst is NULL", j);
+    int32_t want = dst_dtype ? dst_dtype[j] : o.dtype;
+    const bool half_as_value = (want == B200TFS_DT_HALF_REFQUIRK && o.dtype == DT_HALF);
+    if (half_as_value) want = DT_HALF;
+    uint8_t* dst = (uint8_t*)dst_dev[j];
+    if (o.n_chunks == 0) {
+      // tolerant path chosen by the caller: raw little-endian bytes from tensor_content
+      if (o.content_len != o.dst_bytes) return fail(B200TFS_E_SHAPE, "output %d: no values (tensor_content %llu bytes, need %llu)", j,
+                                                     (unsigned long long)o.content_len, (unsigned long long)o.dst_bytes);
+      if (want != o.dtype) return fail(B200TFS_E_DTYPE, "output %d: cast from tensor_content is not supported", j);
+      pb.payload(w + o.content_off, dst, o.content_len, OP_COPY);
+      continue;
+    }
+    if (di.kind == VK_FIXED) {
+      uint32_t op;
+      uint32_t num = 1, den = 1;  // dst bytes per src byte
+      if (want == o.dtype) op = (o.dtype == DT_FLOAT) ? OP_QUIET_DST : OP_COPY;
+      else if (o.dtype == DT_FLOAT && want == DT_HALF) { op = OP_F2H; den = 2; }
+      else if (o.dtype == DT_FLOAT && want == DT_BFLOAT16) { op = OP_F2B; den = 2; }
+      else return fail(B200TFS_E_DTYPE, "output %d: cast DT %d -> DT %d is not supported", j, o.dtype, want);
+      uint64_t run = 0;
+      for (int k = 0; k < o.n_chunks; ++k) {
+        pb.payload(w + o.chunk_off[k], dst + run, o.chunk_len[k] * num / den, op);
+        run += o.chunk_len[k] * num / den;
+      }
+    } else {  // packed varints (incl. bool_val)
+      if (want != o.dtype) return fail(B200TFS_E_DTYPE, "output %d: cast on varint dtypes is not supported", j);
+      VarDecodeJob vj{};
+      vj.n_chunks = o.n_chunks;
+      for (int k = 0; k < o.n_chunks; ++k) { vj.src[k] = w + o.chunk_off[k]; vj.len[k] = o.chunk_len[k]; }
+      vj.dst = dst; vj.n_elems = o.n_elems; vj.dtype = o.dtype; vj.out_index = j; vj.half_as_value = half_as_value;
+      vjobs.push_back(vj);
+    }
+  }
+  int rc = launch_plan(c, pb);
+  if (rc) return rc;
+  if (!vjobs.empty()) {
+    if ((rc = run_vardecode(c, vjobs, status))) return rc;
+  }
+  if (status) CU(cudaStreamSynchronize(c->stream));
+  return B200TFS_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// host-buffer entry points
+// ------------------------------------------------------------------------------------------------
+namespace {
+
+// bytes of source memory a tensor occupies
+uint64_t tensor_src_bytes(const b200tfs_tensor& t) {
+  if (t.flags & B200TFS_F_PRESERIALIZED) return t.packed_len;
+  uint64_t n = 1;
+  for (int i = 0; i < t.rank; ++i) n *= (uint64_t)t.dims[i];
+  return n * dtype_info(t.src_dtype).elem_size;
+}
+
+// copy every tensor of the batch to the device staging buffer, returning device-pointing clones
+int stage_tensors(b200tfs_ctx* c, std::vector<b200tfs_tensor>& ts) {
+  uint64_t total = 0;
+  for (auto& t : ts) {
+    if (!(t.flags & B200TFS_F_PRESERIALIZED)) {
+      if (dtype_info(t.src_dtype).kind == VK_NONE || dtype_info(t.src_dtype).kind == VK_STRING)
+        return fail(B200TFS_E_DTYPE, "dtype %d has no device payload", t.src_dtype);
+      if (t.rank < 0 || t.rank > 254 || (t.rank && !t.dims)) return fail(B200TFS_E_SHAPE, "bad rank/dims");
+      for (int i = 0; i < t.rank; ++i) if (t.dims[i] < 0) return fail(B200TFS_E_SHAPE, "negative dim");
+    }
+    total = ((total + 255) & ~255ull) + tensor_src_bytes(t);
+  }
+  int rc = grow_dev(c, c->stage_dev, total + 256);
+  if (rc) return rc;
+  uint64_t cur = 0;
+  for (auto& t : ts) {
+    cur = (cur + 255) & ~255ull;
+    uint64_t nb = tensor_src_bytes(t);
+    if (nb) {
+      if (!t.data) return fail(B200TFS_E_ARG, "tensor data pointer is NULL");
+      CU(cudaMemcpyAsync((uint8_t*)c->stage_dev.p + cur, t.data, nb, cudaMemcpyHostToDevice, c->stream));
+    }
+    t.data = (uint8_t*)c->stage_dev.p + cur;
+    cur += nb;
+  }
+  return B200TFS_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int b200tfs_encode_tensor_protos_host(b200tfs_ctx* c, int32_t n, const b200tfs_tensor* tensors, void* wire_host, uint64_t wire_cap,
+                                      uint64_t* rec_off, uint64_t* rec_len) {
+  if (!c || n < 0 || (n && (!tensors || !wire_host || !rec_off || !rec_len))) return fail(B200TFS_E_ARG, "bad arguments");
+  if (n == 0) return B200TFS_OK;
+  CU(cudaSetDevice(c->device));
+  std::vector<b200tfs_tensor> ts(tensors, tensors + n);
+  int rc = stage_tensors(c, ts);
+  if (rc) return rc;
+  if ((rc = b200tfs_measure(c, n, ts.data()))) return rc;
+  uint64_t need = 0;
+  if ((rc = b200tfs_tensor_arena_size(n, ts.data(), &need))) return rc;
+  if ((rc = grow_dev(c, c->arena_dev, need))) return rc;
+  if ((rc = b200tfs_encode_tensor_protos(c, n, ts.data(), c->arena_dev.p, c->arena_dev.cap, rec_off, rec_len))) return rc;
+  const uint64_t lo = rec_off[0], hi = rec_off[n - 1] + rec_len[n - 1];
+  if (hi - lo > wire_cap) return fail(B200TFS_E_SIZE, "wire buffer too small: need %llu bytes", (unsigned long long)(hi - lo));
+  CU(cudaMemcpyAsync(wire_host, (uint8_t*)c->arena_dev.p + lo, hi - lo, cudaMemcpyDeviceToHost, c->stream));
+  CU(cudaStreamSynchronize(c->stream));
+  for (int i = 0; i < n; ++i) rec_off[i] -= lo;
+  return B200TFS_OK;
+}
+
+int b200tfs_encode_requests_host(b200tfs_ctx* c, int32_t n, const b200tfs_request* reqs, void* wire_host, uint64_t wire_cap,
+                                 uint64_t* rec_off, uint64_t* rec_len) {
+  if (!c || n < 0 || (n && (!reqs || !wire_host || !rec_off || !rec_len))) return fail(B200TFS_E_ARG, "bad arguments");
+  if (n == 0) return B200TFS_OK;
+  CU(cudaSetDevice(c->device));
+  // flatten every input of every request, stage them, then rebuild request structs on the clones
+  std::vector<b200tfs_tensor> ts;
+  for (int i = 0; i < n; ++i) {
+    if (reqs[i].n_inputs < 0 || (reqs[i].n_inputs && !reqs[i].inputs)) return fail(B200TFS_E_ARG, "bad request %d", i);
+    ts.insert(ts.end(), reqs[i].inputs, reqs[i].inputs + reqs[i].n_inputs);
+  }
+  int rc = stage_tensors(c, ts);
+  if (rc) return rc;
+  if ((rc = b200tfs_measure(c, (int32_t)ts.size(), ts.data()))) return rc;
+  std::vector<b200tfs_request> rq(reqs, reqs + n);
+  size_t k = 0;
+  for (int i = 0; i < n; ++i) { rq[i].inputs = ts.data() + k; k += (size_t)rq[i].n_inputs; }
+  uint64_t need = 0;
+  if ((rc = b200tfs_request_arena_size(n, rq.data(), &need))) return rc;
+  if ((rc = grow_dev(c, c->arena_dev, need))) return rc;
+  if ((rc = b200tfs_encode_requests(c, n, rq.data(), c->arena_dev.p, c->arena_dev.cap, rec_off, rec_len))) return rc;
+  const uint64_t lo = rec_off[0], hi = rec_off[n - 1] + rec_len[n - 1];
+  if (hi - lo > wire_cap) return fail(B200TFS_E_SIZE, "wire buffer too small: need %llu bytes", (unsigned long long)(hi - lo));
+  CU(cudaMemcpyAsync(wire_host, (uint8_t*)c->arena_dev.p + lo, hi - lo, cudaMemcpyDeviceToHost, c->stream));
+  CU(cudaStreamSynchronize(c->stream));
+  for (int i = 0; i < n; ++i) rec_off[i] -= lo;
+  return B200TFS_OK;
+}
+
+static int stage_wire(b200tfs_ctx* c, const void* wire_host, int32_t n, const uint64_t* rec_off, const uint64_t* rec_len, uint64_t* span) {
+  uint64_t hi = 0;
+  for (int i = 0; i < n; ++i) hi = std::max(hi, rec_off[i] + rec_len[i]);
+  int rc = grow_dev(c, c->stage_dev, hi + 64);
+  if (rc) return rc;
+  if (hi) CU(cudaMemcpyAsync(c->stage_dev.p, wire_host, hi, cudaMemcpyHostToDevice, c->stream));
+  *span = hi;
+  return B200TFS_OK;
+}
+
+int b200tfs_parse_responses_host(b200tfs_ctx* c, const void* wire_host, int32_t n, const uint64_t* rec_off, const uint64_t* rec_len,
+                                 int32_t max_outputs, b200tfs_output* outs, int32_t* n_outs, b200tfs_model_spec* specs,
+                                 int32_t* rec_status) {
+  if (!c || n < 0 || (n && (!wire_host || !rec_off || !rec_len))) return fail(B200TFS_E_ARG, "bad arguments");
+  if (n == 0) return B200TFS_OK;
+  CU(cudaSetDevice(c->device));
+  uint64_t span;
+  int rc = stage_wire(c, wire_host, n, rec_off, rec_len, &span);
+  if (rc) return rc;
+  return parse_common(c, c->stage_dev.p, n, rec_off, rec_len, max_outputs, false, outs, n_outs, specs, rec_status);
+}
+
+int b200tfs_parse_tensor_protos_host(b200tfs_ctx* c, const void* wire_host, int32_t n, const uint64_t* rec_off, const uint64_t* rec_len,
+                                     b200tfs_output* outs, int32_t* rec_status) {
+  if (!c || n < 0 || (n && (!wire_host || !rec_off || !rec_len))) return fail(B200TFS_E_ARG, "bad arguments");
+  if (n == 0) return B200TFS_OK;
+  CU(cudaSetDevice(c->device));
+  uint64_t span;
+  int rc = stage_wire(c, wire_host, n, rec_off, rec_len, &span);
+  if (rc) return rc;
+  return parse_common(c, c->stage_dev.p, n, rec_off, rec_len, 1, true, outs, nullptr, nullptr, rec_status);
+}
+
+int b200tfs_unpack_outputs_host(b200tfs_ctx* c, int32_t m, const b200tfs_output* outs, void* const* dst_host, const int32_t* dst_dtype,
+                                int32_t* status) {
+  if (!c || m < 0 || (m && (!outs || !dst_host))) return fail(B200TFS_E_ARG, "bad arguments");
+  if (m == 0) return B200TFS_OK;
+  CU(cudaSetDevice(c->device));
+  if (!c->stage_dev.p) return fail(B200TFS_E_ARG, "no staged wire: call b200tfs_parse_*_host first");
+  std::vector<uint64_t> off(m), nb(m);
+  uint64_t total = 0;
+  for (int j = 0; j < m; ++j) {
+    int32_t want = dst_dtype ? dst_dtype[j] : outs[j].dtype;
+    if (want == B200TFS_DT_HALF_REFQUIRK) want = DT_HALF;
+    nb[j] = outs[j].n_elems * dtype_info(want).elem_size;
+    total = (total + 255) & ~255ull;
+    off[j] = total;
+    total += nb[j];
+  }
+  int rc = grow_dev(c, c->arena_dev, total + 256);
+  if (rc) return rc;
+  std::vector<void*> dd(m);
+  for (int j = 0; j < m; ++j) dd[j] = (uint8_t*)c->arena_dev.p + off[j];
+  if ((rc = b200tfs_unpack_outputs(c, c->stage_dev.p, m, outs, dd.data(), dst_dtype, status))) return rc;
+  for (int j = 0; j < m; ++j)
+    if (nb[j]) {
+      if (!dst_host[j]) return fail(B200TFS_E_ARG, "output %d: dst is NULL", j);
+      CU(cudaMemcpyAsync(dst_host[j], dd[j], nb[j], cudaMemcpyDeviceToHost, c->stream));
+    }
+  CU(cudaStreamSynchronize(c->stream));
+  return B200TFS_OK;
+}
+
+}  // extern "C"
+
+// ------------------------------------------------------------------------------------------------
+// varint dtypes (phase 2: kernels in kernels.cu; wired here)
+// ------------------------------------------------------------------------------------------------
+#include "varint_host.inc"

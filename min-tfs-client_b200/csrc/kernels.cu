@@ -1,0 +1,692 @@
+// kernels.cu - sm_100a kernels of the TensorProto wire codec (pure HBM-bound byte packing: no
+// tensor cores, no tcgen05 - see DESIGN.md "Roofline").
+//
+//   move_kernel        the pack/unpack engine: moves every payload between tensor memory and the
+//                      wire arena (128-bit coalesced loads/stores, destination-aligned; a misaligned
+//                      side is realigned in registers with funnel shifts), applies the per-dtype
+//                      fix-up (float32 sNaN quieting, bool normalisation, f16/bf16 <-> f32 casts)
+//                      and writes the header fragments (tags, varint lengths, dims, keys).
+//   parse_kernel       one lane per PredictResponse / TensorProto: walks the tags (walker.h) and
+//                      tabulates dtype, dims and where the values lie.
+//   varint_*           two-pass packed-varint encode and decode (int_val / int64_val / uint32_val /
+//                      uint64_val / half_val / bool_val).
+//
+// What the reference does at these points: tensors.py:22 (per-element .item() loop feeding
+// RepeatedScalarContainer.extend), prediction_service_pb2_grpc.py:52-53 (SerializeToString /
+// FromString in the protobuf runtime), tensors.py:46 (per-element list -> np.array).
+#include <cuda_bf16.h>
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <string.h>
+
+#include "kernels.h"
+#include "plan.h"
+#include "walker.h"
+#include "wire.h"
+
+namespace b200tfs {
+
+// ------------------------------------------------------------------------------------------------
+// 128-bit global accessors
+// ------------------------------------------------------------------------------------------------
+// streaming load: read once, do not keep in L1
+__device__ __forceinline__ uint4 ld_stream(const uint8_t* p) {
+  uint4 r;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
+  return r;
+}
+// load that may allocate in L1: the shifted path reads every 16-byte block twice (as `lo` of one
+// vector and `hi` of its neighbour), the second read should hit L1
+__device__ __forceinline__ uint4 ld_reuse(const uint8_t* p) {
+  uint4 r;
+  asm volatile("ld.global.nc.v4.u32 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
+  return r;
+}
+__device__ __forceinline__ void st_stream(uint8_t* p, const uint4& v) {
+  asm volatile("st.global.L1::no_allocate.v4.u32 [%0], {%1,%2,%3,%4};"
+               :: "l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+
+__device__ __forceinline__ uint32_t bool_norm_word(uint32_t w) {
+  // per byte: b != 0 -> 1
+  uint32_t t = ((w & 0x7F7F7F7Fu) + 0x7F7F7F7Fu) | w;
+  return (t >> 7) & 0x01010101u;
+}
+
+template <uint32_t OP>
+__device__ __forceinline__ uint4 fix_vec(uint4 v) {
+  if (OP == OP_QUIET_SRC || OP == OP_QUIET_DST) {
+    v.x = quiet_f32(v.x); v.y = quiet_f32(v.y); v.z = quiet_f32(v.z); v.w = quiet_f32(v.w);
+  } else if (OP == OP_BOOL) {
+    v.x = bool_norm_word(v.x); v.y = bool_norm_word(v.y); v.z = bool_norm_word(v.z); v.w = bool_norm_word(v.w);
+  }
+  return v;
+}
+
+// bytes [k, k+16) of the 32-byte little-endian concatenation lo:hi, k = 4*Q + s/8, 0 < k < 16
+template <int Q>
+__device__ __forceinline__ uint4 shift_pair(const uint4& lo, const uint4& hi, uint32_t s) {
+  const uint32_t w[8] = {lo.x, lo.y, lo.z, lo.w, hi.x, hi.y, hi.z, hi.w};
+  uint4 o;
+  o.x = __funnelshift_r(w[Q + 0], w[Q + 1], s);
+  o.y = __funnelshift_r(w[Q + 1], w[Q + 2], s);
+  o.z = __funnelshift_r(w[Q + 2], w[Q + 3], s);
+  o.w = __funnelshift_r(w[Q + 3], w[Q + 4], s);
+  return o;
+}
+
+// ------------------------------------------------------------------------------------------------
+// element-exact byte generator: byte i of the output stream of `op` applied to src.  Used for the
+// ragged head / tail of every payload, for small items, and as the fallback when a payload's
+// alignment does not qualify for a vector path.  Alignment-agnostic by construction.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t ld_u32_bytes(const uint8_t* p) {
+  return (uint32_t)p[0] | ((uint32_t)p[1] << 8) | ((uint32_t)p[2] << 16) | ((uint32_t)p[3] << 24);
+}
+__device__ __forceinline__ uint32_t f16_bits_to_f32_bits(uint32_t h) {
+  return __float_as_uint(__half2float(__ushort_as_half((unsigned short)h)));
+}
+// widening casts follow IEEE-754 convertFormat: NaNs come out quiet with sign and payload kept
+// (what numpy's astype(float32) followed by the reference's float32 round trip produces)
+__device__ __forceinline__ uint32_t widen_f16(uint32_t h) {
+  if ((h & 0x7C00u) == 0x7C00u && (h & 0x3FFu)) return ((h & 0x8000u) << 16) | 0x7FC00000u | ((h & 0x3FFu) << 13);
+  return f16_bits_to_f32_bits(h);
+}
+__device__ __forceinline__ uint32_t widen_bf16(uint32_t h) { return quiet_f32(h << 16); }
+__device__ __forceinline__ uint32_t f32_bits_to_f16_bits(uint32_t w) {
+  return (uint32_t)__half_as_ushort(__float2half_rn(__uint_as_float(w)));
+}
+__device__ __forceinline__ uint32_t f32_bits_to_bf16_bits(uint32_t w) {
+  return (uint32_t)__bfloat16_as_ushort(__float2bfloat16_rn(__uint_as_float(w)));
+}
+
+__device__ __forceinline__ uint8_t gen_byte(uint32_t op, const uint8_t* src, uint64_t i) {
+  switch (op) {
+    case OP_COPY: return src[i];
+    case OP_BOOL: return src[i] != 0;
+    case OP_QUIET_SRC:
+    case OP_QUIET_DST: {
+      uint32_t w = quiet_f32(ld_u32_bytes(src + (i & ~3ull)));
+      return (uint8_t)(w >> (8 * (i & 3)));
+    }
+    case OP_H2F: {
+      uint64_t e = i >> 2;
+      uint32_t h = (uint32_t)src[2 * e] | ((uint32_t)src[2 * e + 1] << 8);
+      return (uint8_t)(widen_f16(h) >> (8 * (i & 3)));
+    }
+    case OP_B2F: {
+      uint64_t e = i >> 2;
+      uint32_t h = (uint32_t)src[2 * e] | ((uint32_t)src[2 * e + 1] << 8);
+      return (uint8_t)(widen_bf16(h) >> (8 * (i & 3)));
+    }
+    case OP_F2H: {
+      uint64_t e = i >> 1;
+      return (uint8_t)(f32_bits_to_f16_bits(ld_u32_bytes(src + 4 * e)) >> (8 * (i & 1)));
+    }
+    case OP_F2B: {
+      uint64_t e = i >> 1;
+      return (uint8_t)(f32_bits_to_bf16_bits(ld_u32_bytes(src + 4 * e)) >> (8 * (i & 1)));
+    }
+  }
+  return 0;
+}
+
+// source bytes consumed per output byte, as a ratio num/den
+__device__ __forceinline__ uint64_t src_bytes_for(uint32_t op, uint64_t n_out) {
+  if (op == OP_H2F || op == OP_B2F) return n_out >> 1;
+  if (op == OP_F2H || op == OP_F2B) return n_out << 1;
+  return n_out;
+}
+
+// ------------------------------------------------------------------------------------------------
+// same-width body: destination vectors [v0, v1) of a payload whose body starts at dst_body (16-byte
+// aligned) / src_body (any alignment).
+// ------------------------------------------------------------------------------------------------
+template <uint32_t OP>
+__device__ __forceinline__ void body_aligned(const uint8_t* src_body, uint8_t* dst_body, uint64_t v0, uint64_t v1) {
+  const uint64_t T = blockDim.x;
+  uint64_t v = v0 + threadIdx.x;
+  for (; v + 3 * T < v1; v += 4 * T) {
+    uint4 a0 = ld_stream(src_body + 16 * v);
+    uint4 a1 = ld_stream(src_body + 16 * (v + T));
+    uint4 a2 = ld_stream(src_body + 16 * (v + 2 * T));
+    uint4 a3 = ld_stream(src_body + 16 * (v + 3 * T));
+    st_stream(dst_body + 16 * v, fix_vec<OP>(a0));
+    st_stream(dst_body + 16 * (v + T), fix_vec<OP>(a1));
+    st_stream(dst_body + 16 * (v + 2 * T), fix_vec<OP>(a2));
+    st_stream(dst_body + 16 * (v + 3 * T), fix_vec<OP>(a3));
+  }
+  for (; v < v1; v += T) st_stream(dst_body + 16 * v, fix_vec<OP>(ld_stream(src_body + 16 * v)));
+}
+
+template <uint32_t OP, int Q>
+__device__ __forceinline__ void body_shifted_q(const uint8_t* S, uint8_t* dst_body, uint64_t v0, uint64_t v1, uint32_t s) {
+  // S = src_body rounded down to 16; output vector v = bytes [k, k+16) of blocks v, v+1 of S
+  constexpr bool PRE = (OP == OP_QUIET_SRC);  // elements line up with the source blocks
+  const uint64_t T = blockDim.x;
+  uint64_t v = v0 + threadIdx.x;
+  for (; v + T < v1; v += 2 * T) {
+    uint4 a0 = ld_reuse(S + 16 * v), b0 = ld_reuse(S + 16 * v + 16);
+    uint4 a1 = ld_reuse(S + 16 * (v + T)), b1 = ld_reuse(S + 16 * (v + T) + 16);
+    if (PRE) { a0 = fix_vec<OP>(a0); b0 = fix_vec<OP>(b0); a1 = fix_vec<OP>(a1); b1 = fix_vec<OP>(b1); }
+    uint4 o0 = shift_pair<Q>(a0, b0, s), o1 = shift_pair<Q>(a1, b1, s);
+    if (!PRE) { o0 = fix_vec<OP>(o0); o1 = fix_vec<OP>(o1); }
+    st_stream(dst_body + 16 * v, o0);
+    st_stream(dst_body + 16 * (v + T), o1);
+  }
+  for (; v < v1; v += T) {
+    uint4 a = ld_reuse(S + 16 * v), b = ld_reuse(S + 16 * v + 16);
+    if (PRE) { a = fix_vec<OP>(a); b = fix_vec<OP>(b); }
+    uint4 o = shift_pair<Q>(a, b, s);
+    if (!PRE) o = fix_vec<OP>(o);
+    st_stream(dst_body + 16 * v, o);
+  }
+}
+
+template <uint32_t OP>
+__device__ __forceinline__ void body_same_width(const uint8_t* src_body, uint8_t* dst_body, uint64_t v0, uint64_t v1) {
+  const uint32_t k = (uint32_t)((uintptr_t)src_body & 15);
+  if (k == 0) { body_aligned<OP>(src_body, dst_body, v0, v1); return; }
+  const uint8_t* S = src_body - k;
+  const uint32_t s = (k & 3) * 8;
+  switch (k >> 2) {  // uniform across the CTA
+    case 0: body_shifted_q<OP, 0>(S, dst_body, v0, v1, s); break;
+    case 1: body_shifted_q<OP, 1>(S, dst_body, v0, v1, s); break;
+    case 2: body_shifted_q<OP, 2>(S, dst_body, v0, v1, s); break;
+    default: body_shifted_q<OP, 3>(S, dst_body, v0, v1, s); break;
+  }
+}
+
+// f16 / bf16 -> f32 (encode-side cast).  Both sides 16-byte aligned; unit u = 16 source bytes -> 32 out.
+template <bool BF>
+__device__ __forceinline__ void body_widen(const uint8_t* src_body, uint8_t* dst_body, uint64_t u0, uint64_t u1) {
+  const uint64_t T = blockDim.x;
+  for (uint64_t u = u0 + threadIdx.x; u < u1; u += T) {
+    uint4 h = ld_stream(src_body + 16 * u);
+    uint4 lo, hi;
+    if (BF) {
+      lo.x = widen_bf16(h.x & 0xFFFF); lo.y = widen_bf16(h.x >> 16); lo.z = widen_bf16(h.y & 0xFFFF); lo.w = widen_bf16(h.y >> 16);
+      hi.x = widen_bf16(h.z & 0xFFFF); hi.y = widen_bf16(h.z >> 16); hi.z = widen_bf16(h.w & 0xFFFF); hi.w = widen_bf16(h.w >> 16);
+    } else {
+      lo.x = widen_f16(h.x & 0xFFFF); lo.y = widen_f16(h.x >> 16); lo.z = widen_f16(h.y & 0xFFFF); lo.w = widen_f16(h.y >> 16);
+      hi.x = widen_f16(h.z & 0xFFFF); hi.y = widen_f16(h.z >> 16); hi.z = widen_f16(h.w & 0xFFFF); hi.w = widen_f16(h.w >> 16);
+    }
+    st_stream(dst_body + 32 * u, lo);
+    st_stream(dst_body + 32 * u + 16, hi);
+  }
+}
+
+// f32 -> f16 / bf16 (decode-side cast).  dst 16-byte aligned; source any alignment.
+template <bool BF>
+__device__ __forceinline__ uint32_t narrow2(uint32_t a, uint32_t b) {
+  return BF ? (f32_bits_to_bf16_bits(a) | (f32_bits_to_bf16_bits(b) << 16))
+            : (f32_bits_to_f16_bits(a) | (f32_bits_to_f16_bits(b) << 16));
+}
+template <bool BF, int Q>
+__device__ __forceinline__ void body_narrow_q(const uint8_t* S, uint8_t* dst_body, uint64_t v0, uint64_t v1, uint32_t s, bool aligned) {
+  const uint64_t T = blockDim.x;
+  for (uint64_t v = v0 + threadIdx.x; v < v1; v += T) {
+    uint4 a = ld_reuse(S + 32 * v), b = ld_reuse(S + 32 * v + 16);
+    uint4 f0, f1;
+    if (aligned) { f0 = a; f1 = b; }
+    else {
+      uint4 c = ld_reuse(S + 32 * v + 32);
+      f0 = shift_pair<Q>(a, b, s); f1 = shift_pair<Q>(b, c, s);
+    }
+    uint4 o;
+    o.x = narrow2<BF>(f0.x, f0.y); o.y = narrow2<BF>(f0.z, f0.w);
+    o.z = narrow2<BF>(f1.x, f1.y); o.w = narrow2<BF>(f1.z, f1.w);
+    st_stream(dst_body + 16 * v, o);
+  }
+}
+template <bool BF>
+__device__ __forceinline__ void body_narrow(const uint8_t* src_body, uint8_t* dst_body, uint64_t v0, uint64_t v1) {
+  const uint32_t k = (uint32_t)((uintptr_t)src_body & 15);
+  const uint8_t* S = src_body - k;
+  const uint32_t s = (k & 3) * 8;
+  switch (k >> 2) {
+    case 0: body_narrow_q<BF, 0>(S, dst_body, v0, v1, s, k == 0); break;
+    case 1: body_narrow_q<BF, 1>(S, dst_body, v0, v1, s, false); break;
+    case 2: body_narrow_q<BF, 2>(S, dst_body, v0, v1, s, false); break;
+    default: body_narrow_q<BF, 3>(S, dst_body, v0, v1, s, false); break;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// one tile of one large payload
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t item_tiles(uint64_t n_out, uint32_t vpt) {
+  uint64_t vecs = (n_out + 15) >> 4;
+  uint64_t t = (vecs + vpt - 1) / vpt;
+  return t ? (uint32_t)t : 1u;
+}
+
+__device__ void move_tile(const MoveItem& it, uint32_t tile, uint32_t vpt) {
+  const uint32_t op = it.op;
+  const uint64_t n_out = it.n_out;
+  const uint8_t* src = it.src;
+  uint8_t* dst = it.dst;
+  const uint32_t n_tiles = item_tiles(n_out, vpt);
+  const bool last = (tile + 1 == n_tiles);
+  const uint64_t n_src = src_bytes_for(op, n_out);
+
+  // geometry of the vector body in destination space
+  uint64_t head = (16 - ((uintptr_t)dst & 15)) & 15;
+  if (head > n_out) head = n_out;
+  bool fast;
+  uint64_t nvec;  // destination vectors handled by a vector path
+  const uint8_t* src_body;
+  switch (op) {
+    case OP_COPY: case OP_BOOL: case OP_QUIET_SRC: case OP_QUIET_DST: {
+      src_body = src + head;
+      fast = true;
+      if (op == OP_QUIET_SRC) fast = (((uintptr_t)src & 3) == 0);
+      if (op == OP_QUIET_DST) fast = ((head & 3) == 0);
+      nvec = (n_out - head) >> 4;
+      uint32_t k = (uint32_t)((uintptr_t)src_body & 15);
+      if (k) {  // the shifted path reads block v+1: keep it inside the source
+        uint64_t avail = (uint64_t)((src + n_src) - (src_body - k)) >> 4;  // whole blocks available
+        uint64_t lim = avail ? avail - 1 : 0;
+        if (nvec > lim) nvec = lim;
+      }
+      break;
+    }
+    case OP_H2F: case OP_B2F: {
+      src_body = src;
+      fast = (head == 0) && (((uintptr_t)src & 15) == 0);
+      nvec = ((n_out) >> 5) << 1;  // whole 32-byte units, counted in 16-byte vectors
+      break;
+    }
+    default: {  // OP_F2H / OP_F2B
+      src_body = src + 2 * head;
+      fast = ((head & 1) == 0);
+      nvec = (n_out - head) >> 4;
+      uint32_t k = (uint32_t)((uintptr_t)src_body & 15);
+      uint64_t span = (uint64_t)((src + n_src) - (src_body - k));
+      uint64_t lim = k ? (span >= 16 ? (span - 16) >> 5 : 0) : (span >> 5);
+      if (nvec > lim) nvec = lim;
+      break;
+    }
+  }
+  if (!fast) { head = 0; nvec = 0; }
+
+  uint8_t* dst_body = dst + head;
+  uint64_t v0 = (uint64_t)tile * vpt, v1 = v0 + vpt;
+  if (v1 > nvec) v1 = nvec;
+  if (v0 < v1) {
+    switch (op) {
+      case OP_COPY: body_same_width<OP_COPY>(src_body, dst_body, v0, v1); break;
+      case OP_BOOL: body_same_width<OP_BOOL>(src_body, dst_body, v0, v1); break;
+      case OP_QUIET_SRC: body_same_width<OP_QUIET_SRC>(src_body, dst_body, v0, v1); break;
+      case OP_QUIET_DST: body_same_width<OP_QUIET_DST>(src_body, dst_body, v0, v1); break;
+      case OP_H2F: body_widen<false>(src_body, dst_body, v0 >> 1, v1 >> 1); break;
+      case OP_B2F: body_widen<true>(src_body, dst_body, v0 >> 1, v1 >> 1); break;
+      case OP_F2H: body_narrow<false>(src_body, dst_body, v0, v1); break;
+      default: body_narrow<true>(src_body, dst_body, v0, v1); break;
+    }
+  }
+  // ragged edges, element-exact
+  if (tile == 0 && head) {
+    for (uint64_t i = threadIdx.x; i < head; i += blockDim.x) dst[i] = gen_byte(op, src, i);
+  }
+  if (last) {
+    uint64_t done = head + (nvec << 4);
+    if (fast) {
+      for (uint64_t i = done + threadIdx.x; i < n_out; i += blockDim.x) dst[i] = gen_byte(op, src, i);
+    }
+  }
+  if (!fast) {  // whole payload through the byte generator, split by tile
+    uint64_t b0 = (uint64_t)tile * vpt * 16, b1 = b0 + (uint64_t)vpt * 16;
+    if (b1 > n_out || last) b1 = n_out;
+    for (uint64_t i = b0 + threadIdx.x; i < b1; i += blockDim.x) dst[i] = gen_byte(op, src, i);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// move_kernel: CTAs [0, n_tiles) each take one tile of a large payload; the CTAs after them take the
+// small items (header fragments, small payloads), one warp per item.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void move_body(const uint8_t* plan) {
+  const PlanHeader& ph = *reinterpret_cast<const PlanHeader*>(plan);
+  const uint32_t b = blockIdx.x;
+  if (b < ph.n_tiles) {
+    uint32_t item, tile;
+    if (ph.uniform_tpi) { item = b / ph.uniform_tpi; tile = b - item * ph.uniform_tpi; }
+    else {
+      TileRef tr = reinterpret_cast<const TileRef*>(plan + ph.off_tiles)[b];
+      item = tr.item; tile = tr.tile;
+    }
+    const MoveItem it = reinterpret_cast<const MoveItem*>(plan + ph.off_items)[item];
+    move_tile(it, tile, ph.vec_per_tile);
+  } else {
+    const uint32_t warps = blockDim.x >> 5;
+    const uint32_t idx = (b - ph.n_tiles) * warps + (threadIdx.x >> 5);
+    if (idx >= ph.n_small) return;
+    const SmallItem si = reinterpret_cast<const SmallItem*>(plan + ph.off_small)[idx];
+    const uint32_t op = si.op & ~OP_FLAG_BLOB;
+    const uint8_t* src = (si.op & OP_FLAG_BLOB) ? plan + si.src : reinterpret_cast<const uint8_t*>(si.src);
+    const uint32_t lane = threadIdx.x & 31;
+    for (uint32_t i = lane; i < si.n_out; i += 32) si.dst[i] = gen_byte(op, src, i);
+  }
+}
+
+__global__ void __launch_bounds__(kMoveThreads) move_kernel(const uint8_t* __restrict__ plan) { move_body(plan); }
+
+__global__ void __launch_bounds__(kMoveThreads) move_kernel_inline(const __grid_constant__ InlinePlan plan) {
+  move_body(plan.bytes);
+}
+
+// ------------------------------------------------------------------------------------------------
+// parse_kernel: one lane per record
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(32) parse_responses_kernel(const uint8_t* __restrict__ w, const uint64_t* __restrict__ rec_off,
+                                                             const uint64_t* __restrict__ rec_len, int n, int max_outputs,
+                                                             b200tfs_output* outs, int32_t* n_outs, b200tfs_model_spec* specs,
+                                                             int32_t* status) {
+  int r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= n) return;
+  int cnt = 0;
+  status[r] = walk_response(w, rec_off[r], rec_len[r], max_outputs, outs + (size_t)r * max_outputs, &cnt, specs + r);
+  n_outs[r] = cnt;
+}
+
+__global__ void __launch_bounds__(32) parse_tensors_kernel(const uint8_t* __restrict__ w, const uint64_t* __restrict__ rec_off,
+                                                           const uint64_t* __restrict__ rec_len, int n, b200tfs_output* outs,
+                                                           int32_t* status) {
+  int r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= n) return;
+  status[r] = walk_tensor_proto(w, rec_off[r], rec_len[r], outs + r);
+}
+
+// ------------------------------------------------------------------------------------------------
+// packed varints.  Encode is  tile lengths -> per-job exclusive scan -> emit ; decode is
+// terminator counts -> the same scan -> decode.  A tile is kVarTileElems elements (encode) or
+// kVarTileBytes wire bytes (decode); every kernel uses kVarThreads threads per CTA.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint64_t load_as_u64(const uint8_t* src, uint64_t e, uint32_t size, uint32_t is_signed) {
+  switch (size) {
+    case 1: { uint8_t v = src[e]; return is_signed ? (uint64_t)(int64_t)(int8_t)v : v; }
+    case 2: { uint16_t v = reinterpret_cast<const uint16_t*>(src)[e]; return is_signed ? (uint64_t)(int64_t)(int16_t)v : v; }
+    case 4: { uint32_t v = reinterpret_cast<const uint32_t*>(src)[e]; return is_signed ? (uint64_t)(int64_t)(int32_t)v : v; }
+    default: return reinterpret_cast<const uint64_t*>(src)[e];
+  }
+}
+
+// block-wide exclusive scan of one value per thread (kVarThreads threads); returns the exclusive
+// prefix and writes the block total to *total
+__device__ __forceinline__ uint32_t block_exclusive_scan(uint32_t v, uint32_t* total, uint32_t* warp_sums /* smem[kVarThreads/32] */) {
+  const uint32_t lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  uint32_t inc = v;
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    uint32_t n = __shfl_up_sync(0xFFFFFFFFu, inc, d);
+    if (lane >= d) inc += n;
+  }
+  if (lane == 31) warp_sums[wid] = inc;
+  __syncthreads();
+  uint32_t base = 0, tot = 0;
+#pragma unroll
+  for (uint32_t w = 0; w < kVarThreads / 32; ++w) {
+    uint32_t x = warp_sums[w];
+    if (w < wid) base += x;
+    tot += x;
+  }
+  __syncthreads();
+  *total = tot;
+  return base + inc - v;
+}
+
+// V1: bytes each encode tile will occupy
+__global__ void __launch_bounds__(kVarThreads) venc_len_kernel(const VarSeg* __restrict__ segs, const uint32_t* __restrict__ tile_seg,
+                                                               const VarJobDev* __restrict__ jobs, uint32_t* __restrict__ tile_val) {
+  __shared__ uint32_t warp_sums[kVarThreads / 32];
+  const uint32_t t = blockIdx.x;
+  const VarSeg sg = segs[tile_seg[t]];
+  const VarJobDev jb = jobs[sg.job];
+  const uint64_t e0 = (uint64_t)(t - sg.first_tile) * kVarTileElems;
+  const uint64_t e1 = min(sg.n, e0 + kVarTileElems);
+  uint32_t sum = 0;
+  for (uint64_t e = e0 + threadIdx.x; e < e1; e += kVarThreads) sum += varint_len_fast(load_as_u64(sg.src, e, jb.elem_size, jb.is_signed));
+  uint32_t total;
+  (void)block_exclusive_scan(sum, &total, warp_sums);
+  if (threadIdx.x == 0) tile_val[t] = total;
+}
+
+// per-job exclusive scan over its tiles (one CTA per job)
+__global__ void __launch_bounds__(kVarThreads) vscan_kernel(const VarJobDev* __restrict__ jobs, const uint32_t* __restrict__ tile_val,
+                                                            uint64_t* __restrict__ tile_off, uint64_t* __restrict__ job_total) {
+  __shared__ uint32_t warp_sums[kVarThreads / 32];
+  const VarJobDev jb = jobs[blockIdx.x];
+  uint64_t carry = 0;
+  for (uint32_t base = 0; base < jb.n_tiles; base += kVarThreads) {
+    const uint32_t i = base + threadIdx.x;
+    const uint32_t v = (i < jb.n_tiles) ? tile_val[jb.first_tile + i] : 0u;
+    uint32_t total;
+    const uint32_t ex = block_exclusive_scan(v, &total, warp_sums);
+    if (i < jb.n_tiles) tile_off[jb.first_tile + i] = carry + ex;
+    carry += total;
+  }
+  if (threadIdx.x == 0) job_total[blockIdx.x] = carry;
+}
+
+// V3: emit.  Elements are loaded striped (coalesced), transposed through shared memory so each thread
+// owns kVarPerThread consecutive elements, scanned, written as bytes into a staging buffer whose
+// 16-byte phase matches the destination, and streamed out with 128-bit stores.
+__global__ void __launch_bounds__(kVarThreads) venc_emit_kernel(const VarSeg* __restrict__ segs, const uint32_t* __restrict__ tile_seg,
+                                                                const VarJobDev* __restrict__ jobs, const uint64_t* __restrict__ tile_off) {
+  __shared__ uint64_t vals[kVarTileElems];
+  __shared__ __align__(16) uint8_t stage[kVarTileElems * 10 + 32];
+  __shared__ uint32_t warp_sums[kVarThreads / 32];
+  const uint32_t t = blockIdx.x;
+  const VarSeg sg = segs[tile_seg[t]];
+  const VarJobDev jb = jobs[sg.job];
+  const uint64_t e0 = (uint64_t)(t - sg.first_tile) * kVarTileElems;
+  const uint32_t cnt = (uint32_t)min((uint64_t)kVarTileElems, sg.n - e0);
+  for (uint32_t i = threadIdx.x; i < cnt; i += kVarThreads) vals[i] = load_as_u64(sg.src, e0 + i, jb.elem_size, jb.is_signed);
+  __syncthreads();
+  uint64_t mine[kVarPerThread];
+  uint32_t sum = 0;
+#pragma unroll
+  for (uint32_t i = 0; i < kVarPerThread; ++i) {
+    const uint32_t idx = threadIdx.x * kVarPerThread + i;
+    mine[i] = idx < cnt ? vals[idx] : 0;
+    sum += idx < cnt ? varint_len_fast(mine[i]) : 0u;
+  }
+  uint32_t total;
+  uint32_t off = block_exclusive_scan(sum, &total, warp_sums);
+  uint8_t* g = jb.dst + tile_off[t];          // first output byte of this tile
+  const uint32_t phase = (uint32_t)((uintptr_t)g & 15);
+  off += phase;
+#pragma unroll
+  for (uint32_t i = 0; i < kVarPerThread; ++i) {
+    if (threadIdx.x * kVarPerThread + i < cnt) {
+      uint64_t v = mine[i];
+      while (v >= 0x80) { stage[off++] = (uint8_t)(v | 0x80); v >>= 7; }
+      stage[off++] = (uint8_t)v;
+    }
+  }
+  __syncthreads();
+  // stage[phase .. phase+total) -> g[0 .. total); whole 16-byte vectors where the tile owns them
+  uint8_t* gbase = g - phase;  // 16-byte aligned
+  const uint32_t lo = phase, hi = phase + total;
+  const uint32_t v_lo = (lo + 15) >> 4, v_hi = hi >> 4;
+  if (v_lo < v_hi) {
+    for (uint32_t v = v_lo + threadIdx.x; v < v_hi; v += kVarThreads) st_stream(gbase + 16 * v, reinterpret_cast<const uint4*>(stage)[v]);
+    for (uint32_t i = lo + threadIdx.x; i < v_lo * 16; i += kVarThreads) gbase[i] = stage[i];
+    for (uint32_t i = v_hi * 16 + threadIdx.x; i < hi; i += kVarThreads) gbase[i] = stage[i];
+  } else {
+    for (uint32_t i = lo + threadIdx.x; i < hi; i += kVarThreads) gbase[i] = stage[i];
+  }
+}
+
+// D1: varint terminators (bytes with the top bit clear) per decode tile
+__global__ void __launch_bounds__(kVarThreads) vdec_count_kernel(const VarSeg* __restrict__ segs, const uint32_t* __restrict__ tile_seg,
+                                                                 uint32_t* __restrict__ tile_val) {
+  __shared__ uint32_t warp_sums[kVarThreads / 32];
+  const uint32_t t = blockIdx.x;
+  const VarSeg sg = segs[tile_seg[t]];
+  const uint64_t b0 = (uint64_t)(t - sg.first_tile) * kVarTileBytes;
+  const uint64_t b1 = min(sg.n, b0 + kVarTileBytes);
+  uint32_t cnt = 0;
+  // 16 bytes per thread; aligned vector loads where the whole block lies inside the chunk
+  const uint8_t* lo = sg.src + b0;
+  const uint8_t* hi = sg.src + b1;
+  const uint8_t* abase = (const uint8_t*)((uintptr_t)lo & ~(uintptr_t)15);
+  for (const uint8_t* p = abase + 16 * threadIdx.x; p < hi; p += 16 * kVarThreads) {
+    if (p >= lo && p + 16 <= hi) {
+      uint4 v = ld_reuse(p);
+      cnt += __popc(~v.x & 0x80808080u) + __popc(~v.y & 0x80808080u) + __popc(~v.z & 0x80808080u) + __popc(~v.w & 0x80808080u);
+    } else {
+      for (int i = 0; i < 16; ++i) if (p + i >= lo && p + i < hi) cnt += !(p[i] & 0x80);
+    }
+  }
+  uint32_t total;
+  (void)block_exclusive_scan(cnt, &total, warp_sums);
+  if (threadIdx.x == 0) tile_val[t] = total;
+}
+
+__device__ __forceinline__ void store_decoded(const VarJobDev& jb, uint64_t idx, uint64_t v, int32_t* status) {
+  uint8_t* d = jb.dst;
+  switch (jb.dtype) {
+    case DT_INT64: case DT_UINT64: reinterpret_cast<uint64_t*>(d)[idx] = v; break;
+    case DT_UINT32: reinterpret_cast<uint32_t*>(d)[idx] = (uint32_t)v; break;
+    case DT_INT32: reinterpret_cast<int32_t*>(d)[idx] = (int32_t)(uint32_t)v; break;
+    case DT_INT16: { int32_t x = (int32_t)(uint32_t)v; if (x < -32768 || x > 32767) *status = B200TFS_E_RANGE; reinterpret_cast<int16_t*>(d)[idx] = (int16_t)x; break; }
+    case DT_INT8: { int32_t x = (int32_t)(uint32_t)v; if (x < -128 || x > 127) *status = B200TFS_E_RANGE; reinterpret_cast<int8_t*>(d)[idx] = (int8_t)x; break; }
+    case DT_UINT16: { int32_t x = (int32_t)(uint32_t)v; if (x < 0 || x > 65535) *status = B200TFS_E_RANGE; reinterpret_cast<uint16_t*>(d)[idx] = (uint16_t)x; break; }
+    case DT_UINT8: { int32_t x = (int32_t)(uint32_t)v; if (x < 0 || x > 255) *status = B200TFS_E_RANGE; d[idx] = (uint8_t)x; break; }
+    case DT_BOOL: d[idx] = v != 0; break;
+    case DT_HALF: case DT_BFLOAT16:
+      if (jb.flags & kVarFlagHalfAsValue) reinterpret_cast<uint16_t*>(d)[idx] = __half_as_ushort(__int2half_rn((int32_t)(uint32_t)v));
+      else reinterpret_cast<uint16_t*>(d)[idx] = (uint16_t)v;
+      break;
+    default: break;
+  }
+}
+
+// D3: decode.  The tile's bytes (plus one byte of look-behind and nine of look-ahead inside the
+// chunk) are staged in shared memory; each thread owns 16 byte positions, finds the varints that
+// START there (previous byte is a terminator), ranks them with a block scan, and decodes each.
+__global__ void __launch_bounds__(kVarThreads) vdec_emit_kernel(const VarSeg* __restrict__ segs, const uint32_t* __restrict__ tile_seg,
+                                                                const VarJobDev* __restrict__ jobs, const uint64_t* __restrict__ tile_off,
+                                                                const uint64_t* __restrict__ job_total, int32_t* __restrict__ job_status) {
+  __shared__ uint8_t sm[kVarTileBytes + 16];
+  __shared__ uint32_t warp_sums[kVarThreads / 32];
+  const uint32_t t = blockIdx.x;
+  const VarSeg sg = segs[tile_seg[t]];
+  const VarJobDev jb = jobs[sg.job];
+  if (job_total[sg.job] != jb.n_elems) {  // element count != prod(shape): reshape() would raise
+    if (threadIdx.x == 0) job_status[sg.job] = B200TFS_E_SHAPE;
+    return;
+  }
+  const uint64_t b0 = (uint64_t)(t - sg.first_tile) * kVarTileBytes;
+  const uint64_t b1 = min(sg.n, b0 + kVarTileBytes);
+  const uint64_t s0 = b0 ? b0 - 1 : 0;                  // look-behind
+  const uint64_t s1 = min(sg.n, b1 + 9);                // look-ahead
+  for (uint64_t i = s0 + threadIdx.x; i < s1; i += kVarThreads) sm[i - s0] = sg.src[i];
+  __syncthreads();
+  // positions owned by this thread: b0 + 16*tid .. +16
+  const uint64_t p0 = b0 + 16ull * threadIdx.x;
+  uint32_t starts = 0;  // bit i: a varint starts at p0+i
+  uint32_t nstart = 0;
+#pragma unroll
+  for (uint32_t i = 0; i < 16; ++i) {
+    const uint64_t p = p0 + i;
+    if (p < b1) {
+      const bool st = (p == 0) || !(sm[p - 1 - s0] & 0x80);
+      starts |= (uint32_t)st << i;
+      nstart += st;
+    }
+  }
+  uint32_t total;
+  const uint32_t rank0 = block_exclusive_scan(nstart, &total, warp_sums);
+  // elements before this tile: terminators before b0 within the job == tile_off[t]; a start at the
+  // very first byte of a later tile is counted by the previous tile's last terminator
+  // (+1 when a varint straddles in from the previous tile: it precedes ours but its terminator is here)
+  uint64_t idx = tile_off[t] + rank0 + ((b0 > 0 && (sm[0] & 0x80)) ? 1u : 0u);
+  int32_t st_local = B200TFS_OK;
+  while (starts) {
+    const uint32_t i = __ffs(starts) - 1;
+    starts &= starts - 1;
+    uint64_t p = p0 + i, v = 0;
+    int k = 0;
+    for (; k < 10; ++k) {
+      if (p + k >= sg.n) { st_local = B200TFS_E_PARSE; break; }
+      const uint8_t b = sm[p + k - s0];
+      v |= (uint64_t)(b & 0x7F) << (7 * k);
+      if (!(b & 0x80)) break;
+    }
+    if (k == 10) st_local = B200TFS_E_PARSE;
+    if (idx < jb.n_elems) store_decoded(jb, idx, v, &st_local);
+    ++idx;
+  }
+  if (st_local != B200TFS_OK) atomicMin(&job_status[sg.job], st_local);
+}
+
+// ------------------------------------------------------------------------------------------------
+// launchers (the only symbols codec_host.cpp sees)
+// ------------------------------------------------------------------------------------------------
+cudaError_t launch_move(const uint8_t* plan_dev, const uint8_t* plan_host, uint32_t plan_bytes, uint32_t n_tiles,
+                        uint32_t n_small, cudaStream_t stream) {
+  const uint32_t warps = kMoveThreads / 32;
+  const uint32_t grid = n_tiles + (n_small + warps - 1) / warps;
+  if (grid == 0) return cudaSuccess;
+  if (plan_dev == nullptr) {
+    InlinePlan ip;
+    memcpy(ip.bytes, plan_host, plan_bytes);
+    move_kernel_inline<<<grid, kMoveThreads, 0, stream>>>(ip);
+  } else {
+    move_kernel<<<grid, kMoveThreads, 0, stream>>>(plan_dev);
+  }
+  return cudaGetLastError();
+}
+
+cudaError_t launch_parse_responses(const uint8_t* w, const uint64_t* rec_off, const uint64_t* rec_len, int n, int max_outputs,
+                                   b200tfs_output* outs, int32_t* n_outs, b200tfs_model_spec* specs, int32_t* status,
+                                   cudaStream_t stream) {
+  if (n <= 0) return cudaSuccess;
+  parse_responses_kernel<<<(n + 31) / 32, 32, 0, stream>>>(w, rec_off, rec_len, n, max_outputs, outs, n_outs, specs, status);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_parse_tensors(const uint8_t* w, const uint64_t* rec_off, const uint64_t* rec_len, int n, b200tfs_output* outs,
+                                 int32_t* status, cudaStream_t stream) {
+  if (n <= 0) return cudaSuccess;
+  parse_tensors_kernel<<<(n + 31) / 32, 32, 0, stream>>>(w, rec_off, rec_len, n, outs, status);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_venc_len(const VarSeg* segs, const uint32_t* tile_seg, const VarJobDev* jobs, uint32_t* tile_val, uint32_t n_tiles,
+                            cudaStream_t stream) {
+  if (!n_tiles) return cudaSuccess;
+  venc_len_kernel<<<n_tiles, kVarThreads, 0, stream>>>(segs, tile_seg, jobs, tile_val);
+  return cudaGetLastError();
+}
+cudaError_t launch_vscan(const VarJobDev* jobs, const uint32_t* tile_val, uint64_t* tile_off, uint64_t* job_total, uint32_t n_jobs,
+                         cudaStream_t stream) {
+  if (!n_jobs) return cudaSuccess;
+  vscan_kernel<<<n_jobs, kVarThreads, 0, stream>>>(jobs, tile_val, tile_off, job_total);
+  return cudaGetLastError();
+}
+cudaError_t launch_venc_emit(const VarSeg* segs, const uint32_t* tile_seg, const VarJobDev* jobs, const uint64_t* tile_off,
+                             uint32_t n_tiles, cudaStream_t stream) {
+  if (!n_tiles) return cudaSuccess;
+  venc_emit_kernel<<<n_tiles, kVarThreads, 0, stream>>>(segs, tile_seg, jobs, tile_off);
+  return cudaGetLastError();
+}
+cudaError_t launch_vdec_count(const VarSeg* segs, const uint32_t* tile_seg, uint32_t* tile_val, uint32_t n_tiles, cudaStream_t stream) {
+  if (!n_tiles) return cudaSuccess;
+  vdec_count_kernel<<<n_tiles, kVarThreads, 0, stream>>>(segs, tile_seg, tile_val);
+  return cudaGetLastError();
+}
+cudaError_t launch_vdec_emit(const VarSeg* segs, const uint32_t* tile_seg, const VarJobDev* jobs, const uint64_t* tile_off,
+                             const uint64_t* job_total, int32_t* job_status, uint32_t n_tiles, cudaStream_t stream) {
+  if (!n_tiles) return cudaSuccess;
+  vdec_emit_kernel<<<n_tiles, kVarThreads, 0, stream>>>(segs, tile_seg, jobs, tile_off, job_total, job_status);
+  return cudaGetLastError();
+}
+
+}  // namespace b200tfs

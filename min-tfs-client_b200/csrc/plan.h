@@ -1,0 +1,80 @@
+// plan.h - the launch plan shared by the host planner (codec_host.cpp) and the kernels (kernels.cu).
+//
+// A plan is a flat byte image: PlanHeader, then MoveItem[n_items], TileRef[n_tiles] (absent when
+// uniform_tpi != 0), SmallItem[n_small], then the header blob (the varint tags / lengths / dims /
+// keys the planner computed - the non-payload bytes of the wire).  It reaches the kernel either
+// by value in the kernel parameter space (<= kInlinePlanBytes, no copy at all: the C2 single-tensor
+// case) or through one pinned-host -> device copy.
+#pragma once
+#include <stdint.h>
+
+namespace b200tfs {
+
+// what a MoveItem / SmallItem does to the bytes it moves
+enum MoveOp : uint32_t {
+  OP_COPY = 0,        // raw little-endian bytes (float64, complex, tensor_content, KEEP_SNAN float32)
+  OP_QUIET_SRC = 1,   // float32 sNaN -> qNaN, 4-byte elements aligned with the SOURCE start (encode)
+  OP_QUIET_DST = 2,   // same, elements aligned with the DESTINATION start (decode)
+  OP_BOOL = 3,        // byte != 0 -> 1 (bool_val written from numpy bool memory)
+  OP_H2F = 4,         // float16  -> float32 (exact), encode-side cast
+  OP_B2F = 5,         // bfloat16 -> float32 (exact), encode-side cast
+  OP_F2H = 6,         // float32 -> float16, round-to-nearest-even, decode-side cast
+  OP_F2B = 7,         // float32 -> bfloat16, round-to-nearest-even, decode-side cast
+  OP_FLAG_BLOB = 0x80000000u  // SmallItem: src is an offset into the plan image, not a pointer
+};
+
+struct MoveItem {     // one large payload, tiled across CTAs
+  const uint8_t* src;
+  uint8_t* dst;
+  uint64_t n_out;     // bytes written
+  uint32_t op;
+  uint32_t first_tile;
+};
+
+struct TileRef { uint32_t item; uint32_t tile; };
+
+struct SmallItem {    // one header fragment or small payload: a warp moves it
+  uint64_t src;       // pointer, or offset into the plan image with OP_FLAG_BLOB
+  uint8_t* dst;
+  uint32_t n_out;
+  uint32_t op;
+};
+
+struct PlanHeader {
+  uint32_t n_items, n_tiles, n_small, uniform_tpi;  // uniform_tpi: every item has this many tiles (no TileRef table)
+  uint32_t vec_per_tile;                            // 16-byte vectors of destination per tile
+  uint32_t off_items, off_tiles, off_small;         // byte offsets inside the plan image
+};
+
+constexpr uint32_t kInlinePlanBytes = 3840;  // fits the classic 4 KB kernel-parameter window
+struct InlinePlan { uint8_t bytes[kInlinePlanBytes]; };
+
+constexpr uint32_t kMoveThreads = 256;      // threads per CTA of move_kernel
+constexpr uint32_t kSmallMax = 2048;        // payloads up to this many bytes take the warp path
+
+// ---- packed-varint jobs ------------------------------------------------------------------------
+constexpr uint32_t kVarThreads = 256;
+constexpr uint32_t kVarPerThread = 8;
+constexpr uint32_t kVarTileElems = kVarThreads * kVarPerThread;  // elements per encode tile
+constexpr uint32_t kVarTileBytes = kVarThreads * 16;             // wire bytes per decode tile
+constexpr int32_t kVarFlagHalfAsValue = 1;  // decode half_val ints as VALUES (the reference's DT_HALF quirk)
+
+struct VarSeg {       // a contiguous run of one job: the whole tensor (encode) or one wire chunk (decode)
+  const uint8_t* src;
+  uint64_t n;         // elements (encode) or bytes (decode)
+  uint32_t job;
+  uint32_t first_tile;
+};
+
+struct VarJobDev {
+  uint8_t* dst;       // encode: first payload byte on the wire; decode: first element of the tensor
+  uint64_t n_elems;
+  int32_t dtype;      // DT_* of the tensor in memory
+  uint32_t elem_size;
+  uint32_t is_signed;
+  int32_t flags;
+  uint32_t first_tile;
+  uint32_t n_tiles;
+};
+
+}  // namespace b200tfs

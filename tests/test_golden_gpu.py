@@ -1,0 +1,112 @@
+"""GPU parity against the golden vectors the unmodified reference produced (tests/golden/*.json).
+
+Every comparison is bit-exact: encoded wire bytes == the reference's SerializeToString output,
+decoded arrays == the reference's tensor_proto_to_ndarray output (or the same exception type).
+"""
+import hashlib
+
+import numpy as np
+import pytest
+from google.protobuf.message import DecodeError
+
+import golden_util as G
+
+pytestmark = pytest.mark.gpu
+
+ENC = G.load("encode.json")
+REQ = G.load("requests.json")
+DEC = G.load("decode.json")
+
+
+@pytest.mark.parametrize("name", [k for k in ENC if not k.startswith("_")])
+def test_encode_tensor_proto(codec, name):
+    case = ENC[name]
+    x = G.apply_transform(G.make_array(case["input"]), case.get("transform"))
+    wire = codec.encode_tensor_protos([x])[0]
+    G.check_wire(wire, case["wire"], name)
+
+
+def test_encode_refused_dtypes(codec):
+    """bytes_/object_/datetime64 raise ValueError like DataType() does; float16/complex, which the
+    reference cannot encode (TypeError), follow TF's convention here instead."""
+    refused = ENC["_refused"]
+    for label, arr in (("bytes_", np.array([b"ab"])), ("object_", np.array([None], dtype=object)),
+                       ("datetime64", np.array(["2020-01-01"], dtype="datetime64[D]"))):
+        assert refused[label] == "ValueError"
+        with pytest.raises(ValueError):
+            codec.encode_tensor_protos([arr])
+    # KAT-8 (TF convention, equals vendored tensor_util_test.py:224-259 goldens)
+    assert codec.encode_tensor_protos([np.array([10, 20], dtype=np.float16)])[0].hex() == "08131204120208026a06809201809a01"
+    import ml_dtypes
+    assert codec.encode_tensor_protos([np.array([10, 20], dtype=ml_dtypes.bfloat16)])[0].hex() == "080e1204120208026a06a08201a08301"
+    assert codec.encode_tensor_protos([np.array([10, 20, 30], dtype=np.float32)], tensor_content=True)[0].hex() == \
+        "0801120412020803220c000020410000a0410000f041"
+
+
+@pytest.mark.parametrize("name", list(REQ))
+def test_encode_predict_request(codec, name):
+    case = REQ[name]
+    inputs = [(k, G.make_array(r)) for k, r in case["inputs"]]
+    wd = "DT_FLOAT" if case.get("wire_dtype") == "DT_FLOAT" else None
+    wire = codec.encode_predict_requests([(case["model_name"], case["model_version"], inputs)], wire_dtype=wd)[0]
+    G.check_wire(wire, case["wire"], name)
+
+
+def test_encode_request_batch_matches_singles(codec):
+    names = ["kat2_c1", "no_version", "mixed_dtypes", "c3_req7", "order_quirk", "no_inputs"]
+    batch = [(REQ[n]["model_name"], REQ[n]["model_version"], [(k, G.make_array(r)) for k, r in REQ[n]["inputs"]]) for n in names]
+    wires = codec.encode_predict_requests(batch)
+    for n, w in zip(names, wires):
+        G.check_wire(w, REQ[n]["wire"], n)
+
+
+@pytest.mark.parametrize("name", list(DEC))
+def test_decode_predict_response(codec, name):
+    rec = DEC[name]
+    wire = G.decode_case_wire(name, rec)
+    if "parse_raises" in rec:
+        with pytest.raises(DecodeError):
+            codec.decode_predict_response(wire, strict=True)
+        return
+    expected = rec["outputs"]
+    raising = {k: v for k, v in expected.items() if "raises" in v}
+    if raising:
+        # the reference decodes output by output; here one call decodes all, so check each on its own
+        for k, v in raising.items():
+            exc = {"ValueError": ValueError, "KeyError": KeyError, "TypeError": TypeError, "OverflowError": OverflowError,
+                   "UnicodeDecodeError": UnicodeDecodeError}[v["raises"]]
+            with pytest.raises(exc):
+                codec.decode_predict_response(wire, strict=True)
+        return
+    outs, spec = codec.decode_predict_response(wire, strict=True)
+    assert set(outs) == set(expected)
+    for k, v in expected.items():
+        got = outs[k]
+        if v["dtype"] == "str":
+            assert got.dtype.kind == "U" and list(got.shape) == v["shape"] and got.ravel().tolist() == v["strings"]
+            continue
+        assert got.dtype.str == v["dtype"], (k, got.dtype)
+        assert list(got.shape) == v["shape"]
+        if "data" in v:
+            assert got.tobytes().hex() == v["data"], k
+        else:
+            assert hashlib.sha256(got.tobytes()).hexdigest() == v["sha256"], k
+    ms = rec["model_spec"]
+    assert (spec.name, spec.version, spec.has_version, spec.version_label, spec.signature_name) == \
+        (ms["name"], ms["version"], ms["has_version"], ms["version_label"], ms["signature_name"])
+
+
+def test_round_trip_all_numeric_dtypes(codec):
+    """encode -> decode is the identity (reference tensors_test.py:111-117), every dtype of the table."""
+    rng = np.random.default_rng(123)
+    for dt in (np.float32, np.float64, np.int8, np.int16, np.int32, np.int64, np.uint8, np.uint16, np.uint32, np.uint64, np.bool_):
+        if dt is np.bool_:
+            x = rng.integers(0, 2, size=(7, 13)).astype(np.bool_)
+        elif np.dtype(dt).kind == "f":
+            x = rng.standard_normal((7, 13)).astype(dt)
+        else:
+            info = np.iinfo(dt)
+            x = rng.integers(info.min, info.max, size=(7, 13), dtype=dt, endpoint=True)
+        wire = codec.encode_tensor_protos([x])[0]
+        back = codec.decode_tensor_protos([wire], strict=True)[0]
+        assert back.dtype == x.dtype and back.shape == x.shape and back.tobytes() == x.tobytes(), dt
