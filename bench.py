@@ -1,0 +1,506 @@
+#!/usr/bin/env python
+"""bench.py - TensorProto encode+decode throughput on B200 (BASELINE.json metric), one JSON line.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--workload c2|c3|c5]
+
+Workload (N=1 default, the config the metric is quoted on): **C2** - one fp32 [1024,1024] tensor per
+step: encode it into a PredictRequest{model_spec{"default",1}, inputs{"x"}} wire buffer AND decode one
+PredictResponse{outputs{"y": fp32[1024,1024]}, model_spec} back to a tensor.  A *step* = that one
+encode + one decode.  ``value`` = tensor payload bytes processed per second (2 x 4 MiB per step),
+inputs already resident in HBM; ``e2e`` = the same through the host-buffer C-ABI entry points, with the
+H2D / D2H copies inside the timed region.  Between steps the buffers rotate through a ring whose
+footprint exceeds the 126 MB L2 (stated in ``config``), so every step reads HBM.
+
+Roofline: the dominant kernel is ``move_kernel`` (one launch per encode, one per decode-unpack);
+algorithmic bytes per launch = 2P + H (read P, write P+H on encode; read P+H, write P on decode;
+P = 4 194 304, H = 47 / 58) - DESIGN.md "Roofline".  Its average launch duration is measured live with
+CUDA events on the launching stream over back-to-back launches of that kernel alone.
+
+Multi-GPU (torchrun, one rank per GPU): independent requests shard across ranks with no data-path
+collective; each rank runs the same per-GPU workload (weak scaling); the only communication is the
+barrier + MAX-reduce of the device-timed region.
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+REPO = os.path.dirname(os.path.abspath(__file__))
+sys.path[:0] = [os.path.join(REPO, "min-tfs-client_b200"), REPO]
+
+L2_BYTES = 126 * 1024 * 1024
+
+
+# ------------------------------------------------------------------------------------------------
+# small wire helpers (bench-local; used to fabricate the response the decode leg consumes and to
+# check results - the oracle is only touched by the cpu_baseline / --impl reference legs)
+# ------------------------------------------------------------------------------------------------
+def _uv(x):
+    out = bytearray()
+    while True:
+        b = x & 0x7F
+        x >>= 7
+        out.append(b | (0x80 if x else 0))
+        if not x:
+            return bytes(out)
+
+
+def _ld(tag, body):
+    return bytes([tag]) + _uv(len(body)) + body
+
+
+def _f32_tensor_header(shape, nbytes):
+    dims = b"".join(_ld(0x12, b"\x08" + _uv(d)) for d in shape)
+    return b"\x08\x01" + _ld(0x12, dims) + b"\x2a" + _uv(nbytes)
+
+
+def response_wire_parts(key, shape, nbytes, model=b"default", version=1, sig=b"serving_default"):
+    """(prefix, suffix) such that prefix + payload + suffix is a canonical PredictResponse."""
+    th = _f32_tensor_header(shape, nbytes)
+    tp_len = len(th) + nbytes
+    entry_len = 1 + len(_uv(len(key))) + len(key) + 1 + len(_uv(tp_len)) + tp_len
+    prefix = b"\x0a" + _uv(entry_len) + _ld(0x0A, key) + b"\x12" + _uv(tp_len) + th
+    spec = _ld(0x0A, model) + _ld(0x12, b"\x08" + _uv(version)) + _ld(0x1A, sig)
+    return prefix, _ld(0x12, spec)
+
+
+def request_wire_parts(key, shape, nbytes, model=b"default", version=1):
+    th = _f32_tensor_header(shape, nbytes)
+    tp_len = len(th) + nbytes
+    entry_len = 1 + len(_uv(len(key))) + len(key) + 1 + len(_uv(tp_len)) + tp_len
+    spec = _ld(0x0A, model) + _ld(0x12, b"\x08" + _uv(version))
+    return _ld(0x0A, spec) + b"\x12" + _uv(entry_len) + _ld(0x0A, key) + b"\x12" + _uv(tp_len) + th
+
+
+# ------------------------------------------------------------------------------------------------
+# clocks
+# ------------------------------------------------------------------------------------------------
+class ClockSampler:
+    FIELDS = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.gpu = str(gpu_index)
+        self.rows = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "--query-gpu=" + self.FIELDS, "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._pump, daemon=True).start()
+        except OSError:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            parts = [p.strip() for p in line.split(",")]
+            if len(parts) >= 9 and parts[0] == self.gpu:
+                self.rows.append((time.time(), parts))
+
+    def stop(self, t0, t1):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        rows = [p for (t, p) in self.rows if t0 <= t <= t1 + 0.1] or [p for (_, p) in self.rows[-3:]]
+        if not rows:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no sample"]}
+        sm = sorted(float(r[1]) for r in rows)
+        reasons = set()
+        for r in rows:
+            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": float(rows[0][2]), "power_w_max": max(float(r[3]) for r in rows),
+                "samples": len(rows), "reasons": sorted(reasons)}
+
+
+# ------------------------------------------------------------------------------------------------
+# distributed plumbing (control plane only)
+# ------------------------------------------------------------------------------------------------
+class World:
+    def __init__(self):
+        self.rank = int(os.environ.get("RANK", "0"))
+        self.local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+        self.size = int(os.environ.get("WORLD_SIZE", "1"))
+        self.dist = None
+        self.torch = None
+        if self.size > 1:
+            import torch
+            import torch.distributed as dist
+
+            self.torch = torch
+            torch.cuda.set_device(self.local_rank)
+            dist.init_process_group("nccl", device_id=torch.device("cuda", self.local_rank))
+            self.dist = dist
+
+    def barrier(self):
+        if self.dist:
+            self.dist.barrier()
+            self.torch.cuda.synchronize()
+
+    def max(self, x):
+        if not self.dist:
+            return x
+        t = self.torch.tensor([x], dtype=self.torch.float64, device="cuda")
+        self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def sum(self, x):
+        if not self.dist:
+            return x
+        t = self.torch.tensor([x], dtype=self.torch.float64, device="cuda")
+        self.dist.all_reduce(t, op=self.dist.ReduceOp.SUM)
+        return float(t.item())
+
+    def close(self):
+        if self.dist:
+            self.dist.destroy_process_group()
+
+
+# ------------------------------------------------------------------------------------------------
+# the GPU arm
+# ------------------------------------------------------------------------------------------------
+class C2Bench:
+    """fp32 [1024,1024]: ring of device-resident tensors / request arenas / response wires / outputs."""
+
+    SHAPE = (1024, 1024)
+
+    def __init__(self, device, ring):
+        from min_tfs_client import _native as N
+
+        self.N = N
+        self.lib = N.load()
+        ctx = C.c_void_p()
+        N.check(self.lib.b200tfs_create(device, C.byref(ctx)))
+        self.ctx = ctx
+        self.ring = ring
+        self.P = int(np.prod(self.SHAPE)) * 4
+        self.host_x = [np.random.default_rng(i).standard_normal(self.SHAPE, dtype=np.float32) for i in range(min(ring, 4))]
+        self.resp_prefix, self.resp_suffix = response_wire_parts(b"y", self.SHAPE, self.P)
+        self.req_header = request_wire_parts(b"x", self.SHAPE, self.P)
+        self.resp_len = len(self.resp_prefix) + self.P + len(self.resp_suffix)
+        self.H_req, self.H_resp = len(self.req_header), len(self.resp_prefix) + len(self.resp_suffix)
+        # request struct (device pointer patched per slot)
+        self.dims = (C.c_int64 * 2)(*self.SHAPE)
+        self.tensor = N.Tensor(data=None, src_dtype=1, wire_dtype=1, rank=2, flags=0, dims=self.dims, key=b"x", key_len=1, packed_len=0)
+        self.tensors = (N.Tensor * 1)(self.tensor)
+        self.request = N.Request(model_name=b"default", model_name_len=7, has_version=1, order=N.ORDER_UPB, version=1, n_inputs=1,
+                                 reserved=0, inputs=self.tensors)
+        self.requests = (N.Request * 1)(self.request)
+        need = C.c_uint64(0)
+        self.tensors[0].data = 256  # any non-NULL pointer for sizing
+        N.check(self.lib.b200tfs_request_arena_size(1, self.requests, C.byref(need)))
+        self.arena_cap = int(need.value)
+        self.src, self.arena, self.resp, self.dst = [], [], [], []
+        resp_host = []
+        for i in range(len(self.host_x)):
+            resp_host.append(np.frombuffer(self.resp_prefix + self.host_x[i].tobytes() + self.resp_suffix, dtype=np.uint8))
+        for i in range(ring):
+            self.src.append(self._malloc(self.P))
+            self.arena.append(self._malloc(self.arena_cap))
+            self.resp.append(self._malloc(self.resp_len + 64))
+            self.dst.append(self._malloc(self.P))
+            hx = self.host_x[i % len(self.host_x)]
+            N.check(self.lib.b200tfs_memcpy_h2d(self.ctx, self.src[i], hx.ctypes.data, self.P))
+            rh = resp_host[i % len(resp_host)]
+            N.check(self.lib.b200tfs_memcpy_h2d(self.ctx, self.resp[i], rh.ctypes.data, self.resp_len))
+            N.check(self.lib.b200tfs_memset(self.ctx, self.arena[i], 0, self.arena_cap))
+            N.check(self.lib.b200tfs_memset(self.ctx, self.dst[i], 0, self.P))
+        self.sync()
+        self.rec_off = (C.c_uint64 * 1)()
+        self.rec_len = (C.c_uint64 * 1)()
+        self.p_off = (C.c_uint64 * 1)(0)
+        self.p_len = (C.c_uint64 * 1)(self.resp_len)
+        self.outs = (N.Output * 4)()
+        self.n_outs = (C.c_int32 * 1)()
+        self.specs = (N.ModelSpec * 1)()
+        self.status = (C.c_int32 * 1)()
+        self.dst_ptr = (C.c_void_p * 1)()
+        self.slot = 0
+        # pinned host buffers for the e2e leg
+        self.pin_x = N.PinnedBuffer(self.P)
+        self.pin_wire = N.PinnedBuffer(self.arena_cap)
+        self.pin_resp = N.PinnedBuffer(self.resp_len)
+        self.pin_out = N.PinnedBuffer(self.P)
+        self.pin_x.array[:] = self.host_x[0].view(np.uint8).reshape(-1)
+        self.pin_resp.array[:] = resp_host[0]
+
+    def _malloc(self, nbytes):
+        p = C.c_void_p()
+        self.N.check(self.lib.b200tfs_malloc(self.ctx, nbytes, C.byref(p)))
+        return p.value
+
+    def sync(self):
+        self.N.check(self.lib.b200tfs_sync(self.ctx))
+
+    def footprint(self):
+        return self.ring * (self.P * 2 + self.arena_cap + self.resp_len)
+
+    # ---- one step, device-resident ------------------------------------------------------------
+    def encode(self, i):
+        self.tensors[0].data = self.src[i]
+        self.N.check(self.lib.b200tfs_encode_requests(self.ctx, 1, self.requests, self.arena[i], self.arena_cap, self.rec_off, self.rec_len))
+
+    def decode(self, i):
+        lib, N = self.lib, self.N
+        N.check(lib.b200tfs_parse_responses(self.ctx, self.resp[i], 1, self.p_off, self.p_len, 4, self.outs, self.n_outs, self.specs, self.status))
+        self.dst_ptr[0] = self.dst[i]
+        N.check(lib.b200tfs_unpack_outputs(self.ctx, self.resp[i], 1, self.outs, self.dst_ptr, None, None))
+
+    def step(self):
+        i = self.slot
+        self.slot = (i + 1) % self.ring
+        self.encode(i)
+        self.decode(i)
+
+    # ---- one step through the host-buffer entry points (e2e) -----------------------------------
+    def step_e2e(self):
+        lib, N = self.lib, self.N
+        self.tensors[0].data = self.pin_x.ptr
+        N.check(lib.b200tfs_encode_requests_host(self.ctx, 1, self.requests, self.pin_wire.ptr, self.arena_cap, self.rec_off, self.rec_len))
+        N.check(lib.b200tfs_parse_responses_host(self.ctx, self.pin_resp.ptr, 1, self.p_off, self.p_len, 4, self.outs, self.n_outs, self.specs,
+                                                 self.status))
+        self.dst_ptr[0] = self.pin_out.ptr
+        N.check(lib.b200tfs_unpack_outputs_host(self.ctx, 1, self.outs, self.dst_ptr, None, None))
+
+    def launches(self):
+        n = C.c_uint64(0)
+        self.N.check(self.lib.b200tfs_kernel_launches(self.ctx, C.byref(n)))
+        return int(n.value)
+
+    # ---- timing helpers --------------------------------------------------------------------------
+    def timed(self, fn, steps):
+        lib, N = self.lib, self.N
+        e0, e1 = C.c_void_p(), C.c_void_p()
+        N.check(lib.b200tfs_event_create(C.byref(e0)))
+        N.check(lib.b200tfs_event_create(C.byref(e1)))
+        self.sync()
+        N.check(lib.b200tfs_event_record(self.ctx, e0))
+        for _ in range(steps):
+            fn()
+        N.check(lib.b200tfs_event_record(self.ctx, e1))
+        N.check(lib.b200tfs_event_sync(e1))
+        self.sync()
+        ms = C.c_float(0)
+        N.check(lib.b200tfs_event_elapsed_ms(e0, e1, C.byref(ms)))
+        lib.b200tfs_event_destroy(e0)
+        lib.b200tfs_event_destroy(e1)
+        return float(ms.value)
+
+    def verify(self):
+        """Bit-exact check of the last ring slot's products against bytes built here from the inputs."""
+        lib, N = self.lib, self.N
+        i = 0
+        self.encode(i)
+        self.decode(i)
+        self.sync()
+        wire = np.empty(int(self.rec_len[0]), dtype=np.uint8)
+        N.check(lib.b200tfs_memcpy_d2h(self.ctx, wire.ctypes.data, self.arena[i] + int(self.rec_off[0]), wire.size))
+        out = np.empty(self.SHAPE, dtype=np.float32)
+        N.check(lib.b200tfs_memcpy_d2h(self.ctx, out.ctypes.data, self.dst[i], self.P))
+        self.sync()
+        expect = self.req_header + self.host_x[0].tobytes()
+        assert wire.tobytes() == expect, "encoded request differs from the expected wire bytes"
+        assert out.tobytes() == self.host_x[0].tobytes(), "decoded tensor differs from the payload"
+        assert self.status[0] == 0 and self.n_outs[0] == 1
+        return True
+
+    def verify_e2e(self):
+        self.step_e2e()
+        n = int(self.rec_len[0])
+        o = int(self.rec_off[0])
+        assert self.pin_wire.array[o:o + n].tobytes() == self.req_header + self.host_x[0].tobytes()
+        assert self.pin_out.array.tobytes() == self.host_x[0].tobytes()
+        return True
+
+
+def peaks():
+    path = os.path.join(REPO, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as fh:
+            return float(json.load(fh)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+# ------------------------------------------------------------------------------------------------
+# CPU legs (the only place oracle/ is touched)
+# ------------------------------------------------------------------------------------------------
+def _cpu_roundtrip(seed):
+    """One C2 unit on one core through the reference port: encode request + decode response."""
+    from oracle import ref_port
+
+    x = np.random.default_rng(seed).standard_normal((1024, 1024), dtype=np.float32)
+    prefix, suffix = response_wire_parts(b"y", (1024, 1024), 4194304)
+    resp = prefix + x.tobytes() + suffix  # fabricating the response is not part of the measured path (and is cheap)
+    t0 = time.perf_counter()
+    wire = ref_port.encode_predict_request("default", 1, [("x", x)])
+    out = ref_port.decode_predict_response(resp)["y"]
+    t1 = time.perf_counter()
+    assert out.tobytes() == x.tobytes() and len(wire) == 4194351
+    return t1 - t0
+
+
+def cpu_baseline_port(units=2):
+    """Scalar (1 core) timing of the reference port on `units` C2 tensors."""
+    t = sum(_cpu_roundtrip(s) for s in range(units))
+    payload = units * 2 * 4194304
+    return {"value": payload / t / 1e9, "unit": "GB/s", "cores": 1, "kind": "port",
+            "sample": f"{units} x fp32[1024,1024] encode+decode through oracle/ref_port.py (per-element Python, protobuf upb), {t:.2f} s"}
+
+
+def cpu_c_oracle(units=8):
+    from oracle import wire_oracle
+
+    x = np.random.default_rng(0).standard_normal((1024, 1024), dtype=np.float32)
+    resp = wire_oracle.build_predict_response([("y", x)])
+    t0 = time.perf_counter()
+    for _ in range(units):
+        wire_oracle.encode_predict_request("default", 1, [("x", x)])
+        wire_oracle.decode_predict_response(resp)
+    t = time.perf_counter() - t0
+    return {"value": units * 2 * 4194304 / t / 1e9, "unit": "GB/s", "cores": 1, "kind": "port (plain C, oracle/wire_oracle.c)"}
+
+
+def run_reference(args, world):
+    """--impl reference: the reference's CPU implementation (Python port over protobuf) on all host cores."""
+    if world.rank != 0:
+        return
+    import multiprocessing as mp
+
+    cores = len(os.sched_getaffinity(0))
+    per_step = cores  # one C2 unit per core per step
+    steps, warmup = max(1, min(args.steps, 5)), max(0, min(args.warmup, 1))
+    with mp.get_context("fork").Pool(cores) as pool:
+        for _ in range(warmup):
+            pool.map(_cpu_roundtrip, range(per_step))
+        t0 = time.perf_counter()
+        for s in range(steps):
+            pool.map(_cpu_roundtrip, range(per_step))
+        wall = time.perf_counter() - t0
+    value = steps * per_step * 2 * 4194304 / wall / 1e9
+    line = {
+        "impl": "reference", "metric": "TensorProto encode+decode GB/s", "value": value, "unit": "GB/s", "n_gpus": args.gpus,
+        "steps": steps, "warmup": warmup, "ms_per_step": wall / steps * 1e3, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+        "config": {"workload": "C2 fp32[1024,1024] single-tensor PredictRequest encode + PredictResponse decode",
+                   "step": f"{per_step} tensors per step, one per host core (bounded sample of the same workload)"},
+        "cpu_baseline": {"value": value, "unit": "GB/s", "cores": cores, "kind": "port",
+                         "sample": f"{steps} steps x {per_step} tensors, multiprocessing pool over {cores} cores, oracle/ref_port.py"},
+        "e2e": {"value": value, "unit": "GB/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line))
+
+
+# ------------------------------------------------------------------------------------------------
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20000)
+    ap.add_argument("--warmup", type=int, default=200)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--ring", type=int, default=48)
+    ap.add_argument("--e2e-steps", type=int, default=200)
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    args = ap.parse_args()
+    world = World()
+    if args.impl == "reference":
+        run_reference(args, world)
+        world.close()
+        return
+    warmup = max(args.warmup, 3)
+    bench = C2Bench(world.local_rank, args.ring)
+    assert bench.footprint() > 2 * L2_BYTES, "ring must exceed L2"
+    bench.verify()
+    for _ in range(warmup):
+        bench.step()
+    bench.sync()
+    launches0 = bench.launches()
+    sampler = ClockSampler(world.local_rank)
+    sampler.start()
+    time.sleep(0.25)
+    world.barrier()
+    t0 = time.time()
+    ms = bench.timed(bench.step, args.steps)
+    t1 = time.time()
+    world.barrier()
+    clocks = sampler.stop(t0, t1)
+    launches = bench.launches() - launches0
+    ms_max = world.max(ms)
+    payload_per_step = 2 * bench.P
+    total_payload = world.sum(float(payload_per_step * args.steps))
+    value = total_payload / (ms_max * 1e-3) / 1e9
+
+    # roofline pass: move_kernel alone, back to back on the launching stream (encode launches, then
+    # decode-unpack launches over an already parsed table)
+    reps = min(max(args.steps, 200), 2000)
+    ring = bench.ring
+
+    def enc_only():
+        bench.encode(enc_only.i % ring)
+        enc_only.i += 1
+    enc_only.i = 0
+    bench.timed(enc_only, 50)
+    enc_ms = bench.timed(enc_only, reps)
+    bench.decode(0)
+    bench.sync()
+
+    def unpack_only():
+        bench.dst_ptr[0] = bench.dst[unpack_only.i % ring]
+        bench.N.check(bench.lib.b200tfs_unpack_outputs(bench.ctx, bench.resp[unpack_only.i % ring], 1, bench.outs, bench.dst_ptr, None, None))
+        unpack_only.i += 1
+    unpack_only.i = 0
+    bench.timed(unpack_only, 50)
+    dec_ms = bench.timed(unpack_only, reps)
+    peak, peak_src = peaks()
+    enc_bytes = 2 * bench.P + bench.H_req
+    dec_bytes = 2 * bench.P + bench.H_resp
+    avg_us = (enc_ms + dec_ms) / (2 * reps) * 1e3
+    achieved = (enc_bytes + dec_bytes) / 2 / (avg_us * 1e-6) / 1e9
+    roofline = {"bound": "hbm", "kernel": "move_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                "traffic": None, "peak_source": peak_src, "algorithmic_bytes_per_launch": (enc_bytes + dec_bytes) / 2,
+                "avg_launch_us": avg_us, "encode_launch_us": enc_ms / reps * 1e3, "decode_launch_us": dec_ms / reps * 1e3,
+                "how": f"{reps} back-to-back launches each, CUDA events on the launching stream, ring > L2"}
+
+    # e2e: host buffers in, host buffers out, copies inside the timed region
+    bench.verify_e2e()
+    for _ in range(5):
+        bench.step_e2e()
+    e2e_steps = max(10, min(args.e2e_steps, args.steps))
+    world.barrier()
+    e2e_ms = world.max(bench.timed(bench.step_e2e, e2e_steps))
+    e2e_value = world.sum(float(payload_per_step * e2e_steps)) / (e2e_ms * 1e-3) / 1e9
+    e2e = {"value": e2e_value, "unit": "GB/s", "h2d_bytes_per_step": bench.P + bench.resp_len, "d2h_bytes_per_step": int(bench.rec_len[0]) + bench.P,
+           "ms_per_step": e2e_ms / e2e_steps, "steps": e2e_steps,
+           "how": "b200tfs_encode_requests_host + b200tfs_parse_responses_host + b200tfs_unpack_outputs_host on pinned host buffers"}
+
+    if world.rank == 0:
+        line = {
+            "metric": "TensorProto encode+decode GB/s", "value": value, "unit": "GB/s", "n_gpus": world.size, "steps": args.steps,
+            "warmup": warmup, "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "u8", "data": "synthetic",
+            "config": {"workload": "C2 fp32[1024,1024] single-tensor PredictRequest encode + PredictResponse decode (BASELINE.json configs[1])",
+                       "payload_bytes_per_step": payload_per_step, "ring_slots": bench.ring, "ring_bytes": bench.footprint(),
+                       "l2": f"inputs rotate through a ring of {bench.ring} slots = {bench.footprint() >> 20} MiB > 126 MiB L2",
+                       "wire_mode": "typed (float_val, sNaN-quieting on: bit-exact vs reference)", "sharding": "independent requests per GPU, no collective"},
+            "roofline": roofline, "e2e": e2e, "gpu_launches": launches, "clocks": clocks,
+        }
+        if world.size == 1 and not args.no_cpu:
+            cb = cpu_baseline_port(2)
+            cb["c_oracle_1core_gbs"] = cpu_c_oracle(8)["value"]
+            line["cpu_baseline"] = cb
+        print(json.dumps(line))
+    world.close()
+
+
+if __name__ == "__main__":
+    main()

@@ -147,6 +147,7 @@ typedef struct b200tfs_output {
   uint64_t n_elems;     /* prod(dims)                                                           */
   uint64_t dst_bytes;   /* n_elems * element size of `dtype` in memory                          */
   uint64_t n_strings;   /* string_val occurrences (strings are unpacked on the host)            */
+  uint64_t dst_off;     /* b200tfs_decode_responses: where the values were written, from dst_dev */
   int32_t status;       /* B200TFS_OK, or the error tensor_proto_to_ndarray raises for it       */
   int32_t reserved;
 } b200tfs_output;
@@ -253,6 +254,31 @@ int b200tfs_parse_tensor_protos(b200tfs_ctx* ctx, const void* arena_dev, int32_t
  * mismatch, integer out of range).  Async when status is NULL.                                    */
 int b200tfs_unpack_outputs(b200tfs_ctx* ctx, const void* arena_dev, int32_t m, const b200tfs_output* outs,
                            void* const* dst_dev, const int32_t* dst_dtype, int32_t* status);
+
+/* Single-launch decode for the steady-state path: one kernel walks the tags AND moves the values,
+ * with no host round trip.  Record i's fixed-width outputs (float_val / double_val / complex) are
+ * written to dst_dev + i*dst_stride, each output 256-byte aligned in table order (b200tfs_output.dst_off);
+ * outputs with varint or string values are tabulated only - finish those with b200tfs_unpack_outputs.
+ * At most B200TFS_FUSED_MAX_OUTPUTS outputs per record.  Asynchronous and CUDA-graph capturable;
+ * collect the table afterwards with b200tfs_decode_results (which synchronises).                  */
+#define B200TFS_FUSED_MAX_OUTPUTS 8
+int b200tfs_decode_responses(b200tfs_ctx* ctx, const void* arena_dev, int32_t n, const uint64_t* rec_off,
+                             const uint64_t* rec_len, void* dst_dev, uint64_t dst_stride);
+/* outs has n*B200TFS_FUSED_MAX_OUTPUTS slots; any pointer may be NULL.                             */
+int b200tfs_decode_results(b200tfs_ctx* ctx, int32_t n, b200tfs_output* outs, int32_t* n_outs,
+                           b200tfs_model_spec* specs, int32_t* rec_status);
+
+/* ---- CUDA graphs: record a fixed sequence of encode / decode calls once, replay it per request ---
+ * Between capture_begin and capture_end the asynchronous entry points (b200tfs_encode_requests,
+ * b200tfs_encode_tensor_protos, b200tfs_decode_responses, b200tfs_memcpy_*) only record work; calls
+ * that must synchronise or allocate fail with B200TFS_E_ARG.  Run the same calls once before capturing
+ * so every scratch buffer has its final size.                                                      */
+int b200tfs_capture_begin(b200tfs_ctx* ctx);
+int b200tfs_capture_end(b200tfs_ctx* ctx, void** graph_exec);
+int b200tfs_graph_launch(b200tfs_ctx* ctx, void* graph_exec);
+int b200tfs_graph_destroy(void* graph_exec);
+/* make every later call on ctx wait for an event recorded on another context's stream            */
+int b200tfs_wait_event(b200tfs_ctx* ctx, void* ev);
 
 /* ---- host-buffer convenience (what a client binds; H2D / D2H happen inside) -------------------- */
 /* tensors[].data are HOST pointers (pinned or pageable).  Encodes n requests and leaves the wire

@@ -76,10 +76,15 @@ struct b200tfs_ctx {
   Growable arena_dev;     // *_host entry points: wire arena (encode) / unpacked tensors (decode)
   uint64_t launches = 0;
   uint32_t tile_bytes_override = 0;
+  bool capturing = false;   // between b200tfs_capture_begin / _end: no syncs, no allocations
+  Growable fused_dev;       // decode_fused tables (device) ...
+  Growable fused_host;      // ... and their pinned mirror
+  int32_t fused_n = 0;      // records of the last b200tfs_decode_responses
 };
 
 static int grow_dev(b200tfs_ctx* c, Growable& g, uint64_t need) {
   if (need <= g.cap) return B200TFS_OK;
+  if (c->capturing) return fail(B200TFS_E_ARG, "scratch buffer would have to grow during graph capture: run the call once before capturing");
   uint64_t cap = std::max<uint64_t>(need, g.cap * 2);
   cap = (cap + 0xFFFFull) & ~0xFFFFull;
   CU(cudaStreamSynchronize(c->stream));
@@ -91,6 +96,7 @@ static int grow_dev(b200tfs_ctx* c, Growable& g, uint64_t need) {
 }
 static int grow_host(b200tfs_ctx* c, Growable& g, uint64_t need) {
   if (need <= g.cap) return B200TFS_OK;
+  if (c->capturing) return fail(B200TFS_E_ARG, "scratch buffer would have to grow during graph capture: run the call once before capturing");
   uint64_t cap = std::max<uint64_t>(need, g.cap * 2);
   cap = (cap + 0xFFFull) & ~0xFFFull;
   CU(cudaStreamSynchronize(c->stream));
@@ -103,6 +109,7 @@ static int grow_host(b200tfs_ctx* c, Growable& g, uint64_t need) {
 
 // claim an upload slot with room for `bytes` in both images
 static int claim_slot(b200tfs_ctx* c, uint64_t bytes, Slot** out) {
+  if (c->capturing) return fail(B200TFS_E_ARG, "this call needs a plan upload, which cannot be captured into a graph (batch too large for the inline plan)");
   Slot& s = c->slots[c->next_slot];
   c->next_slot = (c->next_slot + 1) % kSlots;
   if (s.pending) { CU(cudaEventSynchronize(s.done)); s.pending = false; }
@@ -160,6 +167,8 @@ int b200tfs_destroy(b200tfs_ctx* c) {
     if (s.dev.p) cudaFree(s.dev.p);
     if (s.done) cudaEventDestroy(s.done);
   }
+  if (c->fused_dev.p) cudaFree(c->fused_dev.p);
+  if (c->fused_host.p) cudaFreeHost(c->fused_host.p);
   if (c->scratch_dev.p) cudaFree(c->scratch_dev.p);
   if (c->scratch_host.p) cudaFreeHost(c->scratch_host.p);
   if (c->stage_dev.p) cudaFree(c->stage_dev.p);
@@ -171,6 +180,7 @@ int b200tfs_destroy(b200tfs_ctx* c) {
 
 int b200tfs_sync(b200tfs_ctx* c) {
   if (!c) return fail(B200TFS_E_ARG, "ctx is NULL");
+  if (c->capturing) return fail(B200TFS_E_ARG, "cannot synchronise during graph capture");
   CU(cudaStreamSynchronize(c->stream));
   return B200TFS_OK;
 }
@@ -400,10 +410,11 @@ struct PlanBuilder {
 uint32_t pick_vec_per_tile(const b200tfs_ctx* c, uint64_t large_bytes) {
   uint64_t tile = c->tile_bytes_override;
   if (!tile) {
-    uint64_t target_tiles = (uint64_t)c->sm_count * 4;
+    // one batch per thread (16 KB per CTA) until the machine is full, then fatter tiles
+    uint64_t target_tiles = (uint64_t)c->sm_count * 8;
     tile = (large_bytes + target_tiles - 1) / target_tiles;
-    tile = (tile + 4095) & ~4095ull;
-    tile = std::min<uint64_t>(std::max<uint64_t>(tile, 4096), 65536);
+    tile = (tile + 16383) & ~16383ull;
+    tile = std::min<uint64_t>(std::max<uint64_t>(tile, 16384), 65536);
   }
   tile = std::max<uint64_t>(tile & ~31ull, 32);
   return (uint32_t)(tile / 16);
@@ -419,10 +430,9 @@ int launch_plan(b200tfs_ctx* c, PlanBuilder& pb) {
   uint32_t uniform = 0;
   bool is_uniform = !pb.items.empty();
   for (auto& it : pb.items) {
-    uint64_t vecs = (it.n_out + 15) >> 4;
-    uint64_t t = std::max<uint64_t>(1, (vecs + vpt - 1) / vpt);
+    uint64_t t = tiles_for_host(it.n_out, vpt);
     if (n_tiles + t > 0x7FFFFFFFull) return fail(B200TFS_E_TOOBIG, "batch needs more than 2^31 tiles");
-    it.first_tile = (uint32_t)n_tiles;
+    it.n_tiles = (uint32_t)t;
     if (&it == &pb.items[0]) uniform = (uint32_t)t; else if (t != uniform) is_uniform = false;
     n_tiles += t;
   }
@@ -457,11 +467,9 @@ int launch_plan(b200tfs_ctx* c, PlanBuilder& pb) {
   if (!pb.items.empty()) memcpy(img + ph.off_items, pb.items.data(), pb.items.size() * sizeof(MoveItem));
   if (!uniform && n_tiles) {
     TileRef* tr = (TileRef*)(img + ph.off_tiles);
-    for (uint32_t i = 0; i < pb.items.size(); ++i) {
-      uint32_t t0 = pb.items[i].first_tile;
-      uint32_t t1 = (i + 1 < pb.items.size()) ? pb.items[i + 1].first_tile : (uint32_t)n_tiles;
-      for (uint32_t t = t0; t < t1; ++t) tr[t] = TileRef{i, t - t0};
-    }
+    uint32_t g = 0;
+    for (uint32_t i = 0; i < pb.items.size(); ++i)
+      for (uint32_t t = 0; t < pb.items[i].n_tiles; ++t) tr[g++] = TileRef{i, t};
   }
   SmallItem* sm = (SmallItem*)(img + ph.off_small);
   for (size_t i = 0; i < pb.smalls.size(); ++i) {
@@ -875,6 +883,140 @@ extern "C" int b200tfs_unpack_outputs(b200tfs_ctx* c, const void* arena_dev, int
   if (status) CU(cudaStreamSynchronize(c->stream));
   return B200TFS_OK;
 }
+
+// ------------------------------------------------------------------------------------------------
+// fused single-launch decode + CUDA graph capture
+// ------------------------------------------------------------------------------------------------
+namespace {
+struct FusedLayout { uint64_t outs, nouts, specs, status, total; };
+FusedLayout fused_layout(int32_t n) {
+  FusedLayout L;
+  L.outs = 0;
+  L.nouts = L.outs + sizeof(b200tfs_output) * (uint64_t)n * kFusedMaxOutputs;
+  L.specs = (L.nouts + 4ull * n + 15) & ~15ull;
+  L.status = L.specs + sizeof(b200tfs_model_spec) * (uint64_t)n;
+  L.total = (L.status + 4ull * n + 15) & ~15ull;
+  return L;
+}
+}  // namespace
+
+extern "C" {
+
+int b200tfs_decode_responses(b200tfs_ctx* c, const void* arena_dev, int32_t n, const uint64_t* rec_off, const uint64_t* rec_len,
+                             void* dst_dev, uint64_t dst_stride) {
+  if (!c || n < 0 || (n && (!arena_dev || !rec_off || !rec_len || !dst_dev))) return fail(B200TFS_E_ARG, "bad arguments");
+  if (n == 0) return B200TFS_OK;
+  if (dst_stride & 255) return fail(B200TFS_E_ARG, "dst_stride must be a multiple of 256");
+  if (!c->capturing) CU(cudaSetDevice(c->device));
+  uint64_t wire_total = 0;
+  for (int i = 0; i < n; ++i) wire_total += rec_len[i];
+  const uint32_t vpt = pick_vec_per_tile(c, wire_total);
+  const uint64_t tile_bytes = 16ull * vpt;
+  FusedLayout L = fused_layout(n);
+  int rc;
+  if ((rc = grow_dev(c, c->fused_dev, L.total))) return rc;
+  if ((rc = grow_host(c, c->fused_host, L.total))) return rc;
+  FusedParams fp{};
+  fp.w = (const uint8_t*)arena_dev; fp.dst = (uint8_t*)dst_dev; fp.dst_stride = dst_stride; fp.n = n; fp.vpt = vpt;
+  uint8_t* d = (uint8_t*)c->fused_dev.p;
+  fp.outs = (b200tfs_output*)(d + L.outs); fp.n_outs = (int32_t*)(d + L.nouts);
+  fp.specs = (b200tfs_model_spec*)(d + L.specs); fp.status = (int32_t*)(d + L.status);
+  uint64_t grid = 0;
+  if (n <= kFusedInlineRecs) {
+    for (int i = 0; i < n; ++i) {
+      fp.inl.off[i] = rec_off[i]; fp.inl.len[i] = rec_len[i]; fp.inl.tile_start[i] = (uint32_t)grid;
+      grid += (rec_len[i] + tile_bytes - 1) / tile_bytes + kFusedSlackTiles;
+    }
+    fp.inl.tile_start[n] = (uint32_t)grid;
+  } else {
+    // tables: cta_rec[grid] | tile_start[n+1] | rec_off[n] | rec_len[n]
+    std::vector<uint32_t> ts(n + 1);
+    for (int i = 0; i < n; ++i) { ts[i] = (uint32_t)grid; grid += (rec_len[i] + tile_bytes - 1) / tile_bytes + kFusedSlackTiles; }
+    ts[n] = (uint32_t)grid;
+    if (grid > 0x7FFFFFFFull) return fail(B200TFS_E_TOOBIG, "batch needs more than 2^31 tiles");
+    const uint64_t o_ts = (grid * 4 + 15) & ~15ull, o_off = (o_ts + 4ull * (n + 1) + 15) & ~15ull, o_len = o_off + 8ull * n;
+    const uint64_t image = o_len + 8ull * n;
+    Slot* slot;
+    if ((rc = claim_slot(c, image, &slot))) return rc;
+    uint8_t* h = (uint8_t*)slot->host.p;
+    uint32_t* cr = (uint32_t*)h;
+    for (int i = 0; i < n; ++i) for (uint32_t t = ts[i]; t < ts[i + 1]; ++t) cr[t] = (uint32_t)i;
+    memcpy(h + o_ts, ts.data(), 4ull * (n + 1));
+    memcpy(h + o_off, rec_off, 8ull * n);
+    memcpy(h + o_len, rec_len, 8ull * n);
+    CU(cudaMemcpyAsync(slot->dev.p, h, image, cudaMemcpyHostToDevice, c->stream));
+    CU(cudaEventRecord(slot->done, c->stream));
+    slot->pending = true;
+    uint8_t* sd = (uint8_t*)slot->dev.p;
+    fp.cta_rec = (const uint32_t*)sd; fp.tile_start = (const uint32_t*)(sd + o_ts);
+    fp.rec_off = (const uint64_t*)(sd + o_off); fp.rec_len = (const uint64_t*)(sd + o_len);
+  }
+  if (grid > 0x7FFFFFFFull) return fail(B200TFS_E_TOOBIG, "batch needs more than 2^31 tiles");
+  CU(launch_decode_fused(fp, (uint32_t)grid, c->stream));
+  c->launches += 1;
+  CU(cudaMemcpyAsync(c->fused_host.p, c->fused_dev.p, L.total, cudaMemcpyDeviceToHost, c->stream));
+  c->fused_n = n;
+  return B200TFS_OK;
+}
+
+int b200tfs_decode_results(b200tfs_ctx* c, int32_t n, b200tfs_output* outs, int32_t* n_outs, b200tfs_model_spec* specs,
+                           int32_t* rec_status) {
+  if (!c || n < 0) return fail(B200TFS_E_ARG, "bad arguments");
+  if (c->capturing) return fail(B200TFS_E_ARG, "cannot collect results during graph capture");
+  if (n > c->fused_n) return fail(B200TFS_E_ARG, "only %d records were decoded", c->fused_n);
+  CU(cudaStreamSynchronize(c->stream));
+  FusedLayout L = fused_layout(c->fused_n);
+  const uint8_t* h = (const uint8_t*)c->fused_host.p;
+  if (outs) memcpy(outs, h + L.outs, sizeof(b200tfs_output) * (uint64_t)n * kFusedMaxOutputs);
+  if (n_outs) memcpy(n_outs, h + L.nouts, 4ull * n);
+  if (specs) memcpy(specs, h + L.specs, sizeof(b200tfs_model_spec) * (uint64_t)n);
+  if (rec_status) memcpy(rec_status, h + L.status, 4ull * n);
+  return B200TFS_OK;
+}
+
+int b200tfs_capture_begin(b200tfs_ctx* c) {
+  if (!c) return fail(B200TFS_E_ARG, "ctx is NULL");
+  if (c->capturing) return fail(B200TFS_E_ARG, "already capturing");
+  CU(cudaSetDevice(c->device));
+  CU(cudaStreamSynchronize(c->stream));
+  for (auto& s : c->slots) s.pending = false;
+  CU(cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeThreadLocal));
+  c->capturing = true;
+  return B200TFS_OK;
+}
+
+int b200tfs_capture_end(b200tfs_ctx* c, void** graph_exec) {
+  if (!c || !graph_exec) return fail(B200TFS_E_ARG, "NULL argument");
+  if (!c->capturing) return fail(B200TFS_E_ARG, "not capturing");
+  c->capturing = false;
+  cudaGraph_t g = nullptr;
+  CU(cudaStreamEndCapture(c->stream, &g));
+  cudaGraphExec_t ge = nullptr;
+  cudaError_t e = cudaGraphInstantiate(&ge, g, 0);
+  cudaGraphDestroy(g);
+  if (e != cudaSuccess) return fail(B200TFS_E_CUDA, "cudaGraphInstantiate: %s", cudaGetErrorString(e));
+  *graph_exec = ge;
+  return B200TFS_OK;
+}
+
+int b200tfs_graph_launch(b200tfs_ctx* c, void* graph_exec) {
+  if (!c || !graph_exec) return fail(B200TFS_E_ARG, "NULL argument");
+  CU(cudaGraphLaunch((cudaGraphExec_t)graph_exec, c->stream));
+  return B200TFS_OK;
+}
+
+int b200tfs_graph_destroy(void* graph_exec) {
+  if (graph_exec) CU(cudaGraphExecDestroy((cudaGraphExec_t)graph_exec));
+  return B200TFS_OK;
+}
+
+int b200tfs_wait_event(b200tfs_ctx* c, void* ev) {
+  if (!c || !ev) return fail(B200TFS_E_ARG, "NULL argument");
+  CU(cudaStreamWaitEvent(c->stream, (cudaEvent_t)ev, 0));
+  return B200TFS_OK;
+}
+
+}  // extern "C"
 
 // ------------------------------------------------------------------------------------------------
 // host-buffer entry points

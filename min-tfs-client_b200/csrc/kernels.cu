@@ -142,80 +142,86 @@ __device__ __forceinline__ uint64_t src_bytes_for(uint32_t op, uint64_t n_out) {
 }
 
 // ------------------------------------------------------------------------------------------------
-// same-width body: destination vectors [v0, v1) of a payload whose body starts at dst_body (16-byte
-// aligned) / src_body (any alignment).
+// vector bodies.  `src` / `dst` point at the first byte of the TILE's body; n = destination vectors
+// in the tile.  Every thread issues all loads of a batch (kBatch vectors) before its first store:
+// a 4 MiB tensor is smaller than the HBM bandwidth-delay product, so the whole tile must be in
+// flight at once - one DRAM round trip per batch, not per vector.
 // ------------------------------------------------------------------------------------------------
+constexpr uint32_t kBatch = 4;
+
 template <uint32_t OP>
-__device__ __forceinline__ void body_aligned(const uint8_t* src_body, uint8_t* dst_body, uint64_t v0, uint64_t v1) {
-  const uint64_t T = blockDim.x;
-  uint64_t v = v0 + threadIdx.x;
-  for (; v + 3 * T < v1; v += 4 * T) {
-    uint4 a0 = ld_stream(src_body + 16 * v);
-    uint4 a1 = ld_stream(src_body + 16 * (v + T));
-    uint4 a2 = ld_stream(src_body + 16 * (v + 2 * T));
-    uint4 a3 = ld_stream(src_body + 16 * (v + 3 * T));
-    st_stream(dst_body + 16 * v, fix_vec<OP>(a0));
-    st_stream(dst_body + 16 * (v + T), fix_vec<OP>(a1));
-    st_stream(dst_body + 16 * (v + 2 * T), fix_vec<OP>(a2));
-    st_stream(dst_body + 16 * (v + 3 * T), fix_vec<OP>(a3));
+__device__ __forceinline__ void body_aligned(const uint8_t* __restrict__ src, uint8_t* __restrict__ dst, uint32_t n) {
+  for (uint32_t v = threadIdx.x; v < n; v += kBatch * kMoveThreads) {
+    uint4 a[kBatch];
+#pragma unroll
+    for (uint32_t i = 0; i < kBatch; ++i)
+      if (v + i * kMoveThreads < n) a[i] = ld_stream(src + 16ull * (v + i * kMoveThreads));
+#pragma unroll
+    for (uint32_t i = 0; i < kBatch; ++i)
+      if (v + i * kMoveThreads < n) st_stream(dst + 16ull * (v + i * kMoveThreads), fix_vec<OP>(a[i]));
   }
-  for (; v < v1; v += T) st_stream(dst_body + 16 * v, fix_vec<OP>(ld_stream(src_body + 16 * v)));
 }
 
+// S = source body rounded down to 16 bytes; output vector v = bytes [k, k+16) of blocks v, v+1
 template <uint32_t OP, int Q>
-__device__ __forceinline__ void body_shifted_q(const uint8_t* S, uint8_t* dst_body, uint64_t v0, uint64_t v1, uint32_t s) {
-  // S = src_body rounded down to 16; output vector v = bytes [k, k+16) of blocks v, v+1 of S
+__device__ __forceinline__ void body_shifted_q(const uint8_t* __restrict__ S, uint8_t* __restrict__ dst, uint32_t n, uint32_t s) {
   constexpr bool PRE = (OP == OP_QUIET_SRC);  // elements line up with the source blocks
-  const uint64_t T = blockDim.x;
-  uint64_t v = v0 + threadIdx.x;
-  for (; v + T < v1; v += 2 * T) {
-    uint4 a0 = ld_reuse(S + 16 * v), b0 = ld_reuse(S + 16 * v + 16);
-    uint4 a1 = ld_reuse(S + 16 * (v + T)), b1 = ld_reuse(S + 16 * (v + T) + 16);
-    if (PRE) { a0 = fix_vec<OP>(a0); b0 = fix_vec<OP>(b0); a1 = fix_vec<OP>(a1); b1 = fix_vec<OP>(b1); }
-    uint4 o0 = shift_pair<Q>(a0, b0, s), o1 = shift_pair<Q>(a1, b1, s);
-    if (!PRE) { o0 = fix_vec<OP>(o0); o1 = fix_vec<OP>(o1); }
-    st_stream(dst_body + 16 * v, o0);
-    st_stream(dst_body + 16 * (v + T), o1);
-  }
-  for (; v < v1; v += T) {
-    uint4 a = ld_reuse(S + 16 * v), b = ld_reuse(S + 16 * v + 16);
-    if (PRE) { a = fix_vec<OP>(a); b = fix_vec<OP>(b); }
-    uint4 o = shift_pair<Q>(a, b, s);
-    if (!PRE) o = fix_vec<OP>(o);
-    st_stream(dst_body + 16 * v, o);
+  for (uint32_t v = threadIdx.x; v < n; v += kBatch * kMoveThreads) {
+    uint4 lo[kBatch], hi[kBatch];
+#pragma unroll
+    for (uint32_t i = 0; i < kBatch; ++i)
+      if (v + i * kMoveThreads < n) {
+        lo[i] = ld_reuse(S + 16ull * (v + i * kMoveThreads));
+        hi[i] = ld_reuse(S + 16ull * (v + i * kMoveThreads) + 16);
+      }
+#pragma unroll
+    for (uint32_t i = 0; i < kBatch; ++i)
+      if (v + i * kMoveThreads < n) {
+        uint4 a = lo[i], b = hi[i];
+        if (PRE) { a = fix_vec<OP>(a); b = fix_vec<OP>(b); }
+        uint4 o = shift_pair<Q>(a, b, s);
+        if (!PRE) o = fix_vec<OP>(o);
+        st_stream(dst + 16ull * (v + i * kMoveThreads), o);
+      }
   }
 }
 
 template <uint32_t OP>
-__device__ __forceinline__ void body_same_width(const uint8_t* src_body, uint8_t* dst_body, uint64_t v0, uint64_t v1) {
-  const uint32_t k = (uint32_t)((uintptr_t)src_body & 15);
-  if (k == 0) { body_aligned<OP>(src_body, dst_body, v0, v1); return; }
-  const uint8_t* S = src_body - k;
+__device__ __forceinline__ void body_same_width(const uint8_t* src, uint8_t* dst, uint32_t n) {
+  const uint32_t k = (uint32_t)((uintptr_t)src & 15);
+  if (k == 0) { body_aligned<OP>(src, dst, n); return; }
+  const uint8_t* S = src - k;
   const uint32_t s = (k & 3) * 8;
   switch (k >> 2) {  // uniform across the CTA
-    case 0: body_shifted_q<OP, 0>(S, dst_body, v0, v1, s); break;
-    case 1: body_shifted_q<OP, 1>(S, dst_body, v0, v1, s); break;
-    case 2: body_shifted_q<OP, 2>(S, dst_body, v0, v1, s); break;
-    default: body_shifted_q<OP, 3>(S, dst_body, v0, v1, s); break;
+    case 0: body_shifted_q<OP, 0>(S, dst, n, s); break;
+    case 1: body_shifted_q<OP, 1>(S, dst, n, s); break;
+    case 2: body_shifted_q<OP, 2>(S, dst, n, s); break;
+    default: body_shifted_q<OP, 3>(S, dst, n, s); break;
   }
 }
 
 // f16 / bf16 -> f32 (encode-side cast).  Both sides 16-byte aligned; unit u = 16 source bytes -> 32 out.
 template <bool BF>
-__device__ __forceinline__ void body_widen(const uint8_t* src_body, uint8_t* dst_body, uint64_t u0, uint64_t u1) {
-  const uint64_t T = blockDim.x;
-  for (uint64_t u = u0 + threadIdx.x; u < u1; u += T) {
-    uint4 h = ld_stream(src_body + 16 * u);
-    uint4 lo, hi;
-    if (BF) {
-      lo.x = widen_bf16(h.x & 0xFFFF); lo.y = widen_bf16(h.x >> 16); lo.z = widen_bf16(h.y & 0xFFFF); lo.w = widen_bf16(h.y >> 16);
-      hi.x = widen_bf16(h.z & 0xFFFF); hi.y = widen_bf16(h.z >> 16); hi.z = widen_bf16(h.w & 0xFFFF); hi.w = widen_bf16(h.w >> 16);
-    } else {
-      lo.x = widen_f16(h.x & 0xFFFF); lo.y = widen_f16(h.x >> 16); lo.z = widen_f16(h.y & 0xFFFF); lo.w = widen_f16(h.y >> 16);
-      hi.x = widen_f16(h.z & 0xFFFF); hi.y = widen_f16(h.z >> 16); hi.z = widen_f16(h.w & 0xFFFF); hi.w = widen_f16(h.w >> 16);
-    }
-    st_stream(dst_body + 32 * u, lo);
-    st_stream(dst_body + 32 * u + 16, hi);
+__device__ __forceinline__ void body_widen(const uint8_t* __restrict__ src, uint8_t* __restrict__ dst, uint32_t units) {
+  for (uint32_t u = threadIdx.x; u < units; u += 2 * kMoveThreads) {
+    uint4 h[2];
+#pragma unroll
+    for (uint32_t i = 0; i < 2; ++i) if (u + i * kMoveThreads < units) h[i] = ld_stream(src + 16ull * (u + i * kMoveThreads));
+#pragma unroll
+    for (uint32_t i = 0; i < 2; ++i)
+      if (u + i * kMoveThreads < units) {
+        const uint4 x = h[i];
+        uint4 lo, hi;
+        if (BF) {
+          lo.x = widen_bf16(x.x & 0xFFFF); lo.y = widen_bf16(x.x >> 16); lo.z = widen_bf16(x.y & 0xFFFF); lo.w = widen_bf16(x.y >> 16);
+          hi.x = widen_bf16(x.z & 0xFFFF); hi.y = widen_bf16(x.z >> 16); hi.z = widen_bf16(x.w & 0xFFFF); hi.w = widen_bf16(x.w >> 16);
+        } else {
+          lo.x = widen_f16(x.x & 0xFFFF); lo.y = widen_f16(x.x >> 16); lo.z = widen_f16(x.y & 0xFFFF); lo.w = widen_f16(x.y >> 16);
+          hi.x = widen_f16(x.z & 0xFFFF); hi.y = widen_f16(x.z >> 16); hi.z = widen_f16(x.w & 0xFFFF); hi.w = widen_f16(x.w >> 16);
+        }
+        st_stream(dst + 32ull * (u + i * kMoveThreads), lo);
+        st_stream(dst + 32ull * (u + i * kMoveThreads) + 16, hi);
+      }
   }
 }
 
@@ -226,123 +232,116 @@ __device__ __forceinline__ uint32_t narrow2(uint32_t a, uint32_t b) {
             : (f32_bits_to_f16_bits(a) | (f32_bits_to_f16_bits(b) << 16));
 }
 template <bool BF, int Q>
-__device__ __forceinline__ void body_narrow_q(const uint8_t* S, uint8_t* dst_body, uint64_t v0, uint64_t v1, uint32_t s, bool aligned) {
-  const uint64_t T = blockDim.x;
-  for (uint64_t v = v0 + threadIdx.x; v < v1; v += T) {
-    uint4 a = ld_reuse(S + 32 * v), b = ld_reuse(S + 32 * v + 16);
-    uint4 f0, f1;
-    if (aligned) { f0 = a; f1 = b; }
-    else {
-      uint4 c = ld_reuse(S + 32 * v + 32);
-      f0 = shift_pair<Q>(a, b, s); f1 = shift_pair<Q>(b, c, s);
-    }
-    uint4 o;
-    o.x = narrow2<BF>(f0.x, f0.y); o.y = narrow2<BF>(f0.z, f0.w);
-    o.z = narrow2<BF>(f1.x, f1.y); o.w = narrow2<BF>(f1.z, f1.w);
-    st_stream(dst_body + 16 * v, o);
+__device__ __forceinline__ void body_narrow_q(const uint8_t* __restrict__ S, uint8_t* __restrict__ dst, uint32_t n, uint32_t s, bool aligned) {
+  for (uint32_t v = threadIdx.x; v < n; v += 2 * kMoveThreads) {
+    uint4 a[2], b[2], c[2];
+#pragma unroll
+    for (uint32_t i = 0; i < 2; ++i)
+      if (v + i * kMoveThreads < n) {
+        const uint8_t* p = S + 32ull * (v + i * kMoveThreads);
+        a[i] = ld_reuse(p); b[i] = ld_reuse(p + 16);
+        if (!aligned) c[i] = ld_reuse(p + 32);
+      }
+#pragma unroll
+    for (uint32_t i = 0; i < 2; ++i)
+      if (v + i * kMoveThreads < n) {
+        uint4 f0 = a[i], f1 = b[i];
+        if (!aligned) { f0 = shift_pair<Q>(a[i], b[i], s); f1 = shift_pair<Q>(b[i], c[i], s); }
+        uint4 o;
+        o.x = narrow2<BF>(f0.x, f0.y); o.y = narrow2<BF>(f0.z, f0.w);
+        o.z = narrow2<BF>(f1.x, f1.y); o.w = narrow2<BF>(f1.z, f1.w);
+        st_stream(dst + 16ull * (v + i * kMoveThreads), o);
+      }
   }
 }
 template <bool BF>
-__device__ __forceinline__ void body_narrow(const uint8_t* src_body, uint8_t* dst_body, uint64_t v0, uint64_t v1) {
-  const uint32_t k = (uint32_t)((uintptr_t)src_body & 15);
-  const uint8_t* S = src_body - k;
+__device__ __forceinline__ void body_narrow(const uint8_t* src, uint8_t* dst, uint32_t n) {
+  const uint32_t k = (uint32_t)((uintptr_t)src & 15);
+  const uint8_t* S = src - k;
   const uint32_t s = (k & 3) * 8;
   switch (k >> 2) {
-    case 0: body_narrow_q<BF, 0>(S, dst_body, v0, v1, s, k == 0); break;
-    case 1: body_narrow_q<BF, 1>(S, dst_body, v0, v1, s, false); break;
-    case 2: body_narrow_q<BF, 2>(S, dst_body, v0, v1, s, false); break;
-    default: body_narrow_q<BF, 3>(S, dst_body, v0, v1, s, false); break;
+    case 0: body_narrow_q<BF, 0>(S, dst, n, s, k == 0); break;
+    case 1: body_narrow_q<BF, 1>(S, dst, n, s, false); break;
+    case 2: body_narrow_q<BF, 2>(S, dst, n, s, false); break;
+    default: body_narrow_q<BF, 3>(S, dst, n, s, false); break;
   }
 }
 
 // ------------------------------------------------------------------------------------------------
-// one tile of one large payload
+// one tile of one large payload.  Geometry in destination space: [head bytes][nvec vectors][tail];
+// tile t owns vectors [t*vpt, (t+1)*vpt); tile 0 also writes the head, the last tile the tail.
 // ------------------------------------------------------------------------------------------------
-__device__ __forceinline__ uint32_t item_tiles(uint64_t n_out, uint32_t vpt) {
-  uint64_t vecs = (n_out + 15) >> 4;
-  uint64_t t = (vecs + vpt - 1) / vpt;
+__host__ __device__ __forceinline__ uint32_t tiles_for(uint64_t n_out, uint32_t vpt) {
+  const uint64_t vecs = (n_out + 15) >> 4;
+  const uint64_t t = (vecs + vpt - 1) / vpt;
   return t ? (uint32_t)t : 1u;
 }
 
-__device__ void move_tile(const MoveItem& it, uint32_t tile, uint32_t vpt) {
-  const uint32_t op = it.op;
-  const uint64_t n_out = it.n_out;
-  const uint8_t* src = it.src;
-  uint8_t* dst = it.dst;
-  const uint32_t n_tiles = item_tiles(n_out, vpt);
+__device__ __forceinline__ void move_tile(const uint8_t* __restrict__ src, uint8_t* __restrict__ dst, uint64_t n_out, uint32_t op,
+                                          uint32_t n_tiles, uint32_t tile, uint32_t vpt) {
   const bool last = (tile + 1 == n_tiles);
   const uint64_t n_src = src_bytes_for(op, n_out);
-
-  // geometry of the vector body in destination space
   uint64_t head = (16 - ((uintptr_t)dst & 15)) & 15;
   if (head > n_out) head = n_out;
-  bool fast;
-  uint64_t nvec;  // destination vectors handled by a vector path
-  const uint8_t* src_body;
-  switch (op) {
-    case OP_COPY: case OP_BOOL: case OP_QUIET_SRC: case OP_QUIET_DST: {
-      src_body = src + head;
-      fast = true;
-      if (op == OP_QUIET_SRC) fast = (((uintptr_t)src & 3) == 0);
-      if (op == OP_QUIET_DST) fast = ((head & 3) == 0);
-      nvec = (n_out - head) >> 4;
-      uint32_t k = (uint32_t)((uintptr_t)src_body & 15);
-      if (k) {  // the shifted path reads block v+1: keep it inside the source
-        uint64_t avail = (uint64_t)((src + n_src) - (src_body - k)) >> 4;  // whole blocks available
-        uint64_t lim = avail ? avail - 1 : 0;
-        if (nvec > lim) nvec = lim;
-      }
-      break;
-    }
-    case OP_H2F: case OP_B2F: {
-      src_body = src;
-      fast = (head == 0) && (((uintptr_t)src & 15) == 0);
-      nvec = ((n_out) >> 5) << 1;  // whole 32-byte units, counted in 16-byte vectors
-      break;
-    }
-    default: {  // OP_F2H / OP_F2B
-      src_body = src + 2 * head;
-      fast = ((head & 1) == 0);
-      nvec = (n_out - head) >> 4;
-      uint32_t k = (uint32_t)((uintptr_t)src_body & 15);
-      uint64_t span = (uint64_t)((src + n_src) - (src_body - k));
-      uint64_t lim = k ? (span >= 16 ? (span - 16) >> 5 : 0) : (span >> 5);
+  bool fast = true;
+  uint64_t nvec;                 // destination vectors a vector path may handle
+  const uint8_t* src_body = src + head;
+  if (op <= OP_QUIET_DST) {      // OP_COPY, OP_QUIET_SRC, OP_QUIET_DST (same width); OP_BOOL handled below
+    if (op == OP_QUIET_SRC) fast = (((uintptr_t)src & 3) == 0);
+    if (op == OP_QUIET_DST) fast = ((head & 3) == 0);
+    nvec = (n_out - head) >> 4;
+    const uint32_t k = (uint32_t)((uintptr_t)src_body & 15);
+    if (k) {  // the shifted path also reads block v+1: keep that inside the source
+      const uint64_t blocks = (uint64_t)((src + n_src) - (src_body - k)) >> 4;
+      const uint64_t lim = blocks ? blocks - 1 : 0;
       if (nvec > lim) nvec = lim;
-      break;
     }
+  } else if (op == OP_BOOL) {
+    nvec = (n_out - head) >> 4;
+    const uint32_t k = (uint32_t)((uintptr_t)src_body & 15);
+    if (k) {
+      const uint64_t blocks = (uint64_t)((src + n_src) - (src_body - k)) >> 4;
+      const uint64_t lim = blocks ? blocks - 1 : 0;
+      if (nvec > lim) nvec = lim;
+    }
+  } else if (op == OP_H2F || op == OP_B2F) {
+    src_body = src;
+    fast = (head == 0) && (((uintptr_t)src & 15) == 0);
+    nvec = (n_out >> 5) << 1;    // whole 32-byte units, counted in 16-byte vectors
+  } else {                       // OP_F2H / OP_F2B
+    src_body = src + 2 * head;
+    fast = ((head & 1) == 0);
+    nvec = (n_out - head) >> 4;
+    const uint32_t k = (uint32_t)((uintptr_t)src_body & 15);
+    const uint64_t span = (uint64_t)((src + n_src) - (src_body - k));
+    const uint64_t lim = k ? (span >= 16 ? (span - 16) >> 5 : 0) : (span >> 5);
+    if (nvec > lim) nvec = lim;
   }
-  if (!fast) { head = 0; nvec = 0; }
-
-  uint8_t* dst_body = dst + head;
-  uint64_t v0 = (uint64_t)tile * vpt, v1 = v0 + vpt;
-  if (v1 > nvec) v1 = nvec;
-  if (v0 < v1) {
+  if (!fast) {  // whole payload through the byte generator, split by tile
+    const uint64_t b0 = (uint64_t)tile * vpt * 16;
+    uint64_t b1 = b0 + (uint64_t)vpt * 16;
+    if (b1 > n_out || last) b1 = n_out;
+    for (uint64_t i = b0 + threadIdx.x; i < b1; i += blockDim.x) dst[i] = gen_byte(op, src, i);
+    return;
+  }
+  const uint64_t v0 = (uint64_t)tile * vpt;
+  if (v0 < nvec) {
+    const uint32_t n = (uint32_t)min((uint64_t)vpt, nvec - v0);
+    uint8_t* d = dst + head + 16 * v0;
     switch (op) {
-      case OP_COPY: body_same_width<OP_COPY>(src_body, dst_body, v0, v1); break;
-      case OP_BOOL: body_same_width<OP_BOOL>(src_body, dst_body, v0, v1); break;
-      case OP_QUIET_SRC: body_same_width<OP_QUIET_SRC>(src_body, dst_body, v0, v1); break;
-      case OP_QUIET_DST: body_same_width<OP_QUIET_DST>(src_body, dst_body, v0, v1); break;
-      case OP_H2F: body_widen<false>(src_body, dst_body, v0 >> 1, v1 >> 1); break;
-      case OP_B2F: body_widen<true>(src_body, dst_body, v0 >> 1, v1 >> 1); break;
-      case OP_F2H: body_narrow<false>(src_body, dst_body, v0, v1); break;
-      default: body_narrow<true>(src_body, dst_body, v0, v1); break;
+      case OP_COPY: body_same_width<OP_COPY>(src_body + 16 * v0, d, n); break;
+      case OP_BOOL: body_same_width<OP_BOOL>(src_body + 16 * v0, d, n); break;
+      case OP_QUIET_SRC: body_same_width<OP_QUIET_SRC>(src_body + 16 * v0, d, n); break;
+      case OP_QUIET_DST: body_same_width<OP_QUIET_DST>(src_body + 16 * v0, d, n); break;
+      case OP_H2F: body_widen<false>(src_body + 8 * v0, d, n >> 1); break;
+      case OP_B2F: body_widen<true>(src_body + 8 * v0, d, n >> 1); break;
+      case OP_F2H: body_narrow<false>(src_body + 32 * v0, d, n); break;
+      default: body_narrow<true>(src_body + 32 * v0, d, n); break;
     }
   }
   // ragged edges, element-exact
-  if (tile == 0 && head) {
-    for (uint64_t i = threadIdx.x; i < head; i += blockDim.x) dst[i] = gen_byte(op, src, i);
-  }
-  if (last) {
-    uint64_t done = head + (nvec << 4);
-    if (fast) {
-      for (uint64_t i = done + threadIdx.x; i < n_out; i += blockDim.x) dst[i] = gen_byte(op, src, i);
-    }
-  }
-  if (!fast) {  // whole payload through the byte generator, split by tile
-    uint64_t b0 = (uint64_t)tile * vpt * 16, b1 = b0 + (uint64_t)vpt * 16;
-    if (b1 > n_out || last) b1 = n_out;
-    for (uint64_t i = b0 + threadIdx.x; i < b1; i += blockDim.x) dst[i] = gen_byte(op, src, i);
-  }
+  if (tile == 0) for (uint64_t i = threadIdx.x; i < head; i += blockDim.x) dst[i] = gen_byte(op, src, i);
+  if (last) for (uint64_t i = head + (nvec << 4) + threadIdx.x; i < n_out; i += blockDim.x) dst[i] = gen_byte(op, src, i);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -356,11 +355,11 @@ __device__ __forceinline__ void move_body(const uint8_t* plan) {
     uint32_t item, tile;
     if (ph.uniform_tpi) { item = b / ph.uniform_tpi; tile = b - item * ph.uniform_tpi; }
     else {
-      TileRef tr = reinterpret_cast<const TileRef*>(plan + ph.off_tiles)[b];
+      const TileRef tr = reinterpret_cast<const TileRef*>(plan + ph.off_tiles)[b];
       item = tr.item; tile = tr.tile;
     }
-    const MoveItem it = reinterpret_cast<const MoveItem*>(plan + ph.off_items)[item];
-    move_tile(it, tile, ph.vec_per_tile);
+    const MoveItem& it = reinterpret_cast<const MoveItem*>(plan + ph.off_items)[item];
+    move_tile(it.src, it.dst, it.n_out, it.op, it.n_tiles, tile, ph.vec_per_tile);
   } else {
     const uint32_t warps = blockDim.x >> 5;
     const uint32_t idx = (b - ph.n_tiles) * warps + (threadIdx.x >> 5);
@@ -373,32 +372,108 @@ __device__ __forceinline__ void move_body(const uint8_t* plan) {
   }
 }
 
-__global__ void __launch_bounds__(kMoveThreads) move_kernel(const uint8_t* __restrict__ plan) { move_body(plan); }
+__global__ void __launch_bounds__(kMoveThreads, 3) move_kernel(const uint8_t* __restrict__ plan) { move_body(plan); }
 
-__global__ void __launch_bounds__(kMoveThreads) move_kernel_inline(const __grid_constant__ InlinePlan plan) {
+__global__ void __launch_bounds__(kMoveThreads, 3) move_kernel_inline(const __grid_constant__ InlinePlan plan) {
   move_body(plan.bytes);
 }
 
 // ------------------------------------------------------------------------------------------------
-// parse_kernel: one lane per record
+// parse kernels (two-phase decode): one lane per record walks the tags into the table
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(32) parse_responses_kernel(const uint8_t* __restrict__ w, const uint64_t* __restrict__ rec_off,
                                                              const uint64_t* __restrict__ rec_len, int n, int max_outputs,
                                                              b200tfs_output* outs, int32_t* n_outs, b200tfs_model_spec* specs,
                                                              int32_t* status) {
+  __shared__ __align__(16) uint8_t lines[32][256];
   int r = blockIdx.x * blockDim.x + threadIdx.x;
   if (r >= n) return;
+  Win win; win.buf = lines[threadIdx.x];
+  win_prefetch(&win, w, rec_off[r], rec_len[r]);
   int cnt = 0;
-  status[r] = walk_response(w, rec_off[r], rec_len[r], max_outputs, outs + (size_t)r * max_outputs, &cnt, specs + r);
+  status[r] = walk_response(w, rec_off[r], rec_len[r], max_outputs, outs + (size_t)r * max_outputs, &cnt, specs + r, &win);
   n_outs[r] = cnt;
 }
 
 __global__ void __launch_bounds__(32) parse_tensors_kernel(const uint8_t* __restrict__ w, const uint64_t* __restrict__ rec_off,
                                                            const uint64_t* __restrict__ rec_len, int n, b200tfs_output* outs,
                                                            int32_t* status) {
+  __shared__ __align__(16) uint8_t lines[32][256];
   int r = blockIdx.x * blockDim.x + threadIdx.x;
   if (r >= n) return;
-  status[r] = walk_tensor_proto(w, rec_off[r], rec_len[r], outs + r);
+  Win win; win.buf = lines[threadIdx.x];
+  win_prefetch(&win, w, rec_off[r], rec_len[r]);
+  status[r] = walk_tensor_proto(w, rec_off[r], rec_len[r], outs + r, &win);
+}
+
+// ------------------------------------------------------------------------------------------------
+// decode_fused_kernel: the whole PredictResponse decode in ONE launch.  CTA b belongs to record r
+// (cta_rec[b]) with local tile j.  Thread 0 walks the record's tags out of the line cache (every CTA
+// of the record does the same walk: ~100 header bytes, L2-resident after the first CTA), lays the
+// outputs out in the record's destination slot, and finds which value chunk tile j falls in; then the
+// CTA moves that tile.  CTA j == 0 also publishes the table for the host.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kMoveThreads, 3) decode_fused_kernel(const __grid_constant__ FusedParams fp) {
+  __shared__ __align__(16) uint8_t lines[256];
+  __shared__ b200tfs_output outs_s[kFusedMaxOutputs];
+  __shared__ b200tfs_model_spec spec_s;
+  __shared__ struct { const uint8_t* src; uint8_t* dst; uint64_t n_out; uint32_t op, n_tiles, tile, valid; } job;
+  const uint32_t b = blockIdx.x;
+  uint32_t r, j;
+  uint64_t off, len;
+  if (fp.n <= kFusedInlineRecs) {
+    r = 0;
+    while (r + 1 < (uint32_t)fp.n && b >= fp.inl.tile_start[r + 1]) ++r;
+    j = b - fp.inl.tile_start[r]; off = fp.inl.off[r]; len = fp.inl.len[r];
+  } else {
+    r = fp.cta_rec[b]; j = b - fp.tile_start[r]; off = fp.rec_off[r]; len = fp.rec_len[r];
+  }
+  if (threadIdx.x == 0) {
+    Win win; win.buf = lines;
+    win_prefetch(&win, fp.w, off, len);
+    int cnt = 0;
+    int st = walk_response(fp.w, off, len, kFusedMaxOutputs, outs_s, &cnt, &spec_s, &win);
+    job.valid = 0;
+    // destination layout + tile lookup
+    uint64_t cursor = 0;        // bytes used in this record's destination slot
+    uint32_t t_base = 0;        // tiles consumed by earlier chunks
+    const uint32_t budget = ((r + 1 < (uint32_t)fp.n) ? (fp.n <= kFusedInlineRecs ? fp.inl.tile_start[r + 1] : fp.tile_start[r + 1])
+                                                      : gridDim.x) - (b - j);
+    if (st == B200TFS_OK) {
+      for (int k = 0; k < cnt; ++k) {
+        b200tfs_output& o = outs_s[k];
+        o.dst_off = 0;
+        if (o.status != B200TFS_OK || !o.n_elems) continue;
+        const DtypeInfo di = dtype_info(o.dtype);
+        if (di.kind != VK_FIXED) continue;   // varint / string outputs: tabulated only (two-phase unpack)
+        cursor = (cursor + 255) & ~255ull;
+        if (cursor + o.dst_bytes > fp.dst_stride) { o.status = B200TFS_E_SIZE; continue; }
+        o.dst_off = (uint64_t)r * fp.dst_stride + cursor;
+        uint8_t* d = fp.dst + o.dst_off;
+        const uint32_t op = (o.dtype == DT_FLOAT) ? OP_QUIET_DST : OP_COPY;
+        for (int c = 0; c < o.n_chunks; ++c) {
+          const uint32_t nt = tiles_for(o.chunk_len[c], fp.vpt);
+          if (j >= t_base && j < t_base + nt) {
+            job.src = fp.w + o.chunk_off[c]; job.dst = d; job.n_out = o.chunk_len[c]; job.op = op;
+            job.n_tiles = nt; job.tile = j - t_base; job.valid = 1;
+          }
+          t_base += nt;
+          d += o.chunk_len[c];
+        }
+        cursor += o.dst_bytes;
+      }
+      if (t_base > budget) st = B200TFS_E_NONCANONICAL;  // more chunks than the launch budgeted tiles for
+    }
+    if (j == 0) {
+      fp.status[r] = st;
+      fp.n_outs[r] = (st == B200TFS_OK) ? cnt : 0;
+      fp.specs[r] = spec_s;
+      for (int k = 0; k < cnt && st == B200TFS_OK; ++k) fp.outs[(size_t)r * kFusedMaxOutputs + k] = outs_s[k];
+    }
+    if (st != B200TFS_OK) job.valid = 0;
+  }
+  __syncthreads();
+  if (job.valid) move_tile(job.src, job.dst, job.n_out, job.op, job.n_tiles, job.tile, fp.vpt);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -656,6 +731,14 @@ cudaError_t launch_parse_tensors(const uint8_t* w, const uint64_t* rec_off, cons
                                  int32_t* status, cudaStream_t stream) {
   if (n <= 0) return cudaSuccess;
   parse_tensors_kernel<<<(n + 31) / 32, 32, 0, stream>>>(w, rec_off, rec_len, n, outs, status);
+  return cudaGetLastError();
+}
+
+uint32_t tiles_for_host(uint64_t n_out, uint32_t vpt) { return tiles_for(n_out, vpt); }
+
+cudaError_t launch_decode_fused(const FusedParams& fp, uint32_t grid, cudaStream_t stream) {
+  if (!grid) return cudaSuccess;
+  decode_fused_kernel<<<grid, kMoveThreads, 0, stream>>>(fp);
   return cudaGetLastError();
 }
 

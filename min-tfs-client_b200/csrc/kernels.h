@@ -19,6 +19,8 @@ cudaError_t launch_parse_responses(const uint8_t* w, const uint64_t* rec_off, co
 cudaError_t launch_parse_tensors(const uint8_t* w, const uint64_t* rec_off, const uint64_t* rec_len, int n, b200tfs_output* outs,
                                  int32_t* status, cudaStream_t stream);
 
+cudaError_t launch_decode_fused(const FusedParams& fp, uint32_t grid, cudaStream_t stream);
+uint32_t tiles_for_host(uint64_t n_out, uint32_t vpt);
 cudaError_t launch_venc_len(const VarSeg* segs, const uint32_t* tile_seg, const VarJobDev* jobs, uint32_t* tile_val, uint32_t n_tiles,
                             cudaStream_t stream);
 cudaError_t launch_vscan(const VarJobDev* jobs, const uint32_t* tile_val, uint64_t* tile_off, uint64_t* job_total, uint32_t n_jobs,

@@ -8,6 +8,8 @@
 #pragma once
 #include <stdint.h>
 
+#include "../../include/b200tfs.h"
+
 namespace b200tfs {
 
 // what a MoveItem / SmallItem does to the bytes it moves
@@ -28,7 +30,7 @@ struct MoveItem {     // one large payload, tiled across CTAs
   uint8_t* dst;
   uint64_t n_out;     // bytes written
   uint32_t op;
-  uint32_t first_tile;
+  uint32_t n_tiles;   // max(1, ceil(ceil(n_out/16) / vec_per_tile))
 };
 
 struct TileRef { uint32_t item; uint32_t tile; };
@@ -51,6 +53,30 @@ struct InlinePlan { uint8_t bytes[kInlinePlanBytes]; };
 
 constexpr uint32_t kMoveThreads = 256;      // threads per CTA of move_kernel
 constexpr uint32_t kSmallMax = 2048;        // payloads up to this many bytes take the warp path
+
+// ---- fused single-launch decode ---------------------------------------------------------------
+constexpr int kFusedMaxOutputs = 8;    // outputs tabulated per record by decode_fused_kernel
+constexpr int kFusedInlineRecs = 16;   // up to this many records travel in the kernel parameters
+constexpr uint32_t kFusedSlackTiles = 8;  // tiles budgeted per record beyond ceil(rec_len / tile)
+
+struct FusedInline { uint64_t off[kFusedInlineRecs], len[kFusedInlineRecs]; uint32_t tile_start[kFusedInlineRecs + 1]; };
+
+struct FusedParams {
+  const uint8_t* w;          // wire arena
+  uint8_t* dst;              // destination base; record r owns [r*dst_stride, (r+1)*dst_stride)
+  uint64_t dst_stride;
+  int32_t n;
+  uint32_t vpt;
+  b200tfs_output* outs;      // device table, n * kFusedMaxOutputs
+  int32_t* n_outs;
+  b200tfs_model_spec* specs;
+  int32_t* status;
+  const uint32_t* cta_rec;   // n > kFusedInlineRecs: record of every CTA, tile_start[n+1], rec_off, rec_len
+  const uint32_t* tile_start;
+  const uint64_t* rec_off;
+  const uint64_t* rec_len;
+  FusedInline inl;
+};
 
 // ---- packed-varint jobs ------------------------------------------------------------------------
 constexpr uint32_t kVarThreads = 256;

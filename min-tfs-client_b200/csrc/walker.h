@@ -18,18 +18,69 @@
 
 namespace b200tfs {
 
+// Two 128-byte lines of the wire cached next to the walking lane (shared memory on the device).  A
+// single lane chasing bytes through HBM pays a full DRAM round trip per miss, so it fetches whole
+// lines with eight independent 16-byte loads; the canonical response (header ... payload ... model_spec)
+// then costs two misses, both issued up front by win_prefetch().  On the host the window is unused.
+struct Win {
+  uint64_t line[2];  // absolute address of each cached line (aligned to 128), ~0 = empty
+  uint8_t* buf;      // 256 bytes
+  uint32_t victim;
+};
+
 struct Cursor {
   const uint8_t* w;  // arena base
   uint64_t p;        // current offset
   uint64_t end;      // limit of the enclosing message
   int err;           // sticky B200TFS_E_PARSE
+  Win* win;          // device: line cache; host: nullptr
 };
+
+#if defined(__CUDACC__)
+__device__ __forceinline__ void win_fill(Win* W, uint32_t k, uint64_t line) {
+  const uint4* g = reinterpret_cast<const uint4*>(line);
+  uint4 t0 = g[0], t1 = g[1], t2 = g[2], t3 = g[3], t4 = g[4], t5 = g[5], t6 = g[6], t7 = g[7];
+  uint4* s = reinterpret_cast<uint4*>(W->buf + 128 * k);
+  s[0] = t0; s[1] = t1; s[2] = t2; s[3] = t3; s[4] = t4; s[5] = t5; s[6] = t6; s[7] = t7;
+  W->line[k] = line;
+}
+// fetch the first and the last line of a record together (both loads in flight at once)
+__device__ __forceinline__ void win_prefetch(Win* W, const uint8_t* w, uint64_t off, uint64_t len) {
+  W->line[0] = W->line[1] = ~0ull; W->victim = 0;
+  if (!len) return;
+  const uint64_t a = (uint64_t)(uintptr_t)(w + off) & ~127ull, b = (uint64_t)(uintptr_t)(w + off + len - 1) & ~127ull;
+  const uint4* ga = reinterpret_cast<const uint4*>(a);
+  const uint4* gb = reinterpret_cast<const uint4*>(b);
+  uint4 x0 = ga[0], x1 = ga[1], x2 = ga[2], x3 = ga[3], x4 = ga[4], x5 = ga[5], x6 = ga[6], x7 = ga[7];
+  uint4 y0 = gb[0], y1 = gb[1], y2 = gb[2], y3 = gb[3], y4 = gb[4], y5 = gb[5], y6 = gb[6], y7 = gb[7];
+  uint4* s = reinterpret_cast<uint4*>(W->buf);
+  s[0] = x0; s[1] = x1; s[2] = x2; s[3] = x3; s[4] = x4; s[5] = x5; s[6] = x6; s[7] = x7;
+  s[8] = y0; s[9] = y1; s[10] = y2; s[11] = y3; s[12] = y4; s[13] = y5; s[14] = y6; s[15] = y7;
+  W->line[0] = a; W->line[1] = b;
+}
+#endif
+
+// byte at arena offset p
+B2_HD uint8_t rd8(const Cursor& c, uint64_t p) {
+#if defined(__CUDA_ARCH__)
+  Win* W = c.win;
+  const uint64_t addr = (uint64_t)(uintptr_t)(c.w + p), line = addr & ~127ull;
+  if (line == W->line[0]) return W->buf[addr & 127];
+  if (line == W->line[1]) return W->buf[128 + (addr & 127)];
+  const uint32_t k = W->victim;
+  W->victim = k ^ 1;
+  win_fill(W, k, line);
+  return W->buf[128 * k + (addr & 127)];
+#else
+  return c.w[p];
+#endif
+}
 
 B2_HD uint64_t rd_varint(Cursor& c) {
   uint64_t v = 0;
   for (int i = 0; i < 10; ++i) {
     if (c.p >= c.end) { c.err = B200TFS_E_PARSE; return 0; }
-    uint8_t b = c.w[c.p++];
+    uint8_t b = rd8(c, c.p++);
     v |= (uint64_t)(b & 0x7F) << (7 * i);  // bits past 64 fall off, as in the runtime
     if (!(b & 0x80)) return v;
   }
@@ -53,47 +104,46 @@ B2_HD uint64_t rd_len(Cursor& c) {
   return n;
 }
 
-// Skip one field body of wire type wt (tag already consumed).  Groups nest; an END_GROUP that does
-// not close a group we opened is malformed.
-B2_HD void skip_field(Cursor& c, uint32_t tag) {
-  uint32_t wt = tag & 7;
+// Skip one non-group field body (tag already consumed).
+B2_HD void skip_scalar(Cursor& c, uint32_t wt) {
   if (wt == WT_VARINT) { (void)rd_varint(c); return; }
   if (wt == WT_I64) { if (c.end - c.p < 8) c.err = B200TFS_E_PARSE; else c.p += 8; return; }
   if (wt == WT_I32) { if (c.end - c.p < 4) c.err = B200TFS_E_PARSE; else c.p += 4; return; }
   if (wt == WT_LEN) { uint64_t n = rd_len(c); if (!c.err) c.p += n; return; }
-  if (wt == WT_SGROUP) {
-    // iterative skip with an explicit stack of open group numbers (depth <= 32)
-    uint32_t open[32];
-    int depth = 0;
-    open[depth++] = tag >> 3;
-    while (depth > 0 && !c.err) {
-      if (c.p >= c.end) { c.err = B200TFS_E_PARSE; return; }
-      uint32_t t = rd_tag(c);
-      if (c.err) return;
-      uint32_t w2 = t & 7;
-      if (w2 == WT_SGROUP) {
-        if (depth >= 32) { c.err = B200TFS_E_PARSE; return; }
-        open[depth++] = t >> 3;
-      } else if (w2 == WT_EGROUP) {
-        if (open[depth - 1] != (t >> 3)) { c.err = B200TFS_E_PARSE; return; }
-        --depth;
-      } else if (w2 == WT_VARINT || w2 == WT_I64 || w2 == WT_I32 || w2 == WT_LEN) {
-        skip_field(c, t);  // non-group types never recurse further
-      } else {
-        c.err = B200TFS_E_PARSE; return;
-      }
+  c.err = B200TFS_E_PARSE;
+}
+
+// Skip one field body of any wire type.  Groups nest (explicit stack, no recursion: device stack
+// frames stay static); an END_GROUP that does not close a group we opened is malformed.
+B2_HD void skip_field(Cursor& c, uint32_t tag) {
+  const uint32_t wt = tag & 7;
+  if (wt != WT_SGROUP) { skip_scalar(c, wt); return; }  // stray END_GROUP and wire types 6, 7 fail in there
+  uint32_t open[32];
+  int depth = 0;
+  open[depth++] = tag >> 3;
+  while (depth > 0 && !c.err) {
+    if (c.p >= c.end) { c.err = B200TFS_E_PARSE; return; }
+    const uint32_t t = rd_tag(c);
+    if (c.err) return;
+    const uint32_t w2 = t & 7;
+    if (w2 == WT_SGROUP) {
+      if (depth >= 32) { c.err = B200TFS_E_PARSE; return; }
+      open[depth++] = t >> 3;
+    } else if (w2 == WT_EGROUP) {
+      if (open[depth - 1] != (t >> 3)) { c.err = B200TFS_E_PARSE; return; }
+      --depth;
+    } else {
+      skip_scalar(c, w2);
     }
-    return;
   }
-  c.err = B200TFS_E_PARSE;  // stray END_GROUP, wire types 6 and 7
 }
 
 // Structural UTF-8 check the runtime applies to proto3 `string` fields (shortest form, no
 // surrogates, <= U+10FFFF).
-B2_HD bool utf8_ok(const uint8_t* s, uint64_t n) {
+B2_HD bool utf8_ok(const Cursor& c, uint64_t off, uint64_t n) {
   uint64_t i = 0;
   while (i < n) {
-    uint8_t b = s[i];
+    uint8_t b = rd8(c, off + i);
     if (b < 0x80) { ++i; continue; }
     uint32_t need; uint32_t cp;
     if (b >= 0xC2 && b <= 0xDF) { need = 1; cp = b & 0x1F; }
@@ -102,7 +152,7 @@ B2_HD bool utf8_ok(const uint8_t* s, uint64_t n) {
     else return false;
     if (n - i - 1 < need) return false;
     for (uint32_t k = 1; k <= need; ++k) {
-      uint8_t x = s[i + k];
+      uint8_t x = rd8(c, off + i + k);
       if ((x & 0xC0) != 0x80) return false;
       cp = (cp << 6) | (x & 0x3F);
     }
@@ -127,7 +177,7 @@ B2_HD void out_reset(b200tfs_output& o) {
   for (int i = 0; i < B200TFS_MAX_RANK; ++i) o.dims[i] = 0;
   for (int i = 0; i < B200TFS_MAX_CHUNKS; ++i) { o.chunk_off[i] = 0; o.chunk_len[i] = 0; }
   o.content_off = 0; o.content_len = 0; o.msg_off = 0; o.msg_len = 0;
-  o.n_elems = 0; o.dst_bytes = 0; o.n_strings = 0; o.status = B200TFS_OK; o.reserved = 0;
+  o.n_elems = 0; o.dst_bytes = 0; o.n_strings = 0; o.dst_off = 0; o.status = B200TFS_OK; o.reserved = 0;
 }
 
 // TensorShapeProto (tensor_shape.proto:13-46): dims append (merge); Dim.size last wins inside a Dim.
@@ -138,7 +188,7 @@ B2_HD void walk_shape(Cursor& c, b200tfs_output& o, bool& rank_overflow) {
     if (tag == tag_of(2, WT_LEN)) {  // dim
       uint64_t n = rd_len(c);
       if (c.err) return;
-      Cursor d{c.w, c.p, c.p + n, 0};
+      Cursor d{c.w, c.p, c.p + n, 0, c.win};
       int64_t size = 0;
       while (d.p < d.end && !d.err) {
         uint32_t t = rd_tag(d);
@@ -147,7 +197,7 @@ B2_HD void walk_shape(Cursor& c, b200tfs_output& o, bool& rank_overflow) {
         else if (t == tag_of(2, WT_LEN)) {  // name: a proto3 string, validated then ignored (tensors.py:38-39)
           uint64_t m = rd_len(d);
           if (d.err) break;
-          if (!utf8_ok(d.w + d.p, m)) d.err = B200TFS_E_PARSE;
+          if (!utf8_ok(d, d.p, m)) d.err = B200TFS_E_PARSE;
           d.p += m;
         } else skip_field(d, t);
       }
@@ -171,7 +221,7 @@ B2_HD void walk_tensor(Cursor& c, b200tfs_output& o, RawChunks& raw, bool& rank_
     } else if (field == F_SHAPE && wt == WT_LEN) {
       uint64_t n = rd_len(c);
       if (c.err) return;
-      Cursor s{c.w, c.p, c.p + n, 0};
+      Cursor s{c.w, c.p, c.p + n, 0, c.win};
       walk_shape(s, o, rank_overflow);
       if (s.err) { c.err = s.err; return; }
       c.p += n;
@@ -194,7 +244,7 @@ B2_HD void walk_tensor(Cursor& c, b200tfs_output& o, RawChunks& raw, bool& rank_
         uint32_t fw = fixed_wire_width(field);
         if (fw) {
           if (len % fw) { c.err = B200TFS_E_PARSE; return; }  // packed fixed32/64 must be whole elements
-        } else if (len && (c.w[off + len - 1] & 0x80)) {
+        } else if (len && (rd8(c, off + len - 1) & 0x80)) {
           c.err = B200TFS_E_PARSE; return;                    // packed varints must end on a terminator
         }
         c.p += len;
@@ -268,8 +318,8 @@ B2_HD void finalize_output(b200tfs_output& o, const RawChunks& raw, bool rank_ov
   o.dst_bytes = prod * di.elem_size;
 }
 
-B2_HD bool bytes_equal(const uint8_t* a, const uint8_t* b, uint64_t n) {
-  for (uint64_t i = 0; i < n; ++i) if (a[i] != b[i]) return false;
+B2_HD bool bytes_equal(const Cursor& c, uint64_t a, uint64_t b, uint64_t n) {
+  for (uint64_t i = 0; i < n; ++i) if (rd8(c, a + i) != rd8(c, b + i)) return false;
   return true;
 }
 
@@ -286,7 +336,7 @@ B2_HD void walk_model_spec(Cursor& c, b200tfs_model_spec& s) {
     if (tag == tag_of(1, WT_LEN) || tag == tag_of(3, WT_LEN) || tag == tag_of(4, WT_LEN)) {
       uint64_t n = rd_len(c);
       if (c.err) return;
-      if (!utf8_ok(c.w + c.p, n)) { c.err = B200TFS_E_PARSE; return; }
+      if (!utf8_ok(c, c.p, n)) { c.err = B200TFS_E_PARSE; return; }
       if ((tag >> 3) == 1) { s.name_off = c.p; s.name_len = (uint32_t)n; }
       else if ((tag >> 3) == 3) { s.signature_off = c.p; s.signature_len = (uint32_t)n; }
       else { s.label_off = c.p; s.label_len = (uint32_t)n; s.has_version = 0; s.version = 0; }  // oneof: label displaces version
@@ -294,7 +344,7 @@ B2_HD void walk_model_spec(Cursor& c, b200tfs_model_spec& s) {
     } else if (tag == tag_of(2, WT_LEN)) {  // google.protobuf.Int64Value version
       uint64_t n = rd_len(c);
       if (c.err) return;
-      Cursor v{c.w, c.p, c.p + n, 0};
+      Cursor v{c.w, c.p, c.p + n, 0, c.win};
       if (!s.has_version) s.version = 0;
       while (v.p < v.end && !v.err) {
         uint32_t t = rd_tag(v);
@@ -310,8 +360,8 @@ B2_HD void walk_model_spec(Cursor& c, b200tfs_model_spec& s) {
 
 // One PredictResponse (predict.proto:30-40).  Returns the record status; *n_outs distinct keys.
 B2_HD int walk_response(const uint8_t* w, uint64_t off, uint64_t len, int max_outputs, b200tfs_output* outs,
-                        int* n_outs, b200tfs_model_spec* spec) {
-  Cursor c{w, off, off + len, 0};
+                        int* n_outs, b200tfs_model_spec* spec, Win* win = nullptr) {
+  Cursor c{w, off, off + len, 0, win};
   int n = 0;
   spec_reset(*spec);
   *n_outs = 0;
@@ -321,7 +371,7 @@ B2_HD int walk_response(const uint8_t* w, uint64_t off, uint64_t len, int max_ou
     if (tag == tag_of(1, WT_LEN)) {  // outputs map entry
       uint64_t elen = rd_len(c);
       if (c.err) break;
-      Cursor e{w, c.p, c.p + elen, 0};
+      Cursor e{w, c.p, c.p + elen, 0, c.win};
       b200tfs_output tmp; out_reset(tmp);
       RawChunks raw; raw.n = 0; raw.overflow = false;
       bool rank_overflow = false;
@@ -331,13 +381,13 @@ B2_HD int walk_response(const uint8_t* w, uint64_t off, uint64_t len, int max_ou
         if (t == tag_of(1, WT_LEN)) {
           uint64_t k = rd_len(e);
           if (e.err) break;
-          if (!utf8_ok(w + e.p, k)) { e.err = B200TFS_E_PARSE; break; }
+          if (!utf8_ok(e, e.p, k)) { e.err = B200TFS_E_PARSE; break; }
           tmp.key_off = e.p; tmp.key_len = (uint32_t)k;
           e.p += k;
         } else if (t == tag_of(2, WT_LEN)) {
           uint64_t m = rd_len(e);
           if (e.err) break;
-          Cursor tc{w, e.p, e.p + m, 0};
+          Cursor tc{w, e.p, e.p + m, 0, c.win};
           tmp.msg_off = e.p; tmp.msg_len = m;
           walk_tensor(tc, tmp, raw, rank_overflow);
           if (tc.err) { e.err = tc.err; break; }
@@ -350,7 +400,7 @@ B2_HD int walk_response(const uint8_t* w, uint64_t off, uint64_t len, int max_ou
       // duplicate key: the later entry replaces the earlier one
       int slot = -1;
       for (int i = 0; i < n; ++i)
-        if (outs[i].key_len == tmp.key_len && bytes_equal(w + outs[i].key_off, w + tmp.key_off, tmp.key_len)) { slot = i; break; }
+        if (outs[i].key_len == tmp.key_len && bytes_equal(c, outs[i].key_off, tmp.key_off, tmp.key_len)) { slot = i; break; }
       if (slot < 0) {
         if (n >= max_outputs) return B200TFS_E_SIZE;
         slot = n++;
@@ -359,7 +409,7 @@ B2_HD int walk_response(const uint8_t* w, uint64_t off, uint64_t len, int max_ou
     } else if (tag == tag_of(2, WT_LEN)) {
       uint64_t m = rd_len(c);
       if (c.err) break;
-      Cursor sc{w, c.p, c.p + m, 0};
+      Cursor sc{w, c.p, c.p + m, 0, c.win};
       walk_model_spec(sc, *spec);
       if (sc.err) { c.err = sc.err; break; }
       c.p += m;
@@ -371,8 +421,8 @@ B2_HD int walk_response(const uint8_t* w, uint64_t off, uint64_t len, int max_ou
 }
 
 // A bare TensorProto message (what tensor_proto_to_ndarray receives).
-B2_HD int walk_tensor_proto(const uint8_t* w, uint64_t off, uint64_t len, b200tfs_output* out) {
-  Cursor c{w, off, off + len, 0};
+B2_HD int walk_tensor_proto(const uint8_t* w, uint64_t off, uint64_t len, b200tfs_output* out, Win* win = nullptr) {
+  Cursor c{w, off, off + len, 0, win};
   out_reset(*out);
   RawChunks raw; raw.n = 0; raw.overflow = false;
   bool rank_overflow = false;

@@ -24,7 +24,7 @@ F_KEEP_SNAN = 0x2
 F_PRESERIALIZED = 0x4
 OF_TENSOR_CONTENT, OF_MULTI_CHUNK, OF_DIM_INFERRED, OF_HAS_UNKNOWN, OF_RANK0, OF_VARINT = 0x1, 0x2, 0x4, 0x8, 0x10, 0x20
 ORDER_GIVEN, ORDER_UPB, ORDER_BYTES = 0, 1, 2
-MAX_RANK, MAX_CHUNKS = 16, 8
+MAX_RANK, MAX_CHUNKS, FUSED_MAX_OUTPUTS = 16, 8, 8
 DT_HALF_REFQUIRK = -19
 
 
@@ -57,7 +57,7 @@ class Output(C.Structure):
         ("value_field", C.c_int32), ("n_chunks", C.c_int32), ("dims", C.c_int64 * MAX_RANK),
         ("chunk_off", C.c_uint64 * MAX_CHUNKS), ("chunk_len", C.c_uint64 * MAX_CHUNKS),
         ("content_off", C.c_uint64), ("content_len", C.c_uint64), ("msg_off", C.c_uint64), ("msg_len", C.c_uint64),
-        ("n_elems", C.c_uint64), ("dst_bytes", C.c_uint64), ("n_strings", C.c_uint64), ("status", C.c_int32),
+        ("n_elems", C.c_uint64), ("dst_bytes", C.c_uint64), ("n_strings", C.c_uint64), ("dst_off", C.c_uint64), ("status", C.c_int32),
         ("reserved", C.c_int32),
     ]
 
@@ -114,6 +114,13 @@ SIGNATURES = {
                                           C.POINTER(ModelSpec), _i32p]),
     "b200tfs_parse_tensor_protos": (C.c_int, [_vp, _vp, C.c_int32, _u64p, _u64p, C.POINTER(Output), _i32p]),
     "b200tfs_unpack_outputs": (C.c_int, [_vp, _vp, C.c_int32, C.POINTER(Output), _vpp, _i32p, _i32p]),
+    "b200tfs_decode_responses": (C.c_int, [_vp, _vp, C.c_int32, _u64p, _u64p, _vp, C.c_uint64]),
+    "b200tfs_decode_results": (C.c_int, [_vp, C.c_int32, C.POINTER(Output), _i32p, C.POINTER(ModelSpec), _i32p]),
+    "b200tfs_capture_begin": (C.c_int, [_vp]),
+    "b200tfs_capture_end": (C.c_int, [_vp, _vpp]),
+    "b200tfs_graph_launch": (C.c_int, [_vp, _vp]),
+    "b200tfs_graph_destroy": (C.c_int, [_vp]),
+    "b200tfs_wait_event": (C.c_int, [_vp, _vp]),
     "b200tfs_encode_requests_host": (C.c_int, [_vp, C.c_int32, C.POINTER(Request), _vp, C.c_uint64, _u64p, _u64p]),
     "b200tfs_encode_tensor_protos_host": (C.c_int, [_vp, C.c_int32, C.POINTER(Tensor), _vp, C.c_uint64, _u64p, _u64p]),
     "b200tfs_parse_responses_host": (C.c_int, [_vp, _vp, C.c_int32, _u64p, _u64p, C.c_int32, C.POINTER(Output), _i32p,

@@ -1,0 +1,202 @@
+"""Device-resident C-ABI paths: batched encode, fused single-launch decode, CUDA-graph replay.
+
+The checker is the CPU oracle (oracle/wire_oracle.py), itself pinned to the reference's goldens.
+"""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+from devutil import Dev, tensor_struct
+from min_tfs_client import _native as N
+from oracle import wire_oracle
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture()
+def dev():
+    d = Dev(0)
+    yield d
+    d.close()
+
+
+def _encode_requests_device(dev, batch, order=N.ORDER_UPB):
+    """batch: list of (model, version, [(key, ndarray)]); tensors uploaded first.  Returns list of wires."""
+    keep, reqs = [], []
+    for model, version, inputs in batch:
+        ts = []
+        for k, a in inputs:
+            t, dims = tensor_struct(dev.upload(a), a, key=k.encode())
+            keep.append((t, dims))
+            ts.append(t)
+        arr = (N.Tensor * max(len(ts), 1))(*ts)
+        keep.append(arr)
+        name = model.encode()
+        reqs.append(N.Request(model_name=name, model_name_len=len(name), has_version=int(version is not None), order=order,
+                              version=version or 0, n_inputs=len(ts), reserved=0, inputs=arr))
+    n = len(reqs)
+    rq = (N.Request * n)(*reqs)
+    flat = []
+    for r in reqs:
+        flat += [r.inputs[i] for i in range(r.n_inputs)]
+    need = C.c_uint64()
+    m = (N.Tensor * max(len(flat), 1))(*flat)
+    N.check(dev.lib.b200tfs_measure(dev.ctx, len(flat), m))
+    k = 0
+    for r in reqs:  # copy packed_len back into the request structs
+        for i in range(r.n_inputs):
+            r.inputs[i].packed_len = m[k].packed_len
+            k += 1
+    rq = (N.Request * n)(*reqs)
+    N.check(dev.lib.b200tfs_request_arena_size(n, rq, C.byref(need)))
+    arena = dev.malloc(need.value)
+    off = (C.c_uint64 * n)()
+    ln = (C.c_uint64 * n)()
+    N.check(dev.lib.b200tfs_encode_requests(dev.ctx, n, rq, arena, need.value, off, ln))
+    dev.sync()
+    whole = dev.download(arena, need.value)
+    return [whole[off[i]: off[i] + ln[i]].tobytes() for i in range(n)], (arena, off, ln)
+
+
+def test_c3_batch_encode_device(dev):
+    """256 requests {image fp32[3,224,224], label int64[1]} (BASELINE configs[2]) in one launch set."""
+    rng = np.random.default_rng(0)
+    base = rng.standard_normal((3, 224, 224), dtype=np.float32)
+    batch = []
+    for i in range(256):
+        img = base + np.float32(i)
+        batch.append(("default", 1, [("image", img), ("label", np.array([i % 1000], dtype=np.int64))]))
+    wires, _ = _encode_requests_device(dev, batch)
+    for i in (0, 1, 7, 128, 255):
+        expect = wire_oracle.encode_predict_request("default", 1, batch[i][2])
+        assert wires[i] == expect, i
+    assert len(wires[0]) == 602186  # SURVEY KAT-4
+
+
+def _decode_fused(dev, wires, dst_stride):
+    n = len(wires)
+    off = (C.c_uint64 * n)()
+    ln = (C.c_uint64 * n)()
+    cur = 0
+    for i, w in enumerate(wires):
+        off[i], ln[i] = cur, len(w)
+        cur += (len(w) + 255) & ~255
+    buf = np.zeros(cur + 256, dtype=np.uint8)
+    for i, w in enumerate(wires):
+        buf[off[i]: off[i] + len(w)] = np.frombuffer(w, dtype=np.uint8)
+    arena = dev.upload(buf)
+    dst = dev.malloc(dst_stride * n)
+    N.check(dev.lib.b200tfs_memset(dev.ctx, dst, 0xEE, dst_stride * n))
+    N.check(dev.lib.b200tfs_decode_responses(dev.ctx, arena, n, off, ln, dst, dst_stride))
+    outs = (N.Output * (n * N.FUSED_MAX_OUTPUTS))()
+    n_outs = (C.c_int32 * n)()
+    specs = (N.ModelSpec * n)()
+    status = (C.c_int32 * n)()
+    N.check(dev.lib.b200tfs_decode_results(dev.ctx, n, outs, n_outs, specs, status))
+    return buf, dst, outs, n_outs, specs, status
+
+
+def test_fused_decode_c2(dev):
+    x = np.random.default_rng(0).standard_normal((1024, 1024), dtype=np.float32)
+    x.reshape(-1)[:3] = np.array([0x7F800001, 0xFF800001, 0x7FC00001], dtype=np.uint32).view(np.float32)
+    wire = wire_oracle.build_predict_response([("y", x)], keep_snan=True)
+    buf, dst, outs, n_outs, specs, status = _decode_fused(dev, [wire], 4 << 20)
+    assert status[0] == 0 and n_outs[0] == 1
+    o = outs[0]
+    assert o.dtype == 1 and o.rank == 2 and o.dims[0] == 1024 and o.dims[1] == 1024 and o.status == 0
+    got = dev.download(dst + o.dst_off, o.dst_bytes).view(np.float32).reshape(1024, 1024)
+    ref = wire_oracle.decode_predict_response(wire)["y"]
+    assert got.tobytes() == ref.tobytes()
+    assert buf[specs[0].name_off: specs[0].name_off + specs[0].name_len].tobytes() == b"default" and specs[0].version == 1
+
+
+def test_fused_decode_batch_256(dev):
+    """256 responses {scores fp32[1000]} (BASELINE configs[2] outputs): the n > 16 table path."""
+    wires, refs = [], []
+    for i in range(256):
+        s = np.random.default_rng(10000 + i).standard_normal(1000, dtype=np.float32)
+        wires.append(wire_oracle.build_predict_response([("scores", s)]))
+        refs.append(s)
+    buf, dst, outs, n_outs, specs, status = _decode_fused(dev, wires, 4096)
+    whole = dev.download(dst, 4096 * 256)
+    for i in range(256):
+        assert status[i] == 0 and n_outs[i] == 1
+        o = outs[i * N.FUSED_MAX_OUTPUTS]
+        assert o.dst_off == i * 4096 and o.dst_bytes == 4000
+        assert whole[o.dst_off: o.dst_off + 4000].tobytes() == refs[i].tobytes(), i
+
+
+def test_fused_decode_mixed_and_errors(dev):
+    a = np.arange(12, dtype=np.float32).reshape(3, 4)
+    b = np.array([5, -6, 7], dtype=np.int64)
+    d = np.linspace(0, 1, 33)
+    good = wire_oracle.build_predict_response([("a", a), ("b", b), ("d", d)])
+    bad = good[:-3]
+    buf, dst, outs, n_outs, specs, status = _decode_fused(dev, [good, bad, b""], 1 << 16)
+    assert status[0] == 0 and n_outs[0] == 3
+    assert status[1] == N.E_PARSE
+    assert status[2] == 0 and n_outs[2] == 0
+    by_key = {}
+    for k in range(n_outs[0]):
+        o = outs[k]
+        by_key[buf[o.key_off: o.key_off + o.key_len].tobytes().decode()] = o
+    assert dev.download(dst + by_key["a"].dst_off, 48).tobytes() == a.tobytes()
+    assert dev.download(dst + by_key["d"].dst_off, 33 * 8).tobytes() == d.tobytes()
+    ob = by_key["b"]  # varint output: tabulated, not moved by the fused kernel
+    assert ob.flags & N.OF_VARINT and ob.n_elems == 3 and ob.dtype == 9
+    # ... and finished by the two-phase unpack
+    dptr = (C.c_void_p * 1)(dev.malloc(64))
+    st = (C.c_int32 * 1)()
+    o_arr = (N.Output * 1)(ob)
+    N.check(dev.lib.b200tfs_unpack_outputs(dev.ctx, dev.allocs[0] if False else _arena_of(dev, buf), 1, o_arr, dptr, None, st))
+    assert st[0] == 0 and dev.download(dptr[0], 24).view(np.int64).tolist() == [5, -6, 7]
+
+
+def _arena_of(dev, buf):
+    return dev.upload(buf)
+
+
+def test_graph_replay_encode_decode(dev):
+    """Capture encode + fused decode into a CUDA graph, refill the inputs, replay."""
+    lib = dev.lib
+    x = np.random.default_rng(1).standard_normal((256, 1024), dtype=np.float32)
+    src = dev.upload(x)
+    t, dims = tensor_struct(src, x, key=b"x")
+    ts = (N.Tensor * 1)(t)
+    rq = (N.Request * 1)(N.Request(model_name=b"m", model_name_len=1, has_version=1, order=N.ORDER_UPB, version=3, n_inputs=1,
+                                   reserved=0, inputs=ts))
+    need = C.c_uint64()
+    N.check(lib.b200tfs_request_arena_size(1, rq, C.byref(need)))
+    arena = dev.malloc(need.value)
+    off, ln = (C.c_uint64 * 1)(), (C.c_uint64 * 1)()
+    resp = wire_oracle.build_predict_response([("y", x)])
+    resp_dev = dev.upload(np.frombuffer(resp, dtype=np.uint8))
+    dst = dev.malloc(1 << 20)
+    p_off, p_len = (C.c_uint64 * 1)(0), (C.c_uint64 * 1)(len(resp))
+
+    def both():
+        N.check(lib.b200tfs_encode_requests(dev.ctx, 1, rq, arena, need.value, off, ln))
+        N.check(lib.b200tfs_decode_responses(dev.ctx, resp_dev, 1, p_off, p_len, dst, 1 << 20))
+
+    both()  # warm: sizes every scratch buffer
+    dev.sync()
+    N.check(lib.b200tfs_capture_begin(dev.ctx))
+    both()
+    g = C.c_void_p()
+    N.check(lib.b200tfs_capture_end(dev.ctx, C.byref(g)))
+    # new data in the same buffers, then replay
+    x2 = np.random.default_rng(2).standard_normal((256, 1024), dtype=np.float32)
+    N.check(lib.b200tfs_memcpy_h2d(dev.ctx, src, x2.ctypes.data, x2.nbytes))
+    resp2 = wire_oracle.build_predict_response([("y", x2)])
+    assert len(resp2) == len(resp)
+    r2 = np.frombuffer(resp2, dtype=np.uint8)
+    N.check(lib.b200tfs_memcpy_h2d(dev.ctx, resp_dev, r2.ctypes.data, r2.nbytes))
+    N.check(lib.b200tfs_memset(dev.ctx, arena, 0, need.value))
+    for _ in range(3):
+        N.check(lib.b200tfs_graph_launch(dev.ctx, g))
+    dev.sync()
+    wire = dev.download(arena + off[0], ln[0]).tobytes()
+    assert wire == wire_oracle.encode_predict_request("m", 3, [("x", x2)])
+    assert dev.download(dst, x2.nbytes).tobytes() == x2.tobytes()
+    lib.b200tfs_graph_destroy(g)
