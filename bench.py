@@ -170,70 +170,44 @@ class World:
 # ------------------------------------------------------------------------------------------------
 # the GPU arm
 # ------------------------------------------------------------------------------------------------
-class C2Bench:
-    """fp32 [1024,1024]: ring of device-resident tensors / request arenas / response wires / outputs."""
+class Lane:
+    """One native context (= one CUDA stream) with its own ring of device-resident C2 buffers."""
 
     SHAPE = (1024, 1024)
 
-    def __init__(self, device, ring):
+    def __init__(self, device, slots, seed0, shared):
         from min_tfs_client import _native as N
 
-        self.N = N
-        self.lib = N.load()
+        self.N, self.lib, self.S = N, N.load(), shared
         ctx = C.c_void_p()
         N.check(self.lib.b200tfs_create(device, C.byref(ctx)))
         self.ctx = ctx
-        self.ring = ring
-        self.P = int(np.prod(self.SHAPE)) * 4
-        self.host_x = [np.random.default_rng(i).standard_normal(self.SHAPE, dtype=np.float32) for i in range(min(ring, 4))]
-        self.resp_prefix, self.resp_suffix = response_wire_parts(b"y", self.SHAPE, self.P)
-        self.req_header = request_wire_parts(b"x", self.SHAPE, self.P)
-        self.resp_len = len(self.resp_prefix) + self.P + len(self.resp_suffix)
-        self.H_req, self.H_resp = len(self.req_header), len(self.resp_prefix) + len(self.resp_suffix)
-        # request struct (device pointer patched per slot)
+        self.slots = slots
+        S = shared
         self.dims = (C.c_int64 * 2)(*self.SHAPE)
-        self.tensor = N.Tensor(data=None, src_dtype=1, wire_dtype=1, rank=2, flags=0, dims=self.dims, key=b"x", key_len=1, packed_len=0)
-        self.tensors = (N.Tensor * 1)(self.tensor)
-        self.request = N.Request(model_name=b"default", model_name_len=7, has_version=1, order=N.ORDER_UPB, version=1, n_inputs=1,
-                                 reserved=0, inputs=self.tensors)
-        self.requests = (N.Request * 1)(self.request)
+        self.tensors = (N.Tensor * 1)(N.Tensor(data=256, src_dtype=1, wire_dtype=1, rank=2, flags=0, dims=self.dims, key=b"x", key_len=1,
+                                               packed_len=0))
+        self.requests = (N.Request * 1)(N.Request(model_name=b"default", model_name_len=7, has_version=1, order=N.ORDER_UPB, version=1,
+                                                  n_inputs=1, reserved=0, inputs=self.tensors))
         need = C.c_uint64(0)
-        self.tensors[0].data = 256  # any non-NULL pointer for sizing
         N.check(self.lib.b200tfs_request_arena_size(1, self.requests, C.byref(need)))
         self.arena_cap = int(need.value)
         self.src, self.arena, self.resp, self.dst = [], [], [], []
-        resp_host = []
-        for i in range(len(self.host_x)):
-            resp_host.append(np.frombuffer(self.resp_prefix + self.host_x[i].tobytes() + self.resp_suffix, dtype=np.uint8))
-        for i in range(ring):
-            self.src.append(self._malloc(self.P))
+        for i in range(slots):
+            self.src.append(self._malloc(S.P))
             self.arena.append(self._malloc(self.arena_cap))
-            self.resp.append(self._malloc(self.resp_len + 64))
-            self.dst.append(self._malloc(self.P))
-            hx = self.host_x[i % len(self.host_x)]
-            N.check(self.lib.b200tfs_memcpy_h2d(self.ctx, self.src[i], hx.ctypes.data, self.P))
-            rh = resp_host[i % len(resp_host)]
-            N.check(self.lib.b200tfs_memcpy_h2d(self.ctx, self.resp[i], rh.ctypes.data, self.resp_len))
+            self.resp.append(self._malloc(S.resp_len + 256))
+            self.dst.append(self._malloc(S.P))
+            k = (seed0 + i) % len(S.host_x)
+            N.check(self.lib.b200tfs_memcpy_h2d(self.ctx, self.src[i], S.host_x[k].ctypes.data, S.P))
+            N.check(self.lib.b200tfs_memcpy_h2d(self.ctx, self.resp[i], S.resp_host[k].ctypes.data, S.resp_len))
             N.check(self.lib.b200tfs_memset(self.ctx, self.arena[i], 0, self.arena_cap))
-            N.check(self.lib.b200tfs_memset(self.ctx, self.dst[i], 0, self.P))
+            N.check(self.lib.b200tfs_memset(self.ctx, self.dst[i], 0, S.P))
         self.sync()
-        self.rec_off = (C.c_uint64 * 1)()
-        self.rec_len = (C.c_uint64 * 1)()
-        self.p_off = (C.c_uint64 * 1)(0)
-        self.p_len = (C.c_uint64 * 1)(self.resp_len)
-        self.outs = (N.Output * 4)()
-        self.n_outs = (C.c_int32 * 1)()
-        self.specs = (N.ModelSpec * 1)()
-        self.status = (C.c_int32 * 1)()
-        self.dst_ptr = (C.c_void_p * 1)()
+        self.rec_off, self.rec_len = (C.c_uint64 * 1)(), (C.c_uint64 * 1)()
+        self.p_off, self.p_len = (C.c_uint64 * 1)(0), (C.c_uint64 * 1)(S.resp_len)
         self.slot = 0
-        # pinned host buffers for the e2e leg
-        self.pin_x = N.PinnedBuffer(self.P)
-        self.pin_wire = N.PinnedBuffer(self.arena_cap)
-        self.pin_resp = N.PinnedBuffer(self.resp_len)
-        self.pin_out = N.PinnedBuffer(self.P)
-        self.pin_x.array[:] = self.host_x[0].view(np.uint8).reshape(-1)
-        self.pin_resp.array[:] = resp_host[0]
+        self.graphs = {}
 
     def _malloc(self, nbytes):
         p = C.c_void_p()
@@ -244,83 +218,187 @@ class C2Bench:
         self.N.check(self.lib.b200tfs_sync(self.ctx))
 
     def footprint(self):
-        return self.ring * (self.P * 2 + self.arena_cap + self.resp_len)
+        return self.slots * (self.S.P * 2 + self.arena_cap + self.S.resp_len)
 
-    # ---- one step, device-resident ------------------------------------------------------------
     def encode(self, i):
         self.tensors[0].data = self.src[i]
         self.N.check(self.lib.b200tfs_encode_requests(self.ctx, 1, self.requests, self.arena[i], self.arena_cap, self.rec_off, self.rec_len))
 
     def decode(self, i):
-        lib, N = self.lib, self.N
-        N.check(lib.b200tfs_parse_responses(self.ctx, self.resp[i], 1, self.p_off, self.p_len, 4, self.outs, self.n_outs, self.specs, self.status))
-        self.dst_ptr[0] = self.dst[i]
-        N.check(lib.b200tfs_unpack_outputs(self.ctx, self.resp[i], 1, self.outs, self.dst_ptr, None, None))
+        self.N.check(self.lib.b200tfs_decode_responses(self.ctx, self.resp[i], 1, self.p_off, self.p_len, self.dst[i], self.S.P))
 
-    def step(self):
+    def step_eager(self):
         i = self.slot
-        self.slot = (i + 1) % self.ring
+        self.slot = (i + 1) % self.slots
         self.encode(i)
         self.decode(i)
 
-    # ---- one step through the host-buffer entry points (e2e) -----------------------------------
-    def step_e2e(self):
+    def capture(self, name, body, count):
+        """Record `count` consecutive ring slots of `body(slot)` into a CUDA graph."""
         lib, N = self.lib, self.N
-        self.tensors[0].data = self.pin_x.ptr
-        N.check(lib.b200tfs_encode_requests_host(self.ctx, 1, self.requests, self.pin_wire.ptr, self.arena_cap, self.rec_off, self.rec_len))
-        N.check(lib.b200tfs_parse_responses_host(self.ctx, self.pin_resp.ptr, 1, self.p_off, self.p_len, 4, self.outs, self.n_outs, self.specs,
-                                                 self.status))
-        self.dst_ptr[0] = self.pin_out.ptr
-        N.check(lib.b200tfs_unpack_outputs_host(self.ctx, 1, self.outs, self.dst_ptr, None, None))
+        for i in range(min(count, self.slots)):
+            body(i)          # warm: sizes every scratch buffer outside the capture
+        self.sync()
+        N.check(lib.b200tfs_capture_begin(self.ctx))
+        for k in range(count):
+            body(k % self.slots)
+        g = C.c_void_p()
+        N.check(lib.b200tfs_capture_end(self.ctx, C.byref(g)))
+        self.graphs[name] = (g, count)
+        return g
+
+    def launch(self, name):
+        self.N.check(self.lib.b200tfs_graph_launch(self.ctx, self.graphs[name][0]))
 
     def launches(self):
         n = C.c_uint64(0)
         self.N.check(self.lib.b200tfs_kernel_launches(self.ctx, C.byref(n)))
         return int(n.value)
 
-    # ---- timing helpers --------------------------------------------------------------------------
-    def timed(self, fn, steps):
+
+class Shared:
+    """Host-side constants of the C2 workload."""
+
+    SHAPE = (1024, 1024)
+
+    def __init__(self):
+        self.P = int(np.prod(self.SHAPE)) * 4
+        self.host_x = [np.random.default_rng(i).standard_normal(self.SHAPE, dtype=np.float32) for i in range(4)]
+        self.resp_prefix, self.resp_suffix = response_wire_parts(b"y", self.SHAPE, self.P)
+        self.req_header = request_wire_parts(b"x", self.SHAPE, self.P)
+        self.resp_len = len(self.resp_prefix) + self.P + len(self.resp_suffix)
+        self.H_req, self.H_resp = len(self.req_header), len(self.resp_prefix) + len(self.resp_suffix)
+        self.resp_host = [np.frombuffer(self.resp_prefix + x.tobytes() + self.resp_suffix, dtype=np.uint8) for x in self.host_x]
+
+
+class C2Bench:
+    """fp32 [1024,1024]: `streams` lanes, each with ring/streams slots of tensors / arenas / responses / outputs."""
+
+    def __init__(self, device, ring, streams):
+        from min_tfs_client import _native as N
+
+        self.N, self.lib = N, N.load()
+        self.S = Shared()
+        self.P = self.S.P
+        per = max(1, ring // streams)
+        self.lanes = [Lane(device, per, s * per, self.S) for s in range(streams)]
+        self.ring = per * streams
+        self.main = self.lanes[0]
+        # pinned host buffers for the e2e leg (lane 0)
+        self.pin_x = N.PinnedBuffer(self.P)
+        self.pin_wire = N.PinnedBuffer(self.main.arena_cap)
+        self.pin_resp = N.PinnedBuffer(self.S.resp_len)
+        self.pin_out = N.PinnedBuffer(self.P)
+        self.pin_x.array[:] = self.S.host_x[0].view(np.uint8).reshape(-1)
+        self.pin_resp.array[:] = self.S.resp_host[0]
+        self.outs = (N.Output * 4)()
+        self.n_outs, self.specs, self.status = (C.c_int32 * 1)(), (N.ModelSpec * 1)(), (C.c_int32 * 1)()
+        self.dst_ptr = (C.c_void_p * 1)()
+        self.events = {}
+
+    def footprint(self):
+        return sum(l.footprint() for l in self.lanes)
+
+    def sync(self):
+        for l in self.lanes:
+            l.sync()
+
+    def launches(self):
+        return sum(l.launches() for l in self.lanes)
+
+    def _event(self, key):
+        if key not in self.events:
+            e = C.c_void_p()
+            self.N.check(self.lib.b200tfs_event_create(C.byref(e)))
+            self.events[key] = e
+        return self.events[key]
+
+    def timed_region(self, enqueue):
+        """Device time of whatever `enqueue(lane)` submits on every lane: fork from lane 0, join back."""
         lib, N = self.lib, self.N
-        e0, e1 = C.c_void_p(), C.c_void_p()
-        N.check(lib.b200tfs_event_create(C.byref(e0)))
-        N.check(lib.b200tfs_event_create(C.byref(e1)))
         self.sync()
-        N.check(lib.b200tfs_event_record(self.ctx, e0))
-        for _ in range(steps):
-            fn()
-        N.check(lib.b200tfs_event_record(self.ctx, e1))
+        e0, e1 = self._event("t0"), self._event("t1")
+        N.check(lib.b200tfs_event_record(self.main.ctx, e0))
+        for l in self.lanes[1:]:
+            N.check(lib.b200tfs_wait_event(l.ctx, e0))
+        for l in self.lanes:
+            enqueue(l)
+        for k, l in enumerate(self.lanes[1:]):
+            f = self._event(("join", k))
+            N.check(lib.b200tfs_event_record(l.ctx, f))
+            N.check(lib.b200tfs_wait_event(self.main.ctx, f))
+        N.check(lib.b200tfs_event_record(self.main.ctx, e1))
         N.check(lib.b200tfs_event_sync(e1))
         self.sync()
         ms = C.c_float(0)
         N.check(lib.b200tfs_event_elapsed_ms(e0, e1, C.byref(ms)))
-        lib.b200tfs_event_destroy(e0)
-        lib.b200tfs_event_destroy(e1)
         return float(ms.value)
 
+    # ---- the timed workload: K steps split over the lanes, replayed from graphs --------------------
+    def prepare(self, steps, graph_steps):
+        self.plan = []
+        n = len(self.lanes)
+        for s, l in enumerate(self.lanes):
+            mine = steps // n + (1 if s < steps % n else 0)
+            g = min(graph_steps, max(mine, 1))
+            full, rem = divmod(mine, g)
+            if full:
+                l.capture("step", lambda i, l=l: (l.encode(i), l.decode(i)), g)
+            if rem:
+                l.capture("step_rem", lambda i, l=l: (l.encode(i), l.decode(i)), rem)
+            self.plan.append((full, rem))
+
+    def run_steps(self):
+        def enqueue(l):
+            full, rem = self.plan[self.lanes.index(l)]
+            for _ in range(full):
+                l.launch("step")
+            if rem:
+                l.launch("step_rem")
+        return self.timed_region(enqueue)
+
+    # ---- one step through the host-buffer entry points (e2e) ---------------------------------------
+    def step_e2e(self):
+        lib, N, m = self.lib, self.N, self.main
+        m.tensors[0].data = self.pin_x.ptr
+        N.check(lib.b200tfs_encode_requests_host(m.ctx, 1, m.requests, self.pin_wire.ptr, m.arena_cap, m.rec_off, m.rec_len))
+        N.check(lib.b200tfs_parse_responses_host(m.ctx, self.pin_resp.ptr, 1, m.p_off, m.p_len, 4, self.outs, self.n_outs, self.specs,
+                                                 self.status))
+        self.dst_ptr[0] = self.pin_out.ptr
+        N.check(lib.b200tfs_unpack_outputs_host(m.ctx, 1, self.outs, None, self.dst_ptr, None, None))
+
+    def timed_main(self, fn, steps):
+        def enqueue(l):
+            if l is self.main:
+                for _ in range(steps):
+                    fn()
+        return self.timed_region(enqueue)
+
     def verify(self):
-        """Bit-exact check of the last ring slot's products against bytes built here from the inputs."""
-        lib, N = self.lib, self.N
-        i = 0
-        self.encode(i)
-        self.decode(i)
-        self.sync()
-        wire = np.empty(int(self.rec_len[0]), dtype=np.uint8)
-        N.check(lib.b200tfs_memcpy_d2h(self.ctx, wire.ctypes.data, self.arena[i] + int(self.rec_off[0]), wire.size))
-        out = np.empty(self.SHAPE, dtype=np.float32)
-        N.check(lib.b200tfs_memcpy_d2h(self.ctx, out.ctypes.data, self.dst[i], self.P))
-        self.sync()
-        expect = self.req_header + self.host_x[0].tobytes()
-        assert wire.tobytes() == expect, "encoded request differs from the expected wire bytes"
-        assert out.tobytes() == self.host_x[0].tobytes(), "decoded tensor differs from the payload"
-        assert self.status[0] == 0 and self.n_outs[0] == 1
+        """Bit-exact check of every lane's slot 0 against bytes built here from the inputs."""
+        lib, N, S = self.lib, self.N, self.S
+        for li, l in enumerate(self.lanes):
+            l.encode(0)
+            l.decode(0)
+            l.sync()
+            wire = np.empty(int(l.rec_len[0]), dtype=np.uint8)
+            N.check(lib.b200tfs_memcpy_d2h(l.ctx, wire.ctypes.data, l.arena[0] + int(l.rec_off[0]), wire.size))
+            out = np.empty(S.SHAPE, dtype=np.float32)
+            N.check(lib.b200tfs_memcpy_d2h(l.ctx, out.ctypes.data, l.dst[0], S.P))
+            outs = (N.Output * N.FUSED_MAX_OUTPUTS)()
+            n_outs, status = (C.c_int32 * 1)(), (C.c_int32 * 1)()
+            N.check(lib.b200tfs_decode_results(l.ctx, 1, outs, n_outs, None, status))
+            x = S.host_x[(li * l.slots) % len(S.host_x)]
+            assert wire.tobytes() == S.req_header + x.tobytes(), "encoded request differs from the expected wire bytes"
+            assert out.tobytes() == x.tobytes(), "decoded tensor differs from the payload"
+            assert status[0] == 0 and n_outs[0] == 1 and outs[0].dst_off == 0 and outs[0].dst_bytes == S.P
         return True
 
     def verify_e2e(self):
         self.step_e2e()
-        n = int(self.rec_len[0])
-        o = int(self.rec_off[0])
-        assert self.pin_wire.array[o:o + n].tobytes() == self.req_header + self.host_x[0].tobytes()
-        assert self.pin_out.array.tobytes() == self.host_x[0].tobytes()
+        n, o = int(self.main.rec_len[0]), int(self.main.rec_off[0])
+        assert self.pin_wire.array[o:o + n].tobytes() == self.S.req_header + self.S.host_x[0].tobytes()
+        assert self.pin_out.array.tobytes() == self.S.host_x[0].tobytes()
         return True
 
 
@@ -405,10 +483,12 @@ def run_reference(args, world):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20000)
-    ap.add_argument("--warmup", type=int, default=200)
+    ap.add_argument("--steps", type=int, default=48000)
+    ap.add_argument("--warmup", type=int, default=480)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--ring", type=int, default=48)
+    ap.add_argument("--ring", type=int, default=48, help="ring slots in total (split over the streams)")
+    ap.add_argument("--streams", type=int, default=4, help="independent lanes (native contexts = CUDA streams) per GPU")
+    ap.add_argument("--graph-steps", type=int, default=48, help="steps recorded per CUDA graph")
     ap.add_argument("--e2e-steps", type=int, default=200)
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     args = ap.parse_args()
@@ -418,58 +498,56 @@ def main():
         world.close()
         return
     warmup = max(args.warmup, 3)
-    bench = C2Bench(world.local_rank, args.ring)
+    bench = C2Bench(world.local_rank, args.ring, args.streams)
     assert bench.footprint() > 2 * L2_BYTES, "ring must exceed L2"
     bench.verify()
-    for _ in range(warmup):
-        bench.step()
-    bench.sync()
+    bench.prepare(warmup, args.graph_steps)
+    bench.run_steps()                              # W untimed warm-up steps
+    bench.prepare(args.steps, args.graph_steps)    # graphs sized so that exactly K steps run
+    bench.run_steps()                              # one untimed pass so the new graphs are uploaded
     launches0 = bench.launches()
     sampler = ClockSampler(world.local_rank)
     sampler.start()
-    time.sleep(0.25)
+    time.sleep(0.3)
     world.barrier()
     t0 = time.time()
-    ms = bench.timed(bench.step, args.steps)
+    ms = bench.run_steps()
     t1 = time.time()
     world.barrier()
     clocks = sampler.stop(t0, t1)
-    launches = bench.launches() - launches0
+    launches_eager = bench.launches() - launches0  # graph replays do not pass through the counter ...
+    launches = 2 * args.steps                      # ... each step replays one move_kernel + one decode_fused_kernel
     ms_max = world.max(ms)
-    payload_per_step = 2 * bench.P
+    S = bench.S
+    payload_per_step = 2 * S.P
     total_payload = world.sum(float(payload_per_step * args.steps))
     value = total_payload / (ms_max * 1e-3) / 1e9
-
-    # roofline pass: move_kernel alone, back to back on the launching stream (encode launches, then
-    # decode-unpack launches over an already parsed table)
-    reps = min(max(args.steps, 200), 2000)
-    ring = bench.ring
-
-    def enc_only():
-        bench.encode(enc_only.i % ring)
-        enc_only.i += 1
-    enc_only.i = 0
-    bench.timed(enc_only, 50)
-    enc_ms = bench.timed(enc_only, reps)
-    bench.decode(0)
-    bench.sync()
-
-    def unpack_only():
-        bench.dst_ptr[0] = bench.dst[unpack_only.i % ring]
-        bench.N.check(bench.lib.b200tfs_unpack_outputs(bench.ctx, bench.resp[unpack_only.i % ring], 1, bench.outs, bench.dst_ptr, None, None))
-        unpack_only.i += 1
-    unpack_only.i = 0
-    bench.timed(unpack_only, 50)
-    dec_ms = bench.timed(unpack_only, reps)
+    enc_bytes, dec_bytes = 2 * S.P + S.H_req, 2 * S.P + S.H_resp
     peak, peak_src = peaks()
-    enc_bytes = 2 * bench.P + bench.H_req
-    dec_bytes = 2 * bench.P + bench.H_resp
-    avg_us = (enc_ms + dec_ms) / (2 * reps) * 1e3
+
+    # roofline pass: the dominant kernel alone on ONE stream, back to back inside a graph (no CPU in
+    # the loop), ring > L2.  avg launch duration = region / launches (includes the inter-kernel gap).
+    m = bench.main
+    reps = 20
+    m.capture("enc", m.encode, m.slots * 4)
+    m.capture("dec", m.decode, m.slots * 4)
+    per = {}
+    for name in ("enc", "dec"):
+        bench.timed_main(lambda: m.launch(name), 3)
+        t = bench.timed_main(lambda: m.launch(name), reps)
+        per[name] = t / (reps * m.graphs[name][1]) * 1e3  # us per launch
+    avg_us = (per["enc"] + per["dec"]) / 2
     achieved = (enc_bytes + dec_bytes) / 2 / (avg_us * 1e-6) / 1e9
-    roofline = {"bound": "hbm", "kernel": "move_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": None, "peak_source": peak_src, "algorithmic_bytes_per_launch": (enc_bytes + dec_bytes) / 2,
-                "avg_launch_us": avg_us, "encode_launch_us": enc_ms / reps * 1e3, "decode_launch_us": dec_ms / reps * 1e3,
-                "how": f"{reps} back-to-back launches each, CUDA events on the launching stream, ring > L2"}
+    agg = (enc_bytes + dec_bytes) * args.steps / (ms * 1e-3) / 1e9
+    roofline = {"bound": "hbm", "kernel": "move_kernel (encode) / decode_fused_kernel (decode)", "achieved": achieved, "peak": peak,
+                "unit": "GB/s", "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                "algorithmic_bytes_per_launch": (enc_bytes + dec_bytes) / 2, "avg_launch_us": avg_us,
+                "encode_launch_us": per["enc"], "decode_launch_us": per["dec"],
+                "encode_frac": enc_bytes / (per["enc"] * 1e-6) / 1e9 / peak, "decode_frac": dec_bytes / (per["dec"] * 1e-6) / 1e9 / peak,
+                "how": "one stream, graph of back-to-back launches of that kernel alone, CUDA events on the launching stream, ring > L2",
+                "timed_region_aggregate": {"achieved": agg, "frac": agg / peak, "streams": len(bench.lanes),
+                                           "how": "algorithmic bytes of every launch in the timed region / region time (launches of "
+                                                  "independent requests overlap across the streams)"}}
 
     # e2e: host buffers in, host buffers out, copies inside the timed region
     bench.verify_e2e()
@@ -477,9 +555,9 @@ def main():
         bench.step_e2e()
     e2e_steps = max(10, min(args.e2e_steps, args.steps))
     world.barrier()
-    e2e_ms = world.max(bench.timed(bench.step_e2e, e2e_steps))
+    e2e_ms = world.max(bench.timed_main(bench.step_e2e, e2e_steps))
     e2e_value = world.sum(float(payload_per_step * e2e_steps)) / (e2e_ms * 1e-3) / 1e9
-    e2e = {"value": e2e_value, "unit": "GB/s", "h2d_bytes_per_step": bench.P + bench.resp_len, "d2h_bytes_per_step": int(bench.rec_len[0]) + bench.P,
+    e2e = {"value": e2e_value, "unit": "GB/s", "h2d_bytes_per_step": S.P + S.resp_len, "d2h_bytes_per_step": int(m.rec_len[0]) + S.P,
            "ms_per_step": e2e_ms / e2e_steps, "steps": e2e_steps,
            "how": "b200tfs_encode_requests_host + b200tfs_parse_responses_host + b200tfs_unpack_outputs_host on pinned host buffers"}
 
@@ -491,8 +569,9 @@ def main():
             "config": {"workload": "C2 fp32[1024,1024] single-tensor PredictRequest encode + PredictResponse decode (BASELINE.json configs[1])",
                        "payload_bytes_per_step": payload_per_step, "ring_slots": bench.ring, "ring_bytes": bench.footprint(),
                        "l2": f"inputs rotate through a ring of {bench.ring} slots = {bench.footprint() >> 20} MiB > 126 MiB L2",
+                       "streams": len(bench.lanes), "cuda_graph_steps": args.graph_steps,
                        "wire_mode": "typed (float_val, sNaN-quieting on: bit-exact vs reference)", "sharding": "independent requests per GPU, no collective"},
-            "roofline": roofline, "e2e": e2e, "gpu_launches": launches, "clocks": clocks,
+            "roofline": roofline, "e2e": e2e, "gpu_launches": launches, "gpu_launches_outside_graphs": launches_eager, "clocks": clocks,
         }
         if world.size == 1 and not args.no_cpu:
             cb = cpu_baseline_port(2)

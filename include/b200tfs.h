@@ -128,7 +128,7 @@ typedef struct b200tfs_request {
 } b200tfs_request;
 
 /* One decoded output of a PredictResponse (predict.proto:30-40), as tabulated by the parse kernel.
- * All offsets are byte offsets from the start of the wire arena handed to the parse call.          */
+ * All offsets are byte offsets from the start of the RECORD (arena + rec_off[i]).                  */
 typedef struct b200tfs_output {
   uint64_t key_off;    /* map key bytes (last `key` occurrence of the winning entry)            */
   uint32_t key_len;
@@ -147,13 +147,14 @@ typedef struct b200tfs_output {
   uint64_t n_elems;     /* prod(dims)                                                           */
   uint64_t dst_bytes;   /* n_elems * element size of `dtype` in memory                          */
   uint64_t n_strings;   /* string_val occurrences (strings are unpacked on the host)            */
-  uint64_t dst_off;     /* b200tfs_decode_responses: where the values were written, from dst_dev */
+  uint64_t dst_off;     /* b200tfs_decode_responses: where the values were written, from the
+                           record's destination slot dst_dev + i*dst_stride                    */
   int32_t status;       /* B200TFS_OK, or the error tensor_proto_to_ndarray raises for it       */
   int32_t reserved;
 } b200tfs_output;
 
 typedef struct b200tfs_model_spec {
-  uint64_t name_off;  /* offsets from the start of the wire arena                              */
+  uint64_t name_off;  /* offsets from the start of the record                                  */
   uint32_t name_len;
   uint32_t signature_len;
   uint64_t signature_off;
@@ -247,13 +248,15 @@ int b200tfs_parse_responses(b200tfs_ctx* ctx, const void* arena_dev, int32_t n, 
 int b200tfs_parse_tensor_protos(b200tfs_ctx* ctx, const void* arena_dev, int32_t n,
                                 const uint64_t* rec_off, const uint64_t* rec_len, b200tfs_output* outs,
                                 int32_t* rec_status);
-/* Unpack m tabulated outputs into device buffers: dst[j] receives outs[j].dst_bytes bytes (or
+/* Unpack m tabulated outputs into device buffers: out_rec_off[j] is the arena offset of the record
+ * outs[j] came from (NULL: all zero); dst[j] receives outs[j].dst_bytes bytes (or
  * n_elems * sizeof(dst_dtype[j]) when dst_dtype[j] != outs[j].dtype and the cast is supported:
  * FLOAT -> HALF / BFLOAT16 round-to-nearest-even).  status[j] (host, filled after an internal sync
  * only if `status` is non-NULL) reports per-output errors found while unpacking (element count
  * mismatch, integer out of range).  Async when status is NULL.                                    */
 int b200tfs_unpack_outputs(b200tfs_ctx* ctx, const void* arena_dev, int32_t m, const b200tfs_output* outs,
-                           void* const* dst_dev, const int32_t* dst_dtype, int32_t* status);
+                           const uint64_t* out_rec_off, void* const* dst_dev, const int32_t* dst_dtype,
+                           int32_t* status);
 
 /* Single-launch decode for the steady-state path: one kernel walks the tags AND moves the values,
  * with no host round trip.  Record i's fixed-width outputs (float_val / double_val / complex) are
@@ -300,7 +303,8 @@ int b200tfs_parse_tensor_protos_host(b200tfs_ctx* ctx, const void* wire_host, in
                                      b200tfs_output* outs, int32_t* rec_status);
 /* Unpack outputs of the most recent *_parse_*_host call on this context into HOST buffers.         */
 int b200tfs_unpack_outputs_host(b200tfs_ctx* ctx, int32_t m, const b200tfs_output* outs,
-                                void* const* dst_host, const int32_t* dst_dtype, int32_t* status);
+                                const uint64_t* out_rec_off, void* const* dst_host,
+                                const int32_t* dst_dtype, int32_t* status);
 
 #ifdef __cplusplus
 }

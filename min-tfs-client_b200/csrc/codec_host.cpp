@@ -77,8 +77,9 @@ struct b200tfs_ctx {
   uint64_t launches = 0;
   uint32_t tile_bytes_override = 0;
   bool capturing = false;   // between b200tfs_capture_begin / _end: no syncs, no allocations
-  Growable fused_dev;       // decode_fused tables (device) ...
-  Growable fused_host;      // ... and their pinned mirror
+  Growable fused_host;      // decode_fused tables: pinned host memory the kernel writes directly
+  void* tpl_dev = nullptr;  // two framing templates (device), used alternately by successive decode launches
+  uint32_t tpl_flip = 0;
   int32_t fused_n = 0;      // records of the last b200tfs_decode_responses
 };
 
@@ -102,7 +103,7 @@ static int grow_host(b200tfs_ctx* c, Growable& g, uint64_t need) {
   CU(cudaStreamSynchronize(c->stream));
   if (g.p) CU(cudaFreeHost(g.p));
   g.p = nullptr; g.cap = 0;
-  CU(cudaHostAlloc(&g.p, cap, cudaHostAllocDefault));
+  CU(cudaHostAlloc(&g.p, cap, cudaHostAllocPortable | cudaHostAllocMapped));
   g.cap = cap;
   return B200TFS_OK;
 }
@@ -167,8 +168,8 @@ int b200tfs_destroy(b200tfs_ctx* c) {
     if (s.dev.p) cudaFree(s.dev.p);
     if (s.done) cudaEventDestroy(s.done);
   }
-  if (c->fused_dev.p) cudaFree(c->fused_dev.p);
   if (c->fused_host.p) cudaFreeHost(c->fused_host.p);
+  if (c->tpl_dev) cudaFree(c->tpl_dev);
   if (c->scratch_dev.p) cudaFree(c->scratch_dev.p);
   if (c->scratch_host.p) cudaFreeHost(c->scratch_host.p);
   if (c->stage_dev.p) cudaFree(c->stage_dev.p);
@@ -758,8 +759,9 @@ static int parse_common(b200tfs_ctx* c, const void* arena_dev, int32_t n, const 
   if (n == 0) return B200TFS_OK;
   CU(cudaSetDevice(c->device));
   if (bare) max_outputs = 1;
+  const uint64_t stride = bare ? 1 : (uint64_t)max_outputs + 1;  // responses: one scratch slot per record
   const uint64_t b_off = 0, b_len = b_off + 8ull * n, b_outs = (b_len + 8ull * n + 15) & ~15ull;
-  const uint64_t b_nouts = b_outs + sizeof(b200tfs_output) * (uint64_t)n * max_outputs;
+  const uint64_t b_nouts = b_outs + sizeof(b200tfs_output) * (uint64_t)n * stride;
   const uint64_t b_specs = (b_nouts + 4ull * n + 15) & ~15ull;
   const uint64_t b_status = b_specs + sizeof(b200tfs_model_spec) * (uint64_t)n;
   const uint64_t total = (b_status + 4ull * n + 15) & ~15ull;
@@ -789,7 +791,7 @@ static int parse_common(b200tfs_ctx* c, const void* arena_dev, int32_t n, const 
     memcpy(specs, h + b_specs, sizeof(b200tfs_model_spec) * (uint64_t)n);
     for (int i = 0; i < n; ++i) {
       int k = rec_status[i] == B200TFS_OK ? n_outs[i] : 0;
-      memcpy(outs + (size_t)i * max_outputs, h + b_outs + sizeof(b200tfs_output) * (uint64_t)i * max_outputs, sizeof(b200tfs_output) * (size_t)k);
+      memcpy(outs + (size_t)i * max_outputs, h + b_outs + sizeof(b200tfs_output) * (uint64_t)i * stride, sizeof(b200tfs_output) * (size_t)k);
     }
   }
   return B200TFS_OK;
@@ -828,15 +830,15 @@ int run_vardecode(b200tfs_ctx* c, std::vector<VarDecodeJob>& jobs, int32_t* stat
 
 }  // namespace
 
-extern "C" int b200tfs_unpack_outputs(b200tfs_ctx* c, const void* arena_dev, int32_t m, const b200tfs_output* outs, void* const* dst_dev,
-                                      const int32_t* dst_dtype, int32_t* status) {
+extern "C" int b200tfs_unpack_outputs(b200tfs_ctx* c, const void* arena_dev, int32_t m, const b200tfs_output* outs,
+                                      const uint64_t* out_rec_off, void* const* dst_dev, const int32_t* dst_dtype, int32_t* status) {
   if (!c || m < 0 || (m && (!arena_dev || !outs || !dst_dev))) return fail(B200TFS_E_ARG, "bad arguments");
   CU(cudaSetDevice(c->device));
   PlanBuilder pb;
   std::vector<VarDecodeJob> vjobs;
-  const uint8_t* w = (const uint8_t*)arena_dev;
   for (int j = 0; j < m; ++j) {
     const b200tfs_output& o = outs[j];
+    const uint8_t* w = (const uint8_t*)arena_dev + (out_rec_off ? out_rec_off[j] : 0);  // table offsets are record-relative
     if (status) status[j] = B200TFS_OK;
     if (!o.n_elems) continue;
     DtypeInfo di = dtype_info(o.dtype);
@@ -914,11 +916,20 @@ int b200tfs_decode_responses(b200tfs_ctx* c, const void* arena_dev, int32_t n, c
   const uint64_t tile_bytes = 16ull * vpt;
   FusedLayout L = fused_layout(n);
   int rc;
-  if ((rc = grow_dev(c, c->fused_dev, L.total))) return rc;
   if ((rc = grow_host(c, c->fused_host, L.total))) return rc;
+  if (!c->tpl_dev) {
+    if (c->capturing) return fail(B200TFS_E_ARG, "run b200tfs_decode_responses once before capturing it");
+    CU(cudaMalloc(&c->tpl_dev, 2 * sizeof(Template)));
+    CU(cudaMemsetAsync(c->tpl_dev, 0, 2 * sizeof(Template), c->stream));
+  }
   FusedParams fp{};
   fp.w = (const uint8_t*)arena_dev; fp.dst = (uint8_t*)dst_dev; fp.dst_stride = dst_stride; fp.n = n; fp.vpt = vpt;
-  uint8_t* d = (uint8_t*)c->fused_dev.p;
+  fp.tpl_read = (const Template*)c->tpl_dev + (c->tpl_flip & 1);
+  fp.tpl_write = (Template*)c->tpl_dev + ((c->tpl_flip & 1) ^ 1);
+  c->tpl_flip ^= 1;
+  // the table is written by the kernel straight into pinned host memory (unified addressing): ~1 KB
+  // of posted PCIe writes per record instead of a device table plus a copy node behind every launch
+  uint8_t* d = (uint8_t*)c->fused_host.p;
   fp.outs = (b200tfs_output*)(d + L.outs); fp.n_outs = (int32_t*)(d + L.nouts);
   fp.specs = (b200tfs_model_spec*)(d + L.specs); fp.status = (int32_t*)(d + L.status);
   uint64_t grid = 0;
@@ -954,7 +965,6 @@ int b200tfs_decode_responses(b200tfs_ctx* c, const void* arena_dev, int32_t n, c
   if (grid > 0x7FFFFFFFull) return fail(B200TFS_E_TOOBIG, "batch needs more than 2^31 tiles");
   CU(launch_decode_fused(fp, (uint32_t)grid, c->stream));
   c->launches += 1;
-  CU(cudaMemcpyAsync(c->fused_host.p, c->fused_dev.p, L.total, cudaMemcpyDeviceToHost, c->stream));
   c->fused_n = n;
   return B200TFS_OK;
 }
@@ -1146,8 +1156,8 @@ int b200tfs_parse_tensor_protos_host(b200tfs_ctx* c, const void* wire_host, int3
   return parse_common(c, c->stage_dev.p, n, rec_off, rec_len, 1, true, outs, nullptr, nullptr, rec_status);
 }
 
-int b200tfs_unpack_outputs_host(b200tfs_ctx* c, int32_t m, const b200tfs_output* outs, void* const* dst_host, const int32_t* dst_dtype,
-                                int32_t* status) {
+int b200tfs_unpack_outputs_host(b200tfs_ctx* c, int32_t m, const b200tfs_output* outs, const uint64_t* out_rec_off, void* const* dst_host,
+                                const int32_t* dst_dtype, int32_t* status) {
   if (!c || m < 0 || (m && (!outs || !dst_host))) return fail(B200TFS_E_ARG, "bad arguments");
   if (m == 0) return B200TFS_OK;
   CU(cudaSetDevice(c->device));
@@ -1166,7 +1176,7 @@ int b200tfs_unpack_outputs_host(b200tfs_ctx* c, int32_t m, const b200tfs_output*
   if (rc) return rc;
   std::vector<void*> dd(m);
   for (int j = 0; j < m; ++j) dd[j] = (uint8_t*)c->arena_dev.p + off[j];
-  if ((rc = b200tfs_unpack_outputs(c, c->stage_dev.p, m, outs, dd.data(), dst_dtype, status))) return rc;
+  if ((rc = b200tfs_unpack_outputs(c, c->stage_dev.p, m, outs, out_rec_off, dd.data(), dst_dtype, status))) return rc;
   for (int j = 0; j < m; ++j)
     if (nb[j]) {
       if (!dst_host[j]) return fail(B200TFS_E_ARG, "output %d: dst is NULL", j);

@@ -388,10 +388,12 @@ __global__ void __launch_bounds__(32) parse_responses_kernel(const uint8_t* __re
   __shared__ __align__(16) uint8_t lines[32][256];
   int r = blockIdx.x * blockDim.x + threadIdx.x;
   if (r >= n) return;
-  Win win; win.buf = lines[threadIdx.x];
-  win_prefetch(&win, w, rec_off[r], rec_len[r]);
+  const uint64_t off = rec_off[r], len = rec_len[r];
+  if (len > 0x7FFFFFFFull) { status[r] = B200TFS_E_PARSE; n_outs[r] = 0; return; }
+  Cursor c;
+  cur_open(c, w + off, (uint32_t)len, lines[threadIdx.x]);
   int cnt = 0;
-  status[r] = walk_response(w, rec_off[r], rec_len[r], max_outputs, outs + (size_t)r * max_outputs, &cnt, specs + r, &win);
+  status[r] = walk_response(c, max_outputs, outs + (size_t)r * (max_outputs + 1), &cnt, specs + r);  // +1: scratch slot
   n_outs[r] = cnt;
 }
 
@@ -401,66 +403,144 @@ __global__ void __launch_bounds__(32) parse_tensors_kernel(const uint8_t* __rest
   __shared__ __align__(16) uint8_t lines[32][256];
   int r = blockIdx.x * blockDim.x + threadIdx.x;
   if (r >= n) return;
-  Win win; win.buf = lines[threadIdx.x];
-  win_prefetch(&win, w, rec_off[r], rec_len[r]);
-  status[r] = walk_tensor_proto(w, rec_off[r], rec_len[r], outs + r, &win);
+  const uint64_t off = rec_off[r], len = rec_len[r];
+  if (len > 0x7FFFFFFFull) { status[r] = B200TFS_E_PARSE; return; }
+  Cursor c;
+  cur_open(c, w + off, (uint32_t)len, lines[threadIdx.x]);
+  status[r] = walk_tensor_proto(c, outs + r);
 }
 
 // ------------------------------------------------------------------------------------------------
-// decode_fused_kernel: the whole PredictResponse decode in ONE launch.  CTA b belongs to record r
-// (cta_rec[b]) with local tile j.  Thread 0 walks the record's tags out of the line cache (every CTA
-// of the record does the same walk: ~100 header bytes, L2-resident after the first CTA), lays the
-// outputs out in the record's destination slot, and finds which value chunk tile j falls in; then the
-// CTA moves that tile.  CTA j == 0 also publishes the table for the host.
+// decode_fused_kernel: the whole PredictResponse decode in ONE launch.  CTA b belongs to record r with
+// local tile j.
+//
+// Fast path - framing template.  In steady state every response of a model has the same framing
+// (same keys, dtypes, dims => the same non-payload bytes at the same offsets).  The previous launch
+// left a template of record 0: its framing bytes, where the value chunks lie, and the finished table.
+// Each CTA checks, one byte per thread, that this record's framing bytes equal the template's (and
+// that packed-varint chunks still end on a terminator); identical framing bytes of an identical
+// length parse identically, so the CTA takes its tile straight from the template.  Cost: one DRAM
+// round trip for the two framing lines instead of a serial tag walk (a lone GPU lane needs ~15 us
+// for the ~100 header bytes).
+//
+// Slow path - thread 0 walks the tags through the line cache (walker.h), lays the outputs out in the
+// record's destination slot and finds which value chunk tile j falls in; CTA (record 0, tile 0) also
+// writes the template for the next launch.  CTA j == 0 of every record publishes the table.
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(kMoveThreads, 3) decode_fused_kernel(const __grid_constant__ FusedParams fp) {
-  __shared__ __align__(16) uint8_t lines[256];
-  __shared__ b200tfs_output outs_s[kFusedMaxOutputs];
-  __shared__ b200tfs_model_spec spec_s;
-  __shared__ struct { const uint8_t* src; uint8_t* dst; uint64_t n_out; uint32_t op, n_tiles, tile, valid; } job;
-  const uint32_t b = blockIdx.x;
-  uint32_t r, j;
-  uint64_t off, len;
-  if (fp.n <= kFusedInlineRecs) {
-    r = 0;
-    while (r + 1 < (uint32_t)fp.n && b >= fp.inl.tile_start[r + 1]) ++r;
-    j = b - fp.inl.tile_start[r]; off = fp.inl.off[r]; len = fp.inl.len[r];
-  } else {
-    r = fp.cta_rec[b]; j = b - fp.tile_start[r]; off = fp.rec_off[r]; len = fp.rec_len[r];
+struct FusedJob { const uint8_t* src; uint8_t* dst; uint64_t n_out; uint32_t op, n_tiles, tile, valid; };
+
+__device__ __forceinline__ void publish_words(void* dst, const void* src, uint32_t bytes) {
+  const uint64_t* s = reinterpret_cast<const uint64_t*>(src);
+  uint64_t* d = reinterpret_cast<uint64_t*>(dst);
+  for (uint32_t i = threadIdx.x; i < bytes / 8; i += blockDim.x) d[i] = s[i];
+}
+
+// thread 0: build the template of a walked record (chunks sorted by wire offset, framing bytes)
+__device__ void learn_template(Template* T, Cursor& c, uint32_t len, const b200tfs_output* outs, int cnt, const b200tfs_model_spec& spec,
+                               int st, uint32_t vpt, uint64_t dst_need) {
+  T->valid = 0;
+  if (st != B200TFS_OK || cnt > kFusedMaxOutputs) return;
+  TplChunk ch[kTplChunks];
+  uint32_t n = 0;
+  for (int k = 0; k < cnt; ++k) {
+    const b200tfs_output& o = outs[k];
+    if (o.status != B200TFS_OK && o.status != B200TFS_E_SHAPE && o.status != B200TFS_E_KEY) return;
+    const DtypeInfo di = dtype_info(o.dtype);
+    const bool moved = (o.status == B200TFS_OK) && di.kind == VK_FIXED && o.n_elems;
+    uint32_t run = 0;
+    for (int q = 0; q < o.n_chunks; ++q) {
+      if (n >= kTplChunks) return;
+      TplChunk x;
+      x.wire_off = (uint32_t)o.chunk_off[q]; x.len = (uint32_t)o.chunk_len[q];
+      x.dst_off = (uint32_t)o.dst_off + run; x.op = (o.dtype == DT_FLOAT) ? OP_QUIET_DST : OP_COPY;
+      x.n_tiles = moved ? tiles_for(o.chunk_len[q], vpt) : 0u;
+      x.is_varint = (o.flags & B200TFS_OF_VARINT) ? 1u : 0u; x.fpos = 0; x.pad = 0;
+      if (o.dst_off + run + o.chunk_len[q] > 0xFFFFFFFFull) return;
+      run += (uint32_t)o.chunk_len[q];
+      ch[n++] = x;
+    }
+    if (o.content_len) {  // tensor_content: opaque like a payload, never moved here
+      if (n >= kTplChunks) return;
+      TplChunk x;
+      x.wire_off = (uint32_t)o.content_off; x.len = (uint32_t)o.content_len; x.dst_off = 0; x.op = OP_COPY; x.n_tiles = 0;
+      x.is_varint = 0; x.fpos = 0; x.pad = 0;
+      ch[n++] = x;
+    }
   }
-  if (threadIdx.x == 0) {
-    Win win; win.buf = lines;
-    win_prefetch(&win, fp.w, off, len);
-    int cnt = 0;
-    int st = walk_response(fp.w, off, len, kFusedMaxOutputs, outs_s, &cnt, &spec_s, &win);
+  for (uint32_t i = 1; i < n; ++i) {  // by wire offset; tiles are handed out in this order
+    TplChunk x = ch[i];
+    uint32_t k = i;
+    while (k > 0 && ch[k - 1].wire_off > x.wire_off) { ch[k] = ch[k - 1]; --k; }
+    ch[k] = x;
+  }
+  uint32_t payload = 0, tiles = 0;
+  for (uint32_t i = 0; i < n; ++i) {
+    if (i && ch[i].wire_off < ch[i - 1].wire_off + ch[i - 1].len) return;  // overlapping (content inside? never) - be safe
+    ch[i].fpos = ch[i].wire_off - payload;
+    payload += ch[i].len;
+    tiles += ch[i].n_tiles;
+  }
+  const uint32_t framing = len - payload;
+  if (framing > kTplFraming) return;
+  uint32_t w = 0, ci = 0;
+  for (uint32_t i = 0; i < framing; ++i) {
+    while (ci < n && ch[ci].wire_off == w) { w += ch[ci].len; ++ci; }
+    T->framing[i] = rd8(c, w++);
+  }
+  for (uint32_t i = 0; i < n; ++i) T->chunk[i] = ch[i];
+  T->n_chunks = n; T->n_outs = (uint32_t)cnt; T->framing_len = framing; T->rec_len = len; T->vpt = vpt; T->total_tiles = tiles;
+  T->dst_need = dst_need; T->spec = spec;
+  for (int k = 0; k < cnt; ++k) T->outs[k] = outs[k];
+  __threadfence();
+  T->valid = 1;
+}
+
+// the serial walk, kept out of line so the fast path's registers stay lean (thread 0 only)
+__device__ __noinline__ void fused_slow_path(const FusedParams& fp, uint32_t r, uint32_t j, uint32_t budget, const uint8_t* rec, uint64_t len,
+                                             uint8_t* dst_slot, uint8_t* lines, b200tfs_output* outs_s, b200tfs_model_spec& spec_s,
+                                             FusedJob& job) {
+    int cnt = 0, st;
+    Cursor c;
     job.valid = 0;
-    // destination layout + tile lookup
-    uint64_t cursor = 0;        // bytes used in this record's destination slot
-    uint32_t t_base = 0;        // tiles consumed by earlier chunks
-    const uint32_t budget = ((r + 1 < (uint32_t)fp.n) ? (fp.n <= kFusedInlineRecs ? fp.inl.tile_start[r + 1] : fp.tile_start[r + 1])
-                                                      : gridDim.x) - (b - j);
+    if (len > 0x7FFFFFFFull) st = B200TFS_E_PARSE;
+    else {
+      cur_open(c, rec, (uint32_t)len, lines);
+      st = walk_response(c, kFusedMaxOutputs, outs_s, &cnt, &spec_s);
+    }
+    uint64_t cursor = 0;   // bytes used in this record's destination slot
+    uint32_t t_base = 0;   // tiles consumed by earlier chunks
     if (st == B200TFS_OK) {
+      // lay out in wire order of the chunks so that the template (sorted by wire offset) agrees
       for (int k = 0; k < cnt; ++k) {
         b200tfs_output& o = outs_s[k];
-        o.dst_off = 0;
         if (o.status != B200TFS_OK || !o.n_elems) continue;
-        const DtypeInfo di = dtype_info(o.dtype);
-        if (di.kind != VK_FIXED) continue;   // varint / string outputs: tabulated only (two-phase unpack)
+        if (dtype_info(o.dtype).kind != VK_FIXED) continue;   // varint / string outputs: tabulated only (two-phase unpack)
         cursor = (cursor + 255) & ~255ull;
         if (cursor + o.dst_bytes > fp.dst_stride) { o.status = B200TFS_E_SIZE; continue; }
-        o.dst_off = (uint64_t)r * fp.dst_stride + cursor;
-        uint8_t* d = fp.dst + o.dst_off;
-        const uint32_t op = (o.dtype == DT_FLOAT) ? OP_QUIET_DST : OP_COPY;
-        for (int c = 0; c < o.n_chunks; ++c) {
-          const uint32_t nt = tiles_for(o.chunk_len[c], fp.vpt);
-          if (j >= t_base && j < t_base + nt) {
-            job.src = fp.w + o.chunk_off[c]; job.dst = d; job.n_out = o.chunk_len[c]; job.op = op;
-            job.n_tiles = nt; job.tile = j - t_base; job.valid = 1;
-          }
-          t_base += nt;
-          d += o.chunk_len[c];
-        }
+        o.dst_off = cursor;
         cursor += o.dst_bytes;
+      }
+      // tiles are handed out by ascending wire offset of the chunk (same order the template uses)
+      uint32_t done_mask[kFusedMaxOutputs] = {0};
+      for (;;) {
+        int bk = -1, bq = -1; uint64_t best = ~0ull;
+        for (int k = 0; k < cnt; ++k) {
+          const b200tfs_output& o = outs_s[k];
+          if (o.status != B200TFS_OK || !o.n_elems || dtype_info(o.dtype).kind != VK_FIXED) continue;
+          for (int q = 0; q < o.n_chunks; ++q)
+            if (!(done_mask[k] >> q & 1) && o.chunk_off[q] < best) { best = o.chunk_off[q]; bk = k; bq = q; }
+        }
+        if (bk < 0) break;
+        done_mask[bk] |= 1u << bq;
+        const b200tfs_output& o = outs_s[bk];
+        uint64_t run = 0;
+        for (int q = 0; q < bq; ++q) run += o.chunk_len[q];
+        const uint32_t nt = tiles_for(o.chunk_len[bq], fp.vpt);
+        if (j >= t_base && j < t_base + nt) {
+          job.src = rec + o.chunk_off[bq]; job.dst = dst_slot + o.dst_off + run; job.n_out = o.chunk_len[bq];
+          job.op = (o.dtype == DT_FLOAT) ? OP_QUIET_DST : OP_COPY; job.n_tiles = nt; job.tile = j - t_base; job.valid = 1;
+        }
+        t_base += nt;
       }
       if (t_base > budget) st = B200TFS_E_NONCANONICAL;  // more chunks than the launch budgeted tiles for
     }
@@ -469,9 +549,68 @@ __global__ void __launch_bounds__(kMoveThreads, 3) decode_fused_kernel(const __g
       fp.n_outs[r] = (st == B200TFS_OK) ? cnt : 0;
       fp.specs[r] = spec_s;
       for (int k = 0; k < cnt && st == B200TFS_OK; ++k) fp.outs[(size_t)r * kFusedMaxOutputs + k] = outs_s[k];
+      if (r == 0 && fp.tpl_write != nullptr) {
+        if (len <= 0x7FFFFFFFull) learn_template(fp.tpl_write, c, (uint32_t)len, outs_s, cnt, spec_s, st, fp.vpt, (cursor + 255) & ~255ull);
+        else fp.tpl_write->valid = 0;
+      }
     }
     if (st != B200TFS_OK) job.valid = 0;
+}
+
+__global__ void __launch_bounds__(kMoveThreads, 3) decode_fused_kernel(const __grid_constant__ FusedParams fp) {
+  __shared__ __align__(16) uint8_t lines[256];
+  __shared__ b200tfs_output outs_s[kFusedMaxOutputs + 1];  // +1: scratch slot for an entry whose key repeats
+  __shared__ b200tfs_model_spec spec_s;
+  __shared__ FusedJob job;
+  const uint32_t b = blockIdx.x;
+  uint32_t r, j, budget;
+  uint64_t off, len;
+  if (fp.n <= kFusedInlineRecs) {
+    r = 0;
+    while (r + 1 < (uint32_t)fp.n && b >= fp.inl.tile_start[r + 1]) ++r;
+    j = b - fp.inl.tile_start[r]; off = fp.inl.off[r]; len = fp.inl.len[r];
+    budget = fp.inl.tile_start[r + 1] - fp.inl.tile_start[r];
+  } else {
+    r = fp.cta_rec[b];
+    const uint32_t t0 = fp.tile_start[r];
+    j = b - t0; off = fp.rec_off[r]; len = fp.rec_len[r];
+    budget = fp.tile_start[r + 1] - t0;
   }
+  const uint8_t* rec = fp.w + off;
+  uint8_t* dst_slot = fp.dst + (uint64_t)r * fp.dst_stride;
+
+  // ---- fast path: does this record carry the template's framing? ----
+  const Template* T = fp.tpl_read;
+  if (T != nullptr && T->valid && T->rec_len == len && T->vpt == fp.vpt && T->dst_need <= fp.dst_stride && T->total_tiles <= budget) {
+    const uint32_t i = threadIdx.x, nch = T->n_chunks;
+    bool same = true;
+    if (i < T->framing_len) {
+      uint32_t w = i;
+      for (uint32_t q = 0; q < nch; ++q) if (T->chunk[q].fpos <= i) w += T->chunk[q].len;
+      same = rec[w] == T->framing[i];
+    }
+    if (i < nch && T->chunk[i].is_varint && T->chunk[i].len) same = same && !(rec[T->chunk[i].wire_off + T->chunk[i].len - 1] & 0x80);
+    if (__syncthreads_and(same)) {
+      uint32_t t_base = 0;
+      for (uint32_t q = 0; q < nch; ++q) {
+        const uint32_t nt = T->chunk[q].n_tiles;
+        if (j >= t_base && j < t_base + nt)
+          move_tile(rec + T->chunk[q].wire_off, dst_slot + T->chunk[q].dst_off, T->chunk[q].len, T->chunk[q].op, nt, j - t_base, fp.vpt);
+        t_base += nt;
+      }
+      if (j == 0) {
+        publish_words(fp.outs + (size_t)r * kFusedMaxOutputs, T->outs, T->n_outs * (uint32_t)sizeof(b200tfs_output));
+        publish_words(fp.specs + r, &T->spec, (uint32_t)sizeof(b200tfs_model_spec));
+        if (threadIdx.x == 0) { fp.status[r] = B200TFS_OK; fp.n_outs[r] = (int32_t)T->n_outs; }
+        // hand the template on to the next launch (launches alternate between the two slots)
+        if (r == 0 && fp.tpl_write != nullptr) publish_words(fp.tpl_write, T, (uint32_t)sizeof(Template));
+      }
+      return;
+    }
+  }
+
+  // ---- slow path: thread 0 walks the tags ----
+  if (threadIdx.x == 0) fused_slow_path(fp, r, j, budget, rec, len, dst_slot, lines, outs_s, spec_s, job);
   __syncthreads();
   if (job.valid) move_tile(job.src, job.dst, job.n_out, job.op, job.n_tiles, job.tile, fp.vpt);
 }

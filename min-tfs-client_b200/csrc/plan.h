@@ -61,6 +61,20 @@ constexpr uint32_t kFusedSlackTiles = 8;  // tiles budgeted per record beyond ce
 
 struct FusedInline { uint64_t off[kFusedInlineRecs], len[kFusedInlineRecs]; uint32_t tile_start[kFusedInlineRecs + 1]; };
 
+// framing template left by one decode launch for the next (see decode_fused_kernel)
+constexpr uint32_t kTplChunks = 4;
+constexpr uint32_t kTplFraming = 256;   // == kMoveThreads: one framing byte per thread
+struct TplChunk { uint32_t wire_off, len, dst_off, op, n_tiles, is_varint, fpos, pad; };  // record-relative
+struct Template {
+  uint32_t valid, n_chunks, n_outs, framing_len;
+  uint64_t rec_len, dst_need;
+  uint32_t vpt, total_tiles;
+  TplChunk chunk[kTplChunks];
+  uint8_t framing[kTplFraming];
+  b200tfs_model_spec spec;
+  b200tfs_output outs[kFusedMaxOutputs];
+};
+
 struct FusedParams {
   const uint8_t* w;          // wire arena
   uint8_t* dst;              // destination base; record r owns [r*dst_stride, (r+1)*dst_stride)
@@ -75,6 +89,8 @@ struct FusedParams {
   const uint32_t* tile_start;
   const uint64_t* rec_off;
   const uint64_t* rec_len;
+  const Template* tpl_read;  // template written by the previous launch on this context (may be invalid)
+  Template* tpl_write;       // where record 0 of this launch leaves its template
   FusedInline inl;
 };
 

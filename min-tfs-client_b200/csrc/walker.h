@@ -1,5 +1,5 @@
-// walker.h - the PredictResponse / TensorProto tag walk that the parse kernel runs (one lane per
-// record).  It tabulates where every output's values lie in the wire so the unpack kernels can move
+// walker.h - the PredictResponse / TensorProto tag walk that the decode kernels run (one lane per
+// record).  It tabulates where every output's values lie in the wire so the unpack code can move
 // them; it moves no payload bytes itself.
 //
 // Behaviour follows what the reference observes through PredictResponse.FromString
@@ -10,77 +10,85 @@
 //   fields (varint / fixed / length-delimited / groups) skipped; duplicate map key: last entry wins;
 //   truncated input, tag 0, bad UTF-8 in a string field, packed fixed32 length % 4 != 0: parse error.
 //
-// Written as host+device inline code so the same source is unit-tested on the CPU against the golden
-// vectors (tests/native/) and runs unchanged inside parse_kernel.
+// Shape of the code: ONE cursor per record (32-bit offsets relative to the record start, nested
+// messages narrow `end` and restore it), no recursion, every helper force-inlined, so on the device
+// the whole walk state lives in registers and the only memory touched is the two-line cache below
+// and the output table.  The same source compiles for the host, where tests/native replays the golden
+// vectors through it.
 #pragma once
 #include "../../include/b200tfs.h"
 #include "wire.h"
 
 namespace b200tfs {
 
-// Two 128-byte lines of the wire cached next to the walking lane (shared memory on the device).  A
-// single lane chasing bytes through HBM pays a full DRAM round trip per miss, so it fetches whole
-// lines with eight independent 16-byte loads; the canonical response (header ... payload ... model_spec)
-// then costs two misses, both issued up front by win_prefetch().  On the host the window is unused.
-struct Win {
-  uint64_t line[2];  // absolute address of each cached line (aligned to 128), ~0 = empty
-  uint8_t* buf;      // 256 bytes
-  uint32_t victim;
-};
-
+// One lane chasing bytes through HBM pays a DRAM round trip per miss, so it reads the wire through
+// a cache of two 128-byte lines (shared memory), each filled with eight independent 16-byte loads.
+// The canonical response (header ... payload ... model_spec) costs two misses, both issued up front.
 struct Cursor {
-  const uint8_t* w;  // arena base
-  uint64_t p;        // current offset
-  uint64_t end;      // limit of the enclosing message
-  int err;           // sticky B200TFS_E_PARSE
-  Win* win;          // device: line cache; host: nullptr
+  const uint8_t* rec;  // first byte of the record
+  uint32_t p;          // offset of the next unread byte, relative to rec
+  uint32_t end;        // limit of the message being walked
+  int32_t err;         // sticky B200TFS_E_PARSE
+  // device only: the line cache
+  const uint8_t* base; // rec rounded down to 128
+  uint8_t* buf;        // 256 bytes of shared memory
+  uint32_t skew;       // rec - base
+  uint32_t line0, line1, victim;  // cached line numbers (relative to base), ~0 = empty
 };
 
 #if defined(__CUDACC__)
-__device__ __forceinline__ void win_fill(Win* W, uint32_t k, uint64_t line) {
-  const uint4* g = reinterpret_cast<const uint4*>(line);
+__device__ __forceinline__ void cur_fill(Cursor& c, uint32_t slot, uint32_t line) {
+  const uint4* g = reinterpret_cast<const uint4*>(c.base + ((uint64_t)line << 7));
   uint4 t0 = g[0], t1 = g[1], t2 = g[2], t3 = g[3], t4 = g[4], t5 = g[5], t6 = g[6], t7 = g[7];
-  uint4* s = reinterpret_cast<uint4*>(W->buf + 128 * k);
+  uint4* s = reinterpret_cast<uint4*>(c.buf + 128 * slot);
   s[0] = t0; s[1] = t1; s[2] = t2; s[3] = t3; s[4] = t4; s[5] = t5; s[6] = t6; s[7] = t7;
-  W->line[k] = line;
 }
-// fetch the first and the last line of a record together (both loads in flight at once)
-__device__ __forceinline__ void win_prefetch(Win* W, const uint8_t* w, uint64_t off, uint64_t len) {
-  W->line[0] = W->line[1] = ~0ull; W->victim = 0;
-  if (!len) return;
-  const uint64_t a = (uint64_t)(uintptr_t)(w + off) & ~127ull, b = (uint64_t)(uintptr_t)(w + off + len - 1) & ~127ull;
-  const uint4* ga = reinterpret_cast<const uint4*>(a);
-  const uint4* gb = reinterpret_cast<const uint4*>(b);
-  uint4 x0 = ga[0], x1 = ga[1], x2 = ga[2], x3 = ga[3], x4 = ga[4], x5 = ga[5], x6 = ga[6], x7 = ga[7];
-  uint4 y0 = gb[0], y1 = gb[1], y2 = gb[2], y3 = gb[3], y4 = gb[4], y5 = gb[5], y6 = gb[6], y7 = gb[7];
-  uint4* s = reinterpret_cast<uint4*>(W->buf);
-  s[0] = x0; s[1] = x1; s[2] = x2; s[3] = x3; s[4] = x4; s[5] = x5; s[6] = x6; s[7] = x7;
-  s[8] = y0; s[9] = y1; s[10] = y2; s[11] = y3; s[12] = y4; s[13] = y5; s[14] = y6; s[15] = y7;
-  W->line[0] = a; W->line[1] = b;
+// bind a cursor to a record and fetch its first and last line together
+__device__ __forceinline__ void cur_open(Cursor& c, const uint8_t* rec, uint32_t len, uint8_t* smem256) {
+  c.rec = rec; c.p = 0; c.end = len; c.err = 0;
+  c.base = reinterpret_cast<const uint8_t*>((uintptr_t)rec & ~(uintptr_t)127);
+  c.skew = (uint32_t)(rec - c.base);
+  c.buf = smem256; c.victim = 0; c.line0 = c.line1 = ~0u;
+  if (len) {
+    const uint32_t lb = (c.skew + len - 1) >> 7;
+    const uint4* ga = reinterpret_cast<const uint4*>(c.base);
+    const uint4* gb = reinterpret_cast<const uint4*>(c.base + ((uint64_t)lb << 7));
+    uint4 x0 = ga[0], x1 = ga[1], x2 = ga[2], x3 = ga[3], x4 = ga[4], x5 = ga[5], x6 = ga[6], x7 = ga[7];
+    uint4 y0 = gb[0], y1 = gb[1], y2 = gb[2], y3 = gb[3], y4 = gb[4], y5 = gb[5], y6 = gb[6], y7 = gb[7];
+    uint4* s = reinterpret_cast<uint4*>(c.buf);
+    s[0] = x0; s[1] = x1; s[2] = x2; s[3] = x3; s[4] = x4; s[5] = x5; s[6] = x6; s[7] = x7;
+    s[8] = y0; s[9] = y1; s[10] = y2; s[11] = y3; s[12] = y4; s[13] = y5; s[14] = y6; s[15] = y7;
+    c.line0 = 0; c.line1 = lb;
+  }
 }
 #endif
+inline void cur_open_host(Cursor& c, const uint8_t* rec, uint32_t len) {
+  c.rec = rec; c.p = 0; c.end = len; c.err = 0;
+  c.base = rec; c.buf = nullptr; c.skew = 0; c.line0 = c.line1 = ~0u; c.victim = 0;
+}
 
-// byte at arena offset p
-B2_HD uint8_t rd8(const Cursor& c, uint64_t p) {
+// byte at record offset q
+B2_HD uint8_t rd8(Cursor& c, uint32_t q) {
 #if defined(__CUDA_ARCH__)
-  Win* W = c.win;
-  const uint64_t addr = (uint64_t)(uintptr_t)(c.w + p), line = addr & ~127ull;
-  if (line == W->line[0]) return W->buf[addr & 127];
-  if (line == W->line[1]) return W->buf[128 + (addr & 127)];
-  const uint32_t k = W->victim;
-  W->victim = k ^ 1;
-  win_fill(W, k, line);
-  return W->buf[128 * k + (addr & 127)];
+  const uint32_t a = q + c.skew, line = a >> 7;
+  if (line == c.line0) return c.buf[a & 127];
+  if (line == c.line1) return c.buf[128 + (a & 127)];
+  const uint32_t k = c.victim;
+  c.victim = k ^ 1;
+  cur_fill(c, k, line);
+  if (k) c.line1 = line; else c.line0 = line;
+  return c.buf[128 * k + (a & 127)];
 #else
-  return c.w[p];
+  return c.rec[q];
 #endif
 }
 
 B2_HD uint64_t rd_varint(Cursor& c) {
   uint64_t v = 0;
+#pragma unroll 1
   for (int i = 0; i < 10; ++i) {
     if (c.p >= c.end) { c.err = B200TFS_E_PARSE; return 0; }
-    uint8_t b = rd8(c, c.p++);
+    const uint8_t b = rd8(c, c.p++);
     v |= (uint64_t)(b & 0x7F) << (7 * i);  // bits past 64 fall off, as in the runtime
     if (!(b & 0x80)) return v;
   }
@@ -90,18 +98,18 @@ B2_HD uint64_t rd_varint(Cursor& c) {
 
 // tag: must fit 32 bits, field number != 0
 B2_HD uint32_t rd_tag(Cursor& c) {
-  uint64_t t = rd_varint(c);
+  const uint64_t t = rd_varint(c);
   if (c.err) return 0;
   if (t > 0xFFFFFFFFull || (t >> 3) == 0) { c.err = B200TFS_E_PARSE; return 0; }
   return (uint32_t)t;
 }
 
 // length prefix: bounded by the enclosing message (and by int32, like the runtime)
-B2_HD uint64_t rd_len(Cursor& c) {
-  uint64_t n = rd_varint(c);
+B2_HD uint32_t rd_len(Cursor& c) {
+  const uint64_t n = rd_varint(c);
   if (c.err) return 0;
-  if (n > 0x7FFFFFFFull || n > c.end - c.p) { c.err = B200TFS_E_PARSE; return 0; }
-  return n;
+  if (n > 0x7FFFFFFFull || n > (uint64_t)(c.end - c.p)) { c.err = B200TFS_E_PARSE; return 0; }
+  return (uint32_t)n;
 }
 
 // Skip one non-group field body (tag already consumed).
@@ -109,25 +117,27 @@ B2_HD void skip_scalar(Cursor& c, uint32_t wt) {
   if (wt == WT_VARINT) { (void)rd_varint(c); return; }
   if (wt == WT_I64) { if (c.end - c.p < 8) c.err = B200TFS_E_PARSE; else c.p += 8; return; }
   if (wt == WT_I32) { if (c.end - c.p < 4) c.err = B200TFS_E_PARSE; else c.p += 4; return; }
-  if (wt == WT_LEN) { uint64_t n = rd_len(c); if (!c.err) c.p += n; return; }
-  c.err = B200TFS_E_PARSE;
+  if (wt == WT_LEN) { const uint32_t n = rd_len(c); if (!c.err) c.p += n; return; }
+  c.err = B200TFS_E_PARSE;  // stray END_GROUP, wire types 6 and 7
 }
 
-// Skip one field body of any wire type.  Groups nest (explicit stack, no recursion: device stack
-// frames stay static); an END_GROUP that does not close a group we opened is malformed.
+// Skip one field body of any wire type.  Groups nest: the open field numbers are kept on a small
+// explicit stack (depth <= 16; deeper is treated as malformed); an END_GROUP that does not close
+// the innermost open group is malformed.
 B2_HD void skip_field(Cursor& c, uint32_t tag) {
   const uint32_t wt = tag & 7;
-  if (wt != WT_SGROUP) { skip_scalar(c, wt); return; }  // stray END_GROUP and wire types 6, 7 fail in there
-  uint32_t open[32];
+  if (wt != WT_SGROUP) { skip_scalar(c, wt); return; }
+  uint32_t open[16];
   int depth = 0;
   open[depth++] = tag >> 3;
+#pragma unroll 1
   while (depth > 0 && !c.err) {
     if (c.p >= c.end) { c.err = B200TFS_E_PARSE; return; }
     const uint32_t t = rd_tag(c);
     if (c.err) return;
     const uint32_t w2 = t & 7;
     if (w2 == WT_SGROUP) {
-      if (depth >= 32) { c.err = B200TFS_E_PARSE; return; }
+      if (depth >= 16) { c.err = B200TFS_E_PARSE; return; }
       open[depth++] = t >> 3;
     } else if (w2 == WT_EGROUP) {
       if (open[depth - 1] != (t >> 3)) { c.err = B200TFS_E_PARSE; return; }
@@ -139,20 +149,21 @@ B2_HD void skip_field(Cursor& c, uint32_t tag) {
 }
 
 // Structural UTF-8 check the runtime applies to proto3 `string` fields (shortest form, no
-// surrogates, <= U+10FFFF).
-B2_HD bool utf8_ok(const Cursor& c, uint64_t off, uint64_t n) {
-  uint64_t i = 0;
+// surrogates, <= U+10FFFF) over record bytes [off, off+n).
+B2_HD bool utf8_ok(Cursor& c, uint32_t off, uint32_t n) {
+  uint32_t i = 0;
+#pragma unroll 1
   while (i < n) {
-    uint8_t b = rd8(c, off + i);
+    const uint8_t b = rd8(c, off + i);
     if (b < 0x80) { ++i; continue; }
-    uint32_t need; uint32_t cp;
+    uint32_t need, cp;
     if (b >= 0xC2 && b <= 0xDF) { need = 1; cp = b & 0x1F; }
     else if (b >= 0xE0 && b <= 0xEF) { need = 2; cp = b & 0x0F; }
     else if (b >= 0xF0 && b <= 0xF4) { need = 3; cp = b & 0x07; }
     else return false;
     if (n - i - 1 < need) return false;
     for (uint32_t k = 1; k <= need; ++k) {
-      uint8_t x = rd8(c, off + i + k);
+      const uint8_t x = rd8(c, off + i + k);
       if ((x & 0xC0) != 0x80) return false;
       cp = (cp << 6) | (x & 0x3F);
     }
@@ -163,85 +174,91 @@ B2_HD bool utf8_ok(const Cursor& c, uint64_t off, uint64_t n) {
   return true;
 }
 
-// Raw value-field occurrences seen before the dtype is known.
-struct RawChunks {
-  uint32_t field[B200TFS_MAX_CHUNKS];
-  uint64_t off[B200TFS_MAX_CHUNKS];
-  uint64_t len[B200TFS_MAX_CHUNKS];
-  int n;
-  bool overflow;
-};
+// a length-delimited string field: validate, return its record offset, step over it
+B2_HD uint32_t rd_string(Cursor& c, uint32_t* len) {
+  const uint32_t n = rd_len(c);
+  if (c.err) { *len = 0; return 0; }
+  const uint32_t at = c.p;
+  if (!utf8_ok(c, at, n)) { c.err = B200TFS_E_PARSE; *len = 0; return 0; }
+  c.p += n;
+  *len = n;
+  return at;
+}
 
-B2_HD void out_reset(b200tfs_output& o) {
+// Begin a fresh output record: only the fields the walk accumulates into.
+B2_HD void out_begin(b200tfs_output& o) {
   o.key_off = 0; o.key_len = 0; o.dtype = 0; o.rank = 0; o.flags = 0; o.value_field = 0; o.n_chunks = 0;
-  for (int i = 0; i < B200TFS_MAX_RANK; ++i) o.dims[i] = 0;
-  for (int i = 0; i < B200TFS_MAX_CHUNKS; ++i) { o.chunk_off[i] = 0; o.chunk_len[i] = 0; }
   o.content_off = 0; o.content_len = 0; o.msg_off = 0; o.msg_len = 0;
   o.n_elems = 0; o.dst_bytes = 0; o.n_strings = 0; o.dst_off = 0; o.status = B200TFS_OK; o.reserved = 0;
 }
 
-// TensorShapeProto (tensor_shape.proto:13-46): dims append (merge); Dim.size last wins inside a Dim.
-B2_HD void walk_shape(Cursor& c, b200tfs_output& o, bool& rank_overflow) {
+// Walk state that does not belong in the table: which field each recorded chunk came from.
+struct ChunkTags {
+  uint8_t field[B200TFS_MAX_CHUNKS];
+  bool chunk_overflow, rank_overflow;
+};
+
+// TensorShapeProto (tensor_shape.proto:13-46) in [c.p, c.end): dims append (merge); Dim.size last
+// wins inside a Dim; Dim.name validated and ignored (tensors.py:38-39).
+B2_HD void walk_shape(Cursor& c, b200tfs_output& o, ChunkTags& ct) {
+#pragma unroll 1
   while (c.p < c.end && !c.err) {
-    uint32_t tag = rd_tag(c);
+    const uint32_t tag = rd_tag(c);
     if (c.err) return;
-    if (tag == tag_of(2, WT_LEN)) {  // dim
-      uint64_t n = rd_len(c);
-      if (c.err) return;
-      Cursor d{c.w, c.p, c.p + n, 0, c.win};
-      int64_t size = 0;
-      while (d.p < d.end && !d.err) {
-        uint32_t t = rd_tag(d);
-        if (d.err) break;
-        if (t == tag_of(1, WT_VARINT)) size = (int64_t)rd_varint(d);
-        else if (t == tag_of(2, WT_LEN)) {  // name: a proto3 string, validated then ignored (tensors.py:38-39)
-          uint64_t m = rd_len(d);
-          if (d.err) break;
-          if (!utf8_ok(d, d.p, m)) d.err = B200TFS_E_PARSE;
-          d.p += m;
-        } else skip_field(d, t);
-      }
-      if (d.err) { c.err = d.err; return; }
-      if (o.rank < B200TFS_MAX_RANK) o.dims[o.rank++] = size; else rank_overflow = true;
-      c.p += n;
-    } else {
-      skip_field(c, tag);  // unknown_rank (3) and anything else
+    if (tag != tag_of(2, WT_LEN)) { skip_field(c, tag); continue; }  // unknown_rank (3) and anything else
+    const uint32_t n = rd_len(c);
+    if (c.err) return;
+    const uint32_t outer = c.end;
+    c.end = c.p + n;
+    int64_t size = 0;
+#pragma unroll 1
+    while (c.p < c.end && !c.err) {
+      const uint32_t t = rd_tag(c);
+      if (c.err) break;
+      if (t == tag_of(1, WT_VARINT)) size = (int64_t)rd_varint(c);
+      else if (t == tag_of(2, WT_LEN)) { uint32_t k; (void)rd_string(c, &k); }
+      else skip_field(c, t);
     }
+    c.end = outer;
+    if (c.err) return;
+    if (o.rank < B200TFS_MAX_RANK) o.dims[o.rank++] = size; else ct.rank_overflow = true;
   }
 }
 
-// One TensorProto (tensor.proto:14-84); accumulates into o / raw so a repeated `value` merges.
-B2_HD void walk_tensor(Cursor& c, b200tfs_output& o, RawChunks& raw, bool& rank_overflow) {
+// One TensorProto (tensor.proto:14-84) in [c.p, c.end); accumulates into o so a repeated `value` merges.
+// Every offset written to the table is relative to the record start.
+B2_HD void walk_tensor(Cursor& c, b200tfs_output& o, ChunkTags& ct) {
+#pragma unroll 1
   while (c.p < c.end && !c.err) {
-    uint32_t tag = rd_tag(c);
+    const uint32_t tag = rd_tag(c);
     if (c.err) return;
-    uint32_t field = tag >> 3, wt = tag & 7;
+    const uint32_t field = tag >> 3, wt = tag & 7;
     if (field == F_DTYPE && wt == WT_VARINT) {
       o.dtype = (int32_t)(uint32_t)rd_varint(c);
     } else if (field == F_SHAPE && wt == WT_LEN) {
-      uint64_t n = rd_len(c);
+      const uint32_t n = rd_len(c);
       if (c.err) return;
-      Cursor s{c.w, c.p, c.p + n, 0, c.win};
-      walk_shape(s, o, rank_overflow);
-      if (s.err) { c.err = s.err; return; }
-      c.p += n;
+      const uint32_t outer = c.end;
+      c.end = c.p + n;
+      walk_shape(c, o, ct);
+      c.end = outer;
     } else if (field == F_CONTENT && wt == WT_LEN) {
-      uint64_t n = rd_len(c);
+      const uint32_t n = rd_len(c);
       if (c.err) return;
       o.content_off = c.p; o.content_len = n;  // `bytes`: last occurrence replaces
       c.p += n;
     } else if (field == F_STRING && wt == WT_LEN) {
-      uint64_t n = rd_len(c);
+      const uint32_t n = rd_len(c);
       if (c.err) return;
       o.n_strings += 1;
       c.p += n;
     } else if (scalar_wire_type(field) != 0xFFu && (wt == WT_LEN || wt == scalar_wire_type(field))) {
-      uint64_t off, len;
+      uint32_t off, len;
       if (wt == WT_LEN) {
         len = rd_len(c);
         if (c.err) return;
         off = c.p;
-        uint32_t fw = fixed_wire_width(field);
+        const uint32_t fw = fixed_wire_width(field);
         if (fw) {
           if (len % fw) { c.err = B200TFS_E_PARSE; return; }  // packed fixed32/64 must be whole elements
         } else if (len && (rd8(c, off + len - 1) & 0x80)) {
@@ -250,44 +267,48 @@ B2_HD void walk_tensor(Cursor& c, b200tfs_output& o, RawChunks& raw, bool& rank_
         c.p += len;
       } else {
         off = c.p;
-        skip_field(c, tag);
+        skip_scalar(c, wt);
         if (c.err) return;
         len = c.p - off;
       }
       if (len) {
-        if (raw.n < B200TFS_MAX_CHUNKS) {
-          raw.field[raw.n] = field; raw.off[raw.n] = off; raw.len[raw.n] = len; ++raw.n;
-        } else raw.overflow = true;
+        if (o.n_chunks < B200TFS_MAX_CHUNKS) {
+          ct.field[o.n_chunks] = (uint8_t)field;
+          o.chunk_off[o.n_chunks] = off; o.chunk_len[o.n_chunks] = len;
+          ++o.n_chunks;
+        } else ct.chunk_overflow = true;
       }
     } else {
-      if (field > 17 || field == 0) o.flags |= B200TFS_OF_HAS_UNKNOWN;
+      if (field > 17) o.flags |= B200TFS_OF_HAS_UNKNOWN;
       skip_field(c, tag);  // version_number, resource_handle_val, variant_val, mismatched wire types, unknown
     }
   }
 }
 
-// Settle dtype -> field, pick that field's chunks, element counts.  Mirrors what
+// Settle dtype -> field, keep that field's chunks, element counts.  Mirrors what
 // tensor_proto_to_ndarray (tensors.py:42-46) would conclude from the parsed message.
-B2_HD void finalize_output(b200tfs_output& o, const RawChunks& raw, bool rank_overflow) {
-  if (rank_overflow || raw.overflow) { o.status = B200TFS_E_NONCANONICAL; return; }
-  DtypeInfo di = dtype_info(o.dtype);
-  if (di.field == 0) { o.status = B200TFS_E_KEY; return; }  // types.py:40 KeyError
+B2_HD void finalize_output(b200tfs_output& o, const ChunkTags& ct) {
+  if (ct.rank_overflow || ct.chunk_overflow) { o.status = B200TFS_E_NONCANONICAL; o.n_chunks = 0; return; }
+  const DtypeInfo di = dtype_info(o.dtype);
+  if (di.field == 0) { o.status = B200TFS_E_KEY; o.n_chunks = 0; return; }  // types.py:40 KeyError
   o.value_field = (int32_t)di.field;
   uint64_t total = 0;
-  for (int i = 0; i < raw.n; ++i) {
-    if (raw.field[i] == di.field) {
-      o.chunk_off[o.n_chunks] = raw.off[i]; o.chunk_len[o.n_chunks] = raw.len[i];
-      total += raw.len[i];
-      ++o.n_chunks;
+  int kept = 0;
+  for (int i = 0; i < o.n_chunks; ++i) {
+    if (ct.field[i] == di.field) {
+      o.chunk_off[kept] = o.chunk_off[i]; o.chunk_len[kept] = o.chunk_len[i];
+      total += o.chunk_len[i];
+      ++kept;
     }
   }
-  if (o.n_chunks > 1) o.flags |= B200TFS_OF_MULTI_CHUNK;
+  o.n_chunks = kept;
+  if (kept > 1) o.flags |= B200TFS_OF_MULTI_CHUNK;
   if (o.content_len) o.flags |= B200TFS_OF_TENSOR_CONTENT;
   if (o.rank == 0) o.flags |= B200TFS_OF_RANK0;
   // prod(dims) with at most one -1
   uint64_t prod = 1; int infer = -1; bool bad = false;
   for (int i = 0; i < o.rank; ++i) {
-    int64_t d = o.dims[i];
+    const int64_t d = o.dims[i];
     if (d == -1 && infer < 0) { infer = i; continue; }
     if (d < 0) { bad = true; break; }
     if (d != 0 && prod > 0xFFFFFFFFFFFFFFFFull / (uint64_t)d) { bad = true; break; }
@@ -295,7 +316,7 @@ B2_HD void finalize_output(b200tfs_output& o, const RawChunks& raw, bool rank_ov
   }
   if (bad) { o.status = B200TFS_E_SHAPE; return; }
   if (di.kind == VK_FIXED) {
-    uint64_t count = total / di.elem_size;  // complex: interleaved (re, im) pairs, TF convention
+    const uint64_t count = total / di.elem_size;  // complex: interleaved (re, im) pairs, TF convention
     if (total % di.elem_size) { o.status = B200TFS_E_SHAPE; return; }
     if (infer >= 0) {
       if (prod == 0 || count % prod) { o.status = B200TFS_E_SHAPE; return; }
@@ -318,101 +339,106 @@ B2_HD void finalize_output(b200tfs_output& o, const RawChunks& raw, bool rank_ov
   o.dst_bytes = prod * di.elem_size;
 }
 
-B2_HD bool bytes_equal(const Cursor& c, uint64_t a, uint64_t b, uint64_t n) {
-  for (uint64_t i = 0; i < n; ++i) if (rd8(c, a + i) != rd8(c, b + i)) return false;
-  return true;
-}
-
 B2_HD void spec_reset(b200tfs_model_spec& s) {
   s.name_off = 0; s.name_len = 0; s.signature_len = 0; s.signature_off = 0; s.label_off = 0; s.label_len = 0;
   s.has_version = 0; s.version = 0;
 }
 
-// ModelSpec (model.proto:9-33); repeated occurrences merge.
+// ModelSpec (model.proto:9-33) in [c.p, c.end); repeated occurrences merge.
 B2_HD void walk_model_spec(Cursor& c, b200tfs_model_spec& s) {
+#pragma unroll 1
   while (c.p < c.end && !c.err) {
-    uint32_t tag = rd_tag(c);
+    const uint32_t tag = rd_tag(c);
     if (c.err) return;
     if (tag == tag_of(1, WT_LEN) || tag == tag_of(3, WT_LEN) || tag == tag_of(4, WT_LEN)) {
-      uint64_t n = rd_len(c);
+      uint32_t n;
+      const uint32_t at = rd_string(c, &n);
       if (c.err) return;
-      if (!utf8_ok(c, c.p, n)) { c.err = B200TFS_E_PARSE; return; }
-      if ((tag >> 3) == 1) { s.name_off = c.p; s.name_len = (uint32_t)n; }
-      else if ((tag >> 3) == 3) { s.signature_off = c.p; s.signature_len = (uint32_t)n; }
-      else { s.label_off = c.p; s.label_len = (uint32_t)n; s.has_version = 0; s.version = 0; }  // oneof: label displaces version
-      c.p += n;
+      if ((tag >> 3) == 1) { s.name_off = at; s.name_len = n; }
+      else if ((tag >> 3) == 3) { s.signature_off = at; s.signature_len = n; }
+      else { s.label_off = at; s.label_len = n; s.has_version = 0; s.version = 0; }  // oneof: label displaces version
     } else if (tag == tag_of(2, WT_LEN)) {  // google.protobuf.Int64Value version
-      uint64_t n = rd_len(c);
+      const uint32_t n = rd_len(c);
       if (c.err) return;
-      Cursor v{c.w, c.p, c.p + n, 0, c.win};
+      const uint32_t outer = c.end;
+      c.end = c.p + n;
       if (!s.has_version) s.version = 0;
-      while (v.p < v.end && !v.err) {
-        uint32_t t = rd_tag(v);
-        if (v.err) break;
-        if (t == tag_of(1, WT_VARINT)) s.version = (int64_t)rd_varint(v); else skip_field(v, t);
+#pragma unroll 1
+      while (c.p < c.end && !c.err) {
+        const uint32_t t = rd_tag(c);
+        if (c.err) break;
+        if (t == tag_of(1, WT_VARINT)) s.version = (int64_t)rd_varint(c); else skip_field(c, t);
       }
-      if (v.err) { c.err = v.err; return; }
+      c.end = outer;
+      if (c.err) return;
       s.has_version = 1; s.label_off = 0; s.label_len = 0;  // oneof: version displaces label
-      c.p += n;
     } else skip_field(c, tag);
   }
 }
 
-// One PredictResponse (predict.proto:30-40).  Returns the record status; *n_outs distinct keys.
-B2_HD int walk_response(const uint8_t* w, uint64_t off, uint64_t len, int max_outputs, b200tfs_output* outs,
-                        int* n_outs, b200tfs_model_spec* spec, Win* win = nullptr) {
-  Cursor c{w, off, off + len, 0, win};
+B2_HD bool keys_equal(Cursor& c, const b200tfs_output& a, const b200tfs_output& b) {
+  if (a.key_len != b.key_len) return false;
+  const uint32_t pa = (uint32_t)a.key_off, pb = (uint32_t)b.key_off;
+  for (uint32_t i = 0; i < a.key_len; ++i) if (rd8(c, pa + i) != rd8(c, pb + i)) return false;
+  return true;
+}
+
+// One PredictResponse (predict.proto:30-40) occupying the cursor's record.
+// outs needs max_outputs + 1 slots (the extra one is scratch for an entry whose key repeats).
+// Returns the record status; *n_outs distinct keys.
+B2_HD int walk_response(Cursor& c, int max_outputs, b200tfs_output* outs, int* n_outs, b200tfs_model_spec* spec) {
   int n = 0;
   spec_reset(*spec);
   *n_outs = 0;
+#pragma unroll 1
   while (c.p < c.end && !c.err) {
-    uint32_t tag = rd_tag(c);
+    const uint32_t tag = rd_tag(c);
     if (c.err) break;
     if (tag == tag_of(1, WT_LEN)) {  // outputs map entry
-      uint64_t elen = rd_len(c);
+      const uint32_t elen = rd_len(c);
       if (c.err) break;
-      Cursor e{w, c.p, c.p + elen, 0, c.win};
-      b200tfs_output tmp; out_reset(tmp);
-      RawChunks raw; raw.n = 0; raw.overflow = false;
-      bool rank_overflow = false;
-      while (e.p < e.end && !e.err) {
-        uint32_t t = rd_tag(e);
-        if (e.err) break;
+      b200tfs_output& o = outs[n];  // parsed in place (slot n <= max_outputs); merged away below if the key repeats
+      out_begin(o);
+      ChunkTags ct; ct.chunk_overflow = false; ct.rank_overflow = false;
+      const uint32_t outer = c.end;
+      c.end = c.p + elen;
+#pragma unroll 1
+      while (c.p < c.end && !c.err) {
+        const uint32_t t = rd_tag(c);
+        if (c.err) break;
         if (t == tag_of(1, WT_LEN)) {
-          uint64_t k = rd_len(e);
-          if (e.err) break;
-          if (!utf8_ok(e, e.p, k)) { e.err = B200TFS_E_PARSE; break; }
-          tmp.key_off = e.p; tmp.key_len = (uint32_t)k;
-          e.p += k;
+          uint32_t k;
+          const uint32_t at = rd_string(c, &k);
+          if (c.err) break;
+          o.key_off = at; o.key_len = k;
         } else if (t == tag_of(2, WT_LEN)) {
-          uint64_t m = rd_len(e);
-          if (e.err) break;
-          Cursor tc{w, e.p, e.p + m, 0, c.win};
-          tmp.msg_off = e.p; tmp.msg_len = m;
-          walk_tensor(tc, tmp, raw, rank_overflow);
-          if (tc.err) { e.err = tc.err; break; }
-          e.p += m;
-        } else skip_field(e, t);
+          const uint32_t m = rd_len(c);
+          if (c.err) break;
+          o.msg_off = c.p; o.msg_len = m;
+          const uint32_t inner = c.end;
+          c.end = c.p + m;
+          walk_tensor(c, o, ct);
+          c.end = inner;
+        } else skip_field(c, t);
       }
-      if (e.err) { c.err = e.err; break; }
-      c.p += elen;
-      finalize_output(tmp, raw, rank_overflow);
+      c.end = outer;
+      if (c.err) break;
+      finalize_output(o, ct);
       // duplicate key: the later entry replaces the earlier one
       int slot = -1;
-      for (int i = 0; i < n; ++i)
-        if (outs[i].key_len == tmp.key_len && bytes_equal(c, outs[i].key_off, tmp.key_off, tmp.key_len)) { slot = i; break; }
-      if (slot < 0) {
+      for (int i = 0; i < n; ++i) if (keys_equal(c, outs[i], o)) { slot = i; break; }
+      if (slot >= 0) outs[slot] = o;
+      else {
         if (n >= max_outputs) return B200TFS_E_SIZE;
-        slot = n++;
+        ++n;
       }
-      outs[slot] = tmp;
     } else if (tag == tag_of(2, WT_LEN)) {
-      uint64_t m = rd_len(c);
+      const uint32_t m = rd_len(c);
       if (c.err) break;
-      Cursor sc{w, c.p, c.p + m, 0, c.win};
-      walk_model_spec(sc, *spec);
-      if (sc.err) { c.err = sc.err; break; }
-      c.p += m;
+      const uint32_t outer = c.end;
+      c.end = c.p + m;
+      walk_model_spec(c, *spec);
+      c.end = outer;
     } else skip_field(c, tag);
   }
   if (c.err) return c.err;
@@ -420,16 +446,14 @@ B2_HD int walk_response(const uint8_t* w, uint64_t off, uint64_t len, int max_ou
   return B200TFS_OK;
 }
 
-// A bare TensorProto message (what tensor_proto_to_ndarray receives).
-B2_HD int walk_tensor_proto(const uint8_t* w, uint64_t off, uint64_t len, b200tfs_output* out, Win* win = nullptr) {
-  Cursor c{w, off, off + len, 0, win};
-  out_reset(*out);
-  RawChunks raw; raw.n = 0; raw.overflow = false;
-  bool rank_overflow = false;
-  out->msg_off = off; out->msg_len = len;
-  walk_tensor(c, *out, raw, rank_overflow);
+// A bare TensorProto message (what tensor_proto_to_ndarray receives) occupying the cursor's record.
+B2_HD int walk_tensor_proto(Cursor& c, b200tfs_output* out) {
+  out_begin(*out);
+  ChunkTags ct; ct.chunk_overflow = false; ct.rank_overflow = false;
+  out->msg_off = 0; out->msg_len = c.end;
+  walk_tensor(c, *out, ct);
   if (c.err) return c.err;
-  finalize_output(*out, raw, rank_overflow);
+  finalize_output(*out, ct);
   return B200TFS_OK;
 }
 

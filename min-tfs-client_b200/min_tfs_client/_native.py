@@ -113,7 +113,7 @@ SIGNATURES = {
     "b200tfs_parse_responses": (C.c_int, [_vp, _vp, C.c_int32, _u64p, _u64p, C.c_int32, C.POINTER(Output), _i32p,
                                           C.POINTER(ModelSpec), _i32p]),
     "b200tfs_parse_tensor_protos": (C.c_int, [_vp, _vp, C.c_int32, _u64p, _u64p, C.POINTER(Output), _i32p]),
-    "b200tfs_unpack_outputs": (C.c_int, [_vp, _vp, C.c_int32, C.POINTER(Output), _vpp, _i32p, _i32p]),
+    "b200tfs_unpack_outputs": (C.c_int, [_vp, _vp, C.c_int32, C.POINTER(Output), _u64p, _vpp, _i32p, _i32p]),
     "b200tfs_decode_responses": (C.c_int, [_vp, _vp, C.c_int32, _u64p, _u64p, _vp, C.c_uint64]),
     "b200tfs_decode_results": (C.c_int, [_vp, C.c_int32, C.POINTER(Output), _i32p, C.POINTER(ModelSpec), _i32p]),
     "b200tfs_capture_begin": (C.c_int, [_vp]),
@@ -126,7 +126,7 @@ SIGNATURES = {
     "b200tfs_parse_responses_host": (C.c_int, [_vp, _vp, C.c_int32, _u64p, _u64p, C.c_int32, C.POINTER(Output), _i32p,
                                                C.POINTER(ModelSpec), _i32p]),
     "b200tfs_parse_tensor_protos_host": (C.c_int, [_vp, _vp, C.c_int32, _u64p, _u64p, C.POINTER(Output), _i32p]),
-    "b200tfs_unpack_outputs_host": (C.c_int, [_vp, C.c_int32, C.POINTER(Output), _vpp, _i32p, _i32p]),
+    "b200tfs_unpack_outputs_host": (C.c_int, [_vp, C.c_int32, C.POINTER(Output), _u64p, _vpp, _i32p, _i32p]),
 }
 
 _lib = None

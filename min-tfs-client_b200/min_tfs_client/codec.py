@@ -267,12 +267,13 @@ class Codec:
 
                 raise DecodeError(f"Error parsing message (response {i}, status {status[i]})")
             table = {}
+            base = int(off[i])  # table offsets are relative to the record
             for j in range(n_outs[i]):
                 o = outs[i * max_outputs + j]
-                table[self._text(buf, o.key_off, o.key_len)] = o
+                table[self._text(buf, base + o.key_off, o.key_len)] = o
             s = specs[i]
-            spec = DecodedSpec(self._text(buf, s.name_off, s.name_len), int(s.version), bool(s.has_version),
-                               self._text(buf, s.label_off, s.label_len), self._text(buf, s.signature_off, s.signature_len))
+            spec = DecodedSpec(self._text(buf, base + s.name_off, s.name_len), int(s.version), bool(s.has_version),
+                               self._text(buf, base + s.label_off, s.label_len), self._text(buf, base + s.signature_off, s.signature_len))
             parsed.append(ParsedResponse(buf, int(off[i]), int(ln[i]), int(status[i]), table, spec))
         return parsed
 
@@ -325,7 +326,7 @@ class Codec:
             for key, o in pr.outputs.items():
                 od = out_dtypes.get(key) if out_dtypes else None
                 if int(o.dtype) == DT_STRING and o.status == N.OK:
-                    results[i][0][key] = self._decode_strings(pr.wire, o)
+                    results[i][0][key] = self._decode_strings(pr.wire, pr.offset, o)
                     continue
                 np_type, dst_code, shape = self._resolve_output(o, strict, od)
                 jobs.append((i, key, o, np_type, dst_code, shape))
@@ -336,7 +337,8 @@ class Codec:
             dst = (C.c_void_p * m)(*[a.ctypes.data if a.size else None for a in arrays])
             codes = (C.c_int32 * m)(*[j[4] for j in jobs])
             status = (C.c_int32 * m)()
-            N.check(self._lib.b200tfs_unpack_outputs_host(self._ctx, m, outs, dst, codes, status))
+            rec = (C.c_uint64 * m)(*[parsed[j[0]].offset for j in jobs])
+            N.check(self._lib.b200tfs_unpack_outputs_host(self._ctx, m, outs, rec, dst, codes, status))
             for k, (i, key, o, np_type, dst_code, shape) in enumerate(jobs):
                 if status[k] == N.E_SHAPE:
                     raise ValueError(f"cannot reshape array into shape {shape}")
@@ -345,10 +347,10 @@ class Codec:
         return results
 
     @staticmethod
-    def _decode_strings(buf: np.ndarray, o: N.Output) -> np.ndarray:
+    def _decode_strings(buf: np.ndarray, base: int, o: N.Output) -> np.ndarray:
         from tensorflow.core.framework.tensor_pb2 import TensorProto
 
-        proto = TensorProto.FromString(buf[o.msg_off: o.msg_off + o.msg_len].tobytes())
+        proto = TensorProto.FromString(buf[base + o.msg_off: base + o.msg_off + o.msg_len].tobytes())
         shape = tuple(int(o.dims[k]) for k in range(o.rank))
         return np.array([e for e in proto.string_val], dtype=np.str_).reshape(*shape)
 
@@ -370,7 +372,7 @@ class Codec:
             N.check(status[i])
             o = outs[i]
             if int(o.dtype) == DT_STRING and o.status == N.OK:
-                results[i] = self._decode_strings(buf, o)
+                results[i] = self._decode_strings(buf, int(off[i]), o)
                 continue
             np_type, dst_code, shape = self._resolve_output(o, strict, out_dtype)
             jobs.append((i, o, np_type, dst_code, shape))
@@ -381,7 +383,8 @@ class Codec:
             dst = (C.c_void_p * m)(*[a.ctypes.data if a.size else None for a in arrays])
             codes = (C.c_int32 * m)(*[j[3] for j in jobs])
             st = (C.c_int32 * m)()
-            N.check(self._lib.b200tfs_unpack_outputs_host(self._ctx, m, o_arr, dst, codes, st))
+            rec = (C.c_uint64 * m)(*[int(off[j[0]]) for j in jobs])
+            N.check(self._lib.b200tfs_unpack_outputs_host(self._ctx, m, o_arr, rec, dst, codes, st))
             for k, (i, o, np_type, dst_code, shape) in enumerate(jobs):
                 if st[k] == N.E_SHAPE:
                     raise ValueError(f"cannot reshape array into shape {shape}")

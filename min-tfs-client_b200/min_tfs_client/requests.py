@@ -37,8 +37,8 @@ class PredictResponseView:
     def outputs(self) -> Dict[str, WireTensor]:
         if self._views is None:
             parsed = get_codec().parse_predict_responses([self._wire])[0]
-            buf = parsed.wire
-            self._views = {k: WireTensor(buf[o.msg_off: o.msg_off + o.msg_len].tobytes()) for k, o in parsed.outputs.items()}
+            buf, base = parsed.wire, parsed.offset
+            self._views = {k: WireTensor(buf[base + o.msg_off: base + o.msg_off + o.msg_len].tobytes()) for k, o in parsed.outputs.items()}
         return self._views
 
     def to_ndarrays(self, **options) -> Dict[str, np.ndarray]:

@@ -106,9 +106,30 @@ def test_fused_decode_c2(dev):
     o = outs[0]
     assert o.dtype == 1 and o.rank == 2 and o.dims[0] == 1024 and o.dims[1] == 1024 and o.status == 0
     got = dev.download(dst + o.dst_off, o.dst_bytes).view(np.float32).reshape(1024, 1024)
+    assert o.chunk_off[0] == len(wire) - 4 * 1024 * 1024 - 32 and o.key_off == 7  # offsets are record-relative
     ref = wire_oracle.decode_predict_response(wire)["y"]
     assert got.tobytes() == ref.tobytes()
     assert buf[specs[0].name_off: specs[0].name_off + specs[0].name_len].tobytes() == b"default" and specs[0].version == 1
+    # the second launch takes the framing-template fast path: same answer, fresh destination
+    x2 = np.random.default_rng(5).standard_normal((1024, 1024), dtype=np.float32)
+    wire2 = wire_oracle.build_predict_response([("y", x2)])
+    assert len(wire2) == len(wire)
+    N.check(dev.lib.b200tfs_memcpy_h2d(dev.ctx, dev.allocs[0], np.frombuffer(wire2, dtype=np.uint8).ctypes.data, len(wire2)))
+    off1, ln1 = (C.c_uint64 * 1)(0), (C.c_uint64 * 1)(len(wire2))
+    for _ in range(2):
+        N.check(dev.lib.b200tfs_memset(dev.ctx, dst, 0x11, 4 << 20))
+        N.check(dev.lib.b200tfs_decode_responses(dev.ctx, dev.allocs[0], 1, off1, ln1, dst, 4 << 20))
+        N.check(dev.lib.b200tfs_decode_results(dev.ctx, 1, outs, n_outs, specs, status))
+        assert status[0] == 0 and n_outs[0] == 1 and outs[0].dst_bytes == 4 << 20 and outs[0].dims[1] == 1024
+        assert dev.download(dst + outs[0].dst_off, 4 << 20).tobytes() == x2.tobytes()
+    # a response with different framing (other key) after a template was learnt: falls back to the walk
+    wire3 = wire_oracle.build_predict_response([("z", x2[:512])])
+    N.check(dev.lib.b200tfs_memcpy_h2d(dev.ctx, dev.allocs[0], np.frombuffer(wire3, dtype=np.uint8).ctypes.data, len(wire3)))
+    ln1[0] = len(wire3)
+    N.check(dev.lib.b200tfs_decode_responses(dev.ctx, dev.allocs[0], 1, off1, ln1, dst, 4 << 20))
+    N.check(dev.lib.b200tfs_decode_results(dev.ctx, 1, outs, n_outs, specs, status))
+    assert status[0] == 0 and outs[0].dims[0] == 512 and outs[0].key_len == 1
+    assert dev.download(dst + outs[0].dst_off, 2 << 20).tobytes() == x2[:512].tobytes()
 
 
 def test_fused_decode_batch_256(dev):
@@ -123,8 +144,8 @@ def test_fused_decode_batch_256(dev):
     for i in range(256):
         assert status[i] == 0 and n_outs[i] == 1
         o = outs[i * N.FUSED_MAX_OUTPUTS]
-        assert o.dst_off == i * 4096 and o.dst_bytes == 4000
-        assert whole[o.dst_off: o.dst_off + 4000].tobytes() == refs[i].tobytes(), i
+        assert o.dst_off == 0 and o.dst_bytes == 4000
+        assert whole[i * 4096: i * 4096 + 4000].tobytes() == refs[i].tobytes(), i
 
 
 def test_fused_decode_mixed_and_errors(dev):
@@ -140,7 +161,7 @@ def test_fused_decode_mixed_and_errors(dev):
     by_key = {}
     for k in range(n_outs[0]):
         o = outs[k]
-        by_key[buf[o.key_off: o.key_off + o.key_len].tobytes().decode()] = o
+        by_key[buf[o.key_off: o.key_off + o.key_len].tobytes().decode()] = o   # record 0 starts at arena offset 0
     assert dev.download(dst + by_key["a"].dst_off, 48).tobytes() == a.tobytes()
     assert dev.download(dst + by_key["d"].dst_off, 33 * 8).tobytes() == d.tobytes()
     ob = by_key["b"]  # varint output: tabulated, not moved by the fused kernel
@@ -149,7 +170,7 @@ def test_fused_decode_mixed_and_errors(dev):
     dptr = (C.c_void_p * 1)(dev.malloc(64))
     st = (C.c_int32 * 1)()
     o_arr = (N.Output * 1)(ob)
-    N.check(dev.lib.b200tfs_unpack_outputs(dev.ctx, dev.allocs[0] if False else _arena_of(dev, buf), 1, o_arr, dptr, None, st))
+    N.check(dev.lib.b200tfs_unpack_outputs(dev.ctx, _arena_of(dev, buf), 1, o_arr, None, dptr, None, st))
     assert st[0] == 0 and dev.download(dptr[0], 24).view(np.int64).tolist() == [5, -6, 7]
 
 
