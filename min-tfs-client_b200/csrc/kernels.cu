@@ -147,17 +147,18 @@ __device__ __forceinline__ uint64_t src_bytes_for(uint32_t op, uint64_t n_out) {
 // a 4 MiB tensor is smaller than the HBM bandwidth-delay product, so the whole tile must be in
 // flight at once - one DRAM round trip per batch, not per vector.
 // ------------------------------------------------------------------------------------------------
-constexpr uint32_t kBatch = 4;
+constexpr uint32_t kBatch = 4;         // shifted / cast paths (two source blocks per vector)
+constexpr uint32_t kBatchAligned = 8;  // aligned path: 8 x 16 B per thread = a 32 KB tile in one round trip
 
 template <uint32_t OP>
 __device__ __forceinline__ void body_aligned(const uint8_t* __restrict__ src, uint8_t* __restrict__ dst, uint32_t n) {
-  for (uint32_t v = threadIdx.x; v < n; v += kBatch * kMoveThreads) {
-    uint4 a[kBatch];
+  for (uint32_t v = threadIdx.x; v < n; v += kBatchAligned * kMoveThreads) {
+    uint4 a[kBatchAligned];
 #pragma unroll
-    for (uint32_t i = 0; i < kBatch; ++i)
+    for (uint32_t i = 0; i < kBatchAligned; ++i)
       if (v + i * kMoveThreads < n) a[i] = ld_stream(src + 16ull * (v + i * kMoveThreads));
 #pragma unroll
-    for (uint32_t i = 0; i < kBatch; ++i)
+    for (uint32_t i = 0; i < kBatchAligned; ++i)
       if (v + i * kMoveThreads < n) st_stream(dst + 16ull * (v + i * kMoveThreads), fix_vec<OP>(a[i]));
   }
 }
@@ -549,7 +550,7 @@ __device__ __noinline__ void fused_slow_path(const FusedParams& fp, uint32_t r, 
       fp.n_outs[r] = (st == B200TFS_OK) ? cnt : 0;
       fp.specs[r] = spec_s;
       for (int k = 0; k < cnt && st == B200TFS_OK; ++k) fp.outs[(size_t)r * kFusedMaxOutputs + k] = outs_s[k];
-      if (r == 0 && fp.tpl_write != nullptr) {
+      if (r == 0) {
         if (len <= 0x7FFFFFFFull) learn_template(fp.tpl_write, c, (uint32_t)len, outs_s, cnt, spec_s, st, fp.vpt, (cursor + 255) & ~255ull);
         else fp.tpl_write->valid = 0;
       }
@@ -580,32 +581,48 @@ __global__ void __launch_bounds__(kMoveThreads, 3) decode_fused_kernel(const __g
   uint8_t* dst_slot = fp.dst + (uint64_t)r * fp.dst_stride;
 
   // ---- fast path: does this record carry the template's framing? ----
+  // Every template word this thread needs is loaded up front (independent loads, one L2 round trip),
+  // then the record's framing byte (one DRAM round trip), then the tile.  The table is published by
+  // the record's LAST CTA - a slack CTA that has no tile to move - so no tile waits behind it.
   const Template* T = fp.tpl_read;
-  if (T != nullptr && T->valid && T->rec_len == len && T->vpt == fp.vpt && T->dst_need <= fp.dst_stride && T->total_tiles <= budget) {
-    const uint32_t i = threadIdx.x, nch = T->n_chunks;
-    bool same = true;
-    if (i < T->framing_len) {
-      uint32_t w = i;
-      for (uint32_t q = 0; q < nch; ++q) if (T->chunk[q].fpos <= i) w += T->chunk[q].len;
-      same = rec[w] == T->framing[i];
-    }
-    if (i < nch && T->chunk[i].is_varint && T->chunk[i].len) same = same && !(rec[T->chunk[i].wire_off + T->chunk[i].len - 1] & 0x80);
-    if (__syncthreads_and(same)) {
-      uint32_t t_base = 0;
-      for (uint32_t q = 0; q < nch; ++q) {
-        const uint32_t nt = T->chunk[q].n_tiles;
-        if (j >= t_base && j < t_base + nt)
-          move_tile(rec + T->chunk[q].wire_off, dst_slot + T->chunk[q].dst_off, T->chunk[q].len, T->chunk[q].op, nt, j - t_base, fp.vpt);
-        t_base += nt;
+  {
+    const uint32_t i = threadIdx.x;
+    const uint32_t t_valid = T->valid, nch = T->n_chunks, flen = T->framing_len, t_vpt = T->vpt, t_tiles = T->total_tiles;
+    const uint64_t t_len = T->rec_len, t_need = T->dst_need;
+    const uint8_t want = T->framing[i];
+    TplChunk ch[kTplChunks];
+#pragma unroll
+    for (uint32_t q = 0; q < kTplChunks; ++q) ch[q] = T->chunk[q];
+    if (t_valid && t_len == len && t_vpt == fp.vpt && t_need <= fp.dst_stride && t_tiles < budget) {
+      bool same = true;
+      if (i < flen) {
+        uint32_t w = i;
+#pragma unroll
+        for (uint32_t q = 0; q < kTplChunks; ++q) if (q < nch && ch[q].fpos <= i) w += ch[q].len;
+        same = rec[w] == want;
       }
-      if (j == 0) {
-        publish_words(fp.outs + (size_t)r * kFusedMaxOutputs, T->outs, T->n_outs * (uint32_t)sizeof(b200tfs_output));
-        publish_words(fp.specs + r, &T->spec, (uint32_t)sizeof(b200tfs_model_spec));
-        if (threadIdx.x == 0) { fp.status[r] = B200TFS_OK; fp.n_outs[r] = (int32_t)T->n_outs; }
-        // hand the template on to the next launch (launches alternate between the two slots)
-        if (r == 0 && fp.tpl_write != nullptr) publish_words(fp.tpl_write, T, (uint32_t)sizeof(Template));
+#pragma unroll
+      for (uint32_t q = 0; q < kTplChunks; ++q)
+        if (i == q && q < nch && ch[q].is_varint && ch[q].len) same = same && !(rec[ch[q].wire_off + ch[q].len - 1] & 0x80);
+      if (__syncthreads_and(same)) {
+        uint32_t t_base = 0;
+#pragma unroll
+        for (uint32_t q = 0; q < kTplChunks; ++q) {
+          if (q < nch) {
+            const uint32_t nt = ch[q].n_tiles;
+            if (j >= t_base && j < t_base + nt) move_tile(rec + ch[q].wire_off, dst_slot + ch[q].dst_off, ch[q].len, ch[q].op, nt, j - t_base, fp.vpt);
+            t_base += nt;
+          }
+        }
+        if (j == budget - 1) {
+          publish_words(fp.outs + (size_t)r * kFusedMaxOutputs, T->outs, T->n_outs * (uint32_t)sizeof(b200tfs_output));
+          publish_words(fp.specs + r, &T->spec, (uint32_t)sizeof(b200tfs_model_spec));
+          if (threadIdx.x == 0) { fp.status[r] = B200TFS_OK; fp.n_outs[r] = (int32_t)T->n_outs; }
+          // hand the template on to the next launch (launches alternate between the two slots)
+          if (r == 0) publish_words(fp.tpl_write, T, (uint32_t)sizeof(Template));
+        }
+        return;
       }
-      return;
     }
   }
 
