@@ -171,20 +171,17 @@ class World:
 # the GPU arm
 # ------------------------------------------------------------------------------------------------
 class Lane:
-    """One native context (= one CUDA stream) with its own ring of device-resident C2 buffers."""
+    """One native context (= one CUDA stream).  All lanes share one ring of device-resident C2 buffers."""
 
-    SHAPE = (1024, 1024)
-
-    def __init__(self, device, slots, seed0, shared):
+    def __init__(self, device, shared):
         from min_tfs_client import _native as N
 
         self.N, self.lib, self.S = N, N.load(), shared
         ctx = C.c_void_p()
         N.check(self.lib.b200tfs_create(device, C.byref(ctx)))
         self.ctx = ctx
-        self.slots = slots
         S = shared
-        self.dims = (C.c_int64 * 2)(*self.SHAPE)
+        self.dims = (C.c_int64 * 2)(*S.SHAPE)
         self.tensors = (N.Tensor * 1)(N.Tensor(data=256, src_dtype=1, wire_dtype=1, rank=2, flags=0, dims=self.dims, key=b"x", key_len=1,
                                                packed_len=0))
         self.requests = (N.Request * 1)(N.Request(model_name=b"default", model_name_len=7, has_version=1, order=N.ORDER_UPB, version=1,
@@ -192,24 +189,12 @@ class Lane:
         need = C.c_uint64(0)
         N.check(self.lib.b200tfs_request_arena_size(1, self.requests, C.byref(need)))
         self.arena_cap = int(need.value)
-        self.src, self.arena, self.resp, self.dst = [], [], [], []
-        for i in range(slots):
-            self.src.append(self._malloc(S.P))
-            self.arena.append(self._malloc(self.arena_cap))
-            self.resp.append(self._malloc(S.resp_len + 256))
-            self.dst.append(self._malloc(S.P))
-            k = (seed0 + i) % len(S.host_x)
-            N.check(self.lib.b200tfs_memcpy_h2d(self.ctx, self.src[i], S.host_x[k].ctypes.data, S.P))
-            N.check(self.lib.b200tfs_memcpy_h2d(self.ctx, self.resp[i], S.resp_host[k].ctypes.data, S.resp_len))
-            N.check(self.lib.b200tfs_memset(self.ctx, self.arena[i], 0, self.arena_cap))
-            N.check(self.lib.b200tfs_memset(self.ctx, self.dst[i], 0, S.P))
-        self.sync()
         self.rec_off, self.rec_len = (C.c_uint64 * 1)(), (C.c_uint64 * 1)()
         self.p_off, self.p_len = (C.c_uint64 * 1)(0), (C.c_uint64 * 1)(S.resp_len)
-        self.slot = 0
         self.graphs = {}
+        self.ring = None
 
-    def _malloc(self, nbytes):
+    def malloc(self, nbytes):
         p = C.c_void_p()
         self.N.check(self.lib.b200tfs_malloc(self.ctx, nbytes, C.byref(p)))
         return p.value
@@ -217,34 +202,30 @@ class Lane:
     def sync(self):
         self.N.check(self.lib.b200tfs_sync(self.ctx))
 
-    def footprint(self):
-        return self.slots * (self.S.P * 2 + self.arena_cap + self.S.resp_len)
-
     def encode(self, i):
-        self.tensors[0].data = self.src[i]
-        self.N.check(self.lib.b200tfs_encode_requests(self.ctx, 1, self.requests, self.arena[i], self.arena_cap, self.rec_off, self.rec_len))
+        R = self.ring
+        self.tensors[0].data = R.src[i]
+        self.N.check(self.lib.b200tfs_encode_requests(self.ctx, 1, self.requests, R.arena[i], self.arena_cap, self.rec_off, self.rec_len))
 
     def decode(self, i):
-        self.N.check(self.lib.b200tfs_decode_responses(self.ctx, self.resp[i], 1, self.p_off, self.p_len, self.dst[i], self.S.P))
+        R = self.ring
+        self.N.check(self.lib.b200tfs_decode_responses(self.ctx, R.resp[i], 1, self.p_off, self.p_len, R.dst[i], self.S.P))
 
-    def step_eager(self):
-        i = self.slot
-        self.slot = (i + 1) % self.slots
-        self.encode(i)
-        self.decode(i)
-
-    def capture(self, name, body, count):
-        """Record `count` consecutive ring slots of `body(slot)` into a CUDA graph."""
+    def capture(self, name, body, slots):
+        """Record body(slot) for every slot of `slots`, in order, into one CUDA graph."""
         lib, N = self.lib, self.N
-        for i in range(min(count, self.slots)):
+        for i in slots[:4]:
             body(i)          # warm: sizes every scratch buffer outside the capture
         self.sync()
         N.check(lib.b200tfs_capture_begin(self.ctx))
-        for k in range(count):
-            body(k % self.slots)
+        for i in slots:
+            body(i)
         g = C.c_void_p()
         N.check(lib.b200tfs_capture_end(self.ctx, C.byref(g)))
-        self.graphs[name] = (g, count)
+        old = self.graphs.get(name)
+        if old:
+            lib.b200tfs_graph_destroy(old[0])
+        self.graphs[name] = (g, len(slots))
         return g
 
     def launch(self, name):
@@ -254,6 +235,27 @@ class Lane:
         n = C.c_uint64(0)
         self.N.check(self.lib.b200tfs_kernel_launches(self.ctx, C.byref(n)))
         return int(n.value)
+
+
+class Ring:
+    """`slots` sets of {tensor, request arena, response wire, decoded tensor} resident in HBM."""
+
+    def __init__(self, lane, slots, shared):
+        S, N, lib = shared, lane.N, lane.lib
+        self.slots = slots
+        self.src, self.arena, self.resp, self.dst = [], [], [], []
+        for i in range(slots):
+            self.src.append(lane.malloc(S.P))
+            self.arena.append(lane.malloc(lane.arena_cap))
+            self.resp.append(lane.malloc(S.resp_len + 256))
+            self.dst.append(lane.malloc(S.P))
+            k = i % len(S.host_x)
+            N.check(lib.b200tfs_memcpy_h2d(lane.ctx, self.src[i], S.host_x[k].ctypes.data, S.P))
+            N.check(lib.b200tfs_memcpy_h2d(lane.ctx, self.resp[i], S.resp_host[k].ctypes.data, S.resp_len))
+            N.check(lib.b200tfs_memset(lane.ctx, self.arena[i], 0, lane.arena_cap))
+            N.check(lib.b200tfs_memset(lane.ctx, self.dst[i], 0, S.P))
+        lane.sync()
+        self.bytes = slots * (S.P * 2 + lane.arena_cap + S.resp_len)
 
 
 class Shared:
@@ -272,7 +274,7 @@ class Shared:
 
 
 class C2Bench:
-    """fp32 [1024,1024]: `streams` lanes, each with ring/streams slots of tensors / arenas / responses / outputs."""
+    """fp32 [1024,1024]: `streams` lanes working through one ring of `ring` buffer sets (lane s takes slots s, s+streams, ...)."""
 
     def __init__(self, device, ring, streams):
         from min_tfs_client import _native as N
@@ -280,10 +282,11 @@ class C2Bench:
         self.N, self.lib = N, N.load()
         self.S = Shared()
         self.P = self.S.P
-        per = max(1, ring // streams)
-        self.lanes = [Lane(device, per, s * per, self.S) for s in range(streams)]
-        self.ring = per * streams
+        self.lanes = [Lane(device, self.S) for _ in range(streams)]
         self.main = self.lanes[0]
+        self.ring = Ring(self.main, max(ring, streams), self.S)
+        for l in self.lanes:
+            l.ring = self.ring
         # pinned host buffers for the e2e leg (lane 0)
         self.pin_x = N.PinnedBuffer(self.P)
         self.pin_wire = N.PinnedBuffer(self.main.arena_cap)
@@ -297,7 +300,7 @@ class C2Bench:
         self.events = {}
 
     def footprint(self):
-        return sum(l.footprint() for l in self.lanes)
+        return self.ring.bytes
 
     def sync(self):
         for l in self.lanes:
@@ -337,15 +340,17 @@ class C2Bench:
     # ---- the timed workload: K steps split over the lanes, replayed from graphs --------------------
     def prepare(self, steps, graph_steps):
         self.plan = []
-        n = len(self.lanes)
+        n, R = len(self.lanes), self.ring.slots
         for s, l in enumerate(self.lanes):
             mine = steps // n + (1 if s < steps % n else 0)
             g = min(graph_steps, max(mine, 1))
             full, rem = divmod(mine, g)
+            slots = [(s + k * n) % R for k in range(g)]   # lane s walks the ring with stride n
+            body = lambda i, l=l: (l.encode(i), l.decode(i))  # noqa: E731
             if full:
-                l.capture("step", lambda i, l=l: (l.encode(i), l.decode(i)), g)
+                l.capture("step", body, slots)
             if rem:
-                l.capture("step_rem", lambda i, l=l: (l.encode(i), l.decode(i)), rem)
+                l.capture("step_rem", body, slots[:rem])
             self.plan.append((full, rem))
 
     def run_steps(self):
@@ -375,20 +380,24 @@ class C2Bench:
         return self.timed_region(enqueue)
 
     def verify(self):
-        """Bit-exact check of every lane's slot 0 against bytes built here from the inputs."""
-        lib, N, S = self.lib, self.N, self.S
+        """Bit-exact check, on every lane, of one ring slot against bytes built here from the inputs."""
+        lib, N, S, R = self.lib, self.N, self.S, self.ring
         for li, l in enumerate(self.lanes):
-            l.encode(0)
-            l.decode(0)
+            i = li % R.slots
+            N.check(lib.b200tfs_memset(l.ctx, R.arena[i], 0, l.arena_cap))
+            N.check(lib.b200tfs_memset(l.ctx, R.dst[i], 0, S.P))
+            for _ in range(2):   # second pass takes the decode kernel's template fast path
+                l.encode(i)
+                l.decode(i)
             l.sync()
             wire = np.empty(int(l.rec_len[0]), dtype=np.uint8)
-            N.check(lib.b200tfs_memcpy_d2h(l.ctx, wire.ctypes.data, l.arena[0] + int(l.rec_off[0]), wire.size))
+            N.check(lib.b200tfs_memcpy_d2h(l.ctx, wire.ctypes.data, R.arena[i] + int(l.rec_off[0]), wire.size))
             out = np.empty(S.SHAPE, dtype=np.float32)
-            N.check(lib.b200tfs_memcpy_d2h(l.ctx, out.ctypes.data, l.dst[0], S.P))
+            N.check(lib.b200tfs_memcpy_d2h(l.ctx, out.ctypes.data, R.dst[i], S.P))
             outs = (N.Output * N.FUSED_MAX_OUTPUTS)()
             n_outs, status = (C.c_int32 * 1)(), (C.c_int32 * 1)()
             N.check(lib.b200tfs_decode_results(l.ctx, 1, outs, n_outs, None, status))
-            x = S.host_x[(li * l.slots) % len(S.host_x)]
+            x = S.host_x[i % len(S.host_x)]
             assert wire.tobytes() == S.req_header + x.tobytes(), "encoded request differs from the expected wire bytes"
             assert out.tobytes() == x.tobytes(), "decoded tensor differs from the payload"
             assert status[0] == 0 and n_outs[0] == 1 and outs[0].dst_off == 0 and outs[0].dst_bytes == S.P
@@ -487,7 +496,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=480)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--ring", type=int, default=48, help="ring slots in total (split over the streams)")
-    ap.add_argument("--streams", type=int, default=4, help="independent lanes (native contexts = CUDA streams) per GPU")
+    ap.add_argument("--streams", type=int, default=8, help="independent lanes (native contexts = CUDA streams) per GPU")
     ap.add_argument("--graph-steps", type=int, default=48, help="steps recorded per CUDA graph")
     ap.add_argument("--e2e-steps", type=int, default=200)
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
@@ -529,8 +538,9 @@ def main():
     # the loop), ring > L2.  avg launch duration = region / launches (includes the inter-kernel gap).
     m = bench.main
     reps = 20
-    m.capture("enc", m.encode, m.slots * 4)
-    m.capture("dec", m.decode, m.slots * 4)
+    every = list(range(bench.ring.slots))            # the whole ring, so this pass is out of L2 as well
+    m.capture("enc", m.encode, every)
+    m.capture("dec", m.decode, every)
     per = {}
     for name in ("enc", "dec"):
         bench.timed_main(lambda: m.launch(name), 3)
@@ -567,8 +577,9 @@ def main():
             "warmup": warmup, "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "u8", "data": "synthetic",
             "config": {"workload": "C2 fp32[1024,1024] single-tensor PredictRequest encode + PredictResponse decode (BASELINE.json configs[1])",
-                       "payload_bytes_per_step": payload_per_step, "ring_slots": bench.ring, "ring_bytes": bench.footprint(),
-                       "l2": f"inputs rotate through a ring of {bench.ring} slots = {bench.footprint() >> 20} MiB > 126 MiB L2",
+                       "payload_bytes_per_step": payload_per_step, "ring_slots": bench.ring.slots, "ring_bytes": bench.footprint(),
+                       "l2": f"inputs rotate through a ring of {bench.ring.slots} slots = {bench.footprint() >> 20} MiB > 126 MiB L2 "
+                             "(timed region and roofline pass alike)",
                        "streams": len(bench.lanes), "cuda_graph_steps": args.graph_steps,
                        "wire_mode": "typed (float_val, sNaN-quieting on: bit-exact vs reference)", "sharding": "independent requests per GPU, no collective"},
             "roofline": roofline, "e2e": e2e, "gpu_launches": launches, "gpu_launches_outside_graphs": launches_eager, "clocks": clocks,

@@ -163,27 +163,48 @@ __device__ __forceinline__ void body_aligned(const uint8_t* __restrict__ src, ui
   }
 }
 
-// S = source body rounded down to 16 bytes; output vector v = bytes [k, k+16) of blocks v, v+1
+// S = source body rounded down to 16 bytes; output vector v = bytes [k, k+16) of blocks v, v+1.
+// Each source block is loaded ONCE: lane L takes block v+1 from lane L+1 by shuffle (lane 31, and
+// the last lane of a ragged tile, load it themselves: +1/32 traffic).  ncu showed why: two loads
+// of the same block in flight together are not merged - both go to DRAM (profiles/r01_*).
+__device__ __forceinline__ uint4 shfl_down1(const uint4& v) {
+  uint4 r;
+  r.x = __shfl_down_sync(0xFFFFFFFFu, v.x, 1); r.y = __shfl_down_sync(0xFFFFFFFFu, v.y, 1);
+  r.z = __shfl_down_sync(0xFFFFFFFFu, v.z, 1); r.w = __shfl_down_sync(0xFFFFFFFFu, v.w, 1);
+  return r;
+}
+
 template <uint32_t OP, int Q>
 __device__ __forceinline__ void body_shifted_q(const uint8_t* __restrict__ S, uint8_t* __restrict__ dst, uint32_t n, uint32_t s) {
   constexpr bool PRE = (OP == OP_QUIET_SRC);  // elements line up with the source blocks
-  for (uint32_t v = threadIdx.x; v < n; v += kBatch * kMoveThreads) {
-    uint4 lo[kBatch], hi[kBatch];
+  const bool edge = (threadIdx.x & 31) == 31;
+  // every lane of a warp runs the same number of rounds (shuffles need the whole warp)
+  const uint32_t rounds = (n + kBatch * kMoveThreads - 1) / (kBatch * kMoveThreads);
+  for (uint32_t rd = 0; rd < rounds; ++rd) {
+    const uint32_t v = rd * kBatch * kMoveThreads + threadIdx.x;
+    uint4 lo[kBatch], own[kBatch];
 #pragma unroll
-    for (uint32_t i = 0; i < kBatch; ++i)
-      if (v + i * kMoveThreads < n) {
-        lo[i] = ld_reuse(S + 16ull * (v + i * kMoveThreads));
-        hi[i] = ld_reuse(S + 16ull * (v + i * kMoveThreads) + 16);
+    for (uint32_t i = 0; i < kBatch; ++i) {
+      const uint32_t u = v + i * kMoveThreads;
+      lo[i] = make_uint4(0, 0, 0, 0); own[i] = make_uint4(0, 0, 0, 0);
+      if (u < n) {
+        lo[i] = ld_stream(S + 16ull * u);
+        if (edge || u + 1 >= n) own[i] = ld_stream(S + 16ull * u + 16);
       }
+    }
 #pragma unroll
-    for (uint32_t i = 0; i < kBatch; ++i)
-      if (v + i * kMoveThreads < n) {
-        uint4 a = lo[i], b = hi[i];
+    for (uint32_t i = 0; i < kBatch; ++i) {
+      const uint32_t u = v + i * kMoveThreads;
+      uint4 a = lo[i];
+      uint4 b = shfl_down1(lo[i]);
+      if (edge || u + 1 >= n) b = own[i];
+      if (u < n) {
         if (PRE) { a = fix_vec<OP>(a); b = fix_vec<OP>(b); }
         uint4 o = shift_pair<Q>(a, b, s);
         if (!PRE) o = fix_vec<OP>(o);
-        st_stream(dst + 16ull * (v + i * kMoveThreads), o);
+        st_stream(dst + 16ull * u, o);
       }
+    }
   }
 }
 
@@ -234,25 +255,36 @@ __device__ __forceinline__ uint32_t narrow2(uint32_t a, uint32_t b) {
 }
 template <bool BF, int Q>
 __device__ __forceinline__ void body_narrow_q(const uint8_t* __restrict__ S, uint8_t* __restrict__ dst, uint32_t n, uint32_t s, bool aligned) {
-  for (uint32_t v = threadIdx.x; v < n; v += 2 * kMoveThreads) {
-    uint4 a[2], b[2], c[2];
+  // output vector v (8 halfs) <- source blocks 2v, 2v+1 (+ 2v+2 when shifted: lane L+1's block 2v, by shuffle)
+  const bool edge = (threadIdx.x & 31) == 31;
+  const uint32_t rounds = (n + 2 * kMoveThreads - 1) / (2 * kMoveThreads);
+  for (uint32_t rd = 0; rd < rounds; ++rd) {
+    const uint32_t v = rd * 2 * kMoveThreads + threadIdx.x;
+    uint4 a[2], b[2], own[2];
 #pragma unroll
-    for (uint32_t i = 0; i < 2; ++i)
-      if (v + i * kMoveThreads < n) {
-        const uint8_t* p = S + 32ull * (v + i * kMoveThreads);
-        a[i] = ld_reuse(p); b[i] = ld_reuse(p + 16);
-        if (!aligned) c[i] = ld_reuse(p + 32);
+    for (uint32_t i = 0; i < 2; ++i) {
+      const uint32_t u = v + i * kMoveThreads;
+      a[i] = b[i] = own[i] = make_uint4(0, 0, 0, 0);
+      if (u < n) {
+        const uint8_t* p = S + 32ull * u;
+        a[i] = ld_stream(p); b[i] = ld_stream(p + 16);
+        if (!aligned && (edge || u + 1 >= n)) own[i] = ld_stream(p + 32);
       }
+    }
 #pragma unroll
-    for (uint32_t i = 0; i < 2; ++i)
-      if (v + i * kMoveThreads < n) {
+    for (uint32_t i = 0; i < 2; ++i) {
+      const uint32_t u = v + i * kMoveThreads;
+      uint4 c = shfl_down1(a[i]);
+      if (edge || u + 1 >= n) c = own[i];
+      if (u < n) {
         uint4 f0 = a[i], f1 = b[i];
-        if (!aligned) { f0 = shift_pair<Q>(a[i], b[i], s); f1 = shift_pair<Q>(b[i], c[i], s); }
+        if (!aligned) { f0 = shift_pair<Q>(a[i], b[i], s); f1 = shift_pair<Q>(b[i], c, s); }
         uint4 o;
         o.x = narrow2<BF>(f0.x, f0.y); o.y = narrow2<BF>(f0.z, f0.w);
         o.z = narrow2<BF>(f1.x, f1.y); o.w = narrow2<BF>(f1.z, f1.w);
-        st_stream(dst + 16ull * (v + i * kMoveThreads), o);
+        st_stream(dst + 16ull * u, o);
       }
+    }
   }
 }
 template <bool BF>

@@ -1,0 +1,82 @@
+#!/usr/bin/env python
+"""Summarise gpurun_out/ ncu artefacts into profiles/ (tracked).
+
+    python tools/ncu_summary.py r01      # reads gpurun_out/launches_r01.csv + gpurun_out/prof_r01.ncu-rep
+"""
+import collections
+import csv
+import json
+import os
+import subprocess
+import sys
+
+REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+OUT = os.path.join(REPO, "profiles")
+SRC = os.path.join(REPO, "gpurun_out")
+
+METRICS = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum", "lts__t_bytes.sum", "launch__grid_size",
+           "launch__block_size", "launch__registers_per_thread", "launch__occupancy_limit_registers", "sm__warps_active.avg.pct_of_peak_sustained_active",
+           "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed", "dram__cycles_active.avg", "sm__cycles_elapsed.max",
+           "smsp__inst_executed.sum", "l1tex__t_sectors_pipe_lsu_mem_global_op_ld.sum", "l1tex__t_sectors_pipe_lsu_mem_global_op_st.sum",
+           "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active"]
+
+
+def launches(tag):
+    path = os.path.join(SRC, f"launches_{tag}.csv")
+    lines = [l for l in open(path) if not l.startswith("==")]
+    agg = collections.defaultdict(list)
+    for row in csv.DictReader(lines):
+        if row.get("Metric Name") == "gpu__time_duration.sum":
+            agg[row["Kernel Name"].split("(")[0]].append(float(row["Metric Value"].replace(",", "")))
+    total = sum(sum(v) for v in agg.values())
+    out = []
+    for k, v in sorted(agg.items(), key=lambda kv: -sum(kv[1])):
+        v2 = sorted(v)
+        out.append({"kernel": k, "launches": len(v), "min_ns": v2[0], "median_ns": v2[len(v2) // 2], "max_ns": v2[-1], "sum_ns": sum(v),
+                    "share_of_gpu_time": sum(v) / total})
+    return out
+
+
+def full(tag):
+    rep = os.path.join(SRC, f"prof_{tag}.ncu-rep")
+    raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], stdout=subprocess.PIPE, text=True).stdout
+    rows = list(csv.reader(raw.splitlines()))
+    hdr, units = rows[0], rows[1]
+    out = []
+    for r in rows[2:]:
+        rec = {"kernel": r[hdr.index("Kernel Name")].split("(")[0]}
+        for m in METRICS:
+            if m in hdr:
+                i = hdr.index(m)
+                rec[m] = {"value": r[i], "unit": units[i]}
+        out.append(rec)
+    return out
+
+
+def main():
+    tag = sys.argv[1] if len(sys.argv) > 1 else "r01"
+    os.makedirs(OUT, exist_ok=True)
+    L = launches(tag)
+    F = full(tag)
+    with open(os.path.join(OUT, f"{tag}_ncu_summary.json"), "w") as fh:
+        json.dump({"launch_list": L, "full_capture": F,
+                   "how": {"launch_list": "ncu --metrics gpu__time_duration.sum --clock-control none -s 600 -c 400 python bench.py --steps 960 --warmup 96 --no-cpu",
+                           "full_capture": "ncu --set full --clock-control none --import-source on -k regex:'decode_fused|move_kernel' -s 600 -c 4 "
+                                           "python bench.py --steps 96 --warmup 96 --no-cpu --streams 1"}}, fh, indent=1)
+    with open(os.path.join(OUT, f"{tag}_launches.md"), "w") as fh:
+        fh.write(f"# ncu launch list, {tag} (cold-cache, serialised: compare shares, not absolutes)\n\n")
+        fh.write("| kernel | launches | min ns | median ns | max ns | share of GPU time |\n|---|---|---|---|---|---|\n")
+        for r in L:
+            fh.write(f"| {r['kernel']} | {r['launches']} | {r['min_ns']:.0f} | {r['median_ns']:.0f} | {r['max_ns']:.0f} | {r['share_of_gpu_time']:.3f} |\n")
+        fh.write("\n# ncu --set full, per captured launch\n\n")
+        for r in F:
+            fh.write(f"## {r['kernel']}\n\n")
+            for m in METRICS:
+                if m in r:
+                    fh.write(f"- `{m}` = {r[m]['value']} {r[m]['unit']}\n")
+            fh.write("\n")
+    print(open(os.path.join(OUT, f"{tag}_launches.md")).read())
+
+
+if __name__ == "__main__":
+    main()
