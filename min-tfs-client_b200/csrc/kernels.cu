@@ -613,43 +613,46 @@ __global__ void __launch_bounds__(kMoveThreads, 3) decode_fused_kernel(const __g
   uint8_t* dst_slot = fp.dst + (uint64_t)r * fp.dst_stride;
 
   // ---- fast path: does this record carry the template's framing? ----
-  // Every template word this thread needs is loaded up front (independent loads, one L2 round trip),
-  // then the record's framing byte (one DRAM round trip), then the tile.  The table is published by
-  // the record's LAST CTA - a slack CTA that has no tile to move - so no tile waits behind it.
+  // The template header and chunk table are staged in shared memory by five threads while every
+  // thread fetches its own template framing byte (all independent loads: one L2 round trip), then
+  // the record's framing byte (one DRAM round trip), then the tile.  (An earlier version kept the
+  // chunk table in a per-thread array: it landed in local memory, 32 KB of extra DRAM traffic per CTA.)
+  // The table is published by the record's LAST CTA - a slack CTA with no tile - so no tile waits on it.
   const Template* T = fp.tpl_read;
+  __shared__ TplChunk ch_s[kTplChunks];
+  __shared__ struct { uint32_t valid, n_chunks, n_outs, framing_len, vpt, total_tiles; uint64_t rec_len, dst_need; } th_s;
   {
     const uint32_t i = threadIdx.x;
-    const uint32_t t_valid = T->valid, nch = T->n_chunks, flen = T->framing_len, t_vpt = T->vpt, t_tiles = T->total_tiles;
-    const uint64_t t_len = T->rec_len, t_need = T->dst_need;
     const uint8_t want = T->framing[i];
-    TplChunk ch[kTplChunks];
-#pragma unroll
-    for (uint32_t q = 0; q < kTplChunks; ++q) ch[q] = T->chunk[q];
-    if (t_valid && t_len == len && t_vpt == fp.vpt && t_need <= fp.dst_stride && t_tiles < budget) {
+    if (i < kTplChunks) ch_s[i] = T->chunk[i];
+    if (i == kTplChunks) {
+      th_s.valid = T->valid; th_s.n_chunks = T->n_chunks; th_s.n_outs = T->n_outs; th_s.framing_len = T->framing_len;
+      th_s.vpt = T->vpt; th_s.total_tiles = T->total_tiles; th_s.rec_len = T->rec_len; th_s.dst_need = T->dst_need;
+    }
+    __syncthreads();
+    const uint32_t nch = th_s.n_chunks;
+    if (th_s.valid && th_s.rec_len == len && th_s.vpt == fp.vpt && th_s.dst_need <= fp.dst_stride && th_s.total_tiles < budget) {
       bool same = true;
-      if (i < flen) {
+      if (i < th_s.framing_len) {
         uint32_t w = i;
-#pragma unroll
-        for (uint32_t q = 0; q < kTplChunks; ++q) if (q < nch && ch[q].fpos <= i) w += ch[q].len;
+        for (uint32_t q = 0; q < nch; ++q) if (ch_s[q].fpos <= i) w += ch_s[q].len;
         same = rec[w] == want;
       }
-#pragma unroll
-      for (uint32_t q = 0; q < kTplChunks; ++q)
-        if (i == q && q < nch && ch[q].is_varint && ch[q].len) same = same && !(rec[ch[q].wire_off + ch[q].len - 1] & 0x80);
+      if (i < nch && ch_s[i].is_varint && ch_s[i].len) same = same && !(rec[ch_s[i].wire_off + ch_s[i].len - 1] & 0x80);
       if (__syncthreads_and(same)) {
         uint32_t t_base = 0;
-#pragma unroll
-        for (uint32_t q = 0; q < kTplChunks; ++q) {
-          if (q < nch) {
-            const uint32_t nt = ch[q].n_tiles;
-            if (j >= t_base && j < t_base + nt) move_tile(rec + ch[q].wire_off, dst_slot + ch[q].dst_off, ch[q].len, ch[q].op, nt, j - t_base, fp.vpt);
-            t_base += nt;
+        for (uint32_t q = 0; q < nch; ++q) {
+          const uint32_t nt = ch_s[q].n_tiles;
+          if (j >= t_base && j < t_base + nt) {
+            move_tile(rec + ch_s[q].wire_off, dst_slot + ch_s[q].dst_off, ch_s[q].len, ch_s[q].op, nt, j - t_base, fp.vpt);
+            break;
           }
+          t_base += nt;
         }
         if (j == budget - 1) {
-          publish_words(fp.outs + (size_t)r * kFusedMaxOutputs, T->outs, T->n_outs * (uint32_t)sizeof(b200tfs_output));
+          publish_words(fp.outs + (size_t)r * kFusedMaxOutputs, T->outs, th_s.n_outs * (uint32_t)sizeof(b200tfs_output));
           publish_words(fp.specs + r, &T->spec, (uint32_t)sizeof(b200tfs_model_spec));
-          if (threadIdx.x == 0) { fp.status[r] = B200TFS_OK; fp.n_outs[r] = (int32_t)T->n_outs; }
+          if (threadIdx.x == 0) { fp.status[r] = B200TFS_OK; fp.n_outs[r] = (int32_t)th_s.n_outs; }
           // hand the template on to the next launch (launches alternate between the two slots)
           if (r == 0) publish_words(fp.tpl_write, T, (uint32_t)sizeof(Template));
         }
