@@ -501,11 +501,15 @@ def main():
     ap.add_argument("--e2e-steps", type=int, default=200)
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     args = ap.parse_args()
-    world = World()
-    if args.impl == "reference":
-        run_reference(args, world)
-        world.close()
+    if args.impl == "reference":   # CPU only: rank 0 works alone, nobody needs a process group
+        class _Solo:
+            rank = int(os.environ.get("RANK", "0"))
+        run_reference(args, _Solo())
         return
+    # stdout carries exactly ONE JSON line: park fd 1 on stderr while libraries (NCCL prints its version) are chatty
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
+    world = World()
     warmup = max(args.warmup, 3)
     bench = C2Bench(world.local_rank, args.ring, args.streams)
     assert bench.footprint() > 2 * L2_BYTES, "ring must exceed L2"
@@ -588,7 +592,8 @@ def main():
             cb = cpu_baseline_port(2)
             cb["c_oracle_1core_gbs"] = cpu_c_oracle(8)["value"]
             line["cpu_baseline"] = cb
-        print(json.dumps(line))
+        sys.stdout.flush()
+        os.write(real_stdout, (json.dumps(line) + "\n").encode())
     world.close()
 
 
