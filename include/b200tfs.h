@@ -289,6 +289,18 @@ int b200tfs_wait_event(b200tfs_ctx* ctx, void* ev);
 int b200tfs_encode_requests_host(b200tfs_ctx* ctx, int32_t n, const b200tfs_request* reqs,
                                  void* wire_host, uint64_t wire_cap, uint64_t* rec_off,
                                  uint64_t* rec_len);
+/* Same, but returns as soon as the copies and kernels are queued (it only blocks for the measure pass
+ * when a varint dtype is present): call b200tfs_sync before reading wire_host, which must be pinned
+ * (b200tfs_host_alloc).  Two contexts running the _async entry points overlap H2D with D2H.        */
+int b200tfs_encode_requests_host_async(b200tfs_ctx* ctx, int32_t n, const b200tfs_request* reqs,
+                                       void* wire_host, uint64_t wire_cap, uint64_t* rec_off,
+                                       uint64_t* rec_len);
+/* Host-buffer form of b200tfs_decode_responses: copies the n responses to the device, runs the fused
+ * decode kernel and copies n*dst_stride bytes of decoded values back into dst_host (pinned), all
+ * queued asynchronously.  b200tfs_decode_results then synchronises and returns the table.          */
+int b200tfs_decode_responses_host_async(b200tfs_ctx* ctx, const void* wire_host, int32_t n,
+                                        const uint64_t* rec_off, const uint64_t* rec_len,
+                                        void* dst_host, uint64_t dst_stride);
 int b200tfs_encode_tensor_protos_host(b200tfs_ctx* ctx, int32_t n, const b200tfs_tensor* tensors,
                                       void* wire_host, uint64_t wire_cap, uint64_t* rec_off,
                                       uint64_t* rec_len);

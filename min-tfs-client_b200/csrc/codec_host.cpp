@@ -1096,8 +1096,8 @@ int b200tfs_encode_tensor_protos_host(b200tfs_ctx* c, int32_t n, const b200tfs_t
   return B200TFS_OK;
 }
 
-int b200tfs_encode_requests_host(b200tfs_ctx* c, int32_t n, const b200tfs_request* reqs, void* wire_host, uint64_t wire_cap,
-                                 uint64_t* rec_off, uint64_t* rec_len) {
+int b200tfs_encode_requests_host_async(b200tfs_ctx* c, int32_t n, const b200tfs_request* reqs, void* wire_host, uint64_t wire_cap,
+                                       uint64_t* rec_off, uint64_t* rec_len) {
   if (!c || n < 0 || (n && (!reqs || !wire_host || !rec_off || !rec_len))) return fail(B200TFS_E_ARG, "bad arguments");
   if (n == 0) return B200TFS_OK;
   CU(cudaSetDevice(c->device));
@@ -1109,7 +1109,7 @@ int b200tfs_encode_requests_host(b200tfs_ctx* c, int32_t n, const b200tfs_reques
   }
   int rc = stage_tensors(c, ts);
   if (rc) return rc;
-  if ((rc = b200tfs_measure(c, (int32_t)ts.size(), ts.data()))) return rc;
+  if ((rc = b200tfs_measure(c, (int32_t)ts.size(), ts.data()))) return rc;  // synchronises only if a varint dtype is present
   std::vector<b200tfs_request> rq(reqs, reqs + n);
   size_t k = 0;
   for (int i = 0; i < n; ++i) { rq[i].inputs = ts.data() + k; k += (size_t)rq[i].n_inputs; }
@@ -1120,8 +1120,15 @@ int b200tfs_encode_requests_host(b200tfs_ctx* c, int32_t n, const b200tfs_reques
   const uint64_t lo = rec_off[0], hi = rec_off[n - 1] + rec_len[n - 1];
   if (hi - lo > wire_cap) return fail(B200TFS_E_SIZE, "wire buffer too small: need %llu bytes", (unsigned long long)(hi - lo));
   CU(cudaMemcpyAsync(wire_host, (uint8_t*)c->arena_dev.p + lo, hi - lo, cudaMemcpyDeviceToHost, c->stream));
-  CU(cudaStreamSynchronize(c->stream));
   for (int i = 0; i < n; ++i) rec_off[i] -= lo;
+  return B200TFS_OK;
+}
+
+int b200tfs_encode_requests_host(b200tfs_ctx* c, int32_t n, const b200tfs_request* reqs, void* wire_host, uint64_t wire_cap,
+                                 uint64_t* rec_off, uint64_t* rec_len) {
+  int rc = b200tfs_encode_requests_host_async(c, n, reqs, wire_host, wire_cap, rec_off, rec_len);
+  if (rc) return rc;
+  CU(cudaStreamSynchronize(c->stream));
   return B200TFS_OK;
 }
 
@@ -1156,6 +1163,20 @@ int b200tfs_parse_tensor_protos_host(b200tfs_ctx* c, const void* wire_host, int3
   int rc = stage_wire(c, wire_host, n, rec_off, rec_len, &span);
   if (rc) return rc;
   return parse_common(c, c->stage_dev.p, n, rec_off, rec_len, 1, true, outs, nullptr, nullptr, rec_status);
+}
+
+int b200tfs_decode_responses_host_async(b200tfs_ctx* c, const void* wire_host, int32_t n, const uint64_t* rec_off, const uint64_t* rec_len,
+                                        void* dst_host, uint64_t dst_stride) {
+  if (!c || n < 0 || (n && (!wire_host || !rec_off || !rec_len || !dst_host))) return fail(B200TFS_E_ARG, "bad arguments");
+  if (n == 0) return B200TFS_OK;
+  CU(cudaSetDevice(c->device));
+  uint64_t span;
+  int rc = stage_wire(c, wire_host, n, rec_off, rec_len, &span);
+  if (rc) return rc;
+  if ((rc = grow_dev(c, c->arena_dev, dst_stride * (uint64_t)n + 256))) return rc;
+  if ((rc = b200tfs_decode_responses(c, c->stage_dev.p, n, rec_off, rec_len, c->arena_dev.p, dst_stride))) return rc;
+  CU(cudaMemcpyAsync(dst_host, c->arena_dev.p, dst_stride * (uint64_t)n, cudaMemcpyDeviceToHost, c->stream));
+  return B200TFS_OK;
 }
 
 int b200tfs_unpack_outputs_host(b200tfs_ctx* c, int32_t m, const b200tfs_output* outs, const uint64_t* out_rec_off, void* const* dst_host,
