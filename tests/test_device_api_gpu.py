@@ -221,3 +221,93 @@ def test_graph_replay_encode_decode(dev):
     assert wire == wire_oracle.encode_predict_request("m", 3, [("x", x2)])
     assert dev.download(dst, x2.nbytes).tobytes() == x2.tobytes()
     lib.b200tfs_graph_destroy(g)
+
+
+def test_c5_full_size_batch_1024(dev):
+    """BASELINE configs[4] per-GPU share: 1024 PredictRequests of fp32 [3,224,224] in ONE encode call,
+    then 1024 PredictResponses of the same size through the fused decode (table path, n > 16).
+
+    Size-independent checks: every record length equals the closed form (602164), a stride-64
+    sample is compared byte for byte with the oracle, the XOR-fold of all payload words on the wire equals
+    the XOR-fold of all input words (no byte lost, duplicated or altered anywhere in 617 MB), and
+    decode(encode-side payloads) returns the inputs exactly."""
+    n = 1024
+    base = np.random.default_rng(42).standard_normal((3, 224, 224), dtype=np.float32)
+    big = np.empty((n, 3, 224, 224), dtype=np.float32)
+    for i in range(n):
+        np.add(base, np.float32(i) * np.float32(0.001), out=big[i])
+    src = dev.upload(big)
+    P = 3 * 224 * 224 * 4
+    dims = (C.c_int64 * 3)(3, 224, 224)
+    ts = (N.Tensor * n)()
+    rq = (N.Request * n)()
+    for i in range(n):
+        ts[i] = N.Tensor(data=src + i * P, src_dtype=1, wire_dtype=1, rank=3, flags=0, dims=dims, key=b"image", key_len=5, packed_len=0)
+        rq[i] = N.Request(model_name=b"default", model_name_len=7, has_version=1, order=N.ORDER_UPB, version=1, n_inputs=1, reserved=0,
+                          inputs=C.cast(C.byref(ts, i * C.sizeof(N.Tensor)), C.POINTER(N.Tensor)))
+    need = C.c_uint64()
+    N.check(dev.lib.b200tfs_request_arena_size(n, rq, C.byref(need)))
+    arena = dev.malloc(need.value)
+    off, ln = (C.c_uint64 * n)(), (C.c_uint64 * n)()
+    N.check(dev.lib.b200tfs_encode_requests(dev.ctx, n, rq, arena, need.value, off, ln))
+    dev.sync()
+    assert all(ln[i] == 602164 for i in range(n))
+    whole = dev.download(arena, need.value)
+    for i in range(0, n, 64):
+        expect = wire_oracle.encode_predict_request("default", 1, [("image", big[i])])
+        assert whole[off[i]: off[i] + ln[i]].tobytes() == expect, i
+    fold_in = np.bitwise_xor.reduce(big.view(np.uint32).reshape(-1))
+    fold_wire = np.uint32(0)
+    H = 602164 - P
+    for i in range(n):
+        fold_wire ^= np.bitwise_xor.reduce(whole[off[i] + H: off[i] + H + P].view(np.uint32))
+    assert fold_wire == fold_in
+    # responses of the same payloads, canonical server layout, decoded in one fused launch
+    prefix = wire_oracle.build_predict_response([("image", big[0])])
+    hdr_len = len(prefix) - P - 32      # bytes before the payload (32 = trailing model_spec field)
+    head, tail = prefix[:hdr_len], prefix[hdr_len + P:]
+    stride = (len(prefix) + 255) & ~255
+    buf = np.zeros(stride * n, dtype=np.uint8)
+    hb, tb = np.frombuffer(head, np.uint8), np.frombuffer(tail, np.uint8)
+    roff, rlen = (C.c_uint64 * n)(), (C.c_uint64 * n)()
+    flat = big.view(np.uint8).reshape(n, P)
+    for i in range(n):
+        o = i * stride
+        buf[o: o + hdr_len] = hb
+        buf[o + hdr_len: o + hdr_len + P] = flat[i]
+        buf[o + hdr_len + P: o + len(prefix)] = tb
+        roff[i], rlen[i] = o, len(prefix)
+    assert buf[: len(prefix)].tobytes() == prefix
+    wire_dev = dev.upload(buf)
+    dst_stride = (P + 255) & ~255
+    dst = dev.malloc(dst_stride * n)
+    for _ in range(2):   # second pass: framing-template fast path for all 1024 records
+        N.check(dev.lib.b200tfs_memset(dev.ctx, dst, 0, dst_stride * n))
+        N.check(dev.lib.b200tfs_decode_responses(dev.ctx, wire_dev, n, roff, rlen, dst, dst_stride))
+        outs = (N.Output * (n * N.FUSED_MAX_OUTPUTS))()
+        n_outs, status = (C.c_int32 * n)(), (C.c_int32 * n)()
+        N.check(dev.lib.b200tfs_decode_results(dev.ctx, n, outs, n_outs, None, status))
+        assert all(status[i] == 0 and n_outs[i] == 1 for i in range(n))
+        got = dev.download(dst, dst_stride * n).reshape(n, dst_stride)[:, :P]
+        assert np.array_equal(got, flat)
+
+
+def test_c4_cast_round_trip(dev, codec):
+    """BASELINE configs[3]: fp16 / bf16 [8,512,1024] cast to DT_FLOAT on encode (wire bit-exact vs the oracle on
+    x.astype(float32)) and cast back on decode (round-to-nearest-even: exact for values that came from 16 bits)."""
+    import ml_dtypes
+
+    rng = np.random.default_rng(4)
+    for np_dt in (np.float16, ml_dtypes.bfloat16):
+        x = rng.standard_normal((8, 512, 1024)).astype(np_dt)
+        x.reshape(-1)[:4] = np.array([np.inf, -np.inf, 0.0, -0.0]).astype(np_dt)
+        wire = codec.encode_predict_request("default", {"x": x}, 1, wire_dtype="DT_FLOAT")
+        assert wire == wire_oracle.encode_predict_request("default", 1, [("x", x.astype(np.float32))])
+        resp = wire_oracle.build_predict_response([("y", x.astype(np.float32))])
+        back = codec.decode_predict_response(resp, out_dtypes={"y": np_dt})[0]["y"]
+        assert back.dtype == np.dtype(np_dt) and back.tobytes() == x.tobytes()
+        # a float32 payload that is NOT representable in 16 bits rounds to nearest even, like numpy's astype
+        f = rng.standard_normal((1000, 37)).astype(np.float32)
+        resp = wire_oracle.build_predict_response([("y", f)])
+        back = codec.decode_predict_response(resp, out_dtypes={"y": np_dt})[0]["y"]
+        assert np.array_equal(back.view(np.uint16), f.astype(np_dt).view(np.uint16))
