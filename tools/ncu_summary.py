@@ -38,18 +38,21 @@ def launches(tag):
 
 
 def full(tag):
-    rep = os.path.join(SRC, f"prof_{tag}.ncu-rep")
-    raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], stdout=subprocess.PIPE, text=True).stdout
-    rows = list(csv.reader(raw.splitlines()))
-    hdr, units = rows[0], rows[1]
     out = []
-    for r in rows[2:]:
-        rec = {"kernel": r[hdr.index("Kernel Name")].split("(")[0]}
-        for m in METRICS:
-            if m in hdr:
-                i = hdr.index(m)
-                rec[m] = {"value": r[i], "unit": units[i]}
-        out.append(rec)
+    for suffix in ("", "_enc", "_dec"):
+        rep = os.path.join(SRC, f"prof_{tag}{suffix}.ncu-rep")
+        if not os.path.exists(rep):
+            continue
+        raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], stdout=subprocess.PIPE, text=True).stdout
+        rows = list(csv.reader(raw.splitlines()))
+        hdr, units = rows[0], rows[1]
+        for r in rows[2:]:
+            rec = {"kernel": r[hdr.index("Kernel Name")].split("(")[0], "report": os.path.basename(rep)}
+            for m in METRICS:
+                if m in hdr:
+                    i = hdr.index(m)
+                    rec[m] = {"value": r[i], "unit": units[i]}
+            out.append(rec)
     return out
 
 
@@ -60,9 +63,9 @@ def main():
     F = full(tag)
     with open(os.path.join(OUT, f"{tag}_ncu_summary.json"), "w") as fh:
         json.dump({"launch_list": L, "full_capture": F,
-                   "how": {"launch_list": "ncu --metrics gpu__time_duration.sum --clock-control none -s 600 -c 400 python bench.py --steps 960 --warmup 96 --no-cpu",
-                           "full_capture": "ncu --set full --clock-control none --import-source on -k regex:'decode_fused|move_kernel' -s 600 -c 4 "
-                                           "python bench.py --steps 96 --warmup 96 --no-cpu --streams 1"}}, fh, indent=1)
+                   "how": {"launch_list": "ncu --metrics gpu__time_duration.sum --clock-control none -s 900 -c 400 python bench.py --steps 960 --warmup 96 --no-cpu --e2e-steps 10",
+                           "full_capture": "ncu --set full --clock-control none --import-source on -k regex:<move_kernel_inline|decode_fused> -s 300 -c 2 "
+                                           "python bench.py --steps 96 --warmup 96 --no-cpu --e2e-steps 10 --streams 1"}}, fh, indent=1)
     with open(os.path.join(OUT, f"{tag}_launches.md"), "w") as fh:
         fh.write(f"# ncu launch list, {tag} (cold-cache, serialised: compare shares, not absolutes)\n\n")
         fh.write("| kernel | launches | min ns | median ns | max ns | share of GPU time |\n|---|---|---|---|---|---|\n")
