@@ -274,8 +274,10 @@ int b200tfs_decode_results(b200tfs_ctx* ctx, int32_t n, b200tfs_output* outs, in
 /* ---- CUDA graphs: record a fixed sequence of encode / decode calls once, replay it per request ---
  * Between capture_begin and capture_end the asynchronous entry points (b200tfs_encode_requests,
  * b200tfs_encode_tensor_protos, b200tfs_decode_responses, b200tfs_memcpy_*) only record work; calls
- * that must synchronise or allocate fail with B200TFS_E_ARG.  Run the same calls once before capturing
- * so every scratch buffer has its final size.                                                      */
+ * that must synchronise (b200tfs_measure, the parse / *_host entry points, b200tfs_sync) fail with
+ * B200TFS_E_ARG.  Run the same calls once before capturing so every scratch buffer has its final
+ * size.  Plan images of batches too large for the kernel parameters get buffers of their own that
+ * live until the context is destroyed.                                                             */
 int b200tfs_capture_begin(b200tfs_ctx* ctx);
 int b200tfs_capture_end(b200tfs_ctx* ctx, void** graph_exec);
 int b200tfs_graph_launch(b200tfs_ctx* ctx, void* graph_exec);

@@ -76,7 +76,8 @@ struct b200tfs_ctx {
   Growable arena_dev;     // *_host entry points: wire arena (encode) / unpacked tensors (decode)
   uint64_t launches = 0;
   uint32_t tile_bytes_override = 0;
-  bool capturing = false;   // between b200tfs_capture_begin / _end: no syncs, no allocations
+  bool capturing = false;   // between b200tfs_capture_begin / _end: no syncs; uploads get buffers that live as long as the context
+  std::vector<Slot*> graph_slots;  // plan images referenced by captured graphs
   Growable fused_host;      // decode_fused tables: pinned host memory the kernel writes directly
   void* tpl_dev = nullptr;  // two framing templates (device), used alternately by successive decode launches
   uint32_t tpl_flip = 0;
@@ -110,7 +111,22 @@ static int grow_host(b200tfs_ctx* c, Growable& g, uint64_t need) {
 
 // claim an upload slot with room for `bytes` in both images
 static int claim_slot(b200tfs_ctx* c, uint64_t bytes, Slot** out) {
-  if (c->capturing) return fail(B200TFS_E_ARG, "this call needs a plan upload, which cannot be captured into a graph (batch too large for the inline plan)");
+  if (c->capturing) {
+    // a captured launch must keep its plan image for as long as the graph may be replayed: give it private
+    // buffers (the upload itself is recorded as a copy node and simply repeats on every replay)
+    Slot* g = new Slot();
+    cudaError_t e = cudaHostAlloc(&g->host.p, bytes, cudaHostAllocPortable);
+    if (e == cudaSuccess) e = cudaMalloc(&g->dev.p, bytes);
+    if (e != cudaSuccess) {
+      if (g->host.p) cudaFreeHost(g->host.p);
+      delete g;
+      return fail(B200TFS_E_CUDA, "plan buffers for a captured launch: %s", cudaGetErrorString(e));
+    }
+    g->host.cap = g->dev.cap = bytes;
+    c->graph_slots.push_back(g);
+    *out = g;
+    return B200TFS_OK;
+  }
   Slot& s = c->slots[c->next_slot];
   c->next_slot = (c->next_slot + 1) % kSlots;
   if (s.pending) { CU(cudaEventSynchronize(s.done)); s.pending = false; }
@@ -170,6 +186,7 @@ int b200tfs_destroy(b200tfs_ctx* c) {
   }
   if (c->fused_host.p) cudaFreeHost(c->fused_host.p);
   if (c->tpl_dev) cudaFree(c->tpl_dev);
+  for (Slot* g : c->graph_slots) { cudaFreeHost(g->host.p); cudaFree(g->dev.p); delete g; }
   if (c->scratch_dev.p) cudaFree(c->scratch_dev.p);
   if (c->scratch_host.p) cudaFreeHost(c->scratch_host.p);
   if (c->stage_dev.p) cudaFree(c->stage_dev.p);
@@ -488,7 +505,7 @@ int launch_plan(b200tfs_ctx* c, PlanBuilder& pb) {
   }
   CU(launch_move(plan_dev, img, (uint32_t)image, ph.n_tiles, ph.n_small, c->stream));
   c->launches += 1;
-  if (slot) { CU(cudaEventRecord(slot->done, c->stream)); slot->pending = true; }
+  if (slot && slot->done) { CU(cudaEventRecord(slot->done, c->stream)); slot->pending = true; }
   return B200TFS_OK;
 }
 
@@ -759,6 +776,7 @@ static int parse_common(b200tfs_ctx* c, const void* arena_dev, int32_t n, const 
   if (!c || n < 0 || (n && (!arena_dev || !rec_off || !rec_len || !outs || !rec_status))) return fail(B200TFS_E_ARG, "bad arguments");
   if (!bare && (max_outputs <= 0 || !n_outs || !specs)) return fail(B200TFS_E_ARG, "bad arguments");
   if (n == 0) return B200TFS_OK;
+  if (c->capturing) return fail(B200TFS_E_ARG, "the two-phase parse synchronises and cannot be captured: use b200tfs_decode_responses");
   CU(cudaSetDevice(c->device));
   if (bare) max_outputs = 1;
   const uint64_t stride = bare ? 1 : (uint64_t)max_outputs + 1;  // responses: one scratch slot per record
@@ -958,8 +976,7 @@ int b200tfs_decode_responses(b200tfs_ctx* c, const void* arena_dev, int32_t n, c
     memcpy(h + o_off, rec_off, 8ull * n);
     memcpy(h + o_len, rec_len, 8ull * n);
     CU(cudaMemcpyAsync(slot->dev.p, h, image, cudaMemcpyHostToDevice, c->stream));
-    CU(cudaEventRecord(slot->done, c->stream));
-    slot->pending = true;
+    if (slot->done) { CU(cudaEventRecord(slot->done, c->stream)); slot->pending = true; }
     uint8_t* sd = (uint8_t*)slot->dev.p;
     fp.cta_rec = (const uint32_t*)sd; fp.tile_start = (const uint32_t*)(sd + o_ts);
     fp.rec_off = (const uint64_t*)(sd + o_off); fp.rec_len = (const uint64_t*)(sd + o_len);
@@ -992,7 +1009,7 @@ int b200tfs_capture_begin(b200tfs_ctx* c) {
   CU(cudaSetDevice(c->device));
   CU(cudaStreamSynchronize(c->stream));
   for (auto& s : c->slots) s.pending = false;
-  CU(cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeThreadLocal));
+  CU(cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeRelaxed));
   c->capturing = true;
   return B200TFS_OK;
 }
