@@ -185,6 +185,78 @@ B2_HD uint32_t rd_string(Cursor& c, uint32_t* len) {
   return at;
 }
 
+// Structural validation of the message-typed TensorProto fields this path never reads
+// (resource_handle_val = 14, variant_val = 15).  The runtime parses them recursively, so malformed
+// bytes inside them fail the whole response; this walks the same schemas (resource_handle.proto:16-42,
+// tensor.proto:87-94, tensor_shape.proto:13-46) with an explicit stack instead of recursion
+// (variant_val can nest TensorProtos): tags, lengths, packed-field shape and UTF-8 of string fields.
+enum NestedType : uint32_t { NT_TENSOR = 0, NT_SHAPE, NT_DIM, NT_RESOURCE, NT_DTYPE_AND_SHAPE, NT_VARIANT };
+
+// what field `f` of message type `t` is: 0 = unknown/scalar (skip by wire type), 1 = string (UTF-8),
+// 2 = packed-or-scalar numeric (TensorProto value fields), 0x10 | type = sub-message to descend into
+B2_HD uint32_t nested_field_kind(uint32_t t, uint32_t f) {
+  switch (t) {
+    case NT_TENSOR:
+      if (f == F_SHAPE) return 0x10 | NT_SHAPE;
+      if (f == F_RESOURCE) return 0x10 | NT_RESOURCE;
+      if (f == F_VARIANT) return 0x10 | NT_VARIANT;
+      if (scalar_wire_type(f) != 0xFFu) return 2;
+      return 0;
+    case NT_SHAPE: return f == 2 ? (0x10 | NT_DIM) : 0;
+    case NT_DIM: return f == 2 ? 1 : 0;
+    case NT_RESOURCE:
+      if (f == 1 || f == 2 || f == 3 || f == 5) return 1;
+      return f == 6 ? (0x10 | NT_DTYPE_AND_SHAPE) : 0;
+    case NT_DTYPE_AND_SHAPE: return f == 2 ? (0x10 | NT_SHAPE) : 0;
+    default:  // NT_VARIANT
+      if (f == 1) return 1;
+      return f == 3 ? (0x10 | NT_TENSOR) : 0;
+  }
+}
+
+constexpr int kNestedDepth = 16;
+
+// validate a sub-message of `type` occupying [c.p, c.p + len); leaves c.p at its end.  Returns false
+// (without flagging a parse error) only when nesting exceeds kNestedDepth.
+B2_HD bool validate_nested(Cursor& c, uint32_t type, uint32_t len) {
+  uint32_t end_stack[kNestedDepth];
+  uint8_t type_stack[kNestedDepth];
+  int depth = 0;
+  const uint32_t outer = c.end;
+  c.end = c.p + len;
+#pragma unroll 1
+  for (;;) {
+    if (c.err) break;
+    if (c.p >= c.end) {  // this message is complete: back to its parent
+      if (depth == 0) break;
+      --depth;
+      c.end = end_stack[depth]; type = type_stack[depth];
+      continue;
+    }
+    const uint32_t tag = rd_tag(c);
+    if (c.err) break;
+    const uint32_t f = tag >> 3, wt = tag & 7;
+    const uint32_t kind = nested_field_kind(type, f);
+    if (kind == 1 && wt == WT_LEN) { uint32_t k; (void)rd_string(c, &k); }
+    else if (kind == 2 && wt == WT_LEN) {
+      const uint32_t n = rd_len(c);
+      if (c.err) break;
+      const uint32_t fw = fixed_wire_width(f);
+      if (fw ? (n % fw) != 0 : (n && (rd8(c, c.p + n - 1) & 0x80))) { c.err = B200TFS_E_PARSE; break; }
+      c.p += n;
+    } else if ((kind & 0x10) && wt == WT_LEN) {
+      const uint32_t n = rd_len(c);
+      if (c.err) break;
+      if (depth >= kNestedDepth) { c.end = outer; return false; }
+      end_stack[depth] = c.end; type_stack[depth] = (uint8_t)type;
+      ++depth;
+      c.end = c.p + n; type = kind & 0xF;
+    } else skip_field(c, tag);
+  }
+  c.end = outer;
+  return true;
+}
+
 // Begin a fresh output record: only the fields the walk accumulates into.
 B2_HD void out_begin(b200tfs_output& o) {
   o.key_off = 0; o.key_len = 0; o.dtype = 0; o.rank = 0; o.flags = 0; o.value_field = 0; o.n_chunks = 0;
@@ -278,9 +350,13 @@ B2_HD void walk_tensor(Cursor& c, b200tfs_output& o, ChunkTags& ct) {
           ++o.n_chunks;
         } else ct.chunk_overflow = true;
       }
+    } else if ((field == F_RESOURCE || field == F_VARIANT) && wt == WT_LEN) {
+      const uint32_t n = rd_len(c);
+      if (c.err) return;
+      if (!validate_nested(c, field == F_RESOURCE ? NT_RESOURCE : NT_VARIANT, n)) ct.rank_overflow = true;  // too deep: NONCANONICAL
     } else {
       if (field > 17) o.flags |= B200TFS_OF_HAS_UNKNOWN;
-      skip_field(c, tag);  // version_number, resource_handle_val, variant_val, mismatched wire types, unknown
+      skip_field(c, tag);  // version_number, mismatched wire types, unknown
     }
   }
 }
@@ -400,6 +476,7 @@ B2_HD int walk_response(Cursor& c, int max_outputs, b200tfs_output* outs, int* n
       b200tfs_output& o = outs[n];  // parsed in place (slot n <= max_outputs); merged away below if the key repeats
       out_begin(o);
       ChunkTags ct; ct.chunk_overflow = false; ct.rank_overflow = false;
+      bool foreign = false;  // the entry itself carries a field that is not key/value
       const uint32_t outer = c.end;
       c.end = c.p + elen;
 #pragma unroll 1
@@ -419,10 +496,14 @@ B2_HD int walk_response(Cursor& c, int max_outputs, b200tfs_output* outs, int* n
           c.end = c.p + m;
           walk_tensor(c, o, ct);
           c.end = inner;
-        } else skip_field(c, t);
+        } else { skip_field(c, t); foreign = true; }
       }
       c.end = outer;
       if (c.err) break;
+      // The runtime cannot keep unknown fields inside a map, so an entry that directly carries one
+      // (incl. key/value with a mismatched wire type) stays an unknown field of the response and never
+      // reaches the outputs map (pinned: tests/golden/decode.json "entry_with_foreign_field").
+      if (foreign) continue;
       finalize_output(o, ct);
       // duplicate key: the later entry replaces the earlier one
       int slot = -1;

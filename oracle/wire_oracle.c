@@ -3,10 +3,10 @@
  * legs may (the product has no CPU path at all).
  *
  * A plain-C, scalar restatement of what the reference's Predict hot path puts on the wire and reads
- * back, pinned against vectors produced by the unmodified reference (tests/golden/*.json, generated
+ * back, pinned against vectors produced by the unmodified reference (tests/golden/, generated
  * by tests/golden/make_golden.py in the build container; tests/test_oracle.py replays every one of
  * them through this file).  Parity status: PINNED (encode: 43 TensorProto + 18 PredictRequest
- * vectors; decode: 50 PredictResponse vectors incl. every error class).
+ * vectors; decode: 58 PredictResponse vectors incl. every error class).
  *
  * Reference behaviour restated (paths relative to the reference checkout):
  *   tensor_serving_client/min_tfs_client/tensors.py:28-35   ndarray_to_tensor_proto: dtype enum, one
@@ -125,11 +125,6 @@ static uint64_t int_elem(const void* data, int dt, uint64_t i) {
     case DT_UINT32: return ((const uint32_t*)data)[i];
     default: return ((const uint64_t*)data)[i];
   }
-}
-
-static int is_varint_dtype(int dt) {
-  return dt == DT_INT8 || dt == DT_INT16 || dt == DT_INT32 || dt == DT_INT64 || dt == DT_UINT8 || dt == DT_UINT16 ||
-         dt == DT_UINT32 || dt == DT_UINT64 || dt == DT_HALF || dt == DT_BFLOAT16;
 }
 
 static uint64_t count_elems(const orc_tensor* t) {
@@ -435,6 +430,76 @@ static void read_scalars(rd* r, orc_out* o, unsigned field, unsigned wt) {
   }
 }
 
+/* resource_handle_val / variant_val are never read on this path, but the runtime parses them, so
+ * malformed bytes inside them fail the message: validate structure recursively (schemas:
+ * resource_handle.proto:16-42, tensor.proto:87-94). */
+static void check_shape(rd* r);
+static void check_nested_tensor(rd* r, int depth);
+static void check_string(rd* r) { rd s = get_sub(r); if (!r->bad && !utf8_valid(s.p, (size_t)(s.end - s.p))) r->bad = 1; }
+static void check_shape(rd* r) {
+  while (r->p < r->end && !r->bad) {
+    uint64_t t = get_tag(r);
+    if (r->bad) return;
+    if (t == (2 << 3 | 2)) {
+      rd d = get_sub(r);
+      if (r->bad) return;
+      while (d.p < d.end && !d.bad) {
+        uint64_t dt = get_tag(&d);
+        if (d.bad) break;
+        if (dt == (2 << 3 | 2)) check_string(&d); else skip_value(&d, dt);
+      }
+      if (d.bad) r->bad = 1;
+    } else skip_value(r, t);
+  }
+}
+static void check_resource(rd* r) {
+  while (r->p < r->end && !r->bad) {
+    uint64_t t = get_tag(r);
+    if (r->bad) return;
+    unsigned f = (unsigned)(t >> 3), wt = (unsigned)(t & 7);
+    if (wt == 2 && (f == 1 || f == 2 || f == 3 || f == 5)) check_string(r);
+    else if (wt == 2 && f == 6) {
+      rd d = get_sub(r);
+      if (r->bad) return;
+      while (d.p < d.end && !d.bad) {
+        uint64_t dt = get_tag(&d);
+        if (d.bad) break;
+        if (dt == (2 << 3 | 2)) { rd s = get_sub(&d); if (!d.bad) { check_shape(&s); if (s.bad) d.bad = 1; } }
+        else skip_value(&d, dt);
+      }
+      if (d.bad) r->bad = 1;
+    } else skip_value(r, t);
+  }
+}
+static void check_variant(rd* r, int depth) {
+  while (r->p < r->end && !r->bad) {
+    uint64_t t = get_tag(r);
+    if (r->bad) return;
+    if (t == (1 << 3 | 2)) check_string(r);
+    else if (t == (3 << 3 | 2)) { rd s = get_sub(r); if (!r->bad) { check_nested_tensor(&s, depth + 1); if (s.bad) r->bad = 1; } }
+    else skip_value(r, t);
+  }
+}
+static void check_nested_tensor(rd* r, int depth) {
+  if (depth > 64) { r->bad = 1; return; }
+  while (r->p < r->end && !r->bad) {
+    uint64_t t = get_tag(r);
+    if (r->bad) return;
+    unsigned f = (unsigned)(t >> 3), wt = (unsigned)(t & 7);
+    if (wt != 2) { skip_value(r, t); continue; }
+    rd s = get_sub(r);
+    if (r->bad) return;
+    size_t n = (size_t)(s.end - s.p);
+    if (f == 2) check_shape(&s);
+    else if (f == 14) check_resource(&s);
+    else if (f == 15) check_variant(&s, depth);
+    else if (f == 5 || f == 9) { if (n % 4) s.bad = 1; }
+    else if (f == 6 || f == 12) { if (n % 8) s.bad = 1; }
+    else if (f == 7 || f == 10 || f == 11 || f == 13 || f == 16 || f == 17) { if (n && (s.end[-1] & 0x80)) s.bad = 1; }
+    if (s.bad) r->bad = 1;
+  }
+}
+
 static void read_tensor(rd* r, orc_out* o) {
   while (r->p < r->end && !r->bad) {
     uint64_t t = get_tag(r);
@@ -444,6 +509,8 @@ static void read_tensor(rd* r, orc_out* o) {
     else if (field == 2 && wt == 2) { rd s = get_sub(r); if (r->bad) return; read_shape(&s, o); if (s.bad) r->bad = 1; }
     else if (field == 4 && wt == 2) { rd s = get_sub(r); if (r->bad) return; o->content = s.p; o->content_len = (size_t)(s.end - s.p); }
     else if (field == 8 && wt == 2) { (void)get_sub(r); o->n_strings++; }
+    else if (field == 14 && wt == 2) { rd s = get_sub(r); if (r->bad) return; check_resource(&s); if (s.bad) r->bad = 1; }
+    else if (field == 15 && wt == 2) { rd s = get_sub(r); if (r->bad) return; check_variant(&s, 0); if (s.bad) r->bad = 1; }
     else if ((field >= 5 && field <= 7) || (field >= 9 && field <= 13) || field == 16 || field == 17) read_scalars(r, o, field, wt);
     else skip_value(r, t);
   }
@@ -533,6 +600,8 @@ orc_parsed* orc_parse_response(const uint8_t* wire, int64_t len, orc_desc* descs
       rd e = get_sub(&r);
       if (r.bad) break;
       orc_out o; out_init(&o);
+      int foreign = 0; /* an entry that itself holds an unknown field is kept as an unknown field of the
+                          response by the runtime and never enters the map */
       while (e.p < e.end && !e.bad) {
         uint64_t et = get_tag(&e);
         if (e.bad) break;
@@ -547,9 +616,10 @@ orc_parsed* orc_parse_response(const uint8_t* wire, int64_t len, orc_desc* descs
           o.msg = v.p; o.msg_len = (size_t)(v.end - v.p);
           read_tensor(&v, &o);
           if (v.bad) e.bad = 1;
-        } else skip_value(&e, et);
+        } else { skip_value(&e, et); foreign = 1; }
       }
       if (e.bad || o.nomem) { out_free(&o); r.bad = 1; break; }
+      if (foreign) { out_free(&o); continue; }
       int slot = -1;
       for (int i = 0; i < P->n; ++i)
         if (P->outs[i].key_len == o.key_len && (!o.key_len || !memcmp(P->outs[i].key, o.key, o.key_len))) slot = i;

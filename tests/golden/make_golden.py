@@ -30,13 +30,21 @@ if not os.path.isdir(REF):
     sys.exit("reference not present; goldens can only be regenerated in the build container")
 sys.path[:0] = [REF, os.path.join(REPO, "min-tfs-client_b200")]
 
+# The reference's package has no __init__.py (a namespace package); this repo's drop-in of the same name is a
+# regular package and would win the import.  Pin the name to the reference's directory explicitly.
+import types as _types  # noqa: E402
+
+_ref_pkg = _types.ModuleType("min_tfs_client")
+_ref_pkg.__path__ = [os.path.join(REF, "min_tfs_client")]
+sys.modules["min_tfs_client"] = _ref_pkg
+
 import numpy as np  # noqa: E402
 import google.protobuf  # noqa: E402
 import min_tfs_client.tensors as ref_tensors  # noqa: E402
 from tensorflow.core.framework.tensor_pb2 import TensorProto  # noqa: E402
 from tensorflow_serving.apis.predict_pb2 import PredictRequest, PredictResponse  # noqa: E402
 
-assert list(sys.modules["min_tfs_client"].__path__)[0].startswith("/root/reference"), "not the reference package"
+assert ref_tensors.__file__.startswith("/root/reference/"), "not the reference package: " + ref_tensors.__file__
 
 enc = ref_tensors.ndarray_to_tensor_proto
 dec = ref_tensors.tensor_proto_to_ndarray
@@ -316,6 +324,14 @@ def decode_cases():
         "group_unknown": b"\xC3\x06\xC4\x06" + entry("a", tproto(1, [1], ld(0x2A, f([1])))),
         "version_label_spec": entry("a", tproto(1, [1], ld(0x2A, f([1])))) + ld(0x12, ld(0x0A, b"m") + ld(0x22, b"stable")),
         "empty_model_spec": entry("a", tproto(1, [1], ld(0x2A, f([1])))) + b"\x12\x00",
+        "entry_with_foreign_field": ld(0x0A, ld(0x0A, b"k") + b"\x08\x01" + ld(0x12, tproto(1, [1], ld(0x2A, f([4]))))) + entry("b", tproto(1, [1], ld(0x2A, f([5])))),
+        "entry_with_unknown_number": ld(0x0A, ld(0x0A, b"k") + ld(0x12, tproto(1, [1], ld(0x2A, f([4])))) + b"\xB8\x06\x07"),
+        "entry_key_wrong_wiretype": ld(0x0A, b"\x08\x05" + ld(0x12, tproto(1, [1], ld(0x2A, f([4]))))),
+        "resource_handle_ok": entry("a", tproto(1, [1], ld(0x2A, f([4])) + ld(0x72, ld(0x0A, b"/dev") + ld(0x32, b"\x08\x01" + ld(0x12, shape(2)))))),
+        "resource_handle_malformed": entry("a", tproto(1, [1], ld(0x2A, f([4])) + ld(0x72, b"\x00"))),
+        "resource_handle_bad_utf8": entry("a", tproto(1, [1], ld(0x2A, f([4])) + ld(0x72, ld(0x0A, b"\xff")))),
+        "variant_nested_ok": entry("a", tproto(1, [1], ld(0x2A, f([4])) + ld(0x7A, ld(0x0A, b"T") + ld(0x12, b"\xff\x00") + ld(0x1A, tproto(1, [1], ld(0x2A, f([9]))))))),
+        "variant_nested_malformed": entry("a", tproto(1, [1], ld(0x2A, f([4])) + ld(0x7A, ld(0x1A, tproto(1, [1], b"\x2A\x03\x00\x00\x00"))))),
         "complex64": entry("a", tproto(8, [1], ld(0x4A, f([1, 2])))),
     }
     out = {}

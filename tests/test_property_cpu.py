@@ -1,0 +1,198 @@
+"""Property tests (hypothesis) on the CPU: random messages built with the protobuf runtime, decoded
+by (a) the Python port of the reference and (b) the product's tag walker compiled for the host +
+the C oracle; random requests framed by the product's host planner vs the port's SerializeToString.
+Bit-exact or same-exception, every example.
+"""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+import pytest
+from hypothesis import HealthCheck, given, settings, strategies as st
+
+import golden_util as G
+from min_tfs_client import _native as N
+from min_tfs_client.codec import _Prepared
+from min_tfs_client.constants import numpy_for_enum
+from oracle import ref_port, wire_oracle
+from tensorflow.core.framework import tensor_pb2, tensor_shape_pb2
+from tensorflow_serving.apis import predict_pb2
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+FIXED = [np.float32, np.float64]
+INTS = [np.int8, np.int16, np.int32, np.int64, np.uint8, np.uint16, np.uint32, np.uint64]
+SET = settings(max_examples=300, deadline=None, suppress_health_check=[HealthCheck.too_slow])
+
+
+def _walker():
+    so = os.path.join(HERE, "native", "_build", "libwalker_host.so")
+    subprocess.run(["make", "-s", "-C", os.path.join(HERE, "native")], check=True)
+    L = C.CDLL(so)
+    L.wh_parse_response.restype = C.c_int
+    L.wh_parse_response.argtypes = [C.c_char_p, C.c_uint64, C.c_int, C.POINTER(N.Output), C.POINTER(C.c_int), C.POINTER(N.ModelSpec)]
+    return L
+
+
+WALK = _walker()
+
+shapes = st.lists(st.integers(0, 5), min_size=1, max_size=4)
+keys = st.text(alphabet=st.characters(blacklist_categories=("Cs",)), min_size=0, max_size=12)
+
+
+@st.composite
+def arrays(draw, dtypes=FIXED + INTS + [np.bool_]):
+    dt = draw(st.sampled_from(dtypes))
+    shape = tuple(draw(shapes))
+    n = int(np.prod(shape))
+    raw = draw(st.binary(min_size=n * np.dtype(dt).itemsize, max_size=n * np.dtype(dt).itemsize))
+    a = np.frombuffer(raw, dtype=dt).reshape(shape).copy()
+    if dt is np.bool_:
+        a = (a.view(np.uint8) & 1).astype(np.bool_)
+    return a
+
+
+def _response_bytes(draw, outs):
+    """PredictResponse through the protobuf runtime, optionally perturbed in ways that keep it valid."""
+    resp = predict_pb2.PredictResponse()
+    for k, a in outs:
+        resp.outputs[k].CopyFrom(ref_port.to_tensor_proto(a))
+    if draw(st.booleans()):
+        resp.model_spec.name = draw(keys)
+        if draw(st.booleans()):
+            resp.model_spec.version.value = draw(st.integers(-2 ** 63, 2 ** 63 - 1))
+        else:
+            resp.model_spec.version_label = draw(keys)
+        resp.model_spec.signature_name = draw(keys)
+    wire = resp.SerializeToString(deterministic=draw(st.booleans()))
+    if draw(st.booleans()):   # unknown fields at the top level: varint, fixed64, length-delimited, fixed32, a group
+        wire = b"\xB8\x06\x07" + wire + b"\xC1\x06" + b"\x01" * 8 + b"\xAA\x06\x03abc" + b"\xC5\x06" + b"\x02" * 4 + b"\xC3\x06\xB8\x06\x01\xC4\x06"
+    return wire
+
+
+@SET
+@given(st.data())
+def test_walker_and_oracle_agree_with_port_on_random_responses(data):
+    n_out = data.draw(st.integers(0, 4))
+    outs = []
+    used = set()
+    for _ in range(n_out):
+        k = data.draw(keys)
+        if k in used:
+            continue
+        used.add(k)
+        outs.append((k, data.draw(arrays())))
+    wire = _response_bytes(data.draw, outs)
+    expect = ref_port.decode_predict_response(wire)          # the reference's algorithm on the protobuf runtime
+    # (a) C oracle
+    got = wire_oracle.decode_predict_response(wire)
+    assert set(got) == set(expect)
+    for k in expect:
+        assert got[k].dtype == expect[k].dtype and got[k].shape == expect[k].shape and got[k].tobytes() == expect[k].tobytes(), k
+    # (b) the product's walker (host build): table must locate exactly those values
+    table = (N.Output * 17)()
+    cnt = C.c_int()
+    spec = N.ModelSpec()
+    assert WALK.wh_parse_response(wire, len(wire), 16, table, C.byref(cnt), C.byref(spec)) == N.OK
+    by_key = {wire[table[i].key_off: table[i].key_off + table[i].key_len].decode(): table[i] for i in range(cnt.value)}
+    assert set(by_key) == set(expect)
+    for k, a in expect.items():
+        o = by_key[k]
+        assert o.status == N.OK and numpy_for_enum(o.dtype) == a.dtype.type and tuple(o.dims[i] for i in range(o.rank)) == a.shape
+        raw = b"".join(wire[o.chunk_off[c]: o.chunk_off[c] + o.chunk_len[c]] for c in range(o.n_chunks))
+        if not (o.flags & N.OF_VARINT):
+            vals = np.frombuffer(raw, dtype=a.dtype).copy()
+            if a.dtype == np.float32:
+                u = vals.view(np.uint32)
+                u[(u & 0x7FFFFFFF) > 0x7F800000] |= 0x00400000
+            assert vals.tobytes() == a.tobytes()
+        else:
+            assert sum(1 for b in raw if not b & 0x80) == a.size      # one terminator per element
+
+
+@SET
+@given(st.data())
+def test_truncated_or_corrupted_responses_never_misparse(data):
+    """Cut a valid response anywhere / flip a framing byte: the walker either reports a parse error or
+    produces exactly what the protobuf runtime + reference algorithm produce - never something else."""
+    from google.protobuf.message import DecodeError
+
+    a = data.draw(arrays(FIXED + [np.int32, np.int64]))
+    wire = bytearray(_response_bytes(data.draw, [("k", a)]))
+    if data.draw(st.booleans()) and len(wire) > 1:
+        wire = wire[: data.draw(st.integers(0, len(wire) - 1))]
+    elif len(wire):
+        i = data.draw(st.integers(0, min(len(wire) - 1, 24)))
+        wire[i] ^= 1 << data.draw(st.integers(0, 7))
+    wire = bytes(wire)
+    table = (N.Output * 17)()
+    cnt = C.c_int()
+    spec = N.ModelSpec()
+    st_w = WALK.wh_parse_response(wire, len(wire), 16, table, C.byref(cnt), C.byref(spec))
+    try:
+        parsed = predict_pb2.PredictResponse.FromString(wire)
+    except DecodeError:
+        assert st_w == N.E_PARSE
+        return
+    assert st_w == N.OK, "runtime accepts these bytes but the walker rejected them"
+    assert cnt.value == len(parsed.outputs)
+    for i in range(cnt.value):
+        o = table[i]
+        key = wire[o.key_off: o.key_off + o.key_len].decode()
+        tp = parsed.outputs[key]
+        assert o.dtype == tp.dtype and [o.dims[j] for j in range(o.rank)] == [d.size for d in tp.tensor_shape.dim][: N.MAX_RANK]
+
+
+@SET
+@given(st.data())
+def test_host_planner_frames_random_requests_like_the_runtime(data):
+    n_in = data.draw(st.integers(0, 4))
+    inputs, used = [], set()
+    for _ in range(n_in):
+        k = data.draw(keys)
+        if k in used:
+            continue
+        used.add(k)
+        inputs.append((k, data.draw(arrays(FIXED + [np.bool_]))))
+    name = data.draw(keys)
+    version = data.draw(st.one_of(st.none(), st.integers(-2 ** 63, 2 ** 63 - 1)))
+    expect = ref_port.encode_predict_request(name, version, inputs, deterministic=True)
+    preps = [_Prepared(a, k.encode(), None, False, False) for k, a in inputs]
+    arr = (N.Tensor * max(len(preps), 1))(*[p.struct for p in preps])
+    nb = name.encode()
+    req = N.Request(model_name=nb, model_name_len=len(nb), has_version=int(version is not None), order=N.ORDER_UPB, version=version or 0,
+                    n_inputs=len(preps), reserved=0, inputs=arr)
+    lib = N.load()
+    buf = C.create_string_buffer(1 << 16)
+    flen = C.c_uint64()
+    m = max(len(preps), 1)
+    poff, plen, perm = (C.c_uint64 * m)(), (C.c_uint64 * m)(), (C.c_int32 * m)()
+    N.check(lib.b200tfs_request_frame(C.byref(req), buf, 1 << 16, C.byref(flen), poff, plen, perm))
+    frame = buf.raw[: flen.value]
+    wire, fpos = bytearray(), 0
+    for j in range(len(preps)):
+        take = poff[j] - len(wire)
+        wire += frame[fpos: fpos + take]
+        fpos += take
+        a = preps[perm[j]].array
+        if a.dtype == np.float32:
+            u = a.view(np.uint32).copy()
+            u[(u & 0x7FFFFFFF) > 0x7F800000] |= 0x00400000
+            wire += u.tobytes()
+        elif a.dtype == np.bool_:
+            wire += (a.view(np.uint8) != 0).astype(np.uint8).tobytes()
+        else:
+            wire += a.tobytes()
+    wire += frame[fpos:]
+    assert bytes(wire) == expect
+    # and the C oracle says the same
+    assert wire_oracle.encode_predict_request(name, version, inputs) == expect
+
+
+@SET
+@given(arrays())
+def test_oracle_tensor_proto_equals_port(a):
+    assert wire_oracle.encode_tensor_proto(a) == ref_port.encode_tensor_proto(a)
+    back = wire_oracle.decode_tensor_proto(ref_port.encode_tensor_proto(a))
+    ref = ref_port.decode_tensor_proto(ref_port.encode_tensor_proto(a))
+    assert back.dtype == ref.dtype and back.shape == ref.shape and back.tobytes() == ref.tobytes()
