@@ -147,20 +147,28 @@ __device__ __forceinline__ uint64_t src_bytes_for(uint32_t op, uint64_t n_out) {
 // a 4 MiB tensor is smaller than the HBM bandwidth-delay product, so the whole tile must be in
 // flight at once - one DRAM round trip per batch, not per vector.
 // ------------------------------------------------------------------------------------------------
-constexpr uint32_t kBatch = 4;         // shifted / cast paths (two source blocks per vector)
+
 constexpr uint32_t kBatchAligned = 8;  // aligned path: 8 x 16 B per thread = a 32 KB tile in one round trip
 
-template <uint32_t OP>
-__device__ __forceinline__ void body_aligned(const uint8_t* __restrict__ src, uint8_t* __restrict__ dst, uint32_t n) {
-  for (uint32_t v = threadIdx.x; v < n; v += kBatchAligned * kMoveThreads) {
+// `mid` runs once per thread after the FIRST round's loads are in flight and before any store; it
+// returns false to abandon the tile (the fused decode's template verdict, which needs a DRAM round
+// trip of its own, hides behind the tile's loads this way).  Plain callers pass AlwaysGo.
+struct AlwaysGo { __device__ __forceinline__ bool operator()() const { return true; } };
+
+template <uint32_t OP, class Mid>
+__device__ __forceinline__ bool body_aligned(const uint8_t* __restrict__ src, uint8_t* __restrict__ dst, uint32_t n, Mid& mid) {
+  for (uint32_t base = 0; base < n; base += kBatchAligned * kMoveThreads) {   // uniform trip count across the CTA
+    const uint32_t v = base + threadIdx.x;
     uint4 a[kBatchAligned];
 #pragma unroll
     for (uint32_t i = 0; i < kBatchAligned; ++i)
       if (v + i * kMoveThreads < n) a[i] = ld_stream(src + 16ull * (v + i * kMoveThreads));
+    if (base == 0 && !mid()) return false;
 #pragma unroll
     for (uint32_t i = 0; i < kBatchAligned; ++i)
       if (v + i * kMoveThreads < n) st_stream(dst + 16ull * (v + i * kMoveThreads), fix_vec<OP>(a[i]));
   }
+  return true;
 }
 
 // S = source body rounded down to 16 bytes; output vector v = bytes [k, k+16) of blocks v, v+1.
@@ -174,31 +182,49 @@ __device__ __forceinline__ uint4 shfl_down1(const uint4& v) {
   return r;
 }
 
-template <uint32_t OP, int Q>
-__device__ __forceinline__ void body_shifted_q(const uint8_t* __restrict__ S, uint8_t* __restrict__ dst, uint32_t n, uint32_t s) {
+__device__ __forceinline__ uint4 shfl_lane0(const uint4& v) {
+  uint4 r;
+  r.x = __shfl_sync(0xFFFFFFFFu, v.x, 0); r.y = __shfl_sync(0xFFFFFFFFu, v.y, 0);
+  r.z = __shfl_sync(0xFFFFFFFFu, v.z, 0); r.w = __shfl_sync(0xFFFFFFFFu, v.w, 0);
+  return r;
+}
+
+// Each WARP owns a contiguous run of kBatchShift*32 destination vectors: element i of lane L is vector
+// run + 32*i + L.  Block v+1 then comes from lane L+1 (shuffle), for lane 31 from lane 0's NEXT
+// element, and only the block just past the run is loaded extra (by lane 0).  All kBatchShift loads
+// of a thread are in flight together: a 32 KB tile is one DRAM round trip, like the aligned path.
+constexpr uint32_t kBatchShift = 8;
+
+template <uint32_t OP, int Q, class Mid>
+__device__ __forceinline__ bool body_shifted_q(const uint8_t* __restrict__ S, uint8_t* __restrict__ dst, uint32_t n, uint32_t s, Mid& mid) {
   constexpr bool PRE = (OP == OP_QUIET_SRC);  // elements line up with the source blocks
-  const bool edge = (threadIdx.x & 31) == 31;
-  // every lane of a warp runs the same number of rounds (shuffles need the whole warp)
-  const uint32_t rounds = (n + kBatch * kMoveThreads - 1) / (kBatch * kMoveThreads);
-  for (uint32_t rd = 0; rd < rounds; ++rd) {
-    const uint32_t v = rd * kBatch * kMoveThreads + threadIdx.x;
-    uint4 lo[kBatch], own[kBatch];
+  const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  constexpr uint32_t kRun = kBatchShift * 32;                    // vectors per warp per round
+  constexpr uint32_t kRound = kRun * (kMoveThreads / 32);        // vectors per CTA per round
+  for (uint32_t base = 0; base < n; base += kRound) {            // uniform trip count across the CTA
+    const uint32_t run = base + warp * kRun;
+    const uint32_t run_end = min(run + kRun, n);                 // first vector past this warp's run (block index of `extra`)
+    uint4 lo[kBatchShift], extra = make_uint4(0, 0, 0, 0);
 #pragma unroll
-    for (uint32_t i = 0; i < kBatch; ++i) {
-      const uint32_t u = v + i * kMoveThreads;
-      lo[i] = make_uint4(0, 0, 0, 0); own[i] = make_uint4(0, 0, 0, 0);
-      if (u < n) {
-        lo[i] = ld_stream(S + 16ull * u);
-        if (edge || u + 1 >= n) own[i] = ld_stream(S + 16ull * u + 16);
-      }
+    for (uint32_t i = 0; i < kBatchShift; ++i) {
+      const uint32_t u = run + 32 * i + lane;
+      lo[i] = make_uint4(0, 0, 0, 0);
+      if (u < n) lo[i] = ld_stream(S + 16ull * u);
     }
+    if (lane == 0 && run < n) extra = ld_stream(S + 16ull * run_end);
+    if (base == 0 && !mid()) return false;
+    extra = shfl_lane0(extra);
 #pragma unroll
-    for (uint32_t i = 0; i < kBatch; ++i) {
-      const uint32_t u = v + i * kMoveThreads;
-      uint4 a = lo[i];
-      uint4 b = shfl_down1(lo[i]);
-      if (edge || u + 1 >= n) b = own[i];
+    for (uint32_t i = 0; i < kBatchShift; ++i) {
+      const uint32_t u = run + 32 * i + lane;
+      uint4 b = shfl_down1(lo[i]);                               // lanes 0..30: neighbour's block
+      if (i + 1 < kBatchShift) {
+        const uint4 nxt = shfl_lane0(lo[i + 1]);                 // lane 31: first block of the next element
+        if (lane == 31) b = nxt;
+      }
+      if (u + 1 == run_end) b = extra;                           // last vector of the run (or of a ragged tile)
       if (u < n) {
+        uint4 a = lo[i];
         if (PRE) { a = fix_vec<OP>(a); b = fix_vec<OP>(b); }
         uint4 o = shift_pair<Q>(a, b, s);
         if (!PRE) o = fix_vec<OP>(o);
@@ -206,19 +232,20 @@ __device__ __forceinline__ void body_shifted_q(const uint8_t* __restrict__ S, ui
       }
     }
   }
+  return true;
 }
 
-template <uint32_t OP>
-__device__ __forceinline__ void body_same_width(const uint8_t* src, uint8_t* dst, uint32_t n) {
+template <uint32_t OP, class Mid>
+__device__ __forceinline__ bool body_same_width(const uint8_t* src, uint8_t* dst, uint32_t n, Mid& mid) {
   const uint32_t k = (uint32_t)((uintptr_t)src & 15);
-  if (k == 0) { body_aligned<OP>(src, dst, n); return; }
+  if (k == 0) return body_aligned<OP>(src, dst, n, mid);
   const uint8_t* S = src - k;
   const uint32_t s = (k & 3) * 8;
   switch (k >> 2) {  // uniform across the CTA
-    case 0: body_shifted_q<OP, 0>(S, dst, n, s); break;
-    case 1: body_shifted_q<OP, 1>(S, dst, n, s); break;
-    case 2: body_shifted_q<OP, 2>(S, dst, n, s); break;
-    default: body_shifted_q<OP, 3>(S, dst, n, s); break;
+    case 0: return body_shifted_q<OP, 0>(S, dst, n, s, mid);
+    case 1: return body_shifted_q<OP, 1>(S, dst, n, s, mid);
+    case 2: return body_shifted_q<OP, 2>(S, dst, n, s, mid);
+    default: return body_shifted_q<OP, 3>(S, dst, n, s, mid);
   }
 }
 
@@ -310,8 +337,9 @@ __host__ __device__ __forceinline__ uint32_t tiles_for(uint64_t n_out, uint32_t 
   return t ? (uint32_t)t : 1u;
 }
 
-__device__ __forceinline__ void move_tile(const uint8_t* __restrict__ src, uint8_t* __restrict__ dst, uint64_t n_out, uint32_t op,
-                                          uint32_t n_tiles, uint32_t tile, uint32_t vpt) {
+template <class Mid>
+__device__ __forceinline__ bool move_tile(const uint8_t* __restrict__ src, uint8_t* __restrict__ dst, uint64_t n_out, uint32_t op,
+                                          uint32_t n_tiles, uint32_t tile, uint32_t vpt, Mid& mid) {
   const bool last = (tile + 1 == n_tiles);
   const uint64_t n_src = src_bytes_for(op, n_out);
   uint64_t head = (16 - ((uintptr_t)dst & 15)) & 15;
@@ -351,30 +379,34 @@ __device__ __forceinline__ void move_tile(const uint8_t* __restrict__ src, uint8
     if (nvec > lim) nvec = lim;
   }
   if (!fast) {  // whole payload through the byte generator, split by tile
+    if (!mid()) return false;
     const uint64_t b0 = (uint64_t)tile * vpt * 16;
     uint64_t b1 = b0 + (uint64_t)vpt * 16;
     if (b1 > n_out || last) b1 = n_out;
     for (uint64_t i = b0 + threadIdx.x; i < b1; i += blockDim.x) dst[i] = gen_byte(op, src, i);
-    return;
+    return true;
   }
   const uint64_t v0 = (uint64_t)tile * vpt;
+  bool go;
   if (v0 < nvec) {
     const uint32_t n = (uint32_t)min((uint64_t)vpt, nvec - v0);
     uint8_t* d = dst + head + 16 * v0;
     switch (op) {
-      case OP_COPY: body_same_width<OP_COPY>(src_body + 16 * v0, d, n); break;
-      case OP_BOOL: body_same_width<OP_BOOL>(src_body + 16 * v0, d, n); break;
-      case OP_QUIET_SRC: body_same_width<OP_QUIET_SRC>(src_body + 16 * v0, d, n); break;
-      case OP_QUIET_DST: body_same_width<OP_QUIET_DST>(src_body + 16 * v0, d, n); break;
-      case OP_H2F: body_widen<false>(src_body + 8 * v0, d, n >> 1); break;
-      case OP_B2F: body_widen<true>(src_body + 8 * v0, d, n >> 1); break;
-      case OP_F2H: body_narrow<false>(src_body + 32 * v0, d, n); break;
-      default: body_narrow<true>(src_body + 32 * v0, d, n); break;
+      case OP_COPY: go = body_same_width<OP_COPY>(src_body + 16 * v0, d, n, mid); break;
+      case OP_BOOL: go = body_same_width<OP_BOOL>(src_body + 16 * v0, d, n, mid); break;
+      case OP_QUIET_SRC: go = body_same_width<OP_QUIET_SRC>(src_body + 16 * v0, d, n, mid); break;
+      case OP_QUIET_DST: go = body_same_width<OP_QUIET_DST>(src_body + 16 * v0, d, n, mid); break;
+      case OP_H2F: go = mid(); if (go) body_widen<false>(src_body + 8 * v0, d, n >> 1); break;
+      case OP_B2F: go = mid(); if (go) body_widen<true>(src_body + 8 * v0, d, n >> 1); break;
+      case OP_F2H: go = mid(); if (go) body_narrow<false>(src_body + 32 * v0, d, n); break;
+      default: go = mid(); if (go) body_narrow<true>(src_body + 32 * v0, d, n); break;
     }
-  }
+  } else go = mid();
+  if (!go) return false;
   // ragged edges, element-exact
   if (tile == 0) for (uint64_t i = threadIdx.x; i < head; i += blockDim.x) dst[i] = gen_byte(op, src, i);
   if (last) for (uint64_t i = head + (nvec << 4) + threadIdx.x; i < n_out; i += blockDim.x) dst[i] = gen_byte(op, src, i);
+  return true;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -392,7 +424,8 @@ __device__ __forceinline__ void move_body(const uint8_t* plan) {
       item = tr.item; tile = tr.tile;
     }
     const MoveItem& it = reinterpret_cast<const MoveItem*>(plan + ph.off_items)[item];
-    move_tile(it.src, it.dst, it.n_out, it.op, it.n_tiles, tile, ph.vec_per_tile);
+    AlwaysGo go;
+    move_tile(it.src, it.dst, it.n_out, it.op, it.n_tiles, tile, ph.vec_per_tile, go);
   } else {
     const uint32_t warps = blockDim.x >> 5;
     const uint32_t idx = (b - ph.n_tiles) * warps + (threadIdx.x >> 5);
@@ -632,22 +665,32 @@ __global__ void __launch_bounds__(kMoveThreads, 3) decode_fused_kernel(const __g
     __syncthreads();
     const uint32_t nch = th_s.n_chunks;
     if (th_s.valid && th_s.rec_len == len && th_s.vpt == fp.vpt && th_s.dst_need <= fp.dst_stride && th_s.total_tiles < budget) {
-      bool same = true;
-      if (i < th_s.framing_len) {
-        uint32_t w = i;
-        for (uint32_t q = 0; q < nch; ++q) if (ch_s[q].fpos <= i) w += ch_s[q].len;
-        same = rec[w] == want;
+      // The verdict needs this record's framing bytes (a DRAM round trip).  (Tried: running it as the `mid`
+      // hook of the tile move so that it overlaps the tile's own loads.  Single 4 MiB decode 4.64 -> 4.49 us,
+      // but the registers held across the barrier cost a CTA per SM and the 1024-record batch decode dropped
+      // from 0.74 to 0.65 of peak, so the verdict runs first.)
+      auto verdict = [&]() -> bool {
+        bool same = true;
+        if (i < th_s.framing_len) {
+          uint32_t w = i;
+          for (uint32_t q = 0; q < nch; ++q) if (ch_s[q].fpos <= i) w += ch_s[q].len;
+          same = rec[w] == want;
+        }
+        if (i < nch && ch_s[i].is_varint && ch_s[i].len) same = same && !(rec[ch_s[i].wire_off + ch_s[i].len - 1] & 0x80);
+        return __syncthreads_and(same) != 0;
+      };
+      uint32_t t_base = 0, mine = kTplChunks;
+      for (uint32_t q = 0; q < nch; ++q) {
+        const uint32_t nt = ch_s[q].n_tiles;
+        if (j >= t_base && j < t_base + nt) { mine = q; break; }
+        t_base += nt;
       }
-      if (i < nch && ch_s[i].is_varint && ch_s[i].len) same = same && !(rec[ch_s[i].wire_off + ch_s[i].len - 1] & 0x80);
-      if (__syncthreads_and(same)) {
-        uint32_t t_base = 0;
-        for (uint32_t q = 0; q < nch; ++q) {
-          const uint32_t nt = ch_s[q].n_tiles;
-          if (j >= t_base && j < t_base + nt) {
-            move_tile(rec + ch_s[q].wire_off, dst_slot + ch_s[q].dst_off, ch_s[q].len, ch_s[q].op, nt, j - t_base, fp.vpt);
-            break;
-          }
-          t_base += nt;
+      const bool hit = verdict();
+      if (hit) {
+        if (mine < kTplChunks) {
+          AlwaysGo go;
+          move_tile(rec + ch_s[mine].wire_off, dst_slot + ch_s[mine].dst_off, ch_s[mine].len, ch_s[mine].op, ch_s[mine].n_tiles, j - t_base,
+                    fp.vpt, go);
         }
         if (j == budget - 1) {
           publish_words(fp.outs + (size_t)r * kFusedMaxOutputs, T->outs, th_s.n_outs * (uint32_t)sizeof(b200tfs_output));
@@ -664,7 +707,10 @@ __global__ void __launch_bounds__(kMoveThreads, 3) decode_fused_kernel(const __g
   // ---- slow path: thread 0 walks the tags ----
   if (threadIdx.x == 0) fused_slow_path(fp, r, j, budget, rec, len, dst_slot, lines, outs_s, spec_s, job);
   __syncthreads();
-  if (job.valid) move_tile(job.src, job.dst, job.n_out, job.op, job.n_tiles, job.tile, fp.vpt);
+  if (job.valid) {
+    AlwaysGo go;
+    move_tile(job.src, job.dst, job.n_out, job.op, job.n_tiles, job.tile, fp.vpt, go);
+  }
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -110,3 +110,35 @@ def test_round_trip_all_numeric_dtypes(codec):
         wire = codec.encode_tensor_protos([x])[0]
         back = codec.decode_tensor_protos([wire], strict=True)[0]
         assert back.dtype == x.dtype and back.shape == x.shape and back.tobytes() == x.tobytes(), dt
+
+
+def test_alignment_sweep_against_oracle(codec):
+    """Every relative alignment of payload vs wire: key lengths 0..17 shift the payload offset byte by byte;
+    sizes straddle the small-item / one-tile / multi-tile / ragged-tail boundaries; float32 (quieting path),
+    float64 and bool; on encode the second large input of a request lands misaligned."""
+    from oracle import wire_oracle
+
+    rng = np.random.default_rng(99)
+    sizes = [1, 3, 4, 5, 127, 511, 512, 513, 2047, 4097, 8191, 8192, 8193, 16385, 40001, 262147]
+    for klen in range(0, 18):
+        key = "k" * klen
+        n = sizes[klen % len(sizes)]
+        for dt in (np.float32, np.float64):
+            x = rng.integers(0, 256, size=n * np.dtype(dt).itemsize, dtype=np.uint8).view(dt)   # random bits: NaNs of every kind
+            resp = wire_oracle.build_predict_response([(key, x)], keep_snan=True)
+            got = codec.decode_predict_response(resp, strict=True)[0][key]
+            ref = wire_oracle.decode_predict_response(resp)[key]
+            assert got.tobytes() == ref.tobytes(), (klen, n, dt)
+    for n in sizes:
+        a = rng.integers(0, 256, size=n * 4, dtype=np.uint8).view(np.float32)
+        b = rng.integers(0, 256, size=(n + 7) * 4, dtype=np.uint8).view(np.float32)
+        c = rng.integers(0, 2, size=n + 3).astype(np.bool_)
+        d = rng.standard_normal(n + 1)
+        inputs = [("a", a), ("bb", b), ("ccc", c), ("dddd", d)]
+        wire = codec.encode_predict_requests([("m", 3, inputs)])[0]
+        assert wire == wire_oracle.encode_predict_request("m", 3, inputs), n
+        resp = wire_oracle.build_predict_response(inputs, keep_snan=True)
+        outs = codec.decode_predict_response(resp, strict=True)[0]
+        ref = wire_oracle.decode_predict_response(resp)
+        for k in ref:
+            assert outs[k].tobytes() == ref[k].tobytes(), (n, k)
