@@ -727,6 +727,37 @@ __device__ __forceinline__ uint64_t load_as_u64(const uint8_t* src, uint64_t e, 
   }
 }
 
+// kVarPerThread elements per thread, striped (element base + i*kVarThreads + tid), ALL loads issued
+// before any use (the element width is resolved outside the loop so the loads can be hoisted)
+template <uint32_t SZ, bool SG>
+__device__ __forceinline__ void load_striped_t(const uint8_t* src, uint64_t e0, uint32_t cnt, uint64_t (&v)[kVarPerThread]) {
+#pragma unroll
+  for (uint32_t i = 0; i < kVarPerThread; ++i) {
+    const uint32_t k = i * kVarThreads + threadIdx.x;
+    uint64_t x = 0;
+    if (k < cnt) {
+      const uint64_t e = e0 + k;
+      if (SZ == 1) { const uint8_t t = src[e]; x = SG ? (uint64_t)(int64_t)(int8_t)t : t; }
+      else if (SZ == 2) { const uint16_t t = reinterpret_cast<const uint16_t*>(src)[e]; x = SG ? (uint64_t)(int64_t)(int16_t)t : t; }
+      else if (SZ == 4) { const uint32_t t = reinterpret_cast<const uint32_t*>(src)[e]; x = SG ? (uint64_t)(int64_t)(int32_t)t : t; }
+      else x = reinterpret_cast<const uint64_t*>(src)[e];
+    }
+    v[i] = x;
+  }
+}
+__device__ __forceinline__ void load_striped(const uint8_t* src, uint64_t e0, uint32_t cnt, uint32_t size, uint32_t is_signed,
+                                             uint64_t (&v)[kVarPerThread]) {
+  switch (size * 2 + (is_signed ? 1 : 0)) {
+    case 2: load_striped_t<1, false>(src, e0, cnt, v); break;
+    case 3: load_striped_t<1, true>(src, e0, cnt, v); break;
+    case 4: load_striped_t<2, false>(src, e0, cnt, v); break;
+    case 5: load_striped_t<2, true>(src, e0, cnt, v); break;
+    case 8: load_striped_t<4, false>(src, e0, cnt, v); break;
+    case 9: load_striped_t<4, true>(src, e0, cnt, v); break;
+    default: load_striped_t<8, false>(src, e0, cnt, v); break;
+  }
+}
+
 // block-wide exclusive scan of one value per thread (kVarThreads threads); returns the exclusive
 // prefix and writes the block total to *total
 __device__ __forceinline__ uint32_t block_exclusive_scan(uint32_t v, uint32_t* total, uint32_t* warp_sums /* smem[kVarThreads/32] */) {
@@ -759,29 +790,49 @@ __global__ void __launch_bounds__(kVarThreads) venc_len_kernel(const VarSeg* __r
   const VarSeg sg = segs[tile_seg[t]];
   const VarJobDev jb = jobs[sg.job];
   const uint64_t e0 = (uint64_t)(t - sg.first_tile) * kVarTileElems;
-  const uint64_t e1 = min(sg.n, e0 + kVarTileElems);
+  const uint32_t cnt = (uint32_t)min((uint64_t)kVarTileElems, sg.n - e0);
+  uint64_t v[kVarPerThread];
+  load_striped(sg.src, e0, cnt, jb.elem_size, jb.is_signed, v);
   uint32_t sum = 0;
-  for (uint64_t e = e0 + threadIdx.x; e < e1; e += kVarThreads) sum += varint_len_fast(load_as_u64(sg.src, e, jb.elem_size, jb.is_signed));
+#pragma unroll
+  for (uint32_t i = 0; i < kVarPerThread; ++i) sum += (i * kVarThreads + threadIdx.x < cnt) ? varint_len_fast(v[i]) : 0u;
   uint32_t total;
   (void)block_exclusive_scan(sum, &total, warp_sums);
   if (threadIdx.x == 0) tile_val[t] = total;
 }
 
-// per-job exclusive scan over its tiles (one CTA per job)
-__global__ void __launch_bounds__(kVarThreads) vscan_kernel(const VarJobDev* __restrict__ jobs, const uint32_t* __restrict__ tile_val,
-                                                            uint64_t* __restrict__ tile_off, uint64_t* __restrict__ job_total) {
-  __shared__ uint32_t warp_sums[kVarThreads / 32];
+// per-job exclusive scan over its tiles (one CTA of kScanThreads per job): every thread sums a
+// contiguous run of tiles, one block scan over the run sums, then each thread writes its run's offsets
+constexpr uint32_t kScanThreads = 1024;
+__global__ void __launch_bounds__(kScanThreads) vscan_kernel(const VarJobDev* __restrict__ jobs, const uint32_t* __restrict__ tile_val,
+                                                             uint64_t* __restrict__ tile_off, uint64_t* __restrict__ job_total) {
+  __shared__ uint64_t warp_sums[kScanThreads / 32];
   const VarJobDev jb = jobs[blockIdx.x];
-  uint64_t carry = 0;
-  for (uint32_t base = 0; base < jb.n_tiles; base += kVarThreads) {
-    const uint32_t i = base + threadIdx.x;
-    const uint32_t v = (i < jb.n_tiles) ? tile_val[jb.first_tile + i] : 0u;
-    uint32_t total;
-    const uint32_t ex = block_exclusive_scan(v, &total, warp_sums);
-    if (i < jb.n_tiles) tile_off[jb.first_tile + i] = carry + ex;
-    carry += total;
+  const uint32_t per = (jb.n_tiles + kScanThreads - 1) / kScanThreads;
+  const uint32_t t0 = min(jb.n_tiles, threadIdx.x * per), t1 = min(jb.n_tiles, t0 + per);
+  uint64_t mine = 0;
+  for (uint32_t t = t0; t < t1; ++t) mine += tile_val[jb.first_tile + t];
+  const uint32_t lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  uint64_t inc = mine;
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    const uint64_t n = __shfl_up_sync(0xFFFFFFFFu, inc, d);
+    if (lane >= d) inc += n;
   }
-  if (threadIdx.x == 0) job_total[blockIdx.x] = carry;
+  if (lane == 31) warp_sums[wid] = inc;
+  __syncthreads();
+  uint64_t base = 0, total = 0;
+  for (uint32_t w = 0; w < kScanThreads / 32; ++w) {
+    const uint64_t x = warp_sums[w];
+    if (w < wid) base += x;
+    total += x;
+  }
+  uint64_t run = base + inc - mine;
+  for (uint32_t t = t0; t < t1; ++t) {
+    tile_off[jb.first_tile + t] = run;
+    run += tile_val[jb.first_tile + t];
+  }
+  if (threadIdx.x == 0) job_total[blockIdx.x] = total;
 }
 
 // V3: emit.  Elements are loaded striped (coalesced), transposed through shared memory so each thread
@@ -797,7 +848,12 @@ __global__ void __launch_bounds__(kVarThreads) venc_emit_kernel(const VarSeg* __
   const VarJobDev jb = jobs[sg.job];
   const uint64_t e0 = (uint64_t)(t - sg.first_tile) * kVarTileElems;
   const uint32_t cnt = (uint32_t)min((uint64_t)kVarTileElems, sg.n - e0);
-  for (uint32_t i = threadIdx.x; i < cnt; i += kVarThreads) vals[i] = load_as_u64(sg.src, e0 + i, jb.elem_size, jb.is_signed);
+  {
+    uint64_t v[kVarPerThread];
+    load_striped(sg.src, e0, cnt, jb.elem_size, jb.is_signed, v);
+#pragma unroll
+    for (uint32_t i = 0; i < kVarPerThread; ++i) vals[i * kVarThreads + threadIdx.x] = v[i];
+  }
   __syncthreads();
   uint64_t mine[kVarPerThread];
   uint32_t sum = 0;
@@ -885,7 +941,7 @@ __device__ __forceinline__ void store_decoded(const VarJobDev& jb, uint64_t idx,
 __global__ void __launch_bounds__(kVarThreads) vdec_emit_kernel(const VarSeg* __restrict__ segs, const uint32_t* __restrict__ tile_seg,
                                                                 const VarJobDev* __restrict__ jobs, const uint64_t* __restrict__ tile_off,
                                                                 const uint64_t* __restrict__ job_total, int32_t* __restrict__ job_status) {
-  __shared__ uint8_t sm[kVarTileBytes + 16];
+  __shared__ __align__(16) uint8_t smraw[kVarTileBytes + 48];
   __shared__ uint32_t warp_sums[kVarThreads / 32];
   const uint32_t t = blockIdx.x;
   const VarSeg sg = segs[tile_seg[t]];
@@ -898,42 +954,81 @@ __global__ void __launch_bounds__(kVarThreads) vdec_emit_kernel(const VarSeg* __
   const uint64_t b1 = min(sg.n, b0 + kVarTileBytes);
   const uint64_t s0 = b0 ? b0 - 1 : 0;                  // look-behind
   const uint64_t s1 = min(sg.n, b1 + 9);                // look-ahead
-  for (uint64_t i = s0 + threadIdx.x; i < s1; i += kVarThreads) sm[i - s0] = sg.src[i];
+  // stage [s0, s1) in shared memory with the source's own 16-byte phase, so whole 16-byte blocks move
+  // as vectors; the ragged first/last block is copied bytewise (never reads outside the chunk)
+  const uint8_t* g0 = sg.src + s0;
+  const uint32_t phase = (uint32_t)((uintptr_t)g0 & 15);
+  const uint8_t* gbase = g0 - phase;                    // 16-byte aligned
+  const uint32_t span = phase + (uint32_t)(s1 - s0);    // bytes from gbase to the end of the staged range
+  for (uint32_t k = threadIdx.x; k * 16 < span; k += kVarThreads) {
+    const uint32_t lo = k * 16, hi = lo + 16;
+    if (lo >= phase && hi <= span) *reinterpret_cast<uint4*>(smraw + lo) = ld_stream(gbase + lo);
+    else for (uint32_t q = max(lo, phase); q < min(hi, span); ++q) smraw[q] = gbase[q];
+  }
+  const uint8_t* sm = smraw + phase;                     // sm[i - s0] == chunk byte i, as before
   __syncthreads();
-  // positions owned by this thread: b0 + 16*tid .. +16
-  const uint64_t p0 = b0 + 16ull * threadIdx.x;
-  uint32_t starts = 0;  // bit i: a varint starts at p0+i
-  uint32_t nstart = 0;
+  // Phase 1 - find the starts.  Each thread owns the 16-byte blocks k = tid (and tid + kVarThreads for the
+  // one or two blocks the phase shift adds) of the staged range: one conflict-free 128-bit shared load, then
+  // bit tricks.  A varint STARTS at byte i when byte i-1 has its top bit clear (or i is the chunk's first byte).
+  const int64_t pos0 = (int64_t)s0 - (int64_t)phase;   // chunk position of smraw[0]
+  uint32_t startm[2] = {0u, 0u};
 #pragma unroll
-  for (uint32_t i = 0; i < 16; ++i) {
-    const uint64_t p = p0 + i;
-    if (p < b1) {
-      const bool st = (p == 0) || !(sm[p - 1 - s0] & 0x80);
-      starts |= (uint32_t)st << i;
-      nstart += st;
+  for (uint32_t r = 0; r < 2; ++r) {
+    const uint32_t lo = (threadIdx.x + r * kVarThreads) * 16;
+    if (lo < span) {
+      const uint4 w = *reinterpret_cast<const uint4*>(smraw + lo);
+      auto msb4 = [](uint32_t x) { return (((x >> 7) & 0x01010101u) * 0x01020408u) >> 24; };   // 4 top bits -> nibble
+      const uint32_t cont = msb4(w.x) | (msb4(w.y) << 4) | (msb4(w.z) << 8) | (msb4(w.w) << 12);
+      const uint32_t prev_term = (lo == 0) ? 1u : ((smraw[lo - 1] & 0x80) ? 0u : 1u);
+      uint32_t st = (((~cont) << 1) | prev_term) & 0xFFFFu;
+      // positions of this block inside the tile [b0, b1): bits [first, last)
+      const int64_t rel0 = (int64_t)b0 - (pos0 + lo), rel1 = (int64_t)b1 - (pos0 + lo);
+      const uint32_t first = (uint32_t)max((int64_t)0, min((int64_t)16, rel0)), last = (uint32_t)max((int64_t)0, min((int64_t)16, rel1));
+      const uint32_t valid = ((1u << last) - 1u) & ~((1u << first) - 1u);
+      const int64_t zero_at = -(pos0 + lo);             // bit of chunk position 0, always a start
+      if (zero_at >= 0 && zero_at < 16) st |= 1u << zero_at;
+      startm[r] = st & valid;
     }
   }
-  uint32_t total;
-  const uint32_t rank0 = block_exclusive_scan(nstart, &total, warp_sums);
-  // elements before this tile: terminators before b0 within the job == tile_off[t]; a start at the
-  // very first byte of a later tile is counted by the previous tile's last terminator
-  // (+1 when a varint straddles in from the previous tile: it precedes ours but its terminator is here)
-  uint64_t idx = tile_off[t] + rank0 + ((b0 > 0 && (sm[0] & 0x80)) ? 1u : 0u);
+  // Phase 2 - rank them in position order (second-round blocks lie after every first-round block) and
+  // compact their offsets into a list, so that phase 3 can hand out ELEMENTS, not byte blocks, to threads:
+  // balanced work and fully coalesced stores.
+  __shared__ uint16_t start_at[kVarTileBytes + 32];
+  const uint32_t n_first = __popc(startm[0]), n_second = __popc(startm[1]);
+  uint32_t first_total, second_total;
+  const uint32_t rank_first = block_exclusive_scan(n_first, &first_total, warp_sums);
+  const uint32_t rank_second = block_exclusive_scan(n_second, &second_total, warp_sums);
+#pragma unroll
+  for (uint32_t r = 0; r < 2; ++r) {
+    uint32_t starts = startm[r], at = (r == 0) ? rank_first : first_total + rank_second;
+    const uint32_t lo = (threadIdx.x + r * kVarThreads) * 16;
+    while (starts) {
+      const uint32_t i = __ffs(starts) - 1;
+      starts &= starts - 1;
+      start_at[at++] = (uint16_t)(lo + i);
+    }
+  }
+  __syncthreads();
+  // Phase 3 - element j of the tile starts at smraw[start_at[j]]; its index in the tensor is the number of
+  // terminators before it: tile_off[t] counts those before b0 (+1 when a varint straddles in from the
+  // previous tile: it precedes ours but its terminator is here).
+  const uint32_t n_here = first_total + second_total;
+  const uint64_t idx0 = tile_off[t] + ((b0 > 0 && (sm[0] & 0x80)) ? 1u : 0u);
+  const uint32_t limit = span;                            // staged bytes end here (chunk end or +9 look-ahead)
+  const bool at_chunk_end = (s1 == sg.n);
   int32_t st_local = B200TFS_OK;
-  while (starts) {
-    const uint32_t i = __ffs(starts) - 1;
-    starts &= starts - 1;
-    uint64_t p = p0 + i, v = 0;
+  for (uint32_t j = threadIdx.x; j < n_here; j += kVarThreads) {
+    const uint32_t q = start_at[j];
+    uint64_t v = 0;
     int k = 0;
     for (; k < 10; ++k) {
-      if (p + k >= sg.n) { st_local = B200TFS_E_PARSE; break; }
-      const uint8_t b = sm[p + k - s0];
-      v |= (uint64_t)(b & 0x7F) << (7 * k);
-      if (!(b & 0x80)) break;
+      if (q + k >= limit) { if (at_chunk_end) st_local = B200TFS_E_PARSE; break; }
+      const uint8_t bb = smraw[q + k];
+      v |= (uint64_t)(bb & 0x7F) << (7 * k);
+      if (!(bb & 0x80)) break;
     }
     if (k == 10) st_local = B200TFS_E_PARSE;
-    if (idx < jb.n_elems) store_decoded(jb, idx, v, &st_local);
-    ++idx;
+    if (idx0 + j < jb.n_elems) store_decoded(jb, idx0 + j, v, &st_local);
   }
   if (st_local != B200TFS_OK) atomicMin(&job_status[sg.job], st_local);
 }
@@ -988,7 +1083,7 @@ cudaError_t launch_venc_len(const VarSeg* segs, const uint32_t* tile_seg, const 
 cudaError_t launch_vscan(const VarJobDev* jobs, const uint32_t* tile_val, uint64_t* tile_off, uint64_t* job_total, uint32_t n_jobs,
                          cudaStream_t stream) {
   if (!n_jobs) return cudaSuccess;
-  vscan_kernel<<<n_jobs, kVarThreads, 0, stream>>>(jobs, tile_val, tile_off, job_total);
+  vscan_kernel<<<n_jobs, kScanThreads, 0, stream>>>(jobs, tile_val, tile_off, job_total);
   return cudaGetLastError();
 }
 cudaError_t launch_venc_emit(const VarSeg* segs, const uint32_t* tile_seg, const VarJobDev* jobs, const uint64_t* tile_off,

@@ -142,3 +142,36 @@ def test_alignment_sweep_against_oracle(codec):
         ref = wire_oracle.decode_predict_response(resp)
         for k in ref:
             assert outs[k].tobytes() == ref[k].tobytes(), (n, k)
+
+
+def test_varint_multi_tile_against_oracle(codec):
+    """Packed-varint dtypes across many encode tiles (2048 elements) and decode tiles (4096 wire bytes):
+    varints straddling tile edges, 10-byte negatives, every dtype of the int_val / int64_val / uint32_val /
+    uint64_val / half_val / bool_val family, odd element counts."""
+    import ml_dtypes
+    from oracle import wire_oracle
+
+    rng = np.random.default_rng(5)
+    for dt, n in ((np.int64, 100003), (np.int32, 70001), (np.uint64, 50021), (np.uint32, 33333), (np.int16, 20011), (np.uint16, 20480),
+                  (np.int8, 12289), (np.uint8, 4097), (np.float16, 30011), (ml_dtypes.bfloat16, 8193), (np.bool_, 10007)):
+        if dt is np.bool_:
+            x = rng.integers(0, 2, size=n).astype(np.bool_)
+        elif np.dtype(dt).kind == "f" or dt is ml_dtypes.bfloat16:
+            x = rng.standard_normal(n).astype(dt)
+        else:
+            info = np.iinfo(dt)
+            mag = rng.integers(0, info.bits + 1, size=n)
+            raw = rng.integers(0, 2 ** 63, size=n, dtype=np.uint64) & ((np.uint64(1) << mag.astype(np.uint64)) - np.uint64(1))
+            x = raw.astype(np.uint64).view(np.int64).astype(dt) if info.min < 0 else raw.astype(dt)
+            if info.min < 0:
+                x[::3] = -np.abs(x[::3])
+        wire = codec.encode_tensor_protos([x])[0]
+        assert wire == wire_oracle.encode_tensor_proto(x), dt
+        back = codec.decode_tensor_protos([wire], strict=False)[0]
+        assert back.dtype == x.dtype and back.tobytes() == x.tobytes(), dt
+    # element count that disagrees with the shape -> ValueError, like reshape()
+    good = wire_oracle.encode_tensor_proto(np.arange(5000, dtype=np.int64))
+    bad = good.replace(b"\x08\x09\x12\x05\x12\x03\x08\x88\x27", b"\x08\x09\x12\x05\x12\x03\x08\x89\x27")
+    assert bad != good
+    with pytest.raises(ValueError):
+        codec.decode_tensor_protos([bad])
