@@ -93,6 +93,21 @@ class _Prepared:
         self.struct = t
 
 
+def _wire_bound(p: "_Prepared", tensor_content: bool) -> int:
+    """Upper bound of the bytes one prepared tensor occupies on the wire (payload + its own framing)."""
+    a = p.array
+    frame = 64 + 16 * max(a.ndim, 1) + len(p.key)
+    if p.struct.flags & N.F_PRESERIALIZED:
+        return int(a.size) + frame
+    n = int(a.size)
+    if p.struct.src_dtype != p.struct.wire_dtype:
+        return 4 * n + frame                      # f16 / bf16 -> DT_FLOAT
+    if tensor_content or a.dtype.kind in "fc" and a.dtype.itemsize >= 4 or a.dtype.kind == "b":
+        return a.nbytes + frame
+    per = {1: 10, 2: 10, 4: 10, 8: 10} if a.dtype.kind == "i" else {1: 2, 2: 3, 4: 5, 8: 10}   # varint bytes per element
+    return n * per[a.dtype.itemsize] + frame
+
+
 class DecodedSpec:
     """model_spec of a parsed response (model.proto:9-33)."""
 
@@ -169,8 +184,7 @@ class Codec:
                 dev_idx.append(i)
         if dev_idx:
             ts = (N.Tensor * len(dev_idx))(*[preps[i].struct for i in dev_idx])
-            cap = sum(preps[i].array.nbytes * (10 if preps[i].array.dtype.kind in "iu" and not tensor_content else
-                                               (2 if wire_dtype is not None else 1)) + 1024 for i in dev_idx)
+            cap = sum(_wire_bound(preps[i], tensor_content) + 512 for i in dev_idx)
             wire = np.empty(cap, dtype=np.uint8)
             off = (C.c_uint64 * len(dev_idx))()
             ln = (C.c_uint64 * len(dev_idx))()
@@ -214,10 +228,9 @@ class Codec:
         reqs = (N.Request * n)(*structs)
         cap = 0
         for preps, _, name in keep:
-            cap += 512 + len(name)
+            cap += 1024 + len(name)
             for p in preps:
-                grow = 10 if (p.array.dtype.kind in "iu" and not tensor_content) else 2
-                cap += p.array.nbytes * grow + len(p.key) + 256 + 32 * p.array.ndim
+                cap += _wire_bound(p, tensor_content) + 512
         wire = np.empty(cap, dtype=np.uint8)
         off = (C.c_uint64 * n)()
         ln = (C.c_uint64 * n)()
