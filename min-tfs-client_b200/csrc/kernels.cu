@@ -1,15 +1,18 @@
 // kernels.cu - sm_100a kernels of the TensorProto wire codec (pure HBM-bound byte packing: no
 // tensor cores, no tcgen05 - see DESIGN.md "Roofline").
 //
-//   move_kernel        the pack/unpack engine: moves every payload between tensor memory and the
-//                      wire arena (128-bit coalesced loads/stores, destination-aligned; a misaligned
-//                      side is realigned in registers with funnel shifts), applies the per-dtype
+//   move_kernel{,_inline}  the pack/unpack engine: moves every payload between tensor memory and the
+//                      wire arena (128-bit coalesced loads/stores, destination-aligned, a whole 32 KB
+//                      tile in flight per CTA; a misaligned side is realigned in registers with funnel
+//                      shifts, the neighbour block arriving by warp shuffle), applies the per-dtype
 //                      fix-up (float32 sNaN quieting, bool normalisation, f16/bf16 <-> f32 casts)
 //                      and writes the header fragments (tags, varint lengths, dims, keys).
-//   parse_kernel       one lane per PredictResponse / TensorProto: walks the tags (walker.h) and
+//   decode_fused_kernel    a whole PredictResponse decode in one launch: framing-template check or
+//                      tag walk (walker.h), destination layout, tile move, table to pinned host memory.
+//   parse_*_kernel     two-phase decode: one lane per PredictResponse / TensorProto walks the tags and
 //                      tabulates dtype, dims and where the values lie.
-//   varint_*           two-pass packed-varint encode and decode (int_val / int64_val / uint32_val /
-//                      uint64_val / half_val / bool_val).
+//   venc_* / vdec_* / vscan   packed-varint encode and decode (int_val / int64_val / uint32_val /
+//                      uint64_val / half_val / bool_val): tile byte counts -> per-job scan -> emit.
 //
 // What the reference does at these points: tensors.py:22 (per-element .item() loop feeding
 // RepeatedScalarContainer.extend), prediction_service_pb2_grpc.py:52-53 (SerializeToString /
@@ -18,7 +21,10 @@
 #include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <stdlib.h>
 #include <string.h>
+
+#include <utility>
 
 #include "kernels.h"
 #include "plan.h"
@@ -49,6 +55,14 @@ __device__ __forceinline__ void st_stream(uint8_t* p, const uint4& v) {
   asm volatile("st.global.L1::no_allocate.v4.u32 [%0], {%1,%2,%3,%4};"
                :: "l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
 }
+
+// Programmatic dependent launch: let the NEXT kernel of the stream start launching right away, and
+// hold our own memory accesses until every earlier kernel has completed and flushed.  Both are no-ops
+// unless the launch carries cudaLaunchAttributeProgrammaticStreamSerialization (launch_pdl below), in
+// which case the launch ramp of kernel N+1 overlaps the tail of kernel N instead of following it.
+// Ordering and visibility are unchanged.
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait_prior_grids() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 
 __device__ __forceinline__ uint32_t bool_norm_word(uint32_t w) {
   // per byte: b != 0 -> 1
@@ -143,7 +157,7 @@ __device__ __forceinline__ uint64_t src_bytes_for(uint32_t op, uint64_t n_out) {
 
 // ------------------------------------------------------------------------------------------------
 // vector bodies.  `src` / `dst` point at the first byte of the TILE's body; n = destination vectors
-// in the tile.  Every thread issues all loads of a batch (kBatch vectors) before its first store:
+// in the tile.  Every thread issues all loads of a batch (kBatchAligned / kBatchShift vectors) before its first store:
 // a 4 MiB tensor is smaller than the HBM bandwidth-delay product, so the whole tile must be in
 // flight at once - one DRAM round trip per batch, not per vector.
 // ------------------------------------------------------------------------------------------------
@@ -438,9 +452,15 @@ __device__ __forceinline__ void move_body(const uint8_t* plan) {
   }
 }
 
-__global__ void __launch_bounds__(kMoveThreads, 3) move_kernel(const uint8_t* __restrict__ plan) { move_body(plan); }
+__global__ void __launch_bounds__(kMoveThreads, 3) move_kernel(const uint8_t* __restrict__ plan) {
+  pdl_launch_dependents();
+  pdl_wait_prior_grids();   // the plan image itself was copied by an earlier operation of the stream
+  move_body(plan);
+}
 
 __global__ void __launch_bounds__(kMoveThreads, 3) move_kernel_inline(const __grid_constant__ InlinePlan plan) {
+  pdl_launch_dependents();
+  pdl_wait_prior_grids();   // the plan is in the parameters, but sources / the arena may be outputs of earlier kernels
   move_body(plan.bytes);
 }
 
@@ -624,6 +644,7 @@ __device__ __noinline__ void fused_slow_path(const FusedParams& fp, uint32_t r, 
 }
 
 __global__ void __launch_bounds__(kMoveThreads, 3) decode_fused_kernel(const __grid_constant__ FusedParams fp) {
+  pdl_launch_dependents();
   __shared__ __align__(16) uint8_t lines[256];
   __shared__ b200tfs_output outs_s[kFusedMaxOutputs + 1];  // +1: scratch slot for an entry whose key repeats
   __shared__ b200tfs_model_spec spec_s;
@@ -644,6 +665,7 @@ __global__ void __launch_bounds__(kMoveThreads, 3) decode_fused_kernel(const __g
   }
   const uint8_t* rec = fp.w + off;
   uint8_t* dst_slot = fp.dst + (uint64_t)r * fp.dst_stride;
+  pdl_wait_prior_grids();   // the template was written by the previous decode launch; the wire may be fresh too
 
   // ---- fast path: does this record carry the template's framing? ----
   // The template header and chunk table are staged in shared memory by five threads while every
@@ -718,15 +740,6 @@ __global__ void __launch_bounds__(kMoveThreads, 3) decode_fused_kernel(const __g
 // terminator counts -> the same scan -> decode.  A tile is kVarTileElems elements (encode) or
 // kVarTileBytes wire bytes (decode); every kernel uses kVarThreads threads per CTA.
 // ------------------------------------------------------------------------------------------------
-__device__ __forceinline__ uint64_t load_as_u64(const uint8_t* src, uint64_t e, uint32_t size, uint32_t is_signed) {
-  switch (size) {
-    case 1: { uint8_t v = src[e]; return is_signed ? (uint64_t)(int64_t)(int8_t)v : v; }
-    case 2: { uint16_t v = reinterpret_cast<const uint16_t*>(src)[e]; return is_signed ? (uint64_t)(int64_t)(int16_t)v : v; }
-    case 4: { uint32_t v = reinterpret_cast<const uint32_t*>(src)[e]; return is_signed ? (uint64_t)(int64_t)(int32_t)v : v; }
-    default: return reinterpret_cast<const uint64_t*>(src)[e];
-  }
-}
-
 // kVarPerThread elements per thread, striped (element base + i*kVarThreads + tid), ALL loads issued
 // before any use (the element width is resolved outside the loop so the loads can be hoisted)
 template <uint32_t SZ, bool SG>
@@ -1036,6 +1049,21 @@ __global__ void __launch_bounds__(kVarThreads) vdec_emit_kernel(const VarSeg* __
 // ------------------------------------------------------------------------------------------------
 // launchers (the only symbols codec_host.cpp sees)
 // ------------------------------------------------------------------------------------------------
+// launch, optionally with programmatic stream serialization (see pdl_* above).  Measured on the C2 bench:
+// with it, 8 overlapping lanes gain 4 % (0.89 -> 0.93 of HBM peak) but a single stream of back-to-back
+// launches loses 0.6 us per launch (3.5 -> 4.1 us), so it is opt-in: B200TFS_PDL=1.
+template <class... KArgs, class... Args>
+static cudaError_t launch_pdl(void (*kernel)(KArgs...), uint32_t grid, uint32_t block, cudaStream_t stream, Args&&... args) {
+  static const bool off = [] { const char* e = getenv("B200TFS_PDL"); return !(e && e[0] == '1'); }();
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(grid); cfg.blockDim = dim3(block); cfg.dynamicSmemBytes = 0; cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr; cfg.numAttrs = off ? 0 : 1;
+  return cudaLaunchKernelEx(&cfg, kernel, std::forward<Args>(args)...);
+}
+
 cudaError_t launch_move(const uint8_t* plan_dev, const uint8_t* plan_host, uint32_t plan_bytes, uint32_t n_tiles,
                         uint32_t n_small, cudaStream_t stream) {
   const uint32_t warps = kMoveThreads / 32;
@@ -1044,11 +1072,9 @@ cudaError_t launch_move(const uint8_t* plan_dev, const uint8_t* plan_host, uint3
   if (plan_dev == nullptr) {
     InlinePlan ip;
     memcpy(ip.bytes, plan_host, plan_bytes);
-    move_kernel_inline<<<grid, kMoveThreads, 0, stream>>>(ip);
-  } else {
-    move_kernel<<<grid, kMoveThreads, 0, stream>>>(plan_dev);
+    return launch_pdl(move_kernel_inline, grid, kMoveThreads, stream, ip);
   }
-  return cudaGetLastError();
+  return launch_pdl(move_kernel, grid, kMoveThreads, stream, plan_dev);
 }
 
 cudaError_t launch_parse_responses(const uint8_t* w, const uint64_t* rec_off, const uint64_t* rec_len, int n, int max_outputs,
@@ -1070,8 +1096,7 @@ uint32_t tiles_for_host(uint64_t n_out, uint32_t vpt) { return tiles_for(n_out, 
 
 cudaError_t launch_decode_fused(const FusedParams& fp, uint32_t grid, cudaStream_t stream) {
   if (!grid) return cudaSuccess;
-  decode_fused_kernel<<<grid, kMoveThreads, 0, stream>>>(fp);
-  return cudaGetLastError();
+  return launch_pdl(decode_fused_kernel, grid, kMoveThreads, stream, fp);
 }
 
 cudaError_t launch_venc_len(const VarSeg* segs, const uint32_t* tile_seg, const VarJobDev* jobs, uint32_t* tile_val, uint32_t n_tiles,
