@@ -311,3 +311,32 @@ def test_c4_cast_round_trip(dev, codec):
         resp = wire_oracle.build_predict_response([("y", f)])
         back = codec.decode_predict_response(resp, out_dtypes={"y": np_dt})[0]["y"]
         assert np.array_equal(back.view(np.uint16), f.astype(np_dt).view(np.uint16))
+
+
+def test_one_gib_tensor(dev):
+    """Largest practical single message: fp32 [16384, 16384] = 1 GiB payload (protobuf's limit is 2 GiB; the
+    E_TOOBIG side of that limit is a CPU test).  The whole 1 GiB wire is compared with the C oracle's."""
+    n = 16384
+    P = n * n * 4
+    row = np.random.default_rng(3).integers(0, 2 ** 32, size=n, dtype=np.uint32)
+    full = np.empty((n, n), dtype=np.uint32)
+    for r in range(n):                                             # every row a different rotation: no two blocks equal
+        full[r, : n - (r % n)] = row[r % n:]
+        full[r, n - (r % n):] = row[: r % n]
+    x = full.view(np.float32)                                      # random bits: includes NaNs of every kind (quieting path)
+    src = dev.upload(x)
+    dims = (C.c_int64 * 2)(n, n)
+    ts = (N.Tensor * 1)(N.Tensor(data=src, src_dtype=1, wire_dtype=1, rank=2, flags=0, dims=dims, key=b"x", key_len=1, packed_len=0))
+    rq = (N.Request * 1)(N.Request(model_name=b"default", model_name_len=7, has_version=1, order=N.ORDER_UPB, version=1, n_inputs=1, reserved=0,
+                                   inputs=ts))
+    need, total = C.c_uint64(), C.c_uint64()
+    N.check(dev.lib.b200tfs_request_size(rq, C.byref(total)))
+    N.check(dev.lib.b200tfs_request_arena_size(1, rq, C.byref(need)))
+    arena = dev.malloc(need.value)
+    off, ln = (C.c_uint64 * 1)(), (C.c_uint64 * 1)()
+    N.check(dev.lib.b200tfs_encode_requests(dev.ctx, 1, rq, arena, need.value, off, ln))
+    dev.sync()
+    expect = wire_oracle.encode_predict_request("default", 1, [("x", x)])
+    assert ln[0] == total.value == len(expect)
+    got = dev.download(arena + off[0], ln[0])
+    assert got.tobytes() == expect
