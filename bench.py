@@ -490,11 +490,40 @@ def saturation_pass(bench, peak, n=1024):
     ms = bench.timed_main(lambda: lane.launch("sat"), reps)
     us = ms / (reps * 2) * 1e3
     alg = n * (2 * P + int(ln[0]) - P)
-    lib.b200tfs_free(lane.ctx, src)
+    out = {"workload": f"{n} PredictRequests of fp32[3,224,224] ({n * P >> 20} MiB) encoded by one move_kernel launch (BASELINE configs[4], per-GPU share)",
+           "launch_us": us, "algorithmic_bytes_per_launch": alg, "achieved": alg / (us * 1e-6) / 1e9, "frac": alg / (us * 1e-6) / 1e9 / peak,
+           "how": "CUDA graph of 2 launches replayed 10x on one stream, CUDA events; 1.2 GB working set"}
+    # the decode side of the same share: 1024 PredictResponses of that size through ONE decode_fused_kernel launch
+    prefix, suffix = response_wire_parts(b"image", (3, 224, 224), P)
+    rec = np.frombuffer(prefix + bytes(P) + suffix, dtype=np.uint8)
+    stride = (rec.size + 255) & ~255
     lib.b200tfs_free(lane.ctx, arena)
-    return {"workload": f"{n} PredictRequests of fp32[3,224,224] ({n * P >> 20} MiB) encoded by one move_kernel launch (BASELINE configs[4], per-GPU share)",
-            "launch_us": us, "algorithmic_bytes_per_launch": alg, "achieved": alg / (us * 1e-6) / 1e9, "frac": alg / (us * 1e-6) / 1e9 / peak,
-            "how": "CUDA graph of 2 launches replayed 10x on one stream, CUDA events; 1.2 GB working set"}
+    wire = lane.malloc(stride * n)
+    N.check(lib.b200tfs_memcpy_h2d(lane.ctx, wire, rec.ctypes.data, rec.size))
+    lane.sync()
+    for i in range(1, n):
+        N.check(lib.b200tfs_memcpy_d2d(lane.ctx, wire + i * stride, wire, rec.size))
+    roff = (C.c_uint64 * n)(*[i * stride for i in range(n)])
+    rlen = (C.c_uint64 * n)(*[rec.size] * n)
+    dst_stride = (P + 255) & ~255
+    dst = src   # the request tensors are no longer needed: decode into their buffer (n * P >= n * dst_stride? P is 256-aligned: yes)
+    assert dst_stride == P
+
+    def decode(_):
+        N.check(lib.b200tfs_decode_responses(lane.ctx, wire, n, roff, rlen, dst, dst_stride))
+    lane.capture("sat_dec", decode, [0, 0])
+    bench.timed_main(lambda: lane.launch("sat_dec"), 2)
+    ms = bench.timed_main(lambda: lane.launch("sat_dec"), reps)
+    st = (C.c_int32 * n)()
+    N.check(lib.b200tfs_decode_results(lane.ctx, n, None, None, None, st))
+    assert all(v == 0 for v in st)
+    us_d = ms / (reps * 2) * 1e3
+    alg_d = n * (2 * P + rec.size - P)
+    out["decode"] = {"workload": f"{n} PredictResponses of fp32[3,224,224] decoded by one decode_fused_kernel launch", "launch_us": us_d,
+                     "algorithmic_bytes_per_launch": alg_d, "achieved": alg_d / (us_d * 1e-6) / 1e9, "frac": alg_d / (us_d * 1e-6) / 1e9 / peak}
+    lib.b200tfs_free(lane.ctx, src)
+    lib.b200tfs_free(lane.ctx, wire)
+    return out
 
 
 def peaks():

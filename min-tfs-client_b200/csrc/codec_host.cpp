@@ -425,7 +425,7 @@ struct PlanBuilder {
   }
 };
 
-uint32_t pick_vec_per_tile(const b200tfs_ctx* c, uint64_t large_bytes) {
+uint32_t pick_vec_per_tile(const b200tfs_ctx* c, uint64_t large_bytes, uint64_t max_tile = 65536) {
   uint64_t tile = c->tile_bytes_override;
   if (!tile) {
     // one batch per thread (16 KB per CTA) until the machine is full, then fatter tiles
@@ -434,7 +434,7 @@ uint32_t pick_vec_per_tile(const b200tfs_ctx* c, uint64_t large_bytes) {
     uint64_t target_tiles = (uint64_t)c->sm_count * 8;
     tile = (large_bytes + target_tiles - 1) / target_tiles;
     tile = (tile + 32767) & ~32767ull;
-    tile = std::min<uint64_t>(std::max<uint64_t>(tile, 32768), 65536);
+    tile = std::min<uint64_t>(std::max<uint64_t>(tile, 32768), max_tile);
   }
   tile = std::max<uint64_t>(tile & ~31ull, 32);
   return (uint32_t)(tile / 16);
@@ -932,7 +932,9 @@ int b200tfs_decode_responses(b200tfs_ctx* c, const void* arena_dev, int32_t n, c
   if (!c->capturing) CU(cudaSetDevice(c->device));
   uint64_t wire_total = 0;
   for (int i = 0; i < n; ++i) wire_total += rec_len[i];
-  const uint32_t vpt = pick_vec_per_tile(c, wire_total);
+  // every CTA of the fused kernel first verifies the record's framing (two dependent round trips), so big
+  // batches get fatter tiles than the plain move: measured 0.745 / 0.775 / 0.80 of peak at 64 / 128 / 256 KB
+  const uint32_t vpt = pick_vec_per_tile(c, wire_total, 262144);
   const uint64_t tile_bytes = 16ull * vpt;
   FusedLayout L = fused_layout(n);
   int rc;
