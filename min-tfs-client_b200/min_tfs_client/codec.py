@@ -226,6 +226,16 @@ class Codec:
         if n == 0:
             return []
         reqs = (N.Request * n)(*structs)
+        if n == 1:
+            # one request whose size is closed-form (no varint-packed input): copy straight into the bytes object
+            total = C.c_uint64()
+            if self._lib.b200tfs_request_size(reqs, C.byref(total)) == N.OK:
+                obj, addr = _new_bytes(int(total.value))
+                off = (C.c_uint64 * 1)()
+                ln = (C.c_uint64 * 1)()
+                N.check(self._lib.b200tfs_encode_requests_host(self._ctx, 1, reqs, addr, total.value, off, ln))
+                assert off[0] == 0 and ln[0] == total.value
+                return [obj]
         cap = 0
         for preps, _, name in keep:
             cap += 1024 + len(name)
@@ -245,6 +255,10 @@ class Codec:
         n = len(wires)
         off = (C.c_uint64 * max(n, 1))()
         ln = (C.c_uint64 * max(n, 1))()
+        if n == 1 and isinstance(wires[0], bytes) and len(wires[0]):
+            # a single message: hand its own buffer to the library (read-only view, no copy)
+            ln[0] = len(wires[0])
+            return np.frombuffer(wires[0], dtype=np.uint8), off, ln
         cur = 0
         for i, w in enumerate(wires):
             off[i] = cur
@@ -404,6 +418,22 @@ class Codec:
                 N.check(st[k])
                 results[i] = arrays[k]
         return results  # type: ignore[return-value]
+
+
+# ---- zero-copy helpers -----------------------------------------------------------------------------
+_PyBytes_FromStringAndSize = C.pythonapi.PyBytes_FromStringAndSize
+_PyBytes_FromStringAndSize.restype = C.py_object
+_PyBytes_FromStringAndSize.argtypes = [C.c_void_p, C.c_ssize_t]
+_PyBytes_AsString = C.pythonapi.PyBytes_AsString
+_PyBytes_AsString.restype = C.c_void_p
+_PyBytes_AsString.argtypes = [C.py_object]
+
+
+def _new_bytes(n: int):
+    """An uninitialised bytes object of n bytes and the address of its buffer: the device-to-host copy lands
+    directly in the object grpc will send (no intermediate buffer, no .tobytes())."""
+    obj = _PyBytes_FromStringAndSize(None, n)
+    return obj, _PyBytes_AsString(obj)
 
 
 _tls = threading.local()
