@@ -1,46 +1,43 @@
-"""``DataType``: resolve a numpy type, a ``"DT_*"`` string or a DataType enum int.
+"""``DataType``: one row of the dtype table, looked up by numpy type, ``"DT_*"`` name or enum value.
 
-Interface and error behaviour of the reference's ``min_tfs_client/types.py:13-42``: attributes
-``numpy_dtype, is_numeric, tf_dtype, enum, proto_field_name``; ``ValueError`` for a type outside the
-table or an argument that is not a type/str/int; ``KeyError`` for an unmapped string or enum.
+Public behaviour of the reference's ``min_tfs_client/types.py:13-42``: the constructor accepts a numpy
+scalar type, a TensorFlow dtype name or a ``DataType`` enum integer and exposes ``numpy_dtype``,
+``is_numeric``, ``tf_dtype``, ``enum`` and ``proto_field_name``.  Failure modes are the reference's too:
+``ValueError`` for a type outside the table or an argument of another kind, ``KeyError`` for a name or
+enum value without a row.
 """
-from typing import Union
-
 import numpy as np
 
-from .constants import (
-    ENUM_TO_TF_MAPPING,
-    NP_TO_ENUM_MAPPING,
-    NP_TO_TF_MAPPING,
-    NUMERICAL_TYPES,
-    TF_TO_NP_MAPPING,
-)
+from . import constants as _c
+
+
+def _row_for(key):
+    """numpy scalar type for any of the three accepted spellings."""
+    if isinstance(key, type):
+        return key
+    if isinstance(key, str):
+        return np.dtype(_c.TF_TO_NP_MAPPING[key]).type
+    if isinstance(key, int):
+        return np.dtype(_c.TF_TO_NP_MAPPING[_c.ENUM_TO_TF_MAPPING[key]]).type
+    raise ValueError(f"Expected dtype of types: type, str, or int, got {type(key)}")
 
 
 class DataType:
-    VALID_TYPES = NUMERICAL_TYPES.union({np.str_, np.bool_})
+    VALID_TYPES = frozenset(_c.NUMERICAL_TYPES) | {np.str_, np.bool_}
 
-    def __init__(self, dtype: Union[type, str, int]):
-        resolved = self._get_numpy_dtype(dtype)
-        self._validate_dtype(resolved)
-        row = NP_TO_TF_MAPPING[resolved]
-        self.numpy_dtype = resolved
-        self.is_numeric = resolved in NUMERICAL_TYPES
-        self.tf_dtype = row.TFDType
-        self.enum = NP_TO_ENUM_MAPPING[resolved]
-        self.proto_field_name = row.TensorProtoField
+    __slots__ = ("numpy_dtype", "is_numeric", "tf_dtype", "enum", "proto_field_name")
 
-    def _validate_dtype(self, numpy_dtype: type) -> None:
-        if numpy_dtype in self.VALID_TYPES:
-            return
-        allowed = ", ".join(t.__name__ for t in self.VALID_TYPES)
-        raise ValueError(f"Dtype {numpy_dtype.__name__} is not valid. Allowable values: {allowed}")
+    def __init__(self, dtype):
+        np_type = _row_for(dtype)
+        if np_type not in self.VALID_TYPES:
+            names = ", ".join(t.__name__ for t in self.VALID_TYPES)
+            raise ValueError(f"Dtype {np_type.__name__} is not valid. Allowable values: {names}")
+        tf_name, field = _c.NP_TO_TF_MAPPING[np_type]
+        self.numpy_dtype = np_type
+        self.is_numeric = np_type in _c.NUMERICAL_TYPES
+        self.tf_dtype = tf_name
+        self.enum = _c.NP_TO_ENUM_MAPPING[np_type]
+        self.proto_field_name = field
 
-    def _get_numpy_dtype(self, dtype: Union[type, str, int]) -> type:
-        if isinstance(dtype, type):
-            return dtype
-        if isinstance(dtype, str):
-            return np.dtype(TF_TO_NP_MAPPING[dtype]).type
-        if isinstance(dtype, int):
-            return np.dtype(TF_TO_NP_MAPPING[ENUM_TO_TF_MAPPING[dtype]]).type
-        raise ValueError(f"Expected dtype of types: type, str, or int, got {type(dtype)}")
+    def __repr__(self):
+        return f"DataType({self.tf_dtype})"
