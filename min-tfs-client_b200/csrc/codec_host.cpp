@@ -428,8 +428,7 @@ struct PlanBuilder {
 uint32_t pick_vec_per_tile(const b200tfs_ctx* c, uint64_t large_bytes, uint64_t max_tile = 65536) {
   uint64_t tile = c->tile_bytes_override;
   if (!tile) {
-    // one batch per thread (16 KB per CTA) until the machine is full, then fatter tiles
-    // 32 KB per CTA: the aligned path keeps all of it in flight at once (8 x 16 B per thread), which
+    // 32 KB per CTA: both vector paths keep all of it in flight at once (8 x 16 B per thread), which
     // measured best both for one 4 MiB tensor alone and for many overlapping launches
     uint64_t target_tiles = (uint64_t)c->sm_count * 8;
     tile = (large_bytes + target_tiles - 1) / target_tiles;
@@ -861,6 +860,9 @@ extern "C" int b200tfs_unpack_outputs(b200tfs_ctx* c, const void* arena_dev, int
     const uint8_t* w = (const uint8_t*)arena_dev + (out_rec_off ? out_rec_off[j] : 0);  // table offsets are record-relative
     if (status) status[j] = B200TFS_OK;
     if (!o.n_elems) continue;
+    const bool content_only = o.n_chunks == 0 && o.content_len && o.content_len == o.dst_bytes;
+    if (o.status != B200TFS_OK && !content_only)
+      return fail(B200TFS_E_ARG, "output %d was tabulated with status %d: nothing to unpack", j, o.status);
     DtypeInfo di = dtype_info(o.dtype);
     if (di.kind == VK_NONE || di.kind == VK_STRING) return fail(B200TFS_E_DTYPE, "output %d: dtype %d has no device payload", j, o.dtype);
     if (!dst_dev[j]) return fail(B200TFS_E_ARG, "output %d: dst is NULL", j);

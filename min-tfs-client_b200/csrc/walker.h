@@ -391,6 +391,8 @@ B2_HD void finalize_output(b200tfs_output& o, const ChunkTags& ct) {
     prod *= (uint64_t)d;
   }
   if (bad) { o.status = B200TFS_E_SHAPE; return; }
+  // n_elems / dst_bytes describe the SHAPE (once it is fully known), also when the values do not match it:
+  // the tolerant decoder needs them to accept tensor_content in place of the typed field
   if (di.kind == VK_FIXED) {
     const uint64_t count = total / di.elem_size;  // complex: interleaved (re, im) pairs, TF convention
     if (total % di.elem_size) { o.status = B200TFS_E_SHAPE; return; }
@@ -398,10 +400,12 @@ B2_HD void finalize_output(b200tfs_output& o, const ChunkTags& ct) {
       if (prod == 0 || count % prod) { o.status = B200TFS_E_SHAPE; return; }
       o.dims[infer] = (int64_t)(count / prod); prod = count; o.flags |= B200TFS_OF_DIM_INFERRED;
     }
+    o.n_elems = prod; o.dst_bytes = prod * di.elem_size;
     if (count != prod) { o.status = B200TFS_E_SHAPE; return; }  // reshape() ValueError: no broadcast, no padding
   } else if (di.kind == VK_VARINT || di.kind == VK_BOOL) {
     o.flags |= B200TFS_OF_VARINT;
     if (infer >= 0) { o.status = B200TFS_E_NONCANONICAL; return; }
+    o.n_elems = prod; o.dst_bytes = prod * di.elem_size;
     if ((total == 0) != (prod == 0)) { o.status = B200TFS_E_SHAPE; return; }
     if (total < prod) { o.status = B200TFS_E_SHAPE; return; }   // every element needs at least one byte
   } else {  // strings: unpacked on the host from msg_off/msg_len
@@ -409,10 +413,9 @@ B2_HD void finalize_output(b200tfs_output& o, const ChunkTags& ct) {
       if (prod == 0 || o.n_strings % prod) { o.status = B200TFS_E_SHAPE; return; }
       o.dims[infer] = (int64_t)(o.n_strings / prod); prod = o.n_strings; o.flags |= B200TFS_OF_DIM_INFERRED;
     }
+    o.n_elems = prod; o.dst_bytes = 0;
     if (o.n_strings != prod) { o.status = B200TFS_E_SHAPE; return; }
   }
-  o.n_elems = prod;
-  o.dst_bytes = prod * di.elem_size;
 }
 
 B2_HD void spec_reset(b200tfs_model_spec& s) {

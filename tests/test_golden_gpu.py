@@ -175,3 +175,28 @@ def test_varint_multi_tile_against_oracle(codec):
     assert bad != good
     with pytest.raises(ValueError):
         codec.decode_tensor_protos([bad])
+
+
+def test_modes_tensor_content_and_keep_snan(codec):
+    """The two non-default encode modes against the oracle: tensor_content (TF's own layout, raw little-endian
+    memory for every numeric dtype) and KEEP_SNAN (typed field, float32 bits untouched); and the tolerant decoder
+    reading tensor_content back."""
+    import ml_dtypes
+    from oracle import wire_oracle
+
+    rng = np.random.default_rng(8)
+    bits = rng.integers(0, 2 ** 32, size=5003, dtype=np.uint32).view(np.float32)     # NaNs of every kind
+    assert codec.encode_tensor_protos([bits], keep_snan=True)[0] == wire_oracle.encode_tensor_proto(bits, keep_snan=True)
+    assert codec.encode_tensor_protos([bits], keep_snan=True)[0] != codec.encode_tensor_protos([bits])[0]
+    for x in (bits.reshape(5003, 1), rng.standard_normal((33, 65)), rng.integers(-2 ** 62, 2 ** 62, size=(9, 11), dtype=np.int64),
+              rng.integers(0, 2, size=77).astype(np.bool_), rng.standard_normal(4099).astype(np.float16),
+              rng.standard_normal(130).astype(ml_dtypes.bfloat16), (rng.standard_normal(50) + 1j * rng.standard_normal(50)).astype(np.complex64)):
+        wire = codec.encode_tensor_protos([x], tensor_content=True)[0]
+        assert wire == wire_oracle.encode_tensor_proto(x, tensor_content=True), x.dtype
+        back = codec.decode_tensor_protos([wire], strict=False)[0]                    # tolerant: raw bytes, TF convention
+        assert back.dtype == x.dtype and back.shape == x.shape and back.tobytes() == x.tobytes(), x.dtype
+        if x.size:
+            with pytest.raises((ValueError, KeyError)):                               # the reference reads only the typed field (and has no bfloat16 row)
+                codec.decode_tensor_protos([wire], strict=True)
+    pair = [("a", bits), ("b", rng.standard_normal(7))]
+    assert codec.encode_predict_requests([("m", None, pair)], tensor_content=True)[0] == wire_oracle.encode_predict_request("m", None, pair, tensor_content=True)
