@@ -340,3 +340,52 @@ def test_one_gib_tensor(dev):
     assert ln[0] == total.value == len(expect)
     got = dev.download(arena + off[0], ln[0])
     assert got.tobytes() == expect
+
+
+def test_fused_decode_replays_every_golden_case_twice(dev):
+    """All golden PredictResponses through the single-launch decode, each TWICE in a row: the first launch walks
+    the tags, the second takes the framing-template fast path; both must tabulate the same thing and both must
+    agree with the reference for every fixed-width output (varint / string outputs are tabulated only)."""
+    import hashlib
+
+    import golden_util as G
+    from min_tfs_client.constants import numpy_for_enum
+
+    cases = G.load("decode.json")
+    for name, rec in cases.items():
+        wire = G.decode_case_wire(name, rec)
+        if not wire:
+            continue
+        stride = max(256, (len(wire) + 255) & ~255)
+        snap = []
+        for rep in range(2):
+            buf, dst, outs, n_outs, specs, status = _decode_fused(dev, [wire], stride)
+            if "parse_raises" in rec:
+                assert status[0] == N.E_PARSE, (name, rep)
+                snap.append(None)
+                continue
+            assert status[0] == N.OK, (name, rep, status[0])
+            table = {}
+            for k in range(n_outs[0]):
+                o = outs[k]
+                key = buf[o.key_off: o.key_off + o.key_len].tobytes().decode()
+                vals = None
+                if o.status == N.OK and not (o.flags & N.OF_VARINT) and o.dtype != 7 and o.n_elems:
+                    vals = dev.download(dst + o.dst_off, o.dst_bytes).tobytes()
+                table[key] = (o.dtype, o.rank, tuple(o.dims[i] for i in range(o.rank)), o.status, o.flags, o.n_chunks, o.n_elems, vals)
+            snap.append(table)
+            expected = rec["outputs"]
+            assert set(table) == set(expected), (name, rep)
+            for key, exp in expected.items():
+                dtype, rank, dims, st, flags, n_chunks, n_elems, vals = table[key]
+                if "raises" in exp or exp.get("dtype") == "str" or vals is None:
+                    continue
+                np_t = numpy_for_enum(dtype)
+                if np_t in (np.complex64, np.complex128) or (name == "dtype_half_ref_quirk"):
+                    continue
+                assert np.dtype(np_t).str == exp["dtype"] and list(dims) == exp["shape"], (name, key)
+                if "data" in exp:
+                    assert vals.hex() == exp["data"], (name, key, rep)
+                else:
+                    assert hashlib.sha256(vals).hexdigest() == exp["sha256"], (name, key, rep)
+        assert snap[0] == snap[1], name      # walk and template fast path tabulate identically
