@@ -16,6 +16,7 @@
 
 #include <algorithm>
 #include <string>
+#include <unordered_map>
 #include <vector>
 
 #include "../../include/b200tfs.h"
@@ -64,6 +65,14 @@ struct Slot {  // one in-flight plan upload: pinned image + device image + compl
 
 }  // namespace
 
+struct MeasuredTensor {     // what b200tfs_measure learnt about one varint tensor (device addresses of its counters)
+  uint64_t n_elems = 0, packed_len = 0;
+  int32_t dtype = 0;
+  void* tile_val = nullptr;
+  void* group_sum = nullptr;
+  void* total = nullptr;
+};
+
 struct b200tfs_ctx {
   int device = 0;
   int sm_count = 148;
@@ -82,6 +91,10 @@ struct b200tfs_ctx {
   void* tpl_dev = nullptr;  // two framing templates (device), used alternately by successive decode launches
   uint32_t tpl_flip = 0;
   int32_t fused_n = 0;      // records of the last b200tfs_decode_responses
+  // counters left by b200tfs_measure, keyed by tensor address; consumed by the encode that follows
+  Growable measured_dev;
+  uint64_t measured_used = 0;
+  std::unordered_map<const void*, MeasuredTensor> measured;
 };
 
 static int grow_dev(b200tfs_ctx* c, Growable& g, uint64_t need) {
@@ -188,6 +201,7 @@ int b200tfs_destroy(b200tfs_ctx* c) {
   if (c->tpl_dev) cudaFree(c->tpl_dev);
   for (Slot* g : c->graph_slots) { cudaFreeHost(g->host.p); cudaFree(g->dev.p); delete g; }
   if (c->scratch_dev.p) cudaFree(c->scratch_dev.p);
+  if (c->measured_dev.p) cudaFree(c->measured_dev.p);
   if (c->scratch_host.p) cudaFreeHost(c->scratch_host.p);
   if (c->stage_dev.p) cudaFree(c->stage_dev.p);
   if (c->arena_dev.p) cudaFree(c->arena_dev.p);

@@ -11,8 +11,8 @@
 //                      tag walk (walker.h), destination layout, tile move, table to pinned host memory.
 //   parse_*_kernel     two-phase decode: one lane per PredictResponse / TensorProto walks the tags and
 //                      tabulates dtype, dims and where the values lie.
-//   venc_* / vdec_* / vscan   packed-varint encode and decode (int_val / int64_val / uint32_val /
-//                      uint64_val / half_val / bool_val): tile byte counts -> per-job scan -> emit.
+//   venc_* / vdec_*    packed-varint encode and decode (int_val / int64_val / uint32_val / uint64_val /
+//                      half_val / bool_val): varint_kernels.cuh.
 //
 // What the reference does at these points: tensors.py:22 (per-element .item() loop feeding
 // RepeatedScalarContainer.extend), prediction_service_pb2_grpc.py:52-53 (SerializeToString /
@@ -736,315 +736,9 @@ __global__ void __launch_bounds__(kMoveThreads, 3) decode_fused_kernel(const __g
 }
 
 // ------------------------------------------------------------------------------------------------
-// packed varints.  Encode is  tile lengths -> per-job exclusive scan -> emit ; decode is
-// terminator counts -> the same scan -> decode.  A tile is kVarTileElems elements (encode) or
-// kVarTileBytes wire bytes (decode); every kernel uses kVarThreads threads per CTA.
+// packed varints: venc_len / venc_emit / vdec_count / vdec_emit
 // ------------------------------------------------------------------------------------------------
-// kVarPerThread elements per thread, striped (element base + i*kVarThreads + tid), ALL loads issued
-// before any use (the element width is resolved outside the loop so the loads can be hoisted)
-template <uint32_t SZ, bool SG>
-__device__ __forceinline__ void load_striped_t(const uint8_t* src, uint64_t e0, uint32_t cnt, uint64_t (&v)[kVarPerThread]) {
-#pragma unroll
-  for (uint32_t i = 0; i < kVarPerThread; ++i) {
-    const uint32_t k = i * kVarThreads + threadIdx.x;
-    uint64_t x = 0;
-    if (k < cnt) {
-      const uint64_t e = e0 + k;
-      if (SZ == 1) { const uint8_t t = src[e]; x = SG ? (uint64_t)(int64_t)(int8_t)t : t; }
-      else if (SZ == 2) { const uint16_t t = reinterpret_cast<const uint16_t*>(src)[e]; x = SG ? (uint64_t)(int64_t)(int16_t)t : t; }
-      else if (SZ == 4) { const uint32_t t = reinterpret_cast<const uint32_t*>(src)[e]; x = SG ? (uint64_t)(int64_t)(int32_t)t : t; }
-      else x = reinterpret_cast<const uint64_t*>(src)[e];
-    }
-    v[i] = x;
-  }
-}
-__device__ __forceinline__ void load_striped(const uint8_t* src, uint64_t e0, uint32_t cnt, uint32_t size, uint32_t is_signed,
-                                             uint64_t (&v)[kVarPerThread]) {
-  switch (size * 2 + (is_signed ? 1 : 0)) {
-    case 2: load_striped_t<1, false>(src, e0, cnt, v); break;
-    case 3: load_striped_t<1, true>(src, e0, cnt, v); break;
-    case 4: load_striped_t<2, false>(src, e0, cnt, v); break;
-    case 5: load_striped_t<2, true>(src, e0, cnt, v); break;
-    case 8: load_striped_t<4, false>(src, e0, cnt, v); break;
-    case 9: load_striped_t<4, true>(src, e0, cnt, v); break;
-    default: load_striped_t<8, false>(src, e0, cnt, v); break;
-  }
-}
-
-// block-wide exclusive scan of one value per thread (kVarThreads threads); returns the exclusive
-// prefix and writes the block total to *total
-__device__ __forceinline__ uint32_t block_exclusive_scan(uint32_t v, uint32_t* total, uint32_t* warp_sums /* smem[kVarThreads/32] */) {
-  const uint32_t lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-  uint32_t inc = v;
-#pragma unroll
-  for (int d = 1; d < 32; d <<= 1) {
-    uint32_t n = __shfl_up_sync(0xFFFFFFFFu, inc, d);
-    if (lane >= d) inc += n;
-  }
-  if (lane == 31) warp_sums[wid] = inc;
-  __syncthreads();
-  uint32_t base = 0, tot = 0;
-#pragma unroll
-  for (uint32_t w = 0; w < kVarThreads / 32; ++w) {
-    uint32_t x = warp_sums[w];
-    if (w < wid) base += x;
-    tot += x;
-  }
-  __syncthreads();
-  *total = tot;
-  return base + inc - v;
-}
-
-// V1: bytes each encode tile will occupy
-__global__ void __launch_bounds__(kVarThreads) venc_len_kernel(const VarSeg* __restrict__ segs, const uint32_t* __restrict__ tile_seg,
-                                                               const VarJobDev* __restrict__ jobs, uint32_t* __restrict__ tile_val) {
-  __shared__ uint32_t warp_sums[kVarThreads / 32];
-  const uint32_t t = blockIdx.x;
-  const VarSeg sg = segs[tile_seg[t]];
-  const VarJobDev jb = jobs[sg.job];
-  const uint64_t e0 = (uint64_t)(t - sg.first_tile) * kVarTileElems;
-  const uint32_t cnt = (uint32_t)min((uint64_t)kVarTileElems, sg.n - e0);
-  uint64_t v[kVarPerThread];
-  load_striped(sg.src, e0, cnt, jb.elem_size, jb.is_signed, v);
-  uint32_t sum = 0;
-#pragma unroll
-  for (uint32_t i = 0; i < kVarPerThread; ++i) sum += (i * kVarThreads + threadIdx.x < cnt) ? varint_len_fast(v[i]) : 0u;
-  uint32_t total;
-  (void)block_exclusive_scan(sum, &total, warp_sums);
-  if (threadIdx.x == 0) tile_val[t] = total;
-}
-
-// per-job exclusive scan over its tiles (one CTA of kScanThreads per job): every thread sums a
-// contiguous run of tiles, one block scan over the run sums, then each thread writes its run's offsets
-constexpr uint32_t kScanThreads = 1024;
-__global__ void __launch_bounds__(kScanThreads) vscan_kernel(const VarJobDev* __restrict__ jobs, const uint32_t* __restrict__ tile_val,
-                                                             uint64_t* __restrict__ tile_off, uint64_t* __restrict__ job_total) {
-  __shared__ uint64_t warp_sums[kScanThreads / 32];
-  const VarJobDev jb = jobs[blockIdx.x];
-  const uint32_t per = (jb.n_tiles + kScanThreads - 1) / kScanThreads;
-  const uint32_t t0 = min(jb.n_tiles, threadIdx.x * per), t1 = min(jb.n_tiles, t0 + per);
-  uint64_t mine = 0;
-  for (uint32_t t = t0; t < t1; ++t) mine += tile_val[jb.first_tile + t];
-  const uint32_t lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-  uint64_t inc = mine;
-#pragma unroll
-  for (int d = 1; d < 32; d <<= 1) {
-    const uint64_t n = __shfl_up_sync(0xFFFFFFFFu, inc, d);
-    if (lane >= d) inc += n;
-  }
-  if (lane == 31) warp_sums[wid] = inc;
-  __syncthreads();
-  uint64_t base = 0, total = 0;
-  for (uint32_t w = 0; w < kScanThreads / 32; ++w) {
-    const uint64_t x = warp_sums[w];
-    if (w < wid) base += x;
-    total += x;
-  }
-  uint64_t run = base + inc - mine;
-  for (uint32_t t = t0; t < t1; ++t) {
-    tile_off[jb.first_tile + t] = run;
-    run += tile_val[jb.first_tile + t];
-  }
-  if (threadIdx.x == 0) job_total[blockIdx.x] = total;
-}
-
-// V3: emit.  Elements are loaded striped (coalesced), transposed through shared memory so each thread
-// owns kVarPerThread consecutive elements, scanned, written as bytes into a staging buffer whose
-// 16-byte phase matches the destination, and streamed out with 128-bit stores.
-__global__ void __launch_bounds__(kVarThreads) venc_emit_kernel(const VarSeg* __restrict__ segs, const uint32_t* __restrict__ tile_seg,
-                                                                const VarJobDev* __restrict__ jobs, const uint64_t* __restrict__ tile_off) {
-  __shared__ uint64_t vals[kVarTileElems];
-  __shared__ __align__(16) uint8_t stage[kVarTileElems * 10 + 32];
-  __shared__ uint32_t warp_sums[kVarThreads / 32];
-  const uint32_t t = blockIdx.x;
-  const VarSeg sg = segs[tile_seg[t]];
-  const VarJobDev jb = jobs[sg.job];
-  const uint64_t e0 = (uint64_t)(t - sg.first_tile) * kVarTileElems;
-  const uint32_t cnt = (uint32_t)min((uint64_t)kVarTileElems, sg.n - e0);
-  {
-    uint64_t v[kVarPerThread];
-    load_striped(sg.src, e0, cnt, jb.elem_size, jb.is_signed, v);
-#pragma unroll
-    for (uint32_t i = 0; i < kVarPerThread; ++i) vals[i * kVarThreads + threadIdx.x] = v[i];
-  }
-  __syncthreads();
-  uint64_t mine[kVarPerThread];
-  uint32_t sum = 0;
-#pragma unroll
-  for (uint32_t i = 0; i < kVarPerThread; ++i) {
-    const uint32_t idx = threadIdx.x * kVarPerThread + i;
-    mine[i] = idx < cnt ? vals[idx] : 0;
-    sum += idx < cnt ? varint_len_fast(mine[i]) : 0u;
-  }
-  uint32_t total;
-  uint32_t off = block_exclusive_scan(sum, &total, warp_sums);
-  uint8_t* g = jb.dst + tile_off[t];          // first output byte of this tile
-  const uint32_t phase = (uint32_t)((uintptr_t)g & 15);
-  off += phase;
-#pragma unroll
-  for (uint32_t i = 0; i < kVarPerThread; ++i) {
-    if (threadIdx.x * kVarPerThread + i < cnt) {
-      uint64_t v = mine[i];
-      while (v >= 0x80) { stage[off++] = (uint8_t)(v | 0x80); v >>= 7; }
-      stage[off++] = (uint8_t)v;
-    }
-  }
-  __syncthreads();
-  // stage[phase .. phase+total) -> g[0 .. total); whole 16-byte vectors where the tile owns them
-  uint8_t* gbase = g - phase;  // 16-byte aligned
-  const uint32_t lo = phase, hi = phase + total;
-  const uint32_t v_lo = (lo + 15) >> 4, v_hi = hi >> 4;
-  if (v_lo < v_hi) {
-    for (uint32_t v = v_lo + threadIdx.x; v < v_hi; v += kVarThreads) st_stream(gbase + 16 * v, reinterpret_cast<const uint4*>(stage)[v]);
-    for (uint32_t i = lo + threadIdx.x; i < v_lo * 16; i += kVarThreads) gbase[i] = stage[i];
-    for (uint32_t i = v_hi * 16 + threadIdx.x; i < hi; i += kVarThreads) gbase[i] = stage[i];
-  } else {
-    for (uint32_t i = lo + threadIdx.x; i < hi; i += kVarThreads) gbase[i] = stage[i];
-  }
-}
-
-// D1: varint terminators (bytes with the top bit clear) per decode tile
-__global__ void __launch_bounds__(kVarThreads) vdec_count_kernel(const VarSeg* __restrict__ segs, const uint32_t* __restrict__ tile_seg,
-                                                                 uint32_t* __restrict__ tile_val) {
-  __shared__ uint32_t warp_sums[kVarThreads / 32];
-  const uint32_t t = blockIdx.x;
-  const VarSeg sg = segs[tile_seg[t]];
-  const uint64_t b0 = (uint64_t)(t - sg.first_tile) * kVarTileBytes;
-  const uint64_t b1 = min(sg.n, b0 + kVarTileBytes);
-  uint32_t cnt = 0;
-  // 16 bytes per thread; aligned vector loads where the whole block lies inside the chunk
-  const uint8_t* lo = sg.src + b0;
-  const uint8_t* hi = sg.src + b1;
-  const uint8_t* abase = (const uint8_t*)((uintptr_t)lo & ~(uintptr_t)15);
-  for (const uint8_t* p = abase + 16 * threadIdx.x; p < hi; p += 16 * kVarThreads) {
-    if (p >= lo && p + 16 <= hi) {
-      uint4 v = ld_reuse(p);
-      cnt += __popc(~v.x & 0x80808080u) + __popc(~v.y & 0x80808080u) + __popc(~v.z & 0x80808080u) + __popc(~v.w & 0x80808080u);
-    } else {
-      for (int i = 0; i < 16; ++i) if (p + i >= lo && p + i < hi) cnt += !(p[i] & 0x80);
-    }
-  }
-  uint32_t total;
-  (void)block_exclusive_scan(cnt, &total, warp_sums);
-  if (threadIdx.x == 0) tile_val[t] = total;
-}
-
-__device__ __forceinline__ void store_decoded(const VarJobDev& jb, uint64_t idx, uint64_t v, int32_t* status) {
-  uint8_t* d = jb.dst;
-  switch (jb.dtype) {
-    case DT_INT64: case DT_UINT64: reinterpret_cast<uint64_t*>(d)[idx] = v; break;
-    case DT_UINT32: reinterpret_cast<uint32_t*>(d)[idx] = (uint32_t)v; break;
-    case DT_INT32: reinterpret_cast<int32_t*>(d)[idx] = (int32_t)(uint32_t)v; break;
-    case DT_INT16: { int32_t x = (int32_t)(uint32_t)v; if (x < -32768 || x > 32767) *status = B200TFS_E_RANGE; reinterpret_cast<int16_t*>(d)[idx] = (int16_t)x; break; }
-    case DT_INT8: { int32_t x = (int32_t)(uint32_t)v; if (x < -128 || x > 127) *status = B200TFS_E_RANGE; reinterpret_cast<int8_t*>(d)[idx] = (int8_t)x; break; }
-    case DT_UINT16: { int32_t x = (int32_t)(uint32_t)v; if (x < 0 || x > 65535) *status = B200TFS_E_RANGE; reinterpret_cast<uint16_t*>(d)[idx] = (uint16_t)x; break; }
-    case DT_UINT8: { int32_t x = (int32_t)(uint32_t)v; if (x < 0 || x > 255) *status = B200TFS_E_RANGE; d[idx] = (uint8_t)x; break; }
-    case DT_BOOL: d[idx] = v != 0; break;
-    case DT_HALF: case DT_BFLOAT16:
-      if (jb.flags & kVarFlagHalfAsValue) reinterpret_cast<uint16_t*>(d)[idx] = __half_as_ushort(__int2half_rn((int32_t)(uint32_t)v));
-      else reinterpret_cast<uint16_t*>(d)[idx] = (uint16_t)v;
-      break;
-    default: break;
-  }
-}
-
-// D3: decode.  The tile's bytes (plus one byte of look-behind and nine of look-ahead inside the
-// chunk) are staged in shared memory; each thread owns 16 byte positions, finds the varints that
-// START there (previous byte is a terminator), ranks them with a block scan, and decodes each.
-__global__ void __launch_bounds__(kVarThreads) vdec_emit_kernel(const VarSeg* __restrict__ segs, const uint32_t* __restrict__ tile_seg,
-                                                                const VarJobDev* __restrict__ jobs, const uint64_t* __restrict__ tile_off,
-                                                                const uint64_t* __restrict__ job_total, int32_t* __restrict__ job_status) {
-  __shared__ __align__(16) uint8_t smraw[kVarTileBytes + 48];
-  __shared__ uint32_t warp_sums[kVarThreads / 32];
-  const uint32_t t = blockIdx.x;
-  const VarSeg sg = segs[tile_seg[t]];
-  const VarJobDev jb = jobs[sg.job];
-  if (job_total[sg.job] != jb.n_elems) {  // element count != prod(shape): reshape() would raise
-    if (threadIdx.x == 0) job_status[sg.job] = B200TFS_E_SHAPE;
-    return;
-  }
-  const uint64_t b0 = (uint64_t)(t - sg.first_tile) * kVarTileBytes;
-  const uint64_t b1 = min(sg.n, b0 + kVarTileBytes);
-  const uint64_t s0 = b0 ? b0 - 1 : 0;                  // look-behind
-  const uint64_t s1 = min(sg.n, b1 + 9);                // look-ahead
-  // stage [s0, s1) in shared memory with the source's own 16-byte phase, so whole 16-byte blocks move
-  // as vectors; the ragged first/last block is copied bytewise (never reads outside the chunk)
-  const uint8_t* g0 = sg.src + s0;
-  const uint32_t phase = (uint32_t)((uintptr_t)g0 & 15);
-  const uint8_t* gbase = g0 - phase;                    // 16-byte aligned
-  const uint32_t span = phase + (uint32_t)(s1 - s0);    // bytes from gbase to the end of the staged range
-  for (uint32_t k = threadIdx.x; k * 16 < span; k += kVarThreads) {
-    const uint32_t lo = k * 16, hi = lo + 16;
-    if (lo >= phase && hi <= span) *reinterpret_cast<uint4*>(smraw + lo) = ld_stream(gbase + lo);
-    else for (uint32_t q = max(lo, phase); q < min(hi, span); ++q) smraw[q] = gbase[q];
-  }
-  const uint8_t* sm = smraw + phase;                     // sm[i - s0] == chunk byte i, as before
-  __syncthreads();
-  // Phase 1 - find the starts.  Each thread owns the 16-byte blocks k = tid (and tid + kVarThreads for the
-  // one or two blocks the phase shift adds) of the staged range: one conflict-free 128-bit shared load, then
-  // bit tricks.  A varint STARTS at byte i when byte i-1 has its top bit clear (or i is the chunk's first byte).
-  const int64_t pos0 = (int64_t)s0 - (int64_t)phase;   // chunk position of smraw[0]
-  uint32_t startm[2] = {0u, 0u};
-#pragma unroll
-  for (uint32_t r = 0; r < 2; ++r) {
-    const uint32_t lo = (threadIdx.x + r * kVarThreads) * 16;
-    if (lo < span) {
-      const uint4 w = *reinterpret_cast<const uint4*>(smraw + lo);
-      auto msb4 = [](uint32_t x) { return (((x >> 7) & 0x01010101u) * 0x01020408u) >> 24; };   // 4 top bits -> nibble
-      const uint32_t cont = msb4(w.x) | (msb4(w.y) << 4) | (msb4(w.z) << 8) | (msb4(w.w) << 12);
-      const uint32_t prev_term = (lo == 0) ? 1u : ((smraw[lo - 1] & 0x80) ? 0u : 1u);
-      uint32_t st = (((~cont) << 1) | prev_term) & 0xFFFFu;
-      // positions of this block inside the tile [b0, b1): bits [first, last)
-      const int64_t rel0 = (int64_t)b0 - (pos0 + lo), rel1 = (int64_t)b1 - (pos0 + lo);
-      const uint32_t first = (uint32_t)max((int64_t)0, min((int64_t)16, rel0)), last = (uint32_t)max((int64_t)0, min((int64_t)16, rel1));
-      const uint32_t valid = ((1u << last) - 1u) & ~((1u << first) - 1u);
-      const int64_t zero_at = -(pos0 + lo);             // bit of chunk position 0, always a start
-      if (zero_at >= 0 && zero_at < 16) st |= 1u << zero_at;
-      startm[r] = st & valid;
-    }
-  }
-  // Phase 2 - rank them in position order (second-round blocks lie after every first-round block) and
-  // compact their offsets into a list, so that phase 3 can hand out ELEMENTS, not byte blocks, to threads:
-  // balanced work and fully coalesced stores.
-  __shared__ uint16_t start_at[kVarTileBytes + 32];
-  const uint32_t n_first = __popc(startm[0]), n_second = __popc(startm[1]);
-  uint32_t first_total, second_total;
-  const uint32_t rank_first = block_exclusive_scan(n_first, &first_total, warp_sums);
-  const uint32_t rank_second = block_exclusive_scan(n_second, &second_total, warp_sums);
-#pragma unroll
-  for (uint32_t r = 0; r < 2; ++r) {
-    uint32_t starts = startm[r], at = (r == 0) ? rank_first : first_total + rank_second;
-    const uint32_t lo = (threadIdx.x + r * kVarThreads) * 16;
-    while (starts) {
-      const uint32_t i = __ffs(starts) - 1;
-      starts &= starts - 1;
-      start_at[at++] = (uint16_t)(lo + i);
-    }
-  }
-  __syncthreads();
-  // Phase 3 - element j of the tile starts at smraw[start_at[j]]; its index in the tensor is the number of
-  // terminators before it: tile_off[t] counts those before b0 (+1 when a varint straddles in from the
-  // previous tile: it precedes ours but its terminator is here).
-  const uint32_t n_here = first_total + second_total;
-  const uint64_t idx0 = tile_off[t] + ((b0 > 0 && (sm[0] & 0x80)) ? 1u : 0u);
-  const uint32_t limit = span;                            // staged bytes end here (chunk end or +9 look-ahead)
-  const bool at_chunk_end = (s1 == sg.n);
-  int32_t st_local = B200TFS_OK;
-  for (uint32_t j = threadIdx.x; j < n_here; j += kVarThreads) {
-    const uint32_t q = start_at[j];
-    uint64_t v = 0;
-    int k = 0;
-    for (; k < 10; ++k) {
-      if (q + k >= limit) { if (at_chunk_end) st_local = B200TFS_E_PARSE; break; }
-      const uint8_t bb = smraw[q + k];
-      v |= (uint64_t)(bb & 0x7F) << (7 * k);
-      if (!(bb & 0x80)) break;
-    }
-    if (k == 10) st_local = B200TFS_E_PARSE;
-    if (idx0 + j < jb.n_elems) store_decoded(jb, idx0 + j, v, &st_local);
-  }
-  if (st_local != B200TFS_OK) atomicMin(&job_status[sg.job], st_local);
-}
+#include "varint_kernels.cuh"
 
 // ------------------------------------------------------------------------------------------------
 // launchers (the only symbols codec_host.cpp sees)
@@ -1099,33 +793,25 @@ cudaError_t launch_decode_fused(const FusedParams& fp, uint32_t grid, cudaStream
   return launch_pdl(decode_fused_kernel, grid, kMoveThreads, stream, fp);
 }
 
-cudaError_t launch_venc_len(const VarSeg* segs, const uint32_t* tile_seg, const VarJobDev* jobs, uint32_t* tile_val, uint32_t n_tiles,
-                            cudaStream_t stream) {
-  if (!n_tiles) return cudaSuccess;
-  venc_len_kernel<<<n_tiles, kVarThreads, 0, stream>>>(segs, tile_seg, jobs, tile_val);
+cudaError_t launch_venc_len(const VarTables& tb, cudaStream_t stream) {
+  if (!tb.n_tiles) return cudaSuccess;
+  venc_len_kernel<<<tb.n_tiles, kVarThreads, 0, stream>>>(tb);
   return cudaGetLastError();
 }
-cudaError_t launch_vscan(const VarJobDev* jobs, const uint32_t* tile_val, uint64_t* tile_off, uint64_t* job_total, uint32_t n_jobs,
-                         cudaStream_t stream) {
-  if (!n_jobs) return cudaSuccess;
-  vscan_kernel<<<n_jobs, kScanThreads, 0, stream>>>(jobs, tile_val, tile_off, job_total);
+cudaError_t launch_venc_emit(const VarTables& tb, cudaStream_t stream) {
+  if (!tb.n_tiles) return cudaSuccess;
+  venc_emit_kernel<<<tb.n_tiles, kVarThreads, 0, stream>>>(tb);
   return cudaGetLastError();
 }
-cudaError_t launch_venc_emit(const VarSeg* segs, const uint32_t* tile_seg, const VarJobDev* jobs, const uint64_t* tile_off,
-                             uint32_t n_tiles, cudaStream_t stream) {
-  if (!n_tiles) return cudaSuccess;
-  venc_emit_kernel<<<n_tiles, kVarThreads, 0, stream>>>(segs, tile_seg, jobs, tile_off);
+cudaError_t launch_vdec_count(const VarTables& tb, cudaStream_t stream) {
+  if (!tb.n_tiles) return cudaSuccess;
+  const uint32_t per = kVarThreads / 32;   // one warp per tile
+  vdec_count_kernel<<<(tb.n_tiles + per - 1) / per, kVarThreads, 0, stream>>>(tb);
   return cudaGetLastError();
 }
-cudaError_t launch_vdec_count(const VarSeg* segs, const uint32_t* tile_seg, uint32_t* tile_val, uint32_t n_tiles, cudaStream_t stream) {
-  if (!n_tiles) return cudaSuccess;
-  vdec_count_kernel<<<n_tiles, kVarThreads, 0, stream>>>(segs, tile_seg, tile_val);
-  return cudaGetLastError();
-}
-cudaError_t launch_vdec_emit(const VarSeg* segs, const uint32_t* tile_seg, const VarJobDev* jobs, const uint64_t* tile_off,
-                             const uint64_t* job_total, int32_t* job_status, uint32_t n_tiles, cudaStream_t stream) {
-  if (!n_tiles) return cudaSuccess;
-  vdec_emit_kernel<<<n_tiles, kVarThreads, 0, stream>>>(segs, tile_seg, jobs, tile_off, job_total, job_status);
+cudaError_t launch_vdec_emit(const VarTables& tb, cudaStream_t stream) {
+  if (!tb.n_tiles) return cudaSuccess;
+  vdec_emit_kernel<<<tb.n_tiles, kVarThreads, 0, stream>>>(tb);
   return cudaGetLastError();
 }
 

@@ -21,14 +21,10 @@ cudaError_t launch_parse_tensors(const uint8_t* w, const uint64_t* rec_off, cons
 
 cudaError_t launch_decode_fused(const FusedParams& fp, uint32_t grid, cudaStream_t stream);
 uint32_t tiles_for_host(uint64_t n_out, uint32_t vpt);
-cudaError_t launch_venc_len(const VarSeg* segs, const uint32_t* tile_seg, const VarJobDev* jobs, uint32_t* tile_val, uint32_t n_tiles,
-                            cudaStream_t stream);
-cudaError_t launch_vscan(const VarJobDev* jobs, const uint32_t* tile_val, uint64_t* tile_off, uint64_t* job_total, uint32_t n_jobs,
-                         cudaStream_t stream);
-cudaError_t launch_venc_emit(const VarSeg* segs, const uint32_t* tile_seg, const VarJobDev* jobs, const uint64_t* tile_off,
-                             uint32_t n_tiles, cudaStream_t stream);
-cudaError_t launch_vdec_count(const VarSeg* segs, const uint32_t* tile_seg, uint32_t* tile_val, uint32_t n_tiles, cudaStream_t stream);
-cudaError_t launch_vdec_emit(const VarSeg* segs, const uint32_t* tile_seg, const VarJobDev* jobs, const uint64_t* tile_off,
-                             const uint64_t* job_total, int32_t* job_status, uint32_t n_tiles, cudaStream_t stream);
+// packed varints (varint_kernels.cuh): the tables and counters every kernel uses are addressed through VarTables
+cudaError_t launch_venc_len(const VarTables& tb, cudaStream_t stream);
+cudaError_t launch_venc_emit(const VarTables& tb, cudaStream_t stream);
+cudaError_t launch_vdec_count(const VarTables& tb, cudaStream_t stream);
+cudaError_t launch_vdec_emit(const VarTables& tb, cudaStream_t stream);
 
 }  // namespace b200tfs

@@ -98,7 +98,7 @@ struct FusedParams {
 constexpr uint32_t kVarThreads = 256;
 constexpr uint32_t kVarPerThread = 8;
 constexpr uint32_t kVarTileElems = kVarThreads * kVarPerThread;  // elements per encode tile
-constexpr uint32_t kVarTileBytes = kVarThreads * 16;             // wire bytes per decode tile
+constexpr uint32_t kVarTileBytes = kVarThreads * 32;             // wire bytes per decode tile; tiles are cut at 16-byte-aligned ADDRESSES
 constexpr int32_t kVarFlagHalfAsValue = 1;  // decode half_val ints as VALUES (the reference's DT_HALF quirk)
 
 struct VarSeg {       // a contiguous run of one job: the whole tensor (encode) or one wire chunk (decode)
@@ -108,15 +108,44 @@ struct VarSeg {       // a contiguous run of one job: the whole tensor (encode) 
   uint32_t first_tile;
 };
 
+constexpr uint32_t kVarGroupTiles = kVarThreads;  // tiles per counter group (one counter per thread when a CTA sums its prefix)
+
 struct VarJobDev {
-  uint8_t* dst;       // encode: first payload byte on the wire; decode: first element of the tensor
+  uint8_t* dst;        // encode: first payload byte on the wire; decode: first element of the tensor
   uint64_t n_elems;
-  int32_t dtype;      // DT_* of the tensor in memory
+  uint64_t cap;        // encode: payload bytes the header announced (never written past)
+  uint32_t* tile_val;  // [n_tiles] bytes (encode) / terminators (decode) of every tile of the job
+  uint32_t* group_sum; // [ceil(n_tiles / kVarGroupTiles)] sums of tile_val; zeroed before the counting kernel
+  unsigned long long* total;  // sum over the job; zeroed likewise
+  int32_t* status;     // decode: B200TFS_OK or the first error
+  int32_t dtype;       // DT_* of the tensor in memory
   uint32_t elem_size;
   uint32_t is_signed;
   int32_t flags;
   uint32_t first_tile;
   uint32_t n_tiles;
 };
+
+// what every varint kernel receives (by value, in the parameter space).  A single job with a single segment - one
+// big tensor, the case where the bandwidth matters - travels inline, so that no CTA starts with three dependent loads.
+struct VarTables {
+  const VarSeg* segs;
+  const uint32_t* tile_seg;
+  const VarJobDev* jobs;
+  uint32_t n_tiles;
+  uint32_t single;      // 1: seg0 / job0 below describe every tile
+  VarSeg seg0;
+  VarJobDev job0;
+};
+
+// decode tiles of a chunk [src, src + n): aligned windows of kVarTileBytes starting at src rounded down to 16
+#if defined(__CUDACC__)
+#define B2_PLAN_HD __host__ __device__ __forceinline__
+#else
+#define B2_PLAN_HD inline
+#endif
+B2_PLAN_HD uint64_t var_decode_tiles(const void* src, uint64_t n) {
+  return n ? (((uint64_t)((uintptr_t)src & 15) + n + kVarTileBytes - 1) / kVarTileBytes) : 0;
+}
 
 }  // namespace b200tfs

@@ -1,0 +1,489 @@
+// varint_kernels.cuh - packed-varint encode / decode kernels (included by kernels.cu inside
+// namespace b200tfs).  Fields: int_val / int64_val / uint32_val / uint64_val / half_val / bool_val.
+//
+//   encode:  venc_len_kernel   bytes every tile of 2048 elements will occupy -> tile_val[], and by
+//                              atomics the sums over groups of 256 tiles and the job total (which the
+//                              host needs for the length prefix: b200tfs_measure)
+//            venc_emit_kernel  each CTA derives its own output offset (group sums before its group +
+//                              tile values before it inside the group), builds every varint in
+//                              REGISTERS (7-bit groups spread with three bit-selects per 4 bytes),
+//                              appends whole 32-bit words to a shared-memory image of the output that
+//                              has the destination's 16-byte phase, and streams the image out with
+//                              128-bit stores
+//   decode:  vdec_count_kernel terminators (bytes with the top bit clear) per tile: an ALIGNED 8 KB window of
+//                              the chunk, one warp per tile, sixteen 128-bit loads in flight per lane
+//            vdec_emit_kernel  offset as above; finds the varint starts of the tile with bit tricks,
+//                              compacts them, and decodes one element per thread from a funnel-shifted
+//                              12-byte window (7-bit groups compressed with masks and shifts)
+//
+// There is no separate scan kernel: a tile's prefix is one coalesced read of <= 256 + n_tiles/256
+// counters.  Both emit kernels were instruction-bound in their first form (byte-serial loops, 1389
+// instructions per warp and tile in the encoder): profiles/r01_varint.md.
+//
+// What the reference does here: tensors.py:22 (`.item()` per element into RepeatedScalarContainer,
+// the runtime then writes one varint at a time) and tensors.py:46 (list of Python ints -> np.array).
+
+// (a & m) | (b & ~m) in ONE instruction (left to itself the compiler splits it into two masked operations)
+__device__ __forceinline__ uint32_t bitsel(uint32_t m, uint32_t a, uint32_t b) {
+  uint32_t d;
+  asm("lop3.b32 %0, %1, %2, %3, 0xE4;" : "=r"(d) : "r"(a), "r"(b), "r"(m));
+  return d;
+}
+
+// bytes of the varint of v: bits = position of the top set bit, len = ceil(bits / 7) without a division or a branch
+__device__ __forceinline__ uint32_t vlen64(uint64_t v) {
+  const uint32_t nb = 64u - (uint32_t)__clzll((long long)(v | 1ull));
+  return ((nb + 6u) * 37u) >> 8;   // (nb + 6) / 7 for nb + 6 <= 70
+}
+
+// one element of SZ bytes from GLOBAL memory (read-only path), widened to 64 bits the way the protobuf
+// runtime widens it: sign-extended for the signed dtypes
+template <uint32_t SZ, bool SG>
+__device__ __forceinline__ uint64_t ldg_elem(const uint8_t* p) {
+  if (SZ == 1) { const uint8_t t = __ldg(p); return SG ? (uint64_t)(int64_t)(int8_t)t : t; }
+  if (SZ == 2) { const uint16_t t = __ldg(reinterpret_cast<const uint16_t*>(p)); return SG ? (uint64_t)(int64_t)(int16_t)t : t; }
+  if (SZ == 4) { const uint32_t t = __ldg(reinterpret_cast<const uint32_t*>(p)); return SG ? (uint64_t)(int64_t)(int32_t)t : t; }
+  return __ldg(reinterpret_cast<const unsigned long long*>(p));
+}
+
+// kVarPerThread elements per thread, striped (element base + i*kVarThreads + tid), ALL loads issued
+// before any use; a full tile takes the branch without predicates (one base address, immediate offsets)
+template <uint32_t SZ, bool SG>
+__device__ __forceinline__ void load_striped_t(const uint8_t* src, uint64_t e0, uint32_t cnt, uint64_t (&v)[kVarPerThread]) {
+  const uint8_t* base = src + (e0 + threadIdx.x) * SZ;
+  if (cnt == kVarTileElems) {
+#pragma unroll
+    for (uint32_t i = 0; i < kVarPerThread; ++i) v[i] = ldg_elem<SZ, SG>(base + (uint64_t)i * kVarThreads * SZ);
+  } else {
+#pragma unroll
+    for (uint32_t i = 0; i < kVarPerThread; ++i)
+      v[i] = (i * kVarThreads + threadIdx.x < cnt) ? ldg_elem<SZ, SG>(base + (uint64_t)i * kVarThreads * SZ) : 0ull;
+  }
+}
+__device__ __forceinline__ void load_striped(const uint8_t* src, uint64_t e0, uint32_t cnt, uint32_t size, uint32_t is_signed,
+                                             uint64_t (&v)[kVarPerThread]) {
+  switch (size * 2 + (is_signed ? 1 : 0)) {
+    case 2: load_striped_t<1, false>(src, e0, cnt, v); break;
+    case 3: load_striped_t<1, true>(src, e0, cnt, v); break;
+    case 4: load_striped_t<2, false>(src, e0, cnt, v); break;
+    case 5: load_striped_t<2, true>(src, e0, cnt, v); break;
+    case 8: load_striped_t<4, false>(src, e0, cnt, v); break;
+    case 9: load_striped_t<4, true>(src, e0, cnt, v); break;
+    default: load_striped_t<8, false>(src, e0, cnt, v); break;
+  }
+}
+
+// segment and job of tile t: from the parameter space when there is one of each, else two table look-ups
+__device__ __forceinline__ void fetch_tile(const VarTables& tb, uint32_t t, VarSeg& sg, VarJobDev& jb) {
+  if (tb.single) { sg = tb.seg0; jb = tb.job0; }
+  else { sg = tb.segs[tb.tile_seg[t]]; jb = tb.jobs[sg.job]; }
+}
+
+struct VarShared {            // reduction scratch of one CTA
+  uint32_t w32[kVarThreads / 32];
+  uint64_t w64[kVarThreads / 32];
+};
+
+// this thread's share of the tile's prefix: counters of the groups before the tile's group, and of
+// the tiles before it inside the group (kVarGroupTiles == kVarThreads: one counter per thread)
+__device__ __forceinline__ uint64_t prefix_share(const VarJobDev& jb, uint32_t t_rel) {
+  const uint32_t g = t_rel / kVarGroupTiles;
+  uint64_t s = 0;
+  for (uint32_t i = threadIdx.x; i < g; i += kVarThreads) s += jb.group_sum[i];
+  const uint32_t k = g * kVarGroupTiles + threadIdx.x;
+  if (k < t_rel) s += jb.tile_val[k];
+  return s;
+}
+
+// block-wide exclusive scan of `v` (one value per thread) fused with a block-wide sum of `extra`
+__device__ __forceinline__ uint32_t block_scan_sum(uint32_t v, uint32_t* total, uint64_t extra, uint64_t* extra_total, VarShared& sh) {
+  const uint32_t lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  uint32_t inc = v;
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    const uint32_t n = __shfl_up_sync(0xFFFFFFFFu, inc, d);
+    if (lane >= d) inc += n;
+  }
+#pragma unroll
+  for (int d = 16; d; d >>= 1) extra += __shfl_xor_sync(0xFFFFFFFFu, extra, d);
+  if (lane == 31) sh.w32[wid] = inc;
+  if (lane == 0) sh.w64[wid] = extra;
+  __syncthreads();
+  uint32_t base = 0, tot = 0;
+  uint64_t etot = 0;
+#pragma unroll
+  for (uint32_t w = 0; w < kVarThreads / 32; ++w) {
+    const uint32_t x = sh.w32[w];
+    if (w < wid) base += x;
+    tot += x;
+    etot += sh.w64[w];
+  }
+  __syncthreads();
+  *total = tot;
+  *extra_total = etot;
+  return base + inc - v;
+}
+
+// block-wide sum; valid in thread 0 only (one barrier)
+__device__ __forceinline__ uint32_t block_sum_t0(uint32_t v, VarShared& sh) {
+#pragma unroll
+  for (int d = 16; d; d >>= 1) v += __shfl_xor_sync(0xFFFFFFFFu, v, d);
+  if ((threadIdx.x & 31) == 0) sh.w32[threadIdx.x >> 5] = v;
+  __syncthreads();
+  uint32_t tot = 0;
+  if (threadIdx.x == 0) {
+#pragma unroll
+    for (uint32_t w = 0; w < kVarThreads / 32; ++w) tot += sh.w32[w];
+  }
+  return tot;
+}
+
+__device__ __forceinline__ void publish_tile(const VarJobDev& jb, uint32_t t_rel, uint32_t total) {
+  jb.tile_val[t_rel] = total;
+  atomicAdd(&jb.group_sum[t_rel / kVarGroupTiles], total);
+  atomicAdd(jb.total, (unsigned long long)total);
+}
+
+// E1: bytes each encode tile will occupy
+__global__ void __launch_bounds__(kVarThreads) venc_len_kernel(const __grid_constant__ VarTables tb) {
+  __shared__ VarShared sh;
+  const uint32_t t = blockIdx.x;
+  VarSeg sg;
+  VarJobDev jb;
+  fetch_tile(tb, t, sg, jb);
+  const uint64_t e0 = (uint64_t)(t - sg.first_tile) * kVarTileElems;
+  const uint32_t cnt = (uint32_t)min((uint64_t)kVarTileElems, sg.n - e0);
+  uint64_t v[kVarPerThread];
+  load_striped(sg.src, e0, cnt, jb.elem_size, jb.is_signed, v);
+  uint32_t sum = 0;
+#pragma unroll
+  for (uint32_t i = 0; i < kVarPerThread; ++i) sum += vlen64(v[i]) & ((i * kVarThreads + threadIdx.x < cnt) ? ~0u : 0u);
+  const uint32_t total = block_sum_t0(sum, sh);
+  if (threadIdx.x == 0) publish_tile(jb, t - jb.first_tile, total);
+}
+
+// 28 value bits -> four 7-bit groups, one per byte; bit 7 of every byte is left dirty for the caller's
+// final select (which merges the continuation bits in the same instruction)
+__device__ __forceinline__ uint32_t spread28(uint32_t x) {
+  const uint32_t t = bitsel(0xFFFF0000u, x << 2, x);   // bits 14..27 -> 16..29
+  return bitsel(0xFF00FF00u, t << 1, t);               // bits 7..13 -> 8..14, 23..29 -> 24..30
+}
+
+// E2: emit.  Elements are loaded striped (coalesced) and transposed through shared memory (16-byte chunks
+// XOR-swizzled by row, so both sides are conflict-free) so that each thread owns kVarPerThread
+// consecutive elements; the staging image reuses the same shared memory.
+__global__ void __launch_bounds__(kVarThreads, 5) venc_emit_kernel(const __grid_constant__ VarTables tb) {
+  __shared__ __align__(16) uint8_t smem[kVarTileElems * 10 + 48];
+  __shared__ VarShared sh;
+  uint64_t* vals = reinterpret_cast<uint64_t*>(smem);
+  const uint32_t t = blockIdx.x;
+  VarSeg sg;
+  VarJobDev jb;
+  fetch_tile(tb, t, sg, jb);
+  const uint32_t t_rel = t - jb.first_tile;
+  const uint64_t e0 = (uint64_t)(t - sg.first_tile) * kVarTileElems;
+  const uint32_t cnt = (uint32_t)min((uint64_t)kVarTileElems, sg.n - e0);
+  const uint64_t share = prefix_share(jb, t_rel);
+  {
+    uint64_t v[kVarPerThread];
+    load_striped(sg.src, e0, cnt, jb.elem_size, jb.is_signed, v);
+#pragma unroll
+    for (uint32_t i = 0; i < kVarPerThread; ++i) {
+      const uint32_t k = i * kVarThreads + threadIdx.x, r = k >> 3, c = k & 7;
+      vals[r * 8 + ((((c >> 1) ^ (r >> 1)) & 3) << 1) + (c & 1)] = v[i];
+    }
+  }
+  __syncthreads();
+  uint64_t mine[kVarPerThread];
+  uint32_t lens = 0, sum = 0;                    // eight lengths, one nibble each
+  {
+    const uint32_t r = threadIdx.x;
+#pragma unroll
+    for (uint32_t j = 0; j < kVarPerThread / 2; ++j) {
+      const uint4 q = *reinterpret_cast<const uint4*>(smem + r * 64 + (((j ^ (r >> 1)) & 3) << 4));
+      mine[2 * j] = (uint64_t)q.x | ((uint64_t)q.y << 32);
+      mine[2 * j + 1] = (uint64_t)q.z | ((uint64_t)q.w << 32);
+    }
+#pragma unroll
+    for (uint32_t i = 0; i < kVarPerThread; ++i) lens |= vlen64(mine[i]) << (4 * i);
+    // elements past the end of the tensor (last tile only) take no room
+    const uint32_t have = min(kVarPerThread, cnt - min(cnt, r * kVarPerThread));
+    lens &= __funnelshift_lc(0xFFFFFFFFu, 0u, 4u * have);
+    const uint32_t pairs = (lens & 0x0F0F0F0Fu) + ((lens >> 4) & 0x0F0F0F0Fu);
+    sum = (pairs * 0x01010101u) >> 24;
+  }
+  uint32_t total;
+  uint64_t base;
+  uint32_t off = block_scan_sum(sum, &total, share, &base, sh);   // every thread has read `vals` before the first barrier inside
+  uint8_t* g = jb.dst + base;                  // first output byte of this tile
+  const uint32_t phase = (uint32_t)((uintptr_t)g & 15);
+  off += phase;
+  // ---- build the varints in registers, append 32-bit words ----
+  const uint32_t f0 = off & 3;
+  const uint32_t sbase = (uint32_t)__cvta_generic_to_shared(smem);
+  const uint32_t sa0 = sbase + (off & ~3u);      // shared-window address of the word being filled
+  uint32_t sa = sa0, f = f0, acc = 0;
+#pragma unroll
+  for (uint32_t i = 0; i < kVarPerThread; ++i) {
+    const uint32_t lo = (uint32_t)mine[i], hi = (uint32_t)(mine[i] >> 32);
+    const uint32_t L = (lens >> (4 * i)) & 15u;
+    // continuation bits go into the first L-1 bytes: the low 8(L-1) bits of a mask, by a clamped funnel shift.  (An
+    // absent element - only at the end of the last tile - has L = 0: what it ORs into `acc` lies above byte f and is
+    // never stored, because no element follows it.)
+    const uint32_t s = 8u * L - 8u;
+    const uint32_t w0 = bitsel(0x7F7F7F7Fu, spread28(lo), __funnelshift_lc(0xFFFFFFFFu, 0u, s));
+    uint32_t w1 = 0, w2 = 0;
+    if (L > 4) {
+      w1 = bitsel(0x7F7F7F7Fu, spread28(__funnelshift_r(lo, hi, 28)), __funnelshift_lc(0xFFFFFFFFu, 0u, s - 32u));
+      const uint32_t x2 = hi >> 24;          // bits 56..63: byte 8 carries seven of them, byte 9 the last one ...
+      w2 = x2 | ((x2 & 0x80u) << 1);         // ... and when that one is set, byte 8 continues: the same bit
+    }
+    const uint32_t shb = f * 8u;
+    const uint32_t o0 = acc | (w0 << shb);
+    const uint32_t o1 = __funnelshift_l(w0, w1, shb);
+    const uint32_t o2 = __funnelshift_l(w1, w2, shb);
+    const uint32_t o3 = __funnelshift_l(w2, 0u, shb);
+    const uint32_t n = f + L;
+    // store the words this element completed; keep the incomplete one
+    asm volatile(
+        "{\n\t.reg .pred p0, p1, p2;\n\t.reg .b32 t;\n\t"
+        "setp.ge.u32 p0, %1, 4;\n\tsetp.ge.u32 p1, %1, 8;\n\tsetp.ge.u32 p2, %1, 12;\n\t"
+        "@p0 st.shared.u32 [%2], %3;\n\t@p1 st.shared.u32 [%2+4], %4;\n\t@p2 st.shared.u32 [%2+8], %5;\n\t"
+        "selp.b32 t, %4, %3, p0;\n\tselp.b32 t, %5, t, p1;\n\tselp.b32 %0, %6, t, p2;\n\t}"
+        : "=r"(acc) : "r"(n), "r"(sa), "r"(o0), "r"(o1), "r"(o2), "r"(o3) : "memory");
+    sa += n & ~3u;
+    f = n & 3;
+  }
+  __syncthreads();
+  // the word this thread did not complete: its bytes only (the thread that completes the word stored zeros there)
+  {
+    const uint32_t first = (sa == sa0) ? f0 : 0u;
+    uint8_t* tail = smem + (sa - sbase);
+#pragma unroll
+    for (uint32_t b = 0; b < 3; ++b)
+      if (b >= first && b < f) tail[b] = (uint8_t)(acc >> (8 * b));
+  }
+  __syncthreads();
+  // smem[phase .. phase+total) -> g[0 .. total); whole 16-byte vectors where the tile owns them.  Never past the
+  // payload the header announced (the data changed between b200tfs_measure and the encode: undefined bytes, no overrun)
+  if (base >= jb.cap) return;
+  total = (uint32_t)min((uint64_t)total, jb.cap - base);
+  uint8_t* gbase = g - phase;  // 16-byte aligned
+  const uint32_t lo = phase, hi = phase + total;
+  const uint32_t v_lo = (lo + 15) >> 4, v_hi = hi >> 4;
+  if (v_lo < v_hi) {
+    for (uint32_t v = v_lo + threadIdx.x; v < v_hi; v += kVarThreads) st_stream(gbase + 16 * v, reinterpret_cast<const uint4*>(smem)[v]);
+    for (uint32_t i = lo + threadIdx.x; i < v_lo * 16; i += kVarThreads) gbase[i] = smem[i];
+    for (uint32_t i = v_hi * 16 + threadIdx.x; i < hi; i += kVarThreads) gbase[i] = smem[i];
+  } else {
+    for (uint32_t i = lo + threadIdx.x; i < hi; i += kVarThreads) gbase[i] = smem[i];
+  }
+}
+
+// D1: varint terminators (bytes with the top bit clear) per decode tile.  One WARP per tile: sixteen
+// aligned 128-bit loads per lane in two batches of eight, a warp reduction, no block barrier.
+__global__ void __launch_bounds__(kVarThreads, 5) vdec_count_kernel(const __grid_constant__ VarTables tb) {
+  const uint32_t t = blockIdx.x * (kVarThreads / 32) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (t >= tb.n_tiles) return;
+  VarSeg sg;
+  VarJobDev jb;
+  fetch_tile(tb, t, sg, jb);
+  const uint8_t* lo = sg.src;
+  const uint8_t* hi = sg.src + sg.n;
+  const uint8_t* G = reinterpret_cast<const uint8_t*>((uintptr_t)sg.src & ~(uintptr_t)15) + (uint64_t)(t - sg.first_tile) * kVarTileBytes;
+  uint32_t cnt = 0;
+  constexpr uint32_t kBlocks = kVarTileBytes / 16, kBatch = 8;
+  if (G >= lo && G + kVarTileBytes <= hi) {       // interior tile: no edge handling at all
+#pragma unroll
+    for (uint32_t b = 0; b < kBlocks / 32; b += kBatch) {
+      uint4 v[kBatch];
+#pragma unroll
+      for (uint32_t i = 0; i < kBatch; ++i) v[i] = ld_reuse(G + 16 * (lane + 32 * (b + i)));
+#pragma unroll
+      for (uint32_t i = 0; i < kBatch; ++i)
+        cnt += __popc(~v[i].x & 0x80808080u) + __popc(~v[i].y & 0x80808080u) + __popc(~v[i].z & 0x80808080u) + __popc(~v[i].w & 0x80808080u);
+    }
+  } else {
+    for (uint32_t k = lane; k < kBlocks; k += 32) {
+      const uint8_t* p = G + 16 * k;
+      if (p >= lo && p + 16 <= hi) {
+        const uint4 v = ld_reuse(p);
+        cnt += __popc(~v.x & 0x80808080u) + __popc(~v.y & 0x80808080u) + __popc(~v.z & 0x80808080u) + __popc(~v.w & 0x80808080u);
+      } else if (p + 16 > lo && p < hi) {
+        for (int i = 0; i < 16; ++i) if (p + i >= lo && p + i < hi) cnt += !(p[i] & 0x80);
+      }
+    }
+  }
+#pragma unroll
+  for (int d = 16; d; d >>= 1) cnt += __shfl_xor_sync(0xFFFFFFFFu, cnt, d);
+  if (lane == 0) publish_tile(jb, t - jb.first_tile, cnt);
+}
+
+// how a decoded value is stored
+enum VarStore : int { VS_U64, VS_U32, VS_I16, VS_I8, VS_U16, VS_U8, VS_BOOL, VS_HALF_BITS, VS_HALF_VALUE };
+template <int K>
+__device__ __forceinline__ void store_decoded(uint8_t* d, uint64_t idx, uint64_t v, int32_t* status) {
+  const int32_t x = (int32_t)(uint32_t)v;
+  if (K == VS_U64) reinterpret_cast<uint64_t*>(d)[idx] = v;
+  else if (K == VS_U32) reinterpret_cast<uint32_t*>(d)[idx] = (uint32_t)v;
+  else if (K == VS_I16) { if (x < -32768 || x > 32767) *status = B200TFS_E_RANGE; reinterpret_cast<int16_t*>(d)[idx] = (int16_t)x; }
+  else if (K == VS_I8) { if (x < -128 || x > 127) *status = B200TFS_E_RANGE; reinterpret_cast<int8_t*>(d)[idx] = (int8_t)x; }
+  else if (K == VS_U16) { if (x < 0 || x > 65535) *status = B200TFS_E_RANGE; reinterpret_cast<uint16_t*>(d)[idx] = (uint16_t)x; }
+  else if (K == VS_U8) { if (x < 0 || x > 255) *status = B200TFS_E_RANGE; d[idx] = (uint8_t)x; }
+  else if (K == VS_BOOL) d[idx] = v != 0;
+  else if (K == VS_HALF_BITS) reinterpret_cast<uint16_t*>(d)[idx] = (uint16_t)v;
+  else reinterpret_cast<uint16_t*>(d)[idx] = __half_as_ushort(__int2half_rn(x));
+}
+
+// four bytes of 7-bit groups -> 28 contiguous bits (continuation bits dropped)
+__device__ __forceinline__ uint32_t compress28(uint32_t y) {
+  y &= 0x7F7F7F7Fu;
+  y = (y & 0x007F007Fu) | ((y & 0x7F007F00u) >> 1);
+  return (y & 0x00003FFFu) | ((y >> 2) & 0x0FFFC000u);
+}
+
+// low `bytes` bytes of a word kept, the rest cleared (bytes >= 4: everything)
+__device__ __forceinline__ uint32_t keep_bytes(uint32_t bytes) { return __funnelshift_lc(0xFFFFFFFFu, 0u, 8u * bytes); }
+
+// element j of the tile starts at smraw[start_at[j]]: 12-byte window by funnel shifts, terminator by ffs.
+// Two shapes, chosen per warp: every lane's varint ends inside its first four bytes (values below 2^28:
+// indices, token ids, small counts), or the general branch-free form.
+template <int K>
+__device__ __forceinline__ int32_t decode_elems(const uint8_t* smraw, const uint16_t* start_at, uint32_t n_here, uint32_t limit,
+                                                bool at_chunk_end, uint8_t* dst, uint64_t idx0, uint64_t n_elems) {
+  int32_t st = B200TFS_OK;
+  for (uint32_t j0 = 0; j0 < n_here; j0 += kVarThreads) {      // trip count uniform across the CTA's warps that still have work
+    const uint32_t j = j0 + threadIdx.x;
+    const bool live = j < n_here;
+    const uint32_t q = live ? start_at[j] : 16u;
+    const uint32_t* wp = reinterpret_cast<const uint32_t*>(smraw + (q & ~3u));
+    const uint32_t shb = (q & 3u) * 8u;
+    const uint32_t a0 = wp[0], a1 = wp[1];
+    const uint32_t b0 = __funnelshift_r(a0, a1, shb);
+    const uint32_t t0 = ~b0 & 0x80808080u;
+    uint32_t L, v_lo, v_hi = 0;
+    if (__all_sync(0xFFFFFFFFu, !live || t0 != 0u)) {
+      L = (uint32_t)__ffs((int)t0) >> 3;
+      v_lo = compress28(b0 & keep_bytes(L));
+    } else {
+      const uint32_t a2 = wp[2], a3 = wp[3];
+      const uint32_t b1 = __funnelshift_r(a1, a2, shb), b2 = __funnelshift_r(a2, a3, shb);
+      const uint32_t t1 = ~b1 & 0x80808080u, t2 = ~b2 & 0x00008080u;
+      const uint32_t f0 = (uint32_t)__ffs((int)t0) >> 3, f1 = 4u + ((uint32_t)__ffs((int)t1) >> 3), f2 = 8u + ((uint32_t)__ffs((int)t2) >> 3);
+      L = t0 ? f0 : t1 ? f1 : t2 ? f2 : 11u;                   // 11: more than ten bytes, malformed
+      const uint32_t c0 = compress28(b0 & keep_bytes(L));
+      const uint32_t c1 = compress28(b1 & keep_bytes(max(L, 4u) - 4u));
+      const uint32_t c2 = compress28(b2 & keep_bytes(max(L, 8u) - 8u));
+      v_lo = c0 | (c1 << 28);
+      v_hi = (c1 >> 4) | (c2 << 24);
+    }
+    if (live) {
+      if (L > 10u || q + L > limit) {                // runs past the staged bytes: only possible at the end of the chunk
+        if (L > 10u || at_chunk_end) st = B200TFS_E_PARSE;
+        v_lo = v_hi = 0;
+      }
+      if (idx0 + j < n_elems) store_decoded<K>(dst, idx0 + j, (uint64_t)v_lo | ((uint64_t)v_hi << 32), &st);
+    }
+  }
+  return st;
+}
+
+// D2: decode.  The tile (an aligned window of the chunk) is staged in shared memory between one 16-byte block of
+// look-behind and one of look-ahead, bytes outside the chunk zeroed; each thread owns two 16-byte blocks and
+// finds the varints that START there (previous byte is a terminator - the zero before the chunk's first byte
+// is one); a block scan ranks them; they are compacted into a list so that the decode step hands out
+// ELEMENTS, not byte blocks, to threads: balanced work and coalesced stores.
+__global__ void __launch_bounds__(kVarThreads) vdec_emit_kernel(const __grid_constant__ VarTables tb) {
+  constexpr uint32_t kBlocks = kVarTileBytes / 16;             // 512: two per thread
+  __shared__ __align__(16) uint8_t smraw[16 + kVarTileBytes + 16];
+  __shared__ uint16_t start_at[kVarTileBytes];
+  __shared__ VarShared sh;
+  const uint32_t t = blockIdx.x;
+  VarSeg sg;
+  VarJobDev jb;
+  fetch_tile(tb, t, sg, jb);
+  if (*jb.total != jb.n_elems) {  // element count != prod(shape): reshape() would raise
+    if (threadIdx.x == 0) *jb.status = B200TFS_E_SHAPE;
+    return;
+  }
+  const uint64_t share = prefix_share(jb, t - jb.first_tile);
+  const uint8_t* lo = sg.src;
+  const uint8_t* hi = sg.src + sg.n;
+  const uint8_t* G = reinterpret_cast<const uint8_t*>((uintptr_t)sg.src & ~(uintptr_t)15) + (uint64_t)(t - sg.first_tile) * kVarTileBytes;
+  // stage blocks -1 .. kBlocks (smraw[16 * (k + 1)] <- G[16 * k]); whole blocks inside the chunk move as vectors
+  auto stage = [&](int32_t k) {
+    const uint8_t* p = G + 16 * (int64_t)k;
+    uint8_t* s = smraw + 16 * (k + 1);
+    if (p >= lo && p + 16 <= hi) *reinterpret_cast<uint4*>(s) = ld_stream(p);
+    else {
+      uint4 z = make_uint4(0u, 0u, 0u, 0u);
+      *reinterpret_cast<uint4*>(s) = z;
+      if (p + 16 > lo && p < hi)
+        for (int i = 0; i < 16; ++i) if (p + i >= lo && p + i < hi) s[i] = p[i];
+    }
+  };
+  stage((int32_t)threadIdx.x);
+  stage((int32_t)(threadIdx.x + kVarThreads));
+  if (threadIdx.x < 2) stage(threadIdx.x == 0 ? -1 : (int32_t)kBlocks);
+  __syncthreads();
+  // Phase 1 - find the starts: one conflict-free 128-bit shared load per block, then bit tricks.  A varint
+  // STARTS at byte i when byte i-1 has its top bit clear.
+  uint32_t startm[2];
+#pragma unroll
+  for (uint32_t r = 0; r < 2; ++r) {
+    const uint32_t k = threadIdx.x + r * kVarThreads;
+    const uint8_t* s = smraw + 16 * (k + 1);
+    const uint4 w = *reinterpret_cast<const uint4*>(s);
+    auto msb4 = [](uint32_t x) { return (((x >> 7) & 0x01010101u) * 0x01020408u) >> 24; };   // 4 top bits -> nibble
+    const uint32_t cont = msb4(w.x) | (msb4(w.y) << 4) | (msb4(w.z) << 8) | (msb4(w.w) << 12);
+    const uint32_t prev_term = (s[-1] & 0x80) ? 0u : 1u;
+    uint32_t st = (((~cont) << 1) | prev_term) & 0xFFFFu;
+    const uint8_t* p = G + 16 * k;
+    if (!(p >= lo && p + 16 <= hi)) {              // block straddles an end of the chunk: positions inside it only
+      const int64_t first = max((int64_t)0, min((int64_t)16, (int64_t)(lo - p))), last = max((int64_t)0, min((int64_t)16, (int64_t)(hi - p)));
+      st &= ((1u << last) - 1u) & ~((1u << first) - 1u);
+    }
+    startm[r] = st;
+  }
+  // Phase 2 - rank them in position order (second-round blocks lie after every first-round block): one scan
+  // over both counts packed into a word, fused with the reduction that yields the tile's element offset
+  const uint32_t packed = __popc(startm[0]) | (__popc(startm[1]) << 16);
+  uint32_t packed_total;
+  uint64_t before;
+  const uint32_t rank = block_scan_sum(packed, &packed_total, share, &before, sh);
+  const uint32_t first_total = packed_total & 0xFFFFu, n_here = first_total + (packed_total >> 16);
+#pragma unroll
+  for (uint32_t r = 0; r < 2; ++r) {
+    uint32_t starts = startm[r], at = (r == 0) ? (rank & 0xFFFFu) : first_total + (rank >> 16);
+    const uint32_t at0 = 16 * (threadIdx.x + r * kVarThreads + 1);
+    while (starts) {
+      const uint32_t i = __ffs(starts) - 1;
+      starts &= starts - 1;
+      start_at[at++] = (uint16_t)(at0 + i);
+    }
+  }
+  __syncthreads();
+  // Phase 3 - the index of an element in the tensor is the number of terminators before it: `before`
+  // counts those ahead of the tile (+1 when a varint straddles in from the previous tile: it precedes ours but
+  // its terminator is here).
+  const uint64_t idx0 = before + (smraw[15] >> 7);
+  const int64_t to_end = hi - (G - 16);                  // staged offset of the chunk's end
+  const bool at_end = to_end <= (int64_t)sizeof(smraw);
+  const uint32_t limit = at_end ? (uint32_t)to_end : (uint32_t)sizeof(smraw);
+  int32_t st_local;
+  switch (jb.dtype) {
+    case DT_INT64: case DT_UINT64: st_local = decode_elems<VS_U64>(smraw, start_at, n_here, limit, at_end, jb.dst, idx0, jb.n_elems); break;
+    case DT_INT32: case DT_UINT32: st_local = decode_elems<VS_U32>(smraw, start_at, n_here, limit, at_end, jb.dst, idx0, jb.n_elems); break;
+    case DT_INT16: st_local = decode_elems<VS_I16>(smraw, start_at, n_here, limit, at_end, jb.dst, idx0, jb.n_elems); break;
+    case DT_INT8: st_local = decode_elems<VS_I8>(smraw, start_at, n_here, limit, at_end, jb.dst, idx0, jb.n_elems); break;
+    case DT_UINT16: st_local = decode_elems<VS_U16>(smraw, start_at, n_here, limit, at_end, jb.dst, idx0, jb.n_elems); break;
+    case DT_UINT8: st_local = decode_elems<VS_U8>(smraw, start_at, n_here, limit, at_end, jb.dst, idx0, jb.n_elems); break;
+    case DT_BOOL: st_local = decode_elems<VS_BOOL>(smraw, start_at, n_here, limit, at_end, jb.dst, idx0, jb.n_elems); break;
+    case DT_HALF: case DT_BFLOAT16:
+      st_local = (jb.flags & kVarFlagHalfAsValue) ? decode_elems<VS_HALF_VALUE>(smraw, start_at, n_here, limit, at_end, jb.dst, idx0, jb.n_elems)
+                                                  : decode_elems<VS_HALF_BITS>(smraw, start_at, n_here, limit, at_end, jb.dst, idx0, jb.n_elems);
+      break;
+    default: st_local = B200TFS_OK; break;
+  }
+  if (st_local != B200TFS_OK) atomicMin(jb.status, st_local);
+}

@@ -145,7 +145,7 @@ def test_alignment_sweep_against_oracle(codec):
 
 
 def test_varint_multi_tile_against_oracle(codec):
-    """Packed-varint dtypes across many encode tiles (2048 elements) and decode tiles (4096 wire bytes):
+    """Packed-varint dtypes across many encode tiles (2048 elements) and decode tiles (8 KB windows of wire):
     varints straddling tile edges, 10-byte negatives, every dtype of the int_val / int64_val / uint32_val /
     uint64_val / half_val / bool_val family, odd element counts."""
     import ml_dtypes
@@ -175,6 +175,69 @@ def test_varint_multi_tile_against_oracle(codec):
     assert bad != good
     with pytest.raises(ValueError):
         codec.decode_tensor_protos([bad])
+
+
+def _varint(v):
+    out = bytearray()
+    v &= (1 << 64) - 1
+    while v >= 0x80:
+        out.append((v & 0x7F) | 0x80)
+        v >>= 7
+    out.append(v)
+    return bytes(out)
+
+
+def test_varint_tile_geometry_chunks_and_malformed(codec):
+    """Decode tiles are aligned 8 KB windows of each chunk: sweep the chunk's start alignment (key lengths shift it byte by
+    byte) with wire lengths around one and two tiles, split one tensor's values over several packed occurrences (chunks)
+    with varints straddling tile edges, run many small tensors as one multi-job launch, and feed the malformed tails the
+    protobuf runtime rejects (a last varint that never terminates, an eleven-byte varint)."""
+    from oracle import wire_oracle
+
+    rng = np.random.default_rng(17)
+    # (a) alignment sweep, ~1 and ~2 tiles of wire, ten-byte negatives sprinkled in so varints straddle every edge
+    for klen in range(0, 18):
+        n = (1500, 2731, 2740, 5461, 5470, 9000)[klen % 6]
+        x = rng.integers(0, 2 ** 21, size=n, dtype=np.int64)
+        x[:: 5 + klen] = -x[:: 5 + klen] - 1
+        resp = wire_oracle.build_predict_response([("k" * klen, x), ("z", x[::-1].astype(np.int32))])
+        got = codec.decode_predict_response(resp, strict=True)[0]
+        ref = wire_oracle.decode_predict_response(resp)
+        for k in ref:
+            assert got[k].dtype == ref[k].dtype and got[k].tobytes() == ref[k].tobytes(), (klen, k)
+    # (b) one tensor, values spread over 5 packed int64_val occurrences of ragged lengths (field 10, wire type 2)
+    vals = rng.integers(-2 ** 40, 2 ** 40, size=30011, dtype=np.int64)
+    cuts = [0, 1, 4099, 4100, 20000, 30011]
+    body = b"\x08\x09" + b"\x12\x06\x12\x04\x08" + _varint(30011)      # dtype DT_INT64, shape [30011] (dim submessage of 4 bytes)
+    assert len(_varint(30011)) == 3
+    for a, b in zip(cuts[:-1], cuts[1:]):
+        chunk = b"".join(_varint(int(v)) for v in vals[a:b])
+        body += b"\x52" + _varint(len(chunk)) + chunk
+    ref = wire_oracle.decode_tensor_proto(body)
+    assert ref.tobytes() == vals.tobytes()
+    got = codec.decode_tensor_protos([body], strict=True)[0]
+    assert got.dtype == np.int64 and got.tobytes() == vals.tobytes()
+    # (c) many small tensors in one call: the multi-job tables (not the inline single-job path), both directions
+    smalls = [rng.integers(-5, 70000, size=int(rng.integers(1, 700)), dtype=np.int64).astype(dt)
+              for dt in (np.int64, np.int32, np.uint16, np.int8) for _ in range(13)]
+    smalls = [np.abs(a) if a.dtype.kind == "u" else a for a in smalls]
+    wires = codec.encode_tensor_protos(smalls)
+    for a, w in zip(smalls, wires):
+        assert w == wire_oracle.encode_tensor_proto(a)
+    backs = codec.decode_tensor_protos(wires, strict=True)
+    for a, b in zip(smalls, backs):
+        assert b.dtype == a.dtype and b.tobytes() == a.tobytes()
+    # (d) malformed tails
+    good = wire_oracle.encode_tensor_proto(np.arange(3000, 3005, dtype=np.int64))
+    assert good.endswith(_varint(3004))
+    never_ends = good[:-1] + bytes([good[-1] | 0x80])                      # last byte keeps the continuation bit
+    with pytest.raises(DecodeError):
+        codec.decode_tensor_protos([never_ends])
+    eleven = b"\x08\x09\x12\x04\x12\x02\x08\x01" + b"\x52\x0b" + b"\xff" * 10 + b"\x01"
+    with pytest.raises(DecodeError):
+        codec.decode_tensor_protos([eleven])
+    ten = b"\x08\x09\x12\x04\x12\x02\x08\x01" + b"\x52\x0a" + b"\xff" * 9 + b"\x01"
+    assert codec.decode_tensor_protos([ten], strict=True)[0].tolist() == [-1] == wire_oracle.decode_tensor_proto(ten).tolist()
 
 
 def test_modes_tensor_content_and_keep_snan(codec):
