@@ -17,8 +17,11 @@
 //                              12-byte window (7-bit groups compressed with masks and shifts)
 //
 // There is no separate scan kernel: a tile's prefix is one coalesced read of <= 256 + n_tiles/256
-// counters.  Both emit kernels were instruction-bound in their first form (byte-serial loops, 1389
-// instructions per warp and tile in the encoder): profiles/r01_varint.md.
+// counters.  Two single-pass decoders were measured and dropped (16M int64, B200): a decoupled look-back over
+// per-tile states (emit 113 -> 135 us: ~100 tiles start per microsecond, a 32-wide look-back cannot keep up
+// and seven warps idle at the barrier behind it) and a ticketed "wait until every predecessor has published,
+// then one parallel read" (205 us: the wait is the slowest of 255 neighbours).  The counting pass costs 27 us
+// and leaves the wire in L2 for the decoder.  History and numbers: profiles/r01_varint.md.
 //
 // What the reference does here: tensors.py:22 (`.item()` per element into RepeatedScalarContainer,
 // the runtime then writes one varint at a time) and tensors.py:46 (list of Python ints -> np.array).
@@ -342,48 +345,44 @@ __device__ __forceinline__ uint32_t compress28(uint32_t y) {
   return (y & 0x00003FFFu) | ((y >> 2) & 0x0FFFC000u);
 }
 
-// low `bytes` bytes of a word kept, the rest cleared (bytes >= 4: everything)
-__device__ __forceinline__ uint32_t keep_bytes(uint32_t bytes) { return __funnelshift_lc(0xFFFFFFFFu, 0u, 8u * bytes); }
+// bytes up to and including the first terminator of `t` (terminator flags at bit 7 of each byte) kept, the rest cleared
+__device__ __forceinline__ uint32_t through_terminator(uint32_t t) { return ((t & (0u - t)) << 1) - 1u; }
 
-// element j of the tile starts at smraw[start_at[j]]: 12-byte window by funnel shifts, terminator by ffs.
+// element j of the tile starts at smraw[start_at[j]]: 12-byte window by funnel shifts, cut after its terminator.
 // Two shapes, chosen per warp: every lane's varint ends inside its first four bytes (values below 2^28:
-// indices, token ids, small counts), or the general branch-free form.
+// indices, token ids, small counts), or the general branch-free form.  A varint that never terminates inside the
+// chunk is caught by the caller (the chunk's last byte has its continuation bit set); here only the eleven-byte case.
 template <int K>
-__device__ __forceinline__ int32_t decode_elems(const uint8_t* smraw, const uint16_t* start_at, uint32_t n_here, uint32_t limit,
-                                                bool at_chunk_end, uint8_t* dst, uint64_t idx0, uint64_t n_elems) {
+__device__ __forceinline__ int32_t decode_elems(const uint8_t* smraw, const uint16_t* start_at, uint32_t n_here,
+                                                uint8_t* dst, uint64_t idx0, uint64_t n_elems) {
   int32_t st = B200TFS_OK;
-  for (uint32_t j0 = 0; j0 < n_here; j0 += kVarThreads) {      // trip count uniform across the CTA's warps that still have work
+  const uint64_t room = n_elems > idx0 ? n_elems - idx0 : 0;   // elements of the tensor this tile may still write
+  const uint32_t n_store = (uint32_t)min((uint64_t)n_here, room);
+  uint8_t* out = dst + idx0 * (K == VS_U64 ? 8 : K == VS_U32 ? 4 : (K == VS_I8 || K == VS_U8 || K == VS_BOOL) ? 1 : 2);
+  for (uint32_t j0 = 0; j0 < n_here; j0 += kVarThreads) {      // trip count uniform across the CTA
     const uint32_t j = j0 + threadIdx.x;
-    const bool live = j < n_here;
-    const uint32_t q = live ? start_at[j] : 16u;
+    const uint32_t q = (j < n_here) ? start_at[j] : 16u;
     const uint32_t* wp = reinterpret_cast<const uint32_t*>(smraw + (q & ~3u));
     const uint32_t shb = (q & 3u) * 8u;
     const uint32_t a0 = wp[0], a1 = wp[1];
     const uint32_t b0 = __funnelshift_r(a0, a1, shb);
     const uint32_t t0 = ~b0 & 0x80808080u;
-    uint32_t L, v_lo, v_hi = 0;
-    if (__all_sync(0xFFFFFFFFu, !live || t0 != 0u)) {
-      L = (uint32_t)__ffs((int)t0) >> 3;
-      v_lo = compress28(b0 & keep_bytes(L));
+    uint32_t v_lo, v_hi = 0;
+    if (__all_sync(0xFFFFFFFFu, t0 != 0u)) {
+      v_lo = compress28(b0 & through_terminator(t0));
     } else {
       const uint32_t a2 = wp[2], a3 = wp[3];
       const uint32_t b1 = __funnelshift_r(a1, a2, shb), b2 = __funnelshift_r(a2, a3, shb);
       const uint32_t t1 = ~b1 & 0x80808080u, t2 = ~b2 & 0x00008080u;
-      const uint32_t f0 = (uint32_t)__ffs((int)t0) >> 3, f1 = 4u + ((uint32_t)__ffs((int)t1) >> 3), f2 = 8u + ((uint32_t)__ffs((int)t2) >> 3);
-      L = t0 ? f0 : t1 ? f1 : t2 ? f2 : 11u;                   // 11: more than ten bytes, malformed
-      const uint32_t c0 = compress28(b0 & keep_bytes(L));
-      const uint32_t c1 = compress28(b1 & keep_bytes(max(L, 4u) - 4u));
-      const uint32_t c2 = compress28(b2 & keep_bytes(max(L, 8u) - 8u));
+      const uint32_t m0 = t0 ? through_terminator(t0) : 0xFFFFFFFFu;
+      const uint32_t m1 = t0 ? 0u : (t1 ? through_terminator(t1) : 0xFFFFFFFFu);
+      const uint32_t m2 = (t0 | t1) ? 0u : through_terminator(t2);
+      if ((t0 | t1 | t2) == 0u && j < n_here) st = B200TFS_E_PARSE;       // more than ten bytes
+      const uint32_t c0 = compress28(b0 & m0), c1 = compress28(b1 & m1), c2 = compress28(b2 & m2);
       v_lo = c0 | (c1 << 28);
       v_hi = (c1 >> 4) | (c2 << 24);
     }
-    if (live) {
-      if (L > 10u || q + L > limit) {                // runs past the staged bytes: only possible at the end of the chunk
-        if (L > 10u || at_chunk_end) st = B200TFS_E_PARSE;
-        v_lo = v_hi = 0;
-      }
-      if (idx0 + j < n_elems) store_decoded<K>(dst, idx0 + j, (uint64_t)v_lo | ((uint64_t)v_hi << 32), &st);
-    }
+    if (j < n_store) store_decoded<K>(out, j, (uint64_t)v_lo | ((uint64_t)v_hi << 32), &st);
   }
   return st;
 }
@@ -467,21 +466,19 @@ __global__ void __launch_bounds__(kVarThreads) vdec_emit_kernel(const __grid_con
   // counts those ahead of the tile (+1 when a varint straddles in from the previous tile: it precedes ours but
   // its terminator is here).
   const uint64_t idx0 = before + (smraw[15] >> 7);
-  const int64_t to_end = hi - (G - 16);                  // staged offset of the chunk's end
-  const bool at_end = to_end <= (int64_t)sizeof(smraw);
-  const uint32_t limit = at_end ? (uint32_t)to_end : (uint32_t)sizeof(smraw);
+  if (threadIdx.x == 0 && hi > G && hi <= G + kVarTileBytes && (hi[-1] & 0x80)) atomicMin(jb.status, B200TFS_E_PARSE);   // the chunk's last varint never ends
   int32_t st_local;
   switch (jb.dtype) {
-    case DT_INT64: case DT_UINT64: st_local = decode_elems<VS_U64>(smraw, start_at, n_here, limit, at_end, jb.dst, idx0, jb.n_elems); break;
-    case DT_INT32: case DT_UINT32: st_local = decode_elems<VS_U32>(smraw, start_at, n_here, limit, at_end, jb.dst, idx0, jb.n_elems); break;
-    case DT_INT16: st_local = decode_elems<VS_I16>(smraw, start_at, n_here, limit, at_end, jb.dst, idx0, jb.n_elems); break;
-    case DT_INT8: st_local = decode_elems<VS_I8>(smraw, start_at, n_here, limit, at_end, jb.dst, idx0, jb.n_elems); break;
-    case DT_UINT16: st_local = decode_elems<VS_U16>(smraw, start_at, n_here, limit, at_end, jb.dst, idx0, jb.n_elems); break;
-    case DT_UINT8: st_local = decode_elems<VS_U8>(smraw, start_at, n_here, limit, at_end, jb.dst, idx0, jb.n_elems); break;
-    case DT_BOOL: st_local = decode_elems<VS_BOOL>(smraw, start_at, n_here, limit, at_end, jb.dst, idx0, jb.n_elems); break;
+    case DT_INT64: case DT_UINT64: st_local = decode_elems<VS_U64>(smraw, start_at, n_here, jb.dst, idx0, jb.n_elems); break;
+    case DT_INT32: case DT_UINT32: st_local = decode_elems<VS_U32>(smraw, start_at, n_here, jb.dst, idx0, jb.n_elems); break;
+    case DT_INT16: st_local = decode_elems<VS_I16>(smraw, start_at, n_here, jb.dst, idx0, jb.n_elems); break;
+    case DT_INT8: st_local = decode_elems<VS_I8>(smraw, start_at, n_here, jb.dst, idx0, jb.n_elems); break;
+    case DT_UINT16: st_local = decode_elems<VS_U16>(smraw, start_at, n_here, jb.dst, idx0, jb.n_elems); break;
+    case DT_UINT8: st_local = decode_elems<VS_U8>(smraw, start_at, n_here, jb.dst, idx0, jb.n_elems); break;
+    case DT_BOOL: st_local = decode_elems<VS_BOOL>(smraw, start_at, n_here, jb.dst, idx0, jb.n_elems); break;
     case DT_HALF: case DT_BFLOAT16:
-      st_local = (jb.flags & kVarFlagHalfAsValue) ? decode_elems<VS_HALF_VALUE>(smraw, start_at, n_here, limit, at_end, jb.dst, idx0, jb.n_elems)
-                                                  : decode_elems<VS_HALF_BITS>(smraw, start_at, n_here, limit, at_end, jb.dst, idx0, jb.n_elems);
+      st_local = (jb.flags & kVarFlagHalfAsValue) ? decode_elems<VS_HALF_VALUE>(smraw, start_at, n_here, jb.dst, idx0, jb.n_elems)
+                                                  : decode_elems<VS_HALF_BITS>(smraw, start_at, n_here, jb.dst, idx0, jb.n_elems);
       break;
     default: st_local = B200TFS_OK; break;
   }
