@@ -222,7 +222,11 @@ int b200tfs_request_arena_size(int32_t n, const b200tfs_request* reqs, uint64_t*
 
 /* ---- encode (device tensors -> device wire arena) ---------------------------------------------- */
 /* Pass 1 for the varint-packed dtypes (int_val / int64_val / uint32_val / uint64_val / half_val):
- * fills tensors[i].packed_len on the device and copies the lengths back (synchronises).            */
+ * fills tensors[i].packed_len on the device and copies the lengths back (synchronises).  The tensor's
+ * contents must not change between this call and the encode that uses packed_len (the header announces
+ * that length; the encoder never writes past it, but the bytes would be meaningless).  The per-tile
+ * counters of the measurement stay on the device, keyed by tensors[i].data, and the NEXT encode of that
+ * buffer on this context consumes them instead of counting again; any later encode counts afresh.     */
 int b200tfs_measure(b200tfs_ctx* ctx, int32_t n, b200tfs_tensor* tensors);
 /* n bare TensorProtos (what ndarray_to_tensor_proto(...).SerializeToString() returns).
  * rec_off/rec_len (host arrays of n) receive where each message lies inside the arena.  Async.     */

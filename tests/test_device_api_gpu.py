@@ -313,6 +313,77 @@ def test_c4_cast_round_trip(dev, codec):
         assert np.array_equal(back.view(np.uint16), f.astype(np_dt).view(np.uint16))
 
 
+def test_varint_measure_then_encode_contract(dev):
+    """b200tfs_measure leaves its counters for the next encode of the same buffer: (a) that encode (one kernel fewer) and a
+    second encode of the unchanged tensor (which counts again) produce the same bytes; (b) refill the buffer, measure again,
+    encode: the new contents; (c) two tensors measured in separate calls, encoded together; (d) the same buffer as two
+    inputs of one request."""
+    from oracle import wire_oracle
+
+    lib = dev.lib
+    rng = np.random.default_rng(3)
+
+    keep = []
+
+    def tensor(ptr, n, key=b""):
+        dims = (C.c_int64 * 1)(n)
+        keep.append(dims)                                 # the struct only holds a pointer to it
+        return N.Tensor(data=ptr, src_dtype=9, wire_dtype=9, rank=1, flags=0, dims=dims, key=key, key_len=len(key), packed_len=0)
+
+    def launches():
+        v = C.c_uint64()
+        N.check(lib.b200tfs_kernel_launches(dev.ctx, C.byref(v)))
+        return v.value
+
+    def encode(ts):
+        arr = (N.Tensor * len(ts))(*ts)
+        need = C.c_uint64()
+        N.check(lib.b200tfs_tensor_arena_size(len(ts), arr, C.byref(need)))
+        arena = dev.malloc(need.value)
+        off, ln = (C.c_uint64 * len(ts))(), (C.c_uint64 * len(ts))()
+        before = launches()
+        N.check(lib.b200tfs_encode_tensor_protos(dev.ctx, len(ts), arr, arena, need.value, off, ln))
+        used = launches() - before
+        raw = dev.download(arena, need.value)
+        return [bytes(raw[off[i]: off[i] + ln[i]]) for i in range(len(ts))], used
+
+    n = 70001
+    a = (rng.integers(0, 2 ** 62, size=n, dtype=np.int64) >> rng.integers(0, 62, size=n)).astype(np.int64)
+    pa = dev.upload(a)
+    ta = (N.Tensor * 1)(tensor(pa, n))
+    N.check(lib.b200tfs_measure(dev.ctx, 1, ta))
+    first, l1 = encode([ta[0]])
+    second, l2 = encode([ta[0]])
+    assert first[0] == second[0] == wire_oracle.encode_tensor_proto(a)
+    assert l2 == l1 + 1                                   # the second encode ran the counting kernel again
+    # (b) new contents in the same buffer
+    b = rng.integers(-50, 50, size=n, dtype=np.int64)
+    N.check(lib.b200tfs_memcpy_h2d(dev.ctx, pa, b.ctypes.data, b.nbytes))
+    dev.sync()
+    N.check(lib.b200tfs_measure(dev.ctx, 1, ta))
+    assert encode([ta[0]])[0][0] == wire_oracle.encode_tensor_proto(b)
+    # (c) measured separately, encoded together
+    c2 = rng.integers(0, 300, size=5000, dtype=np.int64)
+    pc = dev.upload(c2)
+    tc = (N.Tensor * 1)(tensor(pc, 5000))
+    N.check(lib.b200tfs_measure(dev.ctx, 1, ta))
+    N.check(lib.b200tfs_measure(dev.ctx, 1, tc))
+    both, _ = encode([ta[0], tc[0]])
+    assert both == [wire_oracle.encode_tensor_proto(b), wire_oracle.encode_tensor_proto(c2)]
+    # (d) one buffer, two inputs of a request
+    two = (N.Tensor * 2)(tensor(pc, 5000, b"x"), tensor(pc, 5000, b"yy"))
+    N.check(lib.b200tfs_measure(dev.ctx, 2, two))
+    rq = (N.Request * 1)(N.Request(model_name=b"m", model_name_len=1, has_version=0, order=N.ORDER_UPB, version=0, n_inputs=2, reserved=0,
+                                   inputs=C.cast(two, C.POINTER(N.Tensor))))
+    need = C.c_uint64()
+    N.check(lib.b200tfs_request_arena_size(1, rq, C.byref(need)))
+    arena = dev.malloc(need.value)
+    off, ln = (C.c_uint64 * 1)(), (C.c_uint64 * 1)()
+    N.check(lib.b200tfs_encode_requests(dev.ctx, 1, rq, arena, need.value, off, ln))
+    raw = dev.download(arena, need.value)
+    assert bytes(raw[off[0]: off[0] + ln[0]]) == wire_oracle.encode_predict_request("m", None, [("x", c2), ("yy", c2)])
+
+
 def test_one_gib_tensor(dev):
     """Largest practical single message: fp32 [16384, 16384] = 1 GiB payload (protobuf's limit is 2 GiB; the
     E_TOOBIG side of that limit is a CPU test).  The whole 1 GiB wire is compared with the C oracle's."""
