@@ -288,7 +288,7 @@ class C2Bench:
         for l in self.lanes:
             l.ring = self.ring
         # pinned host buffers for the e2e leg: `depth` requests in flight, each on its own pair of lanes
-        self.e2e_depth = max(1, min(4, streams // 2))
+        self.e2e_depth = max(1, min(int(os.environ.get("B200TFS_E2E_DEPTH", "4")), streams // 2))
         self.e2e = []
         for j in range(self.e2e_depth):
             slot = {"x": N.PinnedBuffer(self.P), "wire": N.PinnedBuffer(self.main.arena_cap), "resp": N.PinnedBuffer(self.S.resp_len),
@@ -611,7 +611,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=480)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--ring", type=int, default=48, help="ring slots in total (split over the streams)")
-    ap.add_argument("--streams", type=int, default=8, help="independent lanes (native contexts = CUDA streams) per GPU")
+    ap.add_argument("--streams", type=int, default=16, help="independent lanes (native contexts = CUDA streams) per GPU")
     ap.add_argument("--graph-steps", type=int, default=48, help="steps recorded per CUDA graph")
     ap.add_argument("--e2e-steps", type=int, default=200)
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
