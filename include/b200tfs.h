@@ -91,6 +91,11 @@ extern "C" {
 #define B200TFS_ORDER_UPB 1   /* the order SerializeToString(deterministic=True) gives with the protobuf (upb)
                                  runtime the oracle was pinned against: bytewise, but a key that is a strict prefix
                                  of another sorts AFTER it                                                          */
+/* b200tfs_request.flags */
+#define B200TFS_RF_GRPC_FRAME 0x1 /* put gRPC's length-prefixed-message header in front of the record: one byte 0 (not
+                                     compressed) and the message length as a big-endian uint32 (what grpc writes on the HTTP/2
+                                     stream before the bytes request_serializer returned); rec_off/rec_len and
+                                     b200tfs_request_size include the five bytes                                          */
 #define B200TFS_ORDER_BYTES 2 /* plain bytewise order (shorter prefix first)                                     */
 
 #define B200TFS_MAX_RANK 16   /* decode table limit; encode accepts any rank up to 254 (TF's limit)            */
@@ -123,7 +128,7 @@ typedef struct b200tfs_request {
   int32_t order;        /* B200TFS_ORDER_*                                                     */
   int64_t version;
   int32_t n_inputs;
-  int32_t reserved;
+  int32_t flags;        /* B200TFS_RF_*                                                        */
   const b200tfs_tensor* inputs;
 } b200tfs_request;
 

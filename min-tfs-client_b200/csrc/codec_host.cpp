@@ -549,6 +549,7 @@ struct RequestLayout {
   std::vector<int32_t> perm;
   std::vector<uint64_t> tp_len, entry_len;
   uint64_t spec_len = 0, version_len = 0, total = 0;
+  uint64_t prefix = 0;        // bytes in front of the message: gRPC's 5-byte frame header when asked for
   uint64_t largest_off = 0;
   std::vector<uint64_t> payload_off;
 };
@@ -577,7 +578,9 @@ int request_layout(const b200tfs_request& r, RequestLayout* R) {
     spec += 2 + R->version_len;
   }
   R->spec_len = spec;
-  uint64_t total = 1 + varint_len(spec) + spec;
+  if (r.flags & ~B200TFS_RF_GRPC_FRAME) return fail(B200TFS_E_ARG, "unknown request flags 0x%x", (unsigned)r.flags);
+  R->prefix = (r.flags & B200TFS_RF_GRPC_FRAME) ? 5 : 0;
+  uint64_t total = R->prefix + 1 + varint_len(spec) + spec;
   uint64_t largest = 0;
   R->largest_off = 0;
   for (int j = 0; j < n; ++j) {
@@ -595,7 +598,8 @@ int request_layout(const b200tfs_request& r, RequestLayout* R) {
     if (L.payload_len > largest) { largest = L.payload_len; R->largest_off = payload_off; }
     total += 1 + varint_len(el) + el;
   }
-  if (total > kProtoLimit) return fail(B200TFS_E_TOOBIG, "PredictRequest of %llu bytes exceeds protobuf's 2 GiB limit", (unsigned long long)total);
+  if (total - R->prefix > kProtoLimit)
+    return fail(B200TFS_E_TOOBIG, "PredictRequest of %llu bytes exceeds protobuf's 2 GiB limit", (unsigned long long)(total - R->prefix));
   R->total = total;
   return B200TFS_OK;
 }
@@ -606,6 +610,11 @@ int plan_request(const b200tfs_request& r, const RequestLayout& R, uint8_t* rec,
   auto put = [&](const uint8_t* p, size_t k) { pb.blob.insert(pb.blob.end(), p, p + k); };
   size_t mark = pb.blob.size();
   uint8_t* cursor = rec;  // where the pending header run (blob[mark:]) will land
+  if (R.prefix) {         // gRPC length-prefixed message: compressed-flag 0, big-endian uint32 length
+    const uint64_t m = R.total - R.prefix;
+    tmp[0] = 0; tmp[1] = (uint8_t)(m >> 24); tmp[2] = (uint8_t)(m >> 16); tmp[3] = (uint8_t)(m >> 8); tmp[4] = (uint8_t)m;
+    put(tmp, 5);
+  }
   tmp[0] = 0x0A; put(tmp, 1);
   put(tmp, put_varint(tmp, R.spec_len));
   if (r.model_name_len) {

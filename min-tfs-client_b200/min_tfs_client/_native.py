@@ -22,6 +22,7 @@ E_DTYPE, E_SHAPE, E_SIZE, E_PARSE, E_CUDA, E_TOOBIG, E_ARG, E_NONCANONICAL, E_RA
 F_TENSOR_CONTENT = 0x1
 F_KEEP_SNAN = 0x2
 F_PRESERIALIZED = 0x4
+RF_GRPC_FRAME = 0x1
 OF_TENSOR_CONTENT, OF_MULTI_CHUNK, OF_DIM_INFERRED, OF_HAS_UNKNOWN, OF_RANK0, OF_VARINT = 0x1, 0x2, 0x4, 0x8, 0x10, 0x20
 ORDER_GIVEN, ORDER_UPB, ORDER_BYTES = 0, 1, 2
 MAX_RANK, MAX_CHUNKS, FUSED_MAX_OUTPUTS = 16, 8, 8
@@ -47,7 +48,7 @@ class Tensor(C.Structure):
 class Request(C.Structure):
     _fields_ = [
         ("model_name", C.c_char_p), ("model_name_len", C.c_int64), ("has_version", C.c_int32), ("order", C.c_int32),
-        ("version", C.c_int64), ("n_inputs", C.c_int32), ("reserved", C.c_int32), ("inputs", C.POINTER(Tensor)),
+        ("version", C.c_int64), ("n_inputs", C.c_int32), ("flags", C.c_int32), ("inputs", C.POINTER(Tensor)),
     ]
 
 

@@ -193,7 +193,7 @@ class Codec:
                 out[i] = wire[off[j]: off[j] + ln[j]].tobytes()
         return out  # type: ignore[return-value]
 
-    def _build_requests(self, requests, order, wire_dtype, tensor_content, keep_snan):
+    def _build_requests(self, requests, order, wire_dtype, tensor_content, keep_snan, grpc_frame=False):
         order_code = _ORDER[order] if isinstance(order, str) else int(order)
         keep = []
         structs = []
@@ -207,21 +207,23 @@ class Codec:
             arr = (N.Tensor * max(len(preps), 1))(*[p.struct for p in preps])
             name = model_name.encode("utf-8") if isinstance(model_name, str) else bytes(model_name)
             req = N.Request(model_name=name, model_name_len=len(name), has_version=int(model_version is not None), order=order_code,
-                            version=int(model_version) if model_version is not None else 0, n_inputs=len(preps), reserved=0, inputs=arr)
+                            version=int(model_version) if model_version is not None else 0, n_inputs=len(preps), flags=N.RF_GRPC_FRAME if grpc_frame else 0,
+                            inputs=arr)
             keep.append((preps, arr, name))
             structs.append(req)
         return keep, structs
 
     def encode_predict_requests(self, requests: Iterable[Tuple[str, Optional[int], Union[Mapping, Sequence]]], *,
                                 order="deterministic", wire_dtype=None, tensor_content: bool = False,
-                                keep_snan: bool = False) -> List[bytes]:
+                                keep_snan: bool = False, grpc_frame: bool = False) -> List[bytes]:
         """Each item is ``(model_name, model_version, inputs)``; returns one PredictRequest wire per item.
 
         The bytes equal ``PredictRequest.SerializeToString(deterministic=True)`` of the message the
         reference builds in requests.py:41-48 (``order="deterministic"``), or list the map entries in
-        the order given (``order="given"``).
+        the order given (``order="given"``).  ``grpc_frame=True`` puts gRPC's five-byte length-prefixed-message
+        header in front (for a transport that writes HTTP/2 DATA frames itself; grpc-python adds it on its own).
         """
-        keep, structs = self._build_requests(list(requests), order, wire_dtype, tensor_content, keep_snan)
+        keep, structs = self._build_requests(list(requests), order, wire_dtype, tensor_content, keep_snan, grpc_frame)
         n = len(structs)
         if n == 0:
             return []

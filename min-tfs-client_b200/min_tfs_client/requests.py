@@ -63,15 +63,23 @@ def gpu_response_deserializer(wire: bytes) -> PredictResponseView:
     return PredictResponseView(wire)
 
 
+# grpc's default receive limit is 4 MiB and the reference leaves it alone (requests.py:27-30): a response that carries a
+# fp32[1024,1024] tensor (4 194 3xx bytes) is refused with RESOURCE_EXHAUSTED.  Pass these to lift both limits.
+LARGE_MESSAGE_CHANNEL_OPTIONS = (("grpc.max_send_message_length", -1), ("grpc.max_receive_message_length", -1))
+
+
 class TensorServingClient:
-    def __init__(self, host: str, port: int, credentials=None) -> None:
+    def __init__(self, host: str, port: int, credentials=None, channel_options=None) -> None:
+        """Same arguments as the reference (requests.py:22-30); ``channel_options`` (default None: grpc's defaults, like the
+        reference) is handed to ``grpc.insecure_channel`` / ``grpc.secure_channel``, e.g. ``LARGE_MESSAGE_CHANNEL_OPTIONS``."""
         import grpc
 
         self._host_address = f"{host}:{port}"
+        options = list(channel_options) if channel_options else None
         if credentials:
-            self._channel = grpc.secure_channel(self._host_address, credentials)
+            self._channel = grpc.secure_channel(self._host_address, credentials, options=options)
         else:
-            self._channel = grpc.insecure_channel(self._host_address)
+            self._channel = grpc.insecure_channel(self._host_address, options=options)
         self._predict = self._channel.unary_unary(PREDICT_METHOD, request_serializer=gpu_request_serializer,
                                                   response_deserializer=gpu_response_deserializer)
 

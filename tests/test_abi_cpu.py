@@ -126,7 +126,7 @@ def test_request_frame_matches_golden(name):
     arr = (N.Tensor * max(len(preps), 1))(*[p.struct for p in preps])
     name_b = case["model_name"].encode()
     req = N.Request(model_name=name_b, model_name_len=len(name_b), has_version=int(case["model_version"] is not None), order=N.ORDER_UPB,
-                    version=case["model_version"] or 0, n_inputs=len(preps), reserved=0, inputs=arr)
+                    version=case["model_version"] or 0, n_inputs=len(preps), flags=0, inputs=arr)
     lib = N.load()
     total = C.c_uint64()
     N.check(lib.b200tfs_request_size(C.byref(req), C.byref(total)))
@@ -148,6 +148,18 @@ def test_request_frame_matches_golden(name):
         assert len(payload) == plen[j]
         wire += payload
     wire += frame[fpos:]
+    # the same request behind gRPC's length-prefixed-message header: five more bytes in front, every payload 5 further on
+    req.flags = N.RF_GRPC_FRAME
+    total5, flen5 = C.c_uint64(), C.c_uint64()
+    N.check(lib.b200tfs_request_size(C.byref(req), C.byref(total5)))
+    buf5 = C.create_string_buffer(cap)
+    poff5, plen5, perm5 = (C.c_uint64 * n)(), (C.c_uint64 * n)(), (C.c_int32 * n)()
+    N.check(lib.b200tfs_request_frame(C.byref(req), buf5, cap, C.byref(flen5), poff5, plen5, perm5))
+    assert total5.value == total.value + 5 and flen5.value == flen.value + 5
+    assert buf5.raw[: flen5.value] == b"\x00" + int(total.value).to_bytes(4, "big") + frame
+    assert [poff5[j] for j in range(len(preps))] == [poff[j] + 5 for j in range(len(preps))]
+    req.flags = 0x40
+    assert lib.b200tfs_request_size(C.byref(req), C.byref(total5)) == N.E_ARG
     G.check_wire(bytes(wire), case["wire"], name)
 
 

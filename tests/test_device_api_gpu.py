@@ -34,7 +34,7 @@ def _encode_requests_device(dev, batch, order=N.ORDER_UPB):
         keep.append(arr)
         name = model.encode()
         reqs.append(N.Request(model_name=name, model_name_len=len(name), has_version=int(version is not None), order=order,
-                              version=version or 0, n_inputs=len(ts), reserved=0, inputs=arr))
+                              version=version or 0, n_inputs=len(ts), flags=0, inputs=arr))
     n = len(reqs)
     rq = (N.Request * n)(*reqs)
     flat = []
@@ -186,7 +186,7 @@ def test_graph_replay_encode_decode(dev):
     t, dims = tensor_struct(src, x, key=b"x")
     ts = (N.Tensor * 1)(t)
     rq = (N.Request * 1)(N.Request(model_name=b"m", model_name_len=1, has_version=1, order=N.ORDER_UPB, version=3, n_inputs=1,
-                                   reserved=0, inputs=ts))
+                                   flags=0, inputs=ts))
     need = C.c_uint64()
     N.check(lib.b200tfs_request_arena_size(1, rq, C.byref(need)))
     arena = dev.malloc(need.value)
@@ -243,7 +243,7 @@ def test_c5_full_size_batch_1024(dev):
     rq = (N.Request * n)()
     for i in range(n):
         ts[i] = N.Tensor(data=src + i * P, src_dtype=1, wire_dtype=1, rank=3, flags=0, dims=dims, key=b"image", key_len=5, packed_len=0)
-        rq[i] = N.Request(model_name=b"default", model_name_len=7, has_version=1, order=N.ORDER_UPB, version=1, n_inputs=1, reserved=0,
+        rq[i] = N.Request(model_name=b"default", model_name_len=7, has_version=1, order=N.ORDER_UPB, version=1, n_inputs=1, flags=0,
                           inputs=C.cast(C.byref(ts, i * C.sizeof(N.Tensor)), C.POINTER(N.Tensor)))
     need = C.c_uint64()
     N.check(dev.lib.b200tfs_request_arena_size(n, rq, C.byref(need)))
@@ -373,7 +373,7 @@ def test_varint_measure_then_encode_contract(dev):
     # (d) one buffer, two inputs of a request
     two = (N.Tensor * 2)(tensor(pc, 5000, b"x"), tensor(pc, 5000, b"yy"))
     N.check(lib.b200tfs_measure(dev.ctx, 2, two))
-    rq = (N.Request * 1)(N.Request(model_name=b"m", model_name_len=1, has_version=0, order=N.ORDER_UPB, version=0, n_inputs=2, reserved=0,
+    rq = (N.Request * 1)(N.Request(model_name=b"m", model_name_len=1, has_version=0, order=N.ORDER_UPB, version=0, n_inputs=2, flags=0,
                                    inputs=C.cast(two, C.POINTER(N.Tensor))))
     need = C.c_uint64()
     N.check(lib.b200tfs_request_arena_size(1, rq, C.byref(need)))
@@ -398,7 +398,7 @@ def test_one_gib_tensor(dev):
     src = dev.upload(x)
     dims = (C.c_int64 * 2)(n, n)
     ts = (N.Tensor * 1)(N.Tensor(data=src, src_dtype=1, wire_dtype=1, rank=2, flags=0, dims=dims, key=b"x", key_len=1, packed_len=0))
-    rq = (N.Request * 1)(N.Request(model_name=b"default", model_name_len=7, has_version=1, order=N.ORDER_UPB, version=1, n_inputs=1, reserved=0,
+    rq = (N.Request * 1)(N.Request(model_name=b"default", model_name_len=7, has_version=1, order=N.ORDER_UPB, version=1, n_inputs=1, flags=0,
                                    inputs=ts))
     need, total = C.c_uint64(), C.c_uint64()
     N.check(dev.lib.b200tfs_request_size(rq, C.byref(total)))

@@ -52,6 +52,23 @@ def test_encode_predict_request(codec, name):
     G.check_wire(wire, case["wire"], name)
 
 
+def test_grpc_length_prefixed_message(codec):
+    """RF_GRPC_FRAME: 00 + big-endian uint32 length in front of the same PredictRequest bytes (single request, batch of
+    requests, a varint input whose length the device measures)."""
+    from oracle import wire_oracle
+
+    rng = np.random.default_rng(8)
+    reqs = [("default", 1, [("x", rng.standard_normal((64, 257)).astype(np.float32))]),
+            ("m", None, [("ids", rng.integers(0, 50000, size=(4, 300), dtype=np.int64)), ("mask", np.ones((4, 300), dtype=np.bool_))]),
+            ("", 0, [])]
+    plain = codec.encode_predict_requests(reqs)
+    framed = codec.encode_predict_requests(reqs, grpc_frame=True)
+    for (name, version, inputs), p, f in zip(reqs, plain, framed):
+        assert p == wire_oracle.encode_predict_request(name, version, inputs)
+        assert f == b"\x00" + len(p).to_bytes(4, "big") + p
+    assert codec.encode_predict_request("default", dict(reqs[0][2]), 1, grpc_frame=True) == framed[0]
+
+
 def test_encode_request_batch_matches_singles(codec):
     names = ["kat2_c1", "no_version", "mixed_dtypes", "c3_req7", "order_quirk", "no_inputs"]
     batch = [(REQ[n]["model_name"], REQ[n]["model_version"], [(k, G.make_array(r)) for k, r in REQ[n]["inputs"]]) for n in names]

@@ -6,7 +6,7 @@ import pytest
 from numpy.testing import assert_array_almost_equal, assert_array_equal
 
 from fake_server import IdentityServer
-from min_tfs_client.requests import TensorServingClient
+from min_tfs_client.requests import LARGE_MESSAGE_CHANNEL_OPTIONS, TensorServingClient
 from min_tfs_client.tensors import make_ndarray, tensor_proto_to_ndarray
 from oracle import ref_port
 
@@ -48,6 +48,24 @@ def test_predict_request_large_tensor_and_one_shot_decode(served):
     assert_array_equal(outs["ids_output"], ids)
     assert_array_equal(make_ndarray(response.outputs["x_output"]), x)
     assert not response.model_spec.HasField("version") or response.model_spec.version.value == 1
+
+
+def test_c2_sized_round_trip_needs_the_channel_option(served):
+    """BASELINE configs[1] over real gRPC: a fp32[1024,1024] response is a few bytes over grpc's default 4 MiB receive
+    limit, which the reference never lifts (requests.py:27-30) - same RESOURCE_EXHAUSTED here by default, and the
+    round trip, bit-exact, with LARGE_MESSAGE_CHANNEL_OPTIONS."""
+    import grpc
+
+    x = np.random.default_rng(1).standard_normal((1024, 1024), dtype=np.float32)
+    with pytest.raises(grpc.RpcError) as err:
+        TensorServingClient(host="127.0.0.1", port=served.port).predict_request("default", {"x_input": x}, model_version=1, timeout=30)
+    assert err.value.code() == grpc.StatusCode.RESOURCE_EXHAUSTED
+    client = TensorServingClient(host="127.0.0.1", port=served.port, channel_options=LARGE_MESSAGE_CHANNEL_OPTIONS)
+    response = client.predict_request("default", {"x_input": x}, model_version=1, timeout=30)
+    assert len(served.received[-1]) == 4194351 + len("_input")          # KAT-3 (SURVEY 8c) with the longer key
+    assert served.received[-1] == ref_port.encode_predict_request("default", 1, [("x_input", x)], deterministic=True)
+    out = tensor_proto_to_ndarray(response.outputs["x_output"])
+    assert out.dtype == np.float32 and out.shape == (1024, 1024) and out.tobytes() == x.tobytes()
 
 
 def test_out_of_scope_rpcs_raise(served):

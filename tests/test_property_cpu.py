@@ -161,7 +161,7 @@ def test_host_planner_frames_random_requests_like_the_runtime(data):
     arr = (N.Tensor * max(len(preps), 1))(*[p.struct for p in preps])
     nb = name.encode()
     req = N.Request(model_name=nb, model_name_len=len(nb), has_version=int(version is not None), order=N.ORDER_UPB, version=version or 0,
-                    n_inputs=len(preps), reserved=0, inputs=arr)
+                    n_inputs=len(preps), flags=0, inputs=arr)
     lib = N.load()
     buf = C.create_string_buffer(1 << 16)
     flen = C.c_uint64()

@@ -49,7 +49,7 @@ def main():
     ts, rq = (N.Tensor * n)(), (N.Request * n)()
     for i in range(n):
         ts[i] = N.Tensor(data=src + i * P, src_dtype=1, wire_dtype=1, rank=3, flags=0, dims=dims, key=b"image", key_len=5, packed_len=0)
-        rq[i] = N.Request(model_name=b"default", model_name_len=7, has_version=1, order=N.ORDER_UPB, version=1, n_inputs=1, reserved=0,
+        rq[i] = N.Request(model_name=b"default", model_name_len=7, has_version=1, order=N.ORDER_UPB, version=1, n_inputs=1, flags=0,
                           inputs=C.cast(C.byref(ts, i * C.sizeof(N.Tensor)), C.POINTER(N.Tensor)))
     need = C.c_uint64()
     N.check(lib.b200tfs_request_arena_size(n, rq, C.byref(need)))
