@@ -91,6 +91,7 @@ struct b200tfs_ctx {
   void* tpl_dev = nullptr;  // two framing templates (device), used alternately by successive decode launches
   uint32_t tpl_flip = 0;
   int32_t fused_n = 0;      // records of the last b200tfs_decode_responses
+  std::vector<int32_t> pending_status;   // varint decode: which output each status word in scratch_host belongs to
   // counters left by b200tfs_measure, keyed by tensor address; consumed by the encode that follows
   Growable measured_dev;
   uint64_t measured_used = 0;
@@ -872,8 +873,16 @@ int run_vardecode(b200tfs_ctx* c, std::vector<VarDecodeJob>& jobs, int32_t* stat
 
 }  // namespace
 
-extern "C" int b200tfs_unpack_outputs(b200tfs_ctx* c, const void* arena_dev, int32_t m, const b200tfs_output* outs,
-                                      const uint64_t* out_rec_off, void* const* dst_dev, const int32_t* dst_dtype, int32_t* status) {
+// after a synchronise: the status words the varint decoder left in pinned memory -> the caller's array
+static void collect_varint_status(b200tfs_ctx* c, int32_t* status) {
+  if (status)
+    for (size_t i = 0; i < c->pending_status.size(); ++i) status[c->pending_status[i]] = ((const int32_t*)c->scratch_host.p)[i];
+  c->pending_status.clear();
+}
+
+// wait = false: everything is enqueued, nothing synchronised; the caller synchronises and calls collect_varint_status
+static int unpack_outputs_impl(b200tfs_ctx* c, const void* arena_dev, int32_t m, const b200tfs_output* outs, const uint64_t* out_rec_off,
+                               void* const* dst_dev, const int32_t* dst_dtype, int32_t* status, bool wait) {
   if (!c || m < 0 || (m && (!arena_dev || !outs || !dst_dev))) return fail(B200TFS_E_ARG, "bad arguments");
   CU(cudaSetDevice(c->device));
   PlanBuilder pb;
@@ -924,11 +933,20 @@ extern "C" int b200tfs_unpack_outputs(b200tfs_ctx* c, const void* arena_dev, int
   }
   int rc = launch_plan(c, pb);
   if (rc) return rc;
+  c->pending_status.clear();
   if (!vjobs.empty()) {
     if ((rc = run_vardecode(c, vjobs, status))) return rc;
   }
-  if (status) CU(cudaStreamSynchronize(c->stream));
+  if (status && wait) {
+    CU(cudaStreamSynchronize(c->stream));
+    collect_varint_status(c, status);
+  }
   return B200TFS_OK;
+}
+
+extern "C" int b200tfs_unpack_outputs(b200tfs_ctx* c, const void* arena_dev, int32_t m, const b200tfs_output* outs,
+                                      const uint64_t* out_rec_off, void* const* dst_dev, const int32_t* dst_dtype, int32_t* status) {
+  return unpack_outputs_impl(c, arena_dev, m, outs, out_rec_off, dst_dev, dst_dtype, status, true);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -1243,13 +1261,14 @@ int b200tfs_unpack_outputs_host(b200tfs_ctx* c, int32_t m, const b200tfs_output*
   if (rc) return rc;
   std::vector<void*> dd(m);
   for (int j = 0; j < m; ++j) dd[j] = (uint8_t*)c->arena_dev.p + off[j];
-  if ((rc = b200tfs_unpack_outputs(c, c->stage_dev.p, m, outs, out_rec_off, dd.data(), dst_dtype, status))) return rc;
+  if ((rc = unpack_outputs_impl(c, c->stage_dev.p, m, outs, out_rec_off, dd.data(), dst_dtype, status, false))) return rc;
   for (int j = 0; j < m; ++j)
     if (nb[j]) {
       if (!dst_host[j]) return fail(B200TFS_E_ARG, "output %d: dst is NULL", j);
       CU(cudaMemcpyAsync(dst_host[j], dd[j], nb[j], cudaMemcpyDeviceToHost, c->stream));
     }
   CU(cudaStreamSynchronize(c->stream));
+  collect_varint_status(c, status);
   return B200TFS_OK;
 }
 

@@ -122,6 +122,9 @@ class DecodedSpec:
                 f"version_label={self.version_label!r}, signature_name={self.signature_name!r})")
 
 
+_FUSED_MOVES = frozenset((1, 2, 8, 18))   # DT_FLOAT, DT_DOUBLE, DT_COMPLEX64, DT_COMPLEX128: what decode_fused_kernel moves itself
+
+
 class ParsedResponse:
     """Table the parse kernel produced for one PredictResponse: where every output's values lie."""
 
@@ -345,6 +348,10 @@ class Codec:
         rejects); the default additionally accepts what TF itself emits: ``tensor_content``, rank-0
         tensors, complex pairs, bfloat16, and reads ``half_val`` as bit patterns.
         """
+        if out_dtypes is None and len(wires):
+            fused = self._decode_fused(wires, strict)
+            if fused is not None:
+                return fused
         parsed = self.parse_predict_responses(wires, max_outputs=max_outputs)
         if not parsed:
             return []
@@ -373,6 +380,62 @@ class Codec:
                     raise ValueError(f"cannot reshape array into shape {shape}")
                 N.check(status[k])
                 results[i][0][key] = arrays[k]
+        return results
+
+    def _decode_fused(self, wires: Sequence[bytes], strict: bool):
+        """One launch, one synchronise: tag walk (or framing-template check), destination layout and the move of every
+        fixed-width output in ``decode_fused_kernel``; the outputs come back as views of one host buffer.  Varint-packed
+        and tensor_content-only outputs are tabulated by the same launch and unpacked by a second one.  Returns None when
+        a record needs the two-phase path (more than eight outputs, a malformed record: that path raises what the
+        reference raises)."""
+        n = len(wires)
+        buf, off, ln = self._pack_wires(wires)
+        K = N.FUSED_MAX_OUTPUTS
+        stride = (max(int(ln[i]) for i in range(n)) + 256 * (K + 1) + 255) & ~255   # every fixed output fits, each 256-aligned
+        dst = np.empty(n * stride, dtype=np.uint8)
+        N.check(self._lib.b200tfs_decode_responses_host_async(self._ctx, buf.ctypes.data, n, off, ln, dst.ctypes.data, stride))
+        outs = (N.Output * (n * K))()
+        n_outs = (C.c_int32 * n)()
+        specs = (N.ModelSpec * n)()
+        status = (C.c_int32 * n)()
+        N.check(self._lib.b200tfs_decode_results(self._ctx, n, outs, n_outs, specs, status))   # synchronises
+        if any(status[i] != N.OK for i in range(n)):
+            return None
+        results: List[Tuple[Dict[str, np.ndarray], DecodedSpec]] = []
+        jobs = []
+        for i in range(n):
+            base = int(off[i])
+            s = specs[i]
+            spec = DecodedSpec(self._text(buf, base + s.name_off, s.name_len), int(s.version), bool(s.has_version),
+                               self._text(buf, base + s.label_off, s.label_len), self._text(buf, base + s.signature_off, s.signature_len))
+            arrays: Dict[str, np.ndarray] = {}
+            results.append((arrays, spec))
+            for j in range(n_outs[i]):
+                o = outs[i * K + j]
+                key = self._text(buf, base + o.key_off, o.key_len)
+                if int(o.dtype) == DT_STRING and o.status == N.OK:
+                    arrays[key] = self._decode_strings(buf, base, o)
+                    continue
+                np_type, dst_code, shape = self._resolve_output(o, strict, None)
+                if o.status == N.OK and int(o.dtype) in _FUSED_MOVES and o.n_chunks and o.n_elems and dst_code == int(o.dtype):
+                    at = i * stride + int(o.dst_off)
+                    arrays[key] = dst[at: at + int(o.dst_bytes)].view(np_type).reshape(shape)
+                else:
+                    jobs.append((i, key, o, np_type, dst_code, shape))
+        if jobs:
+            m = len(jobs)
+            o_arr = (N.Output * m)(*[j[2] for j in jobs])
+            made = [np.empty(j[5], dtype=j[3]) for j in jobs]
+            ptrs = (C.c_void_p * m)(*[a.ctypes.data if a.size else None for a in made])
+            codes = (C.c_int32 * m)(*[j[4] for j in jobs])
+            st = (C.c_int32 * m)()
+            rec = (C.c_uint64 * m)(*[int(off[j[0]]) for j in jobs])
+            N.check(self._lib.b200tfs_unpack_outputs_host(self._ctx, m, o_arr, rec, ptrs, codes, st))
+            for k, (i, key, o, np_type, dst_code, shape) in enumerate(jobs):
+                if st[k] == N.E_SHAPE:
+                    raise ValueError(f"cannot reshape array into shape {shape}")
+                N.check(st[k])
+                results[i][0][key] = made[k]
         return results
 
     @staticmethod
