@@ -125,6 +125,27 @@ class DecodedSpec:
 _FUSED_MOVES = frozenset((1, 2, 8, 18))   # DT_FLOAT, DT_DOUBLE, DT_COMPLEX64, DT_COMPLEX128: what decode_fused_kernel moves itself
 
 
+class OpenResponse:
+    """One PredictResponse after the fused launch: the table, and the host buffer the fixed-width outputs landed in."""
+
+    def __init__(self, codec, buf, base, dst, table):
+        self._codec, self._buf, self._base, self._dst, self.table = codec, buf, base, dst, table
+
+    def wire_of(self, key) -> bytes:
+        o = self.table[key]
+        return self._buf[self._base + o.msg_off: self._base + o.msg_off + o.msg_len].tobytes()
+
+    def array(self, key, strict: bool) -> Optional[np.ndarray]:
+        """The decoded output, or None when the launch did not move it (varint-packed, string, tensor_content only): the
+        caller then decodes ``wire_of(key)`` on its own.  Raises what the reference raises for this output."""
+        o = self.table[key]
+        if int(o.dtype) not in _FUSED_MOVES or o.status != N.OK or not o.n_chunks or not o.n_elems:
+            return None
+        np_type, dst_code, shape = self._codec._resolve_output(o, strict, None)
+        at = int(o.dst_off)
+        return self._dst[at: at + int(o.dst_bytes)].view(np_type).reshape(shape)
+
+
 class ParsedResponse:
     """Table the parse kernel produced for one PredictResponse: where every output's values lie."""
 
@@ -382,12 +403,9 @@ class Codec:
                 results[i][0][key] = arrays[k]
         return results
 
-    def _decode_fused(self, wires: Sequence[bytes], strict: bool):
-        """One launch, one synchronise: tag walk (or framing-template check), destination layout and the move of every
-        fixed-width output in ``decode_fused_kernel``; the outputs come back as views of one host buffer.  Varint-packed
-        and tensor_content-only outputs are tabulated by the same launch and unpacked by a second one.  Returns None when
-        a record needs the two-phase path (more than eight outputs, a malformed record: that path raises what the
-        reference raises)."""
+    def _fused_launch(self, wires: Sequence[bytes]):
+        """H2D of the wire, decode_fused_kernel, D2H of the decoded fixed-width outputs, one synchronise.  None if any
+        record was not tabulated (malformed, or more than FUSED_MAX_OUTPUTS outputs)."""
         n = len(wires)
         buf, off, ln = self._pack_wires(wires)
         K = N.FUSED_MAX_OUTPUTS
@@ -401,6 +419,34 @@ class Codec:
         N.check(self._lib.b200tfs_decode_results(self._ctx, n, outs, n_outs, specs, status))   # synchronises
         if any(status[i] != N.OK for i in range(n)):
             return None
+        return n, buf, off, dst, stride, outs, n_outs, specs
+
+    def open_predict_response(self, wire: bytes) -> Optional["OpenResponse"]:
+        """Decode one PredictResponse now, hand its outputs out later (``PredictResponseView.outputs``): the launch moves
+        every fixed-width output; ``OpenResponse.array(key, strict)`` applies the reference's per-output rules on demand."""
+        if not len(wire):
+            return None
+        launched = self._fused_launch([wire])
+        if launched is None:
+            return None
+        _, buf, off, dst, _, outs, n_outs, _ = launched
+        table = {}
+        for j in range(n_outs[0]):
+            o = outs[j]
+            table[self._text(buf, int(off[0]) + o.key_off, o.key_len)] = o
+        return OpenResponse(self, buf, int(off[0]), dst, table)
+
+    def _decode_fused(self, wires: Sequence[bytes], strict: bool):
+        """One launch, one synchronise: tag walk (or framing-template check), destination layout and the move of every
+        fixed-width output in ``decode_fused_kernel``; the outputs come back as views of one host buffer.  Varint-packed
+        and tensor_content-only outputs are tabulated by the same launch and unpacked by a second one.  Returns None when
+        a record needs the two-phase path (more than eight outputs, a malformed record: that path raises what the
+        reference raises)."""
+        launched = self._fused_launch(wires)
+        if launched is None:
+            return None
+        n, buf, off, dst, stride, outs, n_outs, specs = launched
+        K = N.FUSED_MAX_OUTPUTS
         results: List[Tuple[Dict[str, np.ndarray], DecodedSpec]] = []
         jobs = []
         for i in range(n):

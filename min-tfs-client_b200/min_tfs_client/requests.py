@@ -36,9 +36,13 @@ class PredictResponseView:
     @property
     def outputs(self) -> Dict[str, WireTensor]:
         if self._views is None:
-            parsed = get_codec().parse_predict_responses([self._wire])[0]
-            buf, base = parsed.wire, parsed.offset
-            self._views = {k: WireTensor(buf[base + o.msg_off: base + o.msg_off + o.msg_len].tobytes()) for k, o in parsed.outputs.items()}
+            opened = get_codec().open_predict_response(self._wire)   # one launch decodes every fixed-width output
+            if opened is not None:
+                self._views = {k: WireTensor(opened=opened, key=k) for k in opened.table}
+            else:   # empty / malformed / more outputs than the fused launch tabulates: the two-phase path (raises like FromString)
+                parsed = get_codec().parse_predict_responses([self._wire])[0]
+                buf, base = parsed.wire, parsed.offset
+                self._views = {k: WireTensor(buf[base + o.msg_off: base + o.msg_off + o.msg_len].tobytes()) for k, o in parsed.outputs.items()}
         return self._views
 
     def to_ndarrays(self, **options) -> Dict[str, np.ndarray]:

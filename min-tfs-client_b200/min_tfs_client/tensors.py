@@ -5,7 +5,7 @@ Same public names and signatures (reference tensors.py:10-46):
 tensor_proto_to_ndarray`` - plus the TensorFlow-style aliases ``make_tensor_proto`` / ``make_ndarray``
 and byte-level entry points that skip the protobuf message object altogether.
 """
-from typing import AnyStr, Iterable, Tuple, Union
+from typing import AnyStr, Iterable, Optional, Tuple, Union
 
 import numpy as np
 from tensorflow.core.framework.tensor_pb2 import TensorProto
@@ -66,13 +66,24 @@ def tensor_proto_to_ndarray(tensor_proto: Union[TensorProto, bytes, "WireTensor"
 
 
 class WireTensor:
-    """One output of a response that is still wire bytes; decoded on demand by the GPU."""
+    """One output of a response: wire bytes, decoded on demand by the GPU - or, when the response was opened by the fused
+    decode launch (``PredictResponseView.outputs``), already decoded and handed out here."""
 
-    def __init__(self, wire: bytes):
-        self._wire = wire
+    def __init__(self, wire: Optional[bytes] = None, opened=None, key=None):
+        self._bytes, self._opened, self._key = wire, opened, key
 
-    def to_ndarray(self, **options) -> np.ndarray:
-        return get_codec().decode_tensor_protos([self._wire], **options)[0]
+    @property
+    def _wire(self) -> bytes:
+        if self._bytes is None:
+            self._bytes = self._opened.wire_of(self._key)
+        return self._bytes
+
+    def to_ndarray(self, strict: bool = False, **options) -> np.ndarray:
+        if self._opened is not None and not options:
+            arr = self._opened.array(self._key, strict)
+            if arr is not None:
+                return arr
+        return get_codec().decode_tensor_protos([self._wire], strict=strict, **options)[0]
 
     def to_proto(self) -> TensorProto:
         return TensorProto.FromString(self._wire)
