@@ -552,9 +552,12 @@ def _cpu_roundtrip(seed):
     return t1 - t0
 
 
-def cpu_baseline_port(units=2):
-    """Scalar (1 core) timing of the reference port on `units` C2 tensors."""
-    t = sum(_cpu_roundtrip(s) for s in range(units))
+def cpu_baseline_port(budget_s=12.0, max_units=64):
+    """Scalar (1 core) timing of the reference port on C2 tensors: as many whole units as fit ~budget_s of CPU work."""
+    t, units = 0.0, 0
+    while units < 2 or (t + t / units <= budget_s and units < max_units):
+        t += _cpu_roundtrip(units)
+        units += 1
     payload = units * 2 * 4194304
     return {"value": payload / t / 1e9, "unit": "GB/s", "cores": 1, "kind": "port",
             "sample": f"{units} x fp32[1024,1024] encode+decode through oracle/ref_port.py (per-element Python, protobuf upb), {t:.2f} s"}
@@ -746,7 +749,7 @@ def main():
             "roofline": roofline, "e2e": e2e, "gpu_launches": launches, "gpu_launches_outside_graphs": launches_eager, "clocks": clocks,
         }
         if world.size == 1 and not args.no_cpu:
-            cb = cpu_baseline_port(2)
+            cb = cpu_baseline_port()
             cb["c_oracle_1core_gbs"] = cpu_c_oracle(8)["value"]
             line["cpu_baseline"] = cb
         sys.stdout.flush()
