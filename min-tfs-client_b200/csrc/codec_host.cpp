@@ -306,10 +306,28 @@ struct TensorLayout {
   uint64_t header_len = 0;   // bytes before the payload
   uint32_t op = OP_COPY;     // MoveOp for fixed-width payloads
   bool varint = false;       // payload produced by the varint kernels
+  uint32_t field = 0;        // field number the values go into
+  uint64_t shape_len = 0;    // bytes of the TensorShapeProto body
   DtypeInfo src_info{}, wire_info{};
 };
 
+// the header_len bytes in front of a tensor's payload, written at w: 08 vi(dtype) 12 vi(shape_len)
+// {12 vi(dim_len) [08 vi(size)]}* [tag vi(payload_len)]
+uint8_t* write_tensor_header(const b200tfs_tensor& t, const struct TensorLayout& L, uint8_t* w) {
+  *w++ = 0x08; w += put_varint(w, (uint64_t)(uint32_t)t.wire_dtype);
+  *w++ = 0x12; w += put_varint(w, L.shape_len);
+  for (int i = 0; i < t.rank; ++i) {
+    const uint64_t d = (uint64_t)t.dims[i];
+    *w++ = 0x12;
+    if (d) { *w++ = (uint8_t)(1 + varint_len(d)); *w++ = 0x08; w += put_varint(w, d); }
+    else *w++ = 0x00;  // Dim(size=0) is an empty sub-message (Q2)
+  }
+  if (L.payload_len) { w += put_varint(w, tag_of(L.field, WT_LEN)); w += put_varint(w, L.payload_len); }
+  return w;
+}
+
 int tensor_layout(const b200tfs_tensor& t, TensorLayout* L, std::vector<uint8_t>* hdr) {
+  *L = TensorLayout{};   // layouts are reused from request to request (request_layout): no field may survive
   if (t.flags & B200TFS_F_PRESERIALIZED) {  // an already serialised TensorProto: all payload, no header
     if (t.packed_len > kProtoLimit) return fail(B200TFS_E_TOOBIG, "serialised TensorProto exceeds 2 GiB");
     L->n_elems = t.packed_len; L->payload_len = t.packed_len; L->header_len = 0; L->op = OP_COPY; L->varint = false;
@@ -361,35 +379,16 @@ int tensor_layout(const b200tfs_tensor& t, TensorLayout* L, std::vector<uint8_t>
     }
   }
   if (L->payload_len > kProtoLimit) return fail(B200TFS_E_TOOBIG, "payload of %llu bytes exceeds protobuf's 2 GiB limit", (unsigned long long)L->payload_len);
-  // header: 08 vi(dtype) 12 vi(shape_len) {12 vi(dim_len) [08 vi(size)]}* [tag vi(payload_len)]
-  uint8_t tmp[16];
-  size_t base = hdr ? hdr->size() : 0;
   uint64_t shape_len = 0;
   for (int i = 0; i < t.rank; ++i) shape_len += 2 + (t.dims[i] ? 1 + varint_len((uint64_t)t.dims[i]) : 0);
   uint64_t hl = 1 + varint_len((uint64_t)(uint32_t)t.wire_dtype) + 1 + varint_len(shape_len) + shape_len;
   if (L->payload_len) hl += varint_len(tag_of(field, WT_LEN)) + varint_len(L->payload_len);
-  L->header_len = hl;
-  if (hdr) {
-    auto put = [&](const uint8_t* p, uint32_t k) { hdr->insert(hdr->end(), p, p + k); };
-    tmp[0] = 0x08; put(tmp, 1);
-    put(tmp, put_varint(tmp, (uint64_t)(uint32_t)t.wire_dtype));
-    tmp[0] = 0x12; put(tmp, 1);
-    put(tmp, put_varint(tmp, shape_len));
-    for (int i = 0; i < t.rank; ++i) {
-      uint64_t d = (uint64_t)t.dims[i];
-      tmp[0] = 0x12; put(tmp, 1);
-      if (d) {
-        tmp[0] = (uint8_t)(1 + varint_len(d)); tmp[1] = 0x08; put(tmp, 2);
-        put(tmp, put_varint(tmp, d));
-      } else {
-        tmp[0] = 0x00; put(tmp, 1);  // Dim(size=0) is an empty sub-message (Q2)
-      }
-    }
-    if (L->payload_len) {
-      put(tmp, put_varint(tmp, tag_of(field, WT_LEN)));
-      put(tmp, put_varint(tmp, L->payload_len));
-    }
-    if (hdr->size() - base != hl) return fail(B200TFS_E_ARG, "internal: header length mismatch");
+  L->header_len = hl; L->field = field; L->shape_len = shape_len;
+  if (hdr) {   // one resize, then raw writes
+    const size_t base = hdr->size();
+    hdr->resize(base + hl);
+    if ((uint64_t)(write_tensor_header(t, *L, hdr->data() + base) - (hdr->data() + base)) != hl)
+      return fail(B200TFS_E_ARG, "internal: header length mismatch");
   }
   return B200TFS_OK;
 }
@@ -561,14 +560,23 @@ int request_layout(const b200tfs_request& r, RequestLayout* R) {
   if (r.model_name_len < 0 || (r.model_name_len && !r.model_name)) return fail(B200TFS_E_ARG, "bad model_name");
   const int n = r.n_inputs;
   R->tl.resize(n); R->perm.resize(n); R->tp_len.resize(n); R->entry_len.resize(n); R->payload_off.resize(n);
-  std::vector<const char*> keys(n);
-  std::vector<int64_t> lens(n);
+  // (no heap traffic for the usual handful of inputs: this runs once per request of a batch)
+  constexpr int kInline = 16;
+  const char* keys_in[kInline];
+  int64_t lens_in[kInline];
+  std::vector<const char*> keys_v;
+  std::vector<int64_t> lens_v;
+  const char** keys = keys_in;
+  int64_t* lens = lens_in;
+  if (n > kInline) { keys_v.resize(n); lens_v.resize(n); keys = keys_v.data(); lens = lens_v.data(); }
   for (int i = 0; i < n; ++i) {
     if (r.inputs[i].key_len < 0 || (r.inputs[i].key_len && !r.inputs[i].key)) return fail(B200TFS_E_ARG, "bad key on input %d", i);
     keys[i] = r.inputs[i].key ? r.inputs[i].key : "";
     lens[i] = r.inputs[i].key_len;
   }
-  int rc = order_keys(n, keys.data(), lens.data(), r.order, R->perm.data());
+  int rc = B200TFS_OK;
+  if (n == 1 && (r.order == B200TFS_ORDER_GIVEN || r.order == B200TFS_ORDER_UPB || r.order == B200TFS_ORDER_BYTES)) R->perm[0] = 0;
+  else rc = order_keys(n, keys, lens, r.order, R->perm.data());
   if (rc) return rc;
   // model_spec{ 0A vi name  [12 vi {08 vi(version)}] }
   uint64_t spec = 0;
@@ -605,52 +613,52 @@ int request_layout(const b200tfs_request& r, RequestLayout* R) {
   return B200TFS_OK;
 }
 
-// append the wire bytes of request r to the plan, record at arena + rec_off
+// append the wire bytes of request r to the plan, record at arena + rec_off.  Every framing byte of the request is
+// written into the blob with one resize and raw stores (this runs once per request of a batch); the tensor layouts are
+// the ones request_layout computed.
 int plan_request(const b200tfs_request& r, const RequestLayout& R, uint8_t* rec, PlanBuilder& pb) {
-  uint8_t tmp[16];
-  auto put = [&](const uint8_t* p, size_t k) { pb.blob.insert(pb.blob.end(), p, p + k); };
-  size_t mark = pb.blob.size();
-  uint8_t* cursor = rec;  // where the pending header run (blob[mark:]) will land
+  uint64_t frame = R.total;
+  for (int j = 0; j < r.n_inputs; ++j) frame -= R.tl[j].payload_len;
+  const size_t base = pb.blob.size();
+  pb.blob.resize(base + frame);
+  uint8_t* const w0 = pb.blob.data() + base;
+  uint8_t* w = w0;
+  size_t mark = base;     // blob offset where the pending header run starts
+  uint8_t* cursor = rec;  // where that run will land
   if (R.prefix) {         // gRPC length-prefixed message: compressed-flag 0, big-endian uint32 length
     const uint64_t m = R.total - R.prefix;
-    tmp[0] = 0; tmp[1] = (uint8_t)(m >> 24); tmp[2] = (uint8_t)(m >> 16); tmp[3] = (uint8_t)(m >> 8); tmp[4] = (uint8_t)m;
-    put(tmp, 5);
+    *w++ = 0; *w++ = (uint8_t)(m >> 24); *w++ = (uint8_t)(m >> 16); *w++ = (uint8_t)(m >> 8); *w++ = (uint8_t)m;
   }
-  tmp[0] = 0x0A; put(tmp, 1);
-  put(tmp, put_varint(tmp, R.spec_len));
+  *w++ = 0x0A; w += put_varint(w, R.spec_len);
   if (r.model_name_len) {
-    tmp[0] = 0x0A; put(tmp, 1);
-    put(tmp, put_varint(tmp, (uint64_t)r.model_name_len));
-    put((const uint8_t*)r.model_name, (size_t)r.model_name_len);
+    *w++ = 0x0A; w += put_varint(w, (uint64_t)r.model_name_len);
+    memcpy(w, r.model_name, (size_t)r.model_name_len); w += r.model_name_len;
   }
   if (r.has_version) {
-    tmp[0] = 0x12; tmp[1] = (uint8_t)R.version_len; put(tmp, 2);
-    if (r.version) { tmp[0] = 0x08; put(tmp, 1); put(tmp, put_varint(tmp, (uint64_t)r.version)); }
+    *w++ = 0x12; *w++ = (uint8_t)R.version_len;
+    if (r.version) { *w++ = 0x08; w += put_varint(w, (uint64_t)r.version); }
   }
   for (int j = 0; j < r.n_inputs; ++j) {
     const b200tfs_tensor& t = r.inputs[R.perm[j]];
-    tmp[0] = 0x12; put(tmp, 1);
-    put(tmp, put_varint(tmp, R.entry_len[j]));
-    tmp[0] = 0x0A; put(tmp, 1);
-    put(tmp, put_varint(tmp, (uint64_t)t.key_len));
-    if (t.key_len) put((const uint8_t*)t.key, (size_t)t.key_len);
-    tmp[0] = 0x12; put(tmp, 1);
-    put(tmp, put_varint(tmp, R.tp_len[j]));
-    TensorLayout L;
-    int rc = tensor_layout(t, &L, &pb.blob);
-    if (rc) return rc;
+    const TensorLayout& L = R.tl[j];
+    *w++ = 0x12; w += put_varint(w, R.entry_len[j]);
+    *w++ = 0x0A; w += put_varint(w, (uint64_t)t.key_len);
+    if (t.key_len) { memcpy(w, t.key, (size_t)t.key_len); w += t.key_len; }
+    *w++ = 0x12; w += put_varint(w, R.tp_len[j]);
+    if (!(t.flags & B200TFS_F_PRESERIALIZED)) w = write_tensor_header(t, L, w);
     if (L.payload_len) {
-      size_t run = pb.blob.size() - mark;
+      const size_t at = base + (size_t)(w - w0), run = at - mark;
       pb.header(cursor, mark, run);
       cursor += run;
-      if ((rc = plan_tensor(t, L, cursor, pb))) return rc;
+      int rc = plan_tensor(t, L, cursor, pb);
+      if (rc) return rc;
       cursor += L.payload_len;
-      mark = pb.blob.size();
+      mark = at;
     }
   }
-  size_t run = pb.blob.size() - mark;
+  const size_t end = base + (size_t)(w - w0), run = end - mark;
   if (run) { pb.header(cursor, mark, run); cursor += run; }
-  if ((uint64_t)(cursor - rec) != R.total) return fail(B200TFS_E_ARG, "internal: request length mismatch");
+  if ((uint64_t)(w - w0) != frame || (uint64_t)(cursor - rec) != R.total) return fail(B200TFS_E_ARG, "internal: request length mismatch");
   return B200TFS_OK;
 }
 
@@ -774,6 +782,11 @@ int b200tfs_encode_requests(b200tfs_ctx* c, int32_t n, const b200tfs_request* re
   if ((uintptr_t)arena_dev & 255) return fail(B200TFS_E_ARG, "arena must be 256-byte aligned");
   CU(cudaSetDevice(c->device));
   PlanBuilder pb;
+  if (n > 16) {   // a batch: one allocation per table instead of a doubling series
+    size_t inputs = 0;
+    for (int i = 0; i < n; ++i) inputs += (size_t)std::max(reqs[i].n_inputs, 0);
+    pb.items.reserve(inputs); pb.smalls.reserve(inputs + (size_t)n); pb.blob.reserve(64 * inputs + 48 * (size_t)n);
+  }
   RequestLayout R;
   uint64_t cursor = 0;
   for (int i = 0; i < n; ++i) {
