@@ -674,6 +674,7 @@ __global__ void __launch_bounds__(kMoveThreads, 3) decode_fused_kernel(const __g
   // chunk table in a per-thread array: it landed in local memory, 32 KB of extra DRAM traffic per CTA.)
   // The table is published by the record's LAST CTA - a slack CTA with no tile - so no tile waits on it.
   const Template* T = fp.tpl_read;
+  uint32_t live = budget;   // CTAs of this record able to take a tile, should the walk be needed
   __shared__ TplChunk ch_s[kTplChunks];
   __shared__ struct { uint32_t valid, n_chunks, n_outs, framing_len, vpt, total_tiles; uint64_t rec_len, dst_need; } th_s;
   {
@@ -707,6 +708,12 @@ __global__ void __launch_bounds__(kMoveThreads, 3) decode_fused_kernel(const __g
         if (j >= t_base && j < t_base + nt) { mine = q; break; }
         t_base += nt;
       }
+      // A slack CTA (the launch budgets kFusedSlackTiles more CTAs per record than tiles_for(len), for records whose
+      // values lie in several chunks) has nothing to do when the record carries the template's framing - and 8 of the 11
+      // CTAs of a 602 KB record are slack: leave now, before the verdict's round trip.  Should the record fail the
+      // verdict after all, the CTAs that stayed walk it; if it then needs more tiles than stayed, its status says so.
+      if (mine == kTplChunks && j != 0 && j != budget - 1) return;
+      live = max(th_s.total_tiles, 1u);
       const bool hit = verdict();
       if (hit) {
         if (mine < kTplChunks) {
@@ -727,7 +734,7 @@ __global__ void __launch_bounds__(kMoveThreads, 3) decode_fused_kernel(const __g
   }
 
   // ---- slow path: thread 0 walks the tags ----
-  if (threadIdx.x == 0) fused_slow_path(fp, r, j, budget, rec, len, dst_slot, lines, outs_s, spec_s, job);
+  if (threadIdx.x == 0) fused_slow_path(fp, r, j, live, rec, len, dst_slot, lines, outs_s, spec_s, job);
   __syncthreads();
   if (job.valid) {
     AlwaysGo go;
