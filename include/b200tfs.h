@@ -272,7 +272,12 @@ int b200tfs_unpack_outputs(b200tfs_ctx* ctx, const void* arena_dev, int32_t m, c
  * written to dst_dev + i*dst_stride, each output 256-byte aligned in table order (b200tfs_output.dst_off);
  * outputs with varint or string values are tabulated only - finish those with b200tfs_unpack_outputs.
  * At most B200TFS_FUSED_MAX_OUTPUTS outputs per record.  Asynchronous and CUDA-graph capturable;
- * collect the table afterwards with b200tfs_decode_results (which synchronises).                  */
+ * collect the table afterwards with b200tfs_decode_results (which synchronises).
+ * Each launch remembers the framing of its record 0; records of the next launch that carry the same
+ * framing skip the tag walk.  One corner is reported rather than decoded: a record that has exactly
+ * that record's LENGTH but other framing, and whose values are spread over more 32 KB..256 KB tiles
+ * than that record's, gets B200TFS_E_NONCANONICAL; decode it with the next launch (which starts
+ * without a remembered framing) or with b200tfs_parse_responses + b200tfs_unpack_outputs.          */
 #define B200TFS_FUSED_MAX_OUTPUTS 8
 int b200tfs_decode_responses(b200tfs_ctx* ctx, const void* arena_dev, int32_t n, const uint64_t* rec_off,
                              const uint64_t* rec_len, void* dst_dev, uint64_t dst_stride);

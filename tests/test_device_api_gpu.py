@@ -132,6 +132,53 @@ def test_fused_decode_c2(dev):
     assert dev.download(dst + outs[0].dst_off, 2 << 20).tobytes() == x2[:512].tobytes()
 
 
+def _vi(v):
+    out = bytearray()
+    while v >= 0x80:
+        out.append((v & 0x7F) | 0x80)
+        v >>= 7
+    out.append(v)
+    return bytes(out)
+
+
+def _response_with_chunks(key, x, cuts):
+    """PredictResponse bytes whose float_val values lie in several packed occurrences (cuts = element indices)."""
+    raw = x.tobytes()
+    tp = b"\x08\x01" + b"\x12" + _vi(2 + len(_vi(x.size)) + 1) + b"\x12" + _vi(1 + len(_vi(x.size))) + b"\x08" + _vi(x.size)
+    for a, b in zip([0] + cuts, cuts + [x.size]):
+        tp += b"\x2a" + _vi(4 * (b - a)) + raw[4 * a: 4 * b]
+    entry = b"\x0a" + _vi(len(key)) + key + b"\x12" + _vi(len(tp)) + tp
+    spec = b"\x0a\x07default\x12\x02\x08\x01\x1a\x0fserving_default"
+    return b"\x0a" + _vi(len(entry)) + entry + b"\x12" + _vi(len(spec)) + spec
+
+
+def test_fused_decode_same_length_other_framing_needs_more_tiles(dev, codec):
+    """The launch budgets slack CTAs per record; when a record has the template's length they leave before the verdict.
+    A record of the SAME length whose framing differs and whose values need MORE tiles than the template's then cannot be
+    covered: it must say so (B200TFS_E_NONCANONICAL), never decode wrongly; the two-phase path and the Python codec (which
+    falls back to it) decode it; and the next fused launch, with no valid template, covers it again."""
+    rng = np.random.default_rng(21)
+    a = rng.standard_normal(20000).astype(np.float32)            # 80000 B in one chunk: 3 tiles of 32 KB
+    b = rng.standard_normal(19999).astype(np.float32)            # 40000 + 39996 B in two chunks: 2 + 2 tiles
+    wa = _response_with_chunks(b"k", a, [])
+    wb = _response_with_chunks(b"k", b, [10000])
+    assert wa == wire_oracle.build_predict_response([("k", a)]) and len(wa) == len(wb)
+    assert wire_oracle.decode_predict_response(wb)["k"].tobytes() == b.tobytes()
+    stride = 1 << 17
+    for _ in range(2):                                           # learn the template, then take the fast path
+        buf, dst, outs, n_outs, specs, status = _decode_fused(dev, [wa], stride)
+        assert status[0] == 0 and dev.download(dst + outs[0].dst_off, a.nbytes).tobytes() == a.tobytes()
+    buf, dst, outs, n_outs, specs, status = _decode_fused(dev, [wb], stride)
+    assert status[0] == N.E_NONCANONICAL
+    buf, dst, outs, n_outs, specs, status = _decode_fused(dev, [wb], stride)   # that launch left no valid template
+    assert status[0] == 0 and n_outs[0] == 1 and outs[0].n_chunks == 2
+    assert dev.download(dst + outs[0].dst_off, b.nbytes).tobytes() == b.tobytes()
+    # the Python codec: same sequence, the second message comes out right (two-phase fallback)
+    assert codec.decode_predict_response(wa)[0]["k"].tobytes() == a.tobytes()
+    assert codec.decode_predict_response(wa)[0]["k"].tobytes() == a.tobytes()
+    assert codec.decode_predict_response(wb)[0]["k"].tobytes() == b.tobytes()
+
+
 def test_fused_decode_batch_256(dev):
     """256 responses {scores fp32[1000]} (BASELINE configs[2] outputs): the n > 16 table path."""
     wires, refs = [], []
