@@ -257,6 +257,38 @@ def test_varint_tile_geometry_chunks_and_malformed(codec):
     assert codec.decode_tensor_protos([ten], strict=True)[0].tolist() == [-1] == wire_oracle.decode_tensor_proto(ten).tolist()
 
 
+def test_varint_randomised_magnitudes_and_sizes(codec):
+    """40 random varint tensors: dtype of the int_val / int64_val / uint32_val / uint64_val family, 1 to ~400k elements,
+    value magnitudes drawn per tensor (all one byte, token-id-like, mixed bit lengths, full range with negatives), random
+    key length (alignment of the chunk on the wire).  Encode byte for byte and decode element for element vs the oracle."""
+    from oracle import wire_oracle
+
+    rng = np.random.default_rng(77)
+    dts = [np.int8, np.int16, np.int32, np.int64, np.uint8, np.uint16, np.uint32, np.uint64]
+    for it in range(40):
+        dt = dts[int(rng.integers(len(dts)))]
+        info = np.iinfo(dt)
+        n = int(np.exp(rng.uniform(0, np.log(400000))))
+        kind = int(rng.integers(4))
+        if kind == 0:
+            x = rng.integers(0, 128, size=n, dtype=np.int64)
+        elif kind == 1:
+            x = rng.integers(0, 50000, size=n, dtype=np.int64)
+        elif kind == 2:
+            x = (rng.integers(0, 2 ** 62, size=n, dtype=np.int64) >> rng.integers(0, 62, size=n))
+        else:
+            x = rng.integers(-2 ** 62, 2 ** 62, size=n, dtype=np.int64)
+        if info.min < 0 and kind >= 2:
+            x[:: 3] = -x[:: 3]
+        x = (x.view(np.uint64) & np.uint64(info.max)).astype(dt) if info.min == 0 else np.clip(x, info.min, info.max).astype(dt)
+        key = "k" * int(rng.integers(0, 20))
+        wire = codec.encode_predict_requests([("m", 1, [(key, x)])])[0]
+        assert wire == wire_oracle.encode_predict_request("m", 1, [(key, x)]), (it, dt, n, kind)
+        resp = wire_oracle.build_predict_response([(key, x)])
+        got = codec.decode_predict_response(resp, strict=True)[0][key]
+        assert got.dtype == x.dtype and got.tobytes() == x.tobytes(), (it, dt, n, kind)
+
+
 def test_modes_tensor_content_and_keep_snan(codec):
     """The two non-default encode modes against the oracle: tensor_content (TF's own layout, raw little-endian
     memory for every numeric dtype) and KEEP_SNAN (typed field, float32 bits untouched); and the tolerant decoder
