@@ -179,6 +179,53 @@ def test_fused_decode_same_length_other_framing_needs_more_tiles(dev, codec):
     assert codec.decode_predict_response(wb)[0]["k"].tobytes() == b.tobytes()
 
 
+def test_fused_decode_staged_batch_variety(dev):
+    """Batches above ~38 MB of wire get tiles of several 32 KB chunks and the TMA-staged kernel: every source alignment (key
+    lengths 0..15 shift the payload byte by byte), float32 (quieting) and float64, two outputs per record, values split over
+    two chunks (destination head not 16-aligned: the register path inside the staged kernel), a record of another length and
+    a malformed one (the walk inside the staged kernel).  Twice: the second launch takes the template path for record 0's
+    look-alikes."""
+    rng = np.random.default_rng(31)
+    wires, refs = [], []
+    for i in range(72):
+        key = b"k" * (i % 16)
+        if i % 9 == 4:
+            x = rng.standard_normal(75000)                                   # float64, 600 KB
+        else:
+            x = rng.integers(0, 2 ** 32, size=150000, dtype=np.uint64).astype(np.uint32).view(np.float32)   # every kind of NaN
+        if i % 9 == 7:
+            y = rng.standard_normal(1000).astype(np.float32)
+            w = wire_oracle.build_predict_response([(key.decode() or "x", x), ("second", y)], keep_snan=True)
+        elif i % 9 == 2 and x.dtype == np.float32:
+            w = _response_with_chunks(key or b"x", x, [50001])
+        elif i == 40:
+            w = wire_oracle.build_predict_response([("short", x[:1234])], keep_snan=True)
+        else:
+            w = wire_oracle.build_predict_response([(key.decode() or "x", x)], keep_snan=True)
+        if i == 41:
+            w = w[:-2]
+        wires.append(w)
+        refs.append(None if i == 41 else wire_oracle.decode_predict_response(w))
+    assert sum(len(w) for w in wires) > 40 << 20
+    stride = 1 << 20
+    for _ in range(2):
+        buf, dst, outs, n_outs, specs, status = _decode_fused(dev, wires, stride)
+        whole = dev.download(dst, stride * len(wires))
+        off = 0
+        for i, w in enumerate(wires):
+            if refs[i] is None:
+                assert status[i] == N.E_PARSE
+            else:
+                assert status[i] == 0 and n_outs[i] == len(refs[i]), i
+                for q in range(n_outs[i]):
+                    o = outs[i * N.FUSED_MAX_OUTPUTS + q]
+                    key = buf[off + o.key_off: off + o.key_off + o.key_len].tobytes().decode()
+                    want = refs[i][key]
+                    got = whole[i * stride + o.dst_off: i * stride + o.dst_off + o.dst_bytes]
+                    assert o.dst_bytes == want.nbytes and got.tobytes() == want.tobytes(), (i, key)
+            off += (len(w) + 255) & ~255
+
+
 def test_fused_decode_batch_256(dev):
     """256 responses {scores fp32[1000]} (BASELINE configs[2] outputs): the n > 16 table path."""
     wires, refs = [], []
