@@ -127,11 +127,39 @@ class ClockSampler:
 # ------------------------------------------------------------------------------------------------
 # distributed plumbing (control plane only)
 # ------------------------------------------------------------------------------------------------
+def bind_to_gpu_numa_node(gpu_index):
+    """Run this process on the CPUs of the NUMA node its GPU hangs off, so that the pinned host buffers of the e2e leg are
+    first-touched there and the PCIe copies do not cross the socket interconnect (what `numactl --cpunodebind` would do
+    per rank).  Returns a description for the bench line; does nothing when the topology cannot be read
+    (B200TFS_BENCH_NUMA=0 turns it off)."""
+    if os.environ.get("B200TFS_BENCH_NUMA", "1") == "0":
+        return "off"
+    try:
+        out = subprocess.run(["nvidia-smi", "--query-gpu=pci.bus_id", "--format=csv,noheader", "-i", str(gpu_index)],
+                             capture_output=True, text=True, timeout=20).stdout.strip().lower()
+        bdf = out[-12:] if len(out) >= 12 else out            # 00000000:1B:00.0 -> 0000:1b:00.0
+        node = int(open(f"/sys/bus/pci/devices/{bdf}/numa_node").read())
+        if node < 0:
+            return "unknown node"
+        cpus = set()
+        for part in open(f"/sys/devices/system/node/node{node}/cpulist").read().strip().split(","):
+            lo, _, hi = part.partition("-")
+            cpus.update(range(int(lo), int(hi or lo) + 1))
+        cpus &= os.sched_getaffinity(0)
+        if not cpus:
+            return "no cpus allowed on node"
+        os.sched_setaffinity(0, cpus)
+        return f"node {node} ({len(cpus)} cpus)"
+    except Exception as e:  # noqa: BLE001 - best effort
+        return f"unavailable ({type(e).__name__})"
+
+
 class World:
     def __init__(self):
         self.rank = int(os.environ.get("RANK", "0"))
         self.local_rank = int(os.environ.get("LOCAL_RANK", "0"))
         self.size = int(os.environ.get("WORLD_SIZE", "1"))
+        self.numa = bind_to_gpu_numa_node(self.local_rank)
         self.dist = None
         self.torch = None
         if self.size > 1:
@@ -745,7 +773,7 @@ def main():
                        "l2": f"inputs rotate through a ring of {bench.ring.slots} slots = {bench.footprint() >> 20} MiB > 126 MiB L2 "
                              "(timed region and roofline pass alike)",
                        "streams": len(bench.lanes), "cuda_graph_steps": args.graph_steps,
-                       "wire_mode": "typed (float_val, sNaN-quieting on: bit-exact vs reference)", "sharding": "independent requests per GPU, no collective"},
+                       "wire_mode": "typed (float_val, sNaN-quieting on: bit-exact vs reference)", "sharding": "independent requests per GPU, no collective", "cpu_binding": world.numa},
             "roofline": roofline, "e2e": e2e, "gpu_launches": launches, "gpu_launches_outside_graphs": launches_eager, "clocks": clocks,
         }
         if world.size == 1 and not args.no_cpu:
