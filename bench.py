@@ -638,13 +638,14 @@ def run_reference(args, world):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=48000)
-    ap.add_argument("--warmup", type=int, default=480)
+    ap.add_argument("--steps", type=int, default=100, help="timed steps; one step = one batch of --batch request/response pairs")
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--batch", type=int, default=480, help="C2 PredictRequest/PredictResponse pairs per step (spread over the lanes)")
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--ring", type=int, default=48, help="ring slots in total (split over the streams)")
     ap.add_argument("--streams", type=int, default=16, help="independent lanes (native contexts = CUDA streams) per GPU")
     ap.add_argument("--graph-steps", type=int, default=48, help="steps recorded per CUDA graph")
-    ap.add_argument("--e2e-steps", type=int, default=200)
+    ap.add_argument("--e2e-steps", type=int, default=200, help="request/response PAIRS timed by the e2e leg")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     args = ap.parse_args()
     if args.impl == "reference":   # CPU only: rank 0 works alone, nobody needs a process group
@@ -657,12 +658,14 @@ def main():
     os.dup2(2, 1)
     world = World()
     warmup = max(args.warmup, 3)
+    batch = max(args.batch, 1)
+    pairs = args.steps * batch                     # a step is a batch of `batch` independent pairs: K steps = K * batch pairs
     bench = C2Bench(world.local_rank, args.ring, args.streams)
     assert bench.footprint() > 2 * L2_BYTES, "ring must exceed L2"
     bench.verify()
-    bench.prepare(warmup, args.graph_steps)
+    bench.prepare(warmup * batch, args.graph_steps)
     bench.run_steps()                              # W untimed warm-up steps
-    bench.prepare(args.steps, args.graph_steps)    # graphs sized so that exactly K steps run
+    bench.prepare(pairs, args.graph_steps)         # graphs sized so that exactly K steps run
     bench.run_steps()                              # one untimed pass so the new graphs are uploaded
     launches0 = bench.launches()
     sampler = ClockSampler(world.local_rank)
@@ -675,11 +678,12 @@ def main():
     world.barrier()
     clocks = sampler.stop(t0, t1)
     launches_eager = bench.launches() - launches0  # graph replays do not pass through the counter ...
-    launches = 2 * args.steps                      # ... each step replays one move_kernel + one decode_fused_kernel
+    launches = 2 * pairs                           # ... each pair replays one move_kernel + one decode_fused_kernel
     ms_max = world.max(ms)
     S = bench.S
-    payload_per_step = 2 * S.P
-    total_payload = world.sum(float(payload_per_step * args.steps))
+    payload_per_pair = 2 * S.P
+    payload_per_step = payload_per_pair * batch
+    total_payload = world.sum(float(payload_per_pair * pairs))
     value = total_payload / (ms_max * 1e-3) / 1e9
     enc_bytes, dec_bytes = 2 * S.P + S.H_req, 2 * S.P + S.H_resp
     peak, peak_src = peaks()
@@ -698,7 +702,7 @@ def main():
         per[name] = t / (reps * m.graphs[name][1]) * 1e3  # us per launch
     avg_us = (per["enc"] + per["dec"]) / 2
     achieved = (enc_bytes + dec_bytes) / 2 / (avg_us * 1e-6) / 1e9
-    agg = (enc_bytes + dec_bytes) * args.steps / (ms * 1e-3) / 1e9
+    agg = (enc_bytes + dec_bytes) * pairs / (ms * 1e-3) / 1e9
     traffic, traffic_src = ncu_traffic()
     roofline = {"bound": "hbm", "kernel": "move_kernel (encode) / decode_fused_kernel (decode)", "achieved": achieved, "peak": peak,
                 "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
@@ -721,7 +725,7 @@ def main():
     for _ in range(8):
         bench.step_e2e()
     bench.e2e_drain()
-    e2e_steps = max(10, min(args.e2e_steps, args.steps))
+    e2e_steps = max(10, min(args.e2e_steps, pairs))    # pairs, not steps: the leg is PCIe-bound, 200 pairs are 50 ms
     world.barrier()
     def e2e_region(l):
         if l is bench.main:
@@ -729,13 +733,13 @@ def main():
                 bench.step_e2e()
             bench.e2e_drain()
     e2e_ms = world.max(bench.timed_region(e2e_region))
-    e2e_value = world.sum(float(payload_per_step * e2e_steps)) / (e2e_ms * 1e-3) / 1e9
-    e2e = {"value": e2e_value, "unit": "GB/s", "h2d_bytes_per_step": S.P + S.resp_len, "d2h_bytes_per_step": S.P + S.H_req + S.P,
-           "ms_per_step": e2e_ms / e2e_steps, "steps": e2e_steps,
+    e2e_value = world.sum(float(payload_per_pair * e2e_steps)) / (e2e_ms * 1e-3) / 1e9
+    e2e = {"value": e2e_value, "unit": "GB/s", "h2d_bytes_per_step": (S.P + S.resp_len) * batch, "d2h_bytes_per_step": (S.P + S.H_req + S.P) * batch,
+           "ms_per_step": e2e_ms / e2e_steps * batch, "pairs_timed": e2e_steps, "pairs_per_step": batch,
            "in_flight": bench.e2e_depth,
            "how": "b200tfs_encode_requests_host_async + b200tfs_decode_responses_host_async / b200tfs_decode_results on pinned host "
-                  "buffers; every step copies its tensor and its response wire H2D and its request wire and decoded tensor D2H "
-                  f"(4 x ~4 MiB over PCIe); up to {bench.e2e_depth} steps in flight so the two copy directions overlap"}
+                  "buffers; every pair copies its tensor and its response wire H2D and its request wire and decoded tensor D2H "
+                  f"(4 x ~4 MiB over PCIe); up to {bench.e2e_depth} pairs in flight so the two copy directions overlap"}
 
     # the drop-in Python API on ordinary numpy arrays / bytes objects (pageable memory, bytes copies): reported, not the headline
     py_api = None
@@ -756,7 +760,7 @@ def main():
                 codec.encode_predict_request("default", {"x": x}, 1)
                 codec.decode_predict_response(resp_bytes)
             dt = (time.perf_counter() - t0) / reps
-            py_api = {"value": payload_per_step / dt / 1e9, "unit": "GB/s", "ms_per_step": dt * 1e3,
+            py_api = {"value": payload_per_pair / dt / 1e9, "unit": "GB/s", "ms_per_pair": dt * 1e3,
                       "how": "min_tfs_client.codec.Codec.encode_predict_request + decode_predict_response on numpy arrays and bytes (wall clock)"}
             codec.close()
         except Exception as exc:  # pragma: no cover
@@ -769,7 +773,8 @@ def main():
             "warmup": warmup, "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "u8", "data": "synthetic",
             "config": {"workload": "C2 fp32[1024,1024] single-tensor PredictRequest encode + PredictResponse decode (BASELINE.json configs[1])",
-                       "payload_bytes_per_step": payload_per_step, "ring_slots": bench.ring.slots, "ring_bytes": bench.footprint(),
+                       "step": f"one batch of {batch} independent request/response pairs, spread over the lanes",
+                       "pairs_per_step": batch, "payload_bytes_per_step": payload_per_step, "ring_slots": bench.ring.slots, "ring_bytes": bench.footprint(),
                        "l2": f"inputs rotate through a ring of {bench.ring.slots} slots = {bench.footprint() >> 20} MiB > 126 MiB L2 "
                              "(timed region and roofline pass alike)",
                        "streams": len(bench.lanes), "cuda_graph_steps": args.graph_steps,
