@@ -9,6 +9,9 @@
 //                      and writes the header fragments (tags, varint lengths, dims, keys).
 //   decode_fused_kernel    a whole PredictResponse decode in one launch: framing-template check or
 //                      tag walk (walker.h), destination layout, tile move, table to pinned host memory.
+//   decode_fused_staged_kernel   the same for big batches (tiles of several 32 KB chunks): the tile's
+//                      source bytes arrive by TMA 1-D bulk copies (cp.async.bulk global -> shared, two
+//                      buffers, mbarrier completion) issued ahead of the template verdict.
 //   parse_*_kernel     two-phase decode: one lane per PredictResponse / TensorProto walks the tags and
 //                      tabulates dtype, dims and where the values lie.
 //   venc_* / vdec_*    packed-varint encode and decode (int_val / int64_val / uint32_val / uint64_val /
