@@ -85,6 +85,11 @@ extern "C" {
 #define B200TFS_OF_HAS_UNKNOWN 0x8u    /* unknown fields were skipped inside this entry                           */
 #define B200TFS_OF_RANK0 0x10u         /* no dims: the reference raises TypeError here (reshape() with no args)   */
 #define B200TFS_OF_VARINT 0x20u        /* values are packed varints: element count is checked while unpacking    */
+#define B200TFS_OF_PAD_EDGE 0x40u      /* set by the CALLER of b200tfs_unpack_outputs on an output tabulated with
+                                          B200TFS_E_SHAPE (or on any B200TFS_OF_VARINT output, whose element count only the
+                                          decode kernels learn): TensorFlow's MakeNdarray convention (tensor_util.py:636-642 in
+                                          the reference's vendored tree) - fewer values than the shape holds: the last one
+                                          repeats; no values at all: zeros.  More values than the shape holds stays an error */
 
 /* map-entry order for requests with several inputs */
 #define B200TFS_ORDER_GIVEN 0 /* emit in the order of b200tfs_request.inputs                                     */

@@ -880,6 +880,7 @@ struct VarDecodeJob {
   int32_t dtype;
   int32_t out_index;
   bool half_as_value;
+  bool pad_edge;   // fewer values than elements: repeat the last one (B200TFS_OF_PAD_EDGE)
 };
 
 int run_vardecode(b200tfs_ctx* c, std::vector<VarDecodeJob>& jobs, int32_t* status);  // below
@@ -900,13 +901,19 @@ static int unpack_outputs_impl(b200tfs_ctx* c, const void* arena_dev, int32_t m,
   CU(cudaSetDevice(c->device));
   PlanBuilder pb;
   std::vector<VarDecodeJob> vjobs;
+  struct Fill { uint8_t* dst; uint32_t elem_size; uint64_t have, n_elems; };
+  std::vector<Fill> fills;   // B200TFS_OF_PAD_EDGE on fixed-width outputs: pad once the values are in place
   for (int j = 0; j < m; ++j) {
     const b200tfs_output& o = outs[j];
     const uint8_t* w = (const uint8_t*)arena_dev + (out_rec_off ? out_rec_off[j] : 0);  // table offsets are record-relative
     if (status) status[j] = B200TFS_OK;
     if (!o.n_elems) continue;
     const bool content_only = o.n_chunks == 0 && o.content_len && o.content_len == o.dst_bytes;
-    if (o.status != B200TFS_OK && !content_only)
+    // TF's MakeNdarray convention, asked for by the caller.  For packed varints the table cannot know the element count
+    // (status OK unless there are fewer value BYTES than elements): the flag then tells the decode kernels to tolerate it.
+    const bool pad = (o.flags & B200TFS_OF_PAD_EDGE) &&
+                     (o.status == B200TFS_E_SHAPE || (o.status == B200TFS_OK && (o.flags & B200TFS_OF_VARINT)));
+    if (o.status != B200TFS_OK && !content_only && !pad)
       return fail(B200TFS_E_ARG, "output %d was tabulated with status %d: nothing to unpack", j, o.status);
     DtypeInfo di = dtype_info(o.dtype);
     if (di.kind == VK_NONE || di.kind == VK_STRING) return fail(B200TFS_E_DTYPE, "output %d: dtype %d has no device payload", j, o.dtype);
@@ -915,6 +922,11 @@ static int unpack_outputs_impl(b200tfs_ctx* c, const void* arena_dev, int32_t m,
     const bool half_as_value = (want == B200TFS_DT_HALF_REFQUIRK && o.dtype == DT_HALF);
     if (half_as_value) want = DT_HALF;
     uint8_t* dst = (uint8_t*)dst_dev[j];
+    if (pad && want != o.dtype) return fail(B200TFS_E_DTYPE, "output %d: cast together with padding is not supported", j);
+    if (o.n_chunks == 0 && pad && !content_only) {   // no values at all: zeros
+      CU(cudaMemsetAsync(dst, 0, o.dst_bytes, c->stream));
+      continue;
+    }
     if (o.n_chunks == 0) {
       // tolerant path chosen by the caller: raw little-endian bytes from tensor_content
       if (o.content_len != o.dst_bytes) return fail(B200TFS_E_SHAPE, "output %d: no values (tensor_content %llu bytes, need %llu)", j,
@@ -935,17 +947,23 @@ static int unpack_outputs_impl(b200tfs_ctx* c, const void* arena_dev, int32_t m,
         pb.payload(w + o.chunk_off[k], dst + run, o.chunk_len[k] * num / den, op);
         run += o.chunk_len[k] * num / den;
       }
+      if (pad) {
+        if (run % di.elem_size || run > o.dst_bytes) return fail(B200TFS_E_SHAPE, "output %d: %llu value bytes for a tensor of %llu", j,
+                                                                  (unsigned long long)run, (unsigned long long)o.dst_bytes);
+        fills.push_back(Fill{dst, di.elem_size, run / di.elem_size, o.n_elems});
+      }
     } else {  // packed varints (incl. bool_val)
       if (want != o.dtype) return fail(B200TFS_E_DTYPE, "output %d: cast on varint dtypes is not supported", j);
       VarDecodeJob vj{};
       vj.n_chunks = o.n_chunks;
       for (int k = 0; k < o.n_chunks; ++k) { vj.src[k] = w + o.chunk_off[k]; vj.len[k] = o.chunk_len[k]; }
-      vj.dst = dst; vj.n_elems = o.n_elems; vj.dtype = o.dtype; vj.out_index = j; vj.half_as_value = half_as_value;
+      vj.dst = dst; vj.n_elems = o.n_elems; vj.dtype = o.dtype; vj.out_index = j; vj.half_as_value = half_as_value; vj.pad_edge = pad;
       vjobs.push_back(vj);
     }
   }
   int rc = launch_plan(c, pb);
   if (rc) return rc;
+  for (const Fill& f : fills) { CU(launch_fill_edge(f.dst, f.elem_size, f.have, nullptr, f.n_elems, c->stream)); c->launches += 1; }
   c->pending_status.clear();
   if (!vjobs.empty()) {
     if ((rc = run_vardecode(c, vjobs, status))) return rc;

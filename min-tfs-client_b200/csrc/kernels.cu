@@ -27,6 +27,7 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <algorithm>
 #include <utility>
 
 #include "kernels.h"
@@ -910,6 +911,21 @@ __global__ void __launch_bounds__(kMoveThreads, 3) decode_fused_staged_kernel(co
 // ------------------------------------------------------------------------------------------------
 #include "varint_kernels.cuh"
 
+// TensorFlow's MakeNdarray padding (B200TFS_OF_PAD_EDGE): elements [have, n_elems) of dst take the value of element
+// have-1, or zero when there is none.  `have` comes from the host (fixed-width values: known from the chunk lengths) or
+// from device memory (packed varints: the terminator count the decode kernels just produced).
+__global__ void __launch_bounds__(256) fill_edge_kernel(uint8_t* __restrict__ dst, uint32_t elem_size, uint64_t have_imm,
+                                                        const unsigned long long* __restrict__ have_dev, uint64_t n_elems) {
+  const uint64_t have = have_dev ? (uint64_t)*have_dev : have_imm;
+  if (have >= n_elems) return;
+  uint8_t last[16];
+#pragma unroll
+  for (uint32_t b = 0; b < 16; ++b) last[b] = (have && b < elem_size) ? dst[(have - 1) * elem_size + b] : (uint8_t)0;
+  for (uint64_t i = have + blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n_elems; i += (uint64_t)gridDim.x * blockDim.x)
+#pragma unroll
+    for (uint32_t b = 0; b < 16; ++b) if (b < elem_size) dst[i * elem_size + b] = last[b];
+}
+
 // ------------------------------------------------------------------------------------------------
 // launchers (the only symbols codec_host.cpp sees)
 // ------------------------------------------------------------------------------------------------
@@ -957,6 +973,14 @@ cudaError_t launch_parse_tensors(const uint8_t* w, const uint64_t* rec_off, cons
 }
 
 uint32_t tiles_for_host(uint64_t n_out, uint32_t vpt) { return tiles_for(n_out, vpt); }
+
+cudaError_t launch_fill_edge(uint8_t* dst, uint32_t elem_size, uint64_t have, const unsigned long long* have_dev, uint64_t n_elems,
+                             cudaStream_t stream) {
+  if (!n_elems) return cudaSuccess;
+  const uint64_t blocks = std::min<uint64_t>((n_elems + 255) / 256, 148 * 8);
+  fill_edge_kernel<<<(uint32_t)blocks, 256, 0, stream>>>(dst, elem_size, have, have_dev, n_elems);
+  return cudaGetLastError();
+}
 
 cudaError_t launch_decode_fused(const FusedParams& fp, uint32_t grid, cudaStream_t stream) {
   if (!grid) return cudaSuccess;

@@ -21,6 +21,9 @@ cudaError_t launch_parse_tensors(const uint8_t* w, const uint64_t* rec_off, cons
 
 cudaError_t launch_decode_fused(const FusedParams& fp, uint32_t grid, cudaStream_t stream);
 uint32_t tiles_for_host(uint64_t n_out, uint32_t vpt);
+// pad elements [have, n_elems) of dst with element have-1 (zeros if have == 0); have from the host or, if have_dev, the device
+cudaError_t launch_fill_edge(uint8_t* dst, uint32_t elem_size, uint64_t have, const unsigned long long* have_dev, uint64_t n_elems,
+                             cudaStream_t stream);
 // packed varints (varint_kernels.cuh): the tables and counters every kernel uses are addressed through VarTables
 cudaError_t launch_venc_len(const VarTables& tb, cudaStream_t stream);
 cudaError_t launch_venc_emit(const VarTables& tb, cudaStream_t stream);

@@ -100,6 +100,7 @@ constexpr uint32_t kVarPerThread = 8;
 constexpr uint32_t kVarTileElems = kVarThreads * kVarPerThread;  // elements per encode tile
 constexpr uint32_t kVarTileBytes = kVarThreads * 32;             // wire bytes per decode tile; tiles are cut at 16-byte-aligned ADDRESSES
 constexpr int32_t kVarFlagHalfAsValue = 1;  // decode half_val ints as VALUES (the reference's DT_HALF quirk)
+constexpr int32_t kVarFlagPadEdge = 2;      // fewer values than elements is not an error: the caller pads (B200TFS_OF_PAD_EDGE)
 
 struct VarSeg {       // a contiguous run of one job: the whole tensor (encode) or one wire chunk (decode)
   const uint8_t* src;

@@ -401,7 +401,7 @@ __global__ void __launch_bounds__(kVarThreads) vdec_emit_kernel(const __grid_con
   VarSeg sg;
   VarJobDev jb;
   fetch_tile(tb, t, sg, jb);
-  if (*jb.total != jb.n_elems) {  // element count != prod(shape): reshape() would raise
+  if ((jb.flags & kVarFlagPadEdge) ? *jb.total > jb.n_elems : *jb.total != jb.n_elems) {  // element count != prod(shape): reshape() would raise
     if (threadIdx.x == 0) *jb.status = B200TFS_E_SHAPE;
     return;
   }

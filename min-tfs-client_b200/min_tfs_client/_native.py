@@ -23,7 +23,7 @@ F_TENSOR_CONTENT = 0x1
 F_KEEP_SNAN = 0x2
 F_PRESERIALIZED = 0x4
 RF_GRPC_FRAME = 0x1
-OF_TENSOR_CONTENT, OF_MULTI_CHUNK, OF_DIM_INFERRED, OF_HAS_UNKNOWN, OF_RANK0, OF_VARINT = 0x1, 0x2, 0x4, 0x8, 0x10, 0x20
+OF_TENSOR_CONTENT, OF_MULTI_CHUNK, OF_DIM_INFERRED, OF_HAS_UNKNOWN, OF_RANK0, OF_VARINT, OF_PAD_EDGE = 0x1, 0x2, 0x4, 0x8, 0x10, 0x20, 0x40
 ORDER_GIVEN, ORDER_UPB, ORDER_BYTES = 0, 1, 2
 MAX_RANK, MAX_CHUNKS, FUSED_MAX_OUTPUTS = 16, 8, 8
 DT_HALF_REFQUIRK = -19

@@ -345,6 +345,11 @@ class Codec:
         content_only = o.n_chunks == 0 and o.content_len and o.n_strings == 0
         if content_only and not strict and o.content_len == int(np.prod(shape, dtype=np.int64)) * np.dtype(np_type).itemsize:
             pass  # tolerant: raw little-endian tensor_content, as TF writes it
+        elif o.status == N.E_SHAPE and not strict and out_dtype is None and self._may_pad(o, np_type):
+            # tolerant: TensorFlow's MakeNdarray padding - no values: zeros; fewer than the shape holds: the last one repeats
+            o.flags |= N.OF_PAD_EDGE
+        elif o.status == N.OK and not strict and out_dtype is None and (o.flags & N.OF_VARINT) and o.n_elems > 0:
+            o.flags |= N.OF_PAD_EDGE   # packed varints: whether there are fewer values than elements is only known to the decode kernels
         elif o.status == N.E_SHAPE:
             raise ValueError(f"cannot reshape array into shape {shape}")
         elif o.status == N.E_NONCANONICAL:
@@ -360,6 +365,18 @@ class Codec:
         elif strict and enum == DT_HALF:
             dst_code = N.DT_HALF_REFQUIRK
         return np_type, dst_code, shape
+
+    @staticmethod
+    def _may_pad(o: N.Output, np_type) -> bool:
+        """An E_SHAPE output the padding rule applies to: the shape is fully known and holds MORE elements than there are
+        values (packed varints: more elements than value bytes would be needed; the kernel then counts exactly)."""
+        if o.n_elems <= 0 or o.content_len or any(o.dims[k] < 0 for k in range(o.rank)):
+            return False
+        value_bytes = sum(int(o.chunk_len[k]) for k in range(o.n_chunks))
+        if o.flags & N.OF_VARINT:
+            return True     # fewer value bytes than elements was what raised E_SHAPE here; a surplus is caught by the decode kernels
+        size = np.dtype(np_type).itemsize
+        return value_bytes % size == 0 and value_bytes // size < o.n_elems
 
     def decode_predict_responses(self, wires: Sequence[bytes], *, strict: bool = False, out_dtypes: Optional[Mapping] = None,
                                  max_outputs: int = 16) -> List[Tuple[Dict[str, np.ndarray], DecodedSpec]]:

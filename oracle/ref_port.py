@@ -94,6 +94,43 @@ def decode_tensor_proto(wire: bytes):
     return from_tensor_proto(tensor_pb2.TensorProto.FromString(wire))
 
 
+def make_ndarray_tf(wire: bytes) -> np.ndarray:
+    """TensorFlow's MakeNdarray for the numeric typed fields, restated over the protobuf runtime from the reference's vendored
+    protobuf_srcs/tensorflow/python/framework/tensor_util.py:565-642: tensor_content wins; else the typed field; no values ->
+    zeros; fewer values than the shape holds -> np.pad(..., "edge").  Pins the tolerant decoder's padding rule."""
+    tp = tensor_pb2.TensorProto.FromString(wire)
+    shape = [d.size for d in tp.tensor_shape.dim]
+    n = int(np.prod(shape, dtype=np.int64))
+    dt = np.dtype({1: "float32", 2: "float64", 3: "int32", 4: "uint8", 5: "int16", 6: "int8", 9: "int64", 10: "bool", 17: "uint16",
+                   22: "uint32", 23: "uint64", 19: "float16", 8: "complex64", 18: "complex128"}[tp.dtype])
+    if tp.tensor_content:
+        return np.frombuffer(tp.tensor_content, dtype=dt).copy().reshape(shape)
+    if tp.dtype == 19:
+        values = np.fromiter(tp.half_val, dtype=np.uint16).view(np.float16)
+    elif tp.dtype == 1:
+        values = np.fromiter(tp.float_val, dtype=dt)
+    elif tp.dtype == 2:
+        values = np.fromiter(tp.double_val, dtype=dt)
+    elif tp.dtype in (3, 4, 5, 6, 17):
+        values = np.fromiter(tp.int_val, dtype=dt)
+    elif tp.dtype == 9:
+        values = np.fromiter(tp.int64_val, dtype=dt)
+    elif tp.dtype == 22:
+        values = np.fromiter(tp.uint32_val, dtype=dt)
+    elif tp.dtype == 23:
+        values = np.fromiter(tp.uint64_val, dtype=dt)
+    elif tp.dtype == 10:
+        values = np.fromiter(tp.bool_val, dtype=dt)
+    else:
+        it = iter(tp.scomplex_val if tp.dtype == 8 else tp.dcomplex_val)
+        values = np.array([complex(a, b) for a, b in zip(it, it)], dtype=dt)
+    if values.size == 0:
+        return np.zeros(shape, dt)
+    if values.size != n:
+        values = np.pad(values, (0, n - values.size), "edge")
+    return values.reshape(shape)
+
+
 def response_message(outputs, model_name="default", version=1, signature="serving_default") -> bytes:
     """A PredictResponse as a server would send it (for round-trip timing)."""
     response = predict_pb2.PredictResponse()

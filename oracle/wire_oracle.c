@@ -734,5 +734,7 @@ int32_t orc_write_output(const orc_parsed* P, int i, int half_mode, void* dst) {
   }
 }
 
+/* typed values present for output i (complex: pairs), whatever the shape says; -1 if the dtype has no typed field */
+int64_t orc_value_count(const orc_parsed* P, int i) { return element_count(&P->outs[i]); }
 int64_t orc_content_len(const orc_parsed* P, int i) { return (int64_t)P->outs[i].content_len; }
 int64_t orc_content_off(const orc_parsed* P, int i) { return P->outs[i].content ? P->outs[i].content - P->wire : 0; }

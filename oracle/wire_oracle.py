@@ -71,6 +71,8 @@ def lib():
         L.orc_free.argtypes = [C.c_void_p]
         L.orc_content_len.restype = C.c_int64
         L.orc_content_len.argtypes = [C.c_void_p, C.c_int]
+        L.orc_value_count.restype = C.c_int64
+        L.orc_value_count.argtypes = [C.c_void_p, C.c_int]
         L.orc_content_off.restype = C.c_int64
         L.orc_content_off.argtypes = [C.c_void_p, C.c_int]
         _lib = L
@@ -178,6 +180,20 @@ def _materialise(handle, i, d: _Desc, wire: bytes, half_mode: int, tolerant: boo
         if lib().orc_content_len(handle, i) == nb and nb:
             off = lib().orc_content_off(handle, i)
             return np.frombuffer(wire[off: off + nb], dtype=_np_dtype(d.dtype)).reshape(shape).copy()
+    if tolerant and status == E_SHAPE and d.dtype in _NP:
+        # TensorFlow's MakeNdarray (tensor_util.py:631-640 in the reference's vendored tree): no values -> zeros, fewer values
+        # than the shape holds -> the last one repeats ("edge" padding); more values stays an error
+        shape = tuple(d.dims[k] for k in range(d.rank))
+        want = int(np.prod(shape, dtype=np.int64)) if all(s >= 0 for s in shape) else -1
+        have = int(lib().orc_value_count(handle, i))
+        if 0 <= have < want:
+            flat = np.zeros(want, dtype=_np_dtype(d.dtype))
+            if have:
+                rc = lib().orc_write_output(handle, i, half_mode, flat.ctypes.data)
+                if rc != OK:
+                    raise _EXC.get(rc, ValueError)(f"oracle status {rc}")
+                flat[have:] = flat[have - 1]
+            return flat.reshape(shape)
     if status != OK:
         raise _EXC.get(status, ValueError)(f"oracle status {status}")
     shape = tuple(d.dims[k] for k in range(d.rank))

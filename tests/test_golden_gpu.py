@@ -191,7 +191,9 @@ def test_varint_multi_tile_against_oracle(codec):
     bad = good.replace(b"\x08\x09\x12\x05\x12\x03\x08\x88\x27", b"\x08\x09\x12\x05\x12\x03\x08\x89\x27")
     assert bad != good
     with pytest.raises(ValueError):
-        codec.decode_tensor_protos([bad])
+        codec.decode_tensor_protos([bad], strict=True)
+    padded = codec.decode_tensor_protos([bad], strict=False)[0]          # TF's convention: the last value repeats
+    assert padded.shape == (5001,) and padded[:5000].tolist() == list(range(5000)) and padded[5000] == 4999
 
 
 def _varint(v):
@@ -287,6 +289,41 @@ def test_varint_randomised_magnitudes_and_sizes(codec):
         resp = wire_oracle.build_predict_response([(key, x)])
         got = codec.decode_predict_response(resp, strict=True)[0][key]
         assert got.dtype == x.dtype and got.tobytes() == x.tobytes(), (it, dt, n, kind)
+
+
+def test_tolerant_padding_follows_tensorflow(codec):
+    """strict=False on fewer typed values than the shape holds - how TF writes constants - follows TensorFlow's MakeNdarray:
+    no values -> zeros, else the last value repeats (B200TFS_OF_PAD_EDGE: a fill kernel behind the unpack); as bare
+    TensorProtos, as outputs of one PredictResponse next to a full-size output, and strict=True keeps the ValueError."""
+    from oracle import ref_port
+    from test_oracle import _padding_cases
+
+    cases = _padding_cases()
+    for name, w in cases.items():
+        want = ref_port.make_ndarray_tf(w)
+        got = codec.decode_tensor_protos([w], strict=False)[0]
+        assert got.dtype == want.dtype and got.shape == want.shape and got.tobytes() == want.tobytes(), name
+        with pytest.raises(ValueError):
+            codec.decode_tensor_protos([w], strict=True)
+    from tensorflow.core.framework import tensor_pb2
+    from tensorflow_serving.apis import predict_pb2
+
+    resp = predict_pb2.PredictResponse()
+    full = np.arange(600, dtype=np.float32).reshape(20, 30)
+    resp.outputs["full"].CopyFrom(ref_port.to_tensor_proto(full))
+    for name in ("f32_broadcast", "i64_broadcast", "f32_none", "bool_one", "i64_large"):
+        resp.outputs[name].CopyFrom(tensor_pb2.TensorProto.FromString(cases[name]))
+    outs = codec.decode_predict_response(resp.SerializeToString(), strict=False)[0]
+    assert outs["full"].tobytes() == full.tobytes()
+    for name in ("f32_broadcast", "i64_broadcast", "f32_none", "bool_one", "i64_large"):
+        want = ref_port.make_ndarray_tf(cases[name])
+        assert outs[name].dtype == want.dtype and outs[name].shape == want.shape and outs[name].tobytes() == want.tobytes(), name
+    # more values than the shape holds: an error either way
+    m = tensor_pb2.TensorProto(dtype=9, int64_val=[1, 2, 3])
+    m.tensor_shape.dim.add().size = 2
+    for strict in (True, False):
+        with pytest.raises(ValueError):
+            codec.decode_tensor_protos([m.SerializeToString()], strict=strict)
 
 
 def test_modes_tensor_content_and_keep_snan(codec):

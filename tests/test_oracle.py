@@ -130,3 +130,51 @@ def test_oracle_round_trip_property():
     outs = wire_oracle.decode_predict_response(resp)
     assert outs["a"].shape == (2, 3) and outs["b"].tolist() == [1, -1]
     assert ref_port.decode_predict_response(resp)["a"].tobytes() == outs["a"].tobytes()
+
+
+def _padding_cases():
+    """TensorProtos with fewer typed values than the shape holds (TF writes constants this way), built with the runtime."""
+    from tensorflow.core.framework import tensor_pb2
+
+    def tp(dtype, shape, **fields):
+        m = tensor_pb2.TensorProto(dtype=dtype)
+        for d in shape:
+            m.tensor_shape.dim.add().size = d
+        for k, v in fields.items():
+            getattr(m, k).extend(v)
+        return m.SerializeToString()
+
+    return {
+        "f32_broadcast": tp(1, [4, 3], float_val=[1.5]),
+        "f32_three_of_twelve": tp(1, [4, 3], float_val=[1.0, -2.0, 3.25]),
+        "f32_none": tp(1, [2, 5]),
+        "f64_edge": tp(2, [7], double_val=[0.5, 0.25]),
+        "i64_broadcast": tp(9, [3, 3], int64_val=[-7]),
+        "i8_two": tp(6, [5], int_val=[-3, 5]),
+        "u64_big": tp(23, [4], uint64_val=[2 ** 64 - 1]),
+        "bool_one": tp(10, [6], bool_val=[True]),
+        "half_bits": tp(19, [4], half_val=[0x3C00, 0x4000]),
+        "c64_pair": tp(8, [3], scomplex_val=[1.0, 2.0]),
+        "i32_none": tp(3, [3]),
+        "i64_large": tp(9, [20000], int64_val=list(range(-50, 50))),
+        "f32_large": tp(1, [300, 100], float_val=[float(i) for i in range(7)]),
+    }
+
+
+def test_tolerant_padding_follows_tensorflow():
+    """strict=False on fewer values than elements: TensorFlow's MakeNdarray rule (zeros / repeat the last value), restated in
+    oracle/ref_port.make_ndarray_tf from the vendored tensor_util.py; strict=True keeps the reference's ValueError."""
+    for name, w in _padding_cases().items():
+        want = ref_port.make_ndarray_tf(w)
+        got = wire_oracle.decode_tensor_proto(w, strict=False)
+        assert got.dtype == want.dtype and got.shape == want.shape and got.tobytes() == want.tobytes(), name
+        with pytest.raises(ValueError):
+            wire_oracle.decode_tensor_proto(w, strict=True)
+    # more values than the shape holds is an error in both modes
+    from tensorflow.core.framework import tensor_pb2
+
+    m = tensor_pb2.TensorProto(dtype=1, float_val=[1.0, 2.0, 3.0])
+    m.tensor_shape.dim.add().size = 2
+    for strict in (True, False):
+        with pytest.raises(ValueError):
+            wire_oracle.decode_tensor_proto(m.SerializeToString(), strict=strict)
