@@ -190,3 +190,17 @@ def test_size_errors():
     t.rank = 2
     assert lib.b200tfs_tensor_proto_size(C.byref(t), None, None) == N.E_SHAPE
     assert b"negative" in lib.b200tfs_last_error()
+
+
+def test_header_is_plain_c99_and_the_library_links_from_c():
+    """include/b200tfs.h through gcc -std=c99 -pedantic -Werror, linked against libb200tfs.so and run: struct sizes as the ctypes
+    mirrors have them, and - no GPU here - b200tfs_create refusing loudly instead of falling back to a CPU path."""
+    import subprocess
+
+    native = os.path.join(os.path.dirname(os.path.abspath(__file__)), "native")
+    N.load()   # builds nothing, but fails early if the library is missing
+    subprocess.run(["make", "-s", "-C", native, "_build/abi_c99"], check=True)
+    out = subprocess.run([os.path.join(native, "_build", "abi_c99")], capture_output=True, text=True, check=True).stdout.splitlines()
+    assert out[0] == f"abi {N.load().b200tfs_abi_version()} sizes {C.sizeof(N.Tensor)} {C.sizeof(N.Request)} {C.sizeof(N.Output)} {C.sizeof(N.ModelSpec)}"
+    if N.device_count() == 0:
+        assert out[1].startswith(f"create {N.E_CUDA} ") and "no CPU path" in out[1]
