@@ -160,8 +160,11 @@ def test_host_planner_frames_random_requests_like_the_runtime(data):
     preps = [_Prepared(a, k.encode(), None, False, False) for k, a in inputs]
     arr = (N.Tensor * max(len(preps), 1))(*[p.struct for p in preps])
     nb = name.encode()
+    framed = data.draw(st.booleans())        # gRPC's five-byte length-prefixed-message header in front, or not
+    if framed:
+        expect = b"\x00" + len(expect).to_bytes(4, "big") + expect
     req = N.Request(model_name=nb, model_name_len=len(nb), has_version=int(version is not None), order=N.ORDER_UPB, version=version or 0,
-                    n_inputs=len(preps), flags=0, inputs=arr)
+                    n_inputs=len(preps), flags=N.RF_GRPC_FRAME if framed else 0, inputs=arr)
     lib = N.load()
     buf = C.create_string_buffer(1 << 16)
     flen = C.c_uint64()
@@ -186,7 +189,7 @@ def test_host_planner_frames_random_requests_like_the_runtime(data):
     wire += frame[fpos:]
     assert bytes(wire) == expect
     # and the C oracle says the same
-    assert wire_oracle.encode_predict_request(name, version, inputs) == expect
+    assert wire_oracle.encode_predict_request(name, version, inputs) == (expect[5:] if framed else expect)
 
 
 @SET
