@@ -79,7 +79,9 @@ class _Prepared:
         else:
             if not arr.dtype.isnative:
                 arr = arr.astype(arr.dtype.newbyteorder("="))
-            arr = np.ascontiguousarray(arr)  # C order, like ndarray.ravel() in tensors.py:34
+            # C order, like ndarray.ravel() in tensors.py:34.  (np.ascontiguousarray promotes a 0-d array to shape (1,):
+            # the reference keeps the empty shape - `tensor_shape {}` = 12 00 - so ask for the layout only.)
+            arr = np.require(arr, requirements="C")
             wire_enum = src_enum if wire_dtype is None else _as_enum(wire_dtype)
             if tensor_content:
                 flags |= N.F_TENSOR_CONTENT
@@ -130,6 +132,7 @@ class OpenResponse:
 
     def __init__(self, codec, buf, base, dst, table):
         self._codec, self._buf, self._base, self._dst, self.table = codec, buf, base, dst, table
+        self._handed = set()
 
     def wire_of(self, key) -> bytes:
         o = self.table[key]
@@ -143,7 +146,11 @@ class OpenResponse:
             return None
         np_type, dst_code, shape = self._codec._resolve_output(o, strict, None)
         at = int(o.dst_off)
-        return self._dst[at: at + int(o.dst_bytes)].view(np_type).reshape(shape)
+        arr = self._dst[at: at + int(o.dst_bytes)].view(np_type).reshape(shape)
+        if key in self._handed:      # tensor_proto_to_ndarray returns a fresh array per call (tensors.py:46): never alias two results
+            return arr.copy()
+        self._handed.add(key)
+        return arr
 
 
 class ParsedResponse:
@@ -255,12 +262,13 @@ class Codec:
         if n == 1:
             # one request whose size is closed-form (no varint-packed input): copy straight into the bytes object
             total = C.c_uint64()
-            if self._lib.b200tfs_request_size(reqs, C.byref(total)) == N.OK:
+            if _HAVE_NEW_BYTES and self._lib.b200tfs_request_size(reqs, C.byref(total)) == N.OK:
                 obj, addr = _new_bytes(int(total.value))
                 off = (C.c_uint64 * 1)()
                 ln = (C.c_uint64 * 1)()
                 N.check(self._lib.b200tfs_encode_requests_host(self._ctx, 1, reqs, addr, total.value, off, ln))
-                assert off[0] == 0 and ln[0] == total.value
+                if off[0] != 0 or ln[0] != total.value:
+                    raise N.NativeError(N.E_ARG, f"encoded length {ln[0]} at {off[0]} does not match the planned {total.value}")
                 return [obj]
         cap = 0
         for preps, _, name in keep:
@@ -301,16 +309,23 @@ class Codec:
         return buf[off: off + length].tobytes().decode("utf-8")
 
     def parse_predict_responses(self, wires: Sequence[bytes], max_outputs: int = 16) -> List[ParsedResponse]:
-        """Run the parse kernel over each PredictResponse; raises DecodeError like ``FromString``."""
+        """Run the parse kernel over each PredictResponse; raises DecodeError like ``FromString``.  ``max_outputs`` sizes
+        the first attempt only: a response with more outputs is parsed again with a table twice as wide, and so on
+        (``PredictResponse.FromString`` has no limit on the map size)."""
         n = len(wires)
         if n == 0:
             return []
         buf, off, ln = self._pack_wires(wires)
-        outs = (N.Output * (n * max_outputs))()
-        n_outs = (C.c_int32 * n)()
-        specs = (N.ModelSpec * n)()
-        status = (C.c_int32 * n)()
-        N.check(self._lib.b200tfs_parse_responses_host(self._ctx, buf.ctypes.data, n, off, ln, max_outputs, outs, n_outs, specs, status))
+        while True:
+            outs = (N.Output * (n * max_outputs))()
+            n_outs = (C.c_int32 * n)()
+            specs = (N.ModelSpec * n)()
+            status = (C.c_int32 * n)()
+            N.check(self._lib.b200tfs_parse_responses_host(self._ctx, buf.ctypes.data, n, off, ln, max_outputs, outs, n_outs, specs, status))
+            if max_outputs < (1 << 20) and any(status[i] == N.E_SIZE for i in range(n)):
+                max_outputs *= 2
+                continue
+            break
         parsed = []
         for i in range(n):
             if status[i] == N.E_SIZE:
@@ -549,12 +564,19 @@ class Codec:
 
 
 # ---- zero-copy helpers -----------------------------------------------------------------------------
-_PyBytes_FromStringAndSize = C.pythonapi.PyBytes_FromStringAndSize
-_PyBytes_FromStringAndSize.restype = C.py_object
-_PyBytes_FromStringAndSize.argtypes = [C.c_void_p, C.c_ssize_t]
-_PyBytes_AsString = C.pythonapi.PyBytes_AsString
-_PyBytes_AsString.restype = C.c_void_p
-_PyBytes_AsString.argtypes = [C.py_object]
+# CPython only: PyBytes_FromStringAndSize(NULL, n) is the documented way to make a bytes object whose buffer the caller
+# fills before anyone else sees the object (https://docs.python.org/3/c-api/bytes.html).  The object is not hashed,
+# interned or shared until the library has written every byte of it; other interpreters take the copying path.
+import platform as _platform
+
+_HAVE_NEW_BYTES = _platform.python_implementation() == "CPython" and hasattr(C, "pythonapi")
+if _HAVE_NEW_BYTES:
+    _PyBytes_FromStringAndSize = C.pythonapi.PyBytes_FromStringAndSize
+    _PyBytes_FromStringAndSize.restype = C.py_object
+    _PyBytes_FromStringAndSize.argtypes = [C.c_void_p, C.c_ssize_t]
+    _PyBytes_AsString = C.pythonapi.PyBytes_AsString
+    _PyBytes_AsString.restype = C.c_void_p
+    _PyBytes_AsString.argtypes = [C.py_object]
 
 
 def _new_bytes(n: int):

@@ -89,8 +89,9 @@ def make_array(recipe):
 
 
 def hexarr(a):
-    a = np.ascontiguousarray(a)
-    return {"gen": "hex", "dtype": a.dtype.str, "shape": list(a.shape), "data": a.tobytes().hex()}
+    a = np.asarray(a)
+    shape = list(a.shape)          # np.ascontiguousarray would promote a 0-d array to shape (1,)
+    return {"gen": "hex", "dtype": a.dtype.str, "shape": shape, "data": np.ascontiguousarray(a).tobytes().hex()}
 
 
 def summarize(wire, full_limit=4096):
@@ -114,7 +115,9 @@ def tensor_cases():
 
     add("kat1_f32_4x4", {"gen": "arange", "dtype": "<f4", "shape": [4, 4]})
     add("f64_ref_unit_golden", hexarr(np.array([0.314, 0.159, 0.268, 0.358], dtype=np.float64)))  # tensors_test.py:66-83
-    add("f32_rank0", hexarr(np.float32(3.0).reshape(())))
+    add("f32_rank0", hexarr(np.float32(3.0).reshape(())))     # KAT-7: 08 01 12 00 2a 04 00 00 40 40
+    add("i64_rank0", hexarr(np.int64(-3)))
+    add("f64_rank0", hexarr(np.float64(2.5)))
     add("f32_0x3", hexarr(np.zeros((0, 3), dtype=np.float32)))
     add("f32_3x0x2", hexarr(np.zeros((3, 0, 2), dtype=np.float32)))
     add("f32_rank8", {"gen": "standard_normal", "seed": 5, "dtype": "<f4", "shape": [1, 2, 1, 3, 1, 2, 1, 5]})
@@ -212,6 +215,8 @@ def request_cases():
                                           ("string_input", {"gen": "strings", "shape": [2], "data": ["hello", "world"]}),
                                           ("bool_input", hexarr(np.array([True, False]))),
                                           ("double_input", {"gen": "standard_normal", "seed": 2, "dtype": "<f8", "shape": [5]})]),
+        # scalar placeholders (keep_prob and friends): 0-d arrays keep an EMPTY tensor_shape (`12 00`), SURVEY Q4
+        ("scalar_inputs", "m", 1, [("keep_prob", hexarr(np.float32(0.5))), ("step", hexarr(np.int64(-7))), ("flag", hexarr(np.bool_(True)))]),
     ]
     out = {}
     for name, model, ver, ins in cases:
