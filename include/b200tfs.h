@@ -32,7 +32,7 @@
 extern "C" {
 #endif
 
-#define B200TFS_ABI_VERSION 1
+#define B200TFS_ABI_VERSION 2
 
 /* ---- status codes ---------------------------------------------------------------------------- */
 #define B200TFS_OK 0
@@ -43,9 +43,13 @@ extern "C" {
 #define B200TFS_E_CUDA (-5)         /* CUDA runtime error / no device                                          */
 #define B200TFS_E_TOOBIG (-6)       /* message would exceed protobuf's 2 GiB limit                            */
 #define B200TFS_E_ARG (-7)          /* bad argument                                                            */
-#define B200TFS_E_NONCANONICAL (-8) /* valid wire, but a layout the device parser does not tabulate            */
+#define B200TFS_E_NONCANONICAL (-8) /* valid wire, but a layout this entry point does not tabulate (the single-launch
+                                       decode: values in more runs / more dims than the table holds inline; both
+                                       parsers: groups or variant tensors nested deeper than 16)                     */
 #define B200TFS_E_RANGE (-9)        /* decoded integer does not fit the target dtype          (OverflowError) */
 #define B200TFS_E_KEY (-10)         /* dtype enum absent / unmapped on decode                       (KeyError) */
+#define B200TFS_E_SPILL (-11)       /* internal to the parsers: a record needs a larger spill area (the two-phase parse
+                                       grows it and runs again; callers never see this code)                        */
 
 /* ---- tensorflow.DataType values used on this path (types.proto:12-68; pinned by the reference's
  *      tests/unit/min_tfs_client/types_test.py:7-23) ------------------------------------------------ */
@@ -81,6 +85,9 @@ extern "C" {
 /* ---- decode flags (b200tfs_output.flags, set by the parser) ----------------------------------- */
 #define B200TFS_OF_TENSOR_CONTENT 0x1u /* values arrived in tensor_content                                        */
 #define B200TFS_OF_MULTI_CHUNK 0x2u    /* values field split over several occurrences / unpacked elements         */
+#define B200TFS_OF_UNPACKED 0x80u      /* some values arrived as unpacked scalar elements (wire type 0 / 1 / 5)   */
+#define B200TFS_OF_SPILLED 0x100u      /* more dims than B200TFS_MAX_RANK and / or more value runs than B200TFS_MAX_RUNS: the rest
+                                          is held by the context (b200tfs_output_dims / b200tfs_output_runs)               */
 #define B200TFS_OF_DIM_INFERRED 0x4u   /* one dim was -1 and was inferred from the element count                 */
 #define B200TFS_OF_HAS_UNKNOWN 0x8u    /* unknown fields were skipped inside this entry                           */
 #define B200TFS_OF_RANK0 0x10u         /* no dims: the reference raises TypeError here (reshape() with no args)   */
@@ -103,8 +110,9 @@ extern "C" {
                                      b200tfs_request_size include the five bytes                                          */
 #define B200TFS_ORDER_BYTES 2 /* plain bytewise order (shorter prefix first)                                     */
 
-#define B200TFS_MAX_RANK 16   /* decode table limit; encode accepts any rank up to 254 (TF's limit)            */
-#define B200TFS_MAX_CHUNKS 8  /* value-field occurrences tabulated per output before E_NONCANONICAL             */
+#define B200TFS_MAX_RANK 16   /* dims held inline by b200tfs_output; deeper shapes spill (b200tfs_output_dims).  Encode
+                                 accepts any rank up to 254 (TF's limit)                                          */
+#define B200TFS_MAX_RUNS 8    /* value runs held inline by b200tfs_output; more spill (b200tfs_output_runs)      */
 
 typedef struct b200tfs_ctx b200tfs_ctx;
 
@@ -137,6 +145,19 @@ typedef struct b200tfs_request {
   const b200tfs_tensor* inputs;
 } b200tfs_request;
 
+/* Where the values of one output lie on the wire.  The reference iterates the merged repeated field whatever
+ * its wire layout (tensors.py:42-46): one packed occurrence, several of them, single unpacked elements, or any
+ * mix.  A run is `count` pieces of `len` value bytes each, `stride` bytes apart - one packed occurrence is a run
+ * of count 1; a row of unpacked elements (tag + 4 value bytes, tag + 4 value bytes, ...) is ONE run of count n,
+ * len 4, stride 5; equally long packed occurrences at equal distances coalesce the same way.                    */
+typedef struct b200tfs_run {
+  uint64_t off;    /* first piece, byte offset from the start of the record                    */
+  uint32_t len;    /* value bytes per piece                                                     */
+  uint32_t count;  /* pieces                                                                    */
+  uint32_t stride; /* distance between the starts of consecutive pieces (0 when count == 1)    */
+  uint32_t field;  /* TensorProto field number the pieces belong to                             */
+} b200tfs_run;
+
 /* One decoded output of a PredictResponse (predict.proto:30-40), as tabulated by the parse kernel.
  * All offsets are byte offsets from the start of the RECORD (arena + rec_off[i]).                  */
 typedef struct b200tfs_output {
@@ -146,10 +167,10 @@ typedef struct b200tfs_output {
   int32_t rank;
   uint32_t flags;      /* B200TFS_OF_*                                                          */
   int32_t value_field; /* TensorProto field the dtype maps to (constants.py:13-29), 0 = unmapped */
-  int32_t n_chunks;    /* occurrences of that field (packed runs or single unpacked elements)   */
-  int64_t dims[B200TFS_MAX_RANK];          /* after -1 inference                                */
-  uint64_t chunk_off[B200TFS_MAX_CHUNKS];
-  uint64_t chunk_len[B200TFS_MAX_CHUNKS];
+  int32_t n_runs;      /* value runs of that field, in wire order (ALL of them; the first
+                          B200TFS_MAX_RUNS are in runs[], see B200TFS_OF_SPILLED)                */
+  int64_t dims[B200TFS_MAX_RANK];          /* after -1 inference; `rank` counts ALL dims        */
+  b200tfs_run runs[B200TFS_MAX_RUNS];
   uint64_t content_off; /* tensor_content (field 4), last occurrence; content_len 0 if absent   */
   uint64_t content_len;
   uint64_t msg_off;     /* the TensorProto sub-message itself (last `value` occurrence)         */
@@ -160,7 +181,9 @@ typedef struct b200tfs_output {
   uint64_t dst_off;     /* b200tfs_decode_responses: where the values were written, from the
                            record's destination slot dst_dev + i*dst_stride                    */
   int32_t status;       /* B200TFS_OK, or the error tensor_proto_to_ndarray raises for it       */
-  int32_t reserved;
+  uint32_t n_inline;    /* entries of runs[] in use (== n_runs unless B200TFS_OF_SPILLED)        */
+  uint32_t spill_rec;   /* B200TFS_OF_SPILLED: record index within the parse call and ordinal of the map   */
+  uint32_t spill_seq;   /* entry inside it whose spill entries complete this output (opaque)     */
 } b200tfs_output;
 
 typedef struct b200tfs_model_spec {
@@ -257,6 +280,14 @@ int b200tfs_encode_requests(b200tfs_ctx* ctx, int32_t n, const b200tfs_request* 
 int b200tfs_parse_responses(b200tfs_ctx* ctx, const void* arena_dev, int32_t n, const uint64_t* rec_off,
                             const uint64_t* rec_len, int32_t max_outputs, b200tfs_output* outs,
                             int32_t* n_outs, b200tfs_model_spec* specs, int32_t* rec_status);
+/* A shape deeper than B200TFS_MAX_RANK or values in more than B200TFS_MAX_RUNS runs (B200TFS_OF_SPILLED): the
+ * complete lists, from the spill area the context keeps of its most recent b200tfs_parse_* call (the two-phase
+ * parse re-runs itself with a larger spill area when a record needs it; the single-launch decode has none and
+ * reports such a record as B200TFS_E_NONCANONICAL - decode it with the two-phase calls).  `dims` receives
+ * min(cap, rank) entries; `runs` min(cap, n_runs) entries of the output's value field.  Outputs without the flag
+ * are answered from the struct itself.                                                                        */
+int b200tfs_output_dims(b200tfs_ctx* ctx, const b200tfs_output* out, int64_t* dims, int32_t cap);
+int b200tfs_output_runs(b200tfs_ctx* ctx, const b200tfs_output* out, b200tfs_run* runs, int32_t cap);
 /* Same walk for n bare TensorProto messages (tensor_proto_to_ndarray on a single message): one
  * output per record, key_len = 0.                                                                  */
 int b200tfs_parse_tensor_protos(b200tfs_ctx* ctx, const void* arena_dev, int32_t n,
@@ -286,6 +317,11 @@ int b200tfs_unpack_outputs(b200tfs_ctx* ctx, const void* arena_dev, int32_t m, c
 #define B200TFS_FUSED_MAX_OUTPUTS 8
 int b200tfs_decode_responses(b200tfs_ctx* ctx, const void* arena_dev, int32_t n, const uint64_t* rec_off,
                              const uint64_t* rec_len, void* dst_dev, uint64_t dst_stride);
+/* How the records of every b200tfs_decode_responses launch of this context were served so far (cumulative; synchronises):
+ * by the framing template handed over in the kernel parameters (the host walked record 0 of a host-resident wire itself,
+ * or adopted the previous launch's template from pinned memory while the stream was idle), by the template the previous
+ * launch left in device memory, or by walking the tags.  Any pointer may be NULL.                                      */
+int b200tfs_decode_stats(b200tfs_ctx* ctx, uint64_t* param_template, uint64_t* device_template, uint64_t* walked);
 /* outs has n*B200TFS_FUSED_MAX_OUTPUTS slots; any pointer may be NULL.                             */
 int b200tfs_decode_results(b200tfs_ctx* ctx, int32_t n, b200tfs_output* outs, int32_t* n_outs,
                            b200tfs_model_spec* specs, int32_t* rec_status);

@@ -22,6 +22,8 @@
 #include "../../include/b200tfs.h"
 #include "kernels.h"
 #include "plan.h"
+#include "tpl.h"
+#include "walker.h"
 #include "wire.h"
 
 using namespace b200tfs;
@@ -90,17 +92,36 @@ struct b200tfs_ctx {
   Growable fused_host;      // decode_fused tables: pinned host memory the kernel writes directly
   void* tpl_dev = nullptr;  // two framing templates (device), used alternately by successive decode launches
   uint32_t tpl_flip = 0;
+  TplInline* tpl_pinned = nullptr;   // where a kernel that learns a template leaves its inline part (pinned, mapped)
+  TplInline tpl_known{};             // the newest template the host knows: its own walk of a host-resident record 0, or tpl_pinned
+                                     // as found with the stream idle; rides in the kernel parameters of the next single-response launch
+  uint32_t serial = 0;               // stamp of the next template learnt
+  uint64_t stage_shift = 0;          // *_host decode: the wire sits at stage_dev + stage_shift (placed so that the payload is 16-byte aligned)
   int32_t fused_n = 0;      // records of the last b200tfs_decode_responses
   std::vector<int32_t> pending_status;   // varint decode: which output each status word in scratch_host belongs to
   // counters left by b200tfs_measure, keyed by tensor address; consumed by the encode that follows
   Growable measured_dev;
   uint64_t measured_used = 0;
   std::unordered_map<const void*, MeasuredTensor> measured;
+  // spill area of the two-phase parse: dims / value runs beyond the table's inline arrays (walker.h SpillEntry)
+  Growable spill_dev;
+  std::vector<SpillEntry> spill_host;   // host copy of the last parse's area (empty when no record spilled)
+  uint32_t spill_per_rec = 16;          // entries per record the next parse starts with
+  uint32_t spill_last_per = 0;          // geometry of spill_host
+  int32_t spill_last_n = 0;
+  Growable gather_dev;                  // unpack: strided / many-run varint outputs are first gathered into one stream here
+  bool has_graphs = false;              // a CUDA graph captured on this context refers to the scratch buffers: they may not move any more
 };
 
-static int grow_dev(b200tfs_ctx* c, Growable& g, uint64_t need) {
+// `baked`: the buffer's address ends up inside captured graphs (every context-owned scratch buffer except the plan-upload
+// slots, which captured launches replace by private ones).  Once a graph exists, such a buffer must not be reallocated:
+// replays would write through the stale address.  Size everything with the largest call BEFORE capturing.
+static const char* kGraphPinned = "a CUDA graph captured on this context refers to its scratch buffers, which this larger call would have to "
+                                  "reallocate: run the largest call once before capturing, or use another context";
+static int grow_dev(b200tfs_ctx* c, Growable& g, uint64_t need, bool baked = true) {
   if (need <= g.cap) return B200TFS_OK;
   if (c->capturing) return fail(B200TFS_E_ARG, "scratch buffer would have to grow during graph capture: run the call once before capturing");
+  if (baked && c->has_graphs) return fail(B200TFS_E_ARG, "%s", kGraphPinned);
   uint64_t cap = std::max<uint64_t>(need, g.cap * 2);
   cap = (cap + 0xFFFFull) & ~0xFFFFull;
   CU(cudaStreamSynchronize(c->stream));
@@ -110,9 +131,10 @@ static int grow_dev(b200tfs_ctx* c, Growable& g, uint64_t need) {
   g.cap = cap;
   return B200TFS_OK;
 }
-static int grow_host(b200tfs_ctx* c, Growable& g, uint64_t need) {
+static int grow_host(b200tfs_ctx* c, Growable& g, uint64_t need, bool baked = true) {
   if (need <= g.cap) return B200TFS_OK;
   if (c->capturing) return fail(B200TFS_E_ARG, "scratch buffer would have to grow during graph capture: run the call once before capturing");
+  if (baked && c->has_graphs) return fail(B200TFS_E_ARG, "%s", kGraphPinned);
   uint64_t cap = std::max<uint64_t>(need, g.cap * 2);
   cap = (cap + 0xFFFull) & ~0xFFFull;
   CU(cudaStreamSynchronize(c->stream));
@@ -145,8 +167,8 @@ static int claim_slot(b200tfs_ctx* c, uint64_t bytes, Slot** out) {
   c->next_slot = (c->next_slot + 1) % kSlots;
   if (s.pending) { CU(cudaEventSynchronize(s.done)); s.pending = false; }
   int rc;
-  if ((rc = grow_host(c, s.host, bytes))) return rc;
-  if ((rc = grow_dev(c, s.dev, bytes))) return rc;
+  if ((rc = grow_host(c, s.host, bytes, false))) return rc;
+  if ((rc = grow_dev(c, s.dev, bytes, false))) return rc;
   *out = &s;
   return B200TFS_OK;
 }
@@ -200,8 +222,11 @@ int b200tfs_destroy(b200tfs_ctx* c) {
   }
   if (c->fused_host.p) cudaFreeHost(c->fused_host.p);
   if (c->tpl_dev) cudaFree(c->tpl_dev);
+  if (c->tpl_pinned) cudaFreeHost(c->tpl_pinned);
   for (Slot* g : c->graph_slots) { cudaFreeHost(g->host.p); cudaFree(g->dev.p); delete g; }
   if (c->scratch_dev.p) cudaFree(c->scratch_dev.p);
+  if (c->spill_dev.p) cudaFree(c->spill_dev.p);
+  if (c->gather_dev.p) cudaFree(c->gather_dev.p);
   if (c->measured_dev.p) cudaFree(c->measured_dev.p);
   if (c->scratch_host.p) cudaFreeHost(c->scratch_host.p);
   if (c->stage_dev.p) cudaFree(c->stage_dev.p);
@@ -428,14 +453,15 @@ struct PlanBuilder {
     // split long headers so one warp never walks more than kSmallMax bytes
     while (n) {
       uint32_t k = (uint32_t)std::min<size_t>(n, kSmallMax);
-      smalls.push_back(SmallItem{(uint64_t)blob_off, dst, k, OP_COPY | OP_FLAG_BLOB});
+      smalls.push_back(SmallItem{(uint64_t)blob_off, dst, k, OP_COPY | OP_FLAG_BLOB, 0, 0});
       dst += k; blob_off += k; n -= k;
     }
   }
-  void payload(const uint8_t* src, uint8_t* dst, uint64_t n_out, uint32_t op) {
+  // glen / gstride != 0: the source is a row of pieces (b200tfs_run with count > 1), gathered byte-exact
+  void payload(const uint8_t* src, uint8_t* dst, uint64_t n_out, uint32_t op, uint32_t glen = 0, uint32_t gstride = 0) {
     if (!n_out) return;
-    if (n_out <= kSmallMax) smalls.push_back(SmallItem{(uint64_t)(uintptr_t)src, dst, (uint32_t)n_out, op});
-    else { items.push_back(MoveItem{src, dst, n_out, op, 0}); large_bytes += n_out; }
+    if (n_out <= kSmallMax) smalls.push_back(SmallItem{(uint64_t)(uintptr_t)src, dst, (uint32_t)n_out, op, glen, gstride});
+    else { items.push_back(MoveItem{src, dst, n_out, op, 0, glen, gstride}); large_bytes += n_out; }
   }
 };
 
@@ -820,7 +846,8 @@ static int parse_common(b200tfs_ctx* c, const void* arena_dev, int32_t n, const 
   const uint64_t b_nouts = b_outs + sizeof(b200tfs_output) * (uint64_t)n * stride;
   const uint64_t b_specs = (b_nouts + 4ull * n + 15) & ~15ull;
   const uint64_t b_status = b_specs + sizeof(b200tfs_model_spec) * (uint64_t)n;
-  const uint64_t total = (b_status + 4ull * n + 15) & ~15ull;
+  const uint64_t b_spill = (b_status + 4ull * n + 15) & ~15ull;      // uint32 spill_used[n]
+  const uint64_t total = (b_spill + 4ull * n + 15) & ~15ull;
   int rc;
   if ((rc = grow_dev(c, c->scratch_dev, total))) return rc;
   if ((rc = grow_host(c, c->scratch_host, total))) return rc;
@@ -829,17 +856,43 @@ static int parse_common(b200tfs_ctx* c, const void* arena_dev, int32_t n, const 
   memcpy(h + b_off, rec_off, 8ull * n);
   memcpy(h + b_len, rec_len, 8ull * n);
   CU(cudaMemcpyAsync(d, h, b_outs, cudaMemcpyHostToDevice, c->stream));
-  if (bare)
-    CU(launch_parse_tensors((const uint8_t*)arena_dev, (const uint64_t*)(d + b_off), (const uint64_t*)(d + b_len), n,
-                            (b200tfs_output*)(d + b_outs), (int32_t*)(d + b_status), c->stream));
-  else
-    CU(launch_parse_responses((const uint8_t*)arena_dev, (const uint64_t*)(d + b_off), (const uint64_t*)(d + b_len), n, max_outputs,
-                              (b200tfs_output*)(d + b_outs), (int32_t*)(d + b_nouts), (b200tfs_model_spec*)(d + b_specs),
-                              (int32_t*)(d + b_status), c->stream));
-  c->launches += 1;
-  CU(cudaMemcpyAsync(h + b_outs, d + b_outs, total - b_outs, cudaMemcpyDeviceToHost, c->stream));
-  CU(cudaStreamSynchronize(c->stream));
+  static_assert(sizeof(SpillEntry) == kSpillEntryBytes, "SpillEntry layout");
+  // The walk runs with a spill area of spill_per_rec entries per record; a record that wants more says how many
+  // (B200TFS_E_SPILL + spill_used) and the walk runs once more with that much - the count is exact, so twice at most.
+  uint32_t per = c->spill_per_rec;
+  c->spill_host.clear(); c->spill_last_n = 0; c->spill_last_per = 0;
+  for (int attempt = 0;; ++attempt) {
+    if ((rc = grow_dev(c, c->spill_dev, (uint64_t)n * per * sizeof(SpillEntry) + 16))) return rc;
+    if (bare)
+      CU(launch_parse_tensors((const uint8_t*)arena_dev, (const uint64_t*)(d + b_off), (const uint64_t*)(d + b_len), n,
+                              (b200tfs_output*)(d + b_outs), (int32_t*)(d + b_status), c->spill_dev.p, per, (uint32_t*)(d + b_spill), c->stream));
+    else
+      CU(launch_parse_responses((const uint8_t*)arena_dev, (const uint64_t*)(d + b_off), (const uint64_t*)(d + b_len), n, max_outputs,
+                                (b200tfs_output*)(d + b_outs), (int32_t*)(d + b_nouts), (b200tfs_model_spec*)(d + b_specs),
+                                (int32_t*)(d + b_status), c->spill_dev.p, per, (uint32_t*)(d + b_spill), c->stream));
+    c->launches += 1;
+    CU(cudaMemcpyAsync(h + b_outs, d + b_outs, total - b_outs, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    const int32_t* st = (const int32_t*)(h + b_status);
+    const uint32_t* used = (const uint32_t*)(h + b_spill);
+    uint32_t want = 0, any = 0;
+    bool again = false;
+    for (int i = 0; i < n; ++i) { any |= used[i]; if (st[i] == B200TFS_E_SPILL) { again = true; want = std::max(want, used[i]); } }
+    if (again && attempt < 2) {
+      if ((uint64_t)n * want * sizeof(SpillEntry) > (1ull << 32)) return fail(B200TFS_E_TOOBIG, "spill area of %u entries x %d records", want, n);
+      per = want;
+      continue;
+    }
+    if (any) {   // bring the area over: unpack and the b200tfs_output_* accessors read it on the host
+      c->spill_host.resize((size_t)n * per);
+      CU(cudaMemcpyAsync(c->spill_host.data(), c->spill_dev.p, (size_t)n * per * sizeof(SpillEntry), cudaMemcpyDeviceToHost, c->stream));
+      CU(cudaStreamSynchronize(c->stream));
+      c->spill_last_n = n; c->spill_last_per = per;
+    }
+    break;
+  }
   memcpy(rec_status, h + b_status, 4ull * n);
+  for (int i = 0; i < n; ++i) if (rec_status[i] == B200TFS_E_SPILL) rec_status[i] = B200TFS_E_NONCANONICAL;   // cannot happen: the second walk had room
   if (bare) {
     memcpy(outs, h + b_outs, sizeof(b200tfs_output) * (uint64_t)n);
   } else {
@@ -849,6 +902,47 @@ static int parse_common(b200tfs_ctx* c, const void* arena_dev, int32_t n, const 
       int k = rec_status[i] == B200TFS_OK ? n_outs[i] : 0;
       memcpy(outs + (size_t)i * max_outputs, h + b_outs + sizeof(b200tfs_output) * (uint64_t)i * stride, sizeof(b200tfs_output) * (size_t)k);
     }
+  }
+  return B200TFS_OK;
+}
+
+// every value run of an output, in wire order: the inline ones, then the spilled ones of its map entry and value field
+static int collect_runs(const b200tfs_ctx* c, const b200tfs_output& o, std::vector<b200tfs_run>& runs) {
+  runs.clear();
+  const uint32_t inl = std::min<uint32_t>(o.n_inline, B200TFS_MAX_RUNS);
+  for (uint32_t k = 0; k < inl; ++k) runs.push_back(o.runs[k]);
+  if ((uint32_t)o.n_runs > inl) {
+    if (!(o.flags & B200TFS_OF_SPILLED) || (int32_t)o.spill_rec >= c->spill_last_n || c->spill_host.empty())
+      return fail(B200TFS_E_ARG, "output lists %d value runs, %u inline, but the context holds no spill area for it (another parse ran since?)",
+                  o.n_runs, inl);
+    const SpillEntry* e = c->spill_host.data() + (size_t)o.spill_rec * c->spill_last_per;
+    for (uint32_t k = 0; k < c->spill_last_per && (int)runs.size() < o.n_runs; ++k)
+      if (e[k].kind == SPILL_RUN && e[k].seq == o.spill_seq && (int32_t)e[k].run.field == o.value_field) runs.push_back(e[k].run);
+    if ((int)runs.size() != o.n_runs) return fail(B200TFS_E_ARG, "spill area does not hold the %d runs this output lists", o.n_runs);
+  }
+  return B200TFS_OK;
+}
+
+int b200tfs_output_runs(b200tfs_ctx* c, const b200tfs_output* o, b200tfs_run* runs, int32_t cap) {
+  if (!c || !o || (cap > 0 && !runs) || cap < 0) return fail(B200TFS_E_ARG, "bad arguments");
+  std::vector<b200tfs_run> all;
+  int rc = collect_runs(c, *o, all);
+  if (rc) return rc;
+  for (int32_t k = 0; k < cap && k < (int32_t)all.size(); ++k) runs[k] = all[k];
+  return B200TFS_OK;
+}
+
+int b200tfs_output_dims(b200tfs_ctx* c, const b200tfs_output* o, int64_t* dims, int32_t cap) {
+  if (!c || !o || (cap > 0 && !dims) || cap < 0) return fail(B200TFS_E_ARG, "bad arguments");
+  int32_t k = 0;
+  for (; k < cap && k < o->rank && k < B200TFS_MAX_RANK; ++k) dims[k] = o->dims[k];
+  if (o->rank > B200TFS_MAX_RANK && cap > B200TFS_MAX_RANK) {
+    if ((int32_t)o->spill_rec >= c->spill_last_n || c->spill_host.empty())
+      return fail(B200TFS_E_ARG, "rank %d output, but the context holds no spill area for it (another parse ran since?)", o->rank);
+    const SpillEntry* e = c->spill_host.data() + (size_t)o->spill_rec * c->spill_last_per;
+    for (uint32_t i = 0; i < c->spill_last_per && k < cap && k < o->rank; ++i)
+      if (e[i].kind == SPILL_DIM && e[i].seq == o->spill_seq) dims[k++] = (int64_t)e[i].run.off;
+    if (k < std::min(cap, o->rank)) return fail(B200TFS_E_ARG, "spill area does not hold the %d dims this output lists", o->rank);
   }
   return B200TFS_OK;
 }
@@ -872,8 +966,8 @@ int b200tfs_parse_tensor_protos(b200tfs_ctx* c, const void* arena_dev, int32_t n
 namespace {
 
 struct VarDecodeJob {
-  const uint8_t* src[B200TFS_MAX_CHUNKS];
-  uint64_t len[B200TFS_MAX_CHUNKS];
+  const uint8_t* src[B200TFS_MAX_RUNS];
+  uint64_t len[B200TFS_MAX_RUNS];
   int n_chunks;
   uint8_t* dst;
   uint64_t n_elems;
@@ -903,12 +997,33 @@ static int unpack_outputs_impl(b200tfs_ctx* c, const void* arena_dev, int32_t m,
   std::vector<VarDecodeJob> vjobs;
   struct Fill { uint8_t* dst; uint32_t elem_size; uint64_t have, n_elems; };
   std::vector<Fill> fills;   // B200TFS_OF_PAD_EDGE on fixed-width outputs: pad once the values are in place
+  // value runs of every output (inline + spilled).  Packed-varint outputs whose values lie in strided runs (rows of unpacked
+  // elements) or in more runs than a decode job lists are first GATHERED into one contiguous stream - the concatenation of
+  // the pieces is itself a packed varint stream - and decoded from there.
+  std::vector<std::vector<b200tfs_run>> all_runs(m);
+  uint64_t gather_bytes = 0;
   for (int j = 0; j < m; ++j) {
     const b200tfs_output& o = outs[j];
+    if (!o.n_elems || o.n_runs == 0) continue;
+    int rc = collect_runs(c, o, all_runs[j]);
+    if (rc) return rc;
+    const uint32_t kind = dtype_info(o.dtype).kind;
+    if (kind == VK_VARINT || kind == VK_BOOL) {
+      bool plain = all_runs[j].size() <= (size_t)B200TFS_MAX_RUNS;
+      uint64_t bytes = 0;
+      for (const b200tfs_run& r : all_runs[j]) { plain = plain && r.count == 1; bytes += (uint64_t)r.len * r.count; }
+      if (!plain) gather_bytes = ((gather_bytes + 15) & ~15ull) + bytes;
+    }
+  }
+  if (gather_bytes) { int rc = grow_dev(c, c->gather_dev, gather_bytes + 64); if (rc) return rc; }
+  uint64_t gather_cur = 0;
+  for (int j = 0; j < m; ++j) {
+    const b200tfs_output& o = outs[j];
+    const std::vector<b200tfs_run>& runs = all_runs[j];
     const uint8_t* w = (const uint8_t*)arena_dev + (out_rec_off ? out_rec_off[j] : 0);  // table offsets are record-relative
     if (status) status[j] = B200TFS_OK;
     if (!o.n_elems) continue;
-    const bool content_only = o.n_chunks == 0 && o.content_len && o.content_len == o.dst_bytes;
+    const bool content_only = o.n_runs == 0 && o.content_len && o.content_len == o.dst_bytes;
     // TF's MakeNdarray convention, asked for by the caller.  For packed varints the table cannot know the element count
     // (status OK unless there are fewer value BYTES than elements): the flag then tells the decode kernels to tolerate it.
     const bool pad = (o.flags & B200TFS_OF_PAD_EDGE) &&
@@ -923,11 +1038,11 @@ static int unpack_outputs_impl(b200tfs_ctx* c, const void* arena_dev, int32_t m,
     if (half_as_value) want = DT_HALF;
     uint8_t* dst = (uint8_t*)dst_dev[j];
     if (pad && want != o.dtype) return fail(B200TFS_E_DTYPE, "output %d: cast together with padding is not supported", j);
-    if (o.n_chunks == 0 && pad && !content_only) {   // no values at all: zeros
+    if (o.n_runs == 0 && pad && !content_only) {   // no values at all: zeros
       CU(cudaMemsetAsync(dst, 0, o.dst_bytes, c->stream));
       continue;
     }
-    if (o.n_chunks == 0) {
+    if (o.n_runs == 0) {
       // tolerant path chosen by the caller: raw little-endian bytes from tensor_content
       if (o.content_len != o.dst_bytes) return fail(B200TFS_E_SHAPE, "output %d: no values (tensor_content %llu bytes, need %llu)", j,
                                                      (unsigned long long)o.content_len, (unsigned long long)o.dst_bytes);
@@ -943,9 +1058,11 @@ static int unpack_outputs_impl(b200tfs_ctx* c, const void* arena_dev, int32_t m,
       else if (o.dtype == DT_FLOAT && want == DT_BFLOAT16) { op = OP_F2B; den = 2; }
       else return fail(B200TFS_E_DTYPE, "output %d: cast DT %d -> DT %d is not supported", j, o.dtype, want);
       uint64_t run = 0;
-      for (int k = 0; k < o.n_chunks; ++k) {
-        pb.payload(w + o.chunk_off[k], dst + run, o.chunk_len[k] * num / den, op);
-        run += o.chunk_len[k] * num / den;
+      for (const b200tfs_run& r : runs) {
+        const uint64_t bytes = (uint64_t)r.len * r.count * num / den;
+        if (r.count == 1) pb.payload(w + r.off, dst + run, bytes, op);
+        else pb.payload(w + r.off, dst + run, bytes, op, r.len, r.stride);
+        run += bytes;
       }
       if (pad) {
         if (run % di.elem_size || run > o.dst_bytes) return fail(B200TFS_E_SHAPE, "output %d: %llu value bytes for a tensor of %llu", j,
@@ -955,8 +1072,24 @@ static int unpack_outputs_impl(b200tfs_ctx* c, const void* arena_dev, int32_t m,
     } else {  // packed varints (incl. bool_val)
       if (want != o.dtype) return fail(B200TFS_E_DTYPE, "output %d: cast on varint dtypes is not supported", j);
       VarDecodeJob vj{};
-      vj.n_chunks = o.n_chunks;
-      for (int k = 0; k < o.n_chunks; ++k) { vj.src[k] = w + o.chunk_off[k]; vj.len[k] = o.chunk_len[k]; }
+      bool plain = runs.size() <= (size_t)B200TFS_MAX_RUNS;
+      for (const b200tfs_run& r : runs) plain = plain && r.count == 1;
+      if (plain) {
+        vj.n_chunks = (int)runs.size();
+        for (size_t k = 0; k < runs.size(); ++k) { vj.src[k] = w + runs[k].off; vj.len[k] = runs[k].len; }
+      } else {   // gather the pieces into one stream (same launch as the fixed-width moves, ahead of the decode kernels)
+        gather_cur = (gather_cur + 15) & ~15ull;
+        uint8_t* g = (uint8_t*)c->gather_dev.p + gather_cur;
+        uint64_t at = 0;
+        for (const b200tfs_run& r : runs) {
+          const uint64_t bytes = (uint64_t)r.len * r.count;
+          if (r.count == 1) pb.payload(w + r.off, g + at, bytes, OP_COPY);
+          else pb.payload(w + r.off, g + at, bytes, OP_COPY, r.len, r.stride);
+          at += bytes;
+        }
+        gather_cur += at;
+        vj.n_chunks = 1; vj.src[0] = g; vj.len[0] = at;
+      }
       vj.dst = dst; vj.n_elems = o.n_elems; vj.dtype = o.dtype; vj.out_index = j; vj.half_as_value = half_as_value; vj.pad_edge = pad;
       vjobs.push_back(vj);
     }
@@ -998,31 +1131,81 @@ FusedLayout fused_layout(int32_t n) {
 
 extern "C" {
 
-int b200tfs_decode_responses(b200tfs_ctx* c, const void* arena_dev, int32_t n, const uint64_t* rec_off, const uint64_t* rec_len,
-                             void* dst_dev, uint64_t dst_stride) {
-  if (!c || n < 0 || (n && (!arena_dev || !rec_off || !rec_len || !dst_dev))) return fail(B200TFS_E_ARG, "bad arguments");
-  if (n == 0) return B200TFS_OK;
-  if (dst_stride & 255) return fail(B200TFS_E_ARG, "dst_stride must be a multiple of 256");
-  if (!c->capturing) CU(cudaSetDevice(c->device));
+// take over the template a kernel left in pinned memory, if it is newer than what the host knows (stream must be idle)
+static void adopt_pinned_template(b200tfs_ctx* c) {
+  if (!c->tpl_pinned) return;
+  const TplInline& p = *c->tpl_pinned;
+  if (p.head.valid && (!c->tpl_known.head.valid || (int32_t)(p.head.serial - c->tpl_known.head.serial) > 0)) c->tpl_known = p;
+}
+
+// tile size of a decode launch over `wire_total` bytes: every CTA of the fused kernel first verifies the record's framing, so
+// big batches get fatter tiles than the plain move: measured 0.745 / 0.775 / 0.80 of peak at 64 / 128 / 256 KB
+static uint32_t decode_vpt(const b200tfs_ctx* c, int32_t n, const uint64_t* rec_len) {
   uint64_t wire_total = 0;
   for (int i = 0; i < n; ++i) wire_total += rec_len[i];
-  // every CTA of the fused kernel first verifies the record's framing (two dependent round trips), so big
-  // batches get fatter tiles than the plain move: measured 0.745 / 0.775 / 0.80 of peak at 64 / 128 / 256 KB
-  const uint32_t vpt = pick_vec_per_tile(c, wire_total, 262144);
+  return pick_vec_per_tile(c, wire_total, 262144);
+}
+
+// Walk record 0 on the host (its bytes are in host memory) and build its template: the launch that follows then takes the
+// template path from its first CTA on.  Returns false when the record does not qualify (the kernel will walk it).
+static bool host_template(const uint8_t* rec0, uint64_t len, uint32_t vpt, uint64_t dst_stride, uint32_t serial, Template* T) {
+  T->in.head.valid = 0;
+  if (!rec0 || len == 0 || len > 0x7FFFFFFFull) return false;
+  b200tfs_output outs[kFusedMaxOutputs + 1];
+  b200tfs_model_spec spec;
+  int cnt = 0;
+  Cursor cur;
+  cur_open_host(cur, rec0, (uint32_t)len);
+  SpillArea sp{nullptr, 0u, 0u};
+  const int st = walk_response(cur, kFusedMaxOutputs, outs, &cnt, &spec, sp);
+  if (st != B200TFS_OK) return false;
+  const uint64_t used = tpl_layout_outputs(outs, cnt, dst_stride);
+  for (int k = 0; k < cnt; ++k) if (outs[k].status == B200TFS_E_SIZE) return false;
+  // the kernel's own check: the chunks' tiles must fit the budget the launch gives the record
+  tpl_learn(T, cur, (uint32_t)len, outs, cnt, spec, st, vpt, (used + 255) & ~255ull, serial);
+  return T->in.head.valid != 0;
+}
+
+// host_rec0: record 0's bytes in HOST memory when the caller has them (the *_host entry points), else nullptr
+static int decode_launch(b200tfs_ctx* c, const void* arena_dev, int32_t n, const uint64_t* rec_off, const uint64_t* rec_len, void* dst_dev,
+                         uint64_t dst_stride, uint32_t vpt, const Template* host_tpl) {
   const uint64_t tile_bytes = 16ull * vpt;
   FusedLayout L = fused_layout(n);
   int rc;
   if ((rc = grow_host(c, c->fused_host, L.total))) return rc;
   if (!c->tpl_dev) {
     if (c->capturing) return fail(B200TFS_E_ARG, "run b200tfs_decode_responses once before capturing it");
-    CU(cudaMalloc(&c->tpl_dev, 2 * sizeof(Template)));
-    CU(cudaMemsetAsync(c->tpl_dev, 0, 2 * sizeof(Template), c->stream));
+    CU(cudaMalloc(&c->tpl_dev, 2 * sizeof(Template) + 64));   // + the three path counters (b200tfs_decode_stats)
+    CU(cudaMemsetAsync(c->tpl_dev, 0, 2 * sizeof(Template) + 64, c->stream));
+    CU(cudaHostAlloc((void**)&c->tpl_pinned, sizeof(TplInline), cudaHostAllocPortable | cudaHostAllocMapped));
+    memset(c->tpl_pinned, 0, sizeof(TplInline));
   }
   FusedParams fp{};
   fp.w = (const uint8_t*)arena_dev; fp.dst = (uint8_t*)dst_dev; fp.dst_stride = dst_stride; fp.n = n; fp.vpt = vpt;
   fp.tpl_read = (const Template*)c->tpl_dev + (c->tpl_flip & 1);
   fp.tpl_write = (Template*)c->tpl_dev + ((c->tpl_flip & 1) ^ 1);
   c->tpl_flip ^= 1;
+  fp.tpl_pinned = c->tpl_pinned;
+  fp.stats = (unsigned long long*)((uint8_t*)c->tpl_dev + 2 * sizeof(Template));
+  if (++c->serial == 0) c->serial = 1;
+  fp.serial = c->serial;
+  fp.tpli.head.valid = 0;
+  if (vpt <= kStageVecsHost) {   // the single-response / small-batch kernel takes its template from the parameters when the host has one
+    if (host_tpl && host_tpl->in.head.valid) {
+      // this launch's device template IS the host's walk of record 0: upload it where the kernel reads it
+      Slot* slot;
+      if ((rc = claim_slot(c, sizeof(Template), &slot))) return rc;
+      memcpy(slot->host.p, host_tpl, sizeof(Template));
+      CU(cudaMemcpyAsync((void*)fp.tpl_read, slot->host.p, sizeof(Template), cudaMemcpyHostToDevice, c->stream));
+      if (slot->done) { CU(cudaEventRecord(slot->done, c->stream)); slot->pending = true; }
+      c->tpl_known = host_tpl->in;
+      fp.tpli = host_tpl->in;
+    } else {
+      if (!c->capturing && cudaStreamQuery(c->stream) == cudaSuccess) adopt_pinned_template(c);
+      const TplHead& h = c->tpl_known.head;
+      if (h.valid && h.rec_len == rec_len[0] && h.vpt == vpt && h.dst_need <= dst_stride) fp.tpli = c->tpl_known;
+    }
+  }
   // the table is written by the kernel straight into pinned host memory (unified addressing): ~1 KB
   // of posted PCIe writes per record instead of a device table plus a copy node behind every launch
   uint8_t* d = (uint8_t*)c->fused_host.p;
@@ -1064,6 +1247,15 @@ int b200tfs_decode_responses(b200tfs_ctx* c, const void* arena_dev, int32_t n, c
   return B200TFS_OK;
 }
 
+int b200tfs_decode_responses(b200tfs_ctx* c, const void* arena_dev, int32_t n, const uint64_t* rec_off, const uint64_t* rec_len,
+                             void* dst_dev, uint64_t dst_stride) {
+  if (!c || n < 0 || (n && (!arena_dev || !rec_off || !rec_len || !dst_dev))) return fail(B200TFS_E_ARG, "bad arguments");
+  if (n == 0) return B200TFS_OK;
+  if (dst_stride & 255) return fail(B200TFS_E_ARG, "dst_stride must be a multiple of 256");
+  if (!c->capturing) CU(cudaSetDevice(c->device));
+  return decode_launch(c, arena_dev, n, rec_off, rec_len, dst_dev, dst_stride, decode_vpt(c, n, rec_len), nullptr);
+}
+
 int b200tfs_decode_results(b200tfs_ctx* c, int32_t n, b200tfs_output* outs, int32_t* n_outs, b200tfs_model_spec* specs,
                            int32_t* rec_status) {
   if (!c || n < 0) return fail(B200TFS_E_ARG, "bad arguments");
@@ -1079,11 +1271,27 @@ int b200tfs_decode_results(b200tfs_ctx* c, int32_t n, b200tfs_output* outs, int3
   return B200TFS_OK;
 }
 
+int b200tfs_decode_stats(b200tfs_ctx* c, uint64_t* param_template, uint64_t* device_template, uint64_t* walked) {
+  if (!c) return fail(B200TFS_E_ARG, "ctx is NULL");
+  if (c->capturing) return fail(B200TFS_E_ARG, "cannot read the counters during graph capture");
+  unsigned long long v[3] = {0, 0, 0};
+  if (c->tpl_dev) {
+    CU(cudaSetDevice(c->device));
+    CU(cudaMemcpyAsync(v, (uint8_t*)c->tpl_dev + 2 * sizeof(Template), sizeof v, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+  }
+  if (param_template) *param_template = v[0];
+  if (device_template) *device_template = v[1];
+  if (walked) *walked = v[2];
+  return B200TFS_OK;
+}
+
 int b200tfs_capture_begin(b200tfs_ctx* c) {
   if (!c) return fail(B200TFS_E_ARG, "ctx is NULL");
   if (c->capturing) return fail(B200TFS_E_ARG, "already capturing");
   CU(cudaSetDevice(c->device));
   CU(cudaStreamSynchronize(c->stream));
+  adopt_pinned_template(c);   // captured single-response decodes carry the template known now in their parameters
   for (auto& s : c->slots) s.pending = false;
   CU(cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeRelaxed));
   c->capturing = true;
@@ -1100,6 +1308,7 @@ int b200tfs_capture_end(b200tfs_ctx* c, void** graph_exec) {
   cudaError_t e = cudaGraphInstantiate(&ge, g, 0);
   cudaGraphDestroy(g);
   if (e != cudaSuccess) return fail(B200TFS_E_CUDA, "cudaGraphInstantiate: %s", cudaGetErrorString(e));
+  c->has_graphs = true;
   *graph_exec = ge;
   return B200TFS_OK;
 }
@@ -1231,6 +1440,7 @@ static int stage_wire(b200tfs_ctx* c, const void* wire_host, int32_t n, const ui
   int rc = grow_dev(c, c->stage_dev, hi + 64);
   if (rc) return rc;
   if (hi) CU(cudaMemcpyAsync(c->stage_dev.p, wire_host, hi, cudaMemcpyHostToDevice, c->stream));
+  c->stage_shift = 0;
   *span = hi;
   return B200TFS_OK;
 }
@@ -1262,12 +1472,29 @@ int b200tfs_decode_responses_host_async(b200tfs_ctx* c, const void* wire_host, i
                                         void* dst_host, uint64_t dst_stride) {
   if (!c || n < 0 || (n && (!wire_host || !rec_off || !rec_len || !dst_host))) return fail(B200TFS_E_ARG, "bad arguments");
   if (n == 0) return B200TFS_OK;
+  if (dst_stride & 255) return fail(B200TFS_E_ARG, "dst_stride must be a multiple of 256");
   CU(cudaSetDevice(c->device));
-  uint64_t span;
-  int rc = stage_wire(c, wire_host, n, rec_off, rec_len, &span);
+  // The wire is in host memory: walk record 0 HERE (sub-microsecond: the walk steps over the payload) so that the launch
+  // takes the template path from its first CTA on, and place the copy so that the largest value chunk lands 16-byte
+  // aligned on the device (aligned loads and stores, no funnel shifts).
+  const uint32_t vpt = decode_vpt(c, n, rec_len);
+  Template T;
+  uint64_t shift = 0;
+  const bool have = vpt <= kStageVecsHost && !c->capturing &&
+                    host_template((const uint8_t*)wire_host + rec_off[0], rec_len[0], vpt, dst_stride, c->serial + 1 ? c->serial + 1 : 1, &T);
+  if (have) {
+    uint32_t big = 0;
+    for (uint32_t q = 1; q < T.in.head.n_chunks; ++q) if (T.in.chunk[q].len > T.in.chunk[big].len) big = q;
+    if (T.in.head.n_chunks) shift = (16 - ((rec_off[0] + T.in.chunk[big].wire_off) & 15)) & 15;
+  }
+  uint64_t hi = 0;
+  for (int i = 0; i < n; ++i) hi = std::max(hi, rec_off[i] + rec_len[i]);
+  int rc = grow_dev(c, c->stage_dev, hi + 64);
   if (rc) return rc;
+  if (hi) CU(cudaMemcpyAsync((uint8_t*)c->stage_dev.p + shift, wire_host, hi, cudaMemcpyHostToDevice, c->stream));
+  c->stage_shift = shift;
   if ((rc = grow_dev(c, c->arena_dev, dst_stride * (uint64_t)n + 256))) return rc;
-  if ((rc = b200tfs_decode_responses(c, c->stage_dev.p, n, rec_off, rec_len, c->arena_dev.p, dst_stride))) return rc;
+  if ((rc = decode_launch(c, (uint8_t*)c->stage_dev.p + shift, n, rec_off, rec_len, c->arena_dev.p, dst_stride, vpt, have ? &T : nullptr))) return rc;
   CU(cudaMemcpyAsync(dst_host, c->arena_dev.p, dst_stride * (uint64_t)n, cudaMemcpyDeviceToHost, c->stream));
   return B200TFS_OK;
 }
@@ -1292,7 +1519,7 @@ int b200tfs_unpack_outputs_host(b200tfs_ctx* c, int32_t m, const b200tfs_output*
   if (rc) return rc;
   std::vector<void*> dd(m);
   for (int j = 0; j < m; ++j) dd[j] = (uint8_t*)c->arena_dev.p + off[j];
-  if ((rc = unpack_outputs_impl(c, c->stage_dev.p, m, outs, out_rec_off, dd.data(), dst_dtype, status, false))) return rc;
+  if ((rc = unpack_outputs_impl(c, (uint8_t*)c->stage_dev.p + c->stage_shift, m, outs, out_rec_off, dd.data(), dst_dtype, status, false))) return rc;
   for (int j = 0; j < m; ++j)
     if (nb[j]) {
       if (!dst_host[j]) return fail(B200TFS_E_ARG, "output %d: dst is NULL", j);

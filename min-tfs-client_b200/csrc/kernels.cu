@@ -32,6 +32,7 @@
 
 #include "kernels.h"
 #include "plan.h"
+#include "tpl.h"
 #include "walker.h"
 #include "wire.h"
 
@@ -121,13 +122,28 @@ __device__ __forceinline__ uint32_t f32_bits_to_bf16_bits(uint32_t w) {
   return (uint32_t)__bfloat16_as_ushort(__float2bfloat16_rn(__uint_as_float(w)));
 }
 
-__device__ __forceinline__ uint8_t gen_byte(uint32_t op, const uint8_t* src, uint64_t i) {
+// the logical source byte stream of an item: contiguous memory, or (gstride != 0) a row of pieces of `glen` value bytes
+// every `gstride` bytes - a run of unpacked elements on the wire (b200tfs_run)
+struct SrcView {
+  const uint8_t* p;
+  uint32_t glen, gstride;
+  __device__ __forceinline__ uint8_t operator[](uint64_t j) const {
+    if (gstride == 0) return p[j];
+    const uint64_t q = j / glen;
+    return p[q * gstride + (j - q * glen)];
+  }
+  __device__ __forceinline__ uint32_t u32(uint64_t j) const {
+    return (uint32_t)(*this)[j] | ((uint32_t)(*this)[j + 1] << 8) | ((uint32_t)(*this)[j + 2] << 16) | ((uint32_t)(*this)[j + 3] << 24);
+  }
+};
+
+__device__ __forceinline__ uint8_t gen_byte(uint32_t op, const SrcView& src, uint64_t i) {
   switch (op) {
     case OP_COPY: return src[i];
     case OP_BOOL: return src[i] != 0;
     case OP_QUIET_SRC:
     case OP_QUIET_DST: {
-      uint32_t w = quiet_f32(ld_u32_bytes(src + (i & ~3ull)));
+      uint32_t w = quiet_f32(src.u32(i & ~3ull));
       return (uint8_t)(w >> (8 * (i & 3)));
     }
     case OP_H2F: {
@@ -142,15 +158,16 @@ __device__ __forceinline__ uint8_t gen_byte(uint32_t op, const uint8_t* src, uin
     }
     case OP_F2H: {
       uint64_t e = i >> 1;
-      return (uint8_t)(f32_bits_to_f16_bits(ld_u32_bytes(src + 4 * e)) >> (8 * (i & 1)));
+      return (uint8_t)(f32_bits_to_f16_bits(src.u32(4 * e)) >> (8 * (i & 1)));
     }
     case OP_F2B: {
       uint64_t e = i >> 1;
-      return (uint8_t)(f32_bits_to_bf16_bits(ld_u32_bytes(src + 4 * e)) >> (8 * (i & 1)));
+      return (uint8_t)(f32_bits_to_bf16_bits(src.u32(4 * e)) >> (8 * (i & 1)));
     }
   }
   return 0;
 }
+__device__ __forceinline__ uint8_t gen_byte(uint32_t op, const uint8_t* src, uint64_t i) { return gen_byte(op, SrcView{src, 0u, 0u}, i); }
 
 // source bytes consumed per output byte, as a ratio num/den
 __device__ __forceinline__ uint64_t src_bytes_for(uint32_t op, uint64_t n_out) {
@@ -355,6 +372,15 @@ __host__ __device__ __forceinline__ uint32_t tiles_for(uint64_t n_out, uint32_t 
   return t ? (uint32_t)t : 1u;
 }
 
+// a gathered source (a run of unpacked elements): element-exact byte path, split by tile
+__device__ __forceinline__ void move_tile_gather(const SrcView& src, uint8_t* __restrict__ dst, uint64_t n_out, uint32_t op, uint32_t n_tiles,
+                                                 uint32_t tile, uint32_t vpt) {
+  const uint64_t b0 = (uint64_t)tile * vpt * 16;
+  uint64_t b1 = b0 + (uint64_t)vpt * 16;
+  if (b1 > n_out || tile + 1 == n_tiles) b1 = n_out;
+  for (uint64_t i = b0 + threadIdx.x; i < b1; i += blockDim.x) dst[i] = gen_byte(op, src, i);
+}
+
 template <class Mid>
 __device__ __forceinline__ bool move_tile(const uint8_t* __restrict__ src, uint8_t* __restrict__ dst, uint64_t n_out, uint32_t op,
                                           uint32_t n_tiles, uint32_t tile, uint32_t vpt, Mid& mid) {
@@ -442,6 +468,7 @@ __device__ __forceinline__ void move_body(const uint8_t* plan) {
       item = tr.item; tile = tr.tile;
     }
     const MoveItem& it = reinterpret_cast<const MoveItem*>(plan + ph.off_items)[item];
+    if (it.gstride) { move_tile_gather(SrcView{it.src, it.glen, it.gstride}, it.dst, it.n_out, it.op, it.n_tiles, tile, ph.vec_per_tile); return; }
     AlwaysGo go;
     move_tile(it.src, it.dst, it.n_out, it.op, it.n_tiles, tile, ph.vec_per_tile, go);
   } else {
@@ -450,7 +477,7 @@ __device__ __forceinline__ void move_body(const uint8_t* plan) {
     if (idx >= ph.n_small) return;
     const SmallItem si = reinterpret_cast<const SmallItem*>(plan + ph.off_small)[idx];
     const uint32_t op = si.op & ~OP_FLAG_BLOB;
-    const uint8_t* src = (si.op & OP_FLAG_BLOB) ? plan + si.src : reinterpret_cast<const uint8_t*>(si.src);
+    const SrcView src{(si.op & OP_FLAG_BLOB) ? plan + si.src : reinterpret_cast<const uint8_t*>(si.src), si.glen, si.gstride};
     const uint32_t lane = threadIdx.x & 31;
     for (uint32_t i = lane; i < si.n_out; i += 32) si.dst[i] = gen_byte(op, src, i);
   }
@@ -474,30 +501,39 @@ __global__ void __launch_bounds__(kMoveThreads, 3) move_kernel_inline(const __gr
 __global__ void __launch_bounds__(32) parse_responses_kernel(const uint8_t* __restrict__ w, const uint64_t* __restrict__ rec_off,
                                                              const uint64_t* __restrict__ rec_len, int n, int max_outputs,
                                                              b200tfs_output* outs, int32_t* n_outs, b200tfs_model_spec* specs,
-                                                             int32_t* status) {
+                                                             int32_t* status, SpillEntry* spill, uint32_t spill_per_rec, uint32_t* spill_used) {
   __shared__ __align__(16) uint8_t lines[32][256];
   int r = blockIdx.x * blockDim.x + threadIdx.x;
   if (r >= n) return;
   const uint64_t off = rec_off[r], len = rec_len[r];
+  spill_used[r] = 0;
   if (len > 0x7FFFFFFFull) { status[r] = B200TFS_E_PARSE; n_outs[r] = 0; return; }
   Cursor c;
   cur_open(c, w + off, (uint32_t)len, lines[threadIdx.x]);
+  SpillArea sp{spill_per_rec ? spill + (size_t)r * spill_per_rec : nullptr, spill_per_rec, 0u};
   int cnt = 0;
-  status[r] = walk_response(c, max_outputs, outs + (size_t)r * (max_outputs + 1), &cnt, specs + r);  // +1: scratch slot
+  b200tfs_output* mine = outs + (size_t)r * (max_outputs + 1);   // +1: scratch slot
+  status[r] = walk_response(c, max_outputs, mine, &cnt, specs + r, sp);
+  for (int k = 0; k < cnt; ++k) mine[k].spill_rec = (uint32_t)r;
   n_outs[r] = cnt;
+  spill_used[r] = sp.used;
 }
 
 __global__ void __launch_bounds__(32) parse_tensors_kernel(const uint8_t* __restrict__ w, const uint64_t* __restrict__ rec_off,
                                                            const uint64_t* __restrict__ rec_len, int n, b200tfs_output* outs,
-                                                           int32_t* status) {
+                                                           int32_t* status, SpillEntry* spill, uint32_t spill_per_rec, uint32_t* spill_used) {
   __shared__ __align__(16) uint8_t lines[32][256];
   int r = blockIdx.x * blockDim.x + threadIdx.x;
   if (r >= n) return;
   const uint64_t off = rec_off[r], len = rec_len[r];
+  spill_used[r] = 0;
   if (len > 0x7FFFFFFFull) { status[r] = B200TFS_E_PARSE; return; }
   Cursor c;
   cur_open(c, w + off, (uint32_t)len, lines[threadIdx.x]);
-  status[r] = walk_tensor_proto(c, outs + r);
+  SpillArea sp{spill_per_rec ? spill + (size_t)r * spill_per_rec : nullptr, spill_per_rec, 0u};
+  status[r] = walk_tensor_proto(c, outs + r, sp);
+  outs[r].spill_rec = (uint32_t)r;
+  spill_used[r] = sp.used;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -509,7 +545,7 @@ __global__ void __launch_bounds__(32) parse_tensors_kernel(const uint8_t* __rest
 // from shared memory (two conflict-free 128-bit loads per output vector and a funnel shift - no warp
 // shuffles), applies the fix-up and streams the vectors out.
 // ------------------------------------------------------------------------------------------------
-constexpr uint32_t kStageVecs = 2048;                       // destination vectors per chunk: 32 KB
+constexpr uint32_t kStageVecs = kStageVecsHost;             // destination vectors per chunk: 32 KB
 constexpr uint32_t kStageBuf = kStageVecs * 16 + 128;       // + the source block after the last vector, rounded
 constexpr uint32_t kStageBufs = 2;
 constexpr uint32_t kFusedDynSmem = kStageBufs * kStageBuf;
@@ -654,7 +690,7 @@ __device__ __forceinline__ void staged_finish(const StagedTile& t, const uint8_t
 // record's destination slot and finds which value chunk tile j falls in; CTA (record 0, tile 0) also
 // writes the template for the next launch.  CTA j == 0 of every record publishes the table.
 // ------------------------------------------------------------------------------------------------
-struct FusedJob { const uint8_t* src; uint8_t* dst; uint64_t n_out; uint32_t op, n_tiles, tile, valid; };
+struct FusedJob { const uint8_t* src; uint8_t* dst; uint64_t n_out; uint32_t op, n_tiles, tile, valid, glen, gstride; };
 
 __device__ __forceinline__ void publish_words(void* dst, const void* src, uint32_t bytes) {
   const uint64_t* s = reinterpret_cast<const uint64_t*>(src);
@@ -662,69 +698,10 @@ __device__ __forceinline__ void publish_words(void* dst, const void* src, uint32
   for (uint32_t i = threadIdx.x; i < bytes / 8; i += blockDim.x) d[i] = s[i];
 }
 
-// thread 0: build the template of a walked record (chunks sorted by wire offset, framing bytes)
-__device__ void learn_template(Template* T, Cursor& c, uint32_t len, const b200tfs_output* outs, int cnt, const b200tfs_model_spec& spec,
-                               int st, uint32_t vpt, uint64_t dst_need) {
-  T->valid = 0;
-  if (st != B200TFS_OK || cnt > kFusedMaxOutputs) return;
-  TplChunk ch[kTplChunks];
-  uint32_t n = 0;
-  for (int k = 0; k < cnt; ++k) {
-    const b200tfs_output& o = outs[k];
-    if (o.status != B200TFS_OK && o.status != B200TFS_E_SHAPE && o.status != B200TFS_E_KEY) return;
-    const DtypeInfo di = dtype_info(o.dtype);
-    const bool moved = (o.status == B200TFS_OK) && di.kind == VK_FIXED && o.n_elems;
-    uint32_t run = 0;
-    for (int q = 0; q < o.n_chunks; ++q) {
-      if (n >= kTplChunks) return;
-      TplChunk x;
-      x.wire_off = (uint32_t)o.chunk_off[q]; x.len = (uint32_t)o.chunk_len[q];
-      x.dst_off = (uint32_t)o.dst_off + run; x.op = (o.dtype == DT_FLOAT) ? OP_QUIET_DST : OP_COPY;
-      x.n_tiles = moved ? tiles_for(o.chunk_len[q], vpt) : 0u;
-      x.is_varint = (o.flags & B200TFS_OF_VARINT) ? 1u : 0u; x.fpos = 0; x.pad = 0;
-      if (o.dst_off + run + o.chunk_len[q] > 0xFFFFFFFFull) return;
-      run += (uint32_t)o.chunk_len[q];
-      ch[n++] = x;
-    }
-    if (o.content_len) {  // tensor_content: opaque like a payload, never moved here
-      if (n >= kTplChunks) return;
-      TplChunk x;
-      x.wire_off = (uint32_t)o.content_off; x.len = (uint32_t)o.content_len; x.dst_off = 0; x.op = OP_COPY; x.n_tiles = 0;
-      x.is_varint = 0; x.fpos = 0; x.pad = 0;
-      ch[n++] = x;
-    }
-  }
-  for (uint32_t i = 1; i < n; ++i) {  // by wire offset; tiles are handed out in this order
-    TplChunk x = ch[i];
-    uint32_t k = i;
-    while (k > 0 && ch[k - 1].wire_off > x.wire_off) { ch[k] = ch[k - 1]; --k; }
-    ch[k] = x;
-  }
-  uint32_t payload = 0, tiles = 0;
-  for (uint32_t i = 0; i < n; ++i) {
-    if (i && ch[i].wire_off < ch[i - 1].wire_off + ch[i - 1].len) return;  // overlapping (content inside? never) - be safe
-    ch[i].fpos = ch[i].wire_off - payload;
-    payload += ch[i].len;
-    tiles += ch[i].n_tiles;
-  }
-  const uint32_t framing = len - payload;
-  if (framing > kTplFraming) return;
-  uint32_t w = 0, ci = 0;
-  for (uint32_t i = 0; i < framing; ++i) {
-    while (ci < n && ch[ci].wire_off == w) { w += ch[ci].len; ++ci; }
-    T->framing[i] = rd8(c, w++);
-  }
-  for (uint32_t i = 0; i < n; ++i) T->chunk[i] = ch[i];
-  T->n_chunks = n; T->n_outs = (uint32_t)cnt; T->framing_len = framing; T->rec_len = len; T->vpt = vpt; T->total_tiles = tiles;
-  T->dst_need = dst_need; T->spec = spec;
-  for (int k = 0; k < cnt; ++k) T->outs[k] = outs[k];
-  __threadfence();
-  T->valid = 1;
-}
-
-// the serial walk, kept out of line so the fast path's registers stay lean (thread 0 only)
-__device__ __noinline__ void fused_slow_path(const FusedParams& fp, uint32_t r, uint32_t j, uint32_t budget, const uint8_t* rec, uint64_t len,
-                                             uint8_t* dst_slot, uint8_t* lines, b200tfs_output* outs_s, b200tfs_model_spec& spec_s,
+// the serial walk, kept out of line so the fast path's registers stay lean (thread 0 only).  `publish`: this CTA writes the
+// record's table (the CTA with j == 0 on the walk path; the record's last CTA when it could not vouch for the template's table)
+__device__ __noinline__ void fused_slow_path(const FusedParams& fp, uint32_t r, uint32_t j, uint32_t budget, bool publish, const uint8_t* rec,
+                                             uint64_t len, uint8_t* dst_slot, uint8_t* lines, b200tfs_output* outs_s, b200tfs_model_spec& spec_s,
                                              FusedJob& job) {
     int cnt = 0, st;
     Cursor c;
@@ -732,21 +709,14 @@ __device__ __noinline__ void fused_slow_path(const FusedParams& fp, uint32_t r, 
     if (len > 0x7FFFFFFFull) st = B200TFS_E_PARSE;
     else {
       cur_open(c, rec, (uint32_t)len, lines);
-      st = walk_response(c, kFusedMaxOutputs, outs_s, &cnt, &spec_s);
+      SpillArea sp{nullptr, 0u, 0u};   // no spill area behind the single-launch decode: such a record is left to the two-phase calls
+      st = walk_response(c, kFusedMaxOutputs, outs_s, &cnt, &spec_s, sp);
+      if (st == B200TFS_E_SPILL) st = B200TFS_E_NONCANONICAL;
     }
     uint64_t cursor = 0;   // bytes used in this record's destination slot
     uint32_t t_base = 0;   // tiles consumed by earlier chunks
     if (st == B200TFS_OK) {
-      // lay out in wire order of the chunks so that the template (sorted by wire offset) agrees
-      for (int k = 0; k < cnt; ++k) {
-        b200tfs_output& o = outs_s[k];
-        if (o.status != B200TFS_OK || !o.n_elems) continue;
-        if (dtype_info(o.dtype).kind != VK_FIXED) continue;   // varint / string outputs: tabulated only (two-phase unpack)
-        cursor = (cursor + 255) & ~255ull;
-        if (cursor + o.dst_bytes > fp.dst_stride) { o.status = B200TFS_E_SIZE; continue; }
-        o.dst_off = cursor;
-        cursor += o.dst_bytes;
-      }
+      cursor = tpl_layout_outputs(outs_s, cnt, fp.dst_stride);
       // tiles are handed out by ascending wire offset of the chunk (same order the template uses)
       uint32_t done_mask[kFusedMaxOutputs] = {0};
       for (;;) {
@@ -754,38 +724,64 @@ __device__ __noinline__ void fused_slow_path(const FusedParams& fp, uint32_t r, 
         for (int k = 0; k < cnt; ++k) {
           const b200tfs_output& o = outs_s[k];
           if (o.status != B200TFS_OK || !o.n_elems || dtype_info(o.dtype).kind != VK_FIXED) continue;
-          for (int q = 0; q < o.n_chunks; ++q)
-            if (!(done_mask[k] >> q & 1) && o.chunk_off[q] < best) { best = o.chunk_off[q]; bk = k; bq = q; }
+          for (int q = 0; q < o.n_runs; ++q)
+            if (!(done_mask[k] >> q & 1) && o.runs[q].off < best) { best = o.runs[q].off; bk = k; bq = q; }
         }
         if (bk < 0) break;
         done_mask[bk] |= 1u << bq;
         const b200tfs_output& o = outs_s[bk];
         uint64_t run = 0;
-        for (int q = 0; q < bq; ++q) run += o.chunk_len[q];
-        const uint32_t nt = tiles_for(o.chunk_len[bq], fp.vpt);
+        for (int q = 0; q < bq; ++q) run += (uint64_t)o.runs[q].len * o.runs[q].count;
+        const b200tfs_run& rn = o.runs[bq];
+        const uint64_t bytes = (uint64_t)rn.len * rn.count;
+        const uint32_t nt = tiles_for(bytes, fp.vpt);
         if (j >= t_base && j < t_base + nt) {
-          job.src = rec + o.chunk_off[bq]; job.dst = dst_slot + o.dst_off + run; job.n_out = o.chunk_len[bq];
+          job.src = rec + rn.off; job.dst = dst_slot + o.dst_off + run; job.n_out = bytes;
           job.op = (o.dtype == DT_FLOAT) ? OP_QUIET_DST : OP_COPY; job.n_tiles = nt; job.tile = j - t_base; job.valid = 1;
+          job.glen = rn.count > 1 ? rn.len : 0u; job.gstride = rn.count > 1 ? rn.stride : 0u;   // a row of unpacked elements: gathered
         }
         t_base += nt;
       }
       if (t_base > budget) st = B200TFS_E_NONCANONICAL;  // more chunks than the launch budgeted tiles for
     }
-    if (j == 0) {
+    if (publish) {
+      if (fp.stats) atomicAdd(&fp.stats[2], 1ull);
       fp.status[r] = st;
       fp.n_outs[r] = (st == B200TFS_OK) ? cnt : 0;
       fp.specs[r] = spec_s;
       for (int k = 0; k < cnt && st == B200TFS_OK; ++k) fp.outs[(size_t)r * kFusedMaxOutputs + k] = outs_s[k];
-      if (r == 0) {
-        if (len <= 0x7FFFFFFFull) learn_template(fp.tpl_write, c, (uint32_t)len, outs_s, cnt, spec_s, st, fp.vpt, (cursor + 255) & ~255ull);
-        else fp.tpl_write->valid = 0;
+      if (r == 0) {   // leave the template for the next launch, and its inline part in pinned memory for the host
+        if (len <= 0x7FFFFFFFull) tpl_learn(fp.tpl_write, c, (uint32_t)len, outs_s, cnt, spec_s, st, fp.vpt, (cursor + 255) & ~255ull, fp.serial);
+        else fp.tpl_write->in.head.valid = 0;
+        if (fp.tpl_pinned) {
+          fp.tpl_pinned->head.valid = 0;
+          if (fp.tpl_write->in.head.valid) {
+            const uint64_t* s8 = reinterpret_cast<const uint64_t*>(&fp.tpl_write->in);
+            uint64_t* d8 = reinterpret_cast<uint64_t*>(fp.tpl_pinned);
+            for (uint32_t q = sizeof(TplHead) / 8; q < sizeof(TplInline) / 8; ++q) d8[q] = s8[q];
+            __threadfence_system();
+            for (uint32_t q = 0; q < sizeof(TplHead) / 8; ++q) d8[q] = s8[q];   // the head (valid flag in its first word) last
+          }
+        }
       }
     }
     if (st != B200TFS_OK) job.valid = 0;
 }
 
-// STAGED: tiles of more than one 32 KB chunk (big batches) take the TMA-staged path above; the other instantiation - a
-// single response, small batches - carries none of that code, so its register allocation is untouched by it.
+// decode_fused_kernel: the whole PredictResponse decode in ONE launch.  CTA b belongs to record r with local tile j.
+//
+// Framing template (tpl.h).  In steady state every response of a model has the same framing (same keys, dtypes, dims => the
+// same non-payload bytes at the same offsets).  The template rides in the kernel parameters when the host has it (it walked
+// record 0 itself, or found the previous launch's template in pinned memory with the stream idle): the CTA issues its tile's
+// loads at once and checks, one byte per thread, that this record's framing bytes equal the template's while those loads are
+// in flight (packed-varint chunks must still end on a terminator) - one DRAM round trip in all.  Otherwise the template the
+// previous launch left in device memory is used (one more dependent load).  A record that misses the template is walked:
+// thread 0 goes through the tags with the line cache (a lone GPU lane needs ~15 us for ~100 header bytes), lays the outputs out
+// and finds which value chunk tile j falls in; CTA (record 0, tile 0) also leaves the template for the next launch.
+//
+// STAGED: tiles of more than one 32 KB chunk (big batches) take the TMA-staged path above; the other instantiation - a single
+// response, small batches - carries none of that code and instead runs the verdict as the `mid` hook of the tile move (the
+// registers that holds across the barrier cost the big-batch kernel a CTA per SM, so only this one does it).
 template <bool STAGED>
 __device__ __forceinline__ void decode_fused_body(const FusedParams& fp) {
   pdl_launch_dependents();
@@ -795,6 +791,8 @@ __device__ __forceinline__ void decode_fused_body(const FusedParams& fp) {
   __shared__ FusedJob job;
   extern __shared__ __align__(128) uint8_t stage_smem[];     // STAGED: kFusedDynSmem bytes, the staged tile's two buffers
   __shared__ __align__(8) uint64_t stage_bars[kStageBufs];
+  __shared__ TplChunk ch_s[kTplChunks];
+  __shared__ TplHead th_s;
   if (STAGED && threadIdx.x == 0) {   // made visible by the template staging's barrier
     for (uint32_t q = 0; q < kStageBufs; ++q) mbar_init(&stage_bars[q], 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -817,31 +815,31 @@ __device__ __forceinline__ void decode_fused_body(const FusedParams& fp) {
   uint8_t* dst_slot = fp.dst + (uint64_t)r * fp.dst_stride;
   pdl_wait_prior_grids();   // the template was written by the previous decode launch; the wire may be fresh too
 
-  // ---- fast path: does this record carry the template's framing? ----
-  // The template header and chunk table are staged in shared memory by five threads while every
-  // thread fetches its own template framing byte (all independent loads: one L2 round trip), then
-  // the record's framing byte (one DRAM round trip), then the tile.  (An earlier version kept the
-  // chunk table in a per-thread array: it landed in local memory, 32 KB of extra DRAM traffic per CTA.)
-  // The table is published by the record's LAST CTA - a slack CTA with no tile - so no tile waits on it.
+  // One template per launch: the one in the kernel parameters when the host supplied it, else the one the previous launch left
+  // in device memory.  (Trying both in turn kept too much state alive across the tile move: 500-700 bytes of spills.)  A record
+  // that misses it is walked; record 0's walk leaves the new template in device AND pinned memory, where the host finds it.
   const Template* T = fp.tpl_read;
+  const bool inl = !STAGED && fp.tpli.head.valid != 0;   // the batch kernel hides the template load behind its bulk copies: no gain, and 80 bytes of spills
   uint32_t live = budget;   // CTAs of this record able to take a tile, should the walk be needed
-  __shared__ TplChunk ch_s[kTplChunks];
-  __shared__ struct { uint32_t valid, n_chunks, n_outs, framing_len, vpt, total_tiles; uint64_t rec_len, dst_need; } th_s;
+  const uint32_t i = threadIdx.x;
   {
-    const uint32_t i = threadIdx.x;
-    const uint8_t want = T->framing[i];
-    if (i < kTplChunks) ch_s[i] = T->chunk[i];
-    if (i == kTplChunks) {
-      th_s.valid = T->valid; th_s.n_chunks = T->n_chunks; th_s.n_outs = T->n_outs; th_s.framing_len = T->framing_len;
-      th_s.vpt = T->vpt; th_s.total_tiles = T->total_tiles; th_s.rec_len = T->rec_len; th_s.dst_need = T->dst_need;
+    uint8_t want;
+    if (inl) {
+      want = fp.tpli.framing[i];
+      if (i < kTplChunks) ch_s[i] = fp.tpli.chunk[i];
+      if (i == kTplChunks) th_s = fp.tpli.head;
+    } else {
+      // five threads stage the header and chunk table while every thread fetches its own template framing byte (all
+      // independent loads: one L2 round trip).  (An earlier version kept the chunk table in a per-thread array: it landed in
+      // local memory, 32 KB of extra DRAM traffic per CTA.)
+      want = T->in.framing[i];
+      if (i < kTplChunks) ch_s[i] = T->in.chunk[i];
+      if (i == kTplChunks) th_s = T->in.head;
     }
     __syncthreads();
     const uint32_t nch = th_s.n_chunks;
     if (th_s.valid && th_s.rec_len == len && th_s.vpt == fp.vpt && th_s.dst_need <= fp.dst_stride && th_s.total_tiles < budget) {
-      // The verdict needs this record's framing bytes (a DRAM round trip).  (Tried: running it as the `mid`
-      // hook of the tile move so that it overlaps the tile's own loads.  Single 4 MiB decode 4.64 -> 4.49 us,
-      // but the registers held across the barrier cost a CTA per SM and the 1024-record batch decode dropped
-      // from 0.74 to 0.65 of peak, so the verdict runs first.)
+      // The verdict needs this record's framing bytes (a DRAM round trip).
       auto verdict = [&]() -> bool {
         bool same = true;
         if (i < th_s.framing_len) {
@@ -864,15 +862,16 @@ __device__ __forceinline__ void decode_fused_body(const FusedParams& fp) {
       // verdict after all, the CTAs that stayed walk it; if it then needs more tiles than stayed, its status says so.
       if (mine == kTplChunks && j != 0 && j != budget - 1) return;
       live = max(th_s.total_tiles, 1u);
-      // the tile's bytes start moving now (TMA bulk copies into shared memory), the verdict's round trip overlaps theirs
-      StagedTile stg{};
-      if (STAGED && mine < kTplChunks)
-        stg = staged_begin(rec + ch_s[mine].wire_off, dst_slot + ch_s[mine].dst_off, ch_s[mine].len, ch_s[mine].op, j - t_base, fp.vpt,
-                           stage_smem, stage_bars);
-      const bool hit = verdict();
-      if (hit) {
-        if (mine < kTplChunks) {
-          if (STAGED && stg.use)
+      bool hit;
+      if (STAGED) {
+        // the tile's bytes start moving now (TMA bulk copies into shared memory), the verdict's round trip overlaps theirs
+        StagedTile stg{};
+        if (mine < kTplChunks)
+          stg = staged_begin(rec + ch_s[mine].wire_off, dst_slot + ch_s[mine].dst_off, ch_s[mine].len, ch_s[mine].op, j - t_base, fp.vpt,
+                             stage_smem, stage_bars);
+        hit = verdict();
+        if (hit && mine < kTplChunks) {
+          if (stg.use)
             staged_finish(stg, rec + ch_s[mine].wire_off, dst_slot + ch_s[mine].dst_off, ch_s[mine].len, ch_s[mine].op, ch_s[mine].n_tiles,
                           j - t_base, stage_smem, stage_bars);
           else {
@@ -881,29 +880,47 @@ __device__ __forceinline__ void decode_fused_body(const FusedParams& fp) {
                       fp.vpt, go);
           }
         }
-        if (j == budget - 1) {
-          publish_words(fp.outs + (size_t)r * kFusedMaxOutputs, T->outs, th_s.n_outs * (uint32_t)sizeof(b200tfs_output));
-          publish_words(fp.specs + r, &T->spec, (uint32_t)sizeof(b200tfs_model_spec));
-          if (threadIdx.x == 0) { fp.status[r] = B200TFS_OK; fp.n_outs[r] = (int32_t)th_s.n_outs; }
-          // hand the template on to the next launch (launches alternate between the two slots)
-          if (r == 0) publish_words(fp.tpl_write, T, (uint32_t)sizeof(Template));
+        if (!hit) staged_drain(stg, stage_bars, 0);   // let the copies land, then walk the record
+      } else if (mine < kTplChunks) {
+        // the tile's loads go out first; the verdict runs while they are in flight and decides whether anything is stored
+        hit = move_tile(rec + ch_s[mine].wire_off, dst_slot + ch_s[mine].dst_off, ch_s[mine].len, ch_s[mine].op, ch_s[mine].n_tiles, j - t_base,
+                        fp.vpt, verdict);
+      } else hit = verdict();
+      if (hit) {
+        if (j == budget - 1) {   // the record's last CTA - a slack CTA with no tile - publishes the table, so no tile waits on it
+          // the table entries live in the device template; an inline template vouches for them only if both carry the same serial
+          const bool table_ok = !inl || (T->in.head.valid && T->in.head.serial == th_s.serial);
+          if (table_ok) {
+            if (threadIdx.x == 0 && fp.stats) atomicAdd(&fp.stats[inl ? 0 : 1], 1ull);
+            publish_words(fp.outs + (size_t)r * kFusedMaxOutputs, T->outs, th_s.n_outs * (uint32_t)sizeof(b200tfs_output));
+            publish_words(fp.specs + r, &T->spec, (uint32_t)sizeof(b200tfs_model_spec));
+            if (threadIdx.x == 0) { fp.status[r] = B200TFS_OK; fp.n_outs[r] = (int32_t)th_s.n_outs; }
+            // hand the template on to the next launch (launches alternate between the two slots)
+            if (r == 0) publish_words(fp.tpl_write, T, (uint32_t)sizeof(Template));
+          } else if (threadIdx.x == 0) {
+            fused_slow_path(fp, r, 0, budget, true, rec, len, dst_slot, lines, outs_s, spec_s, job);   // walk for the table only
+          }
         }
         return;
       }
-      if (STAGED) staged_drain(stg, stage_bars, 0);   // verdict failed: let the copies land, then walk the record
     }
   }
 
-  // ---- slow path: thread 0 walks the tags ----
-  if (threadIdx.x == 0) fused_slow_path(fp, r, j, live, rec, len, dst_slot, lines, outs_s, spec_s, job);
+  // ---- the walk: thread 0 goes through the tags ----
+  if (threadIdx.x == 0) fused_slow_path(fp, r, j, live, j == 0, rec, len, dst_slot, lines, outs_s, spec_s, job);
   __syncthreads();
   if (job.valid) {
-    AlwaysGo go;
-    move_tile(job.src, job.dst, job.n_out, job.op, job.n_tiles, job.tile, fp.vpt, go);
+    if (job.gstride) move_tile_gather(SrcView{job.src, job.glen, job.gstride}, job.dst, job.n_out, job.op, job.n_tiles, job.tile, fp.vpt);
+    else {
+      AlwaysGo go;
+      move_tile(job.src, job.dst, job.n_out, job.op, job.n_tiles, job.tile, fp.vpt, go);
+    }
   }
 }
 
-__global__ void __launch_bounds__(kMoveThreads, 3) decode_fused_kernel(const __grid_constant__ FusedParams fp) { decode_fused_body<false>(fp); }
+// two CTAs per SM: the tile (8 x 128-bit per thread) stays in registers across the verdict's barrier without spilling; this instantiation serves
+// single responses and small batches, where a third resident CTA has nothing to hide
+__global__ void __launch_bounds__(kMoveThreads, 2) decode_fused_kernel(const __grid_constant__ FusedParams fp) { decode_fused_body<false>(fp); }
 __global__ void __launch_bounds__(kMoveThreads, 3) decode_fused_staged_kernel(const __grid_constant__ FusedParams fp) { decode_fused_body<true>(fp); }
 
 // ------------------------------------------------------------------------------------------------
@@ -959,16 +976,17 @@ cudaError_t launch_move(const uint8_t* plan_dev, const uint8_t* plan_host, uint3
 
 cudaError_t launch_parse_responses(const uint8_t* w, const uint64_t* rec_off, const uint64_t* rec_len, int n, int max_outputs,
                                    b200tfs_output* outs, int32_t* n_outs, b200tfs_model_spec* specs, int32_t* status,
-                                   cudaStream_t stream) {
+                                   void* spill, uint32_t spill_per_rec, uint32_t* spill_used, cudaStream_t stream) {
   if (n <= 0) return cudaSuccess;
-  parse_responses_kernel<<<(n + 31) / 32, 32, 0, stream>>>(w, rec_off, rec_len, n, max_outputs, outs, n_outs, specs, status);
+  parse_responses_kernel<<<(n + 31) / 32, 32, 0, stream>>>(w, rec_off, rec_len, n, max_outputs, outs, n_outs, specs, status,
+                                                          (SpillEntry*)spill, spill_per_rec, spill_used);
   return cudaGetLastError();
 }
 
 cudaError_t launch_parse_tensors(const uint8_t* w, const uint64_t* rec_off, const uint64_t* rec_len, int n, b200tfs_output* outs,
-                                 int32_t* status, cudaStream_t stream) {
+                                 int32_t* status, void* spill, uint32_t spill_per_rec, uint32_t* spill_used, cudaStream_t stream) {
   if (n <= 0) return cudaSuccess;
-  parse_tensors_kernel<<<(n + 31) / 32, 32, 0, stream>>>(w, rec_off, rec_len, n, outs, status);
+  parse_tensors_kernel<<<(n + 31) / 32, 32, 0, stream>>>(w, rec_off, rec_len, n, outs, status, (SpillEntry*)spill, spill_per_rec, spill_used);
   return cudaGetLastError();
 }
 

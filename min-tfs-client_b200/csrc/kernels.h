@@ -13,13 +13,17 @@ namespace b200tfs {
 cudaError_t launch_move(const uint8_t* plan_dev, const uint8_t* plan_host, uint32_t plan_bytes, uint32_t n_tiles,
                         uint32_t n_small, cudaStream_t stream);
 
+// spill: n * spill_per_rec entries of kSpillEntryBytes (walker.h SpillEntry) for dims / value runs beyond the table's inline
+// arrays; spill_used[r] receives how many entries record r wanted (more than spill_per_rec: its status is B200TFS_E_SPILL)
+constexpr uint32_t kSpillEntryBytes = 32;
 cudaError_t launch_parse_responses(const uint8_t* w, const uint64_t* rec_off, const uint64_t* rec_len, int n, int max_outputs,
                                    b200tfs_output* outs, int32_t* n_outs, b200tfs_model_spec* specs, int32_t* status,
-                                   cudaStream_t stream);
+                                   void* spill, uint32_t spill_per_rec, uint32_t* spill_used, cudaStream_t stream);
 cudaError_t launch_parse_tensors(const uint8_t* w, const uint64_t* rec_off, const uint64_t* rec_len, int n, b200tfs_output* outs,
-                                 int32_t* status, cudaStream_t stream);
+                                 int32_t* status, void* spill, uint32_t spill_per_rec, uint32_t* spill_used, cudaStream_t stream);
 
 cudaError_t launch_decode_fused(const FusedParams& fp, uint32_t grid, cudaStream_t stream);
+constexpr uint32_t kStageVecsHost = 2048;   // == kStageVecs (kernels.cu): launches with fatter tiles run the TMA-staged batch kernel
 uint32_t tiles_for_host(uint64_t n_out, uint32_t vpt);
 // pad elements [have, n_elems) of dst with element have-1 (zeros if have == 0); have from the host or, if have_dev, the device
 cudaError_t launch_fill_edge(uint8_t* dst, uint32_t elem_size, uint64_t have, const unsigned long long* have_dev, uint64_t n_elems,

@@ -31,6 +31,8 @@ struct MoveItem {     // one large payload, tiled across CTAs
   uint64_t n_out;     // bytes written
   uint32_t op;
   uint32_t n_tiles;   // max(1, ceil(ceil(n_out/16) / vec_per_tile))
+  uint32_t glen, gstride;  // gstride != 0: the source is a row of pieces, `glen` value bytes every `gstride` bytes (a run of
+                           // unpacked elements, b200tfs_run): logical source byte j lies at src[(j / glen) * gstride + j % glen]
 };
 
 struct TileRef { uint32_t item; uint32_t tile; };
@@ -40,6 +42,7 @@ struct SmallItem {    // one header fragment or small payload: a warp moves it
   uint8_t* dst;
   uint32_t n_out;
   uint32_t op;
+  uint32_t glen, gstride;  // as in MoveItem
 };
 
 struct PlanHeader {
@@ -65,12 +68,22 @@ struct FusedInline { uint64_t off[kFusedInlineRecs], len[kFusedInlineRecs]; uint
 constexpr uint32_t kTplChunks = 4;
 constexpr uint32_t kTplFraming = 256;   // == kMoveThreads: one framing byte per thread
 struct TplChunk { uint32_t wire_off, len, dst_off, op, n_tiles, is_varint, fpos, pad; };  // record-relative
-struct Template {
+struct TplHead {
   uint32_t valid, n_chunks, n_outs, framing_len;
   uint64_t rec_len, dst_need;
   uint32_t vpt, total_tiles;
+  uint32_t serial, pad;        // which learning produced it (the table entries below belong to exactly this serial)
+};
+// the part of a template every CTA needs before it can start on its tile: small enough to ride in the kernel parameters
+// (no load at all ahead of the tile's loads) when the host knows it - because it walked record 0 itself (host-buffer entry
+// points) or because an earlier launch left it in pinned memory and the stream has been idle since
+struct TplInline {
+  TplHead head;
   TplChunk chunk[kTplChunks];
   uint8_t framing[kTplFraming];
+};
+struct Template {
+  TplInline in;
   b200tfs_model_spec spec;
   b200tfs_output outs[kFusedMaxOutputs];
 };
@@ -91,7 +104,12 @@ struct FusedParams {
   const uint64_t* rec_len;
   const Template* tpl_read;  // template written by the previous launch on this context (may be invalid)
   Template* tpl_write;       // where record 0 of this launch leaves its template
+  TplInline* tpl_pinned;     // pinned host copy of the inline part, written whenever a template is learnt (valid flag last)
+  unsigned long long* stats; // device counters: records served by [0] the template in the parameters, [1] the device template, [2] the walk
+  uint32_t serial;           // stamp for a template learnt by THIS launch
+  uint32_t pad;
   FusedInline inl;
+  TplInline tpli;            // head.valid != 0: the template as the host knows it (tier 1; tpl_read is tier 2, the walk tier 3)
 };
 
 // ---- packed-varint jobs ------------------------------------------------------------------------

@@ -259,20 +259,79 @@ B2_HD bool validate_nested(Cursor& c, uint32_t type, uint32_t len) {
 
 // Begin a fresh output record: only the fields the walk accumulates into.
 B2_HD void out_begin(b200tfs_output& o) {
-  o.key_off = 0; o.key_len = 0; o.dtype = 0; o.rank = 0; o.flags = 0; o.value_field = 0; o.n_chunks = 0;
+  o.key_off = 0; o.key_len = 0; o.dtype = 0; o.rank = 0; o.flags = 0; o.value_field = 0; o.n_runs = 0;
   o.content_off = 0; o.content_len = 0; o.msg_off = 0; o.msg_len = 0;
-  o.n_elems = 0; o.dst_bytes = 0; o.n_strings = 0; o.dst_off = 0; o.status = B200TFS_OK; o.reserved = 0;
+  o.n_elems = 0; o.dst_bytes = 0; o.n_strings = 0; o.dst_off = 0; o.status = B200TFS_OK;
+  o.n_inline = 0; o.spill_rec = 0; o.spill_seq = 0;
 }
 
-// Walk state that does not belong in the table: which field each recorded chunk came from.
-struct ChunkTags {
-  uint8_t field[B200TFS_MAX_CHUNKS];
-  bool chunk_overflow, rank_overflow;
+// What does not fit the table's inline arrays - dims past B200TFS_MAX_RANK, value runs past B200TFS_MAX_RUNS - is
+// appended to the record's spill region (global memory on the device; the two-phase parse sizes it and runs again
+// when a record wants more: `used` keeps counting past `cap`).  Entries carry the ordinal of the map entry they
+// belong to, so that a later entry with the same key (which replaces the earlier one) is told apart.
+struct SpillEntry {
+  uint32_t kind;        // 1 = dim (run.off holds the size), 2 = value run
+  uint32_t seq;         // map-entry ordinal inside the record
+  b200tfs_run run;
 };
+struct SpillArea {
+  SpillEntry* e;        // this record's region (nullptr when cap == 0)
+  uint32_t cap, used;
+};
+enum : uint32_t { SPILL_DIM = 1, SPILL_RUN = 2 };
+
+// Walk state of one map entry that does not belong in the table.
+struct WalkAux {
+  uint32_t seq;         // ordinal of the entry being walked
+  uint32_t last_spill;  // index (in the record's region) of the last spilled RUN of this entry, ~0u = none
+  bool too_deep;        // variant_val nesting beyond kNestedDepth
+};
+B2_HD void aux_begin(WalkAux& a, uint32_t seq) { a.seq = seq; a.last_spill = ~0u; a.too_deep = false; }
+
+B2_HD void spill_push(SpillArea& sp, uint32_t kind, uint32_t seq, const b200tfs_run& r) {
+  if (sp.used < sp.cap) { SpillEntry& e = sp.e[sp.used]; e.kind = kind; e.seq = seq; e.run = r; }
+  ++sp.used;
+}
+
+B2_HD void add_dim(b200tfs_output& o, SpillArea& sp, const WalkAux& a, int64_t size) {
+  if (o.rank < B200TFS_MAX_RANK) o.dims[o.rank] = size;
+  else {
+    b200tfs_run r; r.off = (uint64_t)size; r.len = 0; r.count = 0; r.stride = 0; r.field = 0;
+    spill_push(sp, SPILL_DIM, a.seq, r);
+    o.flags |= B200TFS_OF_SPILLED;
+  }
+  ++o.rank;
+}
+
+// One more piece of values: `len` bytes at record offset `off`, from TensorProto field `field`.  Short pieces
+// (unpacked scalar elements: at most ten bytes) that follow the previous one at a constant distance extend its run,
+// so that a field written element by element - however long - stays ONE table entry; longer pieces (packed
+// occurrences) each get a run of their own and keep the tiled copy path.
+constexpr uint32_t kCoalesceMax = 16;
+B2_HD void add_piece(b200tfs_output& o, SpillArea& sp, WalkAux& a, uint32_t field, uint32_t off, uint32_t len) {
+  b200tfs_run* last = nullptr;
+  if (o.n_runs > 0) {
+    if (o.n_runs <= B200TFS_MAX_RUNS) last = &o.runs[o.n_runs - 1];
+    else if (a.last_spill < sp.cap) last = &sp.e[a.last_spill].run;
+  }
+  if (last && len <= kCoalesceMax && last->field == field && last->len == len) {
+    if (last->count == 1) {
+      if (off > last->off && off - last->off >= len) { last->stride = (uint32_t)(off - last->off); last->count = 2; return; }
+    } else if (off == last->off + (uint64_t)last->count * last->stride && last->count < 0xFFFFFFFFu) { ++last->count; return; }
+  }
+  b200tfs_run r; r.off = off; r.len = len; r.count = 1; r.stride = 0; r.field = field;
+  if (o.n_runs < B200TFS_MAX_RUNS) o.runs[o.n_runs] = r;
+  else {
+    a.last_spill = sp.used;
+    spill_push(sp, SPILL_RUN, a.seq, r);
+    o.flags |= B200TFS_OF_SPILLED;
+  }
+  ++o.n_runs;
+}
 
 // TensorShapeProto (tensor_shape.proto:13-46) in [c.p, c.end): dims append (merge); Dim.size last
 // wins inside a Dim; Dim.name validated and ignored (tensors.py:38-39).
-B2_HD void walk_shape(Cursor& c, b200tfs_output& o, ChunkTags& ct) {
+B2_HD void walk_shape(Cursor& c, b200tfs_output& o, SpillArea& sp, WalkAux& a) {
 #pragma unroll 1
   while (c.p < c.end && !c.err) {
     const uint32_t tag = rd_tag(c);
@@ -293,13 +352,13 @@ B2_HD void walk_shape(Cursor& c, b200tfs_output& o, ChunkTags& ct) {
     }
     c.end = outer;
     if (c.err) return;
-    if (o.rank < B200TFS_MAX_RANK) o.dims[o.rank++] = size; else ct.rank_overflow = true;
+    add_dim(o, sp, a, size);
   }
 }
 
 // One TensorProto (tensor.proto:14-84) in [c.p, c.end); accumulates into o so a repeated `value` merges.
 // Every offset written to the table is relative to the record start.
-B2_HD void walk_tensor(Cursor& c, b200tfs_output& o, ChunkTags& ct) {
+B2_HD void walk_tensor(Cursor& c, b200tfs_output& o, SpillArea& sp, WalkAux& a) {
 #pragma unroll 1
   while (c.p < c.end && !c.err) {
     const uint32_t tag = rd_tag(c);
@@ -312,7 +371,7 @@ B2_HD void walk_tensor(Cursor& c, b200tfs_output& o, ChunkTags& ct) {
       if (c.err) return;
       const uint32_t outer = c.end;
       c.end = c.p + n;
-      walk_shape(c, o, ct);
+      walk_shape(c, o, sp, a);
       c.end = outer;
     } else if (field == F_CONTENT && wt == WT_LEN) {
       const uint32_t n = rd_len(c);
@@ -342,18 +401,13 @@ B2_HD void walk_tensor(Cursor& c, b200tfs_output& o, ChunkTags& ct) {
         skip_scalar(c, wt);
         if (c.err) return;
         len = c.p - off;
+        o.flags |= B200TFS_OF_UNPACKED;
       }
-      if (len) {
-        if (o.n_chunks < B200TFS_MAX_CHUNKS) {
-          ct.field[o.n_chunks] = (uint8_t)field;
-          o.chunk_off[o.n_chunks] = off; o.chunk_len[o.n_chunks] = len;
-          ++o.n_chunks;
-        } else ct.chunk_overflow = true;
-      }
+      if (len) add_piece(o, sp, a, field, off, len);
     } else if ((field == F_RESOURCE || field == F_VARIANT) && wt == WT_LEN) {
       const uint32_t n = rd_len(c);
       if (c.err) return;
-      if (!validate_nested(c, field == F_RESOURCE ? NT_RESOURCE : NT_VARIANT, n)) ct.rank_overflow = true;  // too deep: NONCANONICAL
+      if (!validate_nested(c, field == F_RESOURCE ? NT_RESOURCE : NT_VARIANT, n)) a.too_deep = true;  // too deep: NONCANONICAL
     } else {
       if (field > 17) o.flags |= B200TFS_OF_HAS_UNKNOWN;
       skip_field(c, tag);  // version_number, mismatched wire types, unknown
@@ -361,36 +415,66 @@ B2_HD void walk_tensor(Cursor& c, b200tfs_output& o, ChunkTags& ct) {
   }
 }
 
-// Settle dtype -> field, keep that field's chunks, element counts.  Mirrors what
+// the k-th spilled entry of `kind` that belongs to map entry `seq` (nullptr if absent / beyond the region)
+B2_HD SpillEntry* spill_find(SpillArea& sp, uint32_t kind, uint32_t seq, uint32_t k) {
+  const uint32_t n = sp.used < sp.cap ? sp.used : sp.cap;
+  for (uint32_t i = 0; i < n; ++i)
+    if (sp.e[i].kind == kind && sp.e[i].seq == seq) { if (k == 0) return &sp.e[i]; --k; }
+  return nullptr;
+}
+
+// Settle dtype -> field, keep that field's runs, element counts.  Mirrors what
 // tensor_proto_to_ndarray (tensors.py:42-46) would conclude from the parsed message.
-B2_HD void finalize_output(b200tfs_output& o, const ChunkTags& ct) {
-  if (ct.rank_overflow || ct.chunk_overflow) { o.status = B200TFS_E_NONCANONICAL; o.n_chunks = 0; return; }
+B2_HD void finalize_output(b200tfs_output& o, SpillArea& sp, const WalkAux& a) {
+  o.spill_seq = a.seq;
+  if (a.too_deep) { o.status = B200TFS_E_NONCANONICAL; o.n_runs = 0; o.n_inline = 0; return; }
   const DtypeInfo di = dtype_info(o.dtype);
-  if (di.field == 0) { o.status = B200TFS_E_KEY; o.n_chunks = 0; return; }  // types.py:40 KeyError
+  if (di.field == 0) { o.status = B200TFS_E_KEY; o.n_runs = 0; o.n_inline = 0; return; }  // types.py:40 KeyError
   o.value_field = (int32_t)di.field;
   uint64_t total = 0;
+  bool gathered = false;
   int kept = 0;
-  for (int i = 0; i < o.n_chunks; ++i) {
-    if (ct.field[i] == di.field) {
-      o.chunk_off[kept] = o.chunk_off[i]; o.chunk_len[kept] = o.chunk_len[i];
-      total += o.chunk_len[i];
+  const int inl = o.n_runs < B200TFS_MAX_RUNS ? o.n_runs : B200TFS_MAX_RUNS;
+  for (int i = 0; i < inl; ++i) {
+    if (o.runs[i].field == di.field) {
+      o.runs[kept] = o.runs[i];
+      total += (uint64_t)o.runs[i].len * o.runs[i].count;
+      gathered = gathered || o.runs[i].count > 1;
       ++kept;
     }
   }
-  o.n_chunks = kept;
-  if (kept > 1) o.flags |= B200TFS_OF_MULTI_CHUNK;
+  o.n_inline = (uint32_t)kept;
+  if (o.n_runs > B200TFS_MAX_RUNS) {   // spilled runs stay where they are (the host keeps those of this field)
+    const uint32_t n = sp.used < sp.cap ? sp.used : sp.cap;
+    for (uint32_t i = 0; i < n; ++i) {
+      const SpillEntry& e = sp.e[i];
+      if (e.kind == SPILL_RUN && e.seq == a.seq && e.run.field == di.field) {
+        total += (uint64_t)e.run.len * e.run.count;
+        gathered = gathered || e.run.count > 1;
+        ++kept;
+      }
+    }
+  }
+  o.n_runs = kept;
+  if (kept > 1 || gathered) o.flags |= B200TFS_OF_MULTI_CHUNK;
   if (o.content_len) o.flags |= B200TFS_OF_TENSOR_CONTENT;
   if (o.rank == 0) o.flags |= B200TFS_OF_RANK0;
   // prod(dims) with at most one -1
   uint64_t prod = 1; int infer = -1; bool bad = false;
   for (int i = 0; i < o.rank; ++i) {
-    const int64_t d = o.dims[i];
+    int64_t d;
+    if (i < B200TFS_MAX_RANK) d = o.dims[i];
+    else { const SpillEntry* e = spill_find(sp, SPILL_DIM, a.seq, (uint32_t)(i - B200TFS_MAX_RANK)); d = e ? (int64_t)e->run.off : 1; }
     if (d == -1 && infer < 0) { infer = i; continue; }
     if (d < 0) { bad = true; break; }
     if (d != 0 && prod > 0xFFFFFFFFFFFFFFFFull / (uint64_t)d) { bad = true; break; }
     prod *= (uint64_t)d;
   }
   if (bad) { o.status = B200TFS_E_SHAPE; return; }
+  auto set_dim = [&](int i, int64_t v) {
+    if (i < B200TFS_MAX_RANK) o.dims[i] = v;
+    else { SpillEntry* e = spill_find(sp, SPILL_DIM, a.seq, (uint32_t)(i - B200TFS_MAX_RANK)); if (e) e->run.off = (uint64_t)v; }
+  };
   // n_elems / dst_bytes describe the SHAPE (once it is fully known), also when the values do not match it:
   // the tolerant decoder needs them to accept tensor_content in place of the typed field
   if (di.kind == VK_FIXED) {
@@ -398,7 +482,7 @@ B2_HD void finalize_output(b200tfs_output& o, const ChunkTags& ct) {
     if (total % di.elem_size) { o.status = B200TFS_E_SHAPE; return; }
     if (infer >= 0) {
       if (prod == 0 || count % prod) { o.status = B200TFS_E_SHAPE; return; }
-      o.dims[infer] = (int64_t)(count / prod); prod = count; o.flags |= B200TFS_OF_DIM_INFERRED;
+      set_dim(infer, (int64_t)(count / prod)); prod = count; o.flags |= B200TFS_OF_DIM_INFERRED;
     }
     o.n_elems = prod; o.dst_bytes = prod * di.elem_size;
     if (count != prod) { o.status = B200TFS_E_SHAPE; return; }  // reshape() ValueError: no broadcast, no padding
@@ -411,7 +495,7 @@ B2_HD void finalize_output(b200tfs_output& o, const ChunkTags& ct) {
   } else {  // strings: unpacked on the host from msg_off/msg_len
     if (infer >= 0) {
       if (prod == 0 || o.n_strings % prod) { o.status = B200TFS_E_SHAPE; return; }
-      o.dims[infer] = (int64_t)(o.n_strings / prod); prod = o.n_strings; o.flags |= B200TFS_OF_DIM_INFERRED;
+      set_dim(infer, (int64_t)(o.n_strings / prod)); prod = o.n_strings; o.flags |= B200TFS_OF_DIM_INFERRED;
     }
     o.n_elems = prod; o.dst_bytes = 0;
     if (o.n_strings != prod) { o.status = B200TFS_E_SHAPE; return; }
@@ -464,9 +548,11 @@ B2_HD bool keys_equal(Cursor& c, const b200tfs_output& a, const b200tfs_output& 
 
 // One PredictResponse (predict.proto:30-40) occupying the cursor's record.
 // outs needs max_outputs + 1 slots (the extra one is scratch for an entry whose key repeats).
-// Returns the record status; *n_outs distinct keys.
-B2_HD int walk_response(Cursor& c, int max_outputs, b200tfs_output* outs, int* n_outs, b200tfs_model_spec* spec) {
+// Returns the record status; *n_outs distinct keys.  B200TFS_E_SPILL: sp.used entries are needed, sp.cap were there.
+B2_HD int walk_response(Cursor& c, int max_outputs, b200tfs_output* outs, int* n_outs, b200tfs_model_spec* spec, SpillArea& sp) {
   int n = 0;
+  uint32_t seq = 0;
+  sp.used = 0;
   spec_reset(*spec);
   *n_outs = 0;
 #pragma unroll 1
@@ -478,7 +564,7 @@ B2_HD int walk_response(Cursor& c, int max_outputs, b200tfs_output* outs, int* n
       if (c.err) break;
       b200tfs_output& o = outs[n];  // parsed in place (slot n <= max_outputs); merged away below if the key repeats
       out_begin(o);
-      ChunkTags ct; ct.chunk_overflow = false; ct.rank_overflow = false;
+      WalkAux aux; aux_begin(aux, seq++);
       bool foreign = false;  // the entry itself carries a field that is not key/value
       const uint32_t outer = c.end;
       c.end = c.p + elen;
@@ -497,7 +583,7 @@ B2_HD int walk_response(Cursor& c, int max_outputs, b200tfs_output* outs, int* n
           o.msg_off = c.p; o.msg_len = m;
           const uint32_t inner = c.end;
           c.end = c.p + m;
-          walk_tensor(c, o, ct);
+          walk_tensor(c, o, sp, aux);
           c.end = inner;
         } else { skip_field(c, t); foreign = true; }
       }
@@ -507,7 +593,7 @@ B2_HD int walk_response(Cursor& c, int max_outputs, b200tfs_output* outs, int* n
       // (incl. key/value with a mismatched wire type) stays an unknown field of the response and never
       // reaches the outputs map (pinned: tests/golden/decode.json "entry_with_foreign_field").
       if (foreign) continue;
-      finalize_output(o, ct);
+      finalize_output(o, sp, aux);
       // duplicate key: the later entry replaces the earlier one
       int slot = -1;
       for (int i = 0; i < n; ++i) if (keys_equal(c, outs[i], o)) { slot = i; break; }
@@ -526,18 +612,21 @@ B2_HD int walk_response(Cursor& c, int max_outputs, b200tfs_output* outs, int* n
     } else skip_field(c, tag);
   }
   if (c.err) return c.err;
+  if (sp.used > sp.cap) return B200TFS_E_SPILL;
   *n_outs = n;
   return B200TFS_OK;
 }
 
 // A bare TensorProto message (what tensor_proto_to_ndarray receives) occupying the cursor's record.
-B2_HD int walk_tensor_proto(Cursor& c, b200tfs_output* out) {
+B2_HD int walk_tensor_proto(Cursor& c, b200tfs_output* out, SpillArea& sp) {
   out_begin(*out);
-  ChunkTags ct; ct.chunk_overflow = false; ct.rank_overflow = false;
+  WalkAux aux; aux_begin(aux, 0);
+  sp.used = 0;
   out->msg_off = 0; out->msg_len = c.end;
-  walk_tensor(c, *out, ct);
+  walk_tensor(c, *out, sp, aux);
   if (c.err) return c.err;
-  finalize_output(*out, ct);
+  if (sp.used > sp.cap) return B200TFS_E_SPILL;
+  finalize_output(*out, sp, aux);
   return B200TFS_OK;
 }
 

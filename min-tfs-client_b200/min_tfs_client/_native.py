@@ -17,15 +17,16 @@ LIB_PATH = os.path.join(os.path.dirname(_HERE), "lib", "libb200tfs.so")
 
 # ---- status codes (b200tfs.h) -----------------------------------------------------------------
 OK = 0
-E_DTYPE, E_SHAPE, E_SIZE, E_PARSE, E_CUDA, E_TOOBIG, E_ARG, E_NONCANONICAL, E_RANGE, E_KEY = range(-1, -11, -1)
+E_DTYPE, E_SHAPE, E_SIZE, E_PARSE, E_CUDA, E_TOOBIG, E_ARG, E_NONCANONICAL, E_RANGE, E_KEY, E_SPILL = range(-1, -12, -1)
 
 F_TENSOR_CONTENT = 0x1
 F_KEEP_SNAN = 0x2
 F_PRESERIALIZED = 0x4
 RF_GRPC_FRAME = 0x1
 OF_TENSOR_CONTENT, OF_MULTI_CHUNK, OF_DIM_INFERRED, OF_HAS_UNKNOWN, OF_RANK0, OF_VARINT, OF_PAD_EDGE = 0x1, 0x2, 0x4, 0x8, 0x10, 0x20, 0x40
+OF_UNPACKED, OF_SPILLED = 0x80, 0x100
 ORDER_GIVEN, ORDER_UPB, ORDER_BYTES = 0, 1, 2
-MAX_RANK, MAX_CHUNKS, FUSED_MAX_OUTPUTS = 16, 8, 8
+MAX_RANK, MAX_RUNS, FUSED_MAX_OUTPUTS = 16, 8, 8
 DT_HALF_REFQUIRK = -19
 
 
@@ -52,14 +53,19 @@ class Request(C.Structure):
     ]
 
 
+class Run(C.Structure):
+    """b200tfs_run: `count` pieces of `len` value bytes, `stride` bytes apart, from TensorProto field `field`."""
+    _fields_ = [("off", C.c_uint64), ("len", C.c_uint32), ("count", C.c_uint32), ("stride", C.c_uint32), ("field", C.c_uint32)]
+
+
 class Output(C.Structure):
     _fields_ = [
         ("key_off", C.c_uint64), ("key_len", C.c_uint32), ("dtype", C.c_int32), ("rank", C.c_int32), ("flags", C.c_uint32),
-        ("value_field", C.c_int32), ("n_chunks", C.c_int32), ("dims", C.c_int64 * MAX_RANK),
-        ("chunk_off", C.c_uint64 * MAX_CHUNKS), ("chunk_len", C.c_uint64 * MAX_CHUNKS),
+        ("value_field", C.c_int32), ("n_runs", C.c_int32), ("dims", C.c_int64 * MAX_RANK),
+        ("runs", Run * MAX_RUNS),
         ("content_off", C.c_uint64), ("content_len", C.c_uint64), ("msg_off", C.c_uint64), ("msg_len", C.c_uint64),
         ("n_elems", C.c_uint64), ("dst_bytes", C.c_uint64), ("n_strings", C.c_uint64), ("dst_off", C.c_uint64), ("status", C.c_int32),
-        ("reserved", C.c_int32),
+        ("n_inline", C.c_uint32), ("spill_rec", C.c_uint32), ("spill_seq", C.c_uint32),
     ]
 
 
@@ -114,9 +120,12 @@ SIGNATURES = {
     "b200tfs_parse_responses": (C.c_int, [_vp, _vp, C.c_int32, _u64p, _u64p, C.c_int32, C.POINTER(Output), _i32p,
                                           C.POINTER(ModelSpec), _i32p]),
     "b200tfs_parse_tensor_protos": (C.c_int, [_vp, _vp, C.c_int32, _u64p, _u64p, C.POINTER(Output), _i32p]),
+    "b200tfs_output_dims": (C.c_int, [_vp, C.POINTER(Output), C.POINTER(C.c_int64), C.c_int32]),
+    "b200tfs_output_runs": (C.c_int, [_vp, C.POINTER(Output), C.POINTER(Run), C.c_int32]),
     "b200tfs_unpack_outputs": (C.c_int, [_vp, _vp, C.c_int32, C.POINTER(Output), _u64p, _vpp, _i32p, _i32p]),
     "b200tfs_decode_responses": (C.c_int, [_vp, _vp, C.c_int32, _u64p, _u64p, _vp, C.c_uint64]),
     "b200tfs_decode_results": (C.c_int, [_vp, C.c_int32, C.POINTER(Output), _i32p, C.POINTER(ModelSpec), _i32p]),
+    "b200tfs_decode_stats": (C.c_int, [_vp, _u64p, _u64p, _u64p]),
     "b200tfs_capture_begin": (C.c_int, [_vp]),
     "b200tfs_capture_end": (C.c_int, [_vp, _vpp]),
     "b200tfs_graph_launch": (C.c_int, [_vp, _vp]),

@@ -142,7 +142,7 @@ class OpenResponse:
         """The decoded output, or None when the launch did not move it (varint-packed, string, tensor_content only): the
         caller then decodes ``wire_of(key)`` on its own.  Raises what the reference raises for this output."""
         o = self.table[key]
-        if int(o.dtype) not in _FUSED_MOVES or o.status != N.OK or not o.n_chunks or not o.n_elems:
+        if int(o.dtype) not in _FUSED_MOVES or o.status != N.OK or not o.n_runs or not o.n_elems:
             return None
         np_type, dst_code, shape = self._codec._resolve_output(o, strict, None)
         at = int(o.dst_off)
@@ -354,10 +354,10 @@ class Codec:
         if o.status == N.E_KEY:
             raise KeyError(enum)
         np_type = numpy_for_enum(enum)
-        shape = tuple(int(o.dims[k]) for k in range(o.rank))
+        shape = self._shape(o)
         if strict and enum in (DT_COMPLEX64, DT_COMPLEX128) and o.n_elems:
             raise ValueError("cannot reshape array: the reference reads complex values as separate floats")
-        content_only = o.n_chunks == 0 and o.content_len and o.n_strings == 0
+        content_only = o.n_runs == 0 and o.content_len and o.n_strings == 0
         if content_only and not strict and o.content_len == int(np.prod(shape, dtype=np.int64)) * np.dtype(np_type).itemsize:
             pass  # tolerant: raw little-endian tensor_content, as TF writes it
         elif o.status == N.E_SHAPE and not strict and out_dtype is None and self._may_pad(o, np_type):
@@ -381,13 +381,28 @@ class Codec:
             dst_code = N.DT_HALF_REFQUIRK
         return np_type, dst_code, shape
 
-    @staticmethod
-    def _may_pad(o: N.Output, np_type) -> bool:
+    def _shape(self, o: N.Output) -> Tuple[int, ...]:
+        """Every dim of an output: the table holds MAX_RANK inline, deeper shapes come from the context's spill area."""
+        if o.rank <= N.MAX_RANK:
+            return tuple(int(o.dims[k]) for k in range(o.rank))
+        dims = (C.c_int64 * o.rank)()
+        N.check(self._lib.b200tfs_output_dims(self._ctx, C.byref(o), dims, o.rank))
+        return tuple(int(d) for d in dims)
+
+    def _runs(self, o: N.Output) -> List[N.Run]:
+        """Every value run of an output (inline + spilled), in wire order."""
+        if o.n_runs <= o.n_inline:
+            return [o.runs[k] for k in range(o.n_runs)]
+        runs = (N.Run * o.n_runs)()
+        N.check(self._lib.b200tfs_output_runs(self._ctx, C.byref(o), runs, o.n_runs))
+        return list(runs)
+
+    def _may_pad(self, o: N.Output, np_type) -> bool:
         """An E_SHAPE output the padding rule applies to: the shape is fully known and holds MORE elements than there are
         values (packed varints: more elements than value bytes would be needed; the kernel then counts exactly)."""
-        if o.n_elems <= 0 or o.content_len or any(o.dims[k] < 0 for k in range(o.rank)):
+        if o.n_elems <= 0 or o.content_len or any(d < 0 for d in self._shape(o)):
             return False
-        value_bytes = sum(int(o.chunk_len[k]) for k in range(o.n_chunks))
+        value_bytes = sum(int(r.len) * int(r.count) for r in self._runs(o))
         if o.flags & N.OF_VARINT:
             return True     # fewer value bytes than elements was what raised E_SHAPE here; a surplus is caught by the decode kernels
         size = np.dtype(np_type).itemsize
@@ -495,7 +510,7 @@ class Codec:
                     arrays[key] = self._decode_strings(buf, base, o)
                     continue
                 np_type, dst_code, shape = self._resolve_output(o, strict, None)
-                if o.status == N.OK and int(o.dtype) in _FUSED_MOVES and o.n_chunks and o.n_elems and dst_code == int(o.dtype):
+                if o.status == N.OK and int(o.dtype) in _FUSED_MOVES and o.n_runs and o.n_elems and dst_code == int(o.dtype):
                     at = i * stride + int(o.dst_off)
                     arrays[key] = dst[at: at + int(o.dst_bytes)].view(np_type).reshape(shape)
                 else:
@@ -521,7 +536,7 @@ class Codec:
         from tensorflow.core.framework.tensor_pb2 import TensorProto
 
         proto = TensorProto.FromString(buf[base + o.msg_off: base + o.msg_off + o.msg_len].tobytes())
-        shape = tuple(int(o.dims[k]) for k in range(o.rank))
+        shape = tuple(int(d.size) for d in proto.tensor_shape.dim)     # the host message is at hand: any rank
         return np.array([e for e in proto.string_val], dtype=np.str_).reshape(*shape)
 
     def decode_predict_response(self, wire: bytes, **kw) -> Tuple[Dict[str, np.ndarray], DecodedSpec]:

@@ -338,6 +338,20 @@ def decode_cases():
         "variant_nested_ok": entry("a", tproto(1, [1], ld(0x2A, f([4])) + ld(0x7A, ld(0x0A, b"T") + ld(0x12, b"\xff\x00") + ld(0x1A, tproto(1, [1], ld(0x2A, f([9]))))))),
         "variant_nested_malformed": entry("a", tproto(1, [1], ld(0x2A, f([4])) + ld(0x7A, ld(0x1A, tproto(1, [1], b"\x2A\x03\x00\x00\x00"))))),
         "complex64": entry("a", tproto(8, [1], ld(0x4A, f([1, 2])))),
+        # layouts the reference reads like any other (it iterates the merged repeated field, tensors.py:42-46) and that go past
+        # the decode table's inline arrays: long rows of unpacked elements, many packed occurrences, many outputs, deep shapes
+        "all_unpacked_1000": entry("a", tproto(1, [10, 100], b"".join(b"\x2D" + f([i * 0.25 - 3]) for i in range(1000)))) + mspec(),
+        "all_unpacked_ints_300": entry("a", tproto(9, [300], b"".join(b"\x50" + vi((i * 7919) % 100000 - 500) for i in range(300)))),
+        "split_packed_x20": entry("a", tproto(1, [sum(1 + 3 * (k % 5) for k in range(20))],
+                                              b"".join(ld(0x2A, f(np.arange(1 + 3 * (k % 5)) + 100 * k)) for k in range(20)))),
+        "split_packed_ints_x20": entry("a", tproto(3, [sum(2 + k % 4 for k in range(20))],
+                                                   b"".join(ld(0x3A, b"".join(vi(((-1) ** j) * (k * 1000 + j) ** 2) for j in range(2 + k % 4))) for k in range(20)))),
+        "unpacked_between_foreign_runs": entry("d", tproto(2, [30], b"".join(
+            ld(0x2A, f([k] * (k % 3 + 1))) + b"\x31" + np.float64(k + 0.5).tobytes() + ld(0x32, np.array([k, -k], dtype=np.float64).tobytes())
+            for k in range(10)))),
+        "outputs_x40": b"".join(entry("out_%02d" % k, tproto(1, [2], ld(0x2A, f([k, -k])))) for k in range(40)) + mspec(),
+        "rank_20": entry("a", tproto(1, [1, 2, 1, 1, 3, 1, 1, 1, 1, 2, 1, 1, 1, 1, 1, 1, 1, 1, 5, 1], ld(0x2A, f(np.arange(60))))),
+        "rank_20_ints_dim_minus_one": entry("a", tproto(1, [1, 2, 1, 1, 3, 1, 1, 1, 1, 2, 1, 1, 1, 1, 1, 1, 1, 1, -1, 1], ld(0x2A, f(np.arange(60))))),
     }
     out = {}
     for name, wire in cases.items():

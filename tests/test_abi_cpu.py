@@ -28,13 +28,13 @@ def test_header_symbols_all_exported_and_bound():
     assert not unbound, f"declared in b200tfs.h but not bound in _native.SIGNATURES: {unbound}"
     extra = sorted(set(N.SIGNATURES) - declared)
     assert not extra, f"bound but not declared in b200tfs.h: {extra}"
-    assert lib.b200tfs_abi_version() == 1
+    assert lib.b200tfs_abi_version() == 2
 
 
 def test_struct_mirrors_match_header_layout():
     # sizes follow from the header's field lists (natural alignment)
     assert C.sizeof(N.Tensor) == 56 and C.sizeof(N.Request) == 48
-    assert C.sizeof(N.Output) == 32 + 8 * N.MAX_RANK + 16 * N.MAX_CHUNKS + 32 + 32 + 8
+    assert C.sizeof(N.Output) == 32 + 8 * N.MAX_RANK + 24 * N.MAX_RUNS + 32 + 32 + 16 and C.sizeof(N.Run) == 24
     assert C.sizeof(N.ModelSpec) == 48
 
 

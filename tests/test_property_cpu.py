@@ -30,7 +30,8 @@ def _walker():
     subprocess.run(["make", "-s", "-C", os.path.join(HERE, "native")], check=True)
     L = C.CDLL(so)
     L.wh_parse_response.restype = C.c_int
-    L.wh_parse_response.argtypes = [C.c_char_p, C.c_uint64, C.c_int, C.POINTER(N.Output), C.POINTER(C.c_int), C.POINTER(N.ModelSpec)]
+    L.wh_parse_response.argtypes = [C.c_char_p, C.c_uint64, C.c_int, C.POINTER(N.Output), C.POINTER(C.c_int), C.POINTER(N.ModelSpec),
+                                    C.c_void_p, C.c_uint32, C.POINTER(C.c_uint32)]
     return L
 
 
@@ -93,13 +94,13 @@ def test_walker_and_oracle_agree_with_port_on_random_responses(data):
     table = (N.Output * 17)()
     cnt = C.c_int()
     spec = N.ModelSpec()
-    assert WALK.wh_parse_response(wire, len(wire), 16, table, C.byref(cnt), C.byref(spec)) == N.OK
+    assert WALK.wh_parse_response(wire, len(wire), 16, table, C.byref(cnt), C.byref(spec), None, 0, None) == N.OK
     by_key = {wire[table[i].key_off: table[i].key_off + table[i].key_len].decode(): table[i] for i in range(cnt.value)}
     assert set(by_key) == set(expect)
     for k, a in expect.items():
         o = by_key[k]
         assert o.status == N.OK and numpy_for_enum(o.dtype) == a.dtype.type and tuple(o.dims[i] for i in range(o.rank)) == a.shape
-        raw = b"".join(wire[o.chunk_off[c]: o.chunk_off[c] + o.chunk_len[c]] for c in range(o.n_chunks))
+        raw = b"".join(wire[r.off + q * r.stride: r.off + q * r.stride + r.len] for r in (o.runs[c] for c in range(o.n_runs)) for q in range(r.count))
         if not (o.flags & N.OF_VARINT):
             vals = np.frombuffer(raw, dtype=a.dtype).copy()
             if a.dtype == np.float32:
@@ -128,7 +129,7 @@ def test_truncated_or_corrupted_responses_never_misparse(data):
     table = (N.Output * 17)()
     cnt = C.c_int()
     spec = N.ModelSpec()
-    st_w = WALK.wh_parse_response(wire, len(wire), 16, table, C.byref(cnt), C.byref(spec))
+    st_w = WALK.wh_parse_response(wire, len(wire), 16, table, C.byref(cnt), C.byref(spec), None, 0, None)
     try:
         parsed = predict_pb2.PredictResponse.FromString(wire)
     except DecodeError:
