@@ -4,8 +4,15 @@
 timeout=60, model_version=None)`` keeps the reference's signature (requests.py:22-65).  The request
 is packed by the encode kernels and sent as raw bytes through the same gRPC method the generated stub
 binds (``/tensorflow.serving.PredictionService/Predict``, prediction_service_pb2_grpc.py:50-54); the
-response bytes are handed to the parse/unpack kernels.  The Classify / Regress / GetModelStatus
-helpers of the reference are outside the Predict hot path and raise.
+response bytes are handed to the parse/unpack kernels.
+
+The reference's other three calls are kept as well (requests.py:67-110).  They are outside the Predict hot path
+(SURVEY.md 8(f) rank 4): small pointer-chasing messages assembled on the host by the protobuf runtime, like
+``DT_STRING`` tensors.  ``model_status_request`` is the reference's; ``classification_request`` /
+``regression_request`` cannot work in the reference (it fills ``request.inputs[k]``, a field neither
+``ClassificationRequest`` nor ``RegressionRequest`` has, and sends them to ``Predict``): here they build the
+``Input{example_list}`` those RPCs define - one ``tf.Example`` per row of ``input_dict`` - and call
+``PredictionService/Classify`` and ``/Regress``.
 """
 from typing import Dict, Optional
 
@@ -15,6 +22,43 @@ from .codec import get_codec
 from .tensors import WireTensor
 
 PREDICT_METHOD = "/tensorflow.serving.PredictionService/Predict"
+CLASSIFY_METHOD = "/tensorflow.serving.PredictionService/Classify"
+REGRESS_METHOD = "/tensorflow.serving.PredictionService/Regress"
+MODEL_STATUS_METHOD = "/tensorflow.serving.ModelService/GetModelStatus"
+
+
+def examples_from_input_dict(input_dict: Dict[str, np.ndarray]):
+    """``Input{example_list{examples}}`` for Classify / Regress (input.proto:13-79, example.proto, feature.proto).
+
+    Row i of every array is example i: ``feature[k]`` holds the row's values flattened - ``float_list`` for floating
+    dtypes, ``int64_list`` for integers and bools, ``bytes_list`` for str / bytes (``coerce_to_bytes``).  0-d arrays are
+    repeated in every example; all other arrays must agree on their first dimension.
+    """
+    from tensorflow_serving.apis.input_pb2 import Input
+
+    from .tensors import coerce_to_bytes
+
+    arrays = {k: np.asarray(v) for k, v in input_dict.items()}
+    rows = {a.shape[0] for a in arrays.values() if a.ndim}
+    if len(rows) > 1:
+        raise ValueError(f"inputs disagree on the number of examples: {sorted(rows)}")
+    n = rows.pop() if rows else (1 if arrays else 0)
+    inp = Input()
+    inp.example_list.SetInParent()
+    for i in range(n):
+        ex = inp.example_list.examples.add()
+        for k, a in arrays.items():
+            row = a if a.ndim == 0 else a[i]
+            feat = ex.features.feature[k]
+            if row.dtype.kind == "f":
+                feat.float_list.value.extend(np.asarray(row, dtype=np.float32).ravel().tolist())
+            elif row.dtype.kind in "iub":
+                feat.int64_list.value.extend(np.asarray(row, dtype=np.int64).ravel().tolist())
+            elif row.dtype.kind in "US":
+                feat.bytes_list.value.extend(coerce_to_bytes(s) for s in np.asarray(row).ravel().tolist())
+            else:
+                raise ValueError(f"input {k!r}: dtype {row.dtype} has no tf.Example feature kind")
+    return inp
 
 
 class PredictResponseView:
@@ -91,14 +135,40 @@ class TensorServingClient:
                         model_version: Optional[int] = None) -> PredictResponseView:
         return self._predict((model_name, model_version, input_dict), timeout)
 
-    def _out_of_scope(self, what):
-        raise NotImplementedError(f"{what} is outside the Predict hot path this package rebuilds (see DESIGN.md)")
+    def _make_example_request(self, request_pb, model_name, input_dict, model_version):
+        request = request_pb()
+        request.model_spec.name = model_name
+        if model_version is not None:
+            request.model_spec.version.value = model_version
+        request.input.CopyFrom(examples_from_input_dict(input_dict))
+        return request
 
-    def classification_request(self, *a, **kw):
-        self._out_of_scope("classification_request")
+    def classification_request(self, model_name: str, input_dict: Dict[str, np.ndarray], timeout: int = 60,
+                               model_version: Optional[int] = None):
+        """Same signature as the reference (requests.py:67-81); returns a ``ClassificationResponse``."""
+        from tensorflow_serving.apis.classification_pb2 import ClassificationRequest, ClassificationResponse
 
-    def regression_request(self, *a, **kw):
-        self._out_of_scope("regression_request")
+        call = self._channel.unary_unary(CLASSIFY_METHOD, request_serializer=ClassificationRequest.SerializeToString,
+                                         response_deserializer=ClassificationResponse.FromString)
+        return call(self._make_example_request(ClassificationRequest, model_name, input_dict, model_version), timeout)
 
-    def model_status_request(self, *a, **kw):
-        self._out_of_scope("model_status_request")
+    def regression_request(self, model_name: str, input_dict: Dict[str, np.ndarray], timeout: int = 60,
+                           model_version: Optional[int] = None):
+        """Same signature as the reference (requests.py:83-97); returns a ``RegressionResponse``."""
+        from tensorflow_serving.apis.regression_pb2 import RegressionRequest, RegressionResponse
+
+        call = self._channel.unary_unary(REGRESS_METHOD, request_serializer=RegressionRequest.SerializeToString,
+                                         response_deserializer=RegressionResponse.FromString)
+        return call(self._make_example_request(RegressionRequest, model_name, input_dict, model_version), timeout)
+
+    def model_status_request(self, model_name: str, model_version: Optional[int] = None, timeout: Optional[int] = 10):
+        """``ModelService/GetModelStatus`` as the reference issues it (requests.py:99-110: the version is set only when truthy)."""
+        from tensorflow_serving.apis.get_model_status_pb2 import GetModelStatusRequest, GetModelStatusResponse
+
+        request = GetModelStatusRequest()
+        request.model_spec.name = model_name
+        if model_version:
+            request.model_spec.version.value = model_version
+        call = self._channel.unary_unary(MODEL_STATUS_METHOD, request_serializer=GetModelStatusRequest.SerializeToString,
+                                         response_deserializer=GetModelStatusResponse.FromString)
+        return call(request, timeout)

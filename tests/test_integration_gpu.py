@@ -66,10 +66,3 @@ def test_c2_sized_round_trip_needs_the_channel_option(served):
     assert served.received[-1] == ref_port.encode_predict_request("default", 1, [("x_input", x)], deterministic=True)
     out = tensor_proto_to_ndarray(response.outputs["x_output"])
     assert out.dtype == np.float32 and out.shape == (1024, 1024) and out.tobytes() == x.tobytes()
-
-
-def test_out_of_scope_rpcs_raise(served):
-    client = TensorServingClient(host="127.0.0.1", port=served.port)
-    for call in (client.classification_request, client.regression_request, client.model_status_request):
-        with pytest.raises(NotImplementedError):
-            call("default", {})

@@ -7,7 +7,9 @@ import numpy as np
 import pytest
 
 from tensorflow.core.framework import tensor_pb2, tensor_shape_pb2, types_pb2
-from tensorflow_serving.apis import model_pb2, predict_pb2
+from tensorflow.core.example import example_pb2, feature_pb2
+from tensorflow_serving.apis import classification_pb2, get_model_status_pb2, input_pb2, model_pb2, predict_pb2, regression_pb2
+from tensorflow_serving.util import status_pb2
 
 REF = "/root/reference/protobuf_srcs"
 
@@ -69,6 +71,25 @@ _TYPE = {1: "double", 2: "float", 3: "int64", 4: "uint64", 5: "int32", 8: "bool"
     ("tensorflow_serving/apis/model.proto", "ModelSpec", model_pb2.ModelSpec),
     ("tensorflow_serving/apis/predict.proto", "PredictRequest", predict_pb2.PredictRequest),
     ("tensorflow_serving/apis/predict.proto", "PredictResponse", predict_pb2.PredictResponse),
+    # the other RPCs of the client (requests.py:67-110)
+    ("tensorflow/core/example/feature.proto", "Feature", feature_pb2.Feature),
+    ("tensorflow/core/example/feature.proto", "Features", feature_pb2.Features),
+    ("tensorflow/core/example/feature.proto", "FloatList", feature_pb2.FloatList),
+    ("tensorflow/core/example/feature.proto", "Int64List", feature_pb2.Int64List),
+    ("tensorflow/core/example/feature.proto", "BytesList", feature_pb2.BytesList),
+    ("tensorflow/core/example/example.proto", "Example", example_pb2.Example),
+    ("tensorflow_serving/apis/input.proto", "Input", input_pb2.Input),
+    ("tensorflow_serving/apis/input.proto", "ExampleList", input_pb2.ExampleList),
+    ("tensorflow_serving/apis/input.proto", "ExampleListWithContext", input_pb2.ExampleListWithContext),
+    ("tensorflow_serving/apis/classification.proto", "ClassificationRequest", classification_pb2.ClassificationRequest),
+    ("tensorflow_serving/apis/classification.proto", "ClassificationResponse", classification_pb2.ClassificationResponse),
+    ("tensorflow_serving/apis/classification.proto", "Class", classification_pb2.Class),
+    ("tensorflow_serving/apis/regression.proto", "RegressionRequest", regression_pb2.RegressionRequest),
+    ("tensorflow_serving/apis/regression.proto", "RegressionResponse", regression_pb2.RegressionResponse),
+    ("tensorflow_serving/apis/get_model_status.proto", "GetModelStatusRequest", get_model_status_pb2.GetModelStatusRequest),
+    ("tensorflow_serving/apis/get_model_status.proto", "GetModelStatusResponse", get_model_status_pb2.GetModelStatusResponse),
+    ("tensorflow_serving/apis/get_model_status.proto", "ModelVersionStatus", get_model_status_pb2.ModelVersionStatus),
+    ("tensorflow_serving/util/status.proto", "StatusProto", status_pb2.StatusProto),
 ])
 def test_fields_match_reference_proto(path, message, cls):
     want = _proto_fields(os.path.join(REF, path), message)

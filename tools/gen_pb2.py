@@ -16,6 +16,12 @@ Schema sources restated here (all under reference ``protobuf_srcs/``):
   tensorflow/core/framework/tensor.proto:14-94           TensorProto, VariantTensorDataProto
   tensorflow_serving/apis/model.proto:9-33               ModelSpec
   tensorflow_serving/apis/predict.proto:12-40            PredictRequest / PredictResponse
+and, for the client's other RPCs (reference requests.py:67-110), host-side messages only:
+  tensorflow/core/example/{feature,example}.proto        tf.Example
+  tensorflow_serving/apis/input.proto                    Input{ExampleList}
+  tensorflow_serving/apis/{classification,regression}.proto
+  tensorflow_serving/apis/get_model_status.proto, tensorflow_serving/util/status.proto,
+  tensorflow/core/{lib/core,protobuf}/error_codes.proto
 
 ``tests/test_schema.py`` re-reads the reference ``.proto`` files (when ``/root/reference`` exists)
 with a tiny tokenizer and checks every field name / number / type / label against these tables.
@@ -174,6 +180,119 @@ def build_files():
     rs = fd.message_type.add(name="PredictResponse")
     _field(rs, "model_spec", 2, "msg:.tensorflow.serving.ModelSpec")
     _map_field(rs, "outputs", 1, "msg:.tensorflow.TensorProto", ".tensorflow.serving.PredictResponse")
+    files.append(fd)
+
+    # ==== the other RPCs of the reference's client (requests.py:67-110): Classify / Regress / GetModelStatus ====
+    # ---- feature.proto / example.proto (tf.Example) ------------------------------------------------
+    fd = dpb.FileDescriptorProto(name="tensorflow/core/example/feature.proto", package="tensorflow", syntax="proto3")
+    for nm, ty in (("BytesList", "bytes"), ("FloatList", "float"), ("Int64List", "int64")):
+        m = fd.message_type.add(name=nm)
+        _field(m, "value", 1, ty, repeated=True, packed=None if ty == "bytes" else True)
+    ft = fd.message_type.add(name="Feature")
+    ft.oneof_decl.add(name="kind")
+    _field(ft, "bytes_list", 1, "msg:.tensorflow.BytesList", oneof=0)
+    _field(ft, "float_list", 2, "msg:.tensorflow.FloatList", oneof=0)
+    _field(ft, "int64_list", 3, "msg:.tensorflow.Int64List", oneof=0)
+    fs = fd.message_type.add(name="Features")
+    _map_field(fs, "feature", 1, "msg:.tensorflow.Feature", ".tensorflow.Features")
+    fl = fd.message_type.add(name="FeatureList")
+    _field(fl, "feature", 1, "msg:.tensorflow.Feature", repeated=True)
+    fls = fd.message_type.add(name="FeatureLists")
+    _map_field(fls, "feature_list", 1, "msg:.tensorflow.FeatureList", ".tensorflow.FeatureLists")
+    files.append(fd)
+
+    fd = dpb.FileDescriptorProto(name="tensorflow/core/example/example.proto", package="tensorflow", syntax="proto3",
+                                 dependency=["tensorflow/core/example/feature.proto"])
+    ex = fd.message_type.add(name="Example")
+    _field(ex, "features", 1, "msg:.tensorflow.Features")
+    sq = fd.message_type.add(name="SequenceExample")
+    _field(sq, "context", 1, "msg:.tensorflow.Features")
+    _field(sq, "feature_lists", 2, "msg:.tensorflow.FeatureLists")
+    files.append(fd)
+
+    # ---- input.proto ------------------------------------------------------------------------------
+    fd = dpb.FileDescriptorProto(name="tensorflow_serving/apis/input.proto", package="tensorflow.serving", syntax="proto3",
+                                 dependency=["tensorflow/core/example/example.proto"])
+    el = fd.message_type.add(name="ExampleList")
+    _field(el, "examples", 1, "msg:.tensorflow.Example", repeated=True)
+    ec = fd.message_type.add(name="ExampleListWithContext")
+    _field(ec, "examples", 1, "msg:.tensorflow.Example", repeated=True)
+    _field(ec, "context", 2, "msg:.tensorflow.Example")
+    inp = fd.message_type.add(name="Input")
+    inp.oneof_decl.add(name="kind")
+    f1 = _field(inp, "example_list", 1, "msg:.tensorflow.serving.ExampleList", oneof=0)
+    f1.options.lazy = True
+    f2 = _field(inp, "example_list_with_context", 2, "msg:.tensorflow.serving.ExampleListWithContext", oneof=0)
+    f2.options.lazy = True
+    files.append(fd)
+
+    # ---- classification.proto / regression.proto ---------------------------------------------------
+    fd = dpb.FileDescriptorProto(name="tensorflow_serving/apis/classification.proto", package="tensorflow.serving", syntax="proto3",
+                                 dependency=["tensorflow_serving/apis/input.proto", "tensorflow_serving/apis/model.proto"])
+    cl = fd.message_type.add(name="Class")
+    _field(cl, "label", 1, "string")
+    _field(cl, "score", 2, "float")
+    cs = fd.message_type.add(name="Classifications")
+    _field(cs, "classes", 1, "msg:.tensorflow.serving.Class", repeated=True)
+    cr = fd.message_type.add(name="ClassificationResult")
+    _field(cr, "classifications", 1, "msg:.tensorflow.serving.Classifications", repeated=True)
+    rq = fd.message_type.add(name="ClassificationRequest")
+    _field(rq, "model_spec", 1, "msg:.tensorflow.serving.ModelSpec")
+    _field(rq, "input", 2, "msg:.tensorflow.serving.Input")
+    rs = fd.message_type.add(name="ClassificationResponse")
+    _field(rs, "model_spec", 2, "msg:.tensorflow.serving.ModelSpec")
+    _field(rs, "result", 1, "msg:.tensorflow.serving.ClassificationResult")
+    files.append(fd)
+
+    fd = dpb.FileDescriptorProto(name="tensorflow_serving/apis/regression.proto", package="tensorflow.serving", syntax="proto3",
+                                 dependency=["tensorflow_serving/apis/input.proto", "tensorflow_serving/apis/model.proto"])
+    rg = fd.message_type.add(name="Regression")
+    _field(rg, "value", 1, "float")
+    rr = fd.message_type.add(name="RegressionResult")
+    _field(rr, "regressions", 1, "msg:.tensorflow.serving.Regression", repeated=True)
+    rq = fd.message_type.add(name="RegressionRequest")
+    _field(rq, "model_spec", 1, "msg:.tensorflow.serving.ModelSpec")
+    _field(rq, "input", 2, "msg:.tensorflow.serving.Input")
+    rs = fd.message_type.add(name="RegressionResponse")
+    _field(rs, "model_spec", 2, "msg:.tensorflow.serving.ModelSpec")
+    _field(rs, "result", 1, "msg:.tensorflow.serving.RegressionResult")
+    files.append(fd)
+
+    # ---- error_codes.proto (x2: lib/core re-exports protobuf/) / status.proto / get_model_status.proto ----
+    fd = dpb.FileDescriptorProto(name="tensorflow/core/protobuf/error_codes.proto", package="tensorflow.error", syntax="proto3")
+    en = fd.enum_type.add(name="Code")
+    for nm, num in (("OK", 0), ("CANCELLED", 1), ("UNKNOWN", 2), ("INVALID_ARGUMENT", 3), ("DEADLINE_EXCEEDED", 4), ("NOT_FOUND", 5),
+                    ("ALREADY_EXISTS", 6), ("PERMISSION_DENIED", 7), ("UNAUTHENTICATED", 16), ("RESOURCE_EXHAUSTED", 8),
+                    ("FAILED_PRECONDITION", 9), ("ABORTED", 10), ("OUT_OF_RANGE", 11), ("UNIMPLEMENTED", 12), ("INTERNAL", 13),
+                    ("UNAVAILABLE", 14), ("DATA_LOSS", 15),
+                    ("DO_NOT_USE_RESERVED_FOR_FUTURE_EXPANSION_USE_DEFAULT_IN_SWITCH_INSTEAD_", 20)):
+        en.value.add(name=nm, number=num)
+    files.append(fd)
+    fd = dpb.FileDescriptorProto(name="tensorflow/core/lib/core/error_codes.proto", syntax="proto3",
+                                 dependency=["tensorflow/core/protobuf/error_codes.proto"])
+    fd.public_dependency.append(0)
+    files.append(fd)
+
+    fd = dpb.FileDescriptorProto(name="tensorflow_serving/util/status.proto", package="tensorflow.serving", syntax="proto3",
+                                 dependency=["tensorflow/core/lib/core/error_codes.proto"])
+    sp = fd.message_type.add(name="StatusProto")
+    _field(sp, "error_code", 1, "enum:.tensorflow.error.Code").json_name = "error_code"
+    _field(sp, "error_message", 2, "string").json_name = "error_message"
+    files.append(fd)
+
+    fd = dpb.FileDescriptorProto(name="tensorflow_serving/apis/get_model_status.proto", package="tensorflow.serving", syntax="proto3",
+                                 dependency=["tensorflow_serving/apis/model.proto", "tensorflow_serving/util/status.proto"])
+    rq = fd.message_type.add(name="GetModelStatusRequest")
+    _field(rq, "model_spec", 1, "msg:.tensorflow.serving.ModelSpec")
+    mv = fd.message_type.add(name="ModelVersionStatus")
+    st = mv.enum_type.add(name="State")
+    for nm, num in (("UNKNOWN", 0), ("START", 10), ("LOADING", 20), ("AVAILABLE", 30), ("UNLOADING", 40), ("END", 50)):
+        st.value.add(name=nm, number=num)
+    _field(mv, "version", 1, "int64")
+    _field(mv, "state", 2, "enum:.tensorflow.serving.ModelVersionStatus.State")
+    _field(mv, "status", 3, "msg:.tensorflow.serving.StatusProto")
+    rs = fd.message_type.add(name="GetModelStatusResponse")
+    _field(rs, "model_version_status", 1, "msg:.tensorflow.serving.ModelVersionStatus", repeated=True).json_name = "model_version_status"
     files.append(fd)
     return files
 
