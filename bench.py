@@ -922,6 +922,9 @@ def c2_single_request_latency(world):
         alg = db.src_bytes + int(st["rec_len"][0]) if name == "encode" else db.resp_len + db.dst_bytes
         out[name] = {"launch_us": us, "algorithmic_bytes": alg, "frac": alg / (us * 1e-6) / 1e9 / peak}
     out["how"] = f"graph of {n} back-to-back single-request launches on one stream over {n} buffer sets ({db.footprint >> 20} MiB > L2), CUDA events"
+    a, b, c = C.c_uint64(), C.c_uint64(), C.c_uint64()
+    N.check(lib.b200tfs_decode_stats(db.ctx, C.byref(a), C.byref(b), C.byref(c)))
+    out["decode_records_served_by"] = {"template_in_parameters": a.value, "template_in_device_memory": b.value, "tag_walk": c.value}
     db.close()
     return out
 

@@ -81,6 +81,8 @@ extern "C" {
                                          reference routes every float32 through a Python double (tensors.py:22). */
 #define B200TFS_F_PRESERIALIZED 0x4u  /* `data` already holds a serialised TensorProto of `packed_len` bytes (how the
                                          host hands over DT_STRING tensors, tensors.py:24): spliced in verbatim        */
+#define B200TFS_F_DEVICE_DATA 0x8u    /* *_host entry points only: `data` of THIS tensor is a device pointer already (a tensor
+                                         that lives in HBM - the usual case for a model's activations): it is not staged      */
 
 /* ---- decode flags (b200tfs_output.flags, set by the parser) ----------------------------------- */
 #define B200TFS_OF_TENSOR_CONTENT 0x1u /* values arrived in tensor_content                                        */

@@ -96,6 +96,11 @@ struct b200tfs_ctx {
   TplInline tpl_known{};             // the newest template the host knows: its own walk of a host-resident record 0, or tpl_pinned
                                      // as found with the stream idle; rides in the kernel parameters of the next single-response launch
   uint32_t serial = 0;               // stamp of the next template learnt
+  cudaEvent_t tpl_event = nullptr;   // recorded behind every eager decode launch: once it has completed, tpl_pinned is current
+  bool tpl_event_pending = false;
+  bool opt_no_inline = false;        // B200TFS_NO_INLINE_TEMPLATE=1: never hand the template over in the kernel parameters (experiments)
+  bool opt_table_dev = false;        // B200TFS_TABLE_DEV=1: the decode table goes to device memory and is fetched by b200tfs_decode_results
+  Growable fused_dev;
   uint64_t stage_shift = 0;          // *_host decode: the wire sits at stage_dev + stage_shift (placed so that the payload is 16-byte aligned)
   int32_t fused_n = 0;      // records of the last b200tfs_decode_responses
   std::vector<int32_t> pending_status;   // varint decode: which output each status word in scratch_host belongs to
@@ -207,6 +212,12 @@ int b200tfs_create(int device, b200tfs_ctx** out) {
   }
   const char* tb = getenv("B200TFS_TILE_BYTES");
   if (tb) c->tile_bytes_override = (uint32_t)strtoul(tb, nullptr, 10);
+  const char* oi = getenv("B200TFS_NO_INLINE_TEMPLATE");
+  c->opt_no_inline = oi && oi[0] == '1';
+  const char* od = getenv("B200TFS_TABLE_DEV");
+  c->opt_table_dev = od && od[0] == '1';
+  e = cudaEventCreateWithFlags(&c->tpl_event, cudaEventDisableTiming);
+  if (e != cudaSuccess) { delete c; return fail(B200TFS_E_CUDA, "cudaEventCreate: %s", cudaGetErrorString(e)); }
   *out = c;
   return B200TFS_OK;
 }
@@ -223,6 +234,8 @@ int b200tfs_destroy(b200tfs_ctx* c) {
   if (c->fused_host.p) cudaFreeHost(c->fused_host.p);
   if (c->tpl_dev) cudaFree(c->tpl_dev);
   if (c->tpl_pinned) cudaFreeHost(c->tpl_pinned);
+  if (c->tpl_event) cudaEventDestroy(c->tpl_event);
+  if (c->fused_dev.p) cudaFree(c->fused_dev.p);
   for (Slot* g : c->graph_slots) { cudaFreeHost(g->host.p); cudaFree(g->dev.p); delete g; }
   if (c->scratch_dev.p) cudaFree(c->scratch_dev.p);
   if (c->spill_dev.p) cudaFree(c->spill_dev.p);
@@ -1199,16 +1212,22 @@ static int decode_launch(b200tfs_ctx* c, const void* arena_dev, int32_t n, const
       CU(cudaMemcpyAsync((void*)fp.tpl_read, slot->host.p, sizeof(Template), cudaMemcpyHostToDevice, c->stream));
       if (slot->done) { CU(cudaEventRecord(slot->done, c->stream)); slot->pending = true; }
       c->tpl_known = host_tpl->in;
-      fp.tpli = host_tpl->in;
+      if (!c->opt_no_inline) fp.tpli = host_tpl->in;
     } else {
-      if (!c->capturing && cudaStreamQuery(c->stream) == cudaSuccess) adopt_pinned_template(c);
+      // the pinned copy is current once the previous decode launch of this context has completed (the stream itself may
+      // well be busy again: the caller's own copy of the next response usually precedes this call)
+      if (!c->capturing && (!c->tpl_event_pending || cudaEventQuery(c->tpl_event) == cudaSuccess)) { c->tpl_event_pending = false; adopt_pinned_template(c); }
       const TplHead& h = c->tpl_known.head;
-      if (h.valid && h.rec_len == rec_len[0] && h.vpt == vpt && h.dst_need <= dst_stride) fp.tpli = c->tpl_known;
+      if (!c->opt_no_inline && h.valid && h.rec_len == rec_len[0] && h.vpt == vpt && h.dst_need <= dst_stride) fp.tpli = c->tpl_known;
     }
   }
   // the table is written by the kernel straight into pinned host memory (unified addressing): ~1 KB
   // of posted PCIe writes per record instead of a device table plus a copy node behind every launch
   uint8_t* d = (uint8_t*)c->fused_host.p;
+  if (c->opt_table_dev) {
+    if ((rc = grow_dev(c, c->fused_dev, L.total))) return rc;
+    d = (uint8_t*)c->fused_dev.p;
+  }
   fp.outs = (b200tfs_output*)(d + L.outs); fp.n_outs = (int32_t*)(d + L.nouts);
   fp.specs = (b200tfs_model_spec*)(d + L.specs); fp.status = (int32_t*)(d + L.status);
   uint64_t grid = 0;
@@ -1244,6 +1263,7 @@ static int decode_launch(b200tfs_ctx* c, const void* arena_dev, int32_t n, const
   CU(launch_decode_fused(fp, (uint32_t)grid, c->stream));
   c->launches += 1;
   c->fused_n = n;
+  if (!c->capturing) { CU(cudaEventRecord(c->tpl_event, c->stream)); c->tpl_event_pending = true; }
   return B200TFS_OK;
 }
 
@@ -1261,8 +1281,9 @@ int b200tfs_decode_results(b200tfs_ctx* c, int32_t n, b200tfs_output* outs, int3
   if (!c || n < 0) return fail(B200TFS_E_ARG, "bad arguments");
   if (c->capturing) return fail(B200TFS_E_ARG, "cannot collect results during graph capture");
   if (n > c->fused_n) return fail(B200TFS_E_ARG, "only %d records were decoded", c->fused_n);
-  CU(cudaStreamSynchronize(c->stream));
   FusedLayout L = fused_layout(c->fused_n);
+  if (c->opt_table_dev && c->fused_dev.p) CU(cudaMemcpyAsync(c->fused_host.p, c->fused_dev.p, L.total, cudaMemcpyDeviceToHost, c->stream));
+  CU(cudaStreamSynchronize(c->stream));
   const uint8_t* h = (const uint8_t*)c->fused_host.p;
   if (outs) memcpy(outs, h + L.outs, sizeof(b200tfs_output) * (uint64_t)n * kFusedMaxOutputs);
   if (n_outs) memcpy(n_outs, h + L.nouts, 4ull * n);
@@ -1355,12 +1376,14 @@ int stage_tensors(b200tfs_ctx* c, std::vector<b200tfs_tensor>& ts) {
       if (t.rank < 0 || t.rank > 254 || (t.rank && !t.dims)) return fail(B200TFS_E_SHAPE, "bad rank/dims");
       for (int i = 0; i < t.rank; ++i) if (t.dims[i] < 0) return fail(B200TFS_E_SHAPE, "negative dim");
     }
+    if (t.flags & B200TFS_F_DEVICE_DATA) continue;   // already in HBM
     total = ((total + 255) & ~255ull) + tensor_src_bytes(t);
   }
   int rc = grow_dev(c, c->stage_dev, total + 256);
   if (rc) return rc;
   uint64_t cur = 0;
   for (auto& t : ts) {
+    if (t.flags & B200TFS_F_DEVICE_DATA) { t.flags &= ~B200TFS_F_DEVICE_DATA; continue; }
     cur = (cur + 255) & ~255ull;
     uint64_t nb = tensor_src_bytes(t);
     if (nb) {

@@ -22,6 +22,7 @@ E_DTYPE, E_SHAPE, E_SIZE, E_PARSE, E_CUDA, E_TOOBIG, E_ARG, E_NONCANONICAL, E_RA
 F_TENSOR_CONTENT = 0x1
 F_KEEP_SNAN = 0x2
 F_PRESERIALIZED = 0x4
+F_DEVICE_DATA = 0x8
 RF_GRPC_FRAME = 0x1
 OF_TENSOR_CONTENT, OF_MULTI_CHUNK, OF_DIM_INFERRED, OF_HAS_UNKNOWN, OF_RANK0, OF_VARINT, OF_PAD_EDGE = 0x1, 0x2, 0x4, 0x8, 0x10, 0x20, 0x40
 OF_UNPACKED, OF_SPILLED = 0x80, 0x100

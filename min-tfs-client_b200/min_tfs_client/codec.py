@@ -21,6 +21,7 @@ from typing import Dict, Iterable, List, Mapping, Optional, Sequence, Tuple, Uni
 import numpy as np
 
 from . import _native as N
+from . import device as D
 from .constants import BFLOAT16, DT_BFLOAT16, NP_TO_ENUM_MAPPING, enum_for_numpy, numpy_for_enum
 from tensorflow.core.framework import types_pb2
 
@@ -40,8 +41,8 @@ def _as_enum(dtype) -> int:
     return enum_for_numpy(dtype)
 
 
-def _validated_enum(arr: np.ndarray) -> int:
-    """Same gate as ``DataType(ndarray.dtype.type)`` (types.py:27-32): ValueError for foreign dtypes."""
+def _validated_enum(arr) -> int:
+    """Same gate as ``DataType(ndarray.dtype.type)`` (types.py:27-32): ValueError for foreign dtypes.  `arr`: anything with a numpy dtype."""
     t = arr.dtype.type
     if t in NP_TO_ENUM_MAPPING:
         return NP_TO_ENUM_MAPPING[t]
@@ -65,9 +66,27 @@ def _string_tensor_proto_bytes(arr: np.ndarray) -> bytes:
 class _Prepared:
     """One input readied for the C ABI; keeps every buffer the Tensor struct points at alive."""
 
-    __slots__ = ("array", "dims", "key", "struct")
+    __slots__ = ("array", "dims", "key", "struct", "on_device", "nbytes", "ndim", "size", "itemsize", "kind")
 
     def __init__(self, value, key: bytes, wire_dtype, tensor_content: bool, keep_snan: bool):
+        self.on_device = D.is_device_object(value)
+        if self.on_device:
+            # a tensor that already lives in HBM (CUDA array interface / DLPack): encoded in place, no host-to-device copy
+            ptr, shape, dtype, keep = D.device_view(value)
+            probe = np.empty(0, dtype=dtype)
+            src_enum = _validated_enum(probe)
+            if src_enum == DT_STRING or not dtype.isnative:
+                raise ValueError("device inputs must be native-endian numeric arrays")
+            wire_enum = src_enum if wire_dtype is None else _as_enum(wire_dtype)
+            flags = N.F_DEVICE_DATA | (N.F_TENSOR_CONTENT if tensor_content else 0) | (N.F_KEEP_SNAN if keep_snan else 0)
+            self.array = keep
+            self.dims = (C.c_int64 * max(len(shape), 1))(*shape)
+            n = int(np.prod(shape, dtype=np.int64))
+            self.nbytes, self.ndim, self.size, self.itemsize, self.kind = n * dtype.itemsize, len(shape), n, dtype.itemsize, dtype.kind
+            self.key = key
+            self.struct = N.Tensor(data=ptr if n else None, src_dtype=src_enum, wire_dtype=wire_enum, rank=len(shape), flags=flags, dims=self.dims,
+                                   key=key, key_len=len(key), packed_len=0)
+            return
         arr = np.asarray(value)
         src_enum = _validated_enum(arr)
         flags = 0
@@ -93,21 +112,22 @@ class _Prepared:
                          flags=flags, dims=self.dims, key=key, key_len=len(key), packed_len=0)
         self.key = key
         self.struct = t
+        a = self.array
+        self.nbytes, self.ndim, self.size, self.itemsize, self.kind = int(a.nbytes), a.ndim, int(a.size), a.dtype.itemsize, a.dtype.kind
 
 
 def _wire_bound(p: "_Prepared", tensor_content: bool) -> int:
     """Upper bound of the bytes one prepared tensor occupies on the wire (payload + its own framing)."""
-    a = p.array
-    frame = 64 + 16 * max(a.ndim, 1) + len(p.key)
+    frame = 64 + 16 * max(p.ndim, 1) + len(p.key)
     if p.struct.flags & N.F_PRESERIALIZED:
-        return int(a.size) + frame
-    n = int(a.size)
+        return p.size + frame
+    n = p.size
     if p.struct.src_dtype != p.struct.wire_dtype:
         return 4 * n + frame                      # f16 / bf16 -> DT_FLOAT
-    if tensor_content or a.dtype.kind in "fc" and a.dtype.itemsize >= 4 or a.dtype.kind == "b":
-        return a.nbytes + frame
-    per = {1: 10, 2: 10, 4: 10, 8: 10} if a.dtype.kind == "i" else {1: 2, 2: 3, 4: 5, 8: 10}   # varint bytes per element
-    return n * per[a.dtype.itemsize] + frame
+    if tensor_content or p.kind in "fc" and p.itemsize >= 4 or p.kind == "b":
+        return p.nbytes + frame
+    per = {1: 10, 2: 10, 4: 10, 8: 10} if p.kind == "i" else {1: 2, 2: 3, 4: 5, 8: 10}   # varint bytes per element
+    return n * per[p.itemsize] + frame
 
 
 class DecodedSpec:
@@ -173,11 +193,36 @@ class Codec:
             raise RuntimeError(f"cannot create a B200 codec context on device {device}: {N.last_error()}")
         self._ctx = ctx
         self.device = device
+        self._pinned = D.PinnedArrays()
+        self._wire_pinned = None      # page-locked landing buffer of encode(..., out="pinned")
 
     def close(self):
         if getattr(self, "_ctx", None):
             self._lib.b200tfs_destroy(self._ctx)
             self._ctx = None
+            self._pinned.release()
+            if self._wire_pinned is not None:
+                self._wire_pinned.free()
+                self._wire_pinned = None
+
+    # ---- page-locked and device-resident arrays ---------------------------------------------------
+    def pinned_empty(self, shape, dtype=np.float32) -> np.ndarray:
+        """An uninitialised page-locked numpy array (lives until the codec is closed).  Inputs that sit in one are copied by the
+        DMA engines at the PCIe rate; handed to ``decode_predict_response(..., out={key: arr})`` the decoded tensor lands in it
+        directly."""
+        return self._pinned.empty(shape, dtype)
+
+    def device_array(self, array) -> "D.DeviceArray":
+        """Upload `array` once; the returned device array can be encoded any number of times without a host-to-device copy."""
+        a = np.require(np.asarray(array), requirements="C")
+        return D.DeviceArray(self, a.shape, a.dtype).copy_from_host(a)
+
+    def _pinned_wire(self, cap: int) -> "N.PinnedBuffer":
+        if self._wire_pinned is None or self._wire_pinned.nbytes < cap:
+            if self._wire_pinned is not None:
+                self._wire_pinned.free()
+            self._wire_pinned = N.PinnedBuffer(max(cap, 1 << 20))
+        return self._wire_pinned
 
     def __del__(self):  # pragma: no cover
         try:
@@ -246,20 +291,25 @@ class Codec:
 
     def encode_predict_requests(self, requests: Iterable[Tuple[str, Optional[int], Union[Mapping, Sequence]]], *,
                                 order="deterministic", wire_dtype=None, tensor_content: bool = False,
-                                keep_snan: bool = False, grpc_frame: bool = False) -> List[bytes]:
+                                keep_snan: bool = False, grpc_frame: bool = False, out=None) -> List[bytes]:
         """Each item is ``(model_name, model_version, inputs)``; returns one PredictRequest wire per item.
 
         The bytes equal ``PredictRequest.SerializeToString(deterministic=True)`` of the message the
         reference builds in requests.py:41-48 (``order="deterministic"``), or list the map entries in
         the order given (``order="given"``).  ``grpc_frame=True`` puts gRPC's five-byte length-prefixed-message
         header in front (for a transport that writes HTTP/2 DATA frames itself; grpc-python adds it on its own).
+        Inputs may be numpy arrays (pageable or ``pinned_empty``) or device arrays (``__cuda_array_interface__`` / DLPack: no
+        host-to-device copy).  ``out="pinned"`` returns uint8 views of the codec's page-locked landing buffer instead of ``bytes``
+        objects (no copy on the host; valid until the next encode on this codec).
         """
         keep, structs = self._build_requests(list(requests), order, wire_dtype, tensor_content, keep_snan, grpc_frame)
         n = len(structs)
         if n == 0:
             return []
         reqs = (N.Request * n)(*structs)
-        if n == 1:
+        if out is not None and out != "pinned":
+            raise ValueError('out must be None or "pinned"')
+        if n == 1 and out is None:
             # one request whose size is closed-form (no varint-packed input): copy straight into the bytes object
             total = C.c_uint64()
             if _HAVE_NEW_BYTES and self._lib.b200tfs_request_size(reqs, C.byref(total)) == N.OK:
@@ -275,9 +325,13 @@ class Codec:
             cap += 1024 + len(name)
             for p in preps:
                 cap += _wire_bound(p, tensor_content) + 512
-        wire = np.empty(cap, dtype=np.uint8)
         off = (C.c_uint64 * n)()
         ln = (C.c_uint64 * n)()
+        if out == "pinned":
+            pw = self._pinned_wire(cap)
+            N.check(self._lib.b200tfs_encode_requests_host(self._ctx, n, reqs, pw.ptr, cap, off, ln))
+            return [pw.array[off[i]: off[i] + ln[i]] for i in range(n)]
+        wire = np.empty(cap, dtype=np.uint8)
         N.check(self._lib.b200tfs_encode_requests_host(self._ctx, n, reqs, wire.ctypes.data, cap, off, ln))
         return [wire[off[i]: off[i] + ln[i]].tobytes() for i in range(n)]
 
@@ -289,10 +343,12 @@ class Codec:
         n = len(wires)
         off = (C.c_uint64 * max(n, 1))()
         ln = (C.c_uint64 * max(n, 1))()
-        if n == 1 and isinstance(wires[0], bytes) and len(wires[0]):
+        if n == 1 and len(wires[0]) and (isinstance(wires[0], (bytes, bytearray, memoryview)) or
+                                         (isinstance(wires[0], np.ndarray) and wires[0].dtype == np.uint8 and wires[0].flags.c_contiguous)):
             # a single message: hand its own buffer to the library (read-only view, no copy)
-            ln[0] = len(wires[0])
-            return np.frombuffer(wires[0], dtype=np.uint8), off, ln
+            view = wires[0] if isinstance(wires[0], np.ndarray) else np.frombuffer(wires[0], dtype=np.uint8)
+            ln[0] = view.size
+            return view, off, ln
         cur = 0
         for i, w in enumerate(wires):
             off[i] = cur
@@ -301,7 +357,7 @@ class Codec:
         buf = np.empty(max(cur, 1), dtype=np.uint8)
         for i, w in enumerate(wires):
             if len(w):
-                buf[off[i]: off[i] + len(w)] = np.frombuffer(w, dtype=np.uint8)
+                buf[off[i]: off[i] + len(w)] = w if isinstance(w, np.ndarray) else np.frombuffer(w, dtype=np.uint8)
         return buf, off, ln
 
     @staticmethod
@@ -539,8 +595,48 @@ class Codec:
         shape = tuple(int(d.size) for d in proto.tensor_shape.dim)     # the host message is at hand: any rank
         return np.array([e for e in proto.string_val], dtype=np.str_).reshape(*shape)
 
-    def decode_predict_response(self, wire: bytes, **kw) -> Tuple[Dict[str, np.ndarray], DecodedSpec]:
+    def decode_predict_response(self, wire: bytes, *, out: Optional[Mapping[str, np.ndarray]] = None, **kw) -> Tuple[Dict[str, np.ndarray], DecodedSpec]:
+        """One response.  ``out={key: array}``: the named outputs are written into the caller's arrays (dtype and shape must
+        match); when the response has that one fixed-width output and the array came from ``pinned_empty``, the device-to-host
+        copy lands in it directly (no staging buffer, no extra copy on the host)."""
+        if out:
+            direct = self._decode_into_pinned(wire, out, kw.get("strict", False)) if len(out) == 1 and not kw.get("out_dtypes") else None
+            if direct is not None:
+                return direct
+            arrays, spec = self.decode_predict_responses([wire], **kw)[0]
+            for k, dst in out.items():
+                if k not in arrays:
+                    raise KeyError(k)
+                if dst.dtype != arrays[k].dtype or dst.shape != arrays[k].shape:
+                    raise ValueError(f"out[{k!r}]: {dst.dtype}{dst.shape} does not match the decoded {arrays[k].dtype}{arrays[k].shape}")
+                np.copyto(dst, arrays[k])
+                arrays[k] = dst
+            return arrays, spec
         return self.decode_predict_responses([wire], **kw)[0]
+
+    def _decode_into_pinned(self, wire, out: Mapping[str, np.ndarray], strict: bool):
+        (key, arr), = out.items()
+        cap = self._pinned.capacity(arr)
+        if cap is None or not len(wire):
+            return None
+        buf, off, ln = self._pack_wires([wire])
+        stride = cap & ~255
+        N.check(self._lib.b200tfs_decode_responses_host_async(self._ctx, buf.ctypes.data, 1, off, ln, arr.ctypes.data, stride))
+        K = N.FUSED_MAX_OUTPUTS
+        outs, n_outs, specs, status = (N.Output * K)(), (C.c_int32 * 1)(), (N.ModelSpec * 1)(), (C.c_int32 * 1)()
+        N.check(self._lib.b200tfs_decode_results(self._ctx, 1, outs, n_outs, specs, status))
+        if status[0] != N.OK or n_outs[0] != 1:
+            return None                                  # not the single-output case after all: the general path redoes it
+        o = outs[0]
+        if self._text(buf, o.key_off, o.key_len) != key or int(o.dtype) not in _FUSED_MOVES or o.status != N.OK or not o.n_runs or o.dst_off != 0:
+            return None
+        np_type, dst_code, shape = self._resolve_output(o, strict, None)
+        if dst_code != int(o.dtype) or np.dtype(np_type) != arr.dtype or tuple(shape) != arr.shape:
+            return None
+        s = specs[0]
+        spec = DecodedSpec(self._text(buf, s.name_off, s.name_len), int(s.version), bool(s.has_version),
+                           self._text(buf, s.label_off, s.label_len), self._text(buf, s.signature_off, s.signature_len))
+        return {key: arr}, spec
 
     def decode_tensor_protos(self, wires: Sequence[bytes], *, strict: bool = False, out_dtype=None) -> List[np.ndarray]:
         """``tensor_proto_to_ndarray`` for serialised TensorProto messages."""
