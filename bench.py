@@ -418,7 +418,10 @@ class DeviceBatch:
         out_size = 2 if wl.out_dtype in (19, 14) else 4
         self.dst_bytes = r0.size * out_size
         self.dst_stride = (self.dst_bytes + 255) & ~255
-        self.resp_stride = (self.resp_len + 255) & ~255
+        # B200TFS_BENCH_RESP_SHIFT (experiments): where inside its 256-byte aligned slot a response starts - e.g. the shift that
+        # makes its payload 16-byte aligned, as a caller who places received bytes with that in mind would have it
+        self.resp_shift = int(os.environ.get("B200TFS_BENCH_RESP_SHIFT", "0"))
+        self.resp_stride = (self.resp_len + self.resp_shift + 255) & ~255
         per_slot = n * (2 * self.src_bytes + self.resp_stride + self.dst_stride)     # sources + arena + response wires + destinations
         self.slots = slots or max(1, min(64, -(-4 * L2_BYTES // max(per_slot, 1))))  # the ring's footprint is at least 4 x L2
         # ---- device: distinct inputs uploaded once, then replicated device-to-device ----
@@ -468,13 +471,15 @@ class DeviceBatch:
                 j0 = done_seed[seed]
                 for q in range(n_in):
                     N.check(lib.b200tfs_memcpy_d2d(self.ctx, st["src"][q] + j * in_stride[q], st["src"][q] + j0 * in_stride[q], ins[q][1].nbytes))
-                N.check(lib.b200tfs_memcpy_d2d(self.ctx, st["resp"] + j * self.resp_stride, st["resp"] + j0 * self.resp_stride, self.resp_len))
+                N.check(lib.b200tfs_memcpy_d2d(self.ctx, st["resp"] + j * self.resp_stride + self.resp_shift,
+                                               st["resp"] + j0 * self.resp_stride + self.resp_shift, self.resp_len))
             else:
                 done_seed[seed] = j
                 for q in range(n_in):
                     self._h2d(st["src"][q] + j * in_stride[q], ins[q][1])
                 rk, rx = self.host_resp[seed]
-                self._h2d(st["resp"] + j * self.resp_stride, np.frombuffer(self.resp_prefix + rx.tobytes() + self.resp_suffix, dtype=np.uint8))
+                self._h2d(st["resp"] + j * self.resp_stride + self.resp_shift,
+                          np.frombuffer(self.resp_prefix + rx.tobytes() + self.resp_suffix, dtype=np.uint8))
         # request structs
         ts = (N.Tensor * max(n * n_in, 1))()
         rq = (N.Request * max(n, 1))()
@@ -500,7 +505,7 @@ class DeviceBatch:
         N.check(lib.b200tfs_memset(self.ctx, st["arena"], 0, st["arena_cap"]))
         N.check(lib.b200tfs_memset(self.ctx, st["dst"], 0, n * self.dst_stride))
         st["rec_off"], st["rec_len"] = (C.c_uint64 * max(n, 1))(), (C.c_uint64 * max(n, 1))()
-        st["roff"] = (C.c_uint64 * max(n, 1))(*[j * self.resp_stride for j in range(n)])
+        st["roff"] = (C.c_uint64 * max(n, 1))(*[j * self.resp_stride + self.resp_shift for j in range(n)])
         st["rlen"] = (C.c_uint64 * max(n, 1))(*[self.resp_len] * n)
         if wl.out_dtype is not None:      # two-phase decode with a cast: table + per-output destinations
             st["outs"] = (N.Output * max(n, 1))()
@@ -905,7 +910,7 @@ def c2_single_request_latency(world):
     one_req = [C.cast(C.byref(st["rq"], j * C.sizeof(N.Request)), C.POINTER(N.Request)) for j in range(n)]
     arenas = [db.malloc(one_cap) for _ in range(n)]
     ro, rl = (C.c_uint64 * 1)(), (C.c_uint64 * 1)()
-    offs = [(C.c_uint64 * 1)(j * db.resp_stride) for j in range(n)]
+    offs = [(C.c_uint64 * 1)(j * db.resp_stride + db.resp_shift) for j in range(n)]
     lens = (C.c_uint64 * 1)(db.resp_len)
 
     def enc(j):

@@ -1148,7 +1148,8 @@ extern "C" {
 static void adopt_pinned_template(b200tfs_ctx* c) {
   if (!c->tpl_pinned) return;
   const TplInline& p = *c->tpl_pinned;
-  if (p.head.valid && (!c->tpl_known.head.valid || (int32_t)(p.head.serial - c->tpl_known.head.serial) > 0)) c->tpl_known = p;
+  // newer than what the host knows - valid or not: a record 0 that could not be learnt retires the old template too
+  if (p.head.serial && (int32_t)(p.head.serial - c->tpl_known.head.serial) > 0) c->tpl_known = p;
 }
 
 // tile size of a decode launch over `wire_total` bytes: every CTA of the fused kernel first verifies the record's framing, so

@@ -753,15 +753,18 @@ __device__ __noinline__ void fused_slow_path(const FusedParams& fp, uint32_t r, 
       if (r == 0) {   // leave the template for the next launch, and its inline part in pinned memory for the host
         if (len <= 0x7FFFFFFFull) tpl_learn(fp.tpl_write, c, (uint32_t)len, outs_s, cnt, spec_s, st, fp.vpt, (cursor + 255) & ~255ull, fp.serial);
         else fp.tpl_write->in.head.valid = 0;
-        if (fp.tpl_pinned) {
+        if (fp.tpl_pinned) {   // valid or not, stamped with this launch's serial: the host drops what it knew before either way
           fp.tpl_pinned->head.valid = 0;
-          if (fp.tpl_write->in.head.valid) {
-            const uint64_t* s8 = reinterpret_cast<const uint64_t*>(&fp.tpl_write->in);
-            uint64_t* d8 = reinterpret_cast<uint64_t*>(fp.tpl_pinned);
-            for (uint32_t q = sizeof(TplHead) / 8; q < sizeof(TplInline) / 8; ++q) d8[q] = s8[q];
-            __threadfence_system();
-            for (uint32_t q = 0; q < sizeof(TplHead) / 8; ++q) d8[q] = s8[q];   // the head (valid flag in its first word) last
-          }
+          __threadfence_system();
+          const uint64_t* s8 = reinterpret_cast<const uint64_t*>(&fp.tpl_write->in);
+          uint64_t* d8 = reinterpret_cast<uint64_t*>(fp.tpl_pinned);
+          const bool ok = fp.tpl_write->in.head.valid != 0;
+          if (ok) for (uint32_t q = sizeof(TplHead) / 8; q < sizeof(TplInline) / 8; ++q) d8[q] = s8[q];
+          __threadfence_system();
+          TplHead h = fp.tpl_write->in.head;
+          h.serial = fp.serial; h.valid = ok ? 1u : 0u;
+          const uint64_t* h8 = reinterpret_cast<const uint64_t*>(&h);
+          for (uint32_t q = sizeof(TplHead) / 8; q-- > 0;) d8[q] = h8[q];   // the word with the valid flag (the first) last
         }
       }
     }
@@ -823,32 +826,43 @@ __device__ __forceinline__ void decode_fused_body(const FusedParams& fp) {
   uint32_t live = budget;   // CTAs of this record able to take a tile, should the walk be needed
   const uint32_t i = threadIdx.x;
   {
-    uint8_t want;
     if (inl) {
-      want = fp.tpli.framing[i];
       if (i < kTplChunks) ch_s[i] = fp.tpli.chunk[i];
       if (i == kTplChunks) th_s = fp.tpli.head;
     } else {
-      // five threads stage the header and chunk table while every thread fetches its own template framing byte (all
-      // independent loads: one L2 round trip).  (An earlier version kept the chunk table in a per-thread array: it landed in
-      // local memory, 32 KB of extra DRAM traffic per CTA.)
-      want = T->in.framing[i];
+      // five threads stage the header and chunk table (independent loads: one L2 round trip).  (An earlier version kept the
+      // chunk table in a per-thread array: it landed in local memory, 32 KB of extra DRAM traffic per CTA.)
       if (i < kTplChunks) ch_s[i] = T->in.chunk[i];
       if (i == kTplChunks) th_s = T->in.head;
     }
     __syncthreads();
     const uint32_t nch = th_s.n_chunks;
     if (th_s.valid && th_s.rec_len == len && th_s.vpt == fp.vpt && th_s.dst_need <= fp.dst_stride && th_s.total_tiles < budget) {
-      // The verdict needs this record's framing bytes (a DRAM round trip).
+      // The verdict: do this record's framing bytes equal the template's (and do packed-varint chunks still end on a terminator)?
+      // It needs the record's framing bytes - a DRAM round trip.  The batch kernel decides per CTA (one byte per thread, one
+      // barrier).  The single-response kernel decides per WARP - every warp compares all framing bytes itself (same bytes, same
+      // answer) - so that no CTA-wide barrier sits between a warp's loads and its stores: a warp whose tile data has arrived
+      // stores it while other warps' loads are still in flight, as in the plain move.
       auto verdict = [&]() -> bool {
         bool same = true;
-        if (i < th_s.framing_len) {
-          uint32_t w = i;
-          for (uint32_t q = 0; q < nch; ++q) if (ch_s[q].fpos <= i) w += ch_s[q].len;
-          same = rec[w] == want;
+        if (STAGED) {
+          if (i < th_s.framing_len) {
+            uint32_t w = i;
+            for (uint32_t q = 0; q < nch; ++q) if (ch_s[q].fpos <= i) w += ch_s[q].len;
+            same = rec[w] == T->in.framing[i];
+          }
+          if (i < nch && ch_s[i].is_varint && ch_s[i].len) same = same && !(rec[ch_s[i].wire_off + ch_s[i].len - 1] & 0x80);
+          return __syncthreads_and(same) != 0;
         }
-        if (i < nch && ch_s[i].is_varint && ch_s[i].len) same = same && !(rec[ch_s[i].wire_off + ch_s[i].len - 1] & 0x80);
-        return __syncthreads_and(same) != 0;
+        const uint32_t lane = i & 31;
+        for (uint32_t k = lane; k < th_s.framing_len; k += 32) {
+          uint32_t w = k;
+          for (uint32_t q = 0; q < nch; ++q) if (ch_s[q].fpos <= k) w += ch_s[q].len;
+          const uint8_t want = inl ? fp.tpli.framing[k] : T->in.framing[k];
+          same = same && rec[w] == want;
+        }
+        if (lane < nch && ch_s[lane].is_varint && ch_s[lane].len) same = same && !(rec[ch_s[lane].wire_off + ch_s[lane].len - 1] & 0x80);
+        return __all_sync(0xFFFFFFFFu, same) != 0;
       };
       uint32_t t_base = 0, mine = kTplChunks;
       for (uint32_t q = 0; q < nch; ++q) {
@@ -929,6 +943,77 @@ __global__ void __launch_bounds__(kMoveThreads, 3) decode_fused_staged_kernel(co
 // packed varints: venc_len / venc_emit / vdec_count / vdec_emit
 // ------------------------------------------------------------------------------------------------
 #include "varint_kernels.cuh"
+
+// ------------------------------------------------------------------------------------------------
+// frame_requests_kernel (plan.h "deferred framing"): one thread per request evaluates the request's values from the job
+// totals the counting kernel just produced, places the record in its slot (largest payload 128-byte aligned, like the host
+// planner's place_record), writes every framing byte and patches the destinations of the payload movers behind it.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(64) frame_requests_kernel(const __grid_constant__ FrameTables ft) {
+  const uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= ft.n) return;
+  const FrameReq rq = ft.reqs[r];
+  uint64_t* val = ft.scratch_vals + rq.first_val;
+  for (uint32_t v = 0; v < rq.n_val; ++v) {
+    const FrameVal fv = ft.vals[rq.first_val + v];
+    uint64_t x = (uint64_t)fv.c;
+    for (uint32_t k = 0; k < fv.n_terms; ++k) {
+      const FrameTerm t = ft.terms[fv.first_term + k];
+      if (t.kind == FT_TOTAL) x += *ft.jobs[t.idx].total;
+      else if (t.kind == FT_VAL) x += val[t.idx];
+      else x += varint_len(val[t.idx]);
+    }
+    val[v] = x;
+  }
+  auto seg_len = [&](const FrameSeg& sg) -> uint64_t {
+    switch (sg.kind) {
+      case FS_BYTES: return sg.b;
+      case FS_VARINT: return varint_len(val[sg.a]);
+      case FS_BE32: return 4;
+      case FS_ITEM: return ft.items[sg.a].n_out;
+      case FS_SMALL: return ft.smalls[sg.a].n_out;
+      default: return *ft.jobs[sg.a].total;
+    }
+  };
+  uint64_t pad = 0;
+  if (rq.align_seg != ~0u) {
+    uint64_t before = 0;
+    for (uint32_t k = 0; k < rq.align_seg; ++k) before += seg_len(ft.segs[rq.first_seg + k]);
+    pad = (128 - ((rq.slot_off + before) & 127)) & 127;
+  }
+  const uint64_t total = val[rq.total_val];
+  const uint64_t start = rq.slot_off + pad;
+  ft.rec_off[r] = start; ft.rec_len[r] = total;
+  if (pad + total > rq.slot_cap || total > 0x7FFFFFFFull + 5) {   // cannot happen with the host's worst-case slots; never write outside one
+    ft.status[r] = total > 0x7FFFFFFFull + 5 ? B200TFS_E_TOOBIG : B200TFS_E_SIZE;
+    for (uint32_t k = 0; k < rq.n_seg; ++k) {   // park the movers on an empty range
+      const FrameSeg sg = ft.segs[rq.first_seg + k];
+      if (sg.kind == FS_ITEM) ft.items[sg.a].n_out = 0;
+      else if (sg.kind == FS_SMALL) ft.smalls[sg.a].n_out = 0;
+      else if (sg.kind == FS_VARJOB) { ft.jobs[sg.a].dst = ft.arena + rq.slot_off; ft.jobs[sg.a].cap = 0; }
+    }
+    return;
+  }
+  ft.status[r] = B200TFS_OK;
+  uint8_t* w = ft.arena + start;
+  for (uint32_t k = 0; k < rq.n_seg; ++k) {
+    const FrameSeg sg = ft.segs[rq.first_seg + k];
+    switch (sg.kind) {
+      case FS_BYTES: { const uint8_t* b = ft.blob + sg.a; for (uint32_t q = 0; q < sg.b; ++q) w[q] = b[q]; w += sg.b; break; }
+      case FS_VARINT: w += put_varint(w, val[sg.a]); break;
+      case FS_BE32: { const uint64_t m = val[sg.a]; w[0] = (uint8_t)(m >> 24); w[1] = (uint8_t)(m >> 16); w[2] = (uint8_t)(m >> 8); w[3] = (uint8_t)m; w += 4; break; }
+      case FS_ITEM: ft.items[sg.a].dst = w; w += ft.items[sg.a].n_out; break;
+      case FS_SMALL: ft.smalls[sg.a].dst = w; w += ft.smalls[sg.a].n_out; break;
+      default: { const uint64_t L = *ft.jobs[sg.a].total; ft.jobs[sg.a].dst = w; ft.jobs[sg.a].cap = L; w += L; break; }
+    }
+  }
+}
+
+cudaError_t launch_frame_requests(const FrameTables& ft, cudaStream_t stream) {
+  if (!ft.n) return cudaSuccess;
+  frame_requests_kernel<<<(ft.n + 63) / 64, 64, 0, stream>>>(ft);
+  return cudaGetLastError();
+}
 
 // TensorFlow's MakeNdarray padding (B200TFS_OF_PAD_EDGE): elements [have, n_elems) of dst take the value of element
 // have-1, or zero when there is none.  `have` comes from the host (fixed-width values: known from the chunk lengths) or

@@ -29,6 +29,7 @@ uint32_t tiles_for_host(uint64_t n_out, uint32_t vpt);
 cudaError_t launch_fill_edge(uint8_t* dst, uint32_t elem_size, uint64_t have, const unsigned long long* have_dev, uint64_t n_elems,
                              cudaStream_t stream);
 // packed varints (varint_kernels.cuh): the tables and counters every kernel uses are addressed through VarTables
+cudaError_t launch_frame_requests(const FrameTables& ft, cudaStream_t stream);
 cudaError_t launch_venc_len(const VarTables& tb, cudaStream_t stream);
 cudaError_t launch_venc_emit(const VarTables& tb, cudaStream_t stream);
 cudaError_t launch_vdec_count(const VarTables& tb, cudaStream_t stream);

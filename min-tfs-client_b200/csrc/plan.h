@@ -157,6 +157,41 @@ struct VarTables {
   VarJobDev job0;
 };
 
+// ---- deferred framing: the length prefixes of packed-varint inputs computed ON THE DEVICE -----------------------------
+// Every length on the wire precedes its content, and a packed-varint payload's length is only known once the counting
+// kernel has run.  Instead of bringing it to the host (b200tfs_measure: a stream synchronise in the middle of an encode),
+// the host describes each request as a little program - byte runs it knows, varints of VALUES the device evaluates
+// (sums of constants, job totals, other values and the varint lengths of other values), and the payloads whose
+// destinations depend on those values - and frame_requests_kernel (one thread per request) lays the record out, writes the
+// framing and patches the destinations into the move plan / the emit jobs that run right behind it.  No host round trip:
+// the whole encode is asynchronous and CUDA-graph capturable.
+enum FrameSegKind : uint32_t {
+  FS_BYTES = 0,   // a = offset into the frame blob, b = byte count
+  FS_VARINT = 1,  // a = value id (request-local): varint(value)
+  FS_BE32 = 2,    // a = value id: four bytes, big endian (gRPC's message length)
+  FS_ITEM = 3,    // a = MoveItem index: its n_out bytes land here (dst patched)
+  FS_SMALL = 4,   // a = SmallItem index: likewise
+  FS_VARJOB = 5   // a = varint job index: total[job] bytes land here (dst and cap patched)
+};
+struct FrameSeg { uint32_t kind, a, b, pad; };
+enum FrameTermKind : uint32_t { FT_TOTAL = 0, FT_VAL = 1, FT_VLEN = 2 };   // + total[job], + value[i], + varint_len(value[i])
+struct FrameTerm { uint32_t kind, idx; };
+struct FrameVal { int64_t c; uint32_t first_term, n_terms; };               // evaluated in order: terms refer to earlier values only
+struct FrameReq {
+  uint32_t first_seg, n_seg, first_val, n_val;
+  uint32_t align_seg;       // the payload segment that should start 128-byte aligned (index relative to first_seg), ~0u: none
+  uint32_t total_val;       // value id of the record's byte length (incl. a gRPC prefix)
+  uint64_t slot_off, slot_cap;   // where the record may lie inside the arena (worst-case sized by the host)
+};
+struct FrameTables {
+  const FrameReq* reqs; const FrameSeg* segs; const FrameVal* vals; const FrameTerm* terms; const uint8_t* blob;
+  uint64_t* scratch_vals;   // one evaluated value per FrameVal
+  uint8_t* arena;
+  MoveItem* items; SmallItem* smalls; VarJobDev* jobs;    // patched
+  uint64_t* rec_off; uint64_t* rec_len; int32_t* status;  // pinned host memory: read by b200tfs_encode_results
+  uint32_t n;
+};
+
 // decode tiles of a chunk [src, src + n): aligned windows of kVarTileBytes starting at src rounded down to 16
 #if defined(__CUDACC__)
 #define B2_PLAN_HD __host__ __device__ __forceinline__

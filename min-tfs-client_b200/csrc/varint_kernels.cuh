@@ -226,6 +226,30 @@ __global__ void __launch_bounds__(kVarThreads, 5) venc_emit_kernel(const __grid_
   const uint32_t sbase = (uint32_t)__cvta_generic_to_shared(smem);
   const uint32_t sa0 = sbase + (off & ~3u);      // shared-window address of the word being filled
   uint32_t sa = sa0, f = f0, acc = 0;
+  // Every varint of the warp fits four bytes (values below 2^28: token ids, indices, class labels, small counts - the bulk of
+  // what int_val / int64_val carry in practice)?  Then an element is one spread word, completes at most one 32-bit word of the
+  // image, and the upper half of the value is never looked at: ~20 instructions per element instead of ~45.
+  const bool narrow = __all_sync(0xFFFFFFFFu, ((lens + 0x33333333u) & 0x88888888u) == 0u);   // every nibble <= 4
+  if (narrow) {
+#pragma unroll
+    for (uint32_t i = 0; i < kVarPerThread; ++i) {
+      const uint32_t lo = (uint32_t)mine[i];
+      const uint32_t L = (lens >> (4 * i)) & 15u;
+      const uint32_t w0 = bitsel(0x7F7F7F7Fu, spread28(lo), __funnelshift_lc(0xFFFFFFFFu, 0u, 8u * L - 8u));   // L = 0: see below
+      const uint32_t shb = f * 8u;
+      const uint32_t o0 = acc | (w0 << shb);
+      const uint32_t o1 = __funnelshift_l(w0, 0u, shb);
+      const uint32_t n = f + L;
+      asm volatile(
+          "{\n\t.reg .pred p0;\n\t"
+          "setp.ge.u32 p0, %1, 4;\n\t"
+          "@p0 st.shared.u32 [%2], %3;\n\t"
+          "selp.b32 %0, %4, %3, p0;\n\t}"
+          : "=r"(acc) : "r"(n), "r"(sa), "r"(o0), "r"(o1) : "memory");
+      sa += n & ~3u;
+      f = n & 3;
+    }
+  } else {
 #pragma unroll
   for (uint32_t i = 0; i < kVarPerThread; ++i) {
     const uint32_t lo = (uint32_t)mine[i], hi = (uint32_t)(mine[i] >> 32);
@@ -256,6 +280,7 @@ __global__ void __launch_bounds__(kVarThreads, 5) venc_emit_kernel(const __grid_
         : "=r"(acc) : "r"(n), "r"(sa), "r"(o0), "r"(o1), "r"(o2), "r"(o3) : "memory");
     sa += n & ~3u;
     f = n & 3;
+  }
   }
   __syncthreads();
   // the word this thread did not complete: its bytes only (the thread that completes the word stored zeros there)

@@ -25,8 +25,8 @@ VARIANTS = [
     ("no inline template", {"B200TFS_NO_INLINE_TEMPLATE": "1"}),
     ("table in device memory", {"B200TFS_TABLE_DEV": "1"}),
     ("table in device memory, no inline", {"B200TFS_TABLE_DEV": "1", "B200TFS_NO_INLINE_TEMPLATE": "1"}),
-    ("PDL", {"B200TFS_PDL": "1"}),
-    ("PDL + table in device memory", {"B200TFS_PDL": "1", "B200TFS_TABLE_DEV": "1"}),
+    ("payload 16-byte aligned (response placed at +5)", {"B200TFS_BENCH_RESP_SHIFT": "5"}),
+    ("payload aligned, no inline", {"B200TFS_BENCH_RESP_SHIFT": "5", "B200TFS_NO_INLINE_TEMPLATE": "1"}),
 ]
 
 
