@@ -496,9 +496,7 @@ class DeviceBatch:
         st["ts"], st["rq"], st["n_ts"] = ts, rq, n * n_in
         self.varint = any(lib.b200tfs_dtype_field(p.struct.wire_dtype) in (7, 10, 13, 16, 17) and not (p.struct.flags & N.F_TENSOR_CONTENT)
                           for p in preps)
-        if self.varint:
-            N.check(lib.b200tfs_measure(self.ctx, st["n_ts"], ts))
-        need = C.c_uint64(0)
+        need = C.c_uint64(0)   # packed-varint inputs stay unmeasured (packed_len 0): sized for b200tfs_encode_requests_async
         N.check(lib.b200tfs_request_arena_size(n, rq, C.byref(need)))
         st["arena_cap"] = int(need.value) + 256
         st["arena"] = self.malloc(st["arena_cap"])
@@ -519,9 +517,18 @@ class DeviceBatch:
         st, N, lib = self.sets[s % self.slots], self.N, self.lib
         if self.n == 0:
             return
-        if self.varint:     # packed-varint inputs: the measure pass supplies the length prefixes (synchronises)
-            N.check(lib.b200tfs_measure(self.ctx, st["n_ts"], st["ts"]))
-        N.check(lib.b200tfs_encode_requests(self.ctx, self.n, st["rq"], st["arena"], st["arena_cap"], st["rec_off"], st["rec_len"]))
+        if self.varint:     # packed-varint inputs: counted, framed and emitted by kernels alone - no host round trip (deferred framing)
+            N.check(lib.b200tfs_encode_requests_async(self.ctx, self.n, st["rq"], st["arena"], st["arena_cap"]))
+            st["results_pending"] = True
+        else:
+            N.check(lib.b200tfs_encode_requests(self.ctx, self.n, st["rq"], st["arena"], st["arena_cap"], st["rec_off"], st["rec_len"]))
+
+    def encode_results(self, s):
+        """Where the records of slot s lie (varint workloads learn it from the device: b200tfs_encode_results synchronises)."""
+        st = self.sets[s % self.slots]
+        if self.varint and self.n:
+            self.encode(s)          # the results buffer belongs to the context's most recent async encode: make it this slot's
+            self.N.check(self.lib.b200tfs_encode_results(self.ctx, self.n, st["rec_off"], st["rec_len"]))
 
     def decode(self, s):
         st, N, lib = self.sets[s % self.slots], self.N, self.lib
@@ -536,7 +543,7 @@ class DeviceBatch:
 
     @property
     def capturable(self):
-        return not self.varint and self.wl.out_dtype is None
+        return self.wl.out_dtype is None
 
     def capture(self, name, body, slot_list):
         """Record body(slot) for every slot of slot_list into one CUDA graph; returns kernels launched per replay."""
@@ -559,6 +566,7 @@ class DeviceBatch:
     # -- algorithmic bytes (read P write P+H on encode; read P+H write P on decode) --
     def algorithmic(self):
         st = self.sets[0]
+        self.encode_results(0)
         enc = sum(self.src_bytes + int(st["rec_len"][j]) for j in range(self.n))
         dec = self.n * (self.resp_len + self.dst_bytes)
         return enc, dec
@@ -585,6 +593,7 @@ class DeviceBatch:
         for s, st in enumerate(self.sets):
             if n == 0:
                 break
+            self.encode_results(s)
             if wl.out_dtype is None and s == 0:
                 status = (C.c_int32 * n)()
                 self.N.check(self.lib.b200tfs_decode_results(self.ctx, n, None, None, None, status))
@@ -833,7 +842,7 @@ def run_workload(wl: Workload, world: World, steps, warmup, e2e_steps, full_veri
         t_enc = db.timer.run(lambda k: db.replay("enc"), reps_k) / (reps_k * db.slots)
         db.timer.run(lambda k: db.replay("dec"), 1)
         t_dec = db.timer.run(lambda k: db.replay("dec"), reps_k) / (reps_k * db.slots)
-    enc_kernel = "move_kernel" + (" (+ venc_len / venc_emit for the int64 labels, + b200tfs_measure's host round trip)" if db.varint else "")
+    enc_kernel = "move_kernel" + (" (+ venc_len, frame_requests_kernel, venc_emit for the int64 labels: deferred framing, no host round trip)" if db.varint else "")
     dec_kernel = ("decode_fused_staged_kernel" if db.resp_len * db.n > 148 * 8 * 32768 else "decode_fused_kernel") if wl.out_dtype is None \
         else "parse_responses_kernel + move_kernel (OP_F2H / OP_F2B)"
     step_alg = enc_alg + dec_alg

@@ -251,7 +251,9 @@ int b200tfs_request_frame(const b200tfs_request* r, void* buf, uint64_t cap, uin
 int b200tfs_order_keys(int32_t n, const char* const* keys, const int64_t* key_lens, int32_t order,
                        int32_t* perm);
 /* Arena bytes needed to encode these records with b200tfs_encode_* (records are placed so that the
- * largest payload of each lands 128-byte aligned; the arena base must be 256-byte aligned).        */
+ * largest payload of each lands 128-byte aligned; the arena base must be 256-byte aligned).  A batch of requests in
+ * which some packed-varint input has packed_len == 0 (not measured) is sized for b200tfs_encode_requests_async: one
+ * worst-case slot per record.                                                                       */
 int b200tfs_tensor_arena_size(int32_t n, const b200tfs_tensor* tensors, uint64_t* bytes);
 int b200tfs_request_arena_size(int32_t n, const b200tfs_request* reqs, uint64_t* bytes);
 
@@ -272,6 +274,24 @@ int b200tfs_encode_tensor_protos(b200tfs_ctx* ctx, int32_t n, const b200tfs_tens
  * builds in requests.py:41-48).  Async.                                                            */
 int b200tfs_encode_requests(b200tfs_ctx* ctx, int32_t n, const b200tfs_request* reqs, void* arena_dev,
                             uint64_t arena_cap, uint64_t* rec_off, uint64_t* rec_len);
+
+/* The same encode WITHOUT the host-side measuring pass: inputs of the packed-varint dtypes may carry packed_len == 0.
+ * Their lengths are counted, the length prefixes (and every length that encloses them) written, and the record placed by
+ * kernels alone - count -> frame_requests_kernel (one thread per request evaluates the dependent varints, writes the
+ * framing, patches the destinations of the payload movers) -> move + emit - so the call never synchronises and can be
+ * captured in a CUDA graph (b200tfs_measure cannot).  Every record gets a 256-byte aligned slot sized for its worst case
+ * (b200tfs_request_arena_size does that when it sees an unmeasured input) and lies inside it with its largest payload
+ * 128-byte aligned; WHERE exactly, and how long it is, is known once the kernels have run: b200tfs_encode_results
+ * synchronises and delivers rec_off / rec_len (or the first per-request error).  Bytes identical to b200tfs_encode_requests. */
+int b200tfs_encode_requests_async(b200tfs_ctx* ctx, int32_t n, const b200tfs_request* reqs, void* arena_dev,
+                                  uint64_t arena_cap);
+int b200tfs_encode_results(b200tfs_ctx* ctx, int32_t n, uint64_t* rec_off, uint64_t* rec_len);
+/* What frame_requests_kernel computes for ONE request, run on the host (the same inline code; needs no device): given the
+ * packed length of every packed-varint input (packed_len[i] for inputs[i]; other entries ignored) it writes every framing
+ * byte of the record into buf at the place it has on the wire and reports where the record lies (rec_off / rec_len) and,
+ * per input, where its payload belongs (payload_off[i] / payload_len[i]; 0 / 0 for an input without values).            */
+int b200tfs_request_frame_deferred(const b200tfs_request* r, const uint64_t* packed_len, void* buf, uint64_t cap,
+                                   uint64_t* rec_off, uint64_t* rec_len, uint64_t* payload_off, uint64_t* payload_len);
 
 /* ---- decode (device wire arena -> table -> device tensors) -------------------------------------- */
 /* Parse n PredictResponse messages lying at rec_off[i]..+rec_len[i] of the device arena.  Runs the

@@ -20,6 +20,7 @@
 #include <vector>
 
 #include "../../include/b200tfs.h"
+#include "frame.h"
 #include "kernels.h"
 #include "plan.h"
 #include "tpl.h"
@@ -115,6 +116,8 @@ struct b200tfs_ctx {
   uint32_t spill_last_per = 0;          // geometry of spill_host
   int32_t spill_last_n = 0;
   Growable gather_dev;                  // unpack: strided / many-run varint outputs are first gathered into one stream here
+  Growable enc_host;                    // b200tfs_encode_requests_async: rec_off | rec_len | status, written by frame_requests_kernel (pinned)
+  int32_t enc_n = 0;
   bool has_graphs = false;              // a CUDA graph captured on this context refers to the scratch buffers: they may not move any more
 };
 
@@ -240,6 +243,7 @@ int b200tfs_destroy(b200tfs_ctx* c) {
   if (c->scratch_dev.p) cudaFree(c->scratch_dev.p);
   if (c->spill_dev.p) cudaFree(c->spill_dev.p);
   if (c->gather_dev.p) cudaFree(c->gather_dev.p);
+  if (c->enc_host.p) cudaFreeHost(c->enc_host.p);
   if (c->measured_dev.p) cudaFree(c->measured_dev.p);
   if (c->scratch_host.p) cudaFreeHost(c->scratch_host.p);
   if (c->stage_dev.p) cudaFree(c->stage_dev.p);
@@ -334,6 +338,9 @@ int b200tfs_cast_supported(int32_t src, int32_t wire) {
 // ------------------------------------------------------------------------------------------------
 // wire-size arithmetic and header bytes
 // ------------------------------------------------------------------------------------------------
+static bool request_needs_deferred(const b200tfs_request& r);                  // varint_host.inc
+static int deferred_slot_bound(const b200tfs_request& r, uint64_t* bound);     // varint_host.inc
+
 namespace {
 
 constexpr uint64_t kProtoLimit = 0x7FFFFFFFull;  // protobuf's 2 GiB message limit
@@ -492,10 +499,18 @@ uint32_t pick_vec_per_tile(const b200tfs_ctx* c, uint64_t large_bytes, uint64_t 
   return (uint32_t)(tile / 16);
 }
 
-// Serialise the plan image and launch move_kernel.  blob offsets inside SmallItems are rebased onto
-// the image.
-int launch_plan(b200tfs_ctx* c, PlanBuilder& pb) {
-  if (pb.items.empty() && pb.smalls.empty()) return B200TFS_OK;
+// Serialise the plan image (blob offsets inside SmallItems are rebased onto the image).  Small images travel in the kernel
+// parameters unless `force_dev`: then - and for large images - the image is uploaded and *plan_dev points at it.
+struct BuiltPlan {
+  PlanHeader ph{};
+  uint8_t inline_buf[kInlinePlanBytes];
+  const uint8_t* host_img = nullptr;
+  uint8_t* plan_dev = nullptr;   // nullptr: inline
+  uint64_t image = 0;
+  Slot* slot = nullptr;
+};
+
+int build_plan(b200tfs_ctx* c, PlanBuilder& pb, bool force_dev, BuiltPlan* bp) {
   const uint32_t vpt = pick_vec_per_tile(c, pb.large_bytes);
   // tiles
   uint64_t n_tiles = 0;
@@ -509,7 +524,8 @@ int launch_plan(b200tfs_ctx* c, PlanBuilder& pb) {
     n_tiles += t;
   }
   if (!is_uniform) uniform = 0;
-  PlanHeader ph{};
+  PlanHeader& ph = bp->ph;
+  ph = PlanHeader{};
   ph.n_items = (uint32_t)pb.items.size();
   ph.n_tiles = (uint32_t)n_tiles;
   ph.n_small = (uint32_t)pb.smalls.size();
@@ -524,17 +540,16 @@ int launch_plan(b200tfs_ctx* c, PlanBuilder& pb) {
   off += pb.blob.size();
   const uint64_t image = (off + 15) & ~15ull;
   if (image > 0xFFFFFFFFull) return fail(B200TFS_E_TOOBIG, "plan image larger than 4 GiB");
-
-  uint8_t inline_buf[kInlinePlanBytes];
+  bp->image = image;
   uint8_t* img;
-  Slot* slot = nullptr;
-  const bool inl = image <= kInlinePlanBytes;
-  if (inl) img = inline_buf;
+  const bool inl = !force_dev && image <= kInlinePlanBytes;
+  if (inl) img = bp->inline_buf;
   else {
-    int rc = claim_slot(c, image, &slot);
+    int rc = claim_slot(c, image, &bp->slot);
     if (rc) return rc;
-    img = (uint8_t*)slot->host.p;
+    img = (uint8_t*)bp->slot->host.p;
   }
+  bp->host_img = img;
   memcpy(img, &ph, sizeof ph);
   if (!pb.items.empty()) memcpy(img + ph.off_items, pb.items.data(), pb.items.size() * sizeof(MoveItem));
   if (!uniform && n_tiles) {
@@ -549,16 +564,26 @@ int launch_plan(b200tfs_ctx* c, PlanBuilder& pb) {
     if (sm[i].op & OP_FLAG_BLOB) sm[i].src += off_blob;
   }
   if (!pb.blob.empty()) memcpy(img + off_blob, pb.blob.data(), pb.blob.size());
-
-  const uint8_t* plan_dev = nullptr;
   if (!inl) {
-    CU(cudaMemcpyAsync(slot->dev.p, img, image, cudaMemcpyHostToDevice, c->stream));
-    plan_dev = (const uint8_t*)slot->dev.p;
+    CU(cudaMemcpyAsync(bp->slot->dev.p, img, image, cudaMemcpyHostToDevice, c->stream));
+    bp->plan_dev = (uint8_t*)bp->slot->dev.p;
   }
-  CU(launch_move(plan_dev, img, (uint32_t)image, ph.n_tiles, ph.n_small, c->stream));
-  c->launches += 1;
-  if (slot && slot->done) { CU(cudaEventRecord(slot->done, c->stream)); slot->pending = true; }
   return B200TFS_OK;
+}
+
+int launch_built_plan(b200tfs_ctx* c, BuiltPlan& bp) {
+  CU(launch_move(bp.plan_dev, bp.host_img, (uint32_t)bp.image, bp.ph.n_tiles, bp.ph.n_small, c->stream));
+  c->launches += 1;
+  if (bp.slot && bp.slot->done) { CU(cudaEventRecord(bp.slot->done, c->stream)); bp.slot->pending = true; }
+  return B200TFS_OK;
+}
+
+int launch_plan(b200tfs_ctx* c, PlanBuilder& pb) {
+  if (pb.items.empty() && pb.smalls.empty()) return B200TFS_OK;
+  BuiltPlan bp;
+  int rc = build_plan(c, pb, false, &bp);
+  if (rc) return rc;
+  return launch_built_plan(c, bp);
 }
 
 // record placement: slots start 256-byte aligned, then padded so the record's largest payload
@@ -776,7 +801,21 @@ int b200tfs_tensor_arena_size(int32_t n, const b200tfs_tensor* tensors, uint64_t
 
 int b200tfs_request_arena_size(int32_t n, const b200tfs_request* reqs, uint64_t* bytes) {
   if (n < 0 || (n && !reqs) || !bytes) return fail(B200TFS_E_ARG, "bad arguments");
+  // a batch with an unmeasured packed-varint input (packed_len == 0) is sized for b200tfs_encode_requests_async: every record
+  // gets a slot for its worst case; measured batches are sized exactly, as b200tfs_encode_requests lays them out
+  bool deferred = false;
+  for (int i = 0; i < n && !deferred; ++i) deferred = request_needs_deferred(reqs[i]);
   uint64_t cursor = 0;
+  if (deferred) {
+    for (int i = 0; i < n; ++i) {
+      uint64_t bound = 0;
+      int rc = deferred_slot_bound(reqs[i], &bound);
+      if (rc) return rc;
+      cursor = ((cursor + 255) & ~255ull) + bound + 128;
+    }
+    *bytes = (cursor + 255) & ~255ull;
+    return B200TFS_OK;
+  }
   RequestLayout R;
   for (int i = 0; i < n; ++i) {
     int rc = request_layout(reqs[i], &R);

@@ -30,6 +30,7 @@
 #include <algorithm>
 #include <utility>
 
+#include "frame.h"
 #include "kernels.h"
 #include "plan.h"
 #include "tpl.h"
@@ -381,30 +382,26 @@ __device__ __forceinline__ void move_tile_gather(const SrcView& src, uint8_t* __
   for (uint64_t i = b0 + threadIdx.x; i < b1; i += blockDim.x) dst[i] = gen_byte(op, src, i);
 }
 
-template <class Mid>
+// DEC: the caller only ever passes OP_COPY / OP_QUIET_DST (the single-launch decode moves float_val / double_val / complex
+// values as they are): the other bodies are not instantiated.  Code size is not cosmetic here - with every body inlined three
+// times the fused decode kernel was 728 KB of SASS, its hot path scattered over it, and a 4 MiB launch paid ~1 us of
+// instruction fetch that no data-path change could touch (profiles/r02_decode_latency.md).
+template <bool DEC, class Mid>
 __device__ __forceinline__ bool move_tile(const uint8_t* __restrict__ src, uint8_t* __restrict__ dst, uint64_t n_out, uint32_t op,
                                           uint32_t n_tiles, uint32_t tile, uint32_t vpt, Mid& mid) {
   const bool last = (tile + 1 == n_tiles);
-  const uint64_t n_src = src_bytes_for(op, n_out);
+  const uint64_t n_src = DEC ? n_out : src_bytes_for(op, n_out);
   uint64_t head = (16 - ((uintptr_t)dst & 15)) & 15;
   if (head > n_out) head = n_out;
   bool fast = true;
   uint64_t nvec;                 // destination vectors a vector path may handle
   const uint8_t* src_body = src + head;
-  if (op <= OP_QUIET_DST) {      // OP_COPY, OP_QUIET_SRC, OP_QUIET_DST (same width); OP_BOOL handled below
-    if (op == OP_QUIET_SRC) fast = (((uintptr_t)src & 3) == 0);
+  if (DEC || op <= OP_QUIET_DST || op == OP_BOOL) {      // same width
+    if (!DEC && op == OP_QUIET_SRC) fast = (((uintptr_t)src & 3) == 0);
     if (op == OP_QUIET_DST) fast = ((head & 3) == 0);
     nvec = (n_out - head) >> 4;
     const uint32_t k = (uint32_t)((uintptr_t)src_body & 15);
     if (k) {  // the shifted path also reads block v+1: keep that inside the source
-      const uint64_t blocks = (uint64_t)((src + n_src) - (src_body - k)) >> 4;
-      const uint64_t lim = blocks ? blocks - 1 : 0;
-      if (nvec > lim) nvec = lim;
-    }
-  } else if (op == OP_BOOL) {
-    nvec = (n_out - head) >> 4;
-    const uint32_t k = (uint32_t)((uintptr_t)src_body & 15);
-    if (k) {
       const uint64_t blocks = (uint64_t)((src + n_src) - (src_body - k)) >> 4;
       const uint64_t lim = blocks ? blocks - 1 : 0;
       if (nvec > lim) nvec = lim;
@@ -435,15 +432,20 @@ __device__ __forceinline__ bool move_tile(const uint8_t* __restrict__ src, uint8
   if (v0 < nvec) {
     const uint32_t n = (uint32_t)min((uint64_t)vpt, nvec - v0);
     uint8_t* d = dst + head + 16 * v0;
-    switch (op) {
-      case OP_COPY: go = body_same_width<OP_COPY>(src_body + 16 * v0, d, n, mid); break;
-      case OP_BOOL: go = body_same_width<OP_BOOL>(src_body + 16 * v0, d, n, mid); break;
-      case OP_QUIET_SRC: go = body_same_width<OP_QUIET_SRC>(src_body + 16 * v0, d, n, mid); break;
-      case OP_QUIET_DST: go = body_same_width<OP_QUIET_DST>(src_body + 16 * v0, d, n, mid); break;
-      case OP_H2F: go = mid(); if (go) body_widen<false>(src_body + 8 * v0, d, n >> 1); break;
-      case OP_B2F: go = mid(); if (go) body_widen<true>(src_body + 8 * v0, d, n >> 1); break;
-      case OP_F2H: go = mid(); if (go) body_narrow<false>(src_body + 32 * v0, d, n); break;
-      default: go = mid(); if (go) body_narrow<true>(src_body + 32 * v0, d, n); break;
+    if (DEC) {
+      if (op == OP_COPY) go = body_same_width<OP_COPY>(src_body + 16 * v0, d, n, mid);
+      else go = body_same_width<OP_QUIET_DST>(src_body + 16 * v0, d, n, mid);
+    } else {
+      switch (op) {
+        case OP_COPY: go = body_same_width<OP_COPY>(src_body + 16 * v0, d, n, mid); break;
+        case OP_BOOL: go = body_same_width<OP_BOOL>(src_body + 16 * v0, d, n, mid); break;
+        case OP_QUIET_SRC: go = body_same_width<OP_QUIET_SRC>(src_body + 16 * v0, d, n, mid); break;
+        case OP_QUIET_DST: go = body_same_width<OP_QUIET_DST>(src_body + 16 * v0, d, n, mid); break;
+        case OP_H2F: go = mid(); if (go) body_widen<false>(src_body + 8 * v0, d, n >> 1); break;
+        case OP_B2F: go = mid(); if (go) body_widen<true>(src_body + 8 * v0, d, n >> 1); break;
+        case OP_F2H: go = mid(); if (go) body_narrow<false>(src_body + 32 * v0, d, n); break;
+        default: go = mid(); if (go) body_narrow<true>(src_body + 32 * v0, d, n); break;
+      }
     }
   } else go = mid();
   if (!go) return false;
@@ -451,6 +453,103 @@ __device__ __forceinline__ bool move_tile(const uint8_t* __restrict__ src, uint8
   if (tile == 0) for (uint64_t i = threadIdx.x; i < head; i += blockDim.x) dst[i] = gen_byte(op, src, i);
   if (last) for (uint64_t i = head + (nvec << 4) + threadIdx.x; i < n_out; i += blockDim.x) dst[i] = gen_byte(op, src, i);
   return true;
+}
+
+// ------------------------------------------------------------------------------------------------
+// decode_tile: the single-response decode's tile move (OP_COPY / OP_QUIET_DST only), written for CODE SIZE: one load phase
+// (each warp owns a contiguous run, as in body_shifted_q), the verdict hook once, one store phase in which source alignment
+// (which of the 8 words of two neighbouring blocks an output word starts in, and the bit shift) and the sNaN fix-up are
+// run-time values behind warp-uniform branches instead of template instantiations.  ~6 KB of SASS where the fully templated
+// move_tile with the verdict inlined into every body took ~240 KB - and the launch ~1 us longer, spent fetching instructions.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint8_t gen_byte_dec(bool quiet, const uint8_t* src, uint64_t i) {
+  if (!quiet) return src[i];
+  const uint32_t w = quiet_f32(ld_u32_bytes(src + (i & ~3ull)));
+  return (uint8_t)(w >> (8 * (i & 3)));
+}
+
+__device__ __forceinline__ uint4 shift_pair_dyn(const uint4& lo, const uint4& hi, uint32_t q, uint32_t s) {
+  switch (q) {   // warp-uniform
+    case 0: return shift_pair<0>(lo, hi, s);
+    case 1: return shift_pair<1>(lo, hi, s);
+    case 2: return shift_pair<2>(lo, hi, s);
+    default: return shift_pair<3>(lo, hi, s);
+  }
+}
+
+template <class Mid>
+__device__ __forceinline__ bool decode_tile(const uint8_t* __restrict__ src, uint8_t* __restrict__ dst, uint64_t n_out, bool quiet,
+                                            uint32_t n_tiles, uint32_t tile, uint32_t vpt, Mid& mid) {
+  const bool last = (tile + 1 == n_tiles);
+  uint64_t head = (16 - ((uintptr_t)dst & 15)) & 15;
+  if (head > n_out) head = n_out;
+  const uint8_t* src_body = src + head;
+  const uint32_t k = (uint32_t)((uintptr_t)src_body & 15);
+  uint64_t nvec = (n_out - head) >> 4;
+  if (k) {  // block v+1 is read as well: keep it inside the source
+    const uint64_t blocks = (uint64_t)((src + n_out) - (src_body - k)) >> 4;
+    const uint64_t lim = blocks ? blocks - 1 : 0;
+    if (nvec > lim) nvec = lim;
+  }
+  if (quiet && (head & 3)) {   // float elements do not line up with the destination vectors: byte path (never for 256-aligned slots)
+    if (!mid()) return false;
+    const uint64_t b0 = (uint64_t)tile * vpt * 16;
+    uint64_t b1 = b0 + (uint64_t)vpt * 16;
+    if (b1 > n_out || last) b1 = n_out;
+    for (uint64_t i = b0 + threadIdx.x; i < b1; i += blockDim.x) dst[i] = gen_byte_dec(true, src, i);
+    return true;
+  }
+  const uint64_t v0 = (uint64_t)tile * vpt;
+  if (v0 < nvec) {
+    const uint32_t n = (uint32_t)min((uint64_t)vpt, nvec - v0);
+    const uint8_t* S = src_body - k + 16 * v0;
+    uint8_t* d = dst + head + 16 * v0;
+    const uint32_t s = (k & 3) * 8, q = k >> 2;
+    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    constexpr uint32_t kRun = kBatchShift * 32, kRound = kRun * (kMoveThreads / 32);
+    for (uint32_t base = 0; base < n; base += kRound) {            // uniform trip count across the CTA
+      const uint32_t run = base + warp * kRun;
+      const uint32_t run_end = min(run + kRun, n);
+      uint4 lo[kBatchShift], extra = make_uint4(0, 0, 0, 0);
+#pragma unroll
+      for (uint32_t i = 0; i < kBatchShift; ++i) {
+        const uint32_t u = run + 32 * i + lane;
+        lo[i] = make_uint4(0, 0, 0, 0);
+        if (u < n) lo[i] = ld_stream(S + 16ull * u);
+      }
+      if (k && lane == 0 && run < n) extra = ld_stream(S + 16ull * run_end);
+      if (base == 0 && !mid()) return false;
+      extra = shfl_lane0(extra);
+#pragma unroll
+      for (uint32_t i = 0; i < kBatchShift; ++i) {
+        const uint32_t u = run + 32 * i + lane;
+        uint4 b = shfl_down1(lo[i]);                               // lanes 0..30: neighbour's block
+        if (i + 1 < kBatchShift) {
+          const uint4 nxt = shfl_lane0(lo[i + 1]);                 // lane 31: first block of the next element
+          if (lane == 31) b = nxt;
+        }
+        if (u + 1 == run_end) b = extra;                           // last vector of the run (or of a ragged tile)
+        if (u < n) {
+          uint4 o = lo[i];
+          if (k) o = shift_pair_dyn(lo[i], b, q, s);
+          if (quiet) o = fix_vec<OP_QUIET_DST>(o);
+          st_stream(d + 16ull * u, o);
+        }
+      }
+    }
+  } else if (!mid()) return false;
+  // ragged edges, element-exact
+  if (tile == 0) for (uint64_t i = threadIdx.x; i < head; i += blockDim.x) dst[i] = gen_byte_dec(quiet, src, i);
+  if (last) for (uint64_t i = head + (nvec << 4) + threadIdx.x; i < n_out; i += blockDim.x) dst[i] = gen_byte_dec(quiet, src, i);
+  return true;
+}
+
+// one out-of-line copy of the decode-side tile move for the paths where speed is not the point (a walked record, a staged
+// tile whose geometry does not qualify): called, not inlined, so that the hot paths stay compact
+__device__ __noinline__ void move_tile_cold(const uint8_t* src, uint8_t* dst, uint64_t n_out, uint32_t op, uint32_t n_tiles, uint32_t tile,
+                                            uint32_t vpt) {
+  AlwaysGo go;
+  move_tile<true>(src, dst, n_out, op, n_tiles, tile, vpt, go);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -470,7 +569,7 @@ __device__ __forceinline__ void move_body(const uint8_t* plan) {
     const MoveItem& it = reinterpret_cast<const MoveItem*>(plan + ph.off_items)[item];
     if (it.gstride) { move_tile_gather(SrcView{it.src, it.glen, it.gstride}, it.dst, it.n_out, it.op, it.n_tiles, tile, ph.vec_per_tile); return; }
     AlwaysGo go;
-    move_tile(it.src, it.dst, it.n_out, it.op, it.n_tiles, tile, ph.vec_per_tile, go);
+    move_tile<false>(it.src, it.dst, it.n_out, it.op, it.n_tiles, tile, ph.vec_per_tile, go);
   } else {
     const uint32_t warps = blockDim.x >> 5;
     const uint32_t idx = (b - ph.n_tiles) * warps + (threadIdx.x >> 5);
@@ -888,17 +987,15 @@ __device__ __forceinline__ void decode_fused_body(const FusedParams& fp) {
           if (stg.use)
             staged_finish(stg, rec + ch_s[mine].wire_off, dst_slot + ch_s[mine].dst_off, ch_s[mine].len, ch_s[mine].op, ch_s[mine].n_tiles,
                           j - t_base, stage_smem, stage_bars);
-          else {
-            AlwaysGo go;
-            move_tile(rec + ch_s[mine].wire_off, dst_slot + ch_s[mine].dst_off, ch_s[mine].len, ch_s[mine].op, ch_s[mine].n_tiles, j - t_base,
-                      fp.vpt, go);
-          }
+          else
+            move_tile_cold(rec + ch_s[mine].wire_off, dst_slot + ch_s[mine].dst_off, ch_s[mine].len, ch_s[mine].op, ch_s[mine].n_tiles, j - t_base,
+                           fp.vpt);
         }
         if (!hit) staged_drain(stg, stage_bars, 0);   // let the copies land, then walk the record
       } else if (mine < kTplChunks) {
         // the tile's loads go out first; the verdict runs while they are in flight and decides whether anything is stored
-        hit = move_tile(rec + ch_s[mine].wire_off, dst_slot + ch_s[mine].dst_off, ch_s[mine].len, ch_s[mine].op, ch_s[mine].n_tiles, j - t_base,
-                        fp.vpt, verdict);
+        hit = decode_tile(rec + ch_s[mine].wire_off, dst_slot + ch_s[mine].dst_off, ch_s[mine].len, ch_s[mine].op == OP_QUIET_DST,
+                          ch_s[mine].n_tiles, j - t_base, fp.vpt, verdict);
       } else hit = verdict();
       if (hit) {
         if (j == budget - 1) {   // the record's last CTA - a slack CTA with no tile - publishes the table, so no tile waits on it
@@ -927,10 +1024,7 @@ __device__ __forceinline__ void decode_fused_body(const FusedParams& fp) {
   __syncthreads();
   if (job.valid) {
     if (job.gstride) move_tile_gather(SrcView{job.src, job.glen, job.gstride}, job.dst, job.n_out, job.op, job.n_tiles, job.tile, fp.vpt);
-    else {
-      AlwaysGo go;
-      move_tile(job.src, job.dst, job.n_out, job.op, job.n_tiles, job.tile, fp.vpt, go);
-    }
+    else move_tile_cold(job.src, job.dst, job.n_out, job.op, job.n_tiles, job.tile, fp.vpt);
   }
 }
 
@@ -951,62 +1045,7 @@ __global__ void __launch_bounds__(kMoveThreads, 3) decode_fused_staged_kernel(co
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(64) frame_requests_kernel(const __grid_constant__ FrameTables ft) {
   const uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
-  if (r >= ft.n) return;
-  const FrameReq rq = ft.reqs[r];
-  uint64_t* val = ft.scratch_vals + rq.first_val;
-  for (uint32_t v = 0; v < rq.n_val; ++v) {
-    const FrameVal fv = ft.vals[rq.first_val + v];
-    uint64_t x = (uint64_t)fv.c;
-    for (uint32_t k = 0; k < fv.n_terms; ++k) {
-      const FrameTerm t = ft.terms[fv.first_term + k];
-      if (t.kind == FT_TOTAL) x += *ft.jobs[t.idx].total;
-      else if (t.kind == FT_VAL) x += val[t.idx];
-      else x += varint_len(val[t.idx]);
-    }
-    val[v] = x;
-  }
-  auto seg_len = [&](const FrameSeg& sg) -> uint64_t {
-    switch (sg.kind) {
-      case FS_BYTES: return sg.b;
-      case FS_VARINT: return varint_len(val[sg.a]);
-      case FS_BE32: return 4;
-      case FS_ITEM: return ft.items[sg.a].n_out;
-      case FS_SMALL: return ft.smalls[sg.a].n_out;
-      default: return *ft.jobs[sg.a].total;
-    }
-  };
-  uint64_t pad = 0;
-  if (rq.align_seg != ~0u) {
-    uint64_t before = 0;
-    for (uint32_t k = 0; k < rq.align_seg; ++k) before += seg_len(ft.segs[rq.first_seg + k]);
-    pad = (128 - ((rq.slot_off + before) & 127)) & 127;
-  }
-  const uint64_t total = val[rq.total_val];
-  const uint64_t start = rq.slot_off + pad;
-  ft.rec_off[r] = start; ft.rec_len[r] = total;
-  if (pad + total > rq.slot_cap || total > 0x7FFFFFFFull + 5) {   // cannot happen with the host's worst-case slots; never write outside one
-    ft.status[r] = total > 0x7FFFFFFFull + 5 ? B200TFS_E_TOOBIG : B200TFS_E_SIZE;
-    for (uint32_t k = 0; k < rq.n_seg; ++k) {   // park the movers on an empty range
-      const FrameSeg sg = ft.segs[rq.first_seg + k];
-      if (sg.kind == FS_ITEM) ft.items[sg.a].n_out = 0;
-      else if (sg.kind == FS_SMALL) ft.smalls[sg.a].n_out = 0;
-      else if (sg.kind == FS_VARJOB) { ft.jobs[sg.a].dst = ft.arena + rq.slot_off; ft.jobs[sg.a].cap = 0; }
-    }
-    return;
-  }
-  ft.status[r] = B200TFS_OK;
-  uint8_t* w = ft.arena + start;
-  for (uint32_t k = 0; k < rq.n_seg; ++k) {
-    const FrameSeg sg = ft.segs[rq.first_seg + k];
-    switch (sg.kind) {
-      case FS_BYTES: { const uint8_t* b = ft.blob + sg.a; for (uint32_t q = 0; q < sg.b; ++q) w[q] = b[q]; w += sg.b; break; }
-      case FS_VARINT: w += put_varint(w, val[sg.a]); break;
-      case FS_BE32: { const uint64_t m = val[sg.a]; w[0] = (uint8_t)(m >> 24); w[1] = (uint8_t)(m >> 16); w[2] = (uint8_t)(m >> 8); w[3] = (uint8_t)m; w += 4; break; }
-      case FS_ITEM: ft.items[sg.a].dst = w; w += ft.items[sg.a].n_out; break;
-      case FS_SMALL: ft.smalls[sg.a].dst = w; w += ft.smalls[sg.a].n_out; break;
-      default: { const uint64_t L = *ft.jobs[sg.a].total; ft.jobs[sg.a].dst = w; ft.jobs[sg.a].cap = L; w += L; break; }
-    }
-  }
+  if (r < ft.n) frame_request(ft, r);     // frame.h: the same code runs on the host under tests/
 }
 
 cudaError_t launch_frame_requests(const FrameTables& ft, cudaStream_t stream) {

@@ -118,6 +118,9 @@ SIGNATURES = {
     "b200tfs_measure": (C.c_int, [_vp, C.c_int32, C.POINTER(Tensor)]),
     "b200tfs_encode_tensor_protos": (C.c_int, [_vp, C.c_int32, C.POINTER(Tensor), _vp, C.c_uint64, _u64p, _u64p]),
     "b200tfs_encode_requests": (C.c_int, [_vp, C.c_int32, C.POINTER(Request), _vp, C.c_uint64, _u64p, _u64p]),
+    "b200tfs_encode_requests_async": (C.c_int, [_vp, C.c_int32, C.POINTER(Request), _vp, C.c_uint64]),
+    "b200tfs_encode_results": (C.c_int, [_vp, C.c_int32, _u64p, _u64p]),
+    "b200tfs_request_frame_deferred": (C.c_int, [C.POINTER(Request), _u64p, _vp, C.c_uint64, _u64p, _u64p, _u64p, _u64p]),
     "b200tfs_parse_responses": (C.c_int, [_vp, _vp, C.c_int32, _u64p, _u64p, C.c_int32, C.POINTER(Output), _i32p,
                                           C.POINTER(ModelSpec), _i32p]),
     "b200tfs_parse_tensor_protos": (C.c_int, [_vp, _vp, C.c_int32, _u64p, _u64p, C.POINTER(Output), _i32p]),

@@ -738,3 +738,90 @@ def test_scratch_buffers_are_pinned_once_a_graph_exists(dev):
     N.check(dev.lib.b200tfs_decode_responses(dev.ctx, arena, 1, off, ln, dst, 1 << 15))
     dev.sync()
     dev.lib.b200tfs_graph_destroy(g)
+
+
+def _requests_on_device(dev, batch, grpc=False):
+    """request structs over uploaded tensors, packed_len left at 0 (nothing measured)"""
+    keep, reqs, ptrs = [], [], []
+    for model, version, inputs in batch:
+        ts = []
+        for k, a in inputs:
+            p = dev.upload(a)
+            ptrs.append((p, a))
+            t, dims = tensor_struct(p, a, key=k.encode())
+            keep.append((t, dims))
+            ts.append(t)
+        arr = (N.Tensor * max(len(ts), 1))(*ts)
+        keep.append(arr)
+        name = model.encode()
+        reqs.append(N.Request(model_name=name, model_name_len=len(name), has_version=int(version is not None), order=N.ORDER_UPB,
+                              version=version or 0, n_inputs=len(ts), flags=N.RF_GRPC_FRAME if grpc else 0, inputs=arr))
+    return (N.Request * len(reqs))(*reqs), keep, ptrs
+
+
+def test_deferred_encode_no_host_round_trip(dev):
+    """b200tfs_encode_requests_async: packed-varint inputs are measured, framed and emitted by kernels alone (count -> frame ->
+    move + emit), bit-exact against the oracle; the whole call is captured in a CUDA graph and the replay re-measures: new label
+    values of other varint lengths give other record lengths, again bit-exact."""
+    rng = np.random.default_rng(31)
+    def batch_for(scale):
+        out = []
+        for i in range(9):
+            img = rng.standard_normal((3, 16, 16)).astype(np.float32)
+            img.reshape(-1)[:2] = np.array([0x7F800001, 0xFF800001], dtype=np.uint32).view(np.float32)
+            label = np.array([[(i * 37) % 1000 * scale]], dtype=np.int64)
+            toks = (rng.integers(0, 50000, size=(2, 40 + i)) * scale - (i % 3)).astype(np.int32)      # some negatives: ten-byte varints
+            out.append(("default", 1 if i % 2 else None, [("image", img), ("label", label), ("tokens", toks), ("mask", toks > 100),
+                                                           ("empty", np.zeros((0, 4), np.int64))]))
+        out.append(("m", 3, [("big", (rng.integers(0, 2 ** 62, size=70000, dtype=np.int64) >> rng.integers(0, 62, size=70000)))]))
+        out.append(("", None, []))
+        return out
+    batch = batch_for(1)
+    for grpc in (False, True):
+        rq, keep, ptrs = _requests_on_device(dev, batch, grpc)
+        n = len(batch)
+        need = C.c_uint64()
+        N.check(dev.lib.b200tfs_request_arena_size(n, rq, C.byref(need)))
+        arena = dev.malloc(need.value)
+        N.check(dev.lib.b200tfs_memset(dev.ctx, arena, 0xCD, need.value))
+        N.check(dev.lib.b200tfs_encode_requests_async(dev.ctx, n, rq, arena, need.value))
+        off, ln = (C.c_uint64 * n)(), (C.c_uint64 * n)()
+        N.check(dev.lib.b200tfs_encode_results(dev.ctx, n, off, ln))
+        whole = dev.download(arena, need.value)
+        for i, (model, version, inputs) in enumerate(batch):
+            want = wire_oracle.encode_predict_request(model, version, inputs)
+            if grpc:
+                want = b"\x00" + len(want).to_bytes(4, "big") + want
+            assert whole[off[i]: off[i] + ln[i]].tobytes() == want, (i, grpc)
+            assert i == 0 or off[i] >= off[i - 1] + ln[i - 1]
+    # captured: the same call as a graph; then other VALUES in the same buffers (other varint lengths) and a replay
+    rq, keep, ptrs = _requests_on_device(dev, batch)
+    n = len(batch)
+    N.check(dev.lib.b200tfs_request_arena_size(n, rq, C.byref(need)))
+    arena = dev.malloc(need.value)
+    N.check(dev.lib.b200tfs_encode_requests_async(dev.ctx, n, rq, arena, need.value))     # sizes the scratch buffers
+    dev.sync()
+    N.check(dev.lib.b200tfs_capture_begin(dev.ctx))
+    N.check(dev.lib.b200tfs_encode_requests_async(dev.ctx, n, rq, arena, need.value))
+    g = C.c_void_p()
+    N.check(dev.lib.b200tfs_capture_end(dev.ctx, C.byref(g)))
+    batch2 = batch_for(977)
+    k = 0
+    for model, version, inputs in batch2:
+        for key, a in inputs:
+            p, old = ptrs[k]
+            k += 1
+            assert old.shape == a.shape and old.dtype == a.dtype
+            if a.nbytes:
+                N.check(dev.lib.b200tfs_memcpy_h2d(dev.ctx, p, np.ascontiguousarray(a).ctypes.data, a.nbytes))
+    dev.sync()
+    N.check(dev.lib.b200tfs_graph_launch(dev.ctx, g))
+    off, ln = (C.c_uint64 * n)(), (C.c_uint64 * n)()
+    N.check(dev.lib.b200tfs_encode_results(dev.ctx, n, off, ln))
+    whole = dev.download(arena, need.value)
+    lens1 = [len(wire_oracle.encode_predict_request(m, v, i)) for m, v, i in batch]
+    for i, (model, version, inputs) in enumerate(batch2):
+        want = wire_oracle.encode_predict_request(model, version, inputs)
+        assert whole[off[i]: off[i] + ln[i]].tobytes() == want, i
+    assert [int(x) for x in ln] != lens1            # the replay really produced other lengths
+    dev.lib.b200tfs_graph_destroy(g)
