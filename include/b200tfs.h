@@ -19,8 +19,8 @@
  * the thread-local message.  Nothing here ever falls back to a CPU codec: without a CUDA device
  * b200tfs_create() fails with B200TFS_E_CUDA and every codec entry point needs a context.
  *
- * Threading: a b200tfs_ctx owns one CUDA stream plus pinned/device scratch and is NOT re-entrant;
- * use one context per calling thread (contexts are cheap).  Distinct contexts are independent.
+ * Threading: a b200tfs_ctx owns pinned/device scratch plus a CUDA stream (or borrows the caller's: b200tfs_set_stream) and is
+ * NOT re-entrant; use one context per calling thread (contexts are cheap).  Distinct contexts are independent.
  */
 #ifndef B200TFS_H_
 #define B200TFS_H_
@@ -207,6 +207,10 @@ int b200tfs_create(int device, b200tfs_ctx** out);
 int b200tfs_destroy(b200tfs_ctx* ctx);
 int b200tfs_sync(b200tfs_ctx* ctx);
 void* b200tfs_stream(b200tfs_ctx* ctx); /* the cudaStream_t every call on this context is ordered on */
+/* Order every LATER call of this context on the caller's stream (a cudaStream_t of the context's device; NULL: back to the
+ * context's own stream).  Work already queued is ordered ahead of it by an event edge - nothing synchronises.  The stream
+ * stays the caller's: it must outlive its use here and is not destroyed with the context.  Not during graph capture.     */
+int b200tfs_set_stream(b200tfs_ctx* ctx, void* stream);
 int b200tfs_kernel_launches(b200tfs_ctx* ctx, uint64_t* count); /* kernels launched so far on this context */
 
 /* ---- memory + timing helpers so a ctypes host needs nothing but this library ------------------- */

@@ -79,7 +79,8 @@ struct MeasuredTensor {     // what b200tfs_measure learnt about one varint tens
 struct b200tfs_ctx {
   int device = 0;
   int sm_count = 148;
-  cudaStream_t stream = nullptr;
+  cudaStream_t stream = nullptr;       // the stream every call is ordered on: the context's own, or the caller's (b200tfs_set_stream)
+  cudaStream_t own_stream = nullptr;
   Slot slots[kSlots];
   int next_slot = 0;
   Growable scratch_dev;   // parse tables / varint tile tables
@@ -207,8 +208,9 @@ int b200tfs_create(int device, b200tfs_ctx** out) {
   c->device = device;
   cudaDeviceProp prop;
   if (cudaGetDeviceProperties(&prop, device) == cudaSuccess) c->sm_count = prop.multiProcessorCount;
-  e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking);
+  e = cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking);
   if (e != cudaSuccess) { delete c; return fail(B200TFS_E_CUDA, "cudaStreamCreate: %s", cudaGetErrorString(e)); }
+  c->stream = c->own_stream;
   for (auto& s : c->slots) {
     e = cudaEventCreateWithFlags(&s.done, cudaEventDisableTiming);
     if (e != cudaSuccess) { delete c; return fail(B200TFS_E_CUDA, "cudaEventCreate: %s", cudaGetErrorString(e)); }
@@ -229,6 +231,7 @@ int b200tfs_destroy(b200tfs_ctx* c) {
   if (!c) return B200TFS_OK;
   cudaSetDevice(c->device);
   cudaStreamSynchronize(c->stream);
+  if (c->stream != c->own_stream) cudaStreamSynchronize(c->own_stream);
   for (auto& s : c->slots) {
     if (s.host.p) cudaFreeHost(s.host.p);
     if (s.dev.p) cudaFree(s.dev.p);
@@ -248,8 +251,26 @@ int b200tfs_destroy(b200tfs_ctx* c) {
   if (c->scratch_host.p) cudaFreeHost(c->scratch_host.p);
   if (c->stage_dev.p) cudaFree(c->stage_dev.p);
   if (c->arena_dev.p) cudaFree(c->arena_dev.p);
-  cudaStreamDestroy(c->stream);
+  cudaStreamDestroy(c->own_stream);
   delete c;
+  return B200TFS_OK;
+}
+
+int b200tfs_set_stream(b200tfs_ctx* c, void* stream) {
+  if (!c) return fail(B200TFS_E_ARG, "ctx is NULL");
+  if (c->capturing) return fail(B200TFS_E_ARG, "cannot change streams during graph capture");
+  cudaStream_t next = stream ? (cudaStream_t)stream : c->own_stream;
+  if (next == c->stream) return B200TFS_OK;
+  CU(cudaSetDevice(c->device));
+  // work already queued on the old stream (plan uploads, kernels reading the scratch buffers) must be visible to the new one:
+  // an event edge, not a host synchronise
+  cudaEvent_t e;
+  CU(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+  cudaError_t rc = cudaEventRecord(e, c->stream);
+  if (rc == cudaSuccess) rc = cudaStreamWaitEvent(next, e, 0);
+  cudaEventDestroy(e);
+  if (rc != cudaSuccess) return fail(B200TFS_E_CUDA, "switching streams: %s", cudaGetErrorString(rc));
+  c->stream = next;
   return B200TFS_OK;
 }
 

@@ -1043,14 +1043,49 @@ __global__ void __launch_bounds__(kMoveThreads, 3) decode_fused_staged_kernel(co
 // totals the counting kernel just produced, places the record in its slot (largest payload 128-byte aligned, like the host
 // planner's place_record), writes every framing byte and patches the destinations of the payload movers behind it.
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(64) frame_requests_kernel(const __grid_constant__ FrameTables ft) {
-  const uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
-  if (r < ft.n) frame_request(ft, r);     // frame.h: the same code runs on the host under tests/
+constexpr uint32_t kFrameWarps = 4;                 // requests per CTA (one warp each)
+constexpr uint32_t kFrameSegs = 64, kFrameVals = 32, kFrameTerms = 64, kFrameBlob = 1024;   // what a warp stages in shared memory
+struct FrameStage {
+  FrameSeg segs[kFrameSegs];
+  FrameVal vals[kFrameVals];
+  FrameTerm terms[kFrameTerms];
+  uint64_t term_total[kFrameTerms];
+  uint64_t val[kFrameVals];
+  uint8_t blob[kFrameBlob];
+};
+
+__global__ void __launch_bounds__(32 * kFrameWarps) frame_requests_kernel(const __grid_constant__ FrameTables ft) {
+  __shared__ FrameStage stage[kFrameWarps];
+  const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t r = blockIdx.x * kFrameWarps + warp;
+  if (r >= ft.n) return;
+  const FrameReq rq = ft.reqs[r];                                   // round 1 (every lane: one broadcast load)
+  if (rq.n_seg > kFrameSegs || rq.n_val > kFrameVals || rq.n_term > kFrameTerms || rq.n_blob > kFrameBlob) {
+    if (lane == 0) frame_request(ft, r);                            // an unusually large request: walk the tables in place
+    return;
+  }
+  FrameStage& S = stage[warp];
+  for (uint32_t k = lane; k < rq.n_seg; k += 32) S.segs[k] = ft.segs[rq.first_seg + k];     // round 2: all independent
+  for (uint32_t k = lane; k < rq.n_val; k += 32) S.vals[k] = ft.vals[rq.first_val + k];
+  for (uint32_t k = lane; k < rq.n_term; k += 32) {
+    const FrameTerm t = ft.terms[rq.first_term + k];
+    S.terms[k] = t;
+    S.term_total[k] = 0;
+  }
+  for (uint32_t k = lane; k < rq.n_blob; k += 32) S.blob[k] = ft.blob[rq.first_blob + k];
+  __syncwarp();
+  for (uint32_t k = lane; k < rq.n_term; k += 32)                                            // round 3: the job totals
+    if (S.terms[k].kind == FT_TOTAL) S.term_total[k] = (uint64_t)ft.totals[S.terms[k].idx];
+  __syncwarp();
+  if (lane == 0) {
+    FrameView V{S.segs, S.vals, S.terms, S.term_total, S.blob, S.val};
+    frame_request_run(ft, rq, V, r);
+  }
 }
 
 cudaError_t launch_frame_requests(const FrameTables& ft, cudaStream_t stream) {
   if (!ft.n) return cudaSuccess;
-  frame_requests_kernel<<<(ft.n + 63) / 64, 64, 0, stream>>>(ft);
+  frame_requests_kernel<<<(ft.n + kFrameWarps - 1) / kFrameWarps, 32 * kFrameWarps, 0, stream>>>(ft);
   return cudaGetLastError();
 }
 

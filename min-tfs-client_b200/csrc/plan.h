@@ -169,9 +169,9 @@ enum FrameSegKind : uint32_t {
   FS_BYTES = 0,   // a = offset into the frame blob, b = byte count
   FS_VARINT = 1,  // a = value id (request-local): varint(value)
   FS_BE32 = 2,    // a = value id: four bytes, big endian (gRPC's message length)
-  FS_ITEM = 3,    // a = MoveItem index: its n_out bytes land here (dst patched)
-  FS_SMALL = 4,   // a = SmallItem index: likewise
-  FS_VARJOB = 5   // a = varint job index: total[job] bytes land here (dst and cap patched)
+  FS_ITEM = 3,    // a = MoveItem index, b = its byte count: the payload lands here (dst patched)
+  FS_SMALL = 4,   // a = SmallItem index, b = its byte count: likewise
+  FS_VARJOB = 5   // a = varint job index, b = value id of its packed length: the varints land here (dst and cap patched)
 };
 struct FrameSeg { uint32_t kind, a, b, pad; };
 enum FrameTermKind : uint32_t { FT_TOTAL = 0, FT_VAL = 1, FT_VLEN = 2 };   // + total[job], + value[i], + varint_len(value[i])
@@ -179,13 +179,16 @@ struct FrameTerm { uint32_t kind, idx; };
 struct FrameVal { int64_t c; uint32_t first_term, n_terms; };               // evaluated in order: terms refer to earlier values only
 struct FrameReq {
   uint32_t first_seg, n_seg, first_val, n_val;
+  uint32_t first_term, n_term, first_blob, n_blob;
   uint32_t align_seg;       // the payload segment that should start 128-byte aligned (index relative to first_seg), ~0u: none
   uint32_t total_val;       // value id of the record's byte length (incl. a gRPC prefix)
   uint64_t slot_off, slot_cap;   // where the record may lie inside the arena (worst-case sized by the host)
 };
 struct FrameTables {
   const FrameReq* reqs; const FrameSeg* segs; const FrameVal* vals; const FrameTerm* terms; const uint8_t* blob;
+  const unsigned long long* totals;   // packed length of every varint job (the counting kernel's result), by job index
   uint64_t* scratch_vals;   // one evaluated value per FrameVal
+  uint64_t* scratch_terms;  // one fetched total per FrameTerm (used by the table-walking path)
   uint8_t* arena;
   MoveItem* items; SmallItem* smalls; VarJobDev* jobs;    // patched
   uint64_t* rec_off; uint64_t* rec_len; int32_t* status;  // pinned host memory: read by b200tfs_encode_results

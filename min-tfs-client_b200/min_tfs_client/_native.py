@@ -91,6 +91,7 @@ SIGNATURES = {
     "b200tfs_destroy": (C.c_int, [_vp]),
     "b200tfs_sync": (C.c_int, [_vp]),
     "b200tfs_stream": (C.c_void_p, [_vp]),
+    "b200tfs_set_stream": (C.c_int, [_vp, _vp]),
     "b200tfs_kernel_launches": (C.c_int, [_vp, _u64p]),
     "b200tfs_malloc": (C.c_int, [_vp, C.c_uint64, _vpp]),
     "b200tfs_free": (C.c_int, [_vp, _vp]),

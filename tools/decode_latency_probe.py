@@ -31,6 +31,14 @@ VARIANTS = [
 
 
 def main():
+    if "--one" in sys.argv:       # in-process, default switches: the thing to run under ncu
+        sys.path[:0] = [os.path.join(REPO, "min-tfs-client_b200"), REPO]
+        import bench
+
+        class W:
+            local_rank = 0
+        print(json.dumps(bench.c2_single_request_latency(W())))
+        return
     rows = {}
     for name, env in VARIANTS:
         e = dict(os.environ, **env)
