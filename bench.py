@@ -922,6 +922,17 @@ def c2_single_request_latency(world):
     offs = [(C.c_uint64 * 1)(j * db.resp_stride + db.resp_shift) for j in range(n)]
     lens = (C.c_uint64 * 1)(db.resp_len)
 
+    if os.environ.get("B200TFS_BENCH_SEED_TEMPLATE") == "1":
+        # experiments with a build whose kernels cannot walk (tools/decode_latency_probe.py): one host-buffer decode of response 0
+        # first - the library walks it on the host and leaves the template for the device-wire launches that follow
+        seed = wl.seed_of(0)
+        rk, rx = db.host_resp[seed]
+        hw = N.PinnedBuffer(db.resp_len)
+        hw.array[:] = np.frombuffer(db.resp_prefix + rx.tobytes() + db.resp_suffix, np.uint8)
+        ho = N.PinnedBuffer(db.dst_stride)
+        N.check(lib.b200tfs_decode_responses_host_async(db.ctx, hw.ptr, 1, (C.c_uint64 * 1)(0), lens, ho.ptr, db.dst_stride))
+        db.sync()
+
     def enc(j):
         N.check(lib.b200tfs_encode_requests(db.ctx, 1, one_req[j], arenas[j], one_cap, ro, rl))
 

@@ -81,6 +81,7 @@ struct b200tfs_ctx {
   int sm_count = 148;
   cudaStream_t stream = nullptr;       // the stream every call is ordered on: the context's own, or the caller's (b200tfs_set_stream)
   cudaStream_t own_stream = nullptr;
+  cudaStream_t aux_stream = nullptr;   // uploads done at capture time, outside the graph being recorded
   Slot slots[kSlots];
   int next_slot = 0;
   Growable scratch_dev;   // parse tables / varint tile tables
@@ -182,6 +183,21 @@ static int claim_slot(b200tfs_ctx* c, uint64_t bytes, Slot** out) {
   return B200TFS_OK;
 }
 
+// Bring a slot's pinned image to its device image.  While a graph is being captured the slot is private to that graph and its
+// image never changes (plans, tables and framing programs are functions of the call's arguments, which a graph freezes
+// anyway): it is copied NOW, on a side stream, instead of being recorded as a copy node that every replay would repeat
+// (2-3 us of stream time per node; a captured C3 encode had three of them).
+static int upload_slot(b200tfs_ctx* c, Slot* slot, uint64_t bytes) {
+  if (c->capturing) {
+    CU(cudaMemcpyAsync(slot->dev.p, slot->host.p, bytes, cudaMemcpyHostToDevice, c->aux_stream));
+    CU(cudaStreamSynchronize(c->aux_stream));
+    return B200TFS_OK;
+  }
+  CU(cudaMemcpyAsync(slot->dev.p, slot->host.p, bytes, cudaMemcpyHostToDevice, c->stream));
+  if (slot->done) { CU(cudaEventRecord(slot->done, c->stream)); slot->pending = true; }
+  return B200TFS_OK;
+}
+
 extern "C" {
 
 int b200tfs_abi_version(void) { return B200TFS_ABI_VERSION; }
@@ -211,6 +227,8 @@ int b200tfs_create(int device, b200tfs_ctx** out) {
   e = cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking);
   if (e != cudaSuccess) { delete c; return fail(B200TFS_E_CUDA, "cudaStreamCreate: %s", cudaGetErrorString(e)); }
   c->stream = c->own_stream;
+  e = cudaStreamCreateWithFlags(&c->aux_stream, cudaStreamNonBlocking);
+  if (e != cudaSuccess) { delete c; return fail(B200TFS_E_CUDA, "cudaStreamCreate: %s", cudaGetErrorString(e)); }
   for (auto& s : c->slots) {
     e = cudaEventCreateWithFlags(&s.done, cudaEventDisableTiming);
     if (e != cudaSuccess) { delete c; return fail(B200TFS_E_CUDA, "cudaEventCreate: %s", cudaGetErrorString(e)); }
@@ -252,6 +270,7 @@ int b200tfs_destroy(b200tfs_ctx* c) {
   if (c->stage_dev.p) cudaFree(c->stage_dev.p);
   if (c->arena_dev.p) cudaFree(c->arena_dev.p);
   cudaStreamDestroy(c->own_stream);
+  if (c->aux_stream) cudaStreamDestroy(c->aux_stream);
   delete c;
   return B200TFS_OK;
 }
@@ -586,7 +605,8 @@ int build_plan(b200tfs_ctx* c, PlanBuilder& pb, bool force_dev, BuiltPlan* bp) {
   }
   if (!pb.blob.empty()) memcpy(img + off_blob, pb.blob.data(), pb.blob.size());
   if (!inl) {
-    CU(cudaMemcpyAsync(bp->slot->dev.p, img, image, cudaMemcpyHostToDevice, c->stream));
+    int rc = upload_slot(c, bp->slot, image);
+    if (rc) return rc;
     bp->plan_dev = (uint8_t*)bp->slot->dev.p;
   }
   return B200TFS_OK;
@@ -595,7 +615,7 @@ int build_plan(b200tfs_ctx* c, PlanBuilder& pb, bool force_dev, BuiltPlan* bp) {
 int launch_built_plan(b200tfs_ctx* c, BuiltPlan& bp) {
   CU(launch_move(bp.plan_dev, bp.host_img, (uint32_t)bp.image, bp.ph.n_tiles, bp.ph.n_small, c->stream));
   c->launches += 1;
-  if (bp.slot && bp.slot->done) { CU(cudaEventRecord(bp.slot->done, c->stream)); bp.slot->pending = true; }
+  if (bp.slot && bp.slot->done && !c->capturing) { CU(cudaEventRecord(bp.slot->done, c->stream)); bp.slot->pending = true; }   // the kernel still reads the image
   return B200TFS_OK;
 }
 
@@ -1263,6 +1283,7 @@ static int decode_launch(b200tfs_ctx* c, const void* arena_dev, int32_t n, const
   fp.stats = (unsigned long long*)((uint8_t*)c->tpl_dev + 2 * sizeof(Template));
   if (++c->serial == 0) c->serial = 1;
   fp.serial = c->serial;
+  { static const uint32_t exp = [] { const char* e = getenv("B200TFS_EXP"); return e ? (uint32_t)atoi(e) : 0u; }(); fp.experiment = exp; }
   fp.tpli.head.valid = 0;
   if (vpt <= kStageVecsHost) {   // the single-response / small-batch kernel takes its template from the parameters when the host has one
     if (host_tpl && host_tpl->in.head.valid) {
@@ -1314,8 +1335,7 @@ static int decode_launch(b200tfs_ctx* c, const void* arena_dev, int32_t n, const
     memcpy(h + o_ts, ts.data(), 4ull * (n + 1));
     memcpy(h + o_off, rec_off, 8ull * n);
     memcpy(h + o_len, rec_len, 8ull * n);
-    CU(cudaMemcpyAsync(slot->dev.p, h, image, cudaMemcpyHostToDevice, c->stream));
-    if (slot->done) { CU(cudaEventRecord(slot->done, c->stream)); slot->pending = true; }
+    if ((rc = upload_slot(c, slot, image))) return rc;
     uint8_t* sd = (uint8_t*)slot->dev.p;
     fp.cta_rec = (const uint32_t*)sd; fp.tile_start = (const uint32_t*)(sd + o_ts);
     fp.rec_off = (const uint64_t*)(sd + o_off); fp.rec_len = (const uint64_t*)(sd + o_len);

@@ -974,6 +974,7 @@ __device__ __forceinline__ void decode_fused_body(const FusedParams& fp) {
       // CTAs of a 602 KB record are slack: leave now, before the verdict's round trip.  Should the record fail the
       // verdict after all, the CTAs that stayed walk it; if it then needs more tiles than stayed, its status says so.
       if (mine == kTplChunks && j != 0 && j != budget - 1) return;
+      if (fp.experiment == 2 && mine == kTplChunks) return;     // experiment: no publisher at all
       live = max(th_s.total_tiles, 1u);
       bool hit;
       if (STAGED) {
@@ -998,7 +999,7 @@ __device__ __forceinline__ void decode_fused_body(const FusedParams& fp) {
                           ch_s[mine].n_tiles, j - t_base, fp.vpt, verdict);
       } else hit = verdict();
       if (hit) {
-        if (j == budget - 1) {   // the record's last CTA - a slack CTA with no tile - publishes the table, so no tile waits on it
+        if (j == budget - 1 && fp.experiment != 1) {   // the record's last CTA - a slack CTA with no tile - publishes the table, so no tile waits on it
           // the table entries live in the device template; an inline template vouches for them only if both carry the same serial
           const bool table_ok = !inl || (T->in.head.valid && T->in.head.serial == th_s.serial);
           if (table_ok) {
@@ -1011,7 +1012,9 @@ __device__ __forceinline__ void decode_fused_body(const FusedParams& fp) {
             if (r == 0 && !(fp.tpl_write->in.head.valid && fp.tpl_write->in.head.serial == T->in.head.serial))
               publish_words(fp.tpl_write, T, (uint32_t)sizeof(Template));
           } else if (threadIdx.x == 0) {
+#ifndef B200TFS_EXPERIMENT_NO_WALK
             fused_slow_path(fp, r, 0, budget, true, rec, len, dst_slot, lines, outs_s, spec_s, job);   // walk for the table only
+#endif
           }
         }
         return;
@@ -1020,7 +1023,12 @@ __device__ __forceinline__ void decode_fused_body(const FusedParams& fp) {
   }
 
   // ---- the walk: thread 0 goes through the tags ----
+#ifdef B200TFS_EXPERIMENT_NO_WALK   // code-size experiment (tools/decode_latency_probe.py): a record that misses the template is refused
+  if (threadIdx.x == 0) { job.valid = 0; if (j == 0) { fp.status[r] = B200TFS_E_NONCANONICAL; fp.n_outs[r] = 0; } }
+  (void)live;
+#else
   if (threadIdx.x == 0) fused_slow_path(fp, r, j, live, j == 0, rec, len, dst_slot, lines, outs_s, spec_s, job);
+#endif
   __syncthreads();
   if (job.valid) {
     if (job.gstride) move_tile_gather(SrcView{job.src, job.glen, job.gstride}, job.dst, job.n_out, job.op, job.n_tiles, job.tile, fp.vpt);

@@ -107,7 +107,7 @@ struct FusedParams {
   TplInline* tpl_pinned;     // pinned host copy of the inline part, written whenever a template is learnt (valid flag last)
   unsigned long long* stats; // device counters: records served by [0] the template in the parameters, [1] the device template, [2] the walk
   uint32_t serial;           // stamp for a template learnt by THIS launch
-  uint32_t pad;
+  uint32_t experiment;       // timing experiments only (B200TFS_EXP): 1 = the record's last CTA skips publishing the table on a template hit
   FusedInline inl;
   TplInline tpli;            // head.valid != 0: the template as the host knows it (tier 1; tpl_read is tier 2, the walk tier 3)
 };

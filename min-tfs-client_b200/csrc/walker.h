@@ -37,7 +37,9 @@ struct Cursor {
 };
 
 #if defined(__CUDACC__)
-__device__ __forceinline__ void cur_fill(Cursor& c, uint32_t slot, uint32_t line) {
+// out of line: a miss is rare (two per canonical response) and its sixteen vector accesses, inlined at every one of the walk's
+// ~100 byte reads, were most of the walk's 230 KB of SASS
+__device__ __noinline__ void cur_fill(Cursor& c, uint32_t slot, uint32_t line) {
   const uint4* g = reinterpret_cast<const uint4*>(c.base + ((uint64_t)line << 7));
   uint4 t0 = g[0], t1 = g[1], t2 = g[2], t3 = g[3], t4 = g[4], t5 = g[5], t6 = g[6], t7 = g[7];
   uint4* s = reinterpret_cast<uint4*>(c.buf + 128 * slot);

@@ -13,7 +13,7 @@ import threading
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(os.path.dirname(_HERE), "lib", "libb200tfs.so")
+LIB_PATH = os.environ.get("B200TFS_LIB") or os.path.join(os.path.dirname(_HERE), "lib", "libb200tfs.so")   # B200TFS_LIB: experiment builds
 
 # ---- status codes (b200tfs.h) -----------------------------------------------------------------
 OK = 0

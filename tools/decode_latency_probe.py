@@ -25,8 +25,12 @@ VARIANTS = [
     ("no inline template", {"B200TFS_NO_INLINE_TEMPLATE": "1"}),
     ("table in device memory", {"B200TFS_TABLE_DEV": "1"}),
     ("table in device memory, no inline", {"B200TFS_TABLE_DEV": "1", "B200TFS_NO_INLINE_TEMPLATE": "1"}),
-    ("payload 16-byte aligned (response placed at +5)", {"B200TFS_BENCH_RESP_SHIFT": "5"}),
-    ("payload aligned, no inline", {"B200TFS_BENCH_RESP_SHIFT": "5", "B200TFS_NO_INLINE_TEMPLATE": "1"}),
+    ("16 KB tiles (272 CTAs)", {"B200TFS_TILE_BYTES": "16384"}),
+    ("8 KB tiles (544 CTAs)", {"B200TFS_TILE_BYTES": "8192"}),
+    ("64 KB tiles (72 CTAs)", {"B200TFS_TILE_BYTES": "65536"}),
+    ("template seeded by a host walk (control for the next row)", {"B200TFS_BENCH_SEED_TEMPLATE": "1"}),
+    ("kernels built WITHOUT the tag walk (decode_fused_kernel 51 KB instead of 315 KB of SASS)",
+     {"B200TFS_BENCH_SEED_TEMPLATE": "1", "B200TFS_LIB": os.path.join(REPO, "min-tfs-client_b200", "lib", "libb200tfs_nowalk.so")}),
 ]
 
 
