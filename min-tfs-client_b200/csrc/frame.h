@@ -20,13 +20,27 @@ struct FrameView {
   uint64_t* val;               // rq.n_val evaluated values (scratch)
 };
 
+// element e of a tiny packed-varint input, widened to 64 bits the way the protobuf runtime widens it (sign-extended if signed)
+B2_HD uint64_t tiny_elem(const TinyVar& t, uint32_t e) {
+  const uint8_t* p = t.src + (uint64_t)e * t.elem_size;
+  uint64_t v = 0;
+  for (uint32_t b = 0; b < t.elem_size; ++b) v |= (uint64_t)p[b] << (8 * b);
+  if (t.is_signed && t.elem_size < 8 && (v >> (8 * t.elem_size - 1)) & 1) v |= ~0ull << (8 * t.elem_size);
+  return v;
+}
+B2_HD uint64_t tiny_total(const TinyVar& t) {
+  uint64_t s = 0;
+  for (uint32_t e = 0; e < t.n; ++e) s += varint_len(tiny_elem(t, e));
+  return s;
+}
+
 B2_HD uint64_t frame_seg_len(const FrameSeg& sg, const uint64_t* val) {
   switch (sg.kind) {
     case FS_BYTES: return sg.b;
     case FS_VARINT: return varint_len(val[sg.a]);
     case FS_BE32: return 4;
     case FS_ITEM: case FS_SMALL: return sg.b;      // the host wrote the payload's length next to its index
-    default: return val[sg.b];                     // FS_VARJOB: b = the value that is its packed length
+    default: return val[sg.b];                     // FS_VARJOB / FS_TINYVAR: b = the value that is its packed length
   }
 }
 
@@ -38,7 +52,7 @@ B2_HD void frame_request_run(const FrameTables& ft, const FrameReq& rq, const Fr
     for (uint32_t k = 0; k < fv.n_terms; ++k) {
       const uint32_t ti = fv.first_term - rq.first_term + k;
       const FrameTerm t = V.terms[ti];
-      if (t.kind == FT_TOTAL) x += V.term_total[ti];
+      if (t.kind == FT_TOTAL || t.kind == FT_TINY) x += V.term_total[ti];
       else if (t.kind == FT_VAL) x += val[t.idx];
       else x += varint_len(val[t.idx]);
     }
@@ -59,7 +73,7 @@ B2_HD void frame_request_run(const FrameTables& ft, const FrameReq& rq, const Fr
       const FrameSeg sg = V.segs[k];
       if (sg.kind == FS_ITEM) ft.items[sg.a].n_out = 0;
       else if (sg.kind == FS_SMALL) ft.smalls[sg.a].n_out = 0;
-      else if (sg.kind == FS_VARJOB) { ft.jobs[sg.a].dst = ft.arena + rq.slot_off; ft.jobs[sg.a].cap = 0; }
+      else if (sg.kind == FS_VARJOB) { ft.jobs[sg.a].dst = ft.arena + rq.slot_off; ft.jobs[sg.a].cap = 0; }   // (FS_TINYVAR: nothing runs behind it)
     }
     return;
   }
@@ -73,6 +87,7 @@ B2_HD void frame_request_run(const FrameTables& ft, const FrameReq& rq, const Fr
       case FS_BE32: { const uint64_t m = val[sg.a]; w[0] = (uint8_t)(m >> 24); w[1] = (uint8_t)(m >> 16); w[2] = (uint8_t)(m >> 8); w[3] = (uint8_t)m; w += 4; break; }
       case FS_ITEM: ft.items[sg.a].dst = w; w += sg.b; break;
       case FS_SMALL: ft.smalls[sg.a].dst = w; w += sg.b; break;
+      case FS_TINYVAR: { const TinyVar t = ft.tiny[sg.a]; for (uint32_t e = 0; e < t.n; ++e) w += put_varint(w, tiny_elem(t, e)); break; }
       default: { const uint64_t L = val[sg.b]; ft.jobs[sg.a].dst = w; ft.jobs[sg.a].cap = L; w += L; break; }
     }
   }
@@ -85,7 +100,7 @@ B2_HD void frame_request(const FrameTables& ft, uint32_t r) {
   uint64_t* tt = ft.scratch_terms + rq.first_term;
   for (uint32_t t = 0; t < rq.n_term; ++t) {
     const FrameTerm ft_t = ft.terms[rq.first_term + t];
-    tt[t] = ft_t.kind == FT_TOTAL ? (uint64_t)ft.totals[ft_t.idx] : 0;
+    tt[t] = ft_t.kind == FT_TOTAL ? (uint64_t)ft.totals[ft_t.idx] : ft_t.kind == FT_TINY ? tiny_total(ft.tiny[ft_t.idx]) : 0;
   }
   FrameView V{ft.segs + rq.first_seg, ft.vals + rq.first_val, ft.terms + rq.first_term, tt, ft.blob + rq.first_blob, ft.scratch_vals + rq.first_val};
   frame_request_run(ft, rq, V, r);

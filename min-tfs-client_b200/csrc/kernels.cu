@@ -1084,6 +1084,14 @@ __global__ void __launch_bounds__(32 * kFrameWarps) frame_requests_kernel(const 
   __syncwarp();
   for (uint32_t k = lane; k < rq.n_term; k += 32)                                            // round 3: the job totals
     if (S.terms[k].kind == FT_TOTAL) S.term_total[k] = (uint64_t)ft.totals[S.terms[k].idx];
+  for (uint32_t k = 0; k < rq.n_term; ++k)                                                   // ... and the tiny inputs: one element per lane
+    if (S.terms[k].kind == FT_TINY) {                                                        // (warp-uniform branch)
+      const TinyVar t = ft.tiny[S.terms[k].idx];
+      uint32_t len = lane < t.n ? varint_len(tiny_elem(t, lane)) : 0u;
+#pragma unroll
+      for (int d = 16; d; d >>= 1) len += __shfl_xor_sync(0xFFFFFFFFu, len, d);
+      if (lane == 0) S.term_total[k] = len;
+    }
   __syncwarp();
   if (lane == 0) {
     FrameView V{S.segs, S.vals, S.terms, S.term_total, S.blob, S.val};

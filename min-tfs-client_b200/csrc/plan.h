@@ -171,10 +171,15 @@ enum FrameSegKind : uint32_t {
   FS_BE32 = 2,    // a = value id: four bytes, big endian (gRPC's message length)
   FS_ITEM = 3,    // a = MoveItem index, b = its byte count: the payload lands here (dst patched)
   FS_SMALL = 4,   // a = SmallItem index, b = its byte count: likewise
-  FS_VARJOB = 5   // a = varint job index, b = value id of its packed length: the varints land here (dst and cap patched)
+  FS_VARJOB = 5,  // a = varint job index, b = value id of its packed length: the varints land here (dst and cap patched)
+  FS_TINYVAR = 6  // a = index into FrameTables::tiny, b = value id of its packed length: a packed-varint input of at most
+                  // kTinyVarElems elements (a label, an id, a few flags) is counted AND written by the framing kernel itself -
+                  // no counting kernel, no emit kernel, no counters to zero for it
 };
+constexpr uint32_t kTinyVarElems = 32;
+struct TinyVar { const uint8_t* src; uint32_t n, elem_size, is_signed, pad; };
 struct FrameSeg { uint32_t kind, a, b, pad; };
-enum FrameTermKind : uint32_t { FT_TOTAL = 0, FT_VAL = 1, FT_VLEN = 2 };   // + total[job], + value[i], + varint_len(value[i])
+enum FrameTermKind : uint32_t { FT_TOTAL = 0, FT_VAL = 1, FT_VLEN = 2, FT_TINY = 3 };   // + total[job], + value[i], + varint_len(value[i]), + packed length of tiny[idx]
 struct FrameTerm { uint32_t kind, idx; };
 struct FrameVal { int64_t c; uint32_t first_term, n_terms; };               // evaluated in order: terms refer to earlier values only
 struct FrameReq {
@@ -187,6 +192,7 @@ struct FrameReq {
 struct FrameTables {
   const FrameReq* reqs; const FrameSeg* segs; const FrameVal* vals; const FrameTerm* terms; const uint8_t* blob;
   const unsigned long long* totals;   // packed length of every varint job (the counting kernel's result), by job index
+  const TinyVar* tiny;                // FS_TINYVAR / FT_TINY
   uint64_t* scratch_vals;   // one evaluated value per FrameVal
   uint64_t* scratch_terms;  // one fetched total per FrameTerm (used by the table-walking path)
   uint8_t* arena;
