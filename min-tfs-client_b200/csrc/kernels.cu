@@ -1084,6 +1084,7 @@ __global__ void __launch_bounds__(32 * kFrameWarps) frame_requests_kernel(const 
   __syncwarp();
   for (uint32_t k = lane; k < rq.n_term; k += 32)                                            // round 3: the job totals
     if (S.terms[k].kind == FT_TOTAL) S.term_total[k] = (uint64_t)ft.totals[S.terms[k].idx];
+    else if (S.terms[k].kind == FT_TOTALF) S.term_total[k] = (uint64_t)ft.totals_fused[S.terms[k].idx];
   for (uint32_t k = 0; k < rq.n_term; ++k)                                                   // ... and the tiny inputs: one element per lane
     if (S.terms[k].kind == FT_TINY) {                                                        // (warp-uniform branch)
       const TinyVar t = ft.tiny[S.terms[k].idx];
@@ -1191,6 +1192,11 @@ cudaError_t launch_decode_fused(const FusedParams& fp, uint32_t grid, cudaStream
 cudaError_t launch_venc_len(const VarTables& tb, cudaStream_t stream) {
   if (!tb.n_tiles) return cudaSuccess;
   venc_len_kernel<<<tb.n_tiles, kVarThreads, 0, stream>>>(tb);
+  return cudaGetLastError();
+}
+cudaError_t launch_venc_fused(const VarTables& tb, const VarFuse& fz, cudaStream_t stream) {
+  if (!tb.n_tiles) return cudaSuccess;
+  venc_fused_kernel<<<tb.n_tiles, kVarThreads, 0, stream>>>(tb, fz);
   return cudaGetLastError();
 }
 cudaError_t launch_venc_emit(const VarTables& tb, cudaStream_t stream) {

@@ -175,18 +175,13 @@ __device__ __forceinline__ uint32_t spread28(uint32_t x) {
 // E2: emit.  Elements are loaded striped (coalesced) and transposed through shared memory (16-byte chunks
 // XOR-swizzled by row, so both sides are conflict-free) so that each thread owns kVarPerThread
 // consecutive elements; the staging image reuses the same shared memory.
-__global__ void __launch_bounds__(kVarThreads, 5) venc_emit_kernel(const __grid_constant__ VarTables tb) {
-  __shared__ __align__(16) uint8_t smem[kVarTileElems * 10 + 48];
-  __shared__ VarShared sh;
+constexpr uint32_t kVarImageBytes = kVarTileElems * 10 + 48;
+
+// the tile's elements, blocked: thread r owns elements [8r, 8r+8) of the tile; `lens` = their varint lengths, one nibble each
+// (elements past the end of the tensor: 0); returns the thread's byte count.  One barrier inside.
+__device__ __forceinline__ uint32_t venc_load_tile(uint8_t* smem, const VarSeg& sg, const VarJobDev& jb, uint64_t e0, uint32_t cnt,
+                                                   uint64_t (&mine)[kVarPerThread], uint32_t& lens) {
   uint64_t* vals = reinterpret_cast<uint64_t*>(smem);
-  const uint32_t t = blockIdx.x;
-  VarSeg sg;
-  VarJobDev jb;
-  fetch_tile(tb, t, sg, jb);
-  const uint32_t t_rel = t - jb.first_tile;
-  const uint64_t e0 = (uint64_t)(t - sg.first_tile) * kVarTileElems;
-  const uint32_t cnt = (uint32_t)min((uint64_t)kVarTileElems, sg.n - e0);
-  const uint64_t share = prefix_share(jb, t_rel);
   {
     uint64_t v[kVarPerThread];
     load_striped(sg.src, e0, cnt, jb.elem_size, jb.is_signed, v);
@@ -197,31 +192,27 @@ __global__ void __launch_bounds__(kVarThreads, 5) venc_emit_kernel(const __grid_
     }
   }
   __syncthreads();
-  uint64_t mine[kVarPerThread];
-  uint32_t lens = 0, sum = 0;                    // eight lengths, one nibble each
-  {
-    const uint32_t r = threadIdx.x;
+  const uint32_t r = threadIdx.x;
 #pragma unroll
-    for (uint32_t j = 0; j < kVarPerThread / 2; ++j) {
-      const uint4 q = *reinterpret_cast<const uint4*>(smem + r * 64 + (((j ^ (r >> 1)) & 3) << 4));
-      mine[2 * j] = (uint64_t)q.x | ((uint64_t)q.y << 32);
-      mine[2 * j + 1] = (uint64_t)q.z | ((uint64_t)q.w << 32);
-    }
-#pragma unroll
-    for (uint32_t i = 0; i < kVarPerThread; ++i) lens |= vlen64(mine[i]) << (4 * i);
-    // elements past the end of the tensor (last tile only) take no room
-    const uint32_t have = min(kVarPerThread, cnt - min(cnt, r * kVarPerThread));
-    lens &= __funnelshift_lc(0xFFFFFFFFu, 0u, 4u * have);
-    const uint32_t pairs = (lens & 0x0F0F0F0Fu) + ((lens >> 4) & 0x0F0F0F0Fu);
-    sum = (pairs * 0x01010101u) >> 24;
+  for (uint32_t j = 0; j < kVarPerThread / 2; ++j) {
+    const uint4 q = *reinterpret_cast<const uint4*>(smem + r * 64 + (((j ^ (r >> 1)) & 3) << 4));
+    mine[2 * j] = (uint64_t)q.x | ((uint64_t)q.y << 32);
+    mine[2 * j + 1] = (uint64_t)q.z | ((uint64_t)q.w << 32);
   }
-  uint32_t total;
-  uint64_t base;
-  uint32_t off = block_scan_sum(sum, &total, share, &base, sh);   // every thread has read `vals` before the first barrier inside
-  uint8_t* g = jb.dst + base;                  // first output byte of this tile
-  const uint32_t phase = (uint32_t)((uintptr_t)g & 15);
-  off += phase;
-  // ---- build the varints in registers, append 32-bit words ----
+  lens = 0;
+#pragma unroll
+  for (uint32_t i = 0; i < kVarPerThread; ++i) lens |= vlen64(mine[i]) << (4 * i);
+  // elements past the end of the tensor (last tile only) take no room
+  const uint32_t have = min(kVarPerThread, cnt - min(cnt, r * kVarPerThread));
+  lens &= __funnelshift_lc(0xFFFFFFFFu, 0u, 4u * have);
+  const uint32_t pairs = (lens & 0x0F0F0F0Fu) + ((lens >> 4) & 0x0F0F0F0Fu);
+  return (pairs * 0x01010101u) >> 24;
+}
+
+// build the thread's varints in registers and append them, whole 32-bit words at a time, to the shared-memory image at byte
+// offset `off`; two barriers inside (every thread must have read its elements out of `smem` before this is called: the
+// block scan between venc_load_tile and here has a barrier)
+__device__ __forceinline__ void venc_build_image(uint8_t* smem, const uint64_t (&mine)[kVarPerThread], uint32_t lens, uint32_t off) {
   const uint32_t f0 = off & 3;
   const uint32_t sbase = (uint32_t)__cvta_generic_to_shared(smem);
   const uint32_t sa0 = sbase + (off & ~3u);      // shared-window address of the word being filled
@@ -251,36 +242,36 @@ __global__ void __launch_bounds__(kVarThreads, 5) venc_emit_kernel(const __grid_
     }
   } else {
 #pragma unroll
-  for (uint32_t i = 0; i < kVarPerThread; ++i) {
-    const uint32_t lo = (uint32_t)mine[i], hi = (uint32_t)(mine[i] >> 32);
-    const uint32_t L = (lens >> (4 * i)) & 15u;
-    // continuation bits go into the first L-1 bytes: the low 8(L-1) bits of a mask, by a clamped funnel shift.  (An
-    // absent element - only at the end of the last tile - has L = 0: what it ORs into `acc` lies above byte f and is
-    // never stored, because no element follows it.)
-    const uint32_t s = 8u * L - 8u;
-    const uint32_t w0 = bitsel(0x7F7F7F7Fu, spread28(lo), __funnelshift_lc(0xFFFFFFFFu, 0u, s));
-    uint32_t w1 = 0, w2 = 0;
-    if (L > 4) {
-      w1 = bitsel(0x7F7F7F7Fu, spread28(__funnelshift_r(lo, hi, 28)), __funnelshift_lc(0xFFFFFFFFu, 0u, s - 32u));
-      const uint32_t x2 = hi >> 24;          // bits 56..63: byte 8 carries seven of them, byte 9 the last one ...
-      w2 = x2 | ((x2 & 0x80u) << 1);         // ... and when that one is set, byte 8 continues: the same bit
+    for (uint32_t i = 0; i < kVarPerThread; ++i) {
+      const uint32_t lo = (uint32_t)mine[i], hi = (uint32_t)(mine[i] >> 32);
+      const uint32_t L = (lens >> (4 * i)) & 15u;
+      // continuation bits go into the first L-1 bytes: the low 8(L-1) bits of a mask, by a clamped funnel shift.  (An
+      // absent element - only at the end of the last tile - has L = 0: what it ORs into `acc` lies above byte f and is
+      // never stored, because no element follows it.)
+      const uint32_t s = 8u * L - 8u;
+      const uint32_t w0 = bitsel(0x7F7F7F7Fu, spread28(lo), __funnelshift_lc(0xFFFFFFFFu, 0u, s));
+      uint32_t w1 = 0, w2 = 0;
+      if (L > 4) {
+        w1 = bitsel(0x7F7F7F7Fu, spread28(__funnelshift_r(lo, hi, 28)), __funnelshift_lc(0xFFFFFFFFu, 0u, s - 32u));
+        const uint32_t x2 = hi >> 24;          // bits 56..63: byte 8 carries seven of them, byte 9 the last one ...
+        w2 = x2 | ((x2 & 0x80u) << 1);         // ... and when that one is set, byte 8 continues: the same bit
+      }
+      const uint32_t shb = f * 8u;
+      const uint32_t o0 = acc | (w0 << shb);
+      const uint32_t o1 = __funnelshift_l(w0, w1, shb);
+      const uint32_t o2 = __funnelshift_l(w1, w2, shb);
+      const uint32_t o3 = __funnelshift_l(w2, 0u, shb);
+      const uint32_t n = f + L;
+      // store the words this element completed; keep the incomplete one
+      asm volatile(
+          "{\n\t.reg .pred p0, p1, p2;\n\t.reg .b32 t;\n\t"
+          "setp.ge.u32 p0, %1, 4;\n\tsetp.ge.u32 p1, %1, 8;\n\tsetp.ge.u32 p2, %1, 12;\n\t"
+          "@p0 st.shared.u32 [%2], %3;\n\t@p1 st.shared.u32 [%2+4], %4;\n\t@p2 st.shared.u32 [%2+8], %5;\n\t"
+          "selp.b32 t, %4, %3, p0;\n\tselp.b32 t, %5, t, p1;\n\tselp.b32 %0, %6, t, p2;\n\t}"
+          : "=r"(acc) : "r"(n), "r"(sa), "r"(o0), "r"(o1), "r"(o2), "r"(o3) : "memory");
+      sa += n & ~3u;
+      f = n & 3;
     }
-    const uint32_t shb = f * 8u;
-    const uint32_t o0 = acc | (w0 << shb);
-    const uint32_t o1 = __funnelshift_l(w0, w1, shb);
-    const uint32_t o2 = __funnelshift_l(w1, w2, shb);
-    const uint32_t o3 = __funnelshift_l(w2, 0u, shb);
-    const uint32_t n = f + L;
-    // store the words this element completed; keep the incomplete one
-    asm volatile(
-        "{\n\t.reg .pred p0, p1, p2;\n\t.reg .b32 t;\n\t"
-        "setp.ge.u32 p0, %1, 4;\n\tsetp.ge.u32 p1, %1, 8;\n\tsetp.ge.u32 p2, %1, 12;\n\t"
-        "@p0 st.shared.u32 [%2], %3;\n\t@p1 st.shared.u32 [%2+4], %4;\n\t@p2 st.shared.u32 [%2+8], %5;\n\t"
-        "selp.b32 t, %4, %3, p0;\n\tselp.b32 t, %5, t, p1;\n\tselp.b32 %0, %6, t, p2;\n\t}"
-        : "=r"(acc) : "r"(n), "r"(sa), "r"(o0), "r"(o1), "r"(o2), "r"(o3) : "memory");
-    sa += n & ~3u;
-    f = n & 3;
-  }
   }
   __syncthreads();
   // the word this thread did not complete: its bytes only (the thread that completes the word stored zeros there)
@@ -292,6 +283,28 @@ __global__ void __launch_bounds__(kVarThreads, 5) venc_emit_kernel(const __grid_
       if (b >= first && b < f) tail[b] = (uint8_t)(acc >> (8 * b));
   }
   __syncthreads();
+}
+
+__global__ void __launch_bounds__(kVarThreads, 5) venc_emit_kernel(const __grid_constant__ VarTables tb) {
+  __shared__ __align__(16) uint8_t smem[kVarImageBytes];
+  __shared__ VarShared sh;
+  const uint32_t t = blockIdx.x;
+  VarSeg sg;
+  VarJobDev jb;
+  fetch_tile(tb, t, sg, jb);
+  const uint32_t t_rel = t - jb.first_tile;
+  const uint64_t e0 = (uint64_t)(t - sg.first_tile) * kVarTileElems;
+  const uint32_t cnt = (uint32_t)min((uint64_t)kVarTileElems, sg.n - e0);
+  const uint64_t share = prefix_share(jb, t_rel);
+  uint64_t mine[kVarPerThread];
+  uint32_t lens;
+  const uint32_t sum = venc_load_tile(smem, sg, jb, e0, cnt, mine, lens);
+  uint32_t total;
+  uint64_t base;
+  uint32_t off = block_scan_sum(sum, &total, share, &base, sh);   // every thread has read its elements before the first barrier inside
+  uint8_t* g = jb.dst + base;                  // first output byte of this tile
+  const uint32_t phase = (uint32_t)((uintptr_t)g & 15);
+  venc_build_image(smem, mine, lens, off + phase);
   // smem[phase .. phase+total) -> g[0 .. total); whole 16-byte vectors where the tile owns them.  Never past the
   // payload the header announced (the data changed between b200tfs_measure and the encode: undefined bytes, no overrun)
   if (base >= jb.cap) return;
@@ -305,6 +318,129 @@ __global__ void __launch_bounds__(kVarThreads, 5) venc_emit_kernel(const __grid_
     for (uint32_t i = v_hi * 16 + threadIdx.x; i < hi; i += kVarThreads) gbase[i] = smem[i];
   } else {
     for (uint32_t i = lo + threadIdx.x; i < hi; i += kVarThreads) gbase[i] = smem[i];
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// E3: ONE pass - count, place and emit in a single kernel (the deferred encode's anchored jobs: a packed-varint payload whose
+// first byte the host could fix in advance).  venc_emit recomputes every length anyway; what it lacks is where its tile's
+// bytes go, i.e. the byte count of all tiles before it.  That prefix comes from a two-level look-back instead of a counting
+// kernel (which read the whole tensor once more - 25 of 95 us on 16M int64):
+//   * tiles take their number from a ticket (started tiles only ever wait for tiles that started earlier);
+//   * a tile publishes its byte count as soon as its lengths are scanned; groups of kVarFuseGroup consecutive tiles: the tile
+//     whose publication completes a group sums the group and resolves the group's exclusive prefix by a decoupled look-back
+//     over GROUP descriptors (a few per microsecond - a 32-wide window always reaches a resolved group; at TILE level ~100
+//     tiles start per microsecond and round 1's tile-level look-back could not keep up), before it builds its own image;
+//   * every tile builds its image first (the expensive part, ~3 us) and only then reads what it needs - the previous group's
+//     inclusive prefix and the counts of the tiles before it inside its group, all long since published - so the look-back
+//     costs nothing on the critical path.  The image is built at phase 0 and realigned on the way out (two 128-bit shared
+//     loads and a funnel shift per 128-bit store), since the destination's phase is not known while building.
+// ------------------------------------------------------------------------------------------------
+constexpr uint32_t kVarFuseGroup = 32;
+constexpr uint32_t kFuseFlag = 0x80000000u;
+constexpr unsigned long long kFuseAgg = 1ull << 62, kFuseInc = 2ull << 62, kFuseMask = (1ull << 62) - 1;
+
+__device__ __forceinline__ uint32_t ld_volatile_u32(const uint32_t* p) { uint32_t v; asm volatile("ld.volatile.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory"); return v; }
+__device__ __forceinline__ unsigned long long ld_volatile_u64(const unsigned long long* p) {
+  unsigned long long v; asm volatile("ld.volatile.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory"); return v;
+}
+
+__global__ void __launch_bounds__(kVarThreads, 5) venc_fused_kernel(const __grid_constant__ VarTables tb, const __grid_constant__ VarFuse fz) {
+  __shared__ __align__(16) uint8_t smem[kVarImageBytes + 16];
+  __shared__ VarShared sh;
+  __shared__ uint32_t s_ticket, s_resolver;
+  __shared__ unsigned long long s_base;
+  if (threadIdx.x == 0) s_ticket = atomicAdd(fz.ticket, 1u);
+  __syncthreads();
+  const uint32_t t = s_ticket;
+  VarSeg sg;
+  VarJobDev jb;
+  fetch_tile(tb, t, sg, jb);
+  const uint32_t t_rel = t - jb.first_tile;
+  const uint64_t e0 = (uint64_t)(t - sg.first_tile) * kVarTileElems;
+  const uint32_t cnt = (uint32_t)min((uint64_t)kVarTileElems, sg.n - e0);
+  // counters of this job: jb.tile_val = per-tile state, jb.group_sum is not used; group descriptors and arrival counters by job group
+  const uint32_t g_rel = t_rel / kVarFuseGroup, k_in = t_rel % kVarFuseGroup;
+  const uint32_t n_groups = (jb.n_tiles + kVarFuseGroup - 1) / kVarFuseGroup;
+  const uint32_t in_group = min(kVarFuseGroup, jb.n_tiles - g_rel * kVarFuseGroup);
+  uint64_t mine[kVarPerThread];
+  uint32_t lens;
+  const uint32_t sum = venc_load_tile(smem, sg, jb, e0, cnt, mine, lens);
+  uint32_t total;
+  uint64_t unused;
+  const uint32_t off = block_scan_sum(sum, &total, 0ull, &unused, sh);
+  unsigned long long* gs = fz.group_state + (uint32_t)jb.flags;       // jb.flags: first group descriptor of this job (host-assigned)
+  uint32_t* arrivals = fz.group_arrivals + (uint32_t)jb.flags;
+  if (threadIdx.x == 0) {
+    // publish this tile's count, then count it as arrived; whoever completes the group resolves it
+    asm volatile("st.volatile.global.u32 [%0], %1;" :: "l"(jb.tile_val + t_rel), "r"(kFuseFlag | total) : "memory");
+    __threadfence();
+    s_resolver = (atomicAdd(arrivals + g_rel, 1u) + 1u == in_group) ? 1u : 0u;
+  }
+  __syncthreads();
+  if (s_resolver && threadIdx.x < 32) {
+    // all counts of the group are published: sum them, then the group's exclusive prefix by look-back over group descriptors
+    const uint32_t lane = threadIdx.x;
+    uint32_t c = 0;
+    if (lane < in_group) c = ld_volatile_u32(jb.tile_val + g_rel * kVarFuseGroup + lane) & ~kFuseFlag;
+#pragma unroll
+    for (int d = 16; d; d >>= 1) c += __shfl_xor_sync(0xFFFFFFFFu, c, d);
+    if (lane == 0 && g_rel + 1 < n_groups) { asm volatile("st.volatile.global.u64 [%0], %1;" :: "l"(gs + g_rel), "l"(kFuseAgg | (unsigned long long)c) : "memory"); __threadfence(); }
+    unsigned long long prefix = 0;
+    int32_t look = (int32_t)g_rel - 1;
+    while (look >= 0) {
+      const int32_t idx = look - (int32_t)lane;
+      unsigned long long d = kFuseInc;   // lanes before the first group contribute a resolved zero
+      if (idx >= 0) { do { d = ld_volatile_u64(gs + idx); } while ((d >> 62) == 0); }
+      const uint32_t inc_mask = __ballot_sync(0xFFFFFFFFu, (d >> 62) == 2);
+      const uint32_t first_inc = inc_mask ? (uint32_t)__ffs(inc_mask) - 1u : 32u;    // nearest resolved group in this window
+      unsigned long long part = (lane <= first_inc) ? (d & kFuseMask) : 0ull;
+#pragma unroll
+      for (int s = 16; s; s >>= 1) part += __shfl_xor_sync(0xFFFFFFFFu, part, s);
+      prefix += part;
+      if (inc_mask) break;
+      look -= 32;
+    }
+    if (lane == 0) {
+      asm volatile("st.volatile.global.u64 [%0], %1;" :: "l"(gs + g_rel), "l"(kFuseInc | (prefix + c)) : "memory");
+      __threadfence();
+      if (g_rel + 1 == n_groups) *jb.total = prefix + c;      // the job's packed length: read by the framing kernel behind us
+    }
+  }
+  venc_build_image(smem + 16, mine, lens, off);      // image at smem[16 ..): block -1 stays free for the realigning copy below
+  if (threadIdx.x < 32) {
+    const uint32_t lane = threadIdx.x;
+    unsigned long long before = 0;
+    if (g_rel > 0 && lane == 0) { unsigned long long d; do { d = ld_volatile_u64(gs + g_rel - 1); } while ((d >> 62) != 2); before = d & kFuseMask; }
+    uint32_t c = 0;
+    if (lane < k_in) { uint32_t v; do { v = ld_volatile_u32(jb.tile_val + g_rel * kVarFuseGroup + lane); } while (!(v & kFuseFlag)); c = v & ~kFuseFlag; }
+#pragma unroll
+    for (int d = 16; d; d >>= 1) c += __shfl_xor_sync(0xFFFFFFFFu, c, d);
+    if (lane == 0) s_base = before + c;
+  }
+  __syncthreads();
+  const uint64_t base = s_base;
+  if (base >= jb.cap) return;
+  total = (uint32_t)min((uint64_t)total, jb.cap - base);
+  // image bytes [0, total) at smem + 16  ->  g[0, total), g = jb.dst + base of any alignment
+  uint8_t* g = jb.dst + base;
+  const uint32_t ph = (uint32_t)((uintptr_t)g & 15);
+  uint8_t* gbase = g - ph;                          // 16-byte aligned; destination vector v covers image bytes [16v - ph, 16v - ph + 16)
+  const uint32_t lo = ph, hi = ph + total;
+  const uint32_t v_lo = (lo + 15) >> 4, v_hi = hi >> 4;
+  const uint8_t* img = smem + 16;
+  if (v_lo < v_hi) {
+    const uint32_t k = (16 - ph) & 15;              // image offset of vector v inside its 16-byte block
+    for (uint32_t v = v_lo + threadIdx.x; v < v_hi; v += kVarThreads) {
+      const uint4* blk = reinterpret_cast<const uint4*>(img + 16 * v - ph - k);    // block holding the vector's first byte (16-aligned)
+      uint4 o = blk[0];
+      if (k) o = shift_pair_dyn(blk[0], blk[1], k >> 2, (k & 3) * 8);
+      st_stream(gbase + 16 * v, o);
+    }
+    for (uint32_t i = lo + threadIdx.x; i < v_lo * 16; i += kVarThreads) gbase[i] = img[i - ph];
+    for (uint32_t i = v_hi * 16 + threadIdx.x; i < hi; i += kVarThreads) gbase[i] = img[i - ph];
+  } else {
+    for (uint32_t i = lo + threadIdx.x; i < hi; i += kVarThreads) gbase[i] = img[i - ph];
   }
 }
 

@@ -105,6 +105,16 @@ def test_deferred_frame_varint_lengths_cross_the_varint_boundaries():
         assert wire == want, n
         wire5, *_ = deferred_wire("m", 7, inputs, grpc=True)
         assert wire5 == b"\x00" + len(want).to_bytes(4, "big") + want
+        # the varint input LAST on the wire and the only large one: the single-pass (anchored) layout - its payload sits at a position
+        # the host fixed in advance (128-byte aligned) and the record is laid out backwards from there
+        last = [("img", x), ("z_ids", ids)]
+        want = wire_oracle.encode_predict_request("m", 7, last)
+        wire, off, poff, plen = deferred_wire("m", 7, last)
+        assert wire == want, n
+        if n > 32:
+            assert poff[1] % 128 == 0 and off + len(want) == poff[1] + plen[1]
+        assert deferred_wire("m", 7, last, grpc=True)[0] == b"\x00" + len(want).to_bytes(4, "big") + want
+        assert deferred_wire("", None, [("only", ids)])[0] == wire_oracle.encode_predict_request("", None, [("only", ids)])
     # a request whose only inputs are empty or zero-element tensors, and one with no inputs at all
     assert deferred_wire("m", None, [("e", np.zeros((0, 3), np.int64))])[0] == wire_oracle.encode_predict_request("m", None, [("e", np.zeros((0, 3), np.int64))])
     assert deferred_wire("", 0, [])[0] == wire_oracle.encode_predict_request("", 0, [])

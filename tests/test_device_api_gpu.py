@@ -773,7 +773,9 @@ def test_deferred_encode_no_host_round_trip(dev):
             toks = (rng.integers(0, 50000, size=(2, 40 + i)) * scale - (i % 3)).astype(np.int32)      # some negatives: ten-byte varints
             out.append(("default", 1 if i % 2 else None, [("image", img), ("label", label), ("tokens", toks), ("mask", toks > 100),
                                                            ("empty", np.zeros((0, 4), np.int64))]))
-        out.append(("m", 3, [("big", (rng.integers(0, 2 ** 62, size=70000, dtype=np.int64) >> rng.integers(0, 62, size=70000)))]))
+        out.append(("m", 3, [("big", (rng.integers(0, 2 ** 62, size=70000, dtype=np.int64) >> rng.integers(0, 62, size=70000)))]))   # single pass
+        out.append(("two", 2, [("a_ids", (rng.integers(0, 50000, size=5000) * scale).astype(np.int64)),                                 # two large varint
+                               ("b_ids", (rng.integers(-9, 300, size=4097) * scale).astype(np.int16)), ("x", rng.standard_normal(9).astype(np.float32))]))  # inputs: two-pass
         out.append(("", None, []))
         return out
     batch = batch_for(1)

@@ -65,6 +65,19 @@ def main():
         t_me, _ = timed(dev, both, args.reps)
         t_m, _ = timed(dev, lambda: N.check(lib.b200tfs_measure(dev.ctx, 1, vt)), args.reps)
         t_e, _ = timed(dev, lambda: N.check(lib.b200tfs_encode_tensor_protos(dev.ctx, 1, vt, arena, need.value, o, ln)), args.reps)
+        # the deferred encode: the same tensor as the only input of a PredictRequest, packed_len unset - no host round trip; the
+        # single-pass kernel (count + place + emit) when B200TFS_NO_FUSED_VARINT is not set, else count -> frame -> emit
+        vt2 = (N.Tensor * 1)(N.Tensor(data=v, src_dtype=dt, wire_dtype=dt, rank=1, flags=0, dims=vd, key=b"ids", key_len=3, packed_len=0))
+        rq = (N.Request * 1)(N.Request(model_name=b"m", model_name_len=1, has_version=0, order=N.ORDER_UPB, version=0, n_inputs=1, flags=0, inputs=vt2))
+        need2 = C.c_uint64()
+        N.check(lib.b200tfs_request_arena_size(1, rq, C.byref(need2)))
+        arena_d = dev.malloc(need2.value)
+        t_def, _ = timed(dev, lambda: N.check(lib.b200tfs_encode_requests_async(dev.ctx, 1, rq, arena_d, need2.value)), args.reps)
+        do, dl = (C.c_uint64 * 1)(), (C.c_uint64 * 1)()
+        N.check(lib.b200tfs_encode_results(dev.ctx, 1, do, dl))
+        got = dev.download(arena_d + int(do[0]), int(dl[0]))
+        ref = dev.download(arena + int(o[0]), int(ln[0]))
+        assert got[-packed:].tobytes() == ref[-packed:].tobytes() and int(dl[0]) > packed      # same packed payload as the measured encode
         outs = (N.Output * 1)()
         st = (C.c_int32 * 1)()
         N.check(lib.b200tfs_parse_tensor_protos(dev.ctx, arena, 1, o, ln, outs, st))
@@ -75,6 +88,7 @@ def main():
         assert np.array_equal(dev.download(back, src_bytes).view(vals.dtype), vals)
         out[name] = {"src_bytes": src_bytes, "packed_bytes": packed,
                      "measure_us": t_m * 1e6, "encode_us": t_e * 1e6, "measure_plus_encode_us": t_me * 1e6, "decode_us": t_d * 1e6,
+                     "deferred_encode_us": t_def * 1e6, "deferred_encode_frac": alg / t_def / 1e9 / peak,
                      "encode_frac": alg / t_me / 1e9 / peak, "encode_only_frac": alg / t_e / 1e9 / peak, "decode_frac": alg / t_d / 1e9 / peak}
     print(json.dumps(out, indent=1))
     dev.close()
