@@ -1189,6 +1189,22 @@ cudaError_t launch_decode_fused(const FusedParams& fp, uint32_t grid, cudaStream
   return launch_pdl(decode_fused_kernel, grid, kMoveThreads, 0, stream, fp);
 }
 
+// CTAs that are resident at once on the current device (persistent kernels take their tiles by ticket); per device, computed once
+template <typename K>
+static uint32_t persistent_grid(K kernel) {
+  static uint32_t cached[64] = {};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev < 0 || dev >= 64) dev = 0;
+  if (!cached[dev]) {
+    int per_sm = 0, sms = 0;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, kVarThreads, 0);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    cached[dev] = (uint32_t)max(1, per_sm) * (uint32_t)max(1, sms);
+  }
+  return cached[dev];
+}
+
 cudaError_t launch_venc_len(const VarTables& tb, cudaStream_t stream) {
   if (!tb.n_tiles) return cudaSuccess;
   venc_len_kernel<<<tb.n_tiles, kVarThreads, 0, stream>>>(tb);
@@ -1196,12 +1212,17 @@ cudaError_t launch_venc_len(const VarTables& tb, cudaStream_t stream) {
 }
 cudaError_t launch_venc_fused(const VarTables& tb, const VarFuse& fz, cudaStream_t stream) {
   if (!tb.n_tiles) return cudaSuccess;
-  venc_fused_kernel<<<tb.n_tiles, kVarThreads, 0, stream>>>(tb, fz);
+  venc_fused_kernel<<<min(tb.n_tiles, persistent_grid(venc_fused_kernel)), kVarThreads, 0, stream>>>(tb, fz);
   return cudaGetLastError();
 }
 cudaError_t launch_venc_emit(const VarTables& tb, cudaStream_t stream) {
   if (!tb.n_tiles) return cudaSuccess;
   venc_emit_kernel<<<tb.n_tiles, kVarThreads, 0, stream>>>(tb);
+  return cudaGetLastError();
+}
+cudaError_t launch_vdec_fused(const VarTables& tb, const VarFuse& fz, cudaStream_t stream) {
+  if (!tb.n_tiles) return cudaSuccess;
+  vdec_fused_kernel<<<min(tb.n_tiles, persistent_grid(vdec_fused_kernel)), kVarThreads, 0, stream>>>(tb, fz);
   return cudaGetLastError();
 }
 cudaError_t launch_vdec_count(const VarTables& tb, cudaStream_t stream) {

@@ -143,6 +143,8 @@ struct VarJobDev {
   int32_t flags;
   uint32_t first_tile;
   uint32_t n_tiles;
+  uint32_t fuse_group0;  // single-pass kernels: the job's first group descriptor (VarFuse)
+  uint32_t pad;
 };
 
 // what every varint kernel receives (by value, in the parameter space).  A single job with a single segment - one
@@ -208,7 +210,7 @@ struct FrameTables {
 };
 
 // single-pass varint encode (venc_fused_kernel): the look-back state behind VarTables.  VarJobDev::tile_val holds the per-tile
-// state (flag | bytes), VarJobDev::flags the job's first group descriptor; everything is zeroed before the launch.
+// state (flag | count), VarJobDev::fuse_group0 the job's first group descriptor; everything is zeroed before the launch.
 struct VarFuse {
   uint32_t* ticket;                    // tiles take their number from here
   unsigned long long* group_state;     // per group of 32 tiles: 2-bit flag (1 = sum known, 2 = inclusive prefix known) | bytes

@@ -345,102 +345,141 @@ __device__ __forceinline__ unsigned long long ld_volatile_u64(const unsigned lon
   unsigned long long v; asm volatile("ld.volatile.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory"); return v;
 }
 
+// --- the two-level look-back, shared by the single-pass encoder (counts = bytes) and decoder (counts = elements) -------------
+struct FuseJob {
+  uint32_t* tile_state;            // [n_tiles] flag | count
+  unsigned long long* gs;          // [n_groups] group descriptors
+  uint32_t* arrivals;              // [n_groups]
+  uint32_t n_tiles;
+};
+
+// Run by ONE warp of the CTA (all 32 lanes), the tile's bookkeeper, while the other warps do the tile's heavy work: lane 0
+// publishes the tile's count; if that completes the tile's group, the warp resolves the group (sum, AGG descriptor, decoupled
+// look-back over earlier groups, INC descriptor).  Returns the job's total in every lane when this warp resolved the job's LAST
+// group, else ~0ull.
+__device__ __forceinline__ unsigned long long fuse_publish_warp(const FuseJob& J, uint32_t t_rel, uint32_t count) {
+  const uint32_t lane = threadIdx.x & 31;
+  const uint32_t g_rel = t_rel / kVarFuseGroup;
+  const uint32_t n_groups = (J.n_tiles + kVarFuseGroup - 1) / kVarFuseGroup;
+  const uint32_t in_group = min(kVarFuseGroup, J.n_tiles - g_rel * kVarFuseGroup);
+  uint32_t resolver = 0;
+  if (lane == 0) {
+    asm volatile("st.volatile.global.u32 [%0], %1;" :: "l"(J.tile_state + t_rel), "r"(kFuseFlag | count) : "memory");
+    __threadfence();
+    resolver = (atomicAdd(J.arrivals + g_rel, 1u) + 1u == in_group) ? 1u : 0u;
+  }
+  resolver = __shfl_sync(0xFFFFFFFFu, resolver, 0);
+  if (!resolver) return ~0ull;
+  uint32_t c = 0;
+  if (lane < in_group) c = ld_volatile_u32(J.tile_state + g_rel * kVarFuseGroup + lane) & ~kFuseFlag;
+#pragma unroll
+  for (int d = 16; d; d >>= 1) c += __shfl_xor_sync(0xFFFFFFFFu, c, d);
+  if (lane == 0 && g_rel + 1 < n_groups) {
+    asm volatile("st.volatile.global.u64 [%0], %1;" :: "l"(J.gs + g_rel), "l"(kFuseAgg | (unsigned long long)c) : "memory");
+    __threadfence();
+  }
+  unsigned long long prefix = 0;
+  int32_t look = (int32_t)g_rel - 1;
+  while (look >= 0) {
+    const int32_t idx = look - (int32_t)lane;
+    unsigned long long d = kFuseInc;   // lanes before the first group contribute a resolved zero
+    if (idx >= 0) { do { d = ld_volatile_u64(J.gs + idx); } while ((d >> 62) == 0); }
+    const uint32_t inc_mask = __ballot_sync(0xFFFFFFFFu, (d >> 62) == 2);
+    const uint32_t first_inc = inc_mask ? (uint32_t)__ffs(inc_mask) - 1u : 32u;    // nearest resolved group in this window
+    unsigned long long part = (lane <= first_inc) ? (d & kFuseMask) : 0ull;
+#pragma unroll
+    for (int s = 16; s; s >>= 1) part += __shfl_xor_sync(0xFFFFFFFFu, part, s);
+    prefix += part;
+    if (inc_mask) break;
+    look -= 32;
+  }
+  if (lane == 0) {
+    asm volatile("st.volatile.global.u64 [%0], %1;" :: "l"(J.gs + g_rel), "l"(kFuseInc | (prefix + c)) : "memory");
+    __threadfence();
+  }
+  return (g_rel + 1 == n_groups) ? prefix + c : ~0ull;
+}
+
+// the bookkeeper warp: the counts of all tiles before t_rel = the previous group's inclusive prefix + the tiles before it inside
+// its group; valid in every lane
+__device__ __forceinline__ unsigned long long fuse_prefix_warp(const FuseJob& J, uint32_t t_rel) {
+  const uint32_t lane = threadIdx.x & 31, g_rel = t_rel / kVarFuseGroup, k_in = t_rel % kVarFuseGroup;
+  unsigned long long before = 0;
+  if (g_rel > 0 && lane == 0) { unsigned long long d; do { d = ld_volatile_u64(J.gs + g_rel - 1); } while ((d >> 62) != 2); before = d & kFuseMask; }
+  uint32_t c = 0;
+  if (lane < k_in) { uint32_t v; do { v = ld_volatile_u32(J.tile_state + g_rel * kVarFuseGroup + lane); } while (!(v & kFuseFlag)); c = v & ~kFuseFlag; }
+#pragma unroll
+  for (int d = 16; d; d >>= 1) c += __shfl_xor_sync(0xFFFFFFFFu, c, d);
+  before = __shfl_sync(0xFFFFFFFFu, before, 0);
+  return before + c;
+}
+
+// Persistent CTAs: each takes tiles by ticket until none are left (the next ticket is fetched while the current tile is being
+// worked on).  The LAST warp is the tile's bookkeeper: while the other seven build their part of the image it publishes the
+// count, resolves the group if need be and fetches the tile's prefix - three dependent L2 round trips that, done by the whole
+// CTA behind barriers (first version: 123 us on 16M int64, 40 % issue-active, barrier stalls 11 per issue), cost more than the
+// counting kernel they replace - and then builds its own 256 elements.
 __global__ void __launch_bounds__(kVarThreads, 5) venc_fused_kernel(const __grid_constant__ VarTables tb, const __grid_constant__ VarFuse fz) {
   __shared__ __align__(16) uint8_t smem[kVarImageBytes + 16];
   __shared__ VarShared sh;
-  __shared__ uint32_t s_ticket, s_resolver;
+  __shared__ uint32_t s_ticket, s_next;
   __shared__ unsigned long long s_base;
+  const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  constexpr uint32_t kKeeper = kVarThreads / 32 - 1;
   if (threadIdx.x == 0) s_ticket = atomicAdd(fz.ticket, 1u);
   __syncthreads();
-  const uint32_t t = s_ticket;
-  VarSeg sg;
-  VarJobDev jb;
-  fetch_tile(tb, t, sg, jb);
-  const uint32_t t_rel = t - jb.first_tile;
-  const uint64_t e0 = (uint64_t)(t - sg.first_tile) * kVarTileElems;
-  const uint32_t cnt = (uint32_t)min((uint64_t)kVarTileElems, sg.n - e0);
-  // counters of this job: jb.tile_val = per-tile state, jb.group_sum is not used; group descriptors and arrival counters by job group
-  const uint32_t g_rel = t_rel / kVarFuseGroup, k_in = t_rel % kVarFuseGroup;
-  const uint32_t n_groups = (jb.n_tiles + kVarFuseGroup - 1) / kVarFuseGroup;
-  const uint32_t in_group = min(kVarFuseGroup, jb.n_tiles - g_rel * kVarFuseGroup);
-  uint64_t mine[kVarPerThread];
-  uint32_t lens;
-  const uint32_t sum = venc_load_tile(smem, sg, jb, e0, cnt, mine, lens);
-  uint32_t total;
-  uint64_t unused;
-  const uint32_t off = block_scan_sum(sum, &total, 0ull, &unused, sh);
-  unsigned long long* gs = fz.group_state + (uint32_t)jb.flags;       // jb.flags: first group descriptor of this job (host-assigned)
-  uint32_t* arrivals = fz.group_arrivals + (uint32_t)jb.flags;
-  if (threadIdx.x == 0) {
-    // publish this tile's count, then count it as arrived; whoever completes the group resolves it
-    asm volatile("st.volatile.global.u32 [%0], %1;" :: "l"(jb.tile_val + t_rel), "r"(kFuseFlag | total) : "memory");
-    __threadfence();
-    s_resolver = (atomicAdd(arrivals + g_rel, 1u) + 1u == in_group) ? 1u : 0u;
-  }
-  __syncthreads();
-  if (s_resolver && threadIdx.x < 32) {
-    // all counts of the group are published: sum them, then the group's exclusive prefix by look-back over group descriptors
-    const uint32_t lane = threadIdx.x;
-    uint32_t c = 0;
-    if (lane < in_group) c = ld_volatile_u32(jb.tile_val + g_rel * kVarFuseGroup + lane) & ~kFuseFlag;
-#pragma unroll
-    for (int d = 16; d; d >>= 1) c += __shfl_xor_sync(0xFFFFFFFFu, c, d);
-    if (lane == 0 && g_rel + 1 < n_groups) { asm volatile("st.volatile.global.u64 [%0], %1;" :: "l"(gs + g_rel), "l"(kFuseAgg | (unsigned long long)c) : "memory"); __threadfence(); }
-    unsigned long long prefix = 0;
-    int32_t look = (int32_t)g_rel - 1;
-    while (look >= 0) {
-      const int32_t idx = look - (int32_t)lane;
-      unsigned long long d = kFuseInc;   // lanes before the first group contribute a resolved zero
-      if (idx >= 0) { do { d = ld_volatile_u64(gs + idx); } while ((d >> 62) == 0); }
-      const uint32_t inc_mask = __ballot_sync(0xFFFFFFFFu, (d >> 62) == 2);
-      const uint32_t first_inc = inc_mask ? (uint32_t)__ffs(inc_mask) - 1u : 32u;    // nearest resolved group in this window
-      unsigned long long part = (lane <= first_inc) ? (d & kFuseMask) : 0ull;
-#pragma unroll
-      for (int s = 16; s; s >>= 1) part += __shfl_xor_sync(0xFFFFFFFFu, part, s);
-      prefix += part;
-      if (inc_mask) break;
-      look -= 32;
+  for (;;) {
+    const uint32_t t = s_ticket;
+    if (t >= tb.n_tiles) break;
+    VarSeg sg;
+    VarJobDev jb;
+    fetch_tile(tb, t, sg, jb);
+    const uint32_t t_rel = t - jb.first_tile;
+    const uint64_t e0 = (uint64_t)(t - sg.first_tile) * kVarTileElems;
+    const uint32_t cnt = (uint32_t)min((uint64_t)kVarTileElems, sg.n - e0);
+    const FuseJob J{jb.tile_val, fz.group_state + jb.fuse_group0, fz.group_arrivals + jb.fuse_group0, jb.n_tiles};
+    uint64_t mine[kVarPerThread];
+    uint32_t lens;
+    const uint32_t sum = venc_load_tile(smem, sg, jb, e0, cnt, mine, lens);
+    uint32_t total;
+    uint64_t unused;
+    const uint32_t off = block_scan_sum(sum, &total, 0ull, &unused, sh);
+    if (warp == kKeeper) {
+      uint32_t nxt = 0;
+      if (lane == 0) nxt = atomicAdd(fz.ticket, 1u);                      // the next tile's ticket: in flight while we work
+      const unsigned long long job_total = fuse_publish_warp(J, t_rel, total);
+      if (lane == 0 && job_total != ~0ull) *jb.total = job_total;         // the packed length: read by the framing kernel behind us
+      const unsigned long long b = fuse_prefix_warp(J, t_rel);
+      if (lane == 0) { s_base = b; s_next = nxt; }
     }
-    if (lane == 0) {
-      asm volatile("st.volatile.global.u64 [%0], %1;" :: "l"(gs + g_rel), "l"(kFuseInc | (prefix + c)) : "memory");
-      __threadfence();
-      if (g_rel + 1 == n_groups) *jb.total = prefix + c;      // the job's packed length: read by the framing kernel behind us
+    venc_build_image(smem + 16, mine, lens, off);      // image at smem[16 ..): block -1 stays free for the realigning copy below
+    const uint64_t base = s_base;                      // (written before the keeper entered the build's barriers)
+    if (base < jb.cap) {
+      const uint32_t n_out = (uint32_t)min((uint64_t)total, jb.cap - base);
+      // image bytes [0, n_out) at smem + 16  ->  g[0, n_out), g = jb.dst + base of any alignment
+      uint8_t* g = jb.dst + base;
+      const uint32_t ph = (uint32_t)((uintptr_t)g & 15);
+      uint8_t* gbase = g - ph;                          // 16-byte aligned; destination vector v covers image bytes [16v - ph, 16v - ph + 16)
+      const uint32_t lo = ph, hi = ph + n_out;
+      const uint32_t v_lo = (lo + 15) >> 4, v_hi = hi >> 4;
+      const uint8_t* img = smem + 16;
+      if (v_lo < v_hi) {
+        const uint32_t k = (16 - ph) & 15;              // image offset of vector v inside its 16-byte block
+        for (uint32_t v = v_lo + threadIdx.x; v < v_hi; v += kVarThreads) {
+          const uint4* blk = reinterpret_cast<const uint4*>(img + 16 * v - ph - k);    // block holding the vector's first byte (16-aligned)
+          uint4 o = blk[0];
+          if (k) o = shift_pair_dyn(blk[0], blk[1], k >> 2, (k & 3) * 8);
+          st_stream(gbase + 16 * v, o);
+        }
+        for (uint32_t i = lo + threadIdx.x; i < v_lo * 16; i += kVarThreads) gbase[i] = img[i - ph];
+        for (uint32_t i = v_hi * 16 + threadIdx.x; i < hi; i += kVarThreads) gbase[i] = img[i - ph];
+      } else {
+        for (uint32_t i = lo + threadIdx.x; i < hi; i += kVarThreads) gbase[i] = img[i - ph];
+      }
     }
-  }
-  venc_build_image(smem + 16, mine, lens, off);      // image at smem[16 ..): block -1 stays free for the realigning copy below
-  if (threadIdx.x < 32) {
-    const uint32_t lane = threadIdx.x;
-    unsigned long long before = 0;
-    if (g_rel > 0 && lane == 0) { unsigned long long d; do { d = ld_volatile_u64(gs + g_rel - 1); } while ((d >> 62) != 2); before = d & kFuseMask; }
-    uint32_t c = 0;
-    if (lane < k_in) { uint32_t v; do { v = ld_volatile_u32(jb.tile_val + g_rel * kVarFuseGroup + lane); } while (!(v & kFuseFlag)); c = v & ~kFuseFlag; }
-#pragma unroll
-    for (int d = 16; d; d >>= 1) c += __shfl_xor_sync(0xFFFFFFFFu, c, d);
-    if (lane == 0) s_base = before + c;
-  }
-  __syncthreads();
-  const uint64_t base = s_base;
-  if (base >= jb.cap) return;
-  total = (uint32_t)min((uint64_t)total, jb.cap - base);
-  // image bytes [0, total) at smem + 16  ->  g[0, total), g = jb.dst + base of any alignment
-  uint8_t* g = jb.dst + base;
-  const uint32_t ph = (uint32_t)((uintptr_t)g & 15);
-  uint8_t* gbase = g - ph;                          // 16-byte aligned; destination vector v covers image bytes [16v - ph, 16v - ph + 16)
-  const uint32_t lo = ph, hi = ph + total;
-  const uint32_t v_lo = (lo + 15) >> 4, v_hi = hi >> 4;
-  const uint8_t* img = smem + 16;
-  if (v_lo < v_hi) {
-    const uint32_t k = (16 - ph) & 15;              // image offset of vector v inside its 16-byte block
-    for (uint32_t v = v_lo + threadIdx.x; v < v_hi; v += kVarThreads) {
-      const uint4* blk = reinterpret_cast<const uint4*>(img + 16 * v - ph - k);    // block holding the vector's first byte (16-aligned)
-      uint4 o = blk[0];
-      if (k) o = shift_pair_dyn(blk[0], blk[1], k >> 2, (k & 3) * 8);
-      st_stream(gbase + 16 * v, o);
-    }
-    for (uint32_t i = lo + threadIdx.x; i < v_lo * 16; i += kVarThreads) gbase[i] = img[i - ph];
-    for (uint32_t i = v_hi * 16 + threadIdx.x; i < hi; i += kVarThreads) gbase[i] = img[i - ph];
-  } else {
-    for (uint32_t i = lo + threadIdx.x; i < hi; i += kVarThreads) gbase[i] = img[i - ph];
+    __syncthreads();                                   // the image and s_base are free again
+    if (threadIdx.x == 0) s_ticket = s_next;
+    __syncthreads();
   }
 }
 
@@ -644,4 +683,121 @@ __global__ void __launch_bounds__(kVarThreads) vdec_emit_kernel(const __grid_con
     default: st_local = B200TFS_OK; break;
   }
   if (st_local != B200TFS_OK) atomicMin(jb.status, st_local);
+}
+
+// D3: ONE pass decode - the terminator counts that place a tile's elements in the tensor come from the same two-level look-back
+// as the encoder's byte counts (fuse_publish_warp / fuse_prefix_warp) instead of a counting kernel that read the wire once more.
+// Persistent CTAs take tiles by ticket; the last warp keeps the books (publish, resolve, prefix) while the others compact the
+// tile's varint starts.  The element-count check (reshape() would raise) moves to the end: the tile that resolves the job's last
+// group knows the total; elements beyond the tensor are never written either way (n_store).
+__global__ void __launch_bounds__(kVarThreads) vdec_fused_kernel(const __grid_constant__ VarTables tb, const __grid_constant__ VarFuse fz) {
+  constexpr uint32_t kBlocks = kVarTileBytes / 16;             // 512: two per thread
+  constexpr uint32_t kKeeper = kVarThreads / 32 - 1;
+  __shared__ __align__(16) uint8_t smraw[16 + kVarTileBytes + 16];
+  __shared__ uint16_t start_at[kVarTileBytes];
+  __shared__ VarShared sh;
+  __shared__ uint32_t s_ticket, s_next;
+  __shared__ unsigned long long s_base;
+  const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) s_ticket = atomicAdd(fz.ticket, 1u);
+  __syncthreads();
+  for (;;) {
+    const uint32_t t = s_ticket;
+    if (t >= tb.n_tiles) break;
+    VarSeg sg;
+    VarJobDev jb;
+    fetch_tile(tb, t, sg, jb);
+    const uint32_t t_rel = t - jb.first_tile;
+    const FuseJob J{jb.tile_val, fz.group_state + jb.fuse_group0, fz.group_arrivals + jb.fuse_group0, jb.n_tiles};
+    const uint8_t* lo = sg.src;
+    const uint8_t* hi = sg.src + sg.n;
+    const uint8_t* G = reinterpret_cast<const uint8_t*>((uintptr_t)sg.src & ~(uintptr_t)15) + (uint64_t)(t - sg.first_tile) * kVarTileBytes;
+    auto stage = [&](int32_t k) {
+      const uint8_t* p = G + 16 * (int64_t)k;
+      uint8_t* s = smraw + 16 * (k + 1);
+      if (p >= lo && p + 16 <= hi) *reinterpret_cast<uint4*>(s) = ld_stream(p);
+      else {
+        uint4 z = make_uint4(0u, 0u, 0u, 0u);
+        *reinterpret_cast<uint4*>(s) = z;
+        if (p + 16 > lo && p < hi)
+          for (int i = 0; i < 16; ++i) if (p + i >= lo && p + i < hi) s[i] = p[i];
+      }
+    };
+    stage((int32_t)threadIdx.x);
+    stage((int32_t)(threadIdx.x + kVarThreads));
+    if (threadIdx.x < 2) stage(threadIdx.x == 0 ? -1 : (int32_t)kBlocks);
+    __syncthreads();
+    // Phase 1 - starts and terminators of this thread's two blocks (bit tricks on one 128-bit shared load each)
+    uint32_t startm[2], terms = 0;
+#pragma unroll
+    for (uint32_t r = 0; r < 2; ++r) {
+      const uint32_t k = threadIdx.x + r * kVarThreads;
+      const uint8_t* s = smraw + 16 * (k + 1);
+      const uint4 w = *reinterpret_cast<const uint4*>(s);
+      auto msb4 = [](uint32_t x) { return (((x >> 7) & 0x01010101u) * 0x01020408u) >> 24; };   // 4 top bits -> nibble
+      const uint32_t cont = msb4(w.x) | (msb4(w.y) << 4) | (msb4(w.z) << 8) | (msb4(w.w) << 12);
+      const uint32_t prev_term = (s[-1] & 0x80) ? 0u : 1u;
+      uint32_t st = (((~cont) << 1) | prev_term) & 0xFFFFu;
+      uint32_t inside = 0xFFFFu;
+      const uint8_t* p = G + 16 * k;
+      if (!(p >= lo && p + 16 <= hi)) {              // block straddles an end of the chunk: positions inside it only
+        const int64_t first = max((int64_t)0, min((int64_t)16, (int64_t)(lo - p))), last = max((int64_t)0, min((int64_t)16, (int64_t)(hi - p)));
+        inside = ((1u << last) - 1u) & ~((1u << first) - 1u);
+      }
+      startm[r] = st & inside;
+      terms += __popc(~cont & inside);
+    }
+    // Phase 2 - rank the starts in position order (second-round blocks lie after every first-round block); the same scan adds
+    // up the tile's terminators
+    const uint32_t packed = __popc(startm[0]) | (__popc(startm[1]) << 16);
+    uint32_t packed_total;
+    uint64_t tile_terms;
+    const uint32_t rank = block_scan_sum(packed, &packed_total, (uint64_t)terms, &tile_terms, sh);
+    const uint32_t first_total = packed_total & 0xFFFFu, n_here = first_total + (packed_total >> 16);
+    if (warp == kKeeper) {
+      uint32_t nxt = 0;
+      if (lane == 0) nxt = atomicAdd(fz.ticket, 1u);
+      const unsigned long long job_total = fuse_publish_warp(J, t_rel, (uint32_t)tile_terms);
+      if (lane == 0 && job_total != ~0ull) {
+        *jb.total = job_total;
+        if ((jb.flags & kVarFlagPadEdge) ? job_total > jb.n_elems : job_total != jb.n_elems) atomicMin(jb.status, B200TFS_E_SHAPE);   // reshape() would raise
+      }
+      const unsigned long long b = fuse_prefix_warp(J, t_rel);
+      if (lane == 0) { s_base = b; s_next = nxt; }
+    }
+#pragma unroll
+    for (uint32_t r = 0; r < 2; ++r) {
+      uint32_t starts = startm[r], at = (r == 0) ? (rank & 0xFFFFu) : first_total + (rank >> 16);
+      const uint32_t at0 = 16 * (threadIdx.x + r * kVarThreads + 1);
+      while (starts) {
+        const uint32_t i = __ffs(starts) - 1;
+        starts &= starts - 1;
+        start_at[at++] = (uint16_t)(at0 + i);
+      }
+    }
+    __syncthreads();
+    // Phase 3 - the index of an element in the tensor is the number of terminators before it (+1 when a varint straddles in
+    // from the previous tile: it precedes ours but its terminator is here)
+    const uint64_t idx0 = s_base + (smraw[15] >> 7);
+    if (threadIdx.x == 0 && hi > G && hi <= G + kVarTileBytes && (hi[-1] & 0x80)) atomicMin(jb.status, B200TFS_E_PARSE);   // the chunk's last varint never ends
+    int32_t st_local;
+    switch (jb.dtype) {
+      case DT_INT64: case DT_UINT64: st_local = decode_elems<VS_U64>(smraw, start_at, n_here, jb.dst, idx0, jb.n_elems); break;
+      case DT_INT32: case DT_UINT32: st_local = decode_elems<VS_U32>(smraw, start_at, n_here, jb.dst, idx0, jb.n_elems); break;
+      case DT_INT16: st_local = decode_elems<VS_I16>(smraw, start_at, n_here, jb.dst, idx0, jb.n_elems); break;
+      case DT_INT8: st_local = decode_elems<VS_I8>(smraw, start_at, n_here, jb.dst, idx0, jb.n_elems); break;
+      case DT_UINT16: st_local = decode_elems<VS_U16>(smraw, start_at, n_here, jb.dst, idx0, jb.n_elems); break;
+      case DT_UINT8: st_local = decode_elems<VS_U8>(smraw, start_at, n_here, jb.dst, idx0, jb.n_elems); break;
+      case DT_BOOL: st_local = decode_elems<VS_BOOL>(smraw, start_at, n_here, jb.dst, idx0, jb.n_elems); break;
+      case DT_HALF: case DT_BFLOAT16:
+        st_local = (jb.flags & kVarFlagHalfAsValue) ? decode_elems<VS_HALF_VALUE>(smraw, start_at, n_here, jb.dst, idx0, jb.n_elems)
+                                                    : decode_elems<VS_HALF_BITS>(smraw, start_at, n_here, jb.dst, idx0, jb.n_elems);
+        break;
+      default: st_local = B200TFS_OK; break;
+    }
+    if (st_local != B200TFS_OK) atomicMin(jb.status, st_local);
+    __syncthreads();                                   // the tile's shared memory and s_base are free again
+    if (threadIdx.x == 0) s_ticket = s_next;
+    __syncthreads();
+  }
 }

@@ -50,11 +50,21 @@ def launches(tag):
 
 
 def full(tag):
+    """one record per captured launch, from the reports (or from their `--page raw --csv` exports made on the GPU box: the reports
+    themselves are 4-5 MB per launch and gpurun brings back 64 MiB at most)"""
     out = []
-    for rep in sorted(glob.glob(os.path.join(SRC, f"prof_{tag}_*.ncu-rep"))):
-        workload = os.path.basename(rep)[len(f"prof_{tag}_"):-len(".ncu-rep")]
-        raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], stdout=subprocess.PIPE, text=True).stdout
-        rows = list(csv.reader(raw.splitlines()))
+    names = sorted(set(glob.glob(os.path.join(SRC, f"prof_{tag}_*.ncu-rep")) + glob.glob(os.path.join(SRC, f"prof_{tag}_*.raw.csv"))))
+    seen = set()
+    for rep in names:
+        workload = os.path.basename(rep)[len(f"prof_{tag}_"):].replace(".ncu-rep", "").replace(".raw.csv", "")
+        if workload in seen:
+            continue
+        seen.add(workload)
+        if rep.endswith(".raw.csv"):
+            raw = open(rep).read()
+        else:
+            raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], stdout=subprocess.PIPE, text=True).stdout
+        rows = list(csv.reader([ln for ln in raw.splitlines() if not ln.startswith("==")]))
         if len(rows) < 3:
             continue
         hdr, units = rows[0], rows[1]
