@@ -1190,7 +1190,7 @@ cudaError_t launch_decode_fused(const FusedParams& fp, uint32_t grid, cudaStream
 }
 
 // CTAs that are resident at once on the current device (persistent kernels take their tiles by ticket); per device, computed once
-template <typename K>
+template <int Tag, typename K>     // Tag: one cache per kernel (the two users have the same function type)
 static uint32_t persistent_grid(K kernel) {
   static uint32_t cached[64] = {};
   int dev = 0;
@@ -1212,7 +1212,7 @@ cudaError_t launch_venc_len(const VarTables& tb, cudaStream_t stream) {
 }
 cudaError_t launch_venc_fused(const VarTables& tb, const VarFuse& fz, cudaStream_t stream) {
   if (!tb.n_tiles) return cudaSuccess;
-  venc_fused_kernel<<<min(tb.n_tiles, persistent_grid(venc_fused_kernel)), kVarThreads, 0, stream>>>(tb, fz);
+  venc_fused_kernel<<<min(tb.n_tiles, persistent_grid<0>(venc_fused_kernel)), kVarThreads, 0, stream>>>(tb, fz);
   return cudaGetLastError();
 }
 cudaError_t launch_venc_emit(const VarTables& tb, cudaStream_t stream) {
@@ -1222,7 +1222,7 @@ cudaError_t launch_venc_emit(const VarTables& tb, cudaStream_t stream) {
 }
 cudaError_t launch_vdec_fused(const VarTables& tb, const VarFuse& fz, cudaStream_t stream) {
   if (!tb.n_tiles) return cudaSuccess;
-  vdec_fused_kernel<<<min(tb.n_tiles, persistent_grid(vdec_fused_kernel)), kVarThreads, 0, stream>>>(tb, fz);
+  vdec_fused_kernel<<<min(tb.n_tiles, persistent_grid<1>(vdec_fused_kernel)), kVarThreads, 0, stream>>>(tb, fz);
   return cudaGetLastError();
 }
 cudaError_t launch_vdec_count(const VarTables& tb, cudaStream_t stream) {

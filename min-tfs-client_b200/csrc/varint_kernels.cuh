@@ -353,31 +353,27 @@ struct FuseJob {
   uint32_t n_tiles;
 };
 
-// Run by ONE warp of the CTA (all 32 lanes), the tile's bookkeeper, while the other warps do the tile's heavy work: lane 0
-// publishes the tile's count; if that completes the tile's group, the warp resolves the group (sum, AGG descriptor, decoupled
-// look-back over earlier groups, INC descriptor).  Returns the job's total in every lane when this warp resolved the job's LAST
+// Run by ONE warp of the CTA (all 32 lanes), the tile's bookkeeper, while the other warps do the tile's heavy work.  Lane 0
+// publishes the tile's count - one store, flag and count in the same word, so no fence and no atomic is needed anywhere in
+// this protocol (a __threadfence here waited for the PREVIOUS tile's streaming stores of the persistent CTA: 192 us instead of
+// 123).  The group's LAST tile (by ticket) resolves the group: it collects the 32 counts (all from earlier tickets, i.e. from
+// tiles that have started and publish before they wait for anything), publishes the AGG descriptor, looks back over earlier
+// groups and publishes the INC descriptor.  Returns the job's total in every lane when this warp resolved the job's LAST
 // group, else ~0ull.
 __device__ __forceinline__ unsigned long long fuse_publish_warp(const FuseJob& J, uint32_t t_rel, uint32_t count) {
   const uint32_t lane = threadIdx.x & 31;
-  const uint32_t g_rel = t_rel / kVarFuseGroup;
+  const uint32_t g_rel = t_rel / kVarFuseGroup, k_in = t_rel % kVarFuseGroup;
   const uint32_t n_groups = (J.n_tiles + kVarFuseGroup - 1) / kVarFuseGroup;
   const uint32_t in_group = min(kVarFuseGroup, J.n_tiles - g_rel * kVarFuseGroup);
-  uint32_t resolver = 0;
-  if (lane == 0) {
-    asm volatile("st.volatile.global.u32 [%0], %1;" :: "l"(J.tile_state + t_rel), "r"(kFuseFlag | count) : "memory");
-    __threadfence();
-    resolver = (atomicAdd(J.arrivals + g_rel, 1u) + 1u == in_group) ? 1u : 0u;
-  }
-  resolver = __shfl_sync(0xFFFFFFFFu, resolver, 0);
-  if (!resolver) return ~0ull;
+  if (lane == 0) asm volatile("st.volatile.global.u32 [%0], %1;" :: "l"(J.tile_state + t_rel), "r"(kFuseFlag | count) : "memory");
+  if (k_in + 1 != in_group) return ~0ull;
   uint32_t c = 0;
-  if (lane < in_group) c = ld_volatile_u32(J.tile_state + g_rel * kVarFuseGroup + lane) & ~kFuseFlag;
+  if (lane < k_in) { uint32_t v; do { v = ld_volatile_u32(J.tile_state + g_rel * kVarFuseGroup + lane); } while (!(v & kFuseFlag)); c = v & ~kFuseFlag; }
+  if (lane == k_in) c = count;
 #pragma unroll
   for (int d = 16; d; d >>= 1) c += __shfl_xor_sync(0xFFFFFFFFu, c, d);
-  if (lane == 0 && g_rel + 1 < n_groups) {
+  if (lane == 0 && g_rel + 1 < n_groups)
     asm volatile("st.volatile.global.u64 [%0], %1;" :: "l"(J.gs + g_rel), "l"(kFuseAgg | (unsigned long long)c) : "memory");
-    __threadfence();
-  }
   unsigned long long prefix = 0;
   int32_t look = (int32_t)g_rel - 1;
   while (look >= 0) {
@@ -393,24 +389,29 @@ __device__ __forceinline__ unsigned long long fuse_publish_warp(const FuseJob& J
     if (inc_mask) break;
     look -= 32;
   }
-  if (lane == 0) {
-    asm volatile("st.volatile.global.u64 [%0], %1;" :: "l"(J.gs + g_rel), "l"(kFuseInc | (prefix + c)) : "memory");
-    __threadfence();
-  }
+  if (lane == 0) asm volatile("st.volatile.global.u64 [%0], %1;" :: "l"(J.gs + g_rel), "l"(kFuseInc | (prefix + c)) : "memory");
   return (g_rel + 1 == n_groups) ? prefix + c : ~0ull;
 }
 
-// the bookkeeper warp: the counts of all tiles before t_rel = the previous group's inclusive prefix + the tiles before it inside
-// its group; valid in every lane
-__device__ __forceinline__ unsigned long long fuse_prefix_warp(const FuseJob& J, uint32_t t_rel) {
+// The counts of all tiles before t_rel = the previous group's inclusive prefix + the tiles before it inside its group, in two
+// steps so that the loads' round trip is spent under the tile's own work: fuse_prefix_issue right after the publication,
+// fuse_prefix_complete when the prefix is needed (it re-reads only what was not there yet).  Bookkeeper warp, all lanes.
+struct FusePending { unsigned long long d; uint32_t v; };
+__device__ __forceinline__ FusePending fuse_prefix_issue(const FuseJob& J, uint32_t t_rel) {
   const uint32_t lane = threadIdx.x & 31, g_rel = t_rel / kVarFuseGroup, k_in = t_rel % kVarFuseGroup;
-  unsigned long long before = 0;
-  if (g_rel > 0 && lane == 0) { unsigned long long d; do { d = ld_volatile_u64(J.gs + g_rel - 1); } while ((d >> 62) != 2); before = d & kFuseMask; }
-  uint32_t c = 0;
-  if (lane < k_in) { uint32_t v; do { v = ld_volatile_u32(J.tile_state + g_rel * kVarFuseGroup + lane); } while (!(v & kFuseFlag)); c = v & ~kFuseFlag; }
+  FusePending p{kFuseInc, kFuseFlag};
+  if (g_rel > 0 && lane == 0) p.d = ld_volatile_u64(J.gs + g_rel - 1);
+  if (lane < k_in) p.v = ld_volatile_u32(J.tile_state + g_rel * kVarFuseGroup + lane);
+  return p;
+}
+__device__ __forceinline__ unsigned long long fuse_prefix_complete(const FuseJob& J, uint32_t t_rel, FusePending p) {
+  const uint32_t lane = threadIdx.x & 31, g_rel = t_rel / kVarFuseGroup;
+  while ((p.d >> 62) != 2) p.d = ld_volatile_u64(J.gs + g_rel - 1);                               // lane 0 only can fail this
+  while (!(p.v & kFuseFlag)) p.v = ld_volatile_u32(J.tile_state + g_rel * kVarFuseGroup + lane);   // lanes < k_in only
+  uint32_t c = p.v & ~kFuseFlag;
 #pragma unroll
   for (int d = 16; d; d >>= 1) c += __shfl_xor_sync(0xFFFFFFFFu, c, d);
-  before = __shfl_sync(0xFFFFFFFFu, before, 0);
+  const unsigned long long before = __shfl_sync(0xFFFFFFFFu, p.d & kFuseMask, 0);
   return before + c;
 }
 
@@ -444,16 +445,21 @@ __global__ void __launch_bounds__(kVarThreads, 5) venc_fused_kernel(const __grid
     uint32_t total;
     uint64_t unused;
     const uint32_t off = block_scan_sum(sum, &total, 0ull, &unused, sh);
+    FusePending pend{};
+    uint32_t nxt = 0;
     if (warp == kKeeper) {
-      uint32_t nxt = 0;
       if (lane == 0) nxt = atomicAdd(fz.ticket, 1u);                      // the next tile's ticket: in flight while we work
       const unsigned long long job_total = fuse_publish_warp(J, t_rel, total);
       if (lane == 0 && job_total != ~0ull) *jb.total = job_total;         // the packed length: read by the framing kernel behind us
-      const unsigned long long b = fuse_prefix_warp(J, t_rel);
-      if (lane == 0) { s_base = b; s_next = nxt; }
+      pend = fuse_prefix_issue(J, t_rel);
     }
     venc_build_image(smem + 16, mine, lens, off);      // image at smem[16 ..): block -1 stays free for the realigning copy below
-    const uint64_t base = s_base;                      // (written before the keeper entered the build's barriers)
+    if (warp == kKeeper) {
+      const unsigned long long b = fuse_prefix_complete(J, t_rel, pend);
+      if (lane == 0) { s_base = b; s_next = nxt; }
+    }
+    __syncthreads();
+    const uint64_t base = s_base;
     if (base < jb.cap) {
       const uint32_t n_out = (uint32_t)min((uint64_t)total, jb.cap - base);
       // image bytes [0, n_out) at smem + 16  ->  g[0, n_out), g = jb.dst + base of any alignment
@@ -754,16 +760,16 @@ __global__ void __launch_bounds__(kVarThreads) vdec_fused_kernel(const __grid_co
     uint64_t tile_terms;
     const uint32_t rank = block_scan_sum(packed, &packed_total, (uint64_t)terms, &tile_terms, sh);
     const uint32_t first_total = packed_total & 0xFFFFu, n_here = first_total + (packed_total >> 16);
+    FusePending pend{};
+    uint32_t nxt = 0;
     if (warp == kKeeper) {
-      uint32_t nxt = 0;
       if (lane == 0) nxt = atomicAdd(fz.ticket, 1u);
       const unsigned long long job_total = fuse_publish_warp(J, t_rel, (uint32_t)tile_terms);
       if (lane == 0 && job_total != ~0ull) {
         *jb.total = job_total;
         if ((jb.flags & kVarFlagPadEdge) ? job_total > jb.n_elems : job_total != jb.n_elems) atomicMin(jb.status, B200TFS_E_SHAPE);   // reshape() would raise
       }
-      const unsigned long long b = fuse_prefix_warp(J, t_rel);
-      if (lane == 0) { s_base = b; s_next = nxt; }
+      pend = fuse_prefix_issue(J, t_rel);
     }
 #pragma unroll
     for (uint32_t r = 0; r < 2; ++r) {
@@ -774,6 +780,10 @@ __global__ void __launch_bounds__(kVarThreads) vdec_fused_kernel(const __grid_co
         starts &= starts - 1;
         start_at[at++] = (uint16_t)(at0 + i);
       }
+    }
+    if (warp == kKeeper) {
+      const unsigned long long b = fuse_prefix_complete(J, t_rel, pend);
+      if (lane == 0) { s_base = b; s_next = nxt; }
     }
     __syncthreads();
     // Phase 3 - the index of an element in the tensor is the number of terminators before it (+1 when a varint straddles in
