@@ -655,6 +655,8 @@ class HostLeg:
             for name in ("enc", "dec"):
                 ctx = C.c_void_p()
                 N.check(lib.b200tfs_create(db.device, C.byref(ctx)))
+                if depth > 1:      # the leg overlaps the copy directions ACROSS calls; slicing inside each call on top of that costs 3 %
+                    N.check(lib.b200tfs_set_pipeline(ctx, 0, 0))
                 L[name] = ctx
             ids = [db.lo + (d * sub + j) % db.n for j in range(sub)]
             first = db.host_in[wl.seed_of(ids[0])]
@@ -709,12 +711,14 @@ class HostLeg:
             N.check(lib.b200tfs_sync(L["enc"]))
             L["busy"] = False
 
-    def step(self):
+    def step(self, sequential=False):
         N, lib, db = self.N, self.lib, self.db
         L = self.lanes[self.k % self.depth]
         self.k += 1
         self._wait(L)
         N.check(lib.b200tfs_encode_requests_host_async(L["enc"], self.sub, L["rq"], L["wire"].ptr, L["wire_cap"], L["rec_off"], L["rec_len"]))
+        if sequential:      # a client: the request is on the wire before the response comes back
+            N.check(lib.b200tfs_sync(L["enc"]))
         if db.wl.out_dtype is None:
             N.check(lib.b200tfs_decode_responses_host_async(L["dec"], L["resp"].ptr, self.sub, L["roff"], L["rlen"], L["out"].ptr, db.dst_stride))
         else:       # cast on decode: the two-phase host entry points (parse synchronises)
@@ -765,15 +769,22 @@ def peaks():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
-def ncu_traffic(workload):
-    """dram read+write bytes per launch (averaged over the step's two kernels) from the newest committed ncu --set full
-    summary that has entries for this workload (profiles/rNN_ncu_summary.json, written by tools/ncu_summary.py)."""
+def ncu_traffic(workload, n_on_rank=None):
+    """dram read+write bytes per launch of the step's dominant kernel(s) (every captured kernel within 2x of the largest: the
+    C2 / C5 step has two, encode and decode; the C3 step one), averaged, from the newest committed ncu --set full summary that has
+    entries for this workload (profiles/rNN_ncu_summary.json, written by tools/ncu_summary.py).  C5 was captured on the per-GPU
+    share at N=8 (1024 requests); another share is scaled by its request count and says so."""
     import glob
 
     unit = {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+    tag, scale, note = workload, 1.0, None
+    if workload == "c5":
+        tag = "c5share"
+        if n_on_rank and n_on_rank != 1024:
+            scale, note = n_on_rank / 1024.0, f"captured on 1024 requests, scaled to this rank's {n_on_rank}"
     for path in sorted(glob.glob(os.path.join(REPO, "profiles", "r*_ncu_summary.json")), reverse=True):
         with open(path) as fh:
-            caps = [c for c in json.load(fh).get("full_capture", []) if c.get("workload", "c2_single") == workload]
+            caps = [c for c in json.load(fh).get("full_capture", []) if c.get("workload", "c2_single") == tag]
         per = {}
         for c in caps:
             r, w = c.get("dram__bytes_read.sum"), c.get("dram__bytes_write.sum")
@@ -781,7 +792,12 @@ def ncu_traffic(workload):
                 per.setdefault(c["kernel"], []).append(float(r["value"]) * unit.get(r["unit"], 1) + float(w["value"]) * unit.get(w["unit"], 1))
         if per:
             avg = {k: sum(v) / len(v) for k, v in per.items()}
-            return sum(avg.values()) / len(avg), {"source": os.path.relpath(path, REPO), "per_kernel_bytes": avg}
+            top = max(avg.values())
+            dom = {k: v * scale for k, v in avg.items() if v * 2 >= top}
+            src = {"source": os.path.relpath(path, REPO), "per_kernel_bytes": dom}
+            if note:
+                src["note"] = note
+            return sum(dom.values()) / len(dom), src
     return None, None
 
 
@@ -847,7 +863,7 @@ def run_workload(wl: Workload, world: World, steps, warmup, e2e_steps, full_veri
         else "parse_responses_kernel + move_kernel (OP_F2H / OP_F2B)"
     step_alg = enc_alg + dec_alg
     achieved = step_alg / ((t_enc + t_dec) * 1e-3) / 1e9 if db.n else 0.0
-    traffic, traffic_src = ncu_traffic(wl.name)
+    traffic, traffic_src = ncu_traffic(wl.name, db.n)
     roofline = {
         "bound": "hbm", "kernel": f"{enc_kernel} (encode) / {dec_kernel} (decode)", "achieved": achieved, "peak": peak, "unit": "GB/s",
         "frac": achieved / peak, "frac_of_nominal_8000": achieved / 8000.0, "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
@@ -886,8 +902,29 @@ def run_workload(wl: Workload, world: World, steps, warmup, e2e_steps, full_veri
                     "ms_per_step": e_ms / units * per_step_units, "requests_timed": units, "sub_batch": sub, "in_flight": depth,
                     "how": "b200tfs_encode_requests_host_async + b200tfs_decode_responses_host_async (+ b200tfs_decode_results) on pinned host buffers: "
                            "request tensors and response wires H2D, request wires and decoded tensors D2H, all inside the timed region; "
-                           f"sub-batches of {sub} requests, {depth} in flight on separate contexts so the two copy directions overlap"}
+                           f"sub-batches of {sub} requests, {depth} in flight on separate contexts so the two copy directions overlap "
+                           "(intra-call slicing switched off on these contexts: b200tfs_set_pipeline(ctx, 0, 0))"}
         leg.close()
+        if wl.name == "c2":
+            # ONE pair at a time, nothing else in flight: what a caller of the drop-in API sees on one request.  The two calls
+            # of the pair slice their copies and kernels over three streams each (b200tfs.h, "Pipelining inside ONE call").
+            one = HostLeg(db, 1, 1)
+            for _ in range(3):
+                one.step()
+            one.drain()
+            pairs = 50
+
+            def one_region(_):
+                for _k in range(pairs):
+                    one.step(sequential=True)
+                    one.drain()
+            o_ms = db.timer.run(one_region, 1)
+            calls = C.c_uint64()
+            db.N.check(db.lib.b200tfs_pipelined_calls(one.lanes[0]["enc"], C.byref(calls)))
+            e2e_line["one_pair_at_a_time"] = {"value": pairs * (db.src_bytes + db.dst_bytes) / (o_ms * 1e-3) / 1e9, "unit": "GB/s",
+                                              "us_per_pair": o_ms / pairs * 1e3, "in_flight": 1, "sliced_encode_calls": int(calls.value),
+                                              "how": "this rank only; encode one request (host waits), then decode one response (host waits): a client's sequence"}
+            one.close()
     # ---- parity, after the timed region ----
     parity = db.verify(full=full_verify)
     out = {"value": value, "ms_per_step": ms_max / steps, "gpu_launches": launches, "mode": mode, "roofline": roofline, "e2e": e2e_line,

@@ -374,7 +374,15 @@ int b200tfs_encode_requests_host(b200tfs_ctx* ctx, int32_t n, const b200tfs_requ
                                  uint64_t* rec_len);
 /* Same, but returns as soon as the copies and kernels are queued (it only blocks for the measure pass
  * when a varint dtype is present): call b200tfs_sync before reading wire_host, which must be pinned
- * (b200tfs_host_alloc).  Two contexts running the _async entry points overlap H2D with D2H.        */
+ * (b200tfs_host_alloc).  Two contexts running the _async entry points overlap H2D with D2H.
+ *
+ * Pipelining inside ONE call: a batch whose fixed-width payloads add up to at least 1 MiB (environment
+ * B200TFS_PIPELINE_MIN, bytes; 0 = never) is cut into up to 8 slices of consecutive wire bytes; the
+ * source bytes of slice k+1 travel host-to-device on a second stream while slice k is encoded and the
+ * wire bytes of slice k-1 travel device-to-host on a third, so a single large request keeps both PCIe
+ * directions busy.  The context's stream ends behind the last copy: b200tfs_sync (or an event recorded
+ * on the context) covers everything, as before.  b200tfs_decode_responses_host_async does the same
+ * for ONE response whose values lie in one fixed-width field.                                      */
 int b200tfs_encode_requests_host_async(b200tfs_ctx* ctx, int32_t n, const b200tfs_request* reqs,
                                        void* wire_host, uint64_t wire_cap, uint64_t* rec_off,
                                        uint64_t* rec_len);
@@ -384,6 +392,14 @@ int b200tfs_encode_requests_host_async(b200tfs_ctx* ctx, int32_t n, const b200tf
 int b200tfs_decode_responses_host_async(b200tfs_ctx* ctx, const void* wire_host, int32_t n,
                                         const uint64_t* rec_off, const uint64_t* rec_len,
                                         void* dst_host, uint64_t dst_stride);
+/* how many *_host_async calls of this context took the sliced, three-stream path so far            */
+int b200tfs_pipelined_calls(b200tfs_ctx* ctx, uint64_t* count);
+/* Tune it per context: calls moving fewer than min_bytes of fixed-width payload stay monolithic (0 = never slice), at most
+ * max_slices slices (2..8; default 4 - every slice costs about seven driver calls, ~7 us of host time).  A caller that keeps
+ * several contexts busy at once already overlaps the two copy directions ACROSS calls and should switch slicing off: measured
+ * on C2 with 8 contexts in flight, 40.2 GB/s monolithic vs 38.9 sliced; one call at a time: 177 -> 161 us (4 MiB), 2454 -> 1692 us
+ * (64 MiB) (profiles/r02_pipeline.md).                                                              */
+int b200tfs_set_pipeline(b200tfs_ctx* ctx, uint64_t min_bytes, int32_t max_slices);
 int b200tfs_encode_tensor_protos_host(b200tfs_ctx* ctx, int32_t n, const b200tfs_tensor* tensors,
                                       void* wire_host, uint64_t wire_cap, uint64_t* rec_off,
                                       uint64_t* rec_len);

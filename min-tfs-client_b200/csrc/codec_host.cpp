@@ -81,7 +81,13 @@ struct b200tfs_ctx {
   int sm_count = 148;
   cudaStream_t stream = nullptr;       // the stream every call is ordered on: the context's own, or the caller's (b200tfs_set_stream)
   cudaStream_t own_stream = nullptr;
-  cudaStream_t aux_stream = nullptr;   // uploads done at capture time, outside the graph being recorded
+  cudaStream_t aux_stream = nullptr;   // uploads done at capture time, outside the graph being recorded; the pipelined host path's H2D copies
+  cudaStream_t d2h_stream = nullptr;   // the pipelined host path's D2H copies
+  static constexpr int kPipeMax = 8;   // slices of one pipelined host call
+  cudaEvent_t pipe_ev[2 * kPipeMax + 2] = {};
+  uint64_t pipe_min = 1ull << 20;      // *_host calls moving at least this many payload bytes are sliced (B200TFS_PIPELINE_MIN; 0 = never)
+  int pipe_max = 4;                    // at most this many slices (B200TFS_PIPELINE_SLICES, 2..kPipeMax): every slice costs ~7 driver calls
+  uint64_t pipelined_calls = 0;        // how many host calls took the sliced path (tests)
   Slot slots[kSlots];
   int next_slot = 0;
   Growable scratch_dev;   // parse tables / varint tile tables
@@ -241,6 +247,13 @@ int b200tfs_create(int device, b200tfs_ctx** out) {
   c->opt_table_dev = od && od[0] == '1';
   e = cudaEventCreateWithFlags(&c->tpl_event, cudaEventDisableTiming);
   if (e != cudaSuccess) { delete c; return fail(B200TFS_E_CUDA, "cudaEventCreate: %s", cudaGetErrorString(e)); }
+  e = cudaStreamCreateWithFlags(&c->d2h_stream, cudaStreamNonBlocking);
+  for (auto& ev : c->pipe_ev) if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ev, cudaEventDisableTiming);
+  if (e != cudaSuccess) { delete c; return fail(B200TFS_E_CUDA, "pipeline stream / events: %s", cudaGetErrorString(e)); }
+  const char* pm = getenv("B200TFS_PIPELINE_MIN");
+  if (pm) c->pipe_min = strtoull(pm, nullptr, 10);
+  const char* ps = getenv("B200TFS_PIPELINE_SLICES");
+  if (ps) c->pipe_max = std::min<int>(b200tfs_ctx::kPipeMax, std::max(2, atoi(ps)));
   *out = c;
   return B200TFS_OK;
 }
@@ -271,6 +284,8 @@ int b200tfs_destroy(b200tfs_ctx* c) {
   if (c->arena_dev.p) cudaFree(c->arena_dev.p);
   cudaStreamDestroy(c->own_stream);
   if (c->aux_stream) cudaStreamDestroy(c->aux_stream);
+  if (c->d2h_stream) cudaStreamDestroy(c->d2h_stream);
+  for (auto& ev : c->pipe_ev) if (ev) cudaEventDestroy(ev);
   delete c;
   return B200TFS_OK;
 }
@@ -895,12 +910,9 @@ int b200tfs_encode_tensor_protos(b200tfs_ctx* c, int32_t n, const b200tfs_tensor
   return run_varjobs(c, pb);
 }
 
-int b200tfs_encode_requests(b200tfs_ctx* c, int32_t n, const b200tfs_request* reqs, void* arena_dev, uint64_t arena_cap,
-                            uint64_t* rec_off, uint64_t* rec_len) {
-  if (!c || n < 0 || (n && (!reqs || !arena_dev || !rec_off || !rec_len))) return fail(B200TFS_E_ARG, "bad arguments");
-  if ((uintptr_t)arena_dev & 255) return fail(B200TFS_E_ARG, "arena must be 256-byte aligned");
-  CU(cudaSetDevice(c->device));
-  PlanBuilder pb;
+// lay the batch out in the arena and collect its pieces (b200tfs_encode_requests launches them at once, the pipelined host path in slices)
+static int plan_requests(int32_t n, const b200tfs_request* reqs, void* arena_dev, uint64_t arena_cap, uint64_t* rec_off, uint64_t* rec_len,
+                         PlanBuilder& pb) {
   if (n > 16) {   // a batch: one allocation per table instead of a doubling series
     size_t inputs = 0;
     for (int i = 0; i < n; ++i) inputs += (size_t)std::max(reqs[i].n_inputs, 0);
@@ -919,8 +931,18 @@ int b200tfs_encode_requests(b200tfs_ctx* c, int32_t n, const b200tfs_request* re
     rec_off[i] = off; rec_len[i] = R.total;
     cursor = off + R.total;
   }
-  int rc = launch_plan(c, pb);
+  return B200TFS_OK;
+}
+
+int b200tfs_encode_requests(b200tfs_ctx* c, int32_t n, const b200tfs_request* reqs, void* arena_dev, uint64_t arena_cap,
+                            uint64_t* rec_off, uint64_t* rec_len) {
+  if (!c || n < 0 || (n && (!reqs || !arena_dev || !rec_off || !rec_len))) return fail(B200TFS_E_ARG, "bad arguments");
+  if ((uintptr_t)arena_dev & 255) return fail(B200TFS_E_ARG, "arena must be 256-byte aligned");
+  CU(cudaSetDevice(c->device));
+  PlanBuilder pb;
+  int rc = plan_requests(n, reqs, arena_dev, arena_cap, rec_off, rec_len, pb);
   if (rc) return rc;
+  if ((rc = launch_plan(c, pb))) return rc;
   return run_varjobs(c, pb);
 }
 
@@ -1260,9 +1282,18 @@ static bool host_template(const uint8_t* rec0, uint64_t len, uint32_t vpt, uint6
   return T->in.head.valid != 0;
 }
 
-// host_rec0: record 0's bytes in HOST memory when the caller has them (the *_host entry points), else nullptr
+// the pipelined host decode of ONE record: launch k covers tiles [tile_lo[k], tile_lo[k+1]) of the full grid (the last one also the
+// slack CTAs behind them), waits for before[k] and is followed by after[k] on the context's stream
+struct DecodeSlices {
+  int K = 0;
+  uint32_t tile_lo[b200tfs_ctx::kPipeMax + 1] = {};
+  cudaEvent_t* before = nullptr;
+  cudaEvent_t* after = nullptr;
+};
+
+// host_tpl: the template of record 0 as the HOST walked it, when the caller has the record's bytes (the *_host entry points), else nullptr
 static int decode_launch(b200tfs_ctx* c, const void* arena_dev, int32_t n, const uint64_t* rec_off, const uint64_t* rec_len, void* dst_dev,
-                         uint64_t dst_stride, uint32_t vpt, const Template* host_tpl) {
+                         uint64_t dst_stride, uint32_t vpt, const Template* host_tpl, const DecodeSlices* sl = nullptr) {
   const uint64_t tile_bytes = 16ull * vpt;
   FusedLayout L = fused_layout(n);
   int rc;
@@ -1341,8 +1372,21 @@ static int decode_launch(b200tfs_ctx* c, const void* arena_dev, int32_t n, const
     fp.rec_off = (const uint64_t*)(sd + o_off); fp.rec_len = (const uint64_t*)(sd + o_len);
   }
   if (grid > 0x7FFFFFFFull) return fail(B200TFS_E_TOOBIG, "batch needs more than 2^31 tiles");
-  CU(launch_decode_fused(fp, (uint32_t)grid, c->stream));
-  c->launches += 1;
+  if (sl) {
+    if (n != 1 || !fp.tpli.head.valid) return fail(B200TFS_E_ARG, "internal: sliced decode without a host template");
+    fp.trusted = 1;
+    for (int k = 0; k < sl->K; ++k) {
+      CU(cudaStreamWaitEvent(c->stream, sl->before[k], 0));
+      fp.tile_bias = sl->tile_lo[k];
+      const uint32_t end = (k + 1 == sl->K) ? (uint32_t)grid : sl->tile_lo[k + 1];
+      CU(launch_decode_fused(fp, end - sl->tile_lo[k], c->stream));
+      CU(cudaEventRecord(sl->after[k], c->stream));
+      c->launches += 1;
+    }
+  } else {
+    CU(launch_decode_fused(fp, (uint32_t)grid, c->stream));
+    c->launches += 1;
+  }
   c->fused_n = n;
   if (!c->capturing) { CU(cudaEventRecord(c->tpl_event, c->stream)); c->tpl_event_pending = true; }
   return B200TFS_OK;
@@ -1447,8 +1491,12 @@ uint64_t tensor_src_bytes(const b200tfs_tensor& t) {
   return n * dtype_info(t.src_dtype).elem_size;
 }
 
-// copy every tensor of the batch to the device staging buffer, returning device-pointing clones
-int stage_tensors(b200tfs_ctx* c, std::vector<b200tfs_tensor>& ts) {
+// one host tensor's place in the device staging buffer
+struct StagePiece { const uint8_t* dev; const uint8_t* host; uint64_t nb; };
+
+// Give every tensor of the batch a place in the device staging buffer and return device-pointing clones.  `defer` == nullptr:
+// the copies are queued on the context's stream right here; else they are only listed (the pipelined path issues them in slices).
+int stage_tensors(b200tfs_ctx* c, std::vector<b200tfs_tensor>& ts, std::vector<StagePiece>* defer = nullptr) {
   uint64_t total = 0;
   for (auto& t : ts) {
     if (!(t.flags & B200TFS_F_PRESERIALIZED)) {
@@ -1469,11 +1517,111 @@ int stage_tensors(b200tfs_ctx* c, std::vector<b200tfs_tensor>& ts) {
     uint64_t nb = tensor_src_bytes(t);
     if (nb) {
       if (!t.data) return fail(B200TFS_E_ARG, "tensor data pointer is NULL");
-      CU(cudaMemcpyAsync((uint8_t*)c->stage_dev.p + cur, t.data, nb, cudaMemcpyHostToDevice, c->stream));
+      if (defer) defer->push_back(StagePiece{(const uint8_t*)c->stage_dev.p + cur, (const uint8_t*)t.data, nb});
+      else CU(cudaMemcpyAsync((uint8_t*)c->stage_dev.p + cur, t.data, nb, cudaMemcpyHostToDevice, c->stream));
     }
     t.data = (uint8_t*)c->stage_dev.p + cur;
     cur += nb;
   }
+  return B200TFS_OK;
+}
+
+bool needs_measure(const std::vector<b200tfs_tensor>& ts) {
+  for (auto& t : ts)
+    if (!(t.flags & (B200TFS_F_PRESERIALIZED | B200TFS_F_TENSOR_CONTENT)) && dtype_info(t.wire_dtype).kind == VK_VARINT) return true;
+  return false;
+}
+
+// source bytes per output byte of a move op, as a fraction num/den; 0/0: the op cannot be cut
+void op_ratio(uint32_t op, uint32_t* num, uint32_t* den) {
+  switch (op) {
+    case OP_COPY: case OP_QUIET_SRC: case OP_QUIET_DST: case OP_BOOL: *num = 1; *den = 1; break;
+    case OP_H2F: case OP_B2F: *num = 1; *den = 2; break;
+    case OP_F2H: case OP_F2B: *num = 2; *den = 1; break;
+    default: *num = 0; *den = 0; break;
+  }
+}
+
+// The pipelined encode: the batch's large payloads are cut into up to kPipeMax slices of consecutive wire bytes; slice k's source
+// bytes travel H2D on one stream while slice k-1 is being encoded on the context's stream and slice k-2's wire bytes travel D2H on
+// a third - one big request alone keeps both PCIe directions busy (monolithic H2D -> kernel -> D2H).
+// Framing bytes and small payloads go with slice 0.  Returns B200TFS_OK with *done = false when the batch does not qualify.
+int encode_pipelined(b200tfs_ctx* c, PlanBuilder& pb, const std::vector<StagePiece>& pieces, uint8_t* wire_host, uint64_t lo, uint64_t hi,
+                     bool* done) {
+  *done = false;
+  if (!c->pipe_min || pb.large_bytes < c->pipe_min || !pb.varjobs.empty() || pb.items.empty()) return B200TFS_OK;
+  for (auto& it : pb.items) {
+    uint32_t num, den;
+    op_ratio(it.op, &num, &den);
+    if (!num || it.glen) return B200TFS_OK;
+  }
+  int K = (int)std::min<uint64_t>(c->pipe_max, std::max<uint64_t>(2, pb.large_bytes / std::max<uint64_t>(c->pipe_min, 1ull << 18)));
+  const uint64_t per = ((pb.large_bytes + K - 1) / K + 65535) & ~65535ull;    // output bytes per slice, cut on 64 KB
+  const uint8_t* arena = (const uint8_t*)c->arena_dev.p;
+  // which piece feeds an item: the one that contains its source (device-resident inputs have none)
+  auto piece_of = [&](const uint8_t* src) -> const StagePiece* {
+    for (auto& p : pieces) if (src >= p.dev && src < p.dev + p.nb) return &p;
+    return nullptr;
+  };
+  std::vector<const StagePiece*> feeds(pb.items.size());
+  std::vector<char> is_large(pieces.size(), 0);
+  for (size_t i = 0; i < pb.items.size(); ++i) {
+    feeds[i] = piece_of(pb.items[i].src);
+    if (feeds[i]) is_large[feeds[i] - pieces.data()] = 1;
+  }
+  // everything queued on this context so far (the previous call's kernels read the staging buffer) precedes our copies
+  cudaEvent_t* ev = c->pipe_ev;
+  CU(cudaEventRecord(ev[2 * b200tfs_ctx::kPipeMax], c->stream));
+  CU(cudaStreamWaitEvent(c->aux_stream, ev[2 * b200tfs_ctx::kPipeMax], 0));
+  CU(cudaStreamWaitEvent(c->d2h_stream, ev[2 * b200tfs_ctx::kPipeMax], 0));
+  size_t item = 0;
+  uint64_t item_done = 0;        // output bytes of pb.items[item] already handed to a slice
+  uint64_t wire_done = lo;       // arena offset up to which the wire has been copied back
+  int rc;
+  for (int k = 0; k < K && (item < pb.items.size() || k == 0); ++k) {
+    PlanBuilder sub;
+    if (k == 0) {
+      sub.smalls.swap(pb.smalls);
+      sub.blob.swap(pb.blob);
+      for (size_t q = 0; q < pieces.size(); ++q)     // sources of small payloads
+        if (!is_large[q]) CU(cudaMemcpyAsync((void*)pieces[q].dev, pieces[q].host, pieces[q].nb, cudaMemcpyHostToDevice, c->aux_stream));
+    }
+    uint64_t room = per;
+    uint64_t wire_end = wire_done;
+    while (item < pb.items.size() && room) {
+      const MoveItem& it = pb.items[item];
+      uint32_t num, den;
+      op_ratio(it.op, &num, &den);
+      const bool last_slice = (k == K - 1);
+      uint64_t take = std::min<uint64_t>(it.n_out - item_done, last_slice ? ~0ull : room);
+      if (take < it.n_out - item_done) take &= ~1023ull;     // cuts fall on 1 KB of output: whole elements and whole 16-byte vectors of either side
+      if (!take) break;
+      if (!last_slice) room -= std::min(room, take);
+      const uint64_t s_off = item_done * num / den, s_len = take * num / den;
+      if (feeds[item])
+        CU(cudaMemcpyAsync((void*)(it.src + s_off), feeds[item]->host + (it.src + s_off - feeds[item]->dev), s_len, cudaMemcpyHostToDevice, c->aux_stream));
+      sub.payload(it.src + s_off, it.dst + item_done, take, it.op);
+      wire_end = (uint64_t)(it.dst + item_done + take - arena);
+      item_done += take;
+      if (item_done == it.n_out) { ++item; item_done = 0; }
+    }
+    const bool final_slice = item >= pb.items.size();
+    if (final_slice) wire_end = hi;
+    CU(cudaEventRecord(ev[2 * k], c->aux_stream));
+    CU(cudaStreamWaitEvent(c->stream, ev[2 * k], 0));
+    if ((rc = launch_plan(c, sub))) return rc;
+    CU(cudaEventRecord(ev[2 * k + 1], c->stream));
+    CU(cudaStreamWaitEvent(c->d2h_stream, ev[2 * k + 1], 0));
+    if (wire_end > wire_done)
+      CU(cudaMemcpyAsync(wire_host + (wire_done - lo), arena + wire_done, wire_end - wire_done, cudaMemcpyDeviceToHost, c->d2h_stream));
+    wire_done = wire_end;
+    if (final_slice) break;
+  }
+  // the context's stream is where callers wait: it ends behind the last copy
+  CU(cudaEventRecord(ev[2 * b200tfs_ctx::kPipeMax + 1], c->d2h_stream));
+  CU(cudaStreamWaitEvent(c->stream, ev[2 * b200tfs_ctx::kPipeMax + 1], 0));
+  c->pipelined_calls += 1;
+  *done = true;
   return B200TFS_OK;
 }
 
@@ -1513,20 +1661,53 @@ int b200tfs_encode_requests_host_async(b200tfs_ctx* c, int32_t n, const b200tfs_
     if (reqs[i].n_inputs < 0 || (reqs[i].n_inputs && !reqs[i].inputs)) return fail(B200TFS_E_ARG, "bad request %d", i);
     ts.insert(ts.end(), reqs[i].inputs, reqs[i].inputs + reqs[i].n_inputs);
   }
-  int rc = stage_tensors(c, ts);
+  // a batch without packed-varint inputs may take the pipelined path: its H2D copies are then issued slice by slice
+  const bool try_pipe = c->pipe_min && !c->capturing && !needs_measure(ts);
+  std::vector<StagePiece> pieces;
+  int rc = stage_tensors(c, ts, try_pipe ? &pieces : nullptr);
   if (rc) return rc;
-  if ((rc = b200tfs_measure(c, (int32_t)ts.size(), ts.data()))) return rc;  // synchronises only if a varint dtype is present
+  if (!try_pipe && (rc = b200tfs_measure(c, (int32_t)ts.size(), ts.data()))) return rc;  // synchronises only if a varint dtype is present
   std::vector<b200tfs_request> rq(reqs, reqs + n);
   size_t k = 0;
   for (int i = 0; i < n; ++i) { rq[i].inputs = ts.data() + k; k += (size_t)rq[i].n_inputs; }
   uint64_t need = 0;
   if ((rc = b200tfs_request_arena_size(n, rq.data(), &need))) return rc;
   if ((rc = grow_dev(c, c->arena_dev, need))) return rc;
+  if (try_pipe) {
+    PlanBuilder pb;
+    if ((rc = plan_requests(n, rq.data(), c->arena_dev.p, c->arena_dev.cap, rec_off, rec_len, pb))) return rc;
+    const uint64_t lo = rec_off[0], hi = rec_off[n - 1] + rec_len[n - 1];
+    if (hi - lo > wire_cap) return fail(B200TFS_E_SIZE, "wire buffer too small: need %llu bytes", (unsigned long long)(hi - lo));
+    bool done = false;
+    if ((rc = encode_pipelined(c, pb, pieces, (uint8_t*)wire_host, lo, hi, &done))) return rc;
+    if (!done) {   // too small to be worth slicing: everything on the context's stream, as one piece
+      for (auto& p : pieces) CU(cudaMemcpyAsync((void*)p.dev, p.host, p.nb, cudaMemcpyHostToDevice, c->stream));
+      if ((rc = launch_plan(c, pb))) return rc;
+      if ((rc = run_varjobs(c, pb))) return rc;
+      CU(cudaMemcpyAsync(wire_host, (uint8_t*)c->arena_dev.p + lo, hi - lo, cudaMemcpyDeviceToHost, c->stream));
+    }
+    for (int i = 0; i < n; ++i) rec_off[i] -= lo;
+    return B200TFS_OK;
+  }
   if ((rc = b200tfs_encode_requests(c, n, rq.data(), c->arena_dev.p, c->arena_dev.cap, rec_off, rec_len))) return rc;
   const uint64_t lo = rec_off[0], hi = rec_off[n - 1] + rec_len[n - 1];
   if (hi - lo > wire_cap) return fail(B200TFS_E_SIZE, "wire buffer too small: need %llu bytes", (unsigned long long)(hi - lo));
   CU(cudaMemcpyAsync(wire_host, (uint8_t*)c->arena_dev.p + lo, hi - lo, cudaMemcpyDeviceToHost, c->stream));
   for (int i = 0; i < n; ++i) rec_off[i] -= lo;
+  return B200TFS_OK;
+}
+
+int b200tfs_pipelined_calls(b200tfs_ctx* c, uint64_t* count) {
+  if (!c || !count) return fail(B200TFS_E_ARG, "bad arguments");
+  *count = c->pipelined_calls;
+  return B200TFS_OK;
+}
+
+int b200tfs_set_pipeline(b200tfs_ctx* c, uint64_t min_bytes, int32_t max_slices) {
+  if (!c) return fail(B200TFS_E_ARG, "ctx is NULL");
+  if (min_bytes && (max_slices < 2 || max_slices > b200tfs_ctx::kPipeMax)) return fail(B200TFS_E_ARG, "max_slices must be in [2, %d]", b200tfs_ctx::kPipeMax);
+  c->pipe_min = min_bytes;
+  if (min_bytes) c->pipe_max = max_slices;
   return B200TFS_OK;
 }
 
@@ -1595,10 +1776,52 @@ int b200tfs_decode_responses_host_async(b200tfs_ctx* c, const void* wire_host, i
   for (int i = 0; i < n; ++i) hi = std::max(hi, rec_off[i] + rec_len[i]);
   int rc = grow_dev(c, c->stage_dev, hi + 64);
   if (rc) return rc;
-  if (hi) CU(cudaMemcpyAsync((uint8_t*)c->stage_dev.p + shift, wire_host, hi, cudaMemcpyHostToDevice, c->stream));
   c->stage_shift = shift;
   if ((rc = grow_dev(c, c->arena_dev, dst_stride * (uint64_t)n + 256))) return rc;
-  if ((rc = decode_launch(c, (uint8_t*)c->stage_dev.p + shift, n, rec_off, rec_len, c->arena_dev.p, dst_stride, vpt, have ? &T : nullptr))) return rc;
+  uint8_t* wire_dev = (uint8_t*)c->stage_dev.p + shift;
+  // One large record whose values lie in one fixed-width chunk: slices of tiles, pipelined like the encode (wire bytes of slice
+  // k+1 travel H2D while slice k is decoded and the tensor bytes of slice k-1 travel D2H).  The kernel skips its framing verdict:
+  // the template was built from these very bytes, and a slice runs before the record's tail has arrived.
+  const TplChunk& ch = T.in.chunk[0];
+  const uint64_t tile_bytes = 16ull * vpt;
+  if (have && n == 1 && c->pipe_min && rec_len[0] >= c->pipe_min && !c->opt_no_inline && T.in.head.n_chunks == 1 && !ch.is_varint &&
+      (ch.op == OP_COPY || ch.op == OP_QUIET_DST) && ch.n_tiles >= 2 && ch.n_tiles == T.in.head.total_tiles) {
+    DecodeSlices sl;
+    sl.K = (int)std::min<uint64_t>(std::min<uint64_t>(c->pipe_max, ch.n_tiles),
+                                   std::max<uint64_t>(2, rec_len[0] / std::max<uint64_t>(c->pipe_min, 1ull << 18)));
+    for (int k = 0; k <= sl.K; ++k) sl.tile_lo[k] = (uint32_t)((uint64_t)ch.n_tiles * k / sl.K);
+    cudaEvent_t* ev = c->pipe_ev;
+    sl.before = ev; sl.after = ev + b200tfs_ctx::kPipeMax;
+    CU(cudaEventRecord(ev[2 * b200tfs_ctx::kPipeMax], c->stream));
+    CU(cudaStreamWaitEvent(c->aux_stream, ev[2 * b200tfs_ctx::kPipeMax], 0));
+    CU(cudaStreamWaitEvent(c->d2h_stream, ev[2 * b200tfs_ctx::kPipeMax], 0));
+    uint64_t wire_done = 0;
+    for (int k = 0; k < sl.K; ++k) {
+      // tiles below tile_lo[k+1] read no further than 48 bytes past their last vector (the next 16-byte block of a shifted source)
+      const uint64_t w_end = (k + 1 == sl.K) ? hi : std::min<uint64_t>(hi, rec_off[0] + ch.wire_off + sl.tile_lo[k + 1] * tile_bytes + 64);
+      if (w_end > wire_done)
+        CU(cudaMemcpyAsync(wire_dev + wire_done, (const uint8_t*)wire_host + wire_done, w_end - wire_done, cudaMemcpyHostToDevice, c->aux_stream));
+      wire_done = std::max(wire_done, w_end);
+      CU(cudaEventRecord(sl.before[k], c->aux_stream));
+    }
+    if ((rc = decode_launch(c, wire_dev, n, rec_off, rec_len, c->arena_dev.p, dst_stride, vpt, &T, &sl))) return rc;
+    const uint64_t need = std::min<uint64_t>(dst_stride, T.in.head.dst_need);
+    uint64_t dst_done = 0;
+    for (int k = 0; k < sl.K; ++k) {
+      // tiles below tile_lo[k+1] have written every byte of the slot below the first vector of tile tile_lo[k+1]
+      const uint64_t d_end = (k + 1 == sl.K) ? need : std::min<uint64_t>(need, ch.dst_off + sl.tile_lo[k + 1] * tile_bytes);
+      CU(cudaStreamWaitEvent(c->d2h_stream, sl.after[k], 0));
+      if (d_end > dst_done)
+        CU(cudaMemcpyAsync((uint8_t*)dst_host + dst_done, (uint8_t*)c->arena_dev.p + dst_done, d_end - dst_done, cudaMemcpyDeviceToHost, c->d2h_stream));
+      dst_done = std::max(dst_done, d_end);
+    }
+    CU(cudaEventRecord(ev[2 * b200tfs_ctx::kPipeMax + 1], c->d2h_stream));
+    CU(cudaStreamWaitEvent(c->stream, ev[2 * b200tfs_ctx::kPipeMax + 1], 0));
+    c->pipelined_calls += 1;
+    return B200TFS_OK;
+  }
+  if (hi) CU(cudaMemcpyAsync(wire_dev, wire_host, hi, cudaMemcpyHostToDevice, c->stream));
+  if ((rc = decode_launch(c, wire_dev, n, rec_off, rec_len, c->arena_dev.p, dst_stride, vpt, have ? &T : nullptr))) return rc;
   CU(cudaMemcpyAsync(dst_host, c->arena_dev.p, dst_stride * (uint64_t)n, cudaMemcpyDeviceToHost, c->stream));
   return B200TFS_OK;
 }

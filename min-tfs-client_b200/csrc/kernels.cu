@@ -899,7 +899,7 @@ __device__ __forceinline__ void decode_fused_body(const FusedParams& fp) {
     for (uint32_t q = 0; q < kStageBufs; ++q) mbar_init(&stage_bars[q], 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  const uint32_t b = blockIdx.x;
+  const uint32_t b = blockIdx.x + fp.tile_bias;
   uint32_t r, j, budget;
   uint64_t off, len;
   if (fp.n <= kFusedInlineRecs) {
@@ -944,6 +944,7 @@ __device__ __forceinline__ void decode_fused_body(const FusedParams& fp) {
       // stores it while other warps' loads are still in flight, as in the plain move.
       auto verdict = [&]() -> bool {
         bool same = true;
+        if (!STAGED && fp.trusted && inl) return true;
         if (STAGED) {
           if (i < th_s.framing_len) {
             uint32_t w = i;
