@@ -1314,7 +1314,6 @@ static int decode_launch(b200tfs_ctx* c, const void* arena_dev, int32_t n, const
   fp.stats = (unsigned long long*)((uint8_t*)c->tpl_dev + 2 * sizeof(Template));
   if (++c->serial == 0) c->serial = 1;
   fp.serial = c->serial;
-  { static const uint32_t exp = [] { const char* e = getenv("B200TFS_EXP"); return e ? (uint32_t)atoi(e) : 0u; }(); fp.experiment = exp; }
   fp.tpli.head.valid = 0;
   if (vpt <= kStageVecsHost) {   // the single-response / small-batch kernel takes its template from the parameters when the host has one
     if (host_tpl && host_tpl->in.head.valid) {

@@ -456,92 +456,14 @@ __device__ __forceinline__ bool move_tile(const uint8_t* __restrict__ src, uint8
 }
 
 // ------------------------------------------------------------------------------------------------
-// decode_tile: the single-response decode's tile move (OP_COPY / OP_QUIET_DST only), written for CODE SIZE: one load phase
-// (each warp owns a contiguous run, as in body_shifted_q), the verdict hook once, one store phase in which source alignment
-// (which of the 8 words of two neighbouring blocks an output word starts in, and the bit shift) and the sNaN fix-up are
-// run-time values behind warp-uniform branches instead of template instantiations.  ~6 KB of SASS where the fully templated
-// move_tile with the verdict inlined into every body took ~240 KB - and the launch ~1 us longer, spent fetching instructions.
-// ------------------------------------------------------------------------------------------------
-__device__ __forceinline__ uint8_t gen_byte_dec(bool quiet, const uint8_t* src, uint64_t i) {
-  if (!quiet) return src[i];
-  const uint32_t w = quiet_f32(ld_u32_bytes(src + (i & ~3ull)));
-  return (uint8_t)(w >> (8 * (i & 3)));
-}
-
+// a source alignment known only at run time (warp-uniform): which of the 8 words of two neighbouring blocks an output word starts in
 __device__ __forceinline__ uint4 shift_pair_dyn(const uint4& lo, const uint4& hi, uint32_t q, uint32_t s) {
-  switch (q) {   // warp-uniform
+  switch (q) {
     case 0: return shift_pair<0>(lo, hi, s);
     case 1: return shift_pair<1>(lo, hi, s);
     case 2: return shift_pair<2>(lo, hi, s);
     default: return shift_pair<3>(lo, hi, s);
   }
-}
-
-template <class Mid>
-__device__ __forceinline__ bool decode_tile(const uint8_t* __restrict__ src, uint8_t* __restrict__ dst, uint64_t n_out, bool quiet,
-                                            uint32_t n_tiles, uint32_t tile, uint32_t vpt, Mid& mid) {
-  const bool last = (tile + 1 == n_tiles);
-  uint64_t head = (16 - ((uintptr_t)dst & 15)) & 15;
-  if (head > n_out) head = n_out;
-  const uint8_t* src_body = src + head;
-  const uint32_t k = (uint32_t)((uintptr_t)src_body & 15);
-  uint64_t nvec = (n_out - head) >> 4;
-  if (k) {  // block v+1 is read as well: keep it inside the source
-    const uint64_t blocks = (uint64_t)((src + n_out) - (src_body - k)) >> 4;
-    const uint64_t lim = blocks ? blocks - 1 : 0;
-    if (nvec > lim) nvec = lim;
-  }
-  if (quiet && (head & 3)) {   // float elements do not line up with the destination vectors: byte path (never for 256-aligned slots)
-    if (!mid()) return false;
-    const uint64_t b0 = (uint64_t)tile * vpt * 16;
-    uint64_t b1 = b0 + (uint64_t)vpt * 16;
-    if (b1 > n_out || last) b1 = n_out;
-    for (uint64_t i = b0 + threadIdx.x; i < b1; i += blockDim.x) dst[i] = gen_byte_dec(true, src, i);
-    return true;
-  }
-  const uint64_t v0 = (uint64_t)tile * vpt;
-  if (v0 < nvec) {
-    const uint32_t n = (uint32_t)min((uint64_t)vpt, nvec - v0);
-    const uint8_t* S = src_body - k + 16 * v0;
-    uint8_t* d = dst + head + 16 * v0;
-    const uint32_t s = (k & 3) * 8, q = k >> 2;
-    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    constexpr uint32_t kRun = kBatchShift * 32, kRound = kRun * (kMoveThreads / 32);
-    for (uint32_t base = 0; base < n; base += kRound) {            // uniform trip count across the CTA
-      const uint32_t run = base + warp * kRun;
-      const uint32_t run_end = min(run + kRun, n);
-      uint4 lo[kBatchShift], extra = make_uint4(0, 0, 0, 0);
-#pragma unroll
-      for (uint32_t i = 0; i < kBatchShift; ++i) {
-        const uint32_t u = run + 32 * i + lane;
-        lo[i] = make_uint4(0, 0, 0, 0);
-        if (u < n) lo[i] = ld_stream(S + 16ull * u);
-      }
-      if (k && lane == 0 && run < n) extra = ld_stream(S + 16ull * run_end);
-      if (base == 0 && !mid()) return false;
-      extra = shfl_lane0(extra);
-#pragma unroll
-      for (uint32_t i = 0; i < kBatchShift; ++i) {
-        const uint32_t u = run + 32 * i + lane;
-        uint4 b = shfl_down1(lo[i]);                               // lanes 0..30: neighbour's block
-        if (i + 1 < kBatchShift) {
-          const uint4 nxt = shfl_lane0(lo[i + 1]);                 // lane 31: first block of the next element
-          if (lane == 31) b = nxt;
-        }
-        if (u + 1 == run_end) b = extra;                           // last vector of the run (or of a ragged tile)
-        if (u < n) {
-          uint4 o = lo[i];
-          if (k) o = shift_pair_dyn(lo[i], b, q, s);
-          if (quiet) o = fix_vec<OP_QUIET_DST>(o);
-          st_stream(d + 16ull * u, o);
-        }
-      }
-    }
-  } else if (!mid()) return false;
-  // ragged edges, element-exact
-  if (tile == 0) for (uint64_t i = threadIdx.x; i < head; i += blockDim.x) dst[i] = gen_byte_dec(quiet, src, i);
-  if (last) for (uint64_t i = head + (nvec << 4) + threadIdx.x; i < n_out; i += blockDim.x) dst[i] = gen_byte_dec(quiet, src, i);
-  return true;
 }
 
 // one out-of-line copy of the decode-side tile move for the paths where speed is not the point (a walked record, a staged
@@ -975,7 +897,6 @@ __device__ __forceinline__ void decode_fused_body(const FusedParams& fp) {
       // CTAs of a 602 KB record are slack: leave now, before the verdict's round trip.  Should the record fail the
       // verdict after all, the CTAs that stayed walk it; if it then needs more tiles than stayed, its status says so.
       if (mine == kTplChunks && j != 0 && j != budget - 1) return;
-      if (fp.experiment == 2 && mine == kTplChunks) return;     // experiment: no publisher at all
       live = max(th_s.total_tiles, 1u);
       bool hit;
       if (STAGED) {
@@ -996,11 +917,11 @@ __device__ __forceinline__ void decode_fused_body(const FusedParams& fp) {
         if (!hit) staged_drain(stg, stage_bars, 0);   // let the copies land, then walk the record
       } else if (mine < kTplChunks) {
         // the tile's loads go out first; the verdict runs while they are in flight and decides whether anything is stored
-        hit = decode_tile(rec + ch_s[mine].wire_off, dst_slot + ch_s[mine].dst_off, ch_s[mine].len, ch_s[mine].op == OP_QUIET_DST,
-                          ch_s[mine].n_tiles, j - t_base, fp.vpt, verdict);
+        hit = move_tile<true>(rec + ch_s[mine].wire_off, dst_slot + ch_s[mine].dst_off, ch_s[mine].len, ch_s[mine].op, ch_s[mine].n_tiles,
+                              j - t_base, fp.vpt, verdict);
       } else hit = verdict();
       if (hit) {
-        if (j == budget - 1 && fp.experiment != 1) {   // the record's last CTA - a slack CTA with no tile - publishes the table, so no tile waits on it
+        if (j == budget - 1) {   // the record's last CTA - a slack CTA with no tile - publishes the table, so no tile waits on it
           // the table entries live in the device template; an inline template vouches for them only if both carry the same serial
           const bool table_ok = !inl || (T->in.head.valid && T->in.head.serial == th_s.serial);
           if (table_ok) {
@@ -1013,9 +934,7 @@ __device__ __forceinline__ void decode_fused_body(const FusedParams& fp) {
             if (r == 0 && !(fp.tpl_write->in.head.valid && fp.tpl_write->in.head.serial == T->in.head.serial))
               publish_words(fp.tpl_write, T, (uint32_t)sizeof(Template));
           } else if (threadIdx.x == 0) {
-#ifndef B200TFS_EXPERIMENT_NO_WALK
             fused_slow_path(fp, r, 0, budget, true, rec, len, dst_slot, lines, outs_s, spec_s, job);   // walk for the table only
-#endif
           }
         }
         return;
@@ -1024,12 +943,7 @@ __device__ __forceinline__ void decode_fused_body(const FusedParams& fp) {
   }
 
   // ---- the walk: thread 0 goes through the tags ----
-#ifdef B200TFS_EXPERIMENT_NO_WALK   // code-size experiment (tools/decode_latency_probe.py): a record that misses the template is refused
-  if (threadIdx.x == 0) { job.valid = 0; if (j == 0) { fp.status[r] = B200TFS_E_NONCANONICAL; fp.n_outs[r] = 0; } }
-  (void)live;
-#else
   if (threadIdx.x == 0) fused_slow_path(fp, r, j, live, j == 0, rec, len, dst_slot, lines, outs_s, spec_s, job);
-#endif
   __syncthreads();
   if (job.valid) {
     if (job.gstride) move_tile_gather(SrcView{job.src, job.glen, job.gstride}, job.dst, job.n_out, job.op, job.n_tiles, job.tile, fp.vpt);

@@ -107,7 +107,7 @@ struct FusedParams {
   TplInline* tpl_pinned;     // pinned host copy of the inline part, written whenever a template is learnt (valid flag last)
   unsigned long long* stats; // device counters: records served by [0] the template in the parameters, [1] the device template, [2] the walk
   uint32_t serial;           // stamp for a template learnt by THIS launch
-  uint32_t experiment;       // timing experiments only (B200TFS_EXP): 1 = the record's last CTA skips publishing the table on a template hit
+  uint32_t pad0;
   uint32_t tile_bias;        // a SLICE of a one-record launch (the pipelined host path): CTA b works as CTA b + tile_bias of the full grid
   uint32_t trusted;          // != 0: the host built the inline template from THIS record's own bytes: no verdict (a slice's launch runs
                              // before the record's tail - and with it part of the framing - has arrived on the device)

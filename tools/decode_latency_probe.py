@@ -28,9 +28,6 @@ VARIANTS = [
     ("16 KB tiles (272 CTAs)", {"B200TFS_TILE_BYTES": "16384"}),
     ("8 KB tiles (544 CTAs)", {"B200TFS_TILE_BYTES": "8192"}),
     ("64 KB tiles (72 CTAs)", {"B200TFS_TILE_BYTES": "65536"}),
-    ("template seeded by a host walk (control for the next row)", {"B200TFS_BENCH_SEED_TEMPLATE": "1"}),
-    ("kernels built WITHOUT the tag walk (decode_fused_kernel 51 KB instead of 315 KB of SASS)",
-     {"B200TFS_BENCH_SEED_TEMPLATE": "1", "B200TFS_LIB": os.path.join(REPO, "min-tfs-client_b200", "lib", "libb200tfs_nowalk.so")}),
 ]
 
 

@@ -67,7 +67,7 @@ def main():
     report = {"size_mib": args.size_mib, "seconds_per_mode": args.seconds, "runs": []}
     counts = [c for c in (1, 2, 4, 8) if c <= total]
     for count in counts:
-        t = time.time() + 25.0      # process start (imports, pinned allocations) takes a while: a generous common start time
+        t = time.time() + 14.0      # process start (imports, pinned allocations) takes a while: a generous common start time
         start = {"h2d": t, "d2h": t + args.seconds + 1.0, "duplex": t + 2 * (args.seconds + 1.0)}
         procs = [subprocess.Popen([sys.executable, os.path.abspath(__file__), "--child", str(g), "--size-mib", str(args.size_mib),
                                    "--seconds", str(args.seconds), "--start", json.dumps(start)], stdout=subprocess.PIPE, text=True)
