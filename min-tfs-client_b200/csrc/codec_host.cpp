@@ -88,6 +88,7 @@ struct b200tfs_ctx {
   uint64_t pipe_min = 1ull << 20;      // *_host calls moving at least this many payload bytes are sliced (B200TFS_PIPELINE_MIN; 0 = never)
   int pipe_max = 4;                    // at most this many slices (B200TFS_PIPELINE_SLICES, 2..kPipeMax): every slice costs ~7 driver calls
   uint64_t pipelined_calls = 0;        // how many host calls took the sliced path (tests)
+  uint32_t decode_cast = 0;            // b200tfs_set_decode_cast: DT_FLOAT outputs of the single-launch decode leave as DT_HALF / DT_BFLOAT16
   Slot slots[kSlots];
   int next_slot = 0;
   Growable scratch_dev;   // parse tables / varint tile tables
@@ -1259,12 +1260,14 @@ static void adopt_pinned_template(b200tfs_ctx* c) {
 static uint32_t decode_vpt(const b200tfs_ctx* c, int32_t n, const uint64_t* rec_len) {
   uint64_t wire_total = 0;
   for (int i = 0; i < n; ++i) wire_total += rec_len[i];
-  return pick_vec_per_tile(c, wire_total, 262144);
+  // a narrowing launch (b200tfs_set_decode_cast) moves its tiles through the general tile routine, whose rounds of 8 KB run one
+  // after the other inside a CTA: small tiles, many CTAs (256 KB tiles: 270 us for the C4 batch; 64 KB: see profiles/r02_c4.md)
+  return pick_vec_per_tile(c, c->decode_cast ? wire_total / 2 : wire_total, c->decode_cast ? 65536 : 262144);
 }
 
 // Walk record 0 on the host (its bytes are in host memory) and build its template: the launch that follows then takes the
 // template path from its first CTA on.  Returns false when the record does not qualify (the kernel will walk it).
-static bool host_template(const uint8_t* rec0, uint64_t len, uint32_t vpt, uint64_t dst_stride, uint32_t serial, Template* T) {
+static bool host_template(const uint8_t* rec0, uint64_t len, uint32_t vpt, uint64_t dst_stride, uint32_t serial, uint32_t cast, Template* T) {
   T->in.head.valid = 0;
   if (!rec0 || len == 0 || len > 0x7FFFFFFFull) return false;
   b200tfs_output outs[kFusedMaxOutputs + 1];
@@ -1275,10 +1278,10 @@ static bool host_template(const uint8_t* rec0, uint64_t len, uint32_t vpt, uint6
   SpillArea sp{nullptr, 0u, 0u};
   const int st = walk_response(cur, kFusedMaxOutputs, outs, &cnt, &spec, sp);
   if (st != B200TFS_OK) return false;
-  const uint64_t used = tpl_layout_outputs(outs, cnt, dst_stride);
+  const uint64_t used = tpl_layout_outputs(outs, cnt, dst_stride, cast);
   for (int k = 0; k < cnt; ++k) if (outs[k].status == B200TFS_E_SIZE) return false;
   // the kernel's own check: the chunks' tiles must fit the budget the launch gives the record
-  tpl_learn(T, cur, (uint32_t)len, outs, cnt, spec, st, vpt, (used + 255) & ~255ull, serial);
+  tpl_learn(T, cur, (uint32_t)len, outs, cnt, spec, st, vpt, (used + 255) & ~255ull, serial, cast);
   return T->in.head.valid != 0;
 }
 
@@ -1314,6 +1317,7 @@ static int decode_launch(b200tfs_ctx* c, const void* arena_dev, int32_t n, const
   fp.stats = (unsigned long long*)((uint8_t*)c->tpl_dev + 2 * sizeof(Template));
   if (++c->serial == 0) c->serial = 1;
   fp.serial = c->serial;
+  fp.cast = c->decode_cast;
   fp.tpli.head.valid = 0;
   if (vpt <= kStageVecsHost) {   // the single-response / small-batch kernel takes its template from the parameters when the host has one
     if (host_tpl && host_tpl->in.head.valid) {
@@ -1330,7 +1334,7 @@ static int decode_launch(b200tfs_ctx* c, const void* arena_dev, int32_t n, const
       // well be busy again: the caller's own copy of the next response usually precedes this call)
       if (!c->capturing && (!c->tpl_event_pending || cudaEventQuery(c->tpl_event) == cudaSuccess)) { c->tpl_event_pending = false; adopt_pinned_template(c); }
       const TplHead& h = c->tpl_known.head;
-      if (!c->opt_no_inline && h.valid && h.rec_len == rec_len[0] && h.vpt == vpt && h.dst_need <= dst_stride) fp.tpli = c->tpl_known;
+      if (!c->opt_no_inline && h.valid && h.rec_len == rec_len[0] && h.vpt == vpt && h.cast == fp.cast && h.dst_need <= dst_stride) fp.tpli = c->tpl_known;
     }
   }
   // the table is written by the kernel straight into pinned host memory (unified addressing): ~1 KB
@@ -1398,6 +1402,15 @@ int b200tfs_decode_responses(b200tfs_ctx* c, const void* arena_dev, int32_t n, c
   if (dst_stride & 255) return fail(B200TFS_E_ARG, "dst_stride must be a multiple of 256");
   if (!c->capturing) CU(cudaSetDevice(c->device));
   return decode_launch(c, arena_dev, n, rec_off, rec_len, dst_dev, dst_stride, decode_vpt(c, n, rec_len), nullptr);
+}
+
+int b200tfs_set_decode_cast(b200tfs_ctx* c, int32_t float_as) {
+  if (!c) return fail(B200TFS_E_ARG, "ctx is NULL");
+  if (c->capturing) return fail(B200TFS_E_ARG, "cannot change the decode cast during graph capture");
+  if (float_as != 0 && float_as != DT_FLOAT && float_as != DT_HALF && float_as != DT_BFLOAT16)
+    return fail(B200TFS_E_DTYPE, "DT_FLOAT outputs can leave as DT_FLOAT, DT_HALF or DT_BFLOAT16, not as dtype %d", float_as);
+  c->decode_cast = (float_as == DT_HALF || float_as == DT_BFLOAT16) ? (uint32_t)float_as : 0u;
+  return B200TFS_OK;
 }
 
 int b200tfs_decode_results(b200tfs_ctx* c, int32_t n, b200tfs_output* outs, int32_t* n_outs, b200tfs_model_spec* specs,
@@ -1765,7 +1778,7 @@ int b200tfs_decode_responses_host_async(b200tfs_ctx* c, const void* wire_host, i
   Template T;
   uint64_t shift = 0;
   const bool have = vpt <= kStageVecsHost && !c->capturing &&
-                    host_template((const uint8_t*)wire_host + rec_off[0], rec_len[0], vpt, dst_stride, c->serial + 1 ? c->serial + 1 : 1, &T);
+                    host_template((const uint8_t*)wire_host + rec_off[0], rec_len[0], vpt, dst_stride, c->serial + 1 ? c->serial + 1 : 1, c->decode_cast, &T);
   if (have) {
     uint32_t big = 0;
     for (uint32_t q = 1; q < T.in.head.n_chunks; ++q) if (T.in.chunk[q].len > T.in.chunk[big].len) big = q;

@@ -285,16 +285,23 @@ __device__ __forceinline__ bool body_same_width(const uint8_t* src, uint8_t* dst
   }
 }
 
-// f16 / bf16 -> f32 (encode-side cast).  Both sides 16-byte aligned; unit u = 16 source bytes -> 32 out.
+// f16 / bf16 -> f32 (encode-side cast).  Both sides 16-byte aligned; unit u = 16 source bytes -> 32 out.  Eight loads per thread
+// are in flight before the first store, like the same-width bodies (two were: 0.74 of peak on the C4 batch).
 template <bool BF>
 __device__ __forceinline__ void body_widen(const uint8_t* __restrict__ src, uint8_t* __restrict__ dst, uint32_t units) {
-  for (uint32_t u = threadIdx.x; u < units; u += 2 * kMoveThreads) {
-    uint4 h[2];
+  constexpr uint32_t kU = 8;
+  for (uint32_t base = 0; base < units; base += kU * kMoveThreads) {      // uniform trip count across the CTA
+    uint4 h[kU];
 #pragma unroll
-    for (uint32_t i = 0; i < 2; ++i) if (u + i * kMoveThreads < units) h[i] = ld_stream(src + 16ull * (u + i * kMoveThreads));
+    for (uint32_t i = 0; i < kU; ++i) {
+      const uint32_t u = base + i * kMoveThreads + threadIdx.x;
+      h[i] = make_uint4(0, 0, 0, 0);
+      if (u < units) h[i] = ld_stream(src + 16ull * u);
+    }
 #pragma unroll
-    for (uint32_t i = 0; i < 2; ++i)
-      if (u + i * kMoveThreads < units) {
+    for (uint32_t i = 0; i < kU; ++i) {
+      const uint32_t u = base + i * kMoveThreads + threadIdx.x;
+      if (u < units) {
         const uint4 x = h[i];
         uint4 lo, hi;
         if (BF) {
@@ -304,9 +311,10 @@ __device__ __forceinline__ void body_widen(const uint8_t* __restrict__ src, uint
           lo.x = widen_f16(x.x & 0xFFFF); lo.y = widen_f16(x.x >> 16); lo.z = widen_f16(x.y & 0xFFFF); lo.w = widen_f16(x.y >> 16);
           hi.x = widen_f16(x.z & 0xFFFF); hi.y = widen_f16(x.z >> 16); hi.z = widen_f16(x.w & 0xFFFF); hi.w = widen_f16(x.w >> 16);
         }
-        st_stream(dst + 32ull * (u + i * kMoveThreads), lo);
-        st_stream(dst + 32ull * (u + i * kMoveThreads) + 16, hi);
+        st_stream(dst + 32ull * u, lo);
+        st_stream(dst + 32ull * u + 16, hi);
       }
+    }
   }
 }
 
@@ -316,29 +324,38 @@ __device__ __forceinline__ uint32_t narrow2(uint32_t a, uint32_t b) {
   return BF ? (f32_bits_to_bf16_bits(a) | (f32_bits_to_bf16_bits(b) << 16))
             : (f32_bits_to_f16_bits(a) | (f32_bits_to_f16_bits(b) << 16));
 }
-template <bool BF, int Q>
-__device__ __forceinline__ void body_narrow_q(const uint8_t* __restrict__ S, uint8_t* __restrict__ dst, uint32_t n, uint32_t s, bool aligned) {
-  // output vector v (8 halfs) <- source blocks 2v, 2v+1 (+ 2v+2 when shifted: lane L+1's block 2v, by shuffle)
-  const bool edge = (threadIdx.x & 31) == 31;
-  const uint32_t rounds = (n + 2 * kMoveThreads - 1) / (2 * kMoveThreads);
-  for (uint32_t rd = 0; rd < rounds; ++rd) {
-    const uint32_t v = rd * 2 * kMoveThreads + threadIdx.x;
-    uint4 a[2], b[2], own[2];
+// Output vector u (8 halfs) <- source blocks 2u, 2u+1 (+ 2u+2 when the source is shifted).  Every warp owns a contiguous run of
+// 32 * kU output vectors per round, so that block 2u+2 is the neighbour lane's block 2(u+1) - by shuffle - and only the run's
+// last vector needs a load of its own; all 2 * kU (+1) loads of a thread are issued before its first store (with two vectors per
+// thread the C4 batch decode ran at 0.48 of peak: 24 warps per SM x 64 B in flight each).
+// `mid` runs once, between the first round's loads and its stores (the fused decode's framing verdict: nothing may be stored
+// before it, but the tile's bytes can already be on their way).
+template <bool BF, int Q, class Mid>
+__device__ __forceinline__ bool body_narrow_q(const uint8_t* __restrict__ S, uint8_t* __restrict__ dst, uint32_t n, uint32_t s, bool aligned, Mid& mid) {
+  constexpr uint32_t kU = 4, kRun = 32 * kU, kRound = kRun * (kMoveThreads / 32);
+  const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (uint32_t base = 0; base < n; base += kRound) {                      // uniform trip count across the CTA
+    const uint32_t run = base + warp * kRun;
+    const uint32_t run_end = min(run + kRun, n);
+    uint4 a[kU], b[kU], extra = make_uint4(0, 0, 0, 0);
 #pragma unroll
-    for (uint32_t i = 0; i < 2; ++i) {
-      const uint32_t u = v + i * kMoveThreads;
-      a[i] = b[i] = own[i] = make_uint4(0, 0, 0, 0);
-      if (u < n) {
-        const uint8_t* p = S + 32ull * u;
-        a[i] = ld_stream(p); b[i] = ld_stream(p + 16);
-        if (!aligned && (edge || u + 1 >= n)) own[i] = ld_stream(p + 32);
-      }
+    for (uint32_t i = 0; i < kU; ++i) {
+      const uint32_t u = run + 32 * i + lane;
+      a[i] = b[i] = make_uint4(0, 0, 0, 0);
+      if (u < n) { const uint8_t* p = S + 32ull * u; a[i] = ld_stream(p); b[i] = ld_stream(p + 16); }
     }
+    if (!aligned && lane == 0 && run < n) extra = ld_stream(S + 32ull * run_end);     // the block behind the run's last vector
+    if (base == 0 && !mid()) return false;
+    extra = shfl_lane0(extra);
 #pragma unroll
-    for (uint32_t i = 0; i < 2; ++i) {
-      const uint32_t u = v + i * kMoveThreads;
-      uint4 c = shfl_down1(a[i]);
-      if (edge || u + 1 >= n) c = own[i];
+    for (uint32_t i = 0; i < kU; ++i) {
+      const uint32_t u = run + 32 * i + lane;
+      uint4 c = shfl_down1(a[i]);                                  // lanes 0..30: the neighbour's first block
+      if (i + 1 < kU) {
+        const uint4 nxt = shfl_lane0(a[i + 1]);                    // lane 31: first block of the next row of this run
+        if (lane == 31) c = nxt;
+      }
+      if (u + 1 == run_end) c = extra;
       if (u < n) {
         uint4 f0 = a[i], f1 = b[i];
         if (!aligned) { f0 = shift_pair<Q>(a[i], b[i], s); f1 = shift_pair<Q>(b[i], c, s); }
@@ -349,17 +366,19 @@ __device__ __forceinline__ void body_narrow_q(const uint8_t* __restrict__ S, uin
       }
     }
   }
+  return true;
 }
-template <bool BF>
-__device__ __forceinline__ void body_narrow(const uint8_t* src, uint8_t* dst, uint32_t n) {
+
+template <bool BF, class Mid>
+__device__ __forceinline__ bool body_narrow(const uint8_t* src, uint8_t* dst, uint32_t n, Mid& mid) {
   const uint32_t k = (uint32_t)((uintptr_t)src & 15);
   const uint8_t* S = src - k;
   const uint32_t s = (k & 3) * 8;
   switch (k >> 2) {
-    case 0: body_narrow_q<BF, 0>(S, dst, n, s, k == 0); break;
-    case 1: body_narrow_q<BF, 1>(S, dst, n, s, false); break;
-    case 2: body_narrow_q<BF, 2>(S, dst, n, s, false); break;
-    default: body_narrow_q<BF, 3>(S, dst, n, s, false); break;
+    case 0: return body_narrow_q<BF, 0>(S, dst, n, s, k == 0, mid);
+    case 1: return body_narrow_q<BF, 1>(S, dst, n, s, false, mid);
+    case 2: return body_narrow_q<BF, 2>(S, dst, n, s, false, mid);
+    default: return body_narrow_q<BF, 3>(S, dst, n, s, false, mid);
   }
 }
 
@@ -443,8 +462,8 @@ __device__ __forceinline__ bool move_tile(const uint8_t* __restrict__ src, uint8
         case OP_QUIET_DST: go = body_same_width<OP_QUIET_DST>(src_body + 16 * v0, d, n, mid); break;
         case OP_H2F: go = mid(); if (go) body_widen<false>(src_body + 8 * v0, d, n >> 1); break;
         case OP_B2F: go = mid(); if (go) body_widen<true>(src_body + 8 * v0, d, n >> 1); break;
-        case OP_F2H: go = mid(); if (go) body_narrow<false>(src_body + 32 * v0, d, n); break;
-        default: go = mid(); if (go) body_narrow<true>(src_body + 32 * v0, d, n); break;
+        case OP_F2H: go = body_narrow<false>(src_body + 32 * v0, d, n, mid); break;
+        default: go = body_narrow<true>(src_body + 32 * v0, d, n, mid); break;
       }
     }
   } else go = mid();
@@ -472,6 +491,19 @@ __device__ __noinline__ void move_tile_cold(const uint8_t* src, uint8_t* dst, ui
                                             uint32_t vpt) {
   AlwaysGo go;
   move_tile<true>(src, dst, n_out, op, n_tiles, tile, vpt, go);
+}
+
+// the narrowing ops (float32 on the wire -> fp16 / bf16 in memory: b200tfs_set_decode_cast) through the general tile move, out of line
+__device__ __noinline__ void move_tile_narrow(const uint8_t* src, uint8_t* dst, uint64_t n_out, uint32_t op, uint32_t n_tiles, uint32_t tile,
+                                              uint32_t vpt) {
+  AlwaysGo go;
+  move_tile<false>(src, dst, n_out, op, n_tiles, tile, vpt, go);
+}
+__device__ __forceinline__ bool op_narrows(uint32_t op) { return op == OP_F2H || op == OP_F2B; }
+// a template chunk's tile, cold: `len` = the chunk's WIRE bytes
+__device__ __forceinline__ void chunk_tile_cold(const uint8_t* src, uint8_t* dst, uint32_t len, uint32_t op, uint32_t n_tiles, uint32_t tile, uint32_t vpt) {
+  if (op_narrows(op)) move_tile_narrow(src, dst, len >> 1, op, n_tiles, tile, vpt);
+  else move_tile_cold(src, dst, len, op, n_tiles, tile, vpt);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -737,7 +769,7 @@ __device__ __noinline__ void fused_slow_path(const FusedParams& fp, uint32_t r, 
     uint64_t cursor = 0;   // bytes used in this record's destination slot
     uint32_t t_base = 0;   // tiles consumed by earlier chunks
     if (st == B200TFS_OK) {
-      cursor = tpl_layout_outputs(outs_s, cnt, fp.dst_stride);
+      cursor = tpl_layout_outputs(outs_s, cnt, fp.dst_stride, fp.cast);
       // tiles are handed out by ascending wire offset of the chunk (same order the template uses)
       uint32_t done_mask[kFusedMaxOutputs] = {0};
       for (;;) {
@@ -754,11 +786,12 @@ __device__ __noinline__ void fused_slow_path(const FusedParams& fp, uint32_t r, 
         uint64_t run = 0;
         for (int q = 0; q < bq; ++q) run += (uint64_t)o.runs[q].len * o.runs[q].count;
         const b200tfs_run& rn = o.runs[bq];
-        const uint64_t bytes = (uint64_t)rn.len * rn.count;
+        const bool narrow = tpl_narrows(fp.cast, o.dtype);
+        const uint64_t bytes = ((uint64_t)rn.len * rn.count) >> (narrow ? 1 : 0);     // bytes written
         const uint32_t nt = tiles_for(bytes, fp.vpt);
         if (j >= t_base && j < t_base + nt) {
-          job.src = rec + rn.off; job.dst = dst_slot + o.dst_off + run; job.n_out = bytes;
-          job.op = (o.dtype == DT_FLOAT) ? OP_QUIET_DST : OP_COPY; job.n_tiles = nt; job.tile = j - t_base; job.valid = 1;
+          job.src = rec + rn.off; job.dst = dst_slot + o.dst_off + (narrow ? run / 2 : run); job.n_out = bytes;
+          job.op = tpl_move_op(fp.cast, o.dtype); job.n_tiles = nt; job.tile = j - t_base; job.valid = 1;
           job.glen = rn.count > 1 ? rn.len : 0u; job.gstride = rn.count > 1 ? rn.stride : 0u;   // a row of unpacked elements: gathered
         }
         t_base += nt;
@@ -772,7 +805,7 @@ __device__ __noinline__ void fused_slow_path(const FusedParams& fp, uint32_t r, 
       fp.specs[r] = spec_s;
       for (int k = 0; k < cnt && st == B200TFS_OK; ++k) fp.outs[(size_t)r * kFusedMaxOutputs + k] = outs_s[k];
       if (r == 0) {   // leave the template for the next launch, and its inline part in pinned memory for the host
-        if (len <= 0x7FFFFFFFull) tpl_learn(fp.tpl_write, c, (uint32_t)len, outs_s, cnt, spec_s, st, fp.vpt, (cursor + 255) & ~255ull, fp.serial);
+        if (len <= 0x7FFFFFFFull) tpl_learn(fp.tpl_write, c, (uint32_t)len, outs_s, cnt, spec_s, st, fp.vpt, (cursor + 255) & ~255ull, fp.serial, fp.cast);
         else fp.tpl_write->in.head.valid = 0;
         if (fp.tpl_pinned) {   // valid or not, stamped with this launch's serial: the host drops what it knew before either way
           fp.tpl_pinned->head.valid = 0;
@@ -806,7 +839,9 @@ __device__ __noinline__ void fused_slow_path(const FusedParams& fp, uint32_t r, 
 // STAGED: tiles of more than one 32 KB chunk (big batches) take the TMA-staged path above; the other instantiation - a single
 // response, small batches - carries none of that code and instead runs the verdict as the `mid` hook of the tile move (the
 // registers that holds across the barrier cost the big-batch kernel a CTA per SM, so only this one does it).
-template <bool STAGED>
+// CAST: the instantiations behind b200tfs_set_decode_cast carry the narrowing tile move as well; the plain ones are exactly the
+// round-1/2 kernels (the extra branch and registers cost the single-response launch 0.25 us when it lived in the same kernel).
+template <bool STAGED, bool CAST>
 __device__ __forceinline__ void decode_fused_body(const FusedParams& fp) {
   pdl_launch_dependents();
   __shared__ __align__(16) uint8_t lines[256];
@@ -858,7 +893,7 @@ __device__ __forceinline__ void decode_fused_body(const FusedParams& fp) {
     }
     __syncthreads();
     const uint32_t nch = th_s.n_chunks;
-    if (th_s.valid && th_s.rec_len == len && th_s.vpt == fp.vpt && th_s.dst_need <= fp.dst_stride && th_s.total_tiles < budget) {
+    if (th_s.valid && th_s.rec_len == len && th_s.vpt == fp.vpt && th_s.cast == fp.cast && th_s.dst_need <= fp.dst_stride && th_s.total_tiles < budget) {
       // The verdict: do this record's framing bytes equal the template's (and do packed-varint chunks still end on a terminator)?
       // It needs the record's framing bytes - a DRAM round trip.  The batch kernel decides per CTA (one byte per thread, one
       // barrier).  The single-response kernel decides per WARP - every warp compares all framing bytes itself (same bytes, same
@@ -902,11 +937,15 @@ __device__ __forceinline__ void decode_fused_body(const FusedParams& fp) {
       if (STAGED) {
         // the tile's bytes start moving now (TMA bulk copies into shared memory), the verdict's round trip overlaps theirs
         StagedTile stg{};
-        if (mine < kTplChunks)
+        const bool narrow = CAST && mine < kTplChunks && op_narrows(ch_s[mine].op);
+        if (mine < kTplChunks && !narrow)
           stg = staged_begin(rec + ch_s[mine].wire_off, dst_slot + ch_s[mine].dst_off, ch_s[mine].len, ch_s[mine].op, j - t_base, fp.vpt,
                              stage_smem, stage_bars);
-        hit = verdict();
-        if (hit && mine < kTplChunks) {
+        if (narrow)   // the general tile move with the verdict between its first loads and its first stores (CTA-uniform: a barrier inside)
+          hit = move_tile<false>(rec + ch_s[mine].wire_off, dst_slot + ch_s[mine].dst_off, (uint64_t)(ch_s[mine].len >> 1), ch_s[mine].op,
+                                 ch_s[mine].n_tiles, j - t_base, fp.vpt, verdict);
+        else hit = verdict();
+        if (hit && mine < kTplChunks && !narrow) {
           if (stg.use)
             staged_finish(stg, rec + ch_s[mine].wire_off, dst_slot + ch_s[mine].dst_off, ch_s[mine].len, ch_s[mine].op, ch_s[mine].n_tiles,
                           j - t_base, stage_smem, stage_bars);
@@ -915,6 +954,10 @@ __device__ __forceinline__ void decode_fused_body(const FusedParams& fp) {
                            fp.vpt);
         }
         if (!hit) staged_drain(stg, stage_bars, 0);   // let the copies land, then walk the record
+      } else if (CAST && mine < kTplChunks && op_narrows(ch_s[mine].op)) {
+        // narrowing tile: its loads go out first as well (general tile move, inlined into the cast instantiations only)
+        hit = move_tile<false>(rec + ch_s[mine].wire_off, dst_slot + ch_s[mine].dst_off, (uint64_t)(ch_s[mine].len >> 1), ch_s[mine].op,
+                               ch_s[mine].n_tiles, j - t_base, fp.vpt, verdict);
       } else if (mine < kTplChunks) {
         // the tile's loads go out first; the verdict runs while they are in flight and decides whether anything is stored
         hit = move_tile<true>(rec + ch_s[mine].wire_off, dst_slot + ch_s[mine].dst_off, ch_s[mine].len, ch_s[mine].op, ch_s[mine].n_tiles,
@@ -947,14 +990,17 @@ __device__ __forceinline__ void decode_fused_body(const FusedParams& fp) {
   __syncthreads();
   if (job.valid) {
     if (job.gstride) move_tile_gather(SrcView{job.src, job.glen, job.gstride}, job.dst, job.n_out, job.op, job.n_tiles, job.tile, fp.vpt);
+    else if (CAST && op_narrows(job.op)) move_tile_narrow(job.src, job.dst, job.n_out, job.op, job.n_tiles, job.tile, fp.vpt);
     else move_tile_cold(job.src, job.dst, job.n_out, job.op, job.n_tiles, job.tile, fp.vpt);
   }
 }
 
 // two CTAs per SM: the tile (8 x 128-bit per thread) stays in registers across the verdict's barrier without spilling; this instantiation serves
 // single responses and small batches, where a third resident CTA has nothing to hide
-__global__ void __launch_bounds__(kMoveThreads, 2) decode_fused_kernel(const __grid_constant__ FusedParams fp) { decode_fused_body<false>(fp); }
-__global__ void __launch_bounds__(kMoveThreads, 3) decode_fused_staged_kernel(const __grid_constant__ FusedParams fp) { decode_fused_body<true>(fp); }
+__global__ void __launch_bounds__(kMoveThreads, 2) decode_fused_kernel(const __grid_constant__ FusedParams fp) { decode_fused_body<false, false>(fp); }
+__global__ void __launch_bounds__(kMoveThreads, 3) decode_fused_staged_kernel(const __grid_constant__ FusedParams fp) { decode_fused_body<true, false>(fp); }
+__global__ void __launch_bounds__(kMoveThreads, 2) decode_fused_cast_kernel(const __grid_constant__ FusedParams fp) { decode_fused_body<false, true>(fp); }
+__global__ void __launch_bounds__(kMoveThreads, 3) decode_fused_staged_cast_kernel(const __grid_constant__ FusedParams fp) { decode_fused_body<true, true>(fp); }
 
 // ------------------------------------------------------------------------------------------------
 // packed varints: venc_len / venc_emit / vdec_count / vdec_emit
@@ -1095,11 +1141,25 @@ cudaError_t launch_fill_edge(uint8_t* dst, uint32_t elem_size, uint64_t have, co
 
 cudaError_t launch_decode_fused(const FusedParams& fp, uint32_t grid, cudaStream_t stream) {
   if (!grid) return cudaSuccess;
-  static const cudaError_t attr = cudaFuncSetAttribute(decode_fused_staged_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFusedDynSmem);
-  if (attr != cudaSuccess) return attr;
+  {   // the opt-in to > 48 KB of dynamic shared memory is per device (a process may drive several: ShardedCodec)
+    static bool opted[64] = {};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev < 0 || dev >= 64) dev = 0;
+    if (!opted[dev]) {
+      cudaError_t attr = cudaFuncSetAttribute(decode_fused_staged_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFusedDynSmem);
+      if (attr == cudaSuccess) attr = cudaFuncSetAttribute(decode_fused_staged_cast_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFusedDynSmem);
+      if (attr != cudaSuccess) return attr;
+      opted[dev] = true;
+    }
+  }
   // Tiles of more than one 32 KB chunk (big batches: up to 256 KB per CTA) go through the TMA-staged path: measured
   // 0.87 -> 0.90 of peak on 1024 x 602 KB.  One-chunk tiles (a single 4 MiB response) keep the register path and no
   // staging buffers: there the staged path gained 0.15 us on one stream but cost 13 % when 16 lanes overlap.
+  if (fp.cast) {
+    if (fp.vpt > kStageVecs) return launch_pdl(decode_fused_staged_cast_kernel, grid, kMoveThreads, kFusedDynSmem, stream, fp);
+    return launch_pdl(decode_fused_cast_kernel, grid, kMoveThreads, 0, stream, fp);
+  }
   if (fp.vpt > kStageVecs) return launch_pdl(decode_fused_staged_kernel, grid, kMoveThreads, kFusedDynSmem, stream, fp);
   return launch_pdl(decode_fused_kernel, grid, kMoveThreads, 0, stream, fp);
 }

@@ -72,7 +72,8 @@ struct TplHead {
   uint32_t valid, n_chunks, n_outs, framing_len;
   uint64_t rec_len, dst_need;
   uint32_t vpt, total_tiles;
-  uint32_t serial, pad;        // which learning produced it (the table entries below belong to exactly this serial)
+  uint32_t serial, cast;       // serial: which learning produced it (the table entries below belong to exactly this serial);
+                               // cast: the float narrowing it was laid out for (0 / DT_HALF / DT_BFLOAT16: FusedParams::cast)
 };
 // the part of a template every CTA needs before it can start on its tile: small enough to ride in the kernel parameters
 // (no load at all ahead of the tile's loads) when the host knows it - because it walked record 0 itself (host-buffer entry
@@ -107,7 +108,7 @@ struct FusedParams {
   TplInline* tpl_pinned;     // pinned host copy of the inline part, written whenever a template is learnt (valid flag last)
   unsigned long long* stats; // device counters: records served by [0] the template in the parameters, [1] the device template, [2] the walk
   uint32_t serial;           // stamp for a template learnt by THIS launch
-  uint32_t pad0;
+  uint32_t cast;             // DT_FLOAT outputs are narrowed on the way out: 0 = no, DT_HALF (19) / DT_BFLOAT16 (14) (b200tfs_set_decode_cast)
   uint32_t tile_bias;        // a SLICE of a one-record launch (the pipelined host path): CTA b works as CTA b + tile_bias of the full grid
   uint32_t trusted;          // != 0: the host built the inline template from THIS record's own bytes: no verdict (a slice's launch runs
                              // before the record's tail - and with it part of the framing - has arrived on the device)

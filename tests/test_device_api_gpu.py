@@ -827,3 +827,71 @@ def test_deferred_encode_no_host_round_trip(dev):
         assert whole[off[i]: off[i] + ln[i]].tobytes() == want, i
     assert [int(x) for x in ln] != lens1            # the replay really produced other lengths
     dev.lib.b200tfs_graph_destroy(g)
+
+
+def _decode_cast(dev, wires, dst_stride, cast):
+    """b200tfs_set_decode_cast + b200tfs_decode_responses on device-resident wires; returns (slots, outs, n_outs, status)."""
+    n = len(wires)
+    off, ln = (C.c_uint64 * n)(), (C.c_uint64 * n)()
+    cur = 0
+    for i, w in enumerate(wires):
+        off[i], ln[i] = cur, len(w)
+        cur += (len(w) + 255) & ~255
+    buf = np.zeros(cur + 256, dtype=np.uint8)
+    for i, w in enumerate(wires):
+        buf[off[i]: off[i] + len(w)] = np.frombuffer(w, dtype=np.uint8)
+    wire_dev = dev.upload(buf)
+    dst = dev.malloc(dst_stride * n + 256)
+    N.check(dev.lib.b200tfs_memset(dev.ctx, dst, 0xEE, dst_stride * n))
+    N.check(dev.lib.b200tfs_set_decode_cast(dev.ctx, cast))
+    N.check(dev.lib.b200tfs_decode_responses(dev.ctx, wire_dev, n, off, ln, dst, dst_stride))
+    outs = (N.Output * (n * N.FUSED_MAX_OUTPUTS))()
+    n_outs, status = (C.c_int32 * n)(), (C.c_int32 * n)()
+    N.check(dev.lib.b200tfs_decode_results(dev.ctx, n, outs, n_outs, None, status))
+    return dev.download(dst, dst_stride * n).reshape(n, dst_stride), outs, n_outs, status
+
+
+@pytest.mark.parametrize("cast", [19, 14])
+def test_fused_decode_narrows_float_outputs(dev, cast):
+    """b200tfs_set_decode_cast: DT_FLOAT outputs leave the single-launch decode as fp16 / bf16 (numpy's astype rounding, bit for
+    bit), other dtypes untouched; walk path (first launch), template path (second), a record the template does not fit (third),
+    odd sizes and a payload that starts at an odd destination phase; then a batch large enough for the TMA-staged kernel."""
+    import ml_dtypes
+
+    np_dt = np.float16 if cast == 19 else ml_dtypes.bfloat16
+    rng = np.random.default_rng(cast)
+    f = (rng.standard_normal(100003) * 100).astype(np.float32)
+    f[:6] = np.array([np.inf, -np.inf, 0.0, -0.0, 65504.0, 1e-8], dtype=np.float32)
+    d = rng.standard_normal(777)
+    small = rng.standard_normal(5).astype(np.float32)
+    wires = [wire_oracle.build_predict_response([("scores", f), ("aux", d), ("s", small)]),
+             wire_oracle.build_predict_response([("scores", f[::-1].copy()), ("aux", d), ("s", small)]),
+             wire_oracle.build_predict_response([("other", f[:4099])])]
+    for rep in range(2):
+        for w in wires:
+            slot, outs, n_outs, status = _decode_cast(dev, [w], 1 << 20, cast)
+            assert status[0] == 0, (rep, status[0])
+            ref = wire_oracle.decode_predict_response(w)
+            buf = np.frombuffer(w, dtype=np.uint8)
+            for k in range(n_outs[0]):
+                o = outs[k]
+                name = bytes(buf[o.key_off: o.key_off + o.key_len]).decode()
+                want = ref[name].astype(np_dt) if ref[name].dtype == np.float32 else ref[name]
+                assert o.status == 0 and o.dst_bytes == want.nbytes, (name, o.dst_bytes)
+                assert slot[0, o.dst_off: o.dst_off + o.dst_bytes].tobytes() == want.tobytes(), (rep, name)
+    # switching the cast off again: the template learnt for the cast must not serve the uncast launch
+    slot, outs, n_outs, status = _decode_cast(dev, [wires[0]], 1 << 20, 1)
+    ref = wire_oracle.decode_predict_response(wires[0])
+    for k in range(n_outs[0]):
+        name = bytes(np.frombuffer(wires[0], dtype=np.uint8)[outs[k].key_off: outs[k].key_off + outs[k].key_len]).decode()
+        assert slot[0, outs[k].dst_off: outs[k].dst_off + outs[k].dst_bytes].tobytes() == ref[name].tobytes()
+    # a batch for the staged kernel: 96 responses x 602 KB of float32
+    imgs = [rng.standard_normal(150528).astype(np.float32) for _ in range(4)]
+    batch = [wire_oracle.build_predict_response([("image", imgs[i % 4])]) for i in range(96)]
+    for rep in range(2):
+        slot, outs, n_outs, status = _decode_cast(dev, batch, (150528 * 2 + 255) & ~255, cast)
+        assert all(status[i] == 0 and n_outs[i] == 1 for i in range(96))
+        for i in range(96):
+            o = outs[i * N.FUSED_MAX_OUTPUTS]
+            assert slot[i, o.dst_off: o.dst_off + o.dst_bytes].tobytes() == imgs[i % 4].astype(np_dt).tobytes(), (rep, i)
+    assert dev.lib.b200tfs_set_decode_cast(dev.ctx, 9) == N.E_DTYPE

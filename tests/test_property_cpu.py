@@ -111,6 +111,23 @@ def test_walker_and_oracle_agree_with_port_on_random_responses(data):
             assert sum(1 for b in raw if not b & 0x80) == a.size      # one terminator per element
 
 
+def _malformed_varints(wire, o):
+    """The varint decode kernels' structural check, restated: every varint of every run ends within ten bytes."""
+    if not (o.flags & N.OF_VARINT):
+        return False
+    for c in range(o.n_runs):
+        r = o.runs[c]
+        for q in range(r.count):
+            run = 0
+            for b in wire[r.off + q * r.stride: r.off + q * r.stride + r.len]:
+                run = run + 1 if b & 0x80 else 0
+                if run >= 10:
+                    return True
+            if run:
+                return True
+    return False
+
+
 @SET
 @given(st.data())
 def test_truncated_or_corrupted_responses_never_misparse(data):
@@ -133,7 +150,11 @@ def test_truncated_or_corrupted_responses_never_misparse(data):
     try:
         parsed = predict_pb2.PredictResponse.FromString(wire)
     except DecodeError:
-        assert st_w == N.E_PARSE
+        # Either the walk itself refuses the record, or - value bytes are opaque to the walk - a packed-varint payload is
+        # malformed INSIDE (a varint longer than ten bytes, or one that never ends): that is what the varint decode kernels
+        # report as B200TFS_E_PARSE when the output is unpacked (tests/test_golden_gpu.py::test_varint_tile_geometry_chunks_and_malformed),
+        # and the Python layer raises DecodeError for the response either way.
+        assert st_w == N.E_PARSE or (st_w == N.OK and any(_malformed_varints(wire, table[i]) for i in range(cnt.value)))
         return
     assert st_w == N.OK, "runtime accepts these bytes but the walker rejected them"
     assert cnt.value == len(parsed.outputs)

@@ -143,3 +143,22 @@ def test_sharded_codec_on_the_device():
             for r, (arrays, spec) in enumerate(outs):
                 assert arrays["scores"].tobytes() == image(10000 + r).tobytes() and spec.name == "default"
         assert sc.encode_predict_requests([]) == []
+
+
+@pytest.mark.gpu
+def test_sharded_codec_batch_kernel_on_every_device():
+    """Shares large enough (80 x 602 KB per GPU) for the TMA-staged batch decode kernel, whose opt-in to > 48 KB of dynamic shared
+    memory is per device: every GPU of the process must get it, not only the first one that launched."""
+    from oracle import wire_oracle
+
+    n_gpu = N.device_count()
+    devices = list(range(n_gpu)) if n_gpu >= 2 else [0, 0]
+    imgs = [image(20000 + k) for k in range(5)]
+    wires = [wire_oracle.build_predict_response([("scores", imgs[k])], "default", 1, "serving_default") for k in range(5)]
+    n = 80 * len(devices)
+    with ShardedCodec(devices) as sc:
+        for _ in range(2):
+            outs = sc.decode_predict_responses([wires[r % 5] for r in range(n)])
+            assert len(outs) == n
+            for r, (arrays, spec) in enumerate(outs):
+                assert arrays["scores"].tobytes() == imgs[r % 5].tobytes(), r
