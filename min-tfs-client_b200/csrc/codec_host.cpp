@@ -109,6 +109,7 @@ struct b200tfs_ctx {
   cudaEvent_t tpl_event = nullptr;   // recorded behind every eager decode launch: once it has completed, tpl_pinned is current
   bool tpl_event_pending = false;
   bool opt_no_inline = false;        // B200TFS_NO_INLINE_TEMPLATE=1: never hand the template over in the kernel parameters (experiments)
+  bool opt_flat_budget = false;      // B200TFS_FLAT_BUDGET=1: every record gets ceil(len / tile) + 8 CTAs whatever the host knows (experiments)
   bool opt_table_dev = false;        // B200TFS_TABLE_DEV=1: the decode table goes to device memory and is fetched by b200tfs_decode_results
   Growable fused_dev;
   uint64_t stage_shift = 0;          // *_host decode: the wire sits at stage_dev + stage_shift (placed so that the payload is 16-byte aligned)
@@ -244,6 +245,8 @@ int b200tfs_create(int device, b200tfs_ctx** out) {
   if (tb) c->tile_bytes_override = (uint32_t)strtoul(tb, nullptr, 10);
   const char* oi = getenv("B200TFS_NO_INLINE_TEMPLATE");
   c->opt_no_inline = oi && oi[0] == '1';
+  const char* ofb = getenv("B200TFS_FLAT_BUDGET");
+  c->opt_flat_budget = ofb && ofb[0] == '1';
   const char* od = getenv("B200TFS_TABLE_DEV");
   c->opt_table_dev = od && od[0] == '1';
   e = cudaEventCreateWithFlags(&c->tpl_event, cudaEventDisableTiming);
@@ -1319,8 +1322,8 @@ static int decode_launch(b200tfs_ctx* c, const void* arena_dev, int32_t n, const
   fp.serial = c->serial;
   fp.cast = c->decode_cast;
   fp.tpli.head.valid = 0;
-  if (vpt <= kStageVecsHost) {   // the single-response / small-batch kernel takes its template from the parameters when the host has one
-    if (host_tpl && host_tpl->in.head.valid) {
+  if (host_tpl && host_tpl->in.head.valid) {
+    if (vpt <= kStageVecsHost) {   // the single-response / small-batch kernel takes its template from the parameters when the host has one
       // this launch's device template IS the host's walk of record 0: upload it where the kernel reads it
       Slot* slot;
       if ((rc = claim_slot(c, sizeof(Template), &slot))) return rc;
@@ -1329,14 +1332,25 @@ static int decode_launch(b200tfs_ctx* c, const void* arena_dev, int32_t n, const
       if (slot->done) { CU(cudaEventRecord(slot->done, c->stream)); slot->pending = true; }
       c->tpl_known = host_tpl->in;
       if (!c->opt_no_inline) fp.tpli = host_tpl->in;
-    } else {
-      // the pinned copy is current once the previous decode launch of this context has completed (the stream itself may
-      // well be busy again: the caller's own copy of the next response usually precedes this call)
-      if (!c->capturing && (!c->tpl_event_pending || cudaEventQuery(c->tpl_event) == cudaSuccess)) { c->tpl_event_pending = false; adopt_pinned_template(c); }
-      const TplHead& h = c->tpl_known.head;
-      if (!c->opt_no_inline && h.valid && h.rec_len == rec_len[0] && h.vpt == vpt && h.cast == fp.cast && h.dst_need <= dst_stride) fp.tpli = c->tpl_known;
     }
+  } else {
+    // the pinned copy is current once the previous decode launch of this context has completed (the stream itself may
+    // well be busy again: the caller's own copy of the next response usually precedes this call)
+    if (!c->capturing && (!c->tpl_event_pending || cudaEventQuery(c->tpl_event) == cudaSuccess)) { c->tpl_event_pending = false; adopt_pinned_template(c); }
+    const TplHead& h = c->tpl_known.head;
+    if (vpt <= kStageVecsHost && !c->opt_no_inline && h.valid && h.rec_len == rec_len[0] && h.vpt == vpt && h.cast == fp.cast && h.dst_need <= dst_stride)
+      fp.tpli = c->tpl_known;
   }
+  // CTAs per record: a record of the length the host knows a template for gets that template's tiles + the publishing CTA + one
+  // spare; any other record ceil(len / tile) + kFusedSlackTiles (its values may lie in several chunks, each rounding up).  With
+  // the flat slack, 8 of the 9 CTAs of a 4 KB response and 137 of the 265 of a narrowed 16 MiB one had no tile.  Should a record
+  // of that length carry OTHER framing that needs more tiles, its status says so (B200TFS_E_NONCANONICAL, b200tfs.h).
+  const TplHead& kh = (host_tpl && host_tpl->in.head.valid) ? host_tpl->in.head : c->tpl_known.head;
+  const bool budget_known = kh.valid && kh.vpt == vpt && kh.cast == fp.cast && kh.dst_need <= dst_stride && !c->opt_flat_budget;
+  auto ctas_for = [&](uint64_t len) -> uint64_t {
+    if (budget_known && len == kh.rec_len) return (uint64_t)kh.total_tiles + 2;
+    return (len + tile_bytes - 1) / tile_bytes + kFusedSlackTiles;
+  };
   // the table is written by the kernel straight into pinned host memory (unified addressing): ~1 KB
   // of posted PCIe writes per record instead of a device table plus a copy node behind every launch
   uint8_t* d = (uint8_t*)c->fused_host.p;
@@ -1350,13 +1364,13 @@ static int decode_launch(b200tfs_ctx* c, const void* arena_dev, int32_t n, const
   if (n <= kFusedInlineRecs) {
     for (int i = 0; i < n; ++i) {
       fp.inl.off[i] = rec_off[i]; fp.inl.len[i] = rec_len[i]; fp.inl.tile_start[i] = (uint32_t)grid;
-      grid += (rec_len[i] + tile_bytes - 1) / tile_bytes + kFusedSlackTiles;
+      grid += ctas_for(rec_len[i]);
     }
     fp.inl.tile_start[n] = (uint32_t)grid;
   } else {
     // tables: cta_rec[grid] | tile_start[n+1] | rec_off[n] | rec_len[n]
     std::vector<uint32_t> ts(n + 1);
-    for (int i = 0; i < n; ++i) { ts[i] = (uint32_t)grid; grid += (rec_len[i] + tile_bytes - 1) / tile_bytes + kFusedSlackTiles; }
+    for (int i = 0; i < n; ++i) { ts[i] = (uint32_t)grid; grid += ctas_for(rec_len[i]); }
     ts[n] = (uint32_t)grid;
     if (grid > 0x7FFFFFFFull) return fail(B200TFS_E_TOOBIG, "batch needs more than 2^31 tiles");
     const uint64_t o_ts = (grid * 4 + 15) & ~15ull, o_off = (o_ts + 4ull * (n + 1) + 15) & ~15ull, o_len = o_off + 8ull * n;
