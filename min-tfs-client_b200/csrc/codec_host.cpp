@@ -88,6 +88,7 @@ struct b200tfs_ctx {
   uint64_t pipe_min = 1ull << 20;      // *_host calls moving at least this many payload bytes are sliced (B200TFS_PIPELINE_MIN; 0 = never)
   int pipe_max = 4;                    // at most this many slices (B200TFS_PIPELINE_SLICES, 2..kPipeMax): every slice costs ~7 driver calls
   uint64_t pipelined_calls = 0;        // how many host calls took the sliced path (tests)
+  Growable guard_dev;                  // the narrowing batch decode's per-record verdicts (FusedParams::guard)
   uint32_t decode_cast = 0;            // b200tfs_set_decode_cast: DT_FLOAT outputs of the single-launch decode leave as DT_HALF / DT_BFLOAT16
   Slot slots[kSlots];
   int next_slot = 0;
@@ -281,6 +282,7 @@ int b200tfs_destroy(b200tfs_ctx* c) {
   if (c->scratch_dev.p) cudaFree(c->scratch_dev.p);
   if (c->spill_dev.p) cudaFree(c->spill_dev.p);
   if (c->gather_dev.p) cudaFree(c->gather_dev.p);
+  if (c->guard_dev.p) cudaFree(c->guard_dev.p);
   if (c->enc_host.p) cudaFreeHost(c->enc_host.p);
   if (c->measured_dev.p) cudaFree(c->measured_dev.p);
   if (c->scratch_host.p) cudaFreeHost(c->scratch_host.p);
@@ -527,6 +529,8 @@ struct PlanBuilder {
   std::vector<uint8_t> blob;
   std::vector<VarJob> varjobs;
   uint64_t large_bytes = 0;
+  const uint32_t* guard = nullptr;   // move_guarded_kernel: item i is stored only if guard[i / guard_div] != 0
+  uint32_t guard_div = 1;
 
   void header(uint8_t* dst, size_t blob_off, size_t n) {
     // split long headers so one warp never walks more than kSmallMax bytes
@@ -590,6 +594,7 @@ int build_plan(b200tfs_ctx* c, PlanBuilder& pb, bool force_dev, BuiltPlan* bp) {
   ph.n_small = (uint32_t)pb.smalls.size();
   ph.uniform_tpi = uniform;
   ph.vec_per_tile = vpt;
+  ph.guard = pb.guard; ph.guard_div = pb.guard_div ? pb.guard_div : 1u;
   uint64_t off = (sizeof(PlanHeader) + 15) & ~15ull;
   ph.off_items = (uint32_t)off; off += pb.items.size() * sizeof(MoveItem);
   ph.off_tiles = (uint32_t)off; if (!uniform) off += n_tiles * sizeof(TileRef);
@@ -1360,35 +1365,81 @@ static int decode_launch(b200tfs_ctx* c, const void* arena_dev, int32_t n, const
   }
   fp.outs = (b200tfs_output*)(d + L.outs); fp.n_outs = (int32_t*)(d + L.nouts);
   fp.specs = (b200tfs_model_spec*)(d + L.specs); fp.status = (int32_t*)(d + L.status);
-  uint64_t grid = 0;
-  if (n <= kFusedInlineRecs) {
-    for (int i = 0; i < n; ++i) {
-      fp.inl.off[i] = rec_off[i]; fp.inl.len[i] = rec_len[i]; fp.inl.tile_start[i] = (uint32_t)grid;
-      grid += ctas_for(rec_len[i]);
+  // lay the CTAs of a launch out: record r owns `per(len)` consecutive CTAs; small batches in the parameters, else one uploaded table
+  auto lay_out = [&](FusedParams& q, auto&& per, uint64_t* grid_out) -> int {
+    uint64_t grid = 0;
+    if (n <= kFusedInlineRecs) {
+      for (int i = 0; i < n; ++i) {
+        q.inl.off[i] = rec_off[i]; q.inl.len[i] = rec_len[i]; q.inl.tile_start[i] = (uint32_t)grid;
+        grid += per(rec_len[i]);
+      }
+      q.inl.tile_start[n] = (uint32_t)grid;
+    } else {
+      // tables: cta_rec[grid] | tile_start[n+1] | rec_off[n] | rec_len[n]
+      std::vector<uint32_t> ts(n + 1);
+      for (int i = 0; i < n; ++i) { ts[i] = (uint32_t)grid; grid += per(rec_len[i]); }
+      ts[n] = (uint32_t)grid;
+      if (grid > 0x7FFFFFFFull) return fail(B200TFS_E_TOOBIG, "batch needs more than 2^31 tiles");
+      const uint64_t o_ts = (grid * 4 + 15) & ~15ull, o_off = (o_ts + 4ull * (n + 1) + 15) & ~15ull, o_len = o_off + 8ull * n;
+      const uint64_t image = o_len + 8ull * n;
+      Slot* slot;
+      int rc2;
+      if ((rc2 = claim_slot(c, image, &slot))) return rc2;
+      uint8_t* h = (uint8_t*)slot->host.p;
+      uint32_t* cr = (uint32_t*)h;
+      for (int i = 0; i < n; ++i) for (uint32_t t = ts[i]; t < ts[i + 1]; ++t) cr[t] = (uint32_t)i;
+      memcpy(h + o_ts, ts.data(), 4ull * (n + 1));
+      memcpy(h + o_off, rec_off, 8ull * n);
+      memcpy(h + o_len, rec_len, 8ull * n);
+      if ((rc2 = upload_slot(c, slot, image))) return rc2;
+      uint8_t* sd = (uint8_t*)slot->dev.p;
+      q.cta_rec = (const uint32_t*)sd; q.tile_start = (const uint32_t*)(sd + o_ts);
+      q.rec_off = (const uint64_t*)(sd + o_off); q.rec_len = (const uint64_t*)(sd + o_len);
     }
-    fp.inl.tile_start[n] = (uint32_t)grid;
-  } else {
-    // tables: cta_rec[grid] | tile_start[n+1] | rec_off[n] | rec_len[n]
-    std::vector<uint32_t> ts(n + 1);
-    for (int i = 0; i < n; ++i) { ts[i] = (uint32_t)grid; grid += ctas_for(rec_len[i]); }
-    ts[n] = (uint32_t)grid;
     if (grid > 0x7FFFFFFFull) return fail(B200TFS_E_TOOBIG, "batch needs more than 2^31 tiles");
-    const uint64_t o_ts = (grid * 4 + 15) & ~15ull, o_off = (o_ts + 4ull * (n + 1) + 15) & ~15ull, o_len = o_off + 8ull * n;
-    const uint64_t image = o_len + 8ull * n;
-    Slot* slot;
-    if ((rc = claim_slot(c, image, &slot))) return rc;
-    uint8_t* h = (uint8_t*)slot->host.p;
-    uint32_t* cr = (uint32_t*)h;
-    for (int i = 0; i < n; ++i) for (uint32_t t = ts[i]; t < ts[i + 1]; ++t) cr[t] = (uint32_t)i;
-    memcpy(h + o_ts, ts.data(), 4ull * (n + 1));
-    memcpy(h + o_off, rec_off, 8ull * n);
-    memcpy(h + o_len, rec_len, 8ull * n);
-    if ((rc = upload_slot(c, slot, image))) return rc;
-    uint8_t* sd = (uint8_t*)slot->dev.p;
-    fp.cta_rec = (const uint32_t*)sd; fp.tile_start = (const uint32_t*)(sd + o_ts);
-    fp.rec_off = (const uint64_t*)(sd + o_off); fp.rec_len = (const uint64_t*)(sd + o_len);
+    *grid_out = grid;
+    return B200TFS_OK;
+  };
+  // The narrowing decode of a batch whose template the host knows, as three launches: the narrowing tile move runs twice as
+  // long inside the fused kernel as in the generic move engine (profiles/r02_c4.md), so (1) two CTAs per record verify the
+  // framing against the host's template - handed over in the parameters, the very one the plan below is built from - leave the
+  // verdict in guard[r] and publish the table, (2) move_guarded_kernel moves every record's chunks from a host-built plan
+  // and stores only where guard[r] says so, (3) the whole decode runs for the records still unguarded (none, normally: its
+  // CTAs leave after one load).
+  const TplInline* kt = (host_tpl && host_tpl->in.head.valid) ? &host_tpl->in : &c->tpl_known;
+  bool split = fp.cast && !sl && budget_known && kh.total_tiles > 0 && (uint64_t)n * kh.rec_len >= (4ull << 20) && !c->opt_no_inline && !c->opt_flat_budget;
+  for (int i = 0; i < n && split; ++i) split = rec_len[i] == kh.rec_len;
+  if (split) {
+    if ((rc = grow_dev(c, c->guard_dev, 4ull * n))) return rc;
+    FusedParams fa = fp;
+    fa.mode = 1; fa.guard = (uint32_t*)c->guard_dev.p; fa.tpli = *kt;
+    uint64_t ga = 0;
+    if ((rc = lay_out(fa, [](uint64_t) -> uint64_t { return 2; }, &ga))) return rc;
+    CU(launch_decode_fused(fa, (uint32_t)ga, c->stream));
+    PlanBuilder pb;
+    uint32_t per_rec = 0;
+    for (uint32_t q = 0; q < kt->head.n_chunks; ++q) if (kt->chunk[q].n_tiles) ++per_rec;
+    pb.items.reserve((size_t)n * per_rec);
+    for (int i = 0; i < n; ++i)
+      for (uint32_t q = 0; q < kt->head.n_chunks; ++q) {
+        const TplChunk& ch = kt->chunk[q];
+        if (!ch.n_tiles) continue;
+        const bool narrow = ch.op == OP_F2H || ch.op == OP_F2B;
+        const uint64_t n_out = narrow ? ch.len / 2 : ch.len;
+        pb.items.push_back(MoveItem{(const uint8_t*)arena_dev + rec_off[i] + ch.wire_off, (uint8_t*)dst_dev + (uint64_t)i * dst_stride + ch.dst_off, n_out,
+                                    ch.op, 0, 0, 0});
+        pb.large_bytes += n_out;
+      }
+    pb.guard = (const uint32_t*)c->guard_dev.p; pb.guard_div = per_rec;
+    BuiltPlan bp;
+    if ((rc = build_plan(c, pb, true, &bp))) return rc;
+    CU(launch_move_guarded(bp.plan_dev, bp.ph.n_tiles, c->stream));
+    if (bp.slot && bp.slot->done && !c->capturing) { CU(cudaEventRecord(bp.slot->done, c->stream)); bp.slot->pending = true; }
+    c->launches += 2;
+    fp.mode = 2; fp.guard = (uint32_t*)c->guard_dev.p;
   }
-  if (grid > 0x7FFFFFFFull) return fail(B200TFS_E_TOOBIG, "batch needs more than 2^31 tiles");
+  uint64_t grid = 0;
+  if ((rc = lay_out(fp, ctas_for, &grid))) return rc;
   if (sl) {
     if (n != 1 || !fp.tpli.head.valid) return fail(B200TFS_E_ARG, "internal: sliced decode without a host template");
     fp.trusted = 1;

@@ -510,6 +510,12 @@ __device__ __forceinline__ void chunk_tile_cold(const uint8_t* src, uint8_t* dst
 // move_kernel: CTAs [0, n_tiles) each take one tile of a large payload; the CTAs after them take the
 // small items (header fragments, small payloads), one warp per item.
 // ------------------------------------------------------------------------------------------------
+struct GuardMid {   // the guarded move: the tile's loads are in flight while the record's guard word arrives; nothing is stored on 0
+  uint32_t g;
+  __device__ __forceinline__ bool operator()() const { return g != 0; }
+};
+
+template <bool GUARD>
 __device__ __forceinline__ void move_body(const uint8_t* plan) {
   const PlanHeader& ph = *reinterpret_cast<const PlanHeader*>(plan);
   const uint32_t b = blockIdx.x;
@@ -521,6 +527,12 @@ __device__ __forceinline__ void move_body(const uint8_t* plan) {
       item = tr.item; tile = tr.tile;
     }
     const MoveItem& it = reinterpret_cast<const MoveItem*>(plan + ph.off_items)[item];
+    if (GUARD) {
+      GuardMid mid{ph.guard[item / ph.guard_div]};
+      if (it.gstride) { if (mid()) move_tile_gather(SrcView{it.src, it.glen, it.gstride}, it.dst, it.n_out, it.op, it.n_tiles, tile, ph.vec_per_tile); return; }
+      move_tile<false>(it.src, it.dst, it.n_out, it.op, it.n_tiles, tile, ph.vec_per_tile, mid);
+      return;
+    }
     if (it.gstride) { move_tile_gather(SrcView{it.src, it.glen, it.gstride}, it.dst, it.n_out, it.op, it.n_tiles, tile, ph.vec_per_tile); return; }
     AlwaysGo go;
     move_tile<false>(it.src, it.dst, it.n_out, it.op, it.n_tiles, tile, ph.vec_per_tile, go);
@@ -539,13 +551,21 @@ __device__ __forceinline__ void move_body(const uint8_t* plan) {
 __global__ void __launch_bounds__(kMoveThreads, 3) move_kernel(const uint8_t* __restrict__ plan) {
   pdl_launch_dependents();
   pdl_wait_prior_grids();   // the plan image itself was copied by an earlier operation of the stream
-  move_body(plan);
+  move_body<false>(plan);
 }
 
 __global__ void __launch_bounds__(kMoveThreads, 3) move_kernel_inline(const __grid_constant__ InlinePlan plan) {
   pdl_launch_dependents();
   pdl_wait_prior_grids();   // the plan is in the parameters, but sources / the arena may be outputs of earlier kernels
-  move_body(plan.bytes);
+  move_body<false>(plan.bytes);
+}
+
+// the same engine over a plan whose items stand for records another kernel vouches for (PlanHeader::guard): the second of the
+// three launches of a narrowing batch decode (FusedParams::mode)
+__global__ void __launch_bounds__(kMoveThreads, 3) move_guarded_kernel(const uint8_t* __restrict__ plan) {
+  pdl_launch_dependents();
+  pdl_wait_prior_grids();
+  move_body<true>(plan);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -873,6 +893,7 @@ __device__ __forceinline__ void decode_fused_body(const FusedParams& fp) {
   const uint8_t* rec = fp.w + off;
   uint8_t* dst_slot = fp.dst + (uint64_t)r * fp.dst_stride;
   pdl_wait_prior_grids();   // the template was written by the previous decode launch; the wire may be fresh too
+  if (CAST && fp.mode == 2 && fp.guard[r] != 0) return;    // verified and moved by the two launches before this one
 
   // One template per launch: the one in the kernel parameters when the host supplied it, else the one the previous launch left
   // in device memory.  (Trying both in turn kept too much state alive across the tile move: 500-700 bytes of spills.)  A record
@@ -893,7 +914,8 @@ __device__ __forceinline__ void decode_fused_body(const FusedParams& fp) {
     }
     __syncthreads();
     const uint32_t nch = th_s.n_chunks;
-    if (th_s.valid && th_s.rec_len == len && th_s.vpt == fp.vpt && th_s.cast == fp.cast && th_s.dst_need <= fp.dst_stride && th_s.total_tiles < budget) {
+    if (th_s.valid && th_s.rec_len == len && th_s.vpt == fp.vpt && th_s.cast == fp.cast && th_s.dst_need <= fp.dst_stride &&
+        (th_s.total_tiles < budget || (CAST && fp.mode == 1))) {
       // The verdict: do this record's framing bytes equal the template's (and do packed-varint chunks still end on a terminator)?
       // It needs the record's framing bytes - a DRAM round trip.  The batch kernel decides per CTA (one byte per thread, one
       // barrier).  The single-response kernel decides per WARP - every warp compares all framing bytes itself (same bytes, same
@@ -926,6 +948,12 @@ __device__ __forceinline__ void decode_fused_body(const FusedParams& fp) {
         const uint32_t nt = ch_s[q].n_tiles;
         if (j >= t_base && j < t_base + nt) { mine = q; break; }
         t_base += nt;
+      }
+      if (CAST && fp.mode == 1) {   // verify only: CTA 0 answers in the record's guard word, CTA 1 (the last) publishes the table
+        mine = kTplChunks;
+        const bool ok = verdict();
+        if (j == 0) { if (threadIdx.x == 0) fp.guard[r] = ok ? 1u : 0u; return; }
+        if (!ok) return;
       }
       // A slack CTA (the launch budgets kFusedSlackTiles more CTAs per record than tiles_for(len), for records whose
       // values lie in several chunks) has nothing to do when the record carries the template's framing - and 8 of the 11
@@ -986,6 +1014,7 @@ __device__ __forceinline__ void decode_fused_body(const FusedParams& fp) {
   }
 
   // ---- the walk: thread 0 goes through the tags ----
+  if (CAST && fp.mode == 1) { if (j == 0 && threadIdx.x == 0) fp.guard[r] = 0u; return; }   // left to the third launch
   if (threadIdx.x == 0) fused_slow_path(fp, r, j, live, j == 0, rec, len, dst_slot, lines, outs_s, spec_s, job);
   __syncthreads();
   if (job.valid) {
@@ -1157,7 +1186,7 @@ cudaError_t launch_decode_fused(const FusedParams& fp, uint32_t grid, cudaStream
   // 0.87 -> 0.90 of peak on 1024 x 602 KB.  One-chunk tiles (a single 4 MiB response) keep the register path and no
   // staging buffers: there the staged path gained 0.15 us on one stream but cost 13 % when 16 lanes overlap.
   if (fp.cast) {
-    if (fp.vpt > kStageVecs) return launch_pdl(decode_fused_staged_cast_kernel, grid, kMoveThreads, kFusedDynSmem, stream, fp);
+    if (fp.vpt > kStageVecs && fp.mode != 1) return launch_pdl(decode_fused_staged_cast_kernel, grid, kMoveThreads, kFusedDynSmem, stream, fp);
     return launch_pdl(decode_fused_cast_kernel, grid, kMoveThreads, 0, stream, fp);
   }
   if (fp.vpt > kStageVecs) return launch_pdl(decode_fused_staged_kernel, grid, kMoveThreads, kFusedDynSmem, stream, fp);
@@ -1178,6 +1207,11 @@ static uint32_t persistent_grid(K kernel) {
     cached[dev] = (uint32_t)max(1, per_sm) * (uint32_t)max(1, sms);
   }
   return cached[dev];
+}
+
+cudaError_t launch_move_guarded(const uint8_t* plan_dev, uint32_t n_tiles, cudaStream_t stream) {
+  if (!n_tiles) return cudaSuccess;
+  return launch_pdl(move_guarded_kernel, n_tiles, kMoveThreads, 0, stream, plan_dev);
 }
 
 cudaError_t launch_venc_len(const VarTables& tb, cudaStream_t stream) {

@@ -13,6 +13,10 @@ namespace b200tfs {
 cudaError_t launch_move(const uint8_t* plan_dev, const uint8_t* plan_host, uint32_t plan_bytes, uint32_t n_tiles,
                         uint32_t n_small, cudaStream_t stream);
 
+// the same engine over a device-resident plan whose items are stored only where PlanHeader::guard says so (codec_host.cpp: the
+// narrowing batch decode)
+cudaError_t launch_move_guarded(const uint8_t* plan_dev, uint32_t n_tiles, cudaStream_t stream);
+
 // spill: n * spill_per_rec entries of kSpillEntryBytes (walker.h SpillEntry) for dims / value runs beyond the table's inline
 // arrays; spill_used[r] receives how many entries record r wanted (more than spill_per_rec: its status is B200TFS_E_SPILL)
 constexpr uint32_t kSpillEntryBytes = 32;

@@ -49,6 +49,9 @@ struct PlanHeader {
   uint32_t n_items, n_tiles, n_small, uniform_tpi;  // uniform_tpi: every item has this many tiles (no TileRef table)
   uint32_t vec_per_tile;                            // 16-byte vectors of destination per tile
   uint32_t off_items, off_tiles, off_small;         // byte offsets inside the plan image
+  uint32_t guard_div;                               // move_guarded_kernel: item i is stored only if guard[i / guard_div] != 0
+  uint32_t pad[3];
+  const uint32_t* guard;
 };
 
 constexpr uint32_t kInlinePlanBytes = 3840;  // fits the classic 4 KB kernel-parameter window
@@ -109,6 +112,10 @@ struct FusedParams {
   unsigned long long* stats; // device counters: records served by [0] the template in the parameters, [1] the device template, [2] the walk
   uint32_t serial;           // stamp for a template learnt by THIS launch
   uint32_t cast;             // DT_FLOAT outputs are narrowed on the way out: 0 = no, DT_HALF (19) / DT_BFLOAT16 (14) (b200tfs_set_decode_cast)
+  uint32_t mode;             // 0: the whole decode.  The narrowing decode of a batch whose template the host knows runs as three launches:
+                             // 1 = verify only (two CTAs per record: framing verdict -> guard[r], table), then move_guarded_kernel over a
+                             // host-built plan, then 2 = the whole decode for the records whose guard is still 0 (the others leave at once)
+  uint32_t* guard;
   uint32_t tile_bias;        // a SLICE of a one-record launch (the pipelined host path): CTA b works as CTA b + tile_bias of the full grid
   uint32_t trusted;          // != 0: the host built the inline template from THIS record's own bytes: no verdict (a slice's launch runs
                              // before the record's tail - and with it part of the framing - has arrived on the device)

@@ -895,3 +895,36 @@ def test_fused_decode_narrows_float_outputs(dev, cast):
             o = outs[i * N.FUSED_MAX_OUTPUTS]
             assert slot[i, o.dst_off: o.dst_off + o.dst_bytes].tobytes() == imgs[i % 4].astype(np_dt).tobytes(), (rep, i)
     assert dev.lib.b200tfs_set_decode_cast(dev.ctx, 9) == N.E_DTYPE
+
+
+@pytest.mark.parametrize("cast", [19, 14])
+def test_narrowing_batch_decode_in_three_launches(dev, cast):
+    """A batch whose record length the host knows a template for: verify launch (guard words + table), guarded move over a
+    host-built plan, fallback launch for the records the verify launch did not vouch for.  Record 5 has the same LENGTH but
+    another key (same key length): its guard stays 0 and the third launch walks it; records of a batch with two outputs each."""
+    import ml_dtypes
+
+    np_dt = np.float16 if cast == 19 else ml_dtypes.bfloat16
+    rng = np.random.default_rng(100 + cast)
+    imgs = [rng.standard_normal(150528).astype(np.float32) * 50 for _ in range(3)]
+    aux = rng.standard_normal(4099).astype(np.float32)
+    def wire(i, key="image"):
+        return wire_oracle.build_predict_response([(key, imgs[i % 3]), ("aux", aux + i)])
+    batch = [wire(i) for i in range(24)]
+    stride = (150528 * 2 + 4099 * 2 + 1024 + 255) & ~255
+    l0 = C.c_uint64(); N.check(dev.lib.b200tfs_kernel_launches(dev.ctx, C.byref(l0)))
+    for rep in range(3):
+        if rep == 2:
+            batch[5] = wire(5, key="imagf")          # same length, other framing
+        slot, outs, n_outs, status = _decode_cast(dev, batch, stride, cast)
+        for i in range(24):
+            assert status[i] == 0 and n_outs[i] == 2, (rep, i, status[i])
+            ref = wire_oracle.decode_predict_response(batch[i])
+            buf = np.frombuffer(batch[i], dtype=np.uint8)
+            for k in range(2):
+                o = outs[i * N.FUSED_MAX_OUTPUTS + k]
+                name = bytes(buf[o.key_off: o.key_off + o.key_len]).decode()
+                want = ref[name].astype(np_dt)
+                assert o.dst_bytes == want.nbytes and slot[i, o.dst_off: o.dst_off + o.dst_bytes].tobytes() == want.tobytes(), (rep, i, name)
+    l1 = C.c_uint64(); N.check(dev.lib.b200tfs_kernel_launches(dev.ctx, C.byref(l1)))
+    assert l1.value - l0.value >= 1 + 3 + 3, "the second and third call run as three launches each"
