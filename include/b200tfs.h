@@ -347,9 +347,11 @@ int b200tfs_decode_responses(b200tfs_ctx* ctx, const void* arena_dev, int32_t n,
  * b200tfs_decode_responses / b200tfs_decode_responses_host_async on this context is written as fp16 / bf16 (IEEE round to nearest
  * even, the rounding of numpy's astype; b200tfs_output.dst_bytes = 2 * n_elems, .dtype stays DT_FLOAT, the wire's).  Outputs of
  * other dtypes are unaffected.  DT_FLOAT (or 0) switches it off.  This is the decode half of BASELINE config C4 (a fp16 / bf16
- * tensor travels as DT_FLOAT); the encode half is b200tfs_tensor.src_dtype != wire_dtype.  One launch, graph-capturable,
- * like the uncast decode (the two-phase route - b200tfs_parse_responses + b200tfs_unpack_outputs with dst_dtype - needs the
- * host between its phases).                                                                         */
+ * tensor travels as DT_FLOAT); the encode half is b200tfs_tensor.src_dtype != wire_dtype.  No host involvement between the
+ * launches and graph-capturable, like the uncast decode (the two-phase route - b200tfs_parse_responses +
+ * b200tfs_unpack_outputs with dst_dtype - needs the host between its phases).  A batch of >= 4 MiB whose record length the
+ * context has seen before runs as three launches (verify, guarded move, fallback: b200tfs_kernel_launches counts them); the
+ * results and the table are the same.                                                               */
 int b200tfs_set_decode_cast(b200tfs_ctx* ctx, int32_t float_as);
 /* How the records of every b200tfs_decode_responses launch of this context were served so far (cumulative; synchronises):
  * by the framing template handed over in the kernel parameters (the host walked record 0 of a host-resident wire itself,
