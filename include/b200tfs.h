@@ -404,6 +404,13 @@ int b200tfs_decode_responses_host_async(b200tfs_ctx* ctx, const void* wire_host,
                                         void* dst_host, uint64_t dst_stride);
 /* how many *_host_async calls of this context took the sliced, three-stream path so far            */
 int b200tfs_pipelined_calls(b200tfs_ctx* ctx, uint64_t* count);
+/* Output straight into the caller's buffer: when wire_host (encode) / dst_host (decode) is page-locked memory the device can
+ * address (b200tfs_host_alloc, cudaHostAlloc, cudaHostRegister), is 256-byte aligned and - encode - has room for the arena
+ * layout (b200tfs_request_arena_size bytes: records start 256-byte aligned, so record 0 need not start at offset 0; read
+ * rec_off), the kernels write it themselves with posted PCIe writes and no device-to-host copy is queued at all (one 4 MiB call:
+ * 177 -> 156 us with four slices).  Pageable or unaligned buffers take the staged route as before.  B200TFS_DIRECT_OUT=0 or
+ * b200tfs_set_pipeline(ctx, 0, 0) switches it off; this counts the calls that took it.                                                            */
+int b200tfs_direct_calls(b200tfs_ctx* ctx, uint64_t* count);
 /* Tune it per context: calls moving fewer than min_bytes of fixed-width payload stay monolithic (0 = never slice), at most
  * max_slices slices (2..8; default 4 - every slice costs about seven driver calls, ~7 us of host time).  A caller that keeps
  * several contexts busy at once already overlaps the two copy directions ACROSS calls and should switch slicing off: measured

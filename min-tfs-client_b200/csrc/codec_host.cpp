@@ -88,6 +88,8 @@ struct b200tfs_ctx {
   uint64_t pipe_min = 1ull << 20;      // *_host calls moving at least this many payload bytes are sliced (B200TFS_PIPELINE_MIN; 0 = never)
   int pipe_max = 4;                    // at most this many slices (B200TFS_PIPELINE_SLICES, 2..kPipeMax): every slice costs ~7 driver calls
   uint64_t pipelined_calls = 0;        // how many host calls took the sliced path (tests)
+  uint64_t direct_calls = 0;           // ... and how many wrote their output straight into the caller's pinned buffer
+  bool opt_direct_out = true;          // B200TFS_DIRECT_OUT=0: always stage the output on the device and copy it back
   Growable guard_dev;                  // the narrowing batch decode's per-record verdicts (FusedParams::guard)
   uint32_t decode_cast = 0;            // b200tfs_set_decode_cast: DT_FLOAT outputs of the single-launch decode leave as DT_HALF / DT_BFLOAT16
   Slot slots[kSlots];
@@ -257,6 +259,8 @@ int b200tfs_create(int device, b200tfs_ctx** out) {
   if (e != cudaSuccess) { delete c; return fail(B200TFS_E_CUDA, "pipeline stream / events: %s", cudaGetErrorString(e)); }
   const char* pm = getenv("B200TFS_PIPELINE_MIN");
   if (pm) c->pipe_min = strtoull(pm, nullptr, 10);
+  const char* pd = getenv("B200TFS_DIRECT_OUT");
+  if (pd && pd[0] == '0') c->opt_direct_out = false;
   const char* ps = getenv("B200TFS_PIPELINE_SLICES");
   if (ps) c->pipe_max = std::min<int>(b200tfs_ctx::kPipeMax, std::max(2, atoi(ps)));
   *out = c;
@@ -1609,6 +1613,17 @@ bool needs_measure(const std::vector<b200tfs_tensor>& ts) {
   return false;
 }
 
+// Is this host pointer page-locked memory the device can address (cudaHostAlloc / cudaHostRegister under unified addressing)?
+// Then a kernel may write its output there itself - posted PCIe writes at the link rate (4 MiB: 96 us from launch to synchronise
+// against 178 for H2D + kernel + D2H, profiles/r02_pipeline.md) - and the device-to-host copy disappears.  (The other direction
+// does not pay: SM-issued reads of host memory run at ~34 GB/s, the copy engine's at 55.)
+uint8_t* device_view_of_host(const void* p) {
+  cudaPointerAttributes a;
+  if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+  if (a.type != cudaMemoryTypeHost || !a.devicePointer) return nullptr;
+  return (uint8_t*)a.devicePointer;
+}
+
 // source bytes per output byte of a move op, as a fraction num/den; 0/0: the op cannot be cut
 void op_ratio(uint32_t op, uint32_t* num, uint32_t* den) {
   switch (op) {
@@ -1623,8 +1638,9 @@ void op_ratio(uint32_t op, uint32_t* num, uint32_t* den) {
 // bytes travel H2D on one stream while slice k-1 is being encoded on the context's stream and slice k-2's wire bytes travel D2H on
 // a third - one big request alone keeps both PCIe directions busy (monolithic H2D -> kernel -> D2H).
 // Framing bytes and small payloads go with slice 0.  Returns B200TFS_OK with *done = false when the batch does not qualify.
+// `direct`: the plan's destinations already lie in the caller's (pinned) wire buffer: no device-to-host copies, two streams.
 int encode_pipelined(b200tfs_ctx* c, PlanBuilder& pb, const std::vector<StagePiece>& pieces, uint8_t* wire_host, uint64_t lo, uint64_t hi,
-                     bool* done) {
+                     bool direct, bool* done) {
   *done = false;
   if (!c->pipe_min || pb.large_bytes < c->pipe_min || !pb.varjobs.empty() || pb.items.empty()) return B200TFS_OK;
   for (auto& it : pb.items) {
@@ -1650,7 +1666,7 @@ int encode_pipelined(b200tfs_ctx* c, PlanBuilder& pb, const std::vector<StagePie
   cudaEvent_t* ev = c->pipe_ev;
   CU(cudaEventRecord(ev[2 * b200tfs_ctx::kPipeMax], c->stream));
   CU(cudaStreamWaitEvent(c->aux_stream, ev[2 * b200tfs_ctx::kPipeMax], 0));
-  CU(cudaStreamWaitEvent(c->d2h_stream, ev[2 * b200tfs_ctx::kPipeMax], 0));
+  if (!direct) CU(cudaStreamWaitEvent(c->d2h_stream, ev[2 * b200tfs_ctx::kPipeMax], 0));
   size_t item = 0;
   uint64_t item_done = 0;        // output bytes of pb.items[item] already handed to a slice
   uint64_t wire_done = lo;       // arena offset up to which the wire has been copied back
@@ -1678,7 +1694,7 @@ int encode_pipelined(b200tfs_ctx* c, PlanBuilder& pb, const std::vector<StagePie
       if (feeds[item])
         CU(cudaMemcpyAsync((void*)(it.src + s_off), feeds[item]->host + (it.src + s_off - feeds[item]->dev), s_len, cudaMemcpyHostToDevice, c->aux_stream));
       sub.payload(it.src + s_off, it.dst + item_done, take, it.op);
-      wire_end = (uint64_t)(it.dst + item_done + take - arena);
+      if (!direct) wire_end = (uint64_t)(it.dst + item_done + take - arena);
       item_done += take;
       if (item_done == it.n_out) { ++item; item_done = 0; }
     }
@@ -1687,16 +1703,19 @@ int encode_pipelined(b200tfs_ctx* c, PlanBuilder& pb, const std::vector<StagePie
     CU(cudaEventRecord(ev[2 * k], c->aux_stream));
     CU(cudaStreamWaitEvent(c->stream, ev[2 * k], 0));
     if ((rc = launch_plan(c, sub))) return rc;
-    CU(cudaEventRecord(ev[2 * k + 1], c->stream));
-    CU(cudaStreamWaitEvent(c->d2h_stream, ev[2 * k + 1], 0));
-    if (wire_end > wire_done)
-      CU(cudaMemcpyAsync(wire_host + (wire_done - lo), arena + wire_done, wire_end - wire_done, cudaMemcpyDeviceToHost, c->d2h_stream));
-    wire_done = wire_end;
+    if (!direct) {
+      CU(cudaEventRecord(ev[2 * k + 1], c->stream));
+      CU(cudaStreamWaitEvent(c->d2h_stream, ev[2 * k + 1], 0));
+      if (wire_end > wire_done)
+        CU(cudaMemcpyAsync(wire_host + (wire_done - lo), arena + wire_done, wire_end - wire_done, cudaMemcpyDeviceToHost, c->d2h_stream));
+      wire_done = wire_end;
+    }
     if (final_slice) break;
   }
-  // the context's stream is where callers wait: it ends behind the last copy
-  CU(cudaEventRecord(ev[2 * b200tfs_ctx::kPipeMax + 1], c->d2h_stream));
-  CU(cudaStreamWaitEvent(c->stream, ev[2 * b200tfs_ctx::kPipeMax + 1], 0));
+  if (!direct) {   // the context's stream is where callers wait: it ends behind the last copy
+    CU(cudaEventRecord(ev[2 * b200tfs_ctx::kPipeMax + 1], c->d2h_stream));
+    CU(cudaStreamWaitEvent(c->stream, ev[2 * b200tfs_ctx::kPipeMax + 1], 0));
+  }
   c->pipelined_calls += 1;
   *done = true;
   return B200TFS_OK;
@@ -1749,23 +1768,30 @@ int b200tfs_encode_requests_host_async(b200tfs_ctx* c, int32_t n, const b200tfs_
   for (int i = 0; i < n; ++i) { rq[i].inputs = ts.data() + k; k += (size_t)rq[i].n_inputs; }
   uint64_t need = 0;
   if ((rc = b200tfs_request_arena_size(n, rq.data(), &need))) return rc;
-  if ((rc = grow_dev(c, c->arena_dev, need))) return rc;
   if (try_pipe) {
+    // A pinned wire buffer with room for the arena layout (records 256-byte aligned, largest payload 128-byte aligned) is written
+    // by the kernels themselves; rec_off then counts from wire_host like always, but record 0 does not start at 0.
+    uint8_t* out_dev = (c->opt_direct_out && c->pipe_min && need <= wire_cap) ? device_view_of_host(wire_host) : nullptr;
+    if (out_dev && ((uintptr_t)out_dev & 255)) out_dev = nullptr;
+    const bool direct = out_dev != nullptr;
+    if (!direct && (rc = grow_dev(c, c->arena_dev, need))) return rc;
     PlanBuilder pb;
-    if ((rc = plan_requests(n, rq.data(), c->arena_dev.p, c->arena_dev.cap, rec_off, rec_len, pb))) return rc;
+    if ((rc = plan_requests(n, rq.data(), direct ? (void*)out_dev : c->arena_dev.p, direct ? wire_cap : c->arena_dev.cap, rec_off, rec_len, pb))) return rc;
     const uint64_t lo = rec_off[0], hi = rec_off[n - 1] + rec_len[n - 1];
-    if (hi - lo > wire_cap) return fail(B200TFS_E_SIZE, "wire buffer too small: need %llu bytes", (unsigned long long)(hi - lo));
+    if (!direct && hi - lo > wire_cap) return fail(B200TFS_E_SIZE, "wire buffer too small: need %llu bytes", (unsigned long long)(hi - lo));
     bool done = false;
-    if ((rc = encode_pipelined(c, pb, pieces, (uint8_t*)wire_host, lo, hi, &done))) return rc;
+    if ((rc = encode_pipelined(c, pb, pieces, (uint8_t*)wire_host, lo, hi, direct, &done))) return rc;
     if (!done) {   // too small to be worth slicing: everything on the context's stream, as one piece
       for (auto& p : pieces) CU(cudaMemcpyAsync((void*)p.dev, p.host, p.nb, cudaMemcpyHostToDevice, c->stream));
       if ((rc = launch_plan(c, pb))) return rc;
       if ((rc = run_varjobs(c, pb))) return rc;
-      CU(cudaMemcpyAsync(wire_host, (uint8_t*)c->arena_dev.p + lo, hi - lo, cudaMemcpyDeviceToHost, c->stream));
+      if (!direct) CU(cudaMemcpyAsync(wire_host, (uint8_t*)c->arena_dev.p + lo, hi - lo, cudaMemcpyDeviceToHost, c->stream));
     }
-    for (int i = 0; i < n; ++i) rec_off[i] -= lo;
+    if (direct) c->direct_calls += 1;
+    else for (int i = 0; i < n; ++i) rec_off[i] -= lo;
     return B200TFS_OK;
   }
+  if ((rc = grow_dev(c, c->arena_dev, need))) return rc;
   if ((rc = b200tfs_encode_requests(c, n, rq.data(), c->arena_dev.p, c->arena_dev.cap, rec_off, rec_len))) return rc;
   const uint64_t lo = rec_off[0], hi = rec_off[n - 1] + rec_len[n - 1];
   if (hi - lo > wire_cap) return fail(B200TFS_E_SIZE, "wire buffer too small: need %llu bytes", (unsigned long long)(hi - lo));
@@ -1777,6 +1803,12 @@ int b200tfs_encode_requests_host_async(b200tfs_ctx* c, int32_t n, const b200tfs_
 int b200tfs_pipelined_calls(b200tfs_ctx* c, uint64_t* count) {
   if (!c || !count) return fail(B200TFS_E_ARG, "bad arguments");
   *count = c->pipelined_calls;
+  return B200TFS_OK;
+}
+
+int b200tfs_direct_calls(b200tfs_ctx* c, uint64_t* count) {
+  if (!c || !count) return fail(B200TFS_E_ARG, "bad arguments");
+  *count = c->direct_calls;
   return B200TFS_OK;
 }
 
@@ -1854,7 +1886,12 @@ int b200tfs_decode_responses_host_async(b200tfs_ctx* c, const void* wire_host, i
   int rc = grow_dev(c, c->stage_dev, hi + 64);
   if (rc) return rc;
   c->stage_shift = shift;
-  if ((rc = grow_dev(c, c->arena_dev, dst_stride * (uint64_t)n + 256))) return rc;
+  // a pinned destination is written by the kernel itself (posted PCIe writes): no staging buffer, no device-to-host copy
+  uint8_t* dst_direct = (c->opt_direct_out && c->pipe_min) ? device_view_of_host(dst_host) : nullptr;
+  if (dst_direct && ((uintptr_t)dst_direct & 255)) dst_direct = nullptr;
+  if (!dst_direct && (rc = grow_dev(c, c->arena_dev, dst_stride * (uint64_t)n + 256))) return rc;
+  uint8_t* dst_dev = dst_direct ? dst_direct : (uint8_t*)c->arena_dev.p;
+  if (dst_direct) c->direct_calls += 1;
   uint8_t* wire_dev = (uint8_t*)c->stage_dev.p + shift;
   // One large record whose values lie in one fixed-width chunk: slices of tiles, pipelined like the encode (wire bytes of slice
   // k+1 travel H2D while slice k is decoded and the tensor bytes of slice k-1 travel D2H).  The kernel skips its framing verdict:
@@ -1871,7 +1908,7 @@ int b200tfs_decode_responses_host_async(b200tfs_ctx* c, const void* wire_host, i
     sl.before = ev; sl.after = ev + b200tfs_ctx::kPipeMax;
     CU(cudaEventRecord(ev[2 * b200tfs_ctx::kPipeMax], c->stream));
     CU(cudaStreamWaitEvent(c->aux_stream, ev[2 * b200tfs_ctx::kPipeMax], 0));
-    CU(cudaStreamWaitEvent(c->d2h_stream, ev[2 * b200tfs_ctx::kPipeMax], 0));
+    if (!dst_direct) CU(cudaStreamWaitEvent(c->d2h_stream, ev[2 * b200tfs_ctx::kPipeMax], 0));
     uint64_t wire_done = 0;
     for (int k = 0; k < sl.K; ++k) {
       // tiles below tile_lo[k+1] read no further than 48 bytes past their last vector (the next 16-byte block of a shifted source)
@@ -1881,25 +1918,27 @@ int b200tfs_decode_responses_host_async(b200tfs_ctx* c, const void* wire_host, i
       wire_done = std::max(wire_done, w_end);
       CU(cudaEventRecord(sl.before[k], c->aux_stream));
     }
-    if ((rc = decode_launch(c, wire_dev, n, rec_off, rec_len, c->arena_dev.p, dst_stride, vpt, &T, &sl))) return rc;
-    const uint64_t need = std::min<uint64_t>(dst_stride, T.in.head.dst_need);
-    uint64_t dst_done = 0;
-    for (int k = 0; k < sl.K; ++k) {
-      // tiles below tile_lo[k+1] have written every byte of the slot below the first vector of tile tile_lo[k+1]
-      const uint64_t d_end = (k + 1 == sl.K) ? need : std::min<uint64_t>(need, ch.dst_off + sl.tile_lo[k + 1] * tile_bytes);
-      CU(cudaStreamWaitEvent(c->d2h_stream, sl.after[k], 0));
-      if (d_end > dst_done)
-        CU(cudaMemcpyAsync((uint8_t*)dst_host + dst_done, (uint8_t*)c->arena_dev.p + dst_done, d_end - dst_done, cudaMemcpyDeviceToHost, c->d2h_stream));
-      dst_done = std::max(dst_done, d_end);
+    if ((rc = decode_launch(c, wire_dev, n, rec_off, rec_len, dst_dev, dst_stride, vpt, &T, &sl))) return rc;
+    if (!dst_direct) {
+      const uint64_t need = std::min<uint64_t>(dst_stride, T.in.head.dst_need);
+      uint64_t dst_done = 0;
+      for (int k = 0; k < sl.K; ++k) {
+        // tiles below tile_lo[k+1] have written every byte of the slot below the first vector of tile tile_lo[k+1]
+        const uint64_t d_end = (k + 1 == sl.K) ? need : std::min<uint64_t>(need, ch.dst_off + sl.tile_lo[k + 1] * tile_bytes);
+        CU(cudaStreamWaitEvent(c->d2h_stream, sl.after[k], 0));
+        if (d_end > dst_done)
+          CU(cudaMemcpyAsync((uint8_t*)dst_host + dst_done, (uint8_t*)c->arena_dev.p + dst_done, d_end - dst_done, cudaMemcpyDeviceToHost, c->d2h_stream));
+        dst_done = std::max(dst_done, d_end);
+      }
+      CU(cudaEventRecord(ev[2 * b200tfs_ctx::kPipeMax + 1], c->d2h_stream));
+      CU(cudaStreamWaitEvent(c->stream, ev[2 * b200tfs_ctx::kPipeMax + 1], 0));
     }
-    CU(cudaEventRecord(ev[2 * b200tfs_ctx::kPipeMax + 1], c->d2h_stream));
-    CU(cudaStreamWaitEvent(c->stream, ev[2 * b200tfs_ctx::kPipeMax + 1], 0));
     c->pipelined_calls += 1;
     return B200TFS_OK;
   }
   if (hi) CU(cudaMemcpyAsync(wire_dev, wire_host, hi, cudaMemcpyHostToDevice, c->stream));
-  if ((rc = decode_launch(c, wire_dev, n, rec_off, rec_len, c->arena_dev.p, dst_stride, vpt, have ? &T : nullptr))) return rc;
-  CU(cudaMemcpyAsync(dst_host, c->arena_dev.p, dst_stride * (uint64_t)n, cudaMemcpyDeviceToHost, c->stream));
+  if ((rc = decode_launch(c, wire_dev, n, rec_off, rec_len, dst_dev, dst_stride, vpt, have ? &T : nullptr))) return rc;
+  if (!dst_direct) CU(cudaMemcpyAsync(dst_host, c->arena_dev.p, dst_stride * (uint64_t)n, cudaMemcpyDeviceToHost, c->stream));
   return B200TFS_OK;
 }
 

@@ -139,6 +139,7 @@ SIGNATURES = {
     "b200tfs_encode_requests_host": (C.c_int, [_vp, C.c_int32, C.POINTER(Request), _vp, C.c_uint64, _u64p, _u64p]),
     "b200tfs_encode_requests_host_async": (C.c_int, [_vp, C.c_int32, C.POINTER(Request), _vp, C.c_uint64, _u64p, _u64p]),
     "b200tfs_pipelined_calls": (C.c_int, [_vp, _u64p]),
+    "b200tfs_direct_calls": (C.c_int, [_vp, _u64p]),
     "b200tfs_set_pipeline": (C.c_int, [_vp, C.c_uint64, C.c_int32]),
     "b200tfs_set_decode_cast": (C.c_int, [_vp, C.c_int32]),
     "b200tfs_decode_responses_host_async": (C.c_int, [_vp, _vp, C.c_int32, _u64p, _u64p, _vp, C.c_uint64]),

@@ -44,7 +44,13 @@ def _with_snan(x):
     return x
 
 
-def _encode_host(dev, batch, pinned_inputs=True, wire_dtypes=None, grpc=False):
+def _direct(dev):
+    n = C.c_uint64()
+    N.check(dev.lib.b200tfs_direct_calls(dev.ctx, C.byref(n)))
+    return n.value
+
+
+def _encode_host(dev, batch, pinned_inputs=True, wire_dtypes=None, grpc=False, pinned_wire=True):
     """batch: [(model, version, [(key, ndarray)])] with HOST arrays -> list of wires via b200tfs_encode_requests_host_async."""
     keep, reqs = [], []
     for bi, (model, version, inputs) in enumerate(batch):
@@ -73,12 +79,19 @@ def _encode_host(dev, batch, pinned_inputs=True, wire_dtypes=None, grpc=False):
     n = len(reqs)
     rq = (N.Request * n)(*reqs)
     cap = sum(sum(a.nbytes * 2 for _, a in inputs) + 4096 for _, _, inputs in batch) + 4096
-    wire = N.PinnedBuffer(cap)
-    wire.array[:] = 0xEE
+    if pinned_wire:      # page-locked: the kernels write it themselves (no device-to-host copy); record 0 need not start at 0
+        wire = N.PinnedBuffer(cap)
+        arr, ptr = wire.array, wire.ptr
+    else:                # pageable: staged on the device and copied back, record 0 at offset 0
+        arr = np.empty(cap, dtype=np.uint8)
+        ptr = arr.ctypes.data
+    arr[:] = 0xEE
     off, ln = (C.c_uint64 * n)(), (C.c_uint64 * n)()
-    N.check(dev.lib.b200tfs_encode_requests_host_async(dev.ctx, n, rq, wire.ptr, cap, off, ln))
+    N.check(dev.lib.b200tfs_encode_requests_host_async(dev.ctx, n, rq, ptr, cap, off, ln))
     dev.sync()
-    return [wire.array[off[i]: off[i] + ln[i]].tobytes() for i in range(n)]
+    if not pinned_wire:
+        assert off[0] == 0
+    return [arr[off[i]: off[i] + ln[i]].tobytes() for i in range(n)]
 
 
 @pytest.mark.parametrize("elems", [65536 + 1, 131072 + 13, 200001, 262144, 1 << 20])
@@ -86,11 +99,12 @@ def test_sliced_encode_matches_the_oracle(elems):
     dev = _dev_with_threshold(4096)
     try:
         x = _with_snan(np.random.default_rng(elems).standard_normal(elems, dtype=np.float32))
-        before = _pipelined(dev)
+        before, d0 = _pipelined(dev), _direct(dev)
+        ref = wire_oracle.encode_predict_request("default", 3, [("x", x)])
         for pinned in (True, False):
-            wires = _encode_host(dev, [("default", 3, [("x", x)])], pinned_inputs=pinned)
-            assert wires[0] == wire_oracle.encode_predict_request("default", 3, [("x", x)])
-        assert _pipelined(dev) == before + 2
+            for pinned_wire in (True, False):
+                assert _encode_host(dev, [("default", 3, [("x", x)])], pinned_inputs=pinned, pinned_wire=pinned_wire)[0] == ref
+        assert _pipelined(dev) == before + 4 and _direct(dev) == d0 + 2
     finally:
         dev.close()
 
@@ -109,7 +123,8 @@ def test_sliced_encode_of_a_mixed_batch():
         tiny = np.arange(5, dtype=np.float32)
         batch = [("m1", 1, [("a", a), ("tiny", tiny)]), ("m2", None, [("h", h), ("b", b)]), ("m3", 7, [("d", d), ("a2", a[:17])])]
         wires = _encode_host(dev, batch, wire_dtypes={(1, 0): 1}, grpc=True)
-        assert _pipelined(dev) == 1
+        assert _pipelined(dev) == 1 and _direct(dev) == 1
+        assert wires == _encode_host(dev, batch, wire_dtypes={(1, 0): 1}, grpc=True, pinned_wire=False)
         want = [wire_oracle.encode_predict_request("m1", 1, [("a", a), ("tiny", tiny)]),
                 wire_oracle.encode_predict_request("m2", None, [("h", h.astype(np.float32)), ("b", b)]),
                 wire_oracle.encode_predict_request("m3", 7, [("d", d), ("a2", a[:17])])]
@@ -132,16 +147,22 @@ def test_default_threshold_slices_a_c2_request_and_leaves_small_ones_alone():
         dev.close()
 
 
-def _decode_host(dev, wire, dst_stride, shift=0):
-    wire_buf, out_buf = N.PinnedBuffer(len(wire) + 512), N.PinnedBuffer(dst_stride)
+def _decode_host(dev, wire, dst_stride, shift=0, pinned_dst=True):
+    wire_buf = N.PinnedBuffer(len(wire) + 512)
     wire_buf.array[shift: shift + len(wire)] = np.frombuffer(wire, dtype=np.uint8)
-    out_buf.array[:] = 0xEE
+    if pinned_dst:       # the kernel writes the tensors into it itself
+        out_buf = N.PinnedBuffer(dst_stride)
+        out, optr = out_buf.array, out_buf.ptr
+    else:
+        out_buf = out = np.empty(dst_stride, dtype=np.uint8)
+        optr = out.ctypes.data
+    out[:] = 0xEE
     off, ln = (C.c_uint64 * 1)(0), (C.c_uint64 * 1)(len(wire))
-    N.check(dev.lib.b200tfs_decode_responses_host_async(dev.ctx, wire_buf.ptr + shift, 1, off, ln, out_buf.ptr, dst_stride))
+    N.check(dev.lib.b200tfs_decode_responses_host_async(dev.ctx, wire_buf.ptr + shift, 1, off, ln, optr, dst_stride))
     outs = (N.Output * N.FUSED_MAX_OUTPUTS)()
     n_outs, specs, status = (C.c_int32 * 1)(), (N.ModelSpec * 1)(), (C.c_int32 * 1)()
     N.check(dev.lib.b200tfs_decode_results(dev.ctx, 1, outs, n_outs, specs, status))
-    return out_buf.array, outs, n_outs[0], status[0], (wire_buf, out_buf)
+    return out, outs, n_outs[0], status[0], (wire_buf, out_buf)
 
 
 @pytest.mark.parametrize("elems,key", [(20000, "y"), (65536 + 3, "scores"), (100001, "a_rather_long_output_name"), (1 << 20, "y")])
@@ -153,7 +174,7 @@ def test_sliced_decode_matches_the_oracle(elems, key):
         ref = wire_oracle.decode_predict_response(wire)[key]
         stride = (len(wire) + 2303 + 255) & ~255
         for rep, shift in enumerate((0, 0, 5)):          # twice the same buffer geometry, then a misaligned host pointer
-            out, outs, n_outs, status, keep = _decode_host(dev, wire, stride, shift)
+            out, outs, n_outs, status, keep = _decode_host(dev, wire, stride, shift, pinned_dst=(rep != 1))
             assert status == 0 and n_outs == 1 and outs[0].status == 0 and outs[0].n_elems == elems
             got = out[outs[0].dst_off: outs[0].dst_off + outs[0].dst_bytes]
             assert got.tobytes() == ref.tobytes(), (rep, shift)

@@ -47,7 +47,26 @@ def child(mib, reps):
     def dec():
         N.check(lib.b200tfs_decode_responses_host_async(dev.ctx, rbuf.ptr, 1, roff, rln, obuf.ptr, stride))
 
-    for name, fn in (("encode", enc), ("decode", dec)):
+    def enc_zero_copy():     # the kernels work on the pinned buffers themselves (unified addressing): SM loads / stores cross PCIe
+        N.check(lib.b200tfs_encode_requests(dev.ctx, 1, rq, wire.ptr, cap, off, ln))
+
+    def dec_zero_copy():
+        N.check(lib.b200tfs_decode_responses(dev.ctx, rbuf.ptr, 1, roff, rln, obuf.ptr, stride))
+
+    # device-resident input, output written by the kernel straight into pinned host memory (posted PCIe writes, no D2H copy)
+    xd = dev.upload(x)
+    td = (N.Tensor * 1)(N.Tensor(data=xd, src_dtype=1, wire_dtype=1, rank=1, flags=0, dims=dims, key=b"x", key_len=1, packed_len=0))
+    rqd = (N.Request * 1)(N.Request(model_name=b"default", model_name_len=7, has_version=1, order=N.ORDER_UPB, version=1, n_inputs=1, flags=0, inputs=td))
+    rd = dev.upload(np.frombuffer(resp, dtype=np.uint8))
+
+    def enc_host_out():
+        N.check(lib.b200tfs_encode_requests(dev.ctx, 1, rqd, wire.ptr, cap, off, ln))
+
+    def dec_host_out():
+        N.check(lib.b200tfs_decode_responses(dev.ctx, rd, 1, roff, rln, obuf.ptr, stride))
+
+    for name, fn in (("encode", enc), ("decode", dec), ("encode_zero_copy", enc_zero_copy), ("decode_zero_copy", dec_zero_copy),
+                     ("encode_device_in_host_out", enc_host_out), ("decode_device_in_host_out", dec_host_out)):
         for _ in range(5):
             fn()
             dev.sync()
