@@ -500,11 +500,6 @@ __device__ __noinline__ void move_tile_narrow(const uint8_t* src, uint8_t* dst, 
   move_tile<false>(src, dst, n_out, op, n_tiles, tile, vpt, go);
 }
 __device__ __forceinline__ bool op_narrows(uint32_t op) { return op == OP_F2H || op == OP_F2B; }
-// a template chunk's tile, cold: `len` = the chunk's WIRE bytes
-__device__ __forceinline__ void chunk_tile_cold(const uint8_t* src, uint8_t* dst, uint32_t len, uint32_t op, uint32_t n_tiles, uint32_t tile, uint32_t vpt) {
-  if (op_narrows(op)) move_tile_narrow(src, dst, len >> 1, op, n_tiles, tile, vpt);
-  else move_tile_cold(src, dst, len, op, n_tiles, tile, vpt);
-}
 
 // ------------------------------------------------------------------------------------------------
 // move_kernel: CTAs [0, n_tiles) each take one tile of a large payload; the CTAs after them take the

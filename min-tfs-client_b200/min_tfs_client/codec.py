@@ -476,6 +476,16 @@ class Codec:
             fused = self._decode_fused(wires, strict)
             if fused is not None:
                 return fused
+        elif out_dtypes and len(wires) and not strict:
+            # every requested cast is the same narrowing of float32 (BASELINE config C4): one launch does it (b200tfs_set_decode_cast)
+            try:
+                wanted = {int(enum_for_numpy(np.dtype(v).type)) for v in out_dtypes.values()}
+            except (KeyError, ValueError, TypeError):
+                wanted = set()
+            if len(wanted) == 1 and next(iter(wanted)) in (int(DT_HALF), int(DT_BFLOAT16)):
+                fused = self._decode_fused(wires, strict, cast=(next(iter(wanted)), dict(out_dtypes)))
+                if fused is not None:
+                    return fused
         parsed = self.parse_predict_responses(wires, max_outputs=max_outputs)
         if not parsed:
             return []
@@ -506,7 +516,7 @@ class Codec:
                 results[i][0][key] = arrays[k]
         return results
 
-    def _fused_launch(self, wires: Sequence[bytes]):
+    def _fused_launch(self, wires: Sequence[bytes], cast_code: int = 0):
         """H2D of the wire, decode_fused_kernel, D2H of the decoded fixed-width outputs, one synchronise.  None if any
         record was not tabulated (malformed, or more than FUSED_MAX_OUTPUTS outputs)."""
         n = len(wires)
@@ -514,7 +524,13 @@ class Codec:
         K = N.FUSED_MAX_OUTPUTS
         stride = (max(int(ln[i]) for i in range(n)) + 256 * (K + 1) + 255) & ~255   # every fixed output fits, each 256-aligned
         dst = np.empty(n * stride, dtype=np.uint8)
-        N.check(self._lib.b200tfs_decode_responses_host_async(self._ctx, buf.ctypes.data, n, off, ln, dst.ctypes.data, stride))
+        if cast_code:
+            N.check(self._lib.b200tfs_set_decode_cast(self._ctx, cast_code))
+        try:
+            N.check(self._lib.b200tfs_decode_responses_host_async(self._ctx, buf.ctypes.data, n, off, ln, dst.ctypes.data, stride))
+        finally:
+            if cast_code:
+                N.check(self._lib.b200tfs_set_decode_cast(self._ctx, 0))
         outs = (N.Output * (n * K))()
         n_outs = (C.c_int32 * n)()
         specs = (N.ModelSpec * n)()
@@ -539,13 +555,14 @@ class Codec:
             table[self._text(buf, int(off[0]) + o.key_off, o.key_len)] = o
         return OpenResponse(self, buf, int(off[0]), dst, table)
 
-    def _decode_fused(self, wires: Sequence[bytes], strict: bool):
+    def _decode_fused(self, wires: Sequence[bytes], strict: bool, cast=None):
         """One launch, one synchronise: tag walk (or framing-template check), destination layout and the move of every
         fixed-width output in ``decode_fused_kernel``; the outputs come back as views of one host buffer.  Varint-packed
         and tensor_content-only outputs are tabulated by the same launch and unpacked by a second one.  Returns None when
         a record needs the two-phase path (more than eight outputs, a malformed record: that path raises what the
         reference raises)."""
-        launched = self._fused_launch(wires)
+        cast_code, cast_keys = cast if cast else (0, {})
+        launched = self._fused_launch(wires, cast_code)
         if launched is None:
             return None
         n, buf, off, dst, stride, outs, n_outs, specs = launched
@@ -565,8 +582,11 @@ class Codec:
                 if int(o.dtype) == DT_STRING and o.status == N.OK:
                     arrays[key] = self._decode_strings(buf, base, o)
                     continue
-                np_type, dst_code, shape = self._resolve_output(o, strict, None)
-                if o.status == N.OK and int(o.dtype) in _FUSED_MOVES and o.n_runs and o.n_elems and dst_code == int(o.dtype):
+                if cast_code and ((int(o.dtype) == 1) != (key in cast_keys)):
+                    return None      # the launch narrowed every float32 output: only right when exactly those were asked for
+                np_type, dst_code, shape = self._resolve_output(o, strict, cast_keys.get(key))
+                if o.status == N.OK and int(o.dtype) in _FUSED_MOVES and o.n_runs and o.n_elems and \
+                        (dst_code == int(o.dtype) or (cast_code and int(o.dtype) == 1 and dst_code == cast_code)):
                     at = i * stride + int(o.dst_off)
                     arrays[key] = dst[at: at + int(o.dst_bytes)].view(np_type).reshape(shape)
                 else:

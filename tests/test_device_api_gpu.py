@@ -928,3 +928,22 @@ def test_narrowing_batch_decode_in_three_launches(dev, cast):
                 assert o.dst_bytes == want.nbytes and slot[i, o.dst_off: o.dst_off + o.dst_bytes].tobytes() == want.tobytes(), (rep, i, name)
     l1 = C.c_uint64(); N.check(dev.lib.b200tfs_kernel_launches(dev.ctx, C.byref(l1)))
     assert l1.value - l0.value >= 1 + 3 + 3, "the second and third call run as three launches each"
+
+
+def test_python_out_dtypes_take_the_narrowing_launch(codec):
+    """decode_predict_response(out_dtypes={key: float16}) on float32 outputs is one launch (no parse + synchronise + unpack);
+    a request that does not cover every float32 output, or asks a non-float output to change, falls back and is still right."""
+    import ml_dtypes
+
+    rng = np.random.default_rng(77)
+    f, g = rng.standard_normal((300, 70)).astype(np.float32), rng.standard_normal(999).astype(np.float32)
+    ids = rng.integers(0, 1000, 50)
+    resp = wire_oracle.build_predict_response([("f", f), ("g", g), ("ids", ids)])
+    for np_dt in (np.float16, ml_dtypes.bfloat16):
+        l0 = codec.kernel_launches()
+        got = codec.decode_predict_response(resp, out_dtypes={"f": np_dt, "g": np_dt})[0]
+        assert got["f"].dtype == np.dtype(np_dt) and got["f"].tobytes() == f.astype(np_dt).tobytes()
+        assert got["g"].tobytes() == g.astype(np_dt).tobytes() and got["ids"].tobytes() == ids.tobytes()
+        assert codec.kernel_launches() - l0 <= 3          # the fused launch + the varint output's two kernels
+        part = codec.decode_predict_response(resp, out_dtypes={"f": np_dt})[0]      # g stays float32: the two-phase route
+        assert part["f"].tobytes() == f.astype(np_dt).tobytes() and part["g"].tobytes() == g.tobytes()
