@@ -995,10 +995,11 @@ __device__ __forceinline__ void decode_fused_body(const FusedParams& fp) {
             publish_words(fp.outs + (size_t)r * kFusedMaxOutputs, T->outs, th_s.n_outs * (uint32_t)sizeof(b200tfs_output));
             publish_words(fp.specs + r, &T->spec, (uint32_t)sizeof(b200tfs_model_spec));
             if (threadIdx.x == 0) { fp.status[r] = B200TFS_OK; fp.n_outs[r] = (int32_t)th_s.n_outs; }
-            // hand the template on to the next launch (launches alternate between the two slots) - unless that slot holds this
-            // very template already (the launch before the previous one left it there)
-            if (r == 0 && !(fp.tpl_write->in.head.valid && fp.tpl_write->in.head.serial == T->in.head.serial))
-              publish_words(fp.tpl_write, T, (uint32_t)sizeof(Template));
+            // hand the template on to the next launch (launches alternate between the two slots).  Unconditionally: the warps
+            // of this CTA are not in step (per-warp verdict), and a test of the target slot ("does it hold this template
+            // already?") read the words the faster warps had just written - the slower ones then skipped their share of the
+            // copy and left a torn template behind (found by compute-sanitizer's slow motion, never seen at full speed).
+            if (r == 0) publish_words(fp.tpl_write, T, (uint32_t)sizeof(Template));
           } else if (threadIdx.x == 0) {
             fused_slow_path(fp, r, 0, budget, true, rec, len, dst_slot, lines, outs_s, spec_s, job);   // walk for the table only
           }

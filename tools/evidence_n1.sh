@@ -15,7 +15,7 @@ timeout 300 python tools/pcie_probe.py > gpurun_out/ev_pcie_probe.log 2>&1
 timeout 600 python tools/decode_latency_probe.py > gpurun_out/ev_decode_latency.json 2> gpurun_out/ev_decode_latency.err; echo "decode latency probe rc=$?"
 timeout 1500 compute-sanitizer --tool memcheck --error-exitcode 9 python -m pytest tests -m gpu -x -q --deselect tests/test_device_api_gpu.py::test_one_gib_tensor --deselect tests/test_golden_gpu.py::test_single_pass_varint_kernels_agree > gpurun_out/ev_memcheck.log 2>&1; echo "memcheck rc=$?"
 tail -3 gpurun_out/ev_memcheck.log
-timeout 1200 compute-sanitizer --tool racecheck --error-exitcode 9 python -m pytest tests/test_golden_gpu.py tests/test_device_api_gpu.py tests/test_host_pipeline_gpu.py -m gpu -x -q -k "varint or round_trip or alignment or staged or padding or deferred or template or sliced" > gpurun_out/ev_racecheck.log 2>&1; echo "racecheck rc=$?"
+timeout 1200 compute-sanitizer --tool racecheck --error-exitcode 9 python -m pytest tests/test_golden_gpu.py tests/test_device_api_gpu.py tests/test_host_pipeline_gpu.py -m gpu -x -q -k "varint or round_trip or alignment or staged or padding or deferred or template or sliced or narrow" > gpurun_out/ev_racecheck.log 2>&1; echo "racecheck rc=$?"
 tail -3 gpurun_out/ev_racecheck.log
 bash tools/evidence_ncu.sh > gpurun_out/ev_prof.log 2>&1; tail -5 gpurun_out/ev_prof.log
 python - <<'PY'

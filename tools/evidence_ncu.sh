@@ -20,6 +20,8 @@ timeout 900 ncu --set full --clock-control none --import-source on -k regex:'^mo
 export_rep prof_r02_c5share 1
 timeout 900 ncu --set full --clock-control none -k regex:'venc_len|frame_requests|^move_kernel$|venc_emit|venc_fused|decode_fused_kernel' -s 10 -c 8 -f -o gpurun_out/prof_r02_c3 python bench.py --workload c3 --steps 2 --warmup 3 --no-cpu --no-extra > gpurun_out/rp_c3.log 2>&1; echo "c3 rc=$?"
 export_rep prof_r02_c3 0
+timeout 900 ncu --set full --clock-control none -k regex:'decode_fused_cast|move_guarded|^move_kernel$' -s 6 -c 4 -f -o gpurun_out/prof_r02_c4 python bench.py --workload c4 --steps 2 --warmup 3 --no-cpu --no-extra > gpurun_out/rp_c4.log 2>&1; echo "c4 rc=$?"
+export_rep prof_r02_c4 0
 timeout 900 ncu --set full --clock-control none --import-source on -k regex:'venc|vdec' -s 8 -c 8 -f -o gpurun_out/prof_r02_varint python tools/varint_probe.py --only mixed --reps 1 > gpurun_out/rp_varint.log 2>&1; echo "varint rc=$?"
 export_rep prof_r02_varint 0
 du -sh gpurun_out; ls -la gpurun_out | head -60
