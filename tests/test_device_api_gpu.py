@@ -951,3 +951,46 @@ def test_python_out_dtypes_take_the_narrowing_launch(codec):
         assert fused_records() == r0 + 1                   # served by the single-launch decode, not by parse + unpack
         part = codec.decode_predict_response(resp, out_dtypes={"f": np_dt})[0]      # g stays float32: the two-phase route
         assert part["f"].tobytes() == f.astype(np_dt).tobytes() and part["g"].tobytes() == g.tobytes()
+
+
+def test_randomised_batches_through_the_fused_decode(codec):
+    """Seeded fuzz of the single-launch decode's bookkeeping (framing templates kept across launches, per-record CTA budgets from
+    a known template, batches mixing records that match the template with records of the same or another length that do not):
+    random responses of 1-4 outputs of random fixed-width / varint dtypes, decoded in random groupings, repeatedly, against
+    the oracle."""
+    rng = np.random.default_rng(20260921)
+    dtypes = [np.float32, np.float64, np.int32, np.int64, np.uint8, np.bool_, np.float32, np.float32]
+    def tensor():
+        dt = dtypes[rng.integers(len(dtypes))]
+        shape = tuple(int(v) for v in rng.integers(1, 40, size=rng.integers(1, 4)))
+        if dt in (np.float32, np.float64):
+            return rng.standard_normal(shape).astype(dt)
+        if dt == np.bool_:
+            return rng.integers(0, 2, size=shape).astype(np.bool_)
+        return rng.integers(-1000 if dt != np.uint8 else 0, 100000 if dt not in (np.uint8,) else 256, size=shape).astype(dt)
+    shapes = []       # a pool of "models": fixed keys / dtypes / shapes, fresh values per response
+    for _ in range(6):
+        keys = ["out%d" % k for k in range(rng.integers(1, 5))]
+        shapes.append([(k, tensor()) for k in keys])
+    def response(m):
+        outs = []
+        for k, proto in shapes[m]:
+            if proto.dtype.kind == "f":
+                v = rng.standard_normal(proto.shape).astype(proto.dtype)
+            elif proto.dtype == np.bool_:
+                v = rng.integers(0, 2, size=proto.shape).astype(np.bool_)
+            else:
+                v = rng.integers(0, 100, size=proto.shape).astype(proto.dtype)      # same varint lengths: same record length
+            outs.append((k, v))
+        return wire_oracle.build_predict_response(outs)
+    for round_ in range(40):
+        n = int(rng.integers(1, 20))
+        favourite = int(rng.integers(len(shapes)))
+        wires = [response(favourite if rng.random() < 0.7 else int(rng.integers(len(shapes)))) for _ in range(n)]
+        got = codec.decode_predict_responses(wires)
+        assert len(got) == n
+        for w, (arrays, spec) in zip(wires, got):
+            ref = wire_oracle.decode_predict_response(w)
+            assert set(arrays) == set(ref), round_
+            for k in ref:
+                assert arrays[k].dtype == ref[k].dtype and arrays[k].shape == ref[k].shape and arrays[k].tobytes() == ref[k].tobytes(), (round_, k)
