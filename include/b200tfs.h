@@ -279,7 +279,8 @@ int b200tfs_encode_tensor_protos(b200tfs_ctx* ctx, int32_t n, const b200tfs_tens
 int b200tfs_encode_requests(b200tfs_ctx* ctx, int32_t n, const b200tfs_request* reqs, void* arena_dev,
                             uint64_t arena_cap, uint64_t* rec_off, uint64_t* rec_len);
 
-/* The same encode WITHOUT the host-side measuring pass: inputs of the packed-varint dtypes may carry packed_len == 0.
+/* The same encode (requests.py:41-48 + PredictRequest.SerializeToString, prediction_service_pb2_grpc.py:52) WITHOUT the host-side
+ * measuring pass: inputs of the packed-varint dtypes (constants.py:16-23: int_val, int64_val, ...) may carry packed_len == 0.
  * Their lengths are counted, the length prefixes (and every length that encloses them) written, and the record placed by
  * kernels alone - count -> frame_requests_kernel (one thread per request evaluates the dependent varints, writes the
  * framing, patches the destinations of the payload movers) -> move + emit - so the call never synchronises and can be
@@ -343,7 +344,8 @@ int b200tfs_unpack_outputs(b200tfs_ctx* ctx, const void* arena_dev, int32_t m, c
 #define B200TFS_FUSED_MAX_OUTPUTS 8
 int b200tfs_decode_responses(b200tfs_ctx* ctx, const void* arena_dev, int32_t n, const uint64_t* rec_off,
                              const uint64_t* rec_len, void* dst_dev, uint64_t dst_stride);
-/* Narrow on the way out: after b200tfs_set_decode_cast(ctx, DT_HALF or DT_BFLOAT16) every DT_FLOAT output of
+/* Narrow on the way out (what a caller of the reference writes as tensor_proto_to_ndarray(...).astype(np.float16), tensors.py:42-46
+ * followed by a host-side cast): after b200tfs_set_decode_cast(ctx, DT_HALF or DT_BFLOAT16) every DT_FLOAT output of
  * b200tfs_decode_responses / b200tfs_decode_responses_host_async on this context is written as fp16 / bf16 (IEEE round to nearest
  * even, the rounding of numpy's astype; b200tfs_output.dst_bytes = 2 * n_elems, .dtype stays DT_FLOAT, the wire's).  Outputs of
  * other dtypes are unaffected.  DT_FLOAT (or 0) switches it off.  This is the decode half of BASELINE config C4 (a fp16 / bf16
