@@ -535,6 +535,7 @@ struct PlanBuilder {
   uint64_t large_bytes = 0;
   const uint32_t* guard = nullptr;   // move_guarded_kernel: item i is stored only if guard[i / guard_div] != 0
   uint32_t guard_div = 1;
+  bool independent = false;          // PlanHeader::independent
 
   void header(uint8_t* dst, size_t blob_off, size_t n) {
     // split long headers so one warp never walks more than kSmallMax bytes
@@ -599,6 +600,7 @@ int build_plan(b200tfs_ctx* c, PlanBuilder& pb, bool force_dev, BuiltPlan* bp) {
   ph.uniform_tpi = uniform;
   ph.vec_per_tile = vpt;
   ph.guard = pb.guard; ph.guard_div = pb.guard_div ? pb.guard_div : 1u;
+  ph.independent = pb.independent ? 1u : 0u;
   uint64_t off = (sizeof(PlanHeader) + 15) & ~15ull;
   ph.off_items = (uint32_t)off; off += pb.items.size() * sizeof(MoveItem);
   ph.off_tiles = (uint32_t)off; if (!uniform) off += n_tiles * sizeof(TileRef);

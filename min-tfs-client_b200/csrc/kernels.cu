@@ -545,7 +545,10 @@ __device__ __forceinline__ void move_body(const uint8_t* plan) {
 
 __global__ void __launch_bounds__(kMoveThreads, 3) move_kernel(const uint8_t* __restrict__ plan) {
   pdl_launch_dependents();
-  pdl_wait_prior_grids();   // the plan image itself was copied by an earlier operation of the stream
+  // The plan image was copied by an earlier OPERATION of the stream (complete before the kernel in front of us could start).
+  // PlanHeader::independent: that kernel - frame_requests_kernel - writes nothing this plan reads or overwrites (every mover's
+  // destination was fixed by the host), so the tiles start while the headers are still being written.
+  if (!reinterpret_cast<const PlanHeader*>(plan)->independent) pdl_wait_prior_grids();
   move_body<false>(plan);
 }
 
@@ -1049,6 +1052,7 @@ struct FrameStage {
 };
 
 __global__ void __launch_bounds__(32 * kFrameWarps) frame_requests_kernel(const __grid_constant__ FrameTables ft) {
+  pdl_launch_dependents();       // an independent move plan (PlanHeader::independent) may start right behind us
   __shared__ FrameStage stage[kFrameWarps];
   const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t r = blockIdx.x * kFrameWarps + warp;
@@ -1115,7 +1119,8 @@ __global__ void __launch_bounds__(256) fill_edge_kernel(uint8_t* __restrict__ ds
 // launches loses 0.6 us per launch (3.5 -> 4.1 us), so it is opt-in: B200TFS_PDL=1.
 template <class... KArgs, class... Args>
 static cudaError_t launch_pdl(void (*kernel)(KArgs...), uint32_t grid, uint32_t block, uint32_t dyn_smem, cudaStream_t stream, Args&&... args) {
-  static const bool off = [] { const char* e = getenv("B200TFS_PDL"); return !(e && e[0] == '1'); }();
+  static const bool env_off = [] { const char* e = getenv("B200TFS_PDL"); return !(e && e[0] == '1'); }();
+  const bool off = env_off;
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3(grid); cfg.blockDim = dim3(block); cfg.dynamicSmemBytes = dyn_smem; cfg.stream = stream;
   cudaLaunchAttribute attr[1];
@@ -1135,7 +1140,18 @@ cudaError_t launch_move(const uint8_t* plan_dev, const uint8_t* plan_host, uint3
     memcpy(ip.bytes, plan_host, plan_bytes);
     return launch_pdl(move_kernel_inline, grid, kMoveThreads, 0, stream, ip);
   }
-  return launch_pdl(move_kernel, grid, kMoveThreads, 0, stream, plan_dev);
+  // a plan whose movers need nothing from the kernel in front of them (PlanHeader::independent) is launched with programmatic
+  // stream serialization whatever B200TFS_PDL says: overlapping that kernel is the point
+  thread_local bool force = false;
+  force = plan_host && reinterpret_cast<const PlanHeader*>(plan_host)->independent != 0;
+  if (!force) return launch_pdl(move_kernel, grid, kMoveThreads, 0, stream, plan_dev);
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(grid); cfg.blockDim = dim3(kMoveThreads); cfg.dynamicSmemBytes = 0; cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr; cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, move_kernel, plan_dev);
 }
 
 cudaError_t launch_parse_responses(const uint8_t* w, const uint64_t* rec_off, const uint64_t* rec_len, int n, int max_outputs,

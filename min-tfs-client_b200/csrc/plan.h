@@ -50,7 +50,9 @@ struct PlanHeader {
   uint32_t vec_per_tile;                            // 16-byte vectors of destination per tile
   uint32_t off_items, off_tiles, off_small;         // byte offsets inside the plan image
   uint32_t guard_div;                               // move_guarded_kernel: item i is stored only if guard[i / guard_div] != 0
-  uint32_t pad[3];
+  uint32_t independent;                             // != 0: nothing in this plan is written by the kernel launched just before (the framing
+                                                    // kernel of a deferred encode whose movers all have host-fixed destinations): no wait for it
+  uint32_t pad[2];
   const uint32_t* guard;
 };
 
