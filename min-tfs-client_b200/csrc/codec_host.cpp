@@ -1690,9 +1690,11 @@ int encode_pipelined(b200tfs_ctx* c, PlanBuilder& pb, const std::vector<StagePie
   const uint64_t per = ((pb.large_bytes + K - 1) / K + 65535) & ~65535ull;    // output bytes per slice, cut on 64 KB
   const uint8_t* arena = (const uint8_t*)c->arena_dev.p;
   // which piece feeds an item: the one that contains its source (device-resident inputs have none)
-  auto piece_of = [&](const uint8_t* src) -> const StagePiece* {
-    for (auto& p : pieces) if (src >= p.dev && src < p.dev + p.nb) return &p;
-    return nullptr;
+  auto piece_of = [&](const uint8_t* src) -> const StagePiece* {      // pieces are in ascending staging-address order (stage_tensors)
+    auto it = std::upper_bound(pieces.begin(), pieces.end(), src, [](const uint8_t* s, const StagePiece& p) { return s < p.dev; });
+    if (it == pieces.begin()) return nullptr;
+    --it;
+    return (src >= it->dev && src < it->dev + it->nb) ? &*it : nullptr;
   };
   std::vector<const StagePiece*> feeds(pb.items.size());
   std::vector<char> is_large(pieces.size(), 0);
