@@ -385,7 +385,8 @@ int b200tfs_encode_requests_host(b200tfs_ctx* ctx, int32_t n, const b200tfs_requ
                                  void* wire_host, uint64_t wire_cap, uint64_t* rec_off,
                                  uint64_t* rec_len);
 /* Same, but returns as soon as the copies and kernels are queued (it only blocks for the measure pass
- * when a varint dtype is present): call b200tfs_sync before reading wire_host, which must be pinned
+ * when a packed-varint input of more than 4096 elements is present; smaller ones - labels, ids, a sequence
+ * of token ids - are measured by the host, whose memory they are in): call b200tfs_sync before reading wire_host, which must be pinned
  * (b200tfs_host_alloc).  Two contexts running the _async entry points overlap H2D with D2H.
  *
  * Pipelining inside ONE call: a batch whose fixed-width payloads add up to at least 1 MiB (environment
