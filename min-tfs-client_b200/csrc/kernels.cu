@@ -402,9 +402,8 @@ __device__ __forceinline__ void move_tile_gather(const SrcView& src, uint8_t* __
 }
 
 // DEC: the caller only ever passes OP_COPY / OP_QUIET_DST (the single-launch decode moves float_val / double_val / complex
-// values as they are): the other bodies are not instantiated.  Code size is not cosmetic here - with every body inlined three
-// times the fused decode kernel was 728 KB of SASS, its hot path scattered over it, and a 4 MiB launch paid ~1 us of
-// instruction fetch that no data-path change could touch (profiles/r02_decode_latency.md).
+// values as they are): the other bodies are not instantiated there (with every body inlined three times the fused decode kernel
+// was 728 KB of SASS).  The narrowing decode (CAST instantiations, move_guarded_kernel) goes through DEC = false.
 template <bool DEC, class Mid>
 __device__ __forceinline__ bool move_tile(const uint8_t* __restrict__ src, uint8_t* __restrict__ dst, uint64_t n_out, uint32_t op,
                                           uint32_t n_tiles, uint32_t tile, uint32_t vpt, Mid& mid) {
@@ -1142,9 +1141,7 @@ cudaError_t launch_move(const uint8_t* plan_dev, const uint8_t* plan_host, uint3
   }
   // a plan whose movers need nothing from the kernel in front of them (PlanHeader::independent) is launched with programmatic
   // stream serialization whatever B200TFS_PDL says: overlapping that kernel is the point
-  thread_local bool force = false;
-  force = plan_host && reinterpret_cast<const PlanHeader*>(plan_host)->independent != 0;
-  if (!force) return launch_pdl(move_kernel, grid, kMoveThreads, 0, stream, plan_dev);
+  if (!(plan_host && reinterpret_cast<const PlanHeader*>(plan_host)->independent)) return launch_pdl(move_kernel, grid, kMoveThreads, 0, stream, plan_dev);
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3(grid); cfg.blockDim = dim3(kMoveThreads); cfg.dynamicSmemBytes = 0; cfg.stream = stream;
   cudaLaunchAttribute attr[1];
