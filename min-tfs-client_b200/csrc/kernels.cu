@@ -12,8 +12,14 @@
 //   decode_fused_staged_kernel   the same for big batches (tiles of several 32 KB chunks): the tile's
 //                      source bytes arrive by TMA 1-D bulk copies (cp.async.bulk global -> shared, two
 //                      buffers, mbarrier completion) issued ahead of the template verdict.
+//   decode_fused{,_staged}_cast_kernel   the same two with the narrowing tile move compiled in (b200tfs_set_decode_cast:
+//                      float32 on the wire -> fp16 / bf16 in memory); mode 1 of the plain one is the VERIFY launch of the
+//                      three-launch narrowing batch decode (two CTAs per record: verdict -> guard word, table).
+//   move_guarded_kernel    the move engine over a host-built plan that stores only for records whose guard word is set.
 //   parse_*_kernel     two-phase decode: one lane per PredictResponse / TensorProto walks the tags and
 //                      tabulates dtype, dims and where the values lie.
+//   frame_requests_kernel  deferred framing (frame.h): one warp per request evaluates the request's framing program from the
+//                      device-side totals, writes every header byte, patches the destinations of the movers behind it.
 //   venc_* / vdec_*    packed-varint encode and decode (int_val / int64_val / uint32_val / uint64_val /
 //                      half_val / bool_val): varint_kernels.cuh.
 //
