@@ -181,6 +181,37 @@ constexpr uint32_t kVarImageBytes = kVarTileElems * 10 + 48;
 // (elements past the end of the tensor: 0); returns the thread's byte count.  One barrier inside.
 __device__ __forceinline__ uint32_t venc_load_tile(uint8_t* smem, const VarSeg& sg, const VarJobDev& jb, uint64_t e0, uint32_t cnt,
                                                    uint64_t (&mine)[kVarPerThread], uint32_t& lens) {
+  const uint32_t r = threadIdx.x;
+  // 64-bit elements of a full tile whose first byte is 16-byte aligned: every thread loads its own eight consecutive elements
+  // with four 128-bit loads - no shared-memory transpose, no barrier (the four loads of a warp cover 2 KB of consecutive bytes
+  // between them; each sector is fetched once and served from L1 to the neighbouring instruction)
+  const uint8_t* first = sg.src + e0 * 8;
+  if (jb.elem_size == 8 && cnt == kVarTileElems && ((uintptr_t)first & 15) == 0) {
+    const uint4* p = reinterpret_cast<const uint4*>(first) + 4 * r;
+    uint4 q[kVarPerThread / 2];
+#pragma unroll
+    for (uint32_t j = 0; j < kVarPerThread / 2; ++j) q[j] = __ldg(p + j);
+    uint32_t any_hi = 0;
+#pragma unroll
+    for (uint32_t j = 0; j < kVarPerThread / 2; ++j) {
+      mine[2 * j] = (uint64_t)q[j].x | ((uint64_t)q[j].y << 32);
+      mine[2 * j + 1] = (uint64_t)q[j].z | ((uint64_t)q[j].w << 32);
+      any_hi |= q[j].y | q[j].w;
+    }
+    lens = 0;
+    if (__all_sync(0xFFFFFFFFu, any_hi == 0u)) {      // the warp's values all fit 32 bits: lengths from the low words alone
+#pragma unroll
+      for (uint32_t i = 0; i < kVarPerThread; ++i) {
+        const uint32_t nb = 32u - (uint32_t)__clz((int)((uint32_t)mine[i] | 1u));
+        lens |= (((nb + 6u) * 37u) >> 8) << (4 * i);
+      }
+    } else {
+#pragma unroll
+      for (uint32_t i = 0; i < kVarPerThread; ++i) lens |= vlen64(mine[i]) << (4 * i);
+    }
+    const uint32_t pairs = (lens & 0x0F0F0F0Fu) + ((lens >> 4) & 0x0F0F0F0Fu);
+    return (pairs * 0x01010101u) >> 24;
+  }
   uint64_t* vals = reinterpret_cast<uint64_t*>(smem);
   {
     uint64_t v[kVarPerThread];
@@ -192,7 +223,6 @@ __device__ __forceinline__ uint32_t venc_load_tile(uint8_t* smem, const VarSeg& 
     }
   }
   __syncthreads();
-  const uint32_t r = threadIdx.x;
 #pragma unroll
   for (uint32_t j = 0; j < kVarPerThread / 2; ++j) {
     const uint4 q = *reinterpret_cast<const uint4*>(smem + r * 64 + (((j ^ (r >> 1)) & 3) << 4));
